@@ -1,0 +1,277 @@
+"""TEST INFRASTRUCTURE ONLY -- ctypes front-end for the two CPU oracles.
+
+* backend "ref":  oracle/_ref/libparm_ref{2,3}d.so -- the UNMODIFIED reference
+  sources compiled against oracle/shim (see oracle/Makefile, oracle/ref_harness.cpp).
+* backend "port": oracle/libparm_oracle.so -- the plain-C restatement
+  (oracle/parm_oracle.c), pinned bit-for-bit against "ref" by tests/test_oracle_pin.py.
+
+Nothing under parm_b200/ may import this module; only tests/, bench.py's
+cpu_baseline / --impl reference legs and __graft_entry__.smoke() do.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+KIND_LJREPULSE, KIND_REPULSION, KIND_LJATTRACTREPULSE, KIND_LJCUT = 0, 1, 2, 3
+VERLET, SOL = 0, 1
+
+_dp = C.POINTER(C.c_double)
+_u32p = C.POINTER(C.c_uint32)
+_u8p = C.POINTER(C.c_uint8)
+
+
+def _d(a):
+    return None if a is None else a.ctypes.data_as(_dp)
+
+
+def build(which=("port", "ref")):
+    """Build the oracle libraries (idempotent; 'ref' needs /root/reference)."""
+    targets = [t for t in which]
+    subprocess.check_call(["make", "-s", "-f", os.path.join(HERE, "Makefile")] + targets)
+
+
+def have(backend, ndim=3):
+    return os.path.exists(_libpath(backend, ndim))
+
+
+def _libpath(backend, ndim):
+    if backend == "ref":
+        return os.path.join(HERE, "_ref", "libparm_ref%dd.so" % ndim)
+    return os.path.join(HERE, "libparm_oracle.so")
+
+
+_libs = {}
+
+
+def _load(backend, ndim):
+    key = (backend, ndim if backend == "ref" else 0)
+    if key in _libs:
+        return _libs[key]
+    path = _libpath(backend, ndim)
+    if not os.path.exists(path):
+        raise FileNotFoundError("oracle library missing: %s (run make -f oracle/Makefile)" % path)
+    lib = C.CDLL(path)
+    p = "ref_" if backend == "ref" else "port_"
+    vp = C.c_void_p
+
+    def sig(name, res, args):
+        f = getattr(lib, p + name)
+        f.restype = res
+        f.argtypes = args
+        return f
+
+    api = {}
+    if backend == "ref":
+        api["sys_create"] = sig("sys_create", vp, [C.c_uint32, _dp, _dp, _dp, _dp])
+        api["ndim"] = sig("ndim", C.c_int, [])
+        api["inject_noise"] = sig("inject_noise", None, [_dp, C.c_size_t])
+        api["probe_draw_order"] = sig("probe_draw_order", None, [C.POINTER(C.c_int)])
+        api["noise_consumed"] = sig("noise_consumed", C.c_size_t, [])
+    else:
+        api["sys_create"] = sig("sys_create", vp, [C.c_int, C.c_uint32, _dp, _dp, _dp, _dp])
+        api["inject_noise"] = sig("inject_noise", None, [vp, _dp, C.c_size_t])
+        api["get_sol_constants"] = sig("get_sol_constants", None, [vp, _dp])
+    api["sys_destroy"] = sig("sys_destroy", None, [vp])
+    api["add_interaction"] = sig("add_interaction", C.c_int,
+                                 [vp, C.c_int, C.c_double, _dp, _u32p, _dp, C.c_int, _u8p, C.c_int, C.c_int])
+    api["make_collection"] = sig("make_collection", C.c_int, [vp, C.c_int, C.c_double, C.c_double, C.c_double])
+    api["update_list"] = sig("update_list", C.c_int, [vp, C.c_int, C.c_int])
+    api["which"] = sig("which", C.c_uint32, [vp, C.c_int])
+    api["numpairs"] = sig("numpairs", C.c_uint32, [vp, C.c_int])
+    api["get_pairs"] = sig("get_pairs", None, [vp, C.c_int, _u32p, _u32p])
+    api["set_atoms"] = sig("set_atoms", None, [vp, _dp, _dp, _dp, _dp])
+    api["get_atoms"] = sig("get_atoms", None, [vp, _dp, _dp, _dp, _dp])
+    api["box_diff"] = sig("box_diff", None, [vp, _dp, _dp, _dp])
+    api["box_V"] = sig("box_V", C.c_double, [vp])
+    api["reset_forces"] = sig("reset_forces", None, [vp])
+    api["inter_set_forces"] = sig("inter_set_forces", None, [vp, C.c_int])
+    api["inter_set_forces_get_pressure"] = sig("inter_set_forces_get_pressure", C.c_double, [vp, C.c_int])
+    api["inter_energy"] = sig("inter_energy", C.c_double, [vp, C.c_int])
+    api["inter_pressure"] = sig("inter_pressure", C.c_double, [vp, C.c_int])
+    api["inter_stress"] = sig("inter_stress", None, [vp, C.c_int, _dp])
+    api["timestep"] = sig("timestep", None, [vp, C.c_int])
+    api["set_forces"] = sig("set_forces", None, [vp, C.c_int])
+    for n in ("energy", "potential_energy", "kinetic_energy", "pressure", "virial", "degrees_of_freedom", "mass"):
+        api[n] = sig(n, C.c_double, [vp])
+    api["temp"] = sig("temp", C.c_double, [vp, C.c_int])
+    api["reset_com_velocity"] = sig("reset_com_velocity", None, [vp])
+    api["scale_velocities"] = sig("scale_velocities", None, [vp, C.c_double])
+    api["scale_velocities_to_temp"] = sig("scale_velocities_to_temp", None, [vp, C.c_double, C.c_int])
+    api["scale_velocities_to_energy"] = sig("scale_velocities_to_energy", None, [vp, C.c_double])
+    api["com_velocity"] = sig("com_velocity", None, [vp, _dp])
+    api["momentum"] = sig("momentum", None, [vp, _dp])
+    api["atoms_kinetic_energy"] = sig("atoms_kinetic_energy", C.c_double, [vp, _dp])
+    api["add_velocity"] = sig("add_velocity", None, [vp, _dp])
+    _libs[key] = api
+    return api
+
+
+class CpuSystem:
+    """One OriginBox + AtomVec + interactions + (optional) Collection on the CPU."""
+
+    def __init__(self, backend, L, x, v=None, m=None):
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        self.n, self.ndim = x.shape
+        self.backend = backend
+        self.api = _load(backend, self.ndim)
+        self.L = np.ascontiguousarray(np.broadcast_to(np.asarray(L, dtype=np.float64), (self.ndim,)))
+        v = np.zeros_like(x) if v is None else np.ascontiguousarray(v, dtype=np.float64)
+        m = np.ones(self.n) if m is None else np.ascontiguousarray(np.broadcast_to(m, (self.n,)), dtype=np.float64)
+        if backend == "ref":
+            assert self.api["ndim"]() == self.ndim
+            self.h = self.api["sys_create"](self.n, _d(self.L), _d(x), _d(v), _d(m))
+        else:
+            self.h = self.api["sys_create"](self.ndim, self.n, _d(self.L), _d(x), _d(v), _d(m))
+        self.m = m
+        self._keep = []
+
+    def close(self):
+        if self.h:
+            if self.backend == "ref":
+                self.api["inject_noise"](None, 0)
+            self.api["sys_destroy"](self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def add_interaction(self, kind, skin, params, types=None, eps_table=None, member=None, injected=False, share_nl=-1):
+        params = np.ascontiguousarray(params, dtype=np.float64).reshape(self.n, 3)
+        t = None if types is None else np.ascontiguousarray(types, dtype=np.uint32)
+        e = None if eps_table is None else np.ascontiguousarray(eps_table, dtype=np.float64)
+        nt = 0 if e is None else e.shape[0]
+        mem = None if member is None else np.ascontiguousarray(member, dtype=np.uint8)
+        r = self.api["add_interaction"](
+            self.h, kind, float(skin), _d(params),
+            None if t is None else t.ctypes.data_as(_u32p), _d(e), nt,
+            None if mem is None else mem.ctypes.data_as(_u8p), int(injected), share_nl)
+        if r < 0:
+            raise RuntimeError("oracle add_interaction failed: %d" % r)
+        return r
+
+    def make_collection(self, integrator, dt, damping=0.0, T=0.0):
+        r = self.api["make_collection"](self.h, integrator, dt, damping, T)
+        if r:
+            raise ValueError("oracle make_collection failed: %d" % r)
+
+    def update_list(self, force=True, nl=0):
+        return bool(self.api["update_list"](self.h, nl, int(force)))
+
+    def which(self, nl=0):
+        return self.api["which"](self.h, nl)
+
+    def pairs(self, nl=0):
+        """Pairs in the reference's own order: (first, last) = (later atom i, earlier atom j<i)."""
+        n = self.api["numpairs"](self.h, nl)
+        a = np.empty(n, np.uint32)
+        b = np.empty(n, np.uint32)
+        if n:
+            self.api["get_pairs"](self.h, nl, a.ctypes.data_as(_u32p), b.ctypes.data_as(_u32p))
+        return a, b
+
+    def set_atoms(self, x=None, v=None, a=None, f=None):
+        arrs = [None if q is None else np.ascontiguousarray(q, dtype=np.float64) for q in (x, v, a, f)]
+        self.api["set_atoms"](self.h, *[_d(q) for q in arrs])
+
+    def get_atoms(self):
+        out = [np.empty((self.n, self.ndim)) for _ in range(4)]
+        self.api["get_atoms"](self.h, *[_d(q) for q in out])
+        return tuple(out)
+
+    def box_diff(self, r1, r2):
+        r1 = np.ascontiguousarray(r1, dtype=np.float64)
+        r2 = np.ascontiguousarray(r2, dtype=np.float64)
+        out = np.empty(self.ndim)
+        self.api["box_diff"](self.h, _d(r1), _d(r2), _d(out))
+        return out
+
+    def forces(self, k=0):
+        """reset_forces + Interaction::set_forces -> per-atom f."""
+        self.api["reset_forces"](self.h)
+        self.api["inter_set_forces"](self.h, k)
+        return self.get_atoms()[3]
+
+    def forces_and_pressure(self, k=0):
+        self.api["reset_forces"](self.h)
+        p = self.api["inter_set_forces_get_pressure"](self.h, k)
+        return self.get_atoms()[3], p
+
+    def inter_energy(self, k=0):
+        return self.api["inter_energy"](self.h, k)
+
+    def inter_pressure(self, k=0):
+        return self.api["inter_pressure"](self.h, k)
+
+    def inter_stress(self, k=0):
+        out = np.empty((self.ndim, self.ndim))
+        self.api["inter_stress"](self.h, k, _d(out))
+        return out
+
+    def timestep(self, n=1):
+        self.api["timestep"](self.h, n)
+
+    def set_forces(self, constraints_and_a=True):
+        self.api["set_forces"](self.h, int(constraints_and_a))
+
+    def inject_noise(self, z):
+        """z: (steps, n_mobile, 2, ndim) standard normals: [.,.,0,:] -> x1, [.,.,1,:] -> x2 of
+        BivariateGauss::gen_vecs (vecrand.cpp:73-85)."""
+        z = np.ascontiguousarray(z, dtype=np.float64)
+        if self.backend == "ref":
+            order = (C.c_int * self.ndim)()
+            self.api["probe_draw_order"](order)
+            order = list(order)  # order[c] = draw index that lands in component c
+            draws = np.empty_like(z)
+            for c, k in enumerate(order):
+                draws[..., k] = z[..., c]
+            z = np.ascontiguousarray(draws)
+            self._keep.append(z)
+            self.api["inject_noise"](_d(z), z.size)
+        else:
+            self._keep.append(z)
+            self.api["inject_noise"](self.h, _d(z), z.size)
+
+    def __getattr__(self, name):
+        if name in ("energy", "potential_energy", "kinetic_energy", "pressure", "virial", "degrees_of_freedom", "mass"):
+            return lambda: self.api[name](self.h)
+        raise AttributeError(name)
+
+    def temp(self, minuscomv=True):
+        return self.api["temp"](self.h, int(minuscomv))
+
+    def reset_com_velocity(self):
+        self.api["reset_com_velocity"](self.h)
+
+    def scale_velocities(self, s):
+        self.api["scale_velocities"](self.h, s)
+
+    def scale_velocities_to_temp(self, T, minuscomv=True):
+        self.api["scale_velocities_to_temp"](self.h, T, int(minuscomv))
+
+    def scale_velocities_to_energy(self, E):
+        self.api["scale_velocities_to_energy"](self.h, E)
+
+    def com_velocity(self):
+        out = np.empty(self.ndim)
+        self.api["com_velocity"](self.h, _d(out))
+        return out
+
+    def momentum(self):
+        out = np.empty(self.ndim)
+        self.api["momentum"](self.h, _d(out))
+        return out
+
+    def atoms_kinetic_energy(self, v0):
+        v0 = np.ascontiguousarray(v0, dtype=np.float64)
+        return self.api["atoms_kinetic_energy"](self.h, _d(v0))
+
+    def add_velocity(self, dv):
+        dv = np.ascontiguousarray(dv, dtype=np.float64)
+        self.api["add_velocity"](self.h, _d(dv))

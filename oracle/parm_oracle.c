@@ -1,0 +1,759 @@
+/* TEST INFRASTRUCTURE ONLY -- never linked into, imported by, or executed from
+ * the product path (parm_b200/). Only tests/, __graft_entry__.smoke() and
+ * bench.py's cpu_baseline / --impl reference legs may load this library.
+ *
+ * Plain-C restatement of ParM's per-timestep MD hot path (the "port" oracle).
+ * Parity pin: tests/test_oracle_pin.py checks every function here bit-for-bit
+ * (pairs, forces, energies, trajectories) against the UNMODIFIED reference
+ * compiled into oracle/_ref/libparm_ref{2,3}d.so, and against the committed
+ * fixtures in tests/golden/ that were generated from that reference build.
+ *
+ * Arithmetic conventions (must match oracle/shim/Eigen/Dense, which defines
+ * the reference build's vector arithmetic since Eigen itself is absent):
+ *   3-element sums associate e0 + (e1 + e2); 2-element sums e0 + e1;
+ *   norm = sqrt(squaredNorm); no FMA contraction (-ffp-contract=off).
+ *
+ * Each function cites the reference file:line it restates (paths relative to
+ * /root/reference/src).
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+typedef struct {
+    double eps, sig, c, cutE; /* c: exponent (kind 1) or cut_distance (2,3) */
+    uint32_t i, j;            /* atom1 = first() = i (later atom), atom2 = j */
+} Pair;
+
+typedef struct {
+    int kind;
+    double *params; /* n x 3 */
+    uint32_t *type;
+    double *eps_table;
+    int ntypes;
+    int nl;
+    uint32_t last_update;
+    Pair *pairs;
+    size_t npairs, cappairs;
+} Inter;
+
+typedef struct {
+    double skin;
+    uint8_t *member;
+    uint32_t *ids; /* SubGroup order */
+    uint32_t nids;
+    double *diam;     /* per SubGroup slot */
+    double *lastlocs; /* per SubGroup slot x D */
+    uint32_t *first, *last;
+    size_t npairs, cap;
+    uint32_t updatenum;
+    int ignorechanged;
+    int injected;
+} NList;
+
+typedef struct {
+    int D;
+    uint32_t n;
+    double L[3];
+    double *x, *v, *a, *f, *m;
+    Inter *inters;
+    int ninters;
+    NList *nls;
+    int nnls;
+    int integrator; /* -1 none, 0 verlet, 1 sol */
+    double dt, damping, force_mag, desT;
+    double c0, c1, c2, sigmar, sigmav, corr, x11, x21, x22;
+    const double *noise;
+    size_t noise_len, noise_pos;
+} Sys;
+
+/* Eigen-shim reduction order: e0 + (e1 + e2) / e0 + e1 */
+static inline double sum3(int D, double e0, double e1, double e2) { return D == 3 ? e0 + (e1 + e2) : e0 + e1; }
+static inline double dotD(int D, const double *a, const double *b) {
+    return sum3(D, a[0] * b[0], a[1] * b[1], D == 3 ? a[2] * b[2] : 0.0);
+}
+
+/* OriginBox::diff, box.hpp:103 -> vec_mod, box.hpp:69-78 */
+static inline void box_diff(const Sys *s, const double *r1, const double *r2, double *out) {
+    for (int k = 0; k < s->D; k++) out[k] = remainder(r1[k] - r2[k], s->L[k]);
+}
+
+static int frozen_le(double m) { return m <= 0 || isinf(m); } /* collection.cpp:445,458 */
+static int frozen_eq(double m) { return m == 0 || isinf(m); } /* box.cpp:406, collection.cpp:304 */
+
+void *port_sys_create(int ndim, uint32_t n, const double *L, const double *x, const double *v, const double *m) {
+    Sys *s = (Sys *)calloc(1, sizeof(Sys));
+    s->D = ndim;
+    s->n = n;
+    for (int k = 0; k < ndim; k++) s->L[k] = L[k];
+    size_t nd = (size_t)n * ndim;
+    s->x = (double *)calloc(nd ? nd : 1, 8);
+    s->v = (double *)calloc(nd ? nd : 1, 8);
+    s->a = (double *)calloc(nd ? nd : 1, 8);
+    s->f = (double *)calloc(nd ? nd : 1, 8);
+    s->m = (double *)calloc(n ? n : 1, 8);
+    memcpy(s->x, x, nd * 8);
+    if (v) memcpy(s->v, v, nd * 8);
+    memcpy(s->m, m, (size_t)n * 8);
+    s->integrator = -1;
+    return s;
+}
+
+void port_sys_destroy(void *h) {
+    Sys *s = (Sys *)h;
+    for (int k = 0; k < s->ninters; k++) {
+        free(s->inters[k].params);
+        free(s->inters[k].type);
+        free(s->inters[k].eps_table);
+        free(s->inters[k].pairs);
+    }
+    for (int k = 0; k < s->nnls; k++) {
+        NList *l = &s->nls[k];
+        free(l->member); free(l->ids); free(l->diam); free(l->lastlocs); free(l->first); free(l->last);
+    }
+    free(s->inters); free(s->nls);
+    free(s->x); free(s->v); free(s->a); free(s->f); free(s->m);
+    free(s);
+}
+
+/* A::max_size(): interaction.hpp:864 (sigma), :1464 (sigma), :1017 and :905 (sigma*sigcut) */
+static double max_size(int kind, const double *p) { return (kind == 0 || kind == 1) ? p[1] : p[1] * p[2]; }
+
+static void collection_update_trackers(Sys *s);
+
+int port_add_interaction(void *h, int kind, double skin, const double *params, const uint32_t *type,
+                         const double *eps_table, int ntypes, const uint8_t *member, int injected, int share_nl) {
+    Sys *s = (Sys *)h;
+    if (kind < 0 || kind > 3) return -1;
+    int nl = share_nl;
+    if (nl < 0) { /* NeighborList ctor, trackers.cpp:10-17 */
+        s->nls = (NList *)realloc(s->nls, sizeof(NList) * (s->nnls + 1));
+        NList *l = &s->nls[s->nnls];
+        memset(l, 0, sizeof(NList));
+        l->skin = skin;
+        l->member = (uint8_t *)calloc(s->n ? s->n : 1, 1);
+        l->ids = (uint32_t *)calloc(s->n ? s->n : 1, 4);
+        l->diam = (double *)calloc(s->n ? s->n : 1, 8);
+        l->lastlocs = (double *)calloc((size_t)(s->n ? s->n : 1) * s->D, 8);
+        l->ignorechanged = 1;
+        l->injected = injected;
+        nl = s->nnls++;
+    }
+    s->inters = (Inter *)realloc(s->inters, sizeof(Inter) * (s->ninters + 1));
+    Inter *I = &s->inters[s->ninters];
+    memset(I, 0, sizeof(Inter));
+    I->kind = kind;
+    I->nl = nl;
+    I->params = (double *)malloc((size_t)(s->n ? s->n : 1) * 3 * 8);
+    memcpy(I->params, params, (size_t)s->n * 3 * 8);
+    I->type = (uint32_t *)calloc(s->n ? s->n : 1, 4);
+    if (type) memcpy(I->type, type, (size_t)s->n * 4);
+    I->ntypes = ntypes > 0 ? ntypes : 1;
+    I->eps_table = (double *)calloc((size_t)I->ntypes * I->ntypes, 8);
+    if (eps_table) memcpy(I->eps_table, eps_table, (size_t)I->ntypes * I->ntypes * 8);
+    NList *l = &s->nls[nl];
+    for (uint32_t i = 0; i < s->n; i++) { /* NListed::add -> NeighborList::add, interaction.hpp:1906-1910, trackers.hpp:194-201 */
+        if (member && !member[i]) continue;
+        if (l->member[i]) return -3; /* SubGroup::add throws on duplicates, box.hpp:495-501 */
+        l->member[i] = 1;
+        l->ids[l->nids] = i;
+        l->diam[l->nids] = max_size(kind, params + 3 * (size_t)i);
+        memcpy(l->lastlocs + (size_t)l->nids * s->D, s->x + (size_t)i * s->D, 8 * s->D);
+        l->nids++;
+        l->ignorechanged = 1;
+    }
+    return s->ninters++;
+}
+
+static void push_pair(NList *l, uint32_t a, uint32_t b) {
+    if (l->npairs == l->cap) {
+        l->cap = l->cap ? l->cap * 2 : 1024;
+        l->first = (uint32_t *)realloc(l->first, l->cap * 4);
+        l->last = (uint32_t *)realloc(l->last, l->cap * 4);
+    }
+    l->first[l->npairs] = a;
+    l->last[l->npairs] = b;
+    l->npairs++;
+}
+
+static int cmp_u32(const void *a, const void *b) {
+    uint32_t x = *(const uint32_t *)a, y = *(const uint32_t *)b;
+    return x < y ? -1 : x > y;
+}
+
+/* predicate of trackers.cpp:65-66 on SubGroup slots i, j */
+static inline int nl_pred(const Sys *s, const NList *l, uint32_t i, uint32_t j) {
+    double d[3] = {0, 0, 0};
+    double diam = (l->diam[i] + l->diam[j]) / 2;
+    box_diff(s, s->x + (size_t)l->ids[i] * s->D, s->x + (size_t)l->ids[j] * s->D, d);
+    return sqrt(sum3(s->D, d[0] * d[0], d[1] * d[1], d[2] * d[2])) < (diam + l->skin);
+}
+
+/* NeighborList::update_list, trackers.cpp:19-85 */
+static int nl_update_list(Sys *s, NList *l, int force) {
+    const int D = s->D;
+    if (!force && !l->ignorechanged) { /* trackers.cpp:23-53 */
+        double bigdist = 0, biggestdist = 0;
+        for (uint32_t i = 0; i < l->nids; i++) {
+            const double *x = s->x + (size_t)l->ids[i] * D, *x0 = l->lastlocs + (size_t)i * D;
+            double d0 = x[0] - x0[0], d1 = x[1] - x0[1], d2 = D == 3 ? x[2] - x0[2] : 0;
+            double curdist = sqrt(sum3(D, d0 * d0, d1 * d1, d2 * d2));
+            if (curdist > biggestdist) {
+                bigdist = biggestdist;
+                biggestdist = curdist;
+            } else if (curdist > bigdist) {
+                bigdist = curdist;
+            } else
+                continue;
+            if (bigdist + biggestdist >= l->skin) {
+                force = 1;
+                break;
+            }
+        }
+        if (!force) return 0;
+    }
+    l->updatenum++;
+    l->ignorechanged = 0;
+    l->npairs = 0;
+    const uint32_t N = l->nids;
+    int usecells = l->injected;
+    int nc[3] = {1, 1, 1};
+    size_t ncell = 1;
+    if (usecells) {
+        double maxd = 0;
+        for (uint32_t i = 0; i < N; i++)
+            if (l->diam[i] > maxd) maxd = l->diam[i];
+        double rc = (maxd + l->skin) * (1 + 1e-9) + 1e-9;
+        for (int d = 0; d < D; d++) {
+            nc[d] = (int)floor(s->L[d] / rc);
+            if (nc[d] < 3) usecells = 0;
+            if (nc[d] > 256) nc[d] = 256;
+            ncell *= (size_t)(nc[d] < 1 ? 1 : nc[d]);
+        }
+    }
+    if (!usecells) { /* trackers.cpp:59-69 verbatim order */
+        for (uint32_t i = 0; i < N; i++) {
+            memcpy(l->lastlocs + (size_t)i * D, s->x + (size_t)l->ids[i] * D, 8 * D);
+            for (uint32_t j = 0; j < i; j++)
+                if (nl_pred(s, l, i, j)) push_pair(l, l->ids[i], l->ids[j]);
+        }
+        return 1;
+    }
+    /* cell-list pair finder: same predicate, same (i asc, j asc) output order */
+    int *cidx = (int *)malloc((size_t)N * D * sizeof(int));
+    uint32_t *cellstart = (uint32_t *)calloc(ncell + 1, 4), *cellatoms = (uint32_t *)malloc((size_t)N * 4);
+    size_t *cellof = (size_t *)malloc((size_t)N * sizeof(size_t));
+    for (uint32_t i = 0; i < N; i++) {
+        const double *x = s->x + (size_t)l->ids[i] * D;
+        memcpy(l->lastlocs + (size_t)i * D, x, 8 * D);
+        size_t c = 0;
+        for (int d = 0; d < D; d++) {
+            double w = x[d] - s->L[d] * floor(x[d] / s->L[d]);
+            int k = (int)floor(w / s->L[d] * nc[d]);
+            if (k < 0) k = 0;
+            if (k >= nc[d]) k = nc[d] - 1;
+            cidx[(size_t)i * D + d] = k;
+            c = c * nc[d] + k;
+        }
+        cellof[i] = c;
+        cellstart[c + 1]++;
+    }
+    for (size_t c = 0; c < ncell; c++) cellstart[c + 1] += cellstart[c];
+    uint32_t *fill = (uint32_t *)malloc(ncell * 4);
+    memcpy(fill, cellstart, ncell * 4);
+    for (uint32_t i = 0; i < N; i++) cellatoms[fill[cellof[i]]++] = i;
+    free(fill);
+    int nst = D == 3 ? 27 : 9;
+    uint32_t *js = NULL;
+    size_t njs = 0, capjs = 0;
+    for (uint32_t i = 0; i < N; i++) {
+        njs = 0;
+        for (int st = 0; st < nst; st++) {
+            int off[3], t = st;
+            for (int d = D - 1; d >= 0; d--) { off[d] = t % 3 - 1; t /= 3; }
+            size_t c = 0;
+            for (int d = 0; d < D; d++) c = c * nc[d] + (size_t)((cidx[(size_t)i * D + d] + off[d] + nc[d]) % nc[d]);
+            for (uint32_t q = cellstart[c]; q < cellstart[c + 1]; q++) {
+                uint32_t j = cellatoms[q];
+                if (j >= i) break;
+                if (nl_pred(s, l, i, j)) {
+                    if (njs == capjs) { capjs = capjs ? capjs * 2 : 256; js = (uint32_t *)realloc(js, capjs * 4); }
+                    js[njs++] = j;
+                }
+            }
+        }
+        qsort(js, njs, 4, cmp_u32);
+        for (size_t q = 0; q < njs; q++) push_pair(l, l->ids[i], l->ids[js[q]]);
+    }
+    free(js); free(cidx); free(cellstart); free(cellatoms); free(cellof);
+    return 1;
+}
+
+/* NListed<A,P>::update_pairs, interaction.hpp:2102-2115; pair constructors:
+ * LJRepulsePair :878-883, RepulsionPair :1531-1536, LJAttractRepulsePair :1255-1270,
+ * LennardJonesCutPair :970-974 + LennardJonesCut ctor :247-252 */
+static void update_pairs(Sys *s, Inter *I) {
+    NList *l = &s->nls[I->nl];
+    if (I->last_update == l->updatenum) return;
+    I->last_update = l->updatenum;
+    if (l->npairs > I->cappairs) {
+        I->cappairs = l->npairs;
+        I->pairs = (Pair *)realloc(I->pairs, I->cappairs * sizeof(Pair));
+    }
+    I->npairs = l->npairs;
+    for (size_t k = 0; k < l->npairs; k++) {
+        uint32_t i = l->first[k], j = l->last[k];
+        const double *p1 = I->params + 3 * (size_t)i, *p2 = I->params + 3 * (size_t)j;
+        Pair P;
+        P.i = i; P.j = j; P.c = 0; P.cutE = 0;
+        if (I->kind == 0) {
+            P.eps = sqrt(p1[0] * p2[0]);
+            P.sig = (p1[1] + p2[1]) / 2;
+        } else if (I->kind == 1) {
+            P.eps = sqrt(p1[0] * p2[0]);
+            P.sig = (p1[1] + p2[1]) / 2.0;
+            P.c = (p1[2] + p2[2]) / 2.0;
+        } else if (I->kind == 2) {
+            P.eps = I->eps_table[(size_t)I->type[i] * I->ntypes + I->type[j]];
+            P.sig = (p1[1] + p2[1]) / 2.0;
+            P.c = p1[2] > p2[2] ? p1[2] : p2[2]; /* max(a1.sigcut, a2.sigcut) */
+            if (P.eps <= 0) {
+                P.c = 1;
+                P.cutE = 0;
+                P.eps = fabs(P.eps);
+            } else {
+                double mid = (1 - pow(P.c, -6));
+                P.cutE = P.eps * (mid * mid);
+            }
+        } else {
+            P.eps = sqrt(p1[0] * p2[0]);
+            P.sig = (p1[1] + p2[1]) / 2;
+            P.c = p1[2] > p2[2] ? p1[2] : p2[2];
+            double rsix = pow(P.c, 6);
+            double mid = (1 - 1 / rsix);
+            P.cutE = P.eps * (mid * mid - 1);
+        }
+        I->pairs[k] = P;
+    }
+}
+
+/* P::forces(box): LJRepulsive::forces interaction.hpp:135-151; RepulsionPair::forces :1544-1550;
+ * LJAttractRepulsePair::forces :1289-1298; LennardJonesCut::forces :259-267.
+ * Returns 0 when the force is exactly Vec::Zero(). rij = diff(atom1->x, atom2->x). */
+static int pair_forces(const Sys *s, const Inter *I, const Pair *P, double *rij, double *f) {
+    const int D = s->D;
+    rij[2] = 0;
+    f[0] = f[1] = f[2] = 0;
+    if (I->kind == 2 && P->eps == 0) return 0;
+    box_diff(s, s->x + (size_t)P->i * D, s->x + (size_t)P->j * D, rij);
+    double dsq = sum3(D, rij[0] * rij[0], rij[1] * rij[1], rij[2] * rij[2]);
+    double scal;
+    if (I->kind == 0) {
+        double rsq = dsq / (P->sig * P->sig);
+        if (rsq > 1) return 0;
+        double rsix = rsq * rsq * rsq;
+        double fmagTimesR = 12 * P->eps / rsix * (1 / rsix - 1);
+        scal = fmagTimesR / dsq;
+    } else if (I->kind == 1) {
+        if (dsq > P->sig * P->sig) return 0;
+        double R = sqrt(dsq);
+        scal = P->eps * pow(1.0 - (R / P->sig), P->c - 1) / P->sig / R;
+    } else if (I->kind == 2) {
+        double rsq = dsq / (P->sig * P->sig);
+        if (rsq > (P->c * P->c)) return 0;
+        double rsix = pow(rsq, -3);
+        double fmagTimesR = 12 * P->eps * rsix * (rsix - 1);
+        scal = fmagTimesR / dsq;
+    } else {
+        double rsq = dsq / (P->sig * P->sig);
+        if (rsq > (P->c * P->c)) return 0;
+        double rsix = rsq * rsq * rsq;
+        double fmagTimesR = 12 * P->eps / rsix * (1 / rsix - 1);
+        scal = fmagTimesR / dsq;
+    }
+    for (int k = 0; k < D; k++) f[k] = rij[k] * scal;
+    return 1;
+}
+
+/* P::energy(box): LJRepulsive::energy :126-133; RepulsionPair::energy :1537-1543;
+ * LJAttractRepulsePair::energy :1271-1288; LennardJonesCut::energy :253-258 */
+static double pair_energy(const Sys *s, const Inter *I, const Pair *P) {
+    const int D = s->D;
+    double rij[3] = {0, 0, 0};
+    box_diff(s, s->x + (size_t)P->i * D, s->x + (size_t)P->j * D, rij);
+    double dsq = sum3(D, rij[0] * rij[0], rij[1] * rij[1], rij[2] * rij[2]);
+    if (I->kind == 0) {
+        double rsq = dsq / (P->sig * P->sig);
+        if (rsq > 1) return 0;
+        double rsix = rsq * rsq * rsq;
+        double mid = (1 - 1 / rsix);
+        return P->eps * (mid * mid);
+    } else if (I->kind == 1) {
+        if (dsq > P->sig * P->sig) return 0.0;
+        double R = sqrt(dsq);
+        return P->eps * pow(1.0 - (R / P->sig), P->c) / P->c;
+    } else if (I->kind == 2) {
+        double rsq = dsq / (P->sig * P->sig);
+        if (rsq > P->c * P->c) return 0;
+        double mid = (1 - pow(rsq, -3));
+        return P->eps * (mid * mid) - P->cutE;
+    } else {
+        double rsq = dsq / (P->sig * P->sig);
+        if (rsq > (P->c * P->c)) return 0;
+        double rsix = rsq * rsq * rsq;
+        double mid = (1 - 1 / rsix);
+        return P->eps * (mid * mid - 1) - P->cutE;
+    }
+}
+
+/* NListed::set_forces :2166-2175, set_forces_get_pressure :2232-2245, pressure :2248-2261,
+ * stress / set_forces_get_stress :2264-2291.  mode bit0: scatter forces; p_out: sum r.f; st: D x D */
+static void inter_loop(Sys *s, Inter *I, int scatter, double *p_out, double *st) {
+    const int D = s->D;
+    update_pairs(s, I);
+    double p = 0;
+    if (st) memset(st, 0, sizeof(double) * D * D);
+    for (size_t k = 0; k < I->npairs; k++) {
+        const Pair *P = &I->pairs[k];
+        double rij[3], f[3];
+        pair_forces(s, I, P, rij, f);
+        if (scatter)
+            for (int d = 0; d < D; d++) {
+                s->f[(size_t)P->i * D + d] += f[d];
+                s->f[(size_t)P->j * D + d] -= f[d];
+            }
+        if (p_out || st) {
+            double r[3] = {0, 0, 0};
+            box_diff(s, s->x + (size_t)P->i * D, s->x + (size_t)P->j * D, r);
+            if (p_out) p += sum3(D, r[0] * f[0], r[1] * f[1], r[2] * f[2]);
+            if (st)
+                for (int a = 0; a < D; a++)
+                    for (int b = 0; b < D; b++) st[a * D + b] += r[a] * f[b];
+        }
+    }
+    if (p_out) *p_out = p;
+}
+
+static double inter_energy(Sys *s, Inter *I) { /* NListed::energy :2154-2163 */
+    update_pairs(s, I);
+    double E = 0;
+    for (size_t k = 0; k < I->npairs; k++) E += pair_energy(s, I, &I->pairs[k]);
+    return E;
+}
+
+/* ---- AtomGroup reductions, box.cpp:239-260, 401-431 ---- */
+static double group_mass(const Sys *s) {
+    double m = 0;
+    for (uint32_t i = 0; i < s->n; i++)
+        if (!frozen_le(s->m[i])) m += s->m[i];
+    return m;
+}
+static void group_momentum(const Sys *s, double *tot) {
+    tot[0] = tot[1] = tot[2] = 0;
+    for (uint32_t i = 0; i < s->n; i++) {
+        if (frozen_le(s->m[i])) continue;
+        for (int d = 0; d < s->D; d++) tot[d] += s->v[(size_t)i * s->D + d] * s->m[i];
+    }
+}
+static void group_com_velocity(const Sys *s, double *out) {
+    group_momentum(s, out);
+    double M = group_mass(s);
+    for (int d = 0; d < s->D; d++) out[d] = out[d] / M;
+}
+static double group_ke(const Sys *s, const double *v0) {
+    double totE = 0;
+    for (uint32_t i = 0; i < s->n; i++) {
+        if (frozen_eq(s->m[i])) continue;
+        double c[3] = {0, 0, 0};
+        for (int d = 0; d < s->D; d++) c[d] = s->v[(size_t)i * s->D + d] - v0[d];
+        totE += s->m[i] / 2 * dotD(s->D, c, c);
+    }
+    return totE;
+}
+
+/* Collection::update_trackers, collection.cpp:45-50 -> NeighborList::update, trackers.hpp:173-176 */
+static void collection_update_trackers(Sys *s) {
+    for (int k = 0; k < s->nnls; k++) nl_update_list(s, &s->nls[k], 0);
+}
+
+/* Collection::set_forces, collection.cpp:159-179 */
+static void collection_set_forces(Sys *s, int constraints_and_a) {
+    const int D = s->D;
+    memset(s->f, 0, (size_t)s->n * D * 8); /* reset_forces box.cpp:427-431 */
+    for (int k = 0; k < s->ninters; k++) inter_loop(s, &s->inters[k], 1, NULL, NULL);
+    if (!constraints_and_a) return;
+    for (uint32_t i = 0; i < s->n; i++) {
+        if (frozen_le(s->m[i])) {
+            for (int d = 0; d < D; d++) s->a[(size_t)i * D + d] = 0;
+            continue;
+        }
+        for (int d = 0; d < D; d++) s->a[(size_t)i * D + d] = s->f[(size_t)i * D + d] / s->m[i];
+    }
+}
+
+/* CollectionSol::set_constants, collection.cpp:230-263; BivariateGauss::set vecrand.cpp:48-63 */
+static int sol_set_constants(Sys *s) {
+    if (s->force_mag <= 0.0) {
+        s->c0 = 1; s->c1 = 1; s->c2 = .5; s->sigmar = 0; s->sigmav = 0; s->corr = 1;
+    } else {
+        double dampdt = s->force_mag * s->dt;
+        s->c0 = exp(-dampdt);
+        s->c1 = (-expm1(-dampdt)) / dampdt;
+        s->c2 = (1 - s->c1) / dampdt;
+        if (dampdt > 1e-4)
+            s->sigmar = sqrt((1 / dampdt) * (2 - (-4 * expm1(-dampdt) + expm1(-2 * dampdt)) / dampdt));
+        else
+            s->sigmar = sqrt(2 * dampdt / 3 - dampdt * dampdt / 2 + 7 * dampdt * dampdt * dampdt / 30);
+        s->sigmav = sqrt(-expm1(-2 * dampdt));
+        double exdpdt = (-expm1(-dampdt));
+        s->corr = exdpdt * exdpdt / dampdt / s->sigmar / s->sigmav;
+    }
+    if (!(s->sigmar >= 0) || !(s->sigmav >= 0) || !(s->corr >= 0) || !(s->corr <= 1)) return -1;
+    s->x11 = s->sigmar;
+    s->x21 = s->sigmav * s->corr;
+    s->x22 = s->sigmav * sqrt(1 - s->corr * s->corr);
+    return 0;
+}
+
+/* Collection ctor + initialize, collection.cpp:3-19; add_tracker/add_interaction collection.hpp:113-120 */
+int port_make_collection(void *h, int integrator, double dt, double damping, double T) {
+    Sys *s = (Sys *)h;
+    if (integrator != 0 && integrator != 1) return -1;
+    s->integrator = integrator;
+    s->dt = dt;
+    if (integrator == 1) {
+        if (dt <= 0) return -2;
+        s->damping = damping;
+        s->force_mag = damping;
+        s->desT = T;
+        if (sol_set_constants(s)) return -2;
+    }
+    /* initialize() with empty interaction/tracker vectors: set_forces(true) zeroes f, a = f/m */
+    memset(s->f, 0, (size_t)s->n * s->D * 8);
+    for (uint32_t i = 0; i < s->n; i++)
+        for (int d = 0; d < s->D; d++) s->a[(size_t)i * s->D + d] = frozen_le(s->m[i]) ? 0.0 : s->f[(size_t)i * s->D + d] / s->m[i];
+    /* add_tracker(nl) x nnls: the k-th call updates trackers 0..k; add_interaction x ninters: all */
+    for (int k = 0; k < s->nnls; k++)
+        for (int q = 0; q <= k; q++) nl_update_list(s, &s->nls[q], 0);
+    for (int k = 0; k < s->ninters; k++) collection_update_trackers(s);
+    return 0;
+}
+
+void port_get_sol_constants(void *h, double *out) {
+    Sys *s = (Sys *)h;
+    out[0] = s->c0; out[1] = s->c1; out[2] = s->c2; out[3] = s->x11; out[4] = s->x21; out[5] = s->x22;
+}
+
+/* z: per step, per non-frozen atom in atom order: D normals (x1) then D normals (x2) */
+void port_inject_noise(void *h, const double *z, size_t len) {
+    Sys *s = (Sys *)h;
+    s->noise = z;
+    s->noise_len = len;
+    s->noise_pos = 0;
+}
+
+/* CollectionVerlet::timestep, collection.cpp:442-469 */
+static void verlet_timestep(Sys *s) {
+    const int D = s->D;
+    const double dt = s->dt;
+    for (uint32_t i = 0; i < s->n; i++) {
+        double *x = s->x + (size_t)i * D, *v = s->v + (size_t)i * D, *a = s->a + (size_t)i * D;
+        if (frozen_le(s->m[i])) {
+            for (int d = 0; d < D; d++) v[d] = 0;
+            continue;
+        }
+        for (int d = 0; d < D; d++) {
+            x[d] += v[d] * dt + a[d] * (dt * dt / 2);
+            v[d] += a[d] * (dt / 2);
+        }
+    }
+    collection_set_forces(s, 0);
+    for (uint32_t i = 0; i < s->n; i++) {
+        double *v = s->v + (size_t)i * D, *a = s->a + (size_t)i * D, *f = s->f + (size_t)i * D;
+        if (frozen_le(s->m[i])) {
+            for (int d = 0; d < D; d++) a[d] = 0;
+            continue;
+        }
+        for (int d = 0; d < D; d++) {
+            a[d] = f[d] / s->m[i];
+            v[d] += a[d] * (dt / 2);
+        }
+    }
+    collection_update_trackers(s);
+}
+
+/* CollectionSol::timestep, collection.cpp:265-322; gen_vecs vecrand.cpp:73-85 */
+static void sol_timestep(Sys *s) {
+    const int D = s->D;
+    const double dt = s->dt;
+    for (uint32_t i = 0; i < s->n; i++) {
+        double *x = s->x + (size_t)i * D, *v = s->v + (size_t)i * D, *a = s->a + (size_t)i * D;
+        if (frozen_le(s->m[i])) {
+            for (int d = 0; d < D; d++) v[d] = 0;
+            continue;
+        }
+        double v0 = sqrt(s->desT / s->m[i]);
+        double r0 = dt * v0;
+        double drG[3] = {0, 0, 0}, dvG[3] = {0, 0, 0};
+        if (s->damping > 0) {
+            double x1[3] = {0, 0, 0}, x2[3] = {0, 0, 0};
+            if (s->noise && s->noise_pos + 2 * D <= s->noise_len) {
+                for (int d = 0; d < D; d++) x1[d] = s->noise[s->noise_pos + d];
+                for (int d = 0; d < D; d++) x2[d] = s->noise[s->noise_pos + D + d];
+                s->noise_pos += 2 * D;
+            }
+            for (int d = 0; d < D; d++) {
+                drG[d] = x1[d] * s->x11;
+                dvG[d] = x1[d] * s->x21 + x2[d] * s->x22;
+            }
+        }
+        for (int d = 0; d < D; d++) {
+            double xn = x[d] + ((v[d] * (s->c1 * dt) + a[d] * (s->c2 * dt * dt)) + drG[d] * r0);
+            double vn = (v[d] * s->c0 + a[d] * (dt * (s->c1 - s->c2))) + dvG[d] * v0;
+            x[d] = xn;
+            v[d] = vn;
+        }
+    }
+    collection_set_forces(s, 0);
+    for (uint32_t i = 0; i < s->n; i++) {
+        double *a = s->a + (size_t)i * D, *f = s->f + (size_t)i * D;
+        if (frozen_eq(s->m[i])) {
+            for (int d = 0; d < D; d++) a[d] = 0;
+            continue;
+        }
+        for (int d = 0; d < D; d++) a[d] = f[d] / s->m[i];
+    }
+    for (uint32_t i = 0; i < s->n; i++) {
+        double *v = s->v + (size_t)i * D, *a = s->a + (size_t)i * D;
+        if (frozen_eq(s->m[i])) {
+            for (int d = 0; d < D; d++) v[d] = 0;
+            continue;
+        }
+        for (int d = 0; d < D; d++) v[d] += a[d] * (dt * s->c2);
+    }
+    collection_update_trackers(s);
+}
+
+void port_timestep(void *h, int nsteps) {
+    Sys *s = (Sys *)h;
+    for (int k = 0; k < nsteps; k++) {
+        if (s->integrator == 0) verlet_timestep(s);
+        else if (s->integrator == 1) sol_timestep(s);
+    }
+}
+
+int port_update_list(void *h, int nl, int force) { Sys *s = (Sys *)h; return nl_update_list(s, &s->nls[nl], force); }
+uint32_t port_which(void *h, int nl) { return ((Sys *)h)->nls[nl].updatenum; }
+uint32_t port_numpairs(void *h, int nl) { return (uint32_t)((Sys *)h)->nls[nl].npairs; }
+void port_get_pairs(void *h, int nl, uint32_t *first, uint32_t *last) {
+    NList *l = &((Sys *)h)->nls[nl];
+    memcpy(first, l->first, l->npairs * 4);
+    memcpy(last, l->last, l->npairs * 4);
+}
+void port_set_atoms(void *h, const double *x, const double *v, const double *a, const double *f) {
+    Sys *s = (Sys *)h;
+    size_t nb = (size_t)s->n * s->D * 8;
+    if (x) memcpy(s->x, x, nb);
+    if (v) memcpy(s->v, v, nb);
+    if (a) memcpy(s->a, a, nb);
+    if (f) memcpy(s->f, f, nb);
+}
+void port_get_atoms(void *h, double *x, double *v, double *a, double *f) {
+    Sys *s = (Sys *)h;
+    size_t nb = (size_t)s->n * s->D * 8;
+    if (x) memcpy(x, s->x, nb);
+    if (v) memcpy(v, s->v, nb);
+    if (a) memcpy(a, s->a, nb);
+    if (f) memcpy(f, s->f, nb);
+}
+void port_box_diff(void *h, const double *r1, const double *r2, double *out) { box_diff((Sys *)h, r1, r2, out); }
+double port_box_V(void *h) { /* box.hpp:122,127 */
+    Sys *s = (Sys *)h;
+    return s->D == 3 ? s->L[0] * s->L[1] * s->L[2] : s->L[0] * s->L[1];
+}
+void port_reset_forces(void *h) { Sys *s = (Sys *)h; memset(s->f, 0, (size_t)s->n * s->D * 8); }
+void port_inter_set_forces(void *h, int k) { Sys *s = (Sys *)h; inter_loop(s, &s->inters[k], 1, NULL, NULL); }
+double port_inter_set_forces_get_pressure(void *h, int k) { Sys *s = (Sys *)h; double p; inter_loop(s, &s->inters[k], 1, &p, NULL); return p; }
+double port_inter_energy(void *h, int k) { Sys *s = (Sys *)h; return inter_energy(s, &s->inters[k]); }
+double port_inter_pressure(void *h, int k) { Sys *s = (Sys *)h; double p; inter_loop(s, &s->inters[k], 0, &p, NULL); return p; }
+void port_inter_stress(void *h, int k, double *out) { Sys *s = (Sys *)h; inter_loop(s, &s->inters[k], 0, NULL, out); }
+
+void port_set_forces(void *h, int constraints_and_a) { collection_set_forces((Sys *)h, constraints_and_a); }
+double port_kinetic_energy(void *h) { double z[3] = {0, 0, 0}; return group_ke((Sys *)h, z); }
+double port_potential_energy(void *h) { /* collection.cpp:98-108 */
+    Sys *s = (Sys *)h;
+    double E = 0;
+    for (int k = 0; k < s->ninters; k++) E += inter_energy(s, &s->inters[k]);
+    return E;
+}
+double port_energy(void *h) { return port_potential_energy(h) + port_kinetic_energy(h); } /* :110-114 */
+double port_degrees_of_freedom(void *h) { /* :116-133 */
+    Sys *s = (Sys *)h;
+    int ndof = 0;
+    for (uint32_t i = 0; i < s->n; i++)
+        if (!frozen_le(s->m[i])) ndof += s->D;
+    return ndof;
+}
+double port_temp(void *h, int minuscomv) { /* :135-142 */
+    Sys *s = (Sys *)h;
+    double v[3] = {0, 0, 0};
+    if (minuscomv) group_com_velocity(s, v);
+    int ndof = (int)port_degrees_of_freedom(h);
+    if (minuscomv) ndof -= s->D;
+    return group_ke(s, v) * 2 / ndof;
+}
+double port_virial(void *h) { /* :73-80 */
+    Sys *s = (Sys *)h;
+    double E = 0;
+    for (int k = 0; k < s->ninters; k++) {
+        double p;
+        inter_loop(s, &s->inters[k], 0, &p, NULL);
+        E += p;
+    }
+    return E;
+}
+double port_pressure(void *h) { /* :85-96 */
+    Sys *s = (Sys *)h;
+    double V = port_box_V(h);
+    double E = 2.0 * port_kinetic_energy(h);
+    for (int k = 0; k < s->ninters; k++) {
+        double p;
+        inter_loop(s, &s->inters[k], 0, &p, NULL);
+        E += p;
+    }
+    return E / V / (double)s->D;
+}
+void port_com_velocity(void *h, double *out) { double t[3]; group_com_velocity((Sys *)h, t); memcpy(out, t, 8 * ((Sys *)h)->D); }
+void port_momentum(void *h, double *out) { double t[3]; group_momentum((Sys *)h, t); memcpy(out, t, 8 * ((Sys *)h)->D); }
+double port_mass(void *h) { return group_mass((Sys *)h); }
+double port_atoms_kinetic_energy(void *h, const double *v0) { double t[3] = {0, 0, 0}; memcpy(t, v0, 8 * ((Sys *)h)->D); return group_ke((Sys *)h, t); }
+void port_add_velocity(void *h, const double *dv) { /* box.cpp:413-417 */
+    Sys *s = (Sys *)h;
+    for (uint32_t i = 0; i < s->n; i++)
+        for (int d = 0; d < s->D; d++) s->v[(size_t)i * s->D + d] += dv[d];
+}
+void port_reset_com_velocity(void *h) { /* box.hpp:423 */
+    Sys *s = (Sys *)h;
+    double c[3];
+    group_com_velocity(s, c);
+    for (int d = 0; d < s->D; d++) c[d] = -c[d];
+    port_add_velocity(h, c);
+}
+void port_scale_velocities(void *h, double scaleby) { /* collection.cpp:21-29 */
+    Sys *s = (Sys *)h;
+    for (uint32_t i = 0; i < s->n; i++) {
+        if (frozen_le(s->m[i])) continue;
+        for (int d = 0; d < s->D; d++) s->v[(size_t)i * s->D + d] *= scaleby;
+    }
+}
+void port_scale_velocities_to_temp(void *h, double T, int minuscomv) { /* :31-35 */
+    double t = port_temp(h, minuscomv);
+    port_scale_velocities(h, sqrt(T / t));
+}
+void port_scale_velocities_to_energy(void *h, double E) { /* :37-43 */
+    double E0 = port_energy(h);
+    double k0 = port_kinetic_energy(h);
+    double goalkinetic = k0 + (E - E0);
+    port_scale_velocities(h, sqrt(goalkinetic / k0));
+}

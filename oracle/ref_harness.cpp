@@ -1,0 +1,403 @@
+// TEST INFRASTRUCTURE ONLY -- never linked into, imported by, or executed from
+// the product path (parm_b200/). Only tests/, __graft_entry__.smoke() and
+// bench.py's cpu_baseline / --impl reference legs may load the library this
+// file is built into.
+//
+// C-ABI harness around the UNMODIFIED reference classes. It is compiled
+// together with /root/reference/src/{vecrand,box,trackers,interaction,
+// collection}.cpp (in place, never copied) against oracle/shim/ into
+// oracle/_ref/libparm_ref{2,3}d.so by oracle/Makefile. Every physics result
+// returned here is computed by the reference's own code:
+//   OriginBox::diff                      box.hpp:97-104
+//   NeighborList::update_list            trackers.cpp:19-85
+//   NListed<A,P>::{set_forces,energy,pressure,stress,...}  interaction.hpp:2102-2291
+//   CollectionVerlet::timestep           collection.cpp:442-469
+//   CollectionSol::timestep              collection.cpp:265-322
+//   Collection::{energy,pressure,temp,...}   collection.cpp:21-142
+//
+// The only non-reference logic is InjectedNeighborList (large-N pair finder,
+// SURVEY 8c): a CPU cell list that evaluates the reference's own predicate
+// (box->diff(...).norm() < diam + skin) and emits pairs in the reference's
+// (i ascending, j<i ascending) order; tests prove it identical to
+// update_list(true) at small N.
+#include <cstdint>
+#include <cstring>
+#include <string>
+
+#include "collection.hpp"
+#include "interaction.hpp"
+
+extern "C" {
+// the shim's normal_distribution reads from here when non-null (noise injection
+// for CollectionSol parity; see oracle/shim/boost/random/normal_distribution.hpp)
+const double *parm_oracle_noise = 0;
+size_t parm_oracle_noise_len = 0;
+size_t parm_oracle_noise_pos = 0;
+}
+
+namespace {
+
+struct FastSubGroup : public SubGroup {
+    // SubGroup::add is O(size) (std::find duplicate check, box.hpp:495-501);
+    // for 1e6 atoms that is 5e11 compares. Skips only the duplicate check.
+    void add_fast(AtomID a) { ids.push_back(a); }
+};
+
+class InjectedNeighborList : public NeighborList {
+   public:
+    sptr<OriginBox> obox;
+    bool injected;
+    InjectedNeighborList(sptr<OriginBox> b, sptr<AtomVec> av, flt skin, bool injected)
+        : NeighborList(boost::static_pointer_cast<Box>(b), av, skin), obox(b), injected(injected) {}
+
+    void add_fast(AtomID a, flt diameter) {
+        static_cast<FastSubGroup &>(atoms).add_fast(a);
+        diameters.push_back(diameter);
+        lastlocs.push_back(a->x);
+        ignorechanged = true;
+    }
+
+    // reference drift rule, trackers.cpp:23-53, then cell-list build
+    bool update_list_cells(bool force) {
+        if (!injected) return update_list(force);
+        if (not force and not ignorechanged) {
+            flt bigdist = 0, biggestdist = 0;
+            for (uint i = 0; i < atoms.size(); i++) {
+                Atom &atm = atoms[i];
+                flt curdist = (atm.x - lastlocs[i]).norm();
+                if (curdist > biggestdist) {
+                    bigdist = biggestdist;
+                    biggestdist = curdist;
+                } else if (curdist > bigdist) {
+                    bigdist = curdist;
+                } else
+                    continue;
+                if (bigdist + biggestdist >= skin) {
+                    force = true;
+                    break;
+                }
+            }
+            if (not force) return false;
+        }
+        updatenum++;
+        ignorechanged = false;
+        curpairs.clear();
+        const uint N = atoms.size();
+        Vec L = obox->box_shape();
+        flt maxd = 0;
+        for (uint i = 0; i < N; i++) maxd = max(maxd, diameters[i]);
+        flt rc = (maxd + skin) * (1 + 1e-9) + 1e-9;
+        int nc[NDIM];
+        bool small = false;
+        size_t ncell = 1;
+        for (uint d = 0; d < NDIM; d++) {
+            nc[d] = (int)floor(L[d] / rc);
+            if (nc[d] < 3) small = true;
+            if (nc[d] > 256) nc[d] = 256;
+            ncell *= (size_t)(nc[d] < 1 ? 1 : nc[d]);
+        }
+        if (small) {  // box too small for a 3^D stencil: reference loop
+            for (uint i = 0; i < N; i++) {
+                AtomID a1 = atoms.get_id(i);
+                lastlocs[i] = a1->x;
+                for (uint j = 0; j < i; j++) {
+                    AtomID a2 = atoms.get_id(j);
+                    flt diam = (diameters[i] + diameters[j]) / 2;
+                    if (box->diff(a1->x, a2->x).norm() < (diam + skin)) curpairs.push_back(IDPair(a1, a2));
+                }
+            }
+            return true;
+        }
+        vector<int> cidx(N * NDIM);
+        vector<uint> cellstart(ncell + 1, 0), cellatoms(N);
+        vector<size_t> cellof(N);
+        for (uint i = 0; i < N; i++) {
+            Atom &a = atoms[i];
+            lastlocs[i] = a.x;
+            size_t c = 0;
+            for (uint d = 0; d < NDIM; d++) {
+                flt w = a.x[d] - L[d] * floor(a.x[d] / L[d]);
+                int k = (int)floor(w / L[d] * nc[d]);
+                if (k < 0) k = 0;
+                if (k >= nc[d]) k = nc[d] - 1;
+                cidx[i * NDIM + d] = k;
+                c = c * nc[d] + k;
+            }
+            cellof[i] = c;
+            cellstart[c + 1]++;
+        }
+        for (size_t c = 0; c < ncell; c++) cellstart[c + 1] += cellstart[c];
+        {
+            vector<uint> fill(cellstart.begin(), cellstart.end() - 1);
+            for (uint i = 0; i < N; i++) cellatoms[fill[cellof[i]]++] = i;  // ascending i inside a cell
+        }
+        vector<uint> js;
+        int nst = 1;
+        for (uint d = 0; d < NDIM; d++) nst *= 3;
+        for (uint i = 0; i < N; i++) {
+            AtomID a1 = atoms.get_id(i);
+            js.clear();
+            for (int s = 0; s < nst; s++) {
+                size_t c = 0;
+                int t = s;
+                int off[NDIM];
+                for (int d = NDIM - 1; d >= 0; d--) { off[d] = t % 3 - 1; t /= 3; }
+                for (uint d = 0; d < NDIM; d++) {
+                    int k = (cidx[i * NDIM + d] + off[d] + nc[d]) % nc[d];
+                    c = c * nc[d] + k;
+                }
+                for (uint q = cellstart[c]; q < cellstart[c + 1]; q++) {
+                    uint j = cellatoms[q];
+                    if (j >= i) break;  // ascending within a cell
+                    AtomID a2 = atoms.get_id(j);
+                    flt diam = (diameters[i] + diameters[j]) / 2;
+                    if (box->diff(a1->x, a2->x).norm() < (diam + skin)) js.push_back(j);
+                }
+            }
+            std::sort(js.begin(), js.end());
+            for (size_t q = 0; q < js.size(); q++) curpairs.push_back(IDPair(a1, atoms.get_id(js[q])));
+        }
+        return true;
+    }
+    void update(Box &newbox) {
+        assert(&newbox == box.get());
+        update_list_cells(false);
+    }
+    uint index_of(const AtomID &a) { return a.n(); }
+};
+
+template <class A, class P>
+class FastNListed : public NListed<A, P> {
+   public:
+    FastNListed(sptr<AtomVec> vec, sptr<NeighborList> nl) : NListed<A, P>(vec, nl) {}
+    void add_fast(A atm, InjectedNeighborList *inl) {
+        if (inl->injected) {
+            inl->add_fast(atm, atm.max_size());
+            this->atoms[atm.n()] = atm;
+        } else {
+            this->add(atm);
+        }
+    }
+};
+
+struct Sys {
+    sptr<OriginBox> box;
+    sptr<AtomVec> atoms;
+    vector<sptr<Interaction> > inters;
+    vector<sptr<InjectedNeighborList> > nls;
+    sptr<Collection> collec;
+    std::string err;
+};
+
+Vec vec_from(const double *p) {
+    Vec v;
+    for (uint d = 0; d < NDIM; d++) v[d] = p[d];
+    return v;
+}
+
+}  // namespace
+
+extern "C" {
+
+int ref_ndim() { return NDIM; }
+size_t ref_sizeof_atom() { return sizeof(Atom); }
+
+void *ref_sys_create(uint32_t n, const double *L, const double *x, const double *v, const double *m) {
+    Sys *s = new Sys();
+    s->box.reset(new OriginBox(vec_from(L)));
+    vector<double> masses(m, m + n);
+    s->atoms.reset(new AtomVec(masses));
+    AtomVec &av = *s->atoms;
+    for (uint i = 0; i < n; i++) {
+        av[i].x = vec_from(x + (size_t)i * NDIM);
+        if (v) av[i].v = vec_from(v + (size_t)i * NDIM);
+    }
+    return s;
+}
+
+void ref_sys_destroy(void *h) { delete static_cast<Sys *>(h); }
+
+// kind: 0 NListed<EpsSigAtom,LJRepulsePair>            params (eps, sigma)
+//       1 NListed<EpsSigExpAtom,RepulsionPair>         params (eps, sigma, exponent)
+//       2 NListed<IEpsSigCutAtom,LJAttractRepulsePair> params (-, sigma, sigcut) + type + eps_table
+//       3 NListed<EpsSigCutAtom,LennardJonesCutPair>   params (eps, sigma, sigcut)
+// params: n x 3 row-major. member: optional n bytes, 0 = atom not added.
+// injected: 0 = reference O(N^2) NeighborList, 1 = cell-list InjectedNeighborList
+// share_nl: -1 = new NeighborList, else index of an existing list to share
+int ref_add_interaction(void *h, int kind, double skin, const double *params, const uint32_t *type,
+                        const double *eps_table, int ntypes, const uint8_t *member, int injected, int share_nl) {
+    Sys *s = static_cast<Sys *>(h);
+    AtomVec &av = *s->atoms;
+    const uint n = av.size();
+    sptr<InjectedNeighborList> nl;
+    if (share_nl >= 0)
+        nl = s->nls[share_nl];
+    else {
+        nl.reset(new InjectedNeighborList(s->box, s->atoms, skin, injected != 0));
+        s->nls.push_back(nl);
+    }
+    sptr<NeighborList> nlbase = boost::static_pointer_cast<NeighborList>(nl);
+    try {
+        if (kind == 0) {
+            sptr<FastNListed<EpsSigAtom, LJRepulsePair> > I(new FastNListed<EpsSigAtom, LJRepulsePair>(s->atoms, nlbase));
+            for (uint i = 0; i < n; i++)
+                if (!member || member[i]) I->add_fast(EpsSigAtom(av.get_id(i), params[3 * i], params[3 * i + 1]), nl.get());
+            s->inters.push_back(I);
+        } else if (kind == 1) {
+            sptr<FastNListed<EpsSigExpAtom, RepulsionPair> > I(new FastNListed<EpsSigExpAtom, RepulsionPair>(s->atoms, nlbase));
+            for (uint i = 0; i < n; i++)
+                if (!member || member[i])
+                    I->add_fast(EpsSigExpAtom(av.get_id(i), params[3 * i], params[3 * i + 1], params[3 * i + 2]), nl.get());
+            s->inters.push_back(I);
+        } else if (kind == 2) {
+            sptr<FastNListed<IEpsSigCutAtom, LJAttractRepulsePair> > I(
+                new FastNListed<IEpsSigCutAtom, LJAttractRepulsePair>(s->atoms, nlbase));
+            for (uint i = 0; i < n; i++) {
+                if (member && !member[i]) continue;
+                uint t = type ? type[i] : 0;
+                vector<flt> eps(eps_table + (size_t)t * ntypes, eps_table + (size_t)(t + 1) * ntypes);
+                I->add_fast(IEpsSigCutAtom(av.get_id(i), eps, t, params[3 * i + 1], params[3 * i + 2]), nl.get());
+            }
+            s->inters.push_back(I);
+        } else if (kind == 3) {
+            sptr<FastNListed<EpsSigCutAtom, LennardJonesCutPair> > I(
+                new FastNListed<EpsSigCutAtom, LennardJonesCutPair>(s->atoms, nlbase));
+            for (uint i = 0; i < n; i++)
+                if (!member || member[i])
+                    I->add_fast(EpsSigCutAtom(av.get_id(i), params[3 * i], params[3 * i + 1], params[3 * i + 2]), nl.get());
+            s->inters.push_back(I);
+        } else
+            return -1;
+    } catch (std::exception &e) {
+        s->err = e.what();
+        return -2;
+    }
+    return (int)s->inters.size() - 1;
+}
+
+// integrator: 0 CollectionVerlet(dt), 1 CollectionSol(dt, damping, T).
+// Mirrors LJatoms.cpp:79-83: construct, add_tracker(nl), add_interaction(I).
+int ref_make_collection(void *h, int integrator, double dt, double damping, double T) {
+    Sys *s = static_cast<Sys *>(h);
+    try {
+        sptr<Box> b = boost::static_pointer_cast<Box>(s->box);
+        sptr<AtomGroup> ag = boost::static_pointer_cast<AtomGroup>(s->atoms);
+        if (integrator == 0)
+            s->collec.reset(new CollectionVerlet(b, ag, dt));
+        else if (integrator == 1)
+            s->collec.reset(new CollectionSol(b, ag, dt, damping, T));
+        else
+            return -1;
+        for (size_t k = 0; k < s->nls.size(); k++) s->collec->add_tracker(boost::static_pointer_cast<StateTracker>(s->nls[k]));
+        for (size_t k = 0; k < s->inters.size(); k++) s->collec->add_interaction(s->inters[k]);
+    } catch (std::exception &e) {
+        s->err = e.what();
+        return -2;
+    }
+    return 0;
+}
+
+const char *ref_last_error(void *h) { return static_cast<Sys *>(h)->err.c_str(); }
+
+int ref_update_list(void *h, int nl, int force) { return static_cast<Sys *>(h)->nls[nl]->update_list_cells(force != 0) ? 1 : 0; }
+uint32_t ref_which(void *h, int nl) { return static_cast<Sys *>(h)->nls[nl]->which(); }
+uint32_t ref_numpairs(void *h, int nl) { return static_cast<Sys *>(h)->nls[nl]->numpairs(); }
+// pairs in the reference's own order; first() is the later atom (trackers.cpp:59-68)
+void ref_get_pairs(void *h, int nl, uint32_t *first, uint32_t *last) {
+    NeighborList &L = *static_cast<Sys *>(h)->nls[nl];
+    uint k = 0;
+    for (vector<IDPair>::iterator it = L.begin(); it != L.end(); ++it, ++k) {
+        first[k] = it->first().n();
+        last[k] = it->last().n();
+    }
+}
+
+void ref_set_atoms(void *h, const double *x, const double *v, const double *a, const double *f) {
+    AtomVec &av = *static_cast<Sys *>(h)->atoms;
+    for (uint i = 0; i < av.size(); i++) {
+        if (x) av[i].x = vec_from(x + (size_t)i * NDIM);
+        if (v) av[i].v = vec_from(v + (size_t)i * NDIM);
+        if (a) av[i].a = vec_from(a + (size_t)i * NDIM);
+        if (f) av[i].f = vec_from(f + (size_t)i * NDIM);
+    }
+}
+void ref_get_atoms(void *h, double *x, double *v, double *a, double *f) {
+    AtomVec &av = *static_cast<Sys *>(h)->atoms;
+    for (uint i = 0; i < av.size(); i++)
+        for (uint d = 0; d < NDIM; d++) {
+            if (x) x[(size_t)i * NDIM + d] = av[i].x[d];
+            if (v) v[(size_t)i * NDIM + d] = av[i].v[d];
+            if (a) a[(size_t)i * NDIM + d] = av[i].a[d];
+            if (f) f[(size_t)i * NDIM + d] = av[i].f[d];
+        }
+}
+
+void ref_box_diff(void *h, const double *r1, const double *r2, double *out) {
+    Vec d = static_cast<Sys *>(h)->box->diff(vec_from(r1), vec_from(r2));
+    for (uint k = 0; k < NDIM; k++) out[k] = d[k];
+}
+double ref_box_V(void *h) { return static_cast<Sys *>(h)->box->V(); }
+
+// Interaction-level calls (do not reset forces: exactly the virtuals)
+void ref_reset_forces(void *h) { static_cast<Sys *>(h)->atoms->reset_forces(); }
+void ref_inter_set_forces(void *h, int k) { Sys *s = static_cast<Sys *>(h); s->inters[k]->set_forces(*s->box); }
+double ref_inter_set_forces_get_pressure(void *h, int k) { Sys *s = static_cast<Sys *>(h); return s->inters[k]->set_forces_get_pressure(*s->box); }
+double ref_inter_energy(void *h, int k) { Sys *s = static_cast<Sys *>(h); return s->inters[k]->energy(*s->box); }
+double ref_inter_pressure(void *h, int k) { Sys *s = static_cast<Sys *>(h); return s->inters[k]->pressure(*s->box); }
+void ref_inter_stress(void *h, int k, double *out) {
+    Sys *s = static_cast<Sys *>(h);
+    Matrix m = s->inters[k]->stress(*s->box);
+    for (uint i = 0; i < NDIM; i++)
+        for (uint j = 0; j < NDIM; j++) out[i * NDIM + j] = m(i, j);
+}
+
+// Collection-level
+void ref_timestep(void *h, int nsteps) {
+    Collection &c = *static_cast<Sys *>(h)->collec;
+    for (int i = 0; i < nsteps; i++) c.timestep();
+}
+void ref_set_forces(void *h, int constraints_and_a) { static_cast<Sys *>(h)->collec->set_forces(constraints_and_a != 0); }
+double ref_energy(void *h) { return static_cast<Sys *>(h)->collec->energy(); }
+double ref_potential_energy(void *h) { return static_cast<Sys *>(h)->collec->potential_energy(); }
+double ref_kinetic_energy(void *h) { return static_cast<Sys *>(h)->collec->kinetic_energy(); }
+double ref_temp(void *h, int minuscomv) { return static_cast<Sys *>(h)->collec->temp(minuscomv != 0); }
+double ref_pressure(void *h) { return static_cast<Sys *>(h)->collec->pressure(); }
+double ref_virial(void *h) { return static_cast<Sys *>(h)->collec->virial(); }
+double ref_degrees_of_freedom(void *h) { return static_cast<Sys *>(h)->collec->degrees_of_freedom(); }
+void ref_reset_com_velocity(void *h) { static_cast<Sys *>(h)->collec->reset_com_velocity(); }
+void ref_scale_velocities(void *h, double s) { static_cast<Sys *>(h)->collec->scale_velocities(s); }
+void ref_scale_velocities_to_temp(void *h, double T, int minuscomv) { static_cast<Sys *>(h)->collec->scale_velocities_to_temp(T, minuscomv != 0); }
+void ref_scale_velocities_to_energy(void *h, double E) { static_cast<Sys *>(h)->collec->scale_velocities_to_energy(E); }
+void ref_com_velocity(void *h, double *out) {
+    Vec v = static_cast<Sys *>(h)->atoms->com_velocity();
+    for (uint k = 0; k < NDIM; k++) out[k] = v[k];
+}
+void ref_momentum(void *h, double *out) {
+    Vec v = static_cast<Sys *>(h)->atoms->momentum();
+    for (uint k = 0; k < NDIM; k++) out[k] = v[k];
+}
+double ref_mass(void *h) { return static_cast<Sys *>(h)->atoms->mass(); }
+double ref_atoms_kinetic_energy(void *h, const double *v0) { return static_cast<Sys *>(h)->atoms->kinetic_energy(vec_from(v0)); }
+void ref_add_velocity(void *h, const double *dv) { static_cast<Sys *>(h)->atoms->add_velocity(vec_from(dv)); }
+
+// Noise injection for CollectionSol: subsequent Gaussian draws made by the
+// reference come from `draws` (in draw order) instead of the RNG.
+void ref_inject_noise(const double *draws, size_t n) {
+    parm_oracle_noise = draws;
+    parm_oracle_noise_len = n;
+    parm_oracle_noise_pos = 0;
+}
+size_t ref_noise_consumed() { return parm_oracle_noise_pos; }
+// Which component receives which draw in `Vec(gauss(), gauss(), gauss())`
+// (argument evaluation order is compiler-specific): out[c] = draw index.
+void ref_probe_draw_order(int *out) {
+    double probe[NDIM];
+    for (uint d = 0; d < NDIM; d++) probe[d] = (double)d;
+    ref_inject_noise(probe, NDIM);
+    Vec v = rand_vec();
+    ref_inject_noise(0, 0);
+    for (uint d = 0; d < NDIM; d++) out[d] = (int)v[d];
+}
+void ref_seed(uint32_t n) { seed(n); }
+
+}  // extern "C"

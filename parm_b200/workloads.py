@@ -1,0 +1,163 @@
+"""Synthetic inputs for the BASELINE.json configs.
+
+Pure numpy, host side. Every generator returns a dict:
+  ndim, L (ndim,), x (N,ndim), v (N,ndim), m (N,), kind, params (N,3), types (N,) uint32,
+  eps_table (T,T), skin, dt, integrator, and for CollectionSol damping/T.
+params columns follow the C ABI (include/parm_b200.h): (eps, sigma, exponent|sigcut).
+
+Velocities: N(0,1)*sqrt(T/m), centre-of-mass velocity removed, rescaled so that the
+reference's temp() formula (collection.cpp:135-142: 2*KE(v - v_com)/(ndof - NDIM))
+gives exactly T.
+"""
+import numpy as np
+
+KIND_LJREPULSE, KIND_REPULSION, KIND_LJATTRACTREPULSE, KIND_LJCUT = 0, 1, 2, 3
+VERLET, SOL = 0, 1
+
+
+def _velocities(rng, n, ndim, T, m):
+    v = rng.standard_normal((n, ndim)) * np.sqrt(T / m)[:, None]
+    v -= (v * m[:, None]).sum(0) / m.sum()
+    ke = 0.5 * (m[:, None] * v * v).sum()
+    t = 2 * ke / (ndim * n - ndim)
+    return v * np.sqrt(T / t)
+
+
+def _lattice(shape, spacing):
+    g = np.meshgrid(*[np.arange(s, dtype=np.float64) for s in shape], indexing="ij")
+    return np.stack([q.ravel() for q in g], axis=1) * spacing
+
+
+def lj_lattice(shape, rho=1.1939, T=1.44, jitter=0.05, skin=0.3, dt=0.004, sigcut=2.5, seed=3003,
+               kind=KIND_LJATTRACTREPULSE):
+    """Configs 3 and 5: one-species LJ (ParM sigma = potential minimum), simple-cubic start."""
+    rng = np.random.default_rng(seed)
+    shape = tuple(shape)
+    n = int(np.prod(shape))
+    a = rho ** (-1.0 / 3.0)
+    x = _lattice(shape, a) + rng.uniform(-jitter, jitter, (n, 3)) * a + 0.5 * a
+    L = np.array(shape, dtype=np.float64) * a
+    m = np.ones(n)
+    v = _velocities(rng, n, 3, T, m)
+    params = np.zeros((n, 3))
+    params[:, 0] = 1.0
+    params[:, 1] = 1.0
+    params[:, 2] = sigcut
+    return dict(ndim=3, L=L, x=x, v=v, m=m, kind=kind, params=params, types=np.zeros(n, np.uint32),
+                eps_table=np.ones((1, 1)), skin=skin, dt=dt, integrator=VERLET, name="lj3d_%dx%dx%d" % shape)
+
+
+def config1(seed=1001, kind=KIND_LJCUT):
+    """LJatoms.cpp-like: N=1000, phi=0.3, sigcut 2.5, skin 1.0, dt 1e-4 (LJatoms.cpp:11-17,26-27,38)."""
+    rng = np.random.default_rng(seed)
+    n = 1000
+    L = (n * np.pi / 6 / 0.3) ** (1.0 / 3.0)
+    a = L / 10
+    x = _lattice((10, 10, 10), a) + rng.uniform(-0.1, 0.1, (n, 3)) * a + 0.5 * a
+    m = np.ones(n)
+    v = _velocities(rng, n, 3, 1.0, m)
+    params = np.tile(np.array([1.0, 1.0, 2.5]), (n, 1))
+    return dict(ndim=3, L=np.full(3, L), x=x, v=v, m=m, kind=kind, params=params, types=np.zeros(n, np.uint32),
+                eps_table=np.ones((1, 1)), skin=1.0, dt=1e-4, integrator=VERLET, name="config1_lj1000")
+
+
+def config2(nx=250, ny=400, seed=2002):
+    """2-D bidisperse harmonic repulsion (RepulsionPair, exponent 2), phi=0.9 (tests.py:236-252)."""
+    rng = np.random.default_rng(seed)
+    n = nx * ny
+    sig = np.where(rng.permutation(n) < n // 2, 1.0, 1.4)
+    phi = 0.90
+    area = (np.pi * sig ** 2 / 4).sum() / phi
+    # rectangular cells so that the box is close to square
+    ax = np.sqrt(area * ny / nx) / ny * 1.0
+    Lx, Ly = None, None
+    ax = np.sqrt(area / (nx * ny))
+    Lx, Ly = nx * ax, ny * ax
+    x = _lattice((nx, ny), ax) + rng.uniform(-0.2, 0.2, (n, 2)) * ax + 0.5 * ax
+    m = np.ones(n)
+    v = _velocities(rng, n, 2, 1e-3, m)
+    params = np.stack([np.ones(n), sig, np.full(n, 2.0)], axis=1)
+    return dict(ndim=2, L=np.array([Lx, Ly]), x=x, v=v, m=m, kind=KIND_REPULSION, params=params,
+                types=np.zeros(n, np.uint32), eps_table=np.ones((1, 1)), skin=0.4, dt=0.01, integrator=VERLET,
+                name="config2_harmonic2d_%d" % n)
+
+
+def config3(side=100, **kw):
+    return lj_lattice((side, side, side), seed=3003, **kw)
+
+
+def config4(shape=(100, 200, 200), seed=4004):
+    """3-D binary WCA-like LJRepulse glass former, CollectionSol xi=1, T=1."""
+    rng = np.random.default_rng(seed)
+    shape = tuple(shape)
+    n = int(np.prod(shape))
+    sig = np.where(rng.permutation(n) < n // 2, 1.0, 1.4)
+    phi = 0.55
+    rho = phi / (np.pi / 6 * (sig ** 3).mean())
+    a = rho ** (-1.0 / 3.0)
+    x = _lattice(shape, a) + rng.uniform(-0.05, 0.05, (n, 3)) * a + 0.5 * a
+    L = np.array(shape, dtype=np.float64) * a
+    m = np.ones(n)
+    v = _velocities(rng, n, 3, 1.0, m)
+    params = np.stack([np.ones(n), sig, np.zeros(n)], axis=1)
+    return dict(ndim=3, L=L, x=x, v=v, m=m, kind=KIND_LJREPULSE, params=params, types=np.zeros(n, np.uint32),
+                eps_table=np.ones((1, 1)), skin=0.3, dt=0.002, integrator=SOL, damping=1.0, T=1.0,
+                name="config4_wca_%dx%dx%d" % shape)
+
+
+def config5(shape=(200, 200, 400), **kw):
+    return lj_lattice(shape, seed=5005, **kw)
+
+
+def hertzian12(seed=131):
+    """pyparm/tests.py:218-274 (RandomHertzianVerletTest): 3-D, N=12, Repulsion eps=1.2,
+    sigma 1.0/1.4 half/half, exponent 2, m=sigma^3, phi=0.3, skin 0.4, dt 0.01; positions from
+    numpy's legacy RandomState(seed) uniform in [0, L) exactly as tests.py:266-271 draws them."""
+    n = 12
+    sig = np.array([1.0] * (n // 2) + [1.4] * (n // 2))
+    m = sig ** 3
+    Vs = (np.pi / 6 * sig ** 3).sum()
+    L = (Vs / 0.3) ** (1.0 / 3.0)
+    rs = np.random.RandomState(seed)
+    x = rs.uniform(0, L, (n, 3))
+    v = rs.normal(size=(n, 3)) / np.sqrt(m)[:, None]
+    params = np.stack([np.full(n, 1.2), sig, np.full(n, 2.0)], axis=1)
+    return dict(ndim=3, L=np.full(3, L), x=x, v=v, m=m, kind=KIND_REPULSION, params=params,
+                types=np.zeros(n, np.uint32), eps_table=np.ones((1, 1)), skin=0.4, dt=0.01, integrator=VERLET,
+                name="hertzian12")
+
+
+def random_system(n, ndim, kind, seed, rho=0.9, ntypes=2, polydisperse=True, T=1.0, skin=0.3, frozen=0):
+    """Small ragged random systems for parity tests: jittered lattice with vacancies, shifted by
+    random whole box images, non-cubic box, per-atom eps/sigma/exponent/sigcut, several
+    types with negative / zero table entries (LJAttractRepulsePair's repulsive-only and off branches)."""
+    rng = np.random.default_rng(seed)
+    side = int(np.ceil(n ** (1.0 / ndim)))
+    a = rho ** (-1.0 / ndim)
+    shape = [side] * ndim
+    shape[-1] = side + 1 if ndim > 1 else side  # non-cubic box (box.hpp:102 allows per-axis sizes)
+    L = np.array(shape, dtype=np.float64) * a
+    sites = _lattice(shape, a)
+    pick = rng.permutation(len(sites))[:n]      # ragged: random vacancies
+    x = sites[pick] + rng.uniform(-0.12, 0.12, (n, ndim)) * a + 0.5 * a
+    # unwrapped on purpose: ParM never wraps Atom::x, only diff() is periodic (trackers.cpp:27)
+    x += rng.integers(-2, 3, (n, ndim)) * L
+    m = rng.uniform(0.5, 2.0, n)
+    if frozen:
+        m[rng.choice(n, frozen, replace=False)] = 0.0
+    mm = np.where(m > 0, m, 1.0)
+    v = rng.standard_normal((n, ndim)) * np.sqrt(T / mm)[:, None]
+    sig = rng.uniform(0.8, 1.4, n) if polydisperse else np.ones(n)
+    eps = rng.uniform(0.5, 1.5, n)
+    third = {KIND_LJREPULSE: np.zeros(n), KIND_REPULSION: rng.choice([2.0, 2.5, 1.5], n),
+             KIND_LJATTRACTREPULSE: rng.choice([2.0, 2.5], n), KIND_LJCUT: rng.choice([2.0, 2.5], n)}[kind]
+    params = np.stack([eps, sig, third], axis=1)
+    types = rng.integers(0, ntypes, n).astype(np.uint32)
+    tab = rng.uniform(0.5, 1.5, (ntypes, ntypes))
+    tab = (tab + tab.T) / 2
+    if ntypes > 1:
+        tab[0, 1] = tab[1, 0] = -0.7   # eps<=0 -> purely repulsive branch, interaction.hpp:1261-1266
+    if ntypes > 2:
+        tab[0, 2] = tab[2, 0] = 0.0    # eps==0 -> no force, interaction.hpp:1290
+    return dict(ndim=ndim, L=L, x=x, v=v, m=m, kind=kind, params=params, types=types, eps_table=tab,
+                skin=skin, dt=0.002, integrator=VERLET, name="random_%d_%dd_k%d" % (n, ndim, kind))
