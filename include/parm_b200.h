@@ -1,0 +1,164 @@
+/* parm_b200 -- C ABI of the B200-native ParM hot path.
+ *
+ * ParM has no FFI/plugin registry: its boundary is the public C++ class API
+ * (SURVEY.md 8b). The look-alike C++ headers in parm_b200/include/parm/ keep that
+ * API source-compatible and call ONLY the functions declared here; this file is
+ * therefore the exact set of entry points a binding (the C++ facade, a SWIG/ctypes
+ * module, ...) needs.  Every entry point cites the reference interface it replaces
+ * (paths relative to the reference's src/).
+ *
+ * Conventions
+ *   - every function returns 0 on success, non-zero on failure; the message is
+ *     available from parm_b200_last_error() (thread-local).  Error classes mirror
+ *     the reference's exception types (SURVEY 8b "Error convention").
+ *   - all pointers are HOST pointers; vectors are NDIM doubles; "n x NDIM" arrays
+ *     are addressed with an explicit byte stride so that both ParM's AoS
+ *     `struct Atom` (box.hpp:234-249) and plain numpy arrays can be passed.
+ *   - atoms are always addressed by their AtomVec index (AtomID::n(), box.hpp:288-298);
+ *     the library re-orders them internally (cell order) and hides that.
+ *   - a context is bound to one CUDA device and one host thread (the reference is
+ *     single-threaded and not re-entrant; same contract).
+ *   - there is NO CPU fallback: without a usable CUDA device every call fails
+ *     with PARM_ERR_CUDA.
+ */
+#ifndef PARM_B200_H
+#define PARM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PARM_OK 0
+#define PARM_ERR_INVALID 1   /* std::invalid_argument in the reference */
+#define PARM_ERR_RUNTIME 2   /* std::runtime_error */
+#define PARM_ERR_CUDA 3      /* CUDA / NCCL failure (-> std::runtime_error) */
+#define PARM_ERR_UNSUPPORTED 4 /* feature outside the hot-path scope */
+
+typedef struct parm_ctx parm_ctx;     /* OriginBox + AtomVec device state */
+typedef struct parm_nlist parm_nlist; /* NeighborList */
+typedef struct parm_inter parm_inter; /* NListed<A,P> */
+typedef struct parm_integ parm_integ; /* Collection{Verlet,Sol} */
+
+const char *parm_b200_last_error(void);
+/* number of kernels launched by this library since load (bench.py's gpu_launches) */
+uint64_t parm_b200_launch_count(void);
+const char *parm_b200_version(void);
+
+/* ---- context: AtomVec(N, m) box.hpp:441-479 + OriginBox(L) box.hpp:97-158 ---- */
+int parm_ctx_create(int ndim, uint32_t n_atoms, int device, parm_ctx **out);
+int parm_ctx_destroy(parm_ctx *ctx);
+/* OriginBox::boxsize (box.hpp:99-101); OriginBox::resize_to (box.cpp:21-25) re-calls this */
+int parm_set_box(parm_ctx *ctx, const double *L);
+int parm_get_box(parm_ctx *ctx, double *L);
+/* OriginBox::diff for a batch of point pairs, on the device (box.hpp:103, vec_mod :69-78) */
+int parm_box_diff(parm_ctx *ctx, uint32_t npts, const double *r1, const double *r2, double *out);
+
+#define PARM_X 1u
+#define PARM_V 2u
+#define PARM_A 4u
+#define PARM_F 8u
+#define PARM_M 16u
+#define PARM_ALL 31u
+/* Atom fields (box.hpp:234-249) host->device / device->host. Pointers address the
+ * field of atom 0; consecutive atoms are stride_vec (x,v,a,f) / stride_m (m) BYTES
+ * apart. For ParM's AoS pass &atoms[0].x, ... with both strides = sizeof(Atom). */
+int parm_upload_atoms(parm_ctx *ctx, unsigned mask, const double *x, const double *v, const double *a,
+                      const double *f, const double *m, size_t stride_vec, size_t stride_m);
+int parm_download_atoms(parm_ctx *ctx, unsigned mask, double *x, double *v, double *a, double *f, double *m,
+                        size_t stride_vec, size_t stride_m);
+/* page-lock a host buffer (the AtomVec mirror) so transfers run at PCIe speed */
+int parm_host_register(void *ptr, size_t bytes);
+int parm_host_unregister(void *ptr);
+int parm_sync(parm_ctx *ctx);
+
+/* ---- AtomGroup reductions box.cpp:239-260, 401-431; Collection collection.cpp:21-29,116-133 ---- */
+#define PARM_RED_MASS 0      /* out[1]      AtomGroup::mass,  skips m<=0||inf */
+#define PARM_RED_MOMENTUM 1  /* out[NDIM]   AtomGroup::momentum */
+#define PARM_RED_KE 2        /* out[1]      AtomGroup::kinetic_energy(v0), skips m==0||inf */
+#define PARM_RED_COM 3       /* out[NDIM]   AtomGroup::com (sum x m / mass) */
+#define PARM_RED_NDOF 4      /* out[1]      NDIM * #mobile atoms, Collection::degrees_of_freedom */
+#define PARM_RED_COMFORCE 5  /* out[NDIM]   AtomGroup::com_force */
+int parm_reduce(parm_ctx *ctx, int what, const double *v0, double *out);
+int parm_scale_velocities(parm_ctx *ctx, double scaleby); /* Collection::scale_velocities collection.cpp:21-29 */
+int parm_add_velocity(parm_ctx *ctx, const double *dv);   /* AtomGroup::add_velocity box.cpp:413-417 */
+int parm_reset_forces(parm_ctx *ctx);                     /* AtomGroup::reset_forces box.cpp:427-431 */
+
+/* ---- NeighborList trackers.hpp:157-214, trackers.cpp:10-85 ---- */
+int parm_nlist_create(parm_ctx *ctx, double skin, parm_nlist **out);
+int parm_nlist_destroy(parm_nlist *nl);
+/* NeighborList::add(AtomID, diameter) for every atom at once: diam[i] < 0 or NaN
+ * means atom i was never add()ed. Sets ignorechanged (trackers.hpp:194-201). */
+int parm_nlist_set_diameters(parm_nlist *nl, const double *diam);
+/* NeighborList::update_list(force) trackers.cpp:19-85: drift rule then pair build. */
+int parm_nlist_update(parm_nlist *nl, int force, int *rebuilt);
+int parm_nlist_which(parm_nlist *nl, uint32_t *updatenum);  /* which() */
+int parm_nlist_numpairs(parm_nlist *nl, uint64_t *npairs);  /* numpairs() */
+/* curpairs in the reference's order (trackers.cpp:59-68): first = later atom i,
+ * last = earlier atom j < i, sorted by (i, j).  cap = capacity of both arrays. */
+int parm_nlist_download_pairs(parm_nlist *nl, uint32_t *first, uint32_t *last, uint64_t cap);
+/* mean / max neighbours per atom in the device (full) list, for bench rooflines */
+int parm_nlist_stats(parm_nlist *nl, double *mean_full_neighbors, uint32_t *max_full_neighbors);
+
+/* ---- NListed<A,P> interaction.hpp:1876-1945, 2102-2291 ---- */
+#define PARM_PAIR_LJREPULSE 0        /* NListed<EpsSigAtom, LJRepulsePair>       :857-891, 119-152 */
+#define PARM_PAIR_REPULSION 1        /* NListed<EpsSigExpAtom, RepulsionPair>    :1454-1465, 1528-1550 */
+#define PARM_PAIR_LJATTRACTREPULSE 2 /* NListed<IEpsSigCutAtom, LJAttractRepulsePair> :989-1018, 1251-1299 */
+#define PARM_PAIR_LJCUT 3            /* NListed<EpsSigCutAtom, LennardJonesCutPair>   :897-905, 967-987, 238-281 */
+int parm_inter_create(parm_ctx *ctx, parm_nlist *nl, int pair_kind, parm_inter **out);
+int parm_inter_destroy(parm_inter *inter);
+/* per-atom A structs for all atoms at once. params is n x 3 doubles:
+ *   kind 0: (epsilon, sigma, -)   kind 1: (eps, sigma, exponent)
+ *   kind 2: (-, sigma, sigcut) + type[i] = IEpsSigCutAtom::indx and the symmetric
+ *           ntypes x ntypes table eps_table[t1*ntypes+t2] = epsilons[indx]
+ *   kind 3: (epsilon, sigma, sigcut)
+ * The library also forwards A::max_size() to the NeighborList (NListed::add,
+ * interaction.hpp:1906-1910) when set_diameters != 0. member: optional n bytes. */
+int parm_inter_set_params(parm_inter *inter, const double *params, const uint32_t *type, const double *eps_table,
+                          int ntypes, const uint8_t *member, int set_diameters);
+#define PARM_WANT_ENERGY 1u
+#define PARM_WANT_VIRIAL 2u
+#define PARM_WANT_STRESS 4u
+/* set_forces / set_forces_get_pressure / set_forces_get_stress (:2166-2175, 2232-2245,
+ * 2264-2277): ADDS pair forces to Atom::f. out (may be NULL if want==0) receives
+ * [E][virial][stress NDIM*NDIM row-major] for the requested quantities, in that order. */
+int parm_inter_set_forces(parm_inter *inter, unsigned want, double *out);
+int parm_inter_energy(parm_inter *inter, double *E);        /* energy(Box&)   :2154-2163 */
+int parm_inter_pressure(parm_inter *inter, double *p);      /* pressure(Box&) :2248-2261 (sum r.f) */
+int parm_inter_stress(parm_inter *inter, double *stress);   /* stress(Box&)   :2279-2291 */
+int parm_inter_contacts(parm_inter *inter, uint64_t *contacts, uint64_t *overlaps); /* :2126-2151 */
+
+/* ---- Collection / CollectionVerlet / CollectionSol collection.hpp:23-130,205-263,360-374 ---- */
+int parm_verlet_create(parm_ctx *ctx, double dt, parm_integ **out);
+int parm_sol_create(parm_ctx *ctx, double dt, double damping, double T, uint64_t seed, parm_integ **out);
+int parm_integ_destroy(parm_integ *integ);
+/* add_interaction / add_tracker (collection.hpp:113-120): append, then update_trackers() */
+int parm_integ_add_interaction(parm_integ *integ, parm_inter *inter);
+int parm_integ_add_tracker(parm_integ *integ, parm_nlist *nl);
+/* Collection constructor (collection.cpp:3-11): store the vectors as given, no update_trackers() */
+int parm_integ_register_interaction(parm_integ *integ, parm_inter *inter);
+int parm_integ_register_tracker(parm_integ *integ, parm_nlist *nl);
+int parm_integ_initialize(parm_integ *integ);                  /* Collection::initialize collection.cpp:13-19 */
+int parm_integ_set_dt(parm_integ *integ, double dt);           /* set_dt; Sol recomputes constants :230-263 */
+int parm_integ_set_temperature(parm_integ *integ, double damping, double T); /* CollectionSol::change_temperature */
+int parm_integ_set_forces(parm_integ *integ, int constraints_and_a); /* Collection::set_forces :159-179 */
+/* nsteps x timestep() (collection.cpp:442-469 / 265-322). Asynchronous: returns when the
+ * steps are enqueued and every rebuild decision has been taken; parm_sync / any download waits. */
+int parm_integ_timestep(parm_integ *integ, int nsteps);
+int parm_integ_update_trackers(parm_integ *integ);             /* collection.cpp:45-50 */
+int parm_integ_potential_energy(parm_integ *integ, double *E); /* collection.cpp:98-108 */
+int parm_integ_virial(parm_integ *integ, double *w);           /* collection.cpp:73-80 */
+/* CollectionSol exact-parity hook: use these standard normals instead of the device RNG.
+ * z: per step, per mobile atom in AtomVec order, NDIM normals (x1) then NDIM (x2)
+ * (BivariateGauss::gen_vecs vecrand.cpp:73-85). len in doubles. NULL/0 restores the RNG. */
+int parm_integ_inject_noise(parm_integ *integ, const double *z, size_t len);
+int parm_integ_get_sol_constants(parm_integ *integ, double *c /* c0,c1,c2,x11,x21,x22 */);
+/* steps / rebuilds executed so far, kernels launched by this integrator */
+int parm_integ_stats(parm_integ *integ, uint64_t *steps, uint64_t *rebuilds, uint64_t *launches);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,452 @@
+// NListed<A,P> on the device: the pair force / energy / virial / stress loop
+// (interaction.hpp:2102-2291) over the four pair functors in scope:
+//   LJRepulsePair        :875-891 + LJRepulsive :119-152
+//   RepulsionPair        :1528-1550
+//   LJAttractRepulsePair :1251-1299
+//   LennardJonesCutPair  :967-987 + LennardJonesCut :238-281
+// One thread per atom walks its FULL neighbour row (no Newton's-third-law scatter, hence no
+// atomics and a run-to-run deterministic sum); energy/virial/stress are reduced with warp
+// shuffles, then per block, then by one folding block (deterministic), and halved because
+// every pair is visited from both ends.
+#include <math.h>
+#include <string.h>
+
+#include <algorithm>
+#include <map>
+#include <tuple>
+
+#include "internal.cuh"
+
+#define F_BLOCK 128
+#define NPART 13 // E, virial, stress[9], contacts, overlaps
+
+enum { MODE_F = 0, MODE_FALL = 1, MODE_OBS = 2 };
+
+template <int KIND>
+__device__ __forceinline__ void pair_eval(const PairConst &P, double dsq, bool want_e, double &scal, double &e) {
+    scal = 0.0;
+    e = 0.0;
+    if (KIND == PARM_PAIR_REPULSION) {
+        // RepulsionPair::forces / energy, interaction.hpp:1537-1550
+        if (dsq > P.sig2) return;
+        double R = sqrt(dsq);
+        double t = 1.0 - R / P.sig;
+        double pm1, p0; // pow(t, n-1), pow(t, n)
+        if (P.expo == 2.0) {
+            pm1 = t;
+            p0 = t * t;
+        } else if (P.expo == 2.5) {
+            double sq = sqrt(t);
+            pm1 = t * sq;
+            p0 = t * t * sq;
+        } else {
+            pm1 = pow(t, P.expo - 1.0);
+            p0 = pm1 * t;
+        }
+        scal = P.eps * pm1 / P.sig / R;
+        if (want_e) e = P.eps * p0 / P.expo;
+    } else {
+        // rsq = dsq/(sig*sig); if (rsq > cut*cut) -> 0; rsix = sigma^6/r^6
+        // f = rij * (12 eps rsix (rsix - 1) / dsq)      (:135-151, :259-267, :1289-1298)
+        if (dsq * P.inv_sig2 > P.cut2) return;
+        double w = 1.0 / dsq;
+        double s2 = P.sig2 * w;
+        double ir6 = s2 * s2 * s2;
+        scal = 12.0 * P.eps * ir6 * (ir6 - 1.0) * w;
+        if (want_e) {
+            double mid = 1.0 - ir6;
+            if (KIND == PARM_PAIR_LJCUT)
+                e = P.eps * (mid * mid - 1.0) - P.cutE; // :253-258
+            else
+                e = P.eps * (mid * mid) - P.cutE;       // :126-133 (cutE = 0), :1271-1288
+        }
+    }
+}
+
+template <int KIND, bool ONE_SPECIES, int MODE>
+__global__ void __launch_bounds__(F_BLOCK)
+k_force(const double4 *__restrict__ pos, const uint32_t *__restrict__ nbr, const uint32_t *__restrict__ cnt, uint32_t kmax,
+        const uint8_t *__restrict__ spec, const PairConst *__restrict__ table, int nspecies, PairConst P1, double *f,
+        uint32_t n, uint32_t npad, BoxDev box, int accumulate, double *partials) {
+    extern __shared__ PairConst s_table[];
+    if (!ONE_SPECIES) {
+        for (int q = threadIdx.x; q < nspecies * nspecies; q += blockDim.x) s_table[q] = table[q];
+        __syncthreads();
+    }
+    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool want_obs = MODE != MODE_F;
+    double fx = 0, fy = 0, fz = 0;
+    double acc[NPART];
+    if (want_obs)
+#pragma unroll
+        for (int q = 0; q < NPART; q++) acc[q] = 0.0;
+    if (s < n) {
+        const uint32_t my = cnt[s];
+        const double4 pi = pos[s];
+        const uint32_t *col = nbr + ((size_t)(s >> 5) * kmax) * PARM_TILE + (s & 31u);
+        const PairConst *row = ONE_SPECIES ? nullptr : s_table + (int)spec[s] * nspecies;
+#pragma unroll 2
+        for (uint32_t k = 0; k < my; k++) {
+            const uint32_t j = __ldg(col + (size_t)k * PARM_TILE);
+            const double4 pj = ld_pos4(pos + j);
+            // OriginBox::diff(atom1->x, atom2->x), box.hpp:103
+            double dx = min_image_fast(pi.x - pj.x, box.L[0], box.invL[0]);
+            double dy = min_image_fast(pi.y - pj.y, box.L[1], box.invL[1]);
+            double dz = min_image_fast(pi.z - pj.z, box.L[2], box.invL[2]);
+            double dsq = dx * dx + (dy * dy + dz * dz);
+            double scal, e;
+            if (ONE_SPECIES) {
+                pair_eval<KIND>(P1, dsq, want_obs, scal, e);
+            } else {
+                const PairConst &P = row[__ldg(spec + j)];
+                pair_eval<KIND>(P, dsq, want_obs, scal, e);
+            }
+            double gx = dx * scal, gy = dy * scal, gz = dz * scal;
+            fx += gx;
+            fy += gy;
+            fz += gz;
+            if (want_obs) {
+                acc[0] += e;
+                acc[1] += dx * gx + (dy * gy + dz * gz); // r.dot(f), :2241
+                acc[2] += dx * gx; acc[3] += dx * gy; acc[4] += dx * gz; // stress += r * f^T, :2274
+                acc[5] += dy * gx; acc[6] += dy * gy; acc[7] += dy * gz;
+                acc[8] += dz * gx; acc[9] += dz * gy; acc[10] += dz * gz;
+                acc[11] += (e != 0.0) ? 1.0 : 0.0; // contacts :2126-2137
+                acc[12] += (e > 0.0) ? 1.0 : 0.0;  // overlaps :2140-2151
+            }
+        }
+        if (MODE != MODE_OBS) {
+            if (accumulate) {
+                f[s] += fx;
+                f[npad + s] += fy;
+                f[2 * (size_t)npad + s] += fz;
+            } else {
+                f[s] = fx;
+                f[npad + s] = fy;
+                f[2 * (size_t)npad + s] = fz;
+            }
+        }
+    }
+    if (want_obs) {
+        __shared__ double red[NPART][F_BLOCK / 32];
+        const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+        for (int q = 0; q < NPART; q++) {
+            double x = acc[q];
+#pragma unroll
+            for (int o = 16; o; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+            if (lane == 0) red[q][w] = x;
+        }
+        __syncthreads();
+        if (threadIdx.x < NPART) {
+            double x = 0;
+            for (int ww = 0; ww < F_BLOCK / 32; ww++) x += red[threadIdx.x][ww];
+            partials[(size_t)blockIdx.x * NPART + threadIdx.x] = x;
+        }
+    }
+}
+
+// folds the per-block partials; every pair was visited from both ends -> * 0.5
+__global__ void k_force_fold(const double *__restrict__ partials, uint32_t nblocks, double *out) {
+    __shared__ double red[256 / 32];
+    for (int q = 0; q < NPART; q++) {
+        double x = 0;
+        for (uint32_t b = threadIdx.x; b < nblocks; b += blockDim.x) x += partials[(size_t)b * NPART + q];
+#pragma unroll
+        for (int o = 16; o; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = x;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double t = 0;
+            for (int w = 0; w < 256 / 32; w++) t += red[w];
+            out[q] = t * 0.5;
+        }
+        __syncthreads();
+    }
+}
+
+template <int KIND, bool ONE>
+static cudaError_t launch_mode(int mode, dim3 grid, size_t smem, cudaStream_t st, const double4 *pos, const uint32_t *nbr,
+                               const uint32_t *cnt, uint32_t kmax, const uint8_t *spec, const PairConst *table, int nsp,
+                               PairConst P1, double *f, uint32_t n, uint32_t npad, BoxDev box, int acc, double *partials) {
+    if (mode == MODE_F) {
+        if (smem > 48 * 1024) cudaFuncSetAttribute(k_force<KIND, ONE, MODE_F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        k_force<KIND, ONE, MODE_F><<<grid, F_BLOCK, smem, st>>>(pos, nbr, cnt, kmax, spec, table, nsp, P1, f, n, npad, box, acc, partials);
+    } else if (mode == MODE_FALL) {
+        if (smem > 48 * 1024) cudaFuncSetAttribute(k_force<KIND, ONE, MODE_FALL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        k_force<KIND, ONE, MODE_FALL><<<grid, F_BLOCK, smem, st>>>(pos, nbr, cnt, kmax, spec, table, nsp, P1, f, n, npad, box, acc, partials);
+    } else {
+        if (smem > 48 * 1024) cudaFuncSetAttribute(k_force<KIND, ONE, MODE_OBS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        k_force<KIND, ONE, MODE_OBS><<<grid, F_BLOCK, smem, st>>>(pos, nbr, cnt, kmax, spec, table, nsp, P1, f, n, npad, box, acc, partials);
+    }
+    return cudaGetLastError();
+}
+
+template <int KIND>
+static cudaError_t launch_kind(bool one, int mode, dim3 grid, size_t smem, cudaStream_t st, const double4 *pos,
+                               const uint32_t *nbr, const uint32_t *cnt, uint32_t kmax, const uint8_t *spec,
+                               const PairConst *table, int nsp, PairConst P1, double *f, uint32_t n, uint32_t npad,
+                               BoxDev box, int acc, double *partials) {
+    if (one) return launch_mode<KIND, true>(mode, grid, 0, st, pos, nbr, cnt, kmax, spec, table, nsp, P1, f, n, npad, box, acc, partials);
+    return launch_mode<KIND, false>(mode, grid, smem, st, pos, nbr, cnt, kmax, spec, table, nsp, P1, f, n, npad, box, acc, partials);
+}
+
+// d_out: device pointer to NPART doubles (E, virial, stress[9], contacts, overlaps) or NULL
+static int launch_forces(parm_inter *it, int mode, bool accumulate, double *d_out) {
+    parm_ctx *c = it->ctx;
+    parm_nlist *nl = it->nl;
+    if (!it->have_params) { parm_set_error("NListed: no atoms were added (parm_inter_set_params not called)"); return PARM_ERR_INVALID; }
+    if (nl->updatenum == 0) {
+        // the reference would iterate an empty pair vector (update_pairs with which()==0)
+        if (mode != MODE_OBS && !accumulate) CK(cudaMemsetAsync(c->f, 0, 3 * (size_t)c->npad * 8, c->stream));
+        if (d_out) CK(cudaMemsetAsync(d_out, 0, NPART * 8, c->stream));
+        return 0;
+    }
+    const uint32_t nblocks = (c->n + F_BLOCK - 1) / F_BLOCK;
+    if (c->n == 0) {
+        if (d_out) CK(cudaMemsetAsync(d_out, 0, NPART * 8, c->stream));
+        return 0;
+    }
+    if (mode != MODE_F && (size_t)nblocks * NPART > it->partial_doubles) {
+        if (it->d_partials) cudaFree(it->d_partials);
+        it->d_partials = 0;
+        it->partial_doubles = (size_t)nblocks * NPART;
+        CK(cudaMalloc(&it->d_partials, it->partial_doubles * 8));
+    }
+    const bool one = it->nspecies == 1;
+    size_t smem = one ? 0 : (size_t)it->nspecies * it->nspecies * sizeof(PairConst);
+    PairConst P1 = it->h_table[0];
+    cudaError_t e;
+#define ARGS one, mode, dim3(nblocks), smem, c->stream, c->pos, nl->nbr, nl->cnt, nl->kmax, it->d_spec, it->d_table, \
+             it->nspecies, P1, c->f, c->n, c->npad, c->box, accumulate ? 1 : 0, it->d_partials
+    switch (it->kind) {
+        case PARM_PAIR_LJREPULSE: e = launch_kind<PARM_PAIR_LJREPULSE>(ARGS); break;
+        case PARM_PAIR_REPULSION: e = launch_kind<PARM_PAIR_REPULSION>(ARGS); break;
+        case PARM_PAIR_LJATTRACTREPULSE: e = launch_kind<PARM_PAIR_LJATTRACTREPULSE>(ARGS); break;
+        default: e = launch_kind<PARM_PAIR_LJCUT>(ARGS); break;
+    }
+#undef ARGS
+    parm_count_launch(c);
+    CK(e);
+    if (mode != MODE_F) {
+        if (!d_out) { parm_set_error("internal: observables requested without an output buffer"); return PARM_ERR_RUNTIME; }
+        k_force_fold<<<1, 256, 0, c->stream>>>(it->d_partials, nblocks, d_out);
+        CK_LAUNCH(c);
+    }
+    return 0;
+}
+
+int parm_inter_launch_forces(parm_inter *it, unsigned want, bool accumulate, double *d_out) {
+    return launch_forces(it, want ? MODE_FALL : MODE_F, accumulate, d_out);
+}
+
+// ---- host API ---------------------------------------------------------------------------
+extern "C" int parm_inter_create(parm_ctx *c, parm_nlist *nl, int kind, parm_inter **out) {
+    if (!c || !nl || !out) { parm_set_error("parm_inter_create: NULL argument"); return PARM_ERR_INVALID; }
+    *out = 0;
+    if (nl->ctx != c) { parm_set_error("parm_inter_create: NeighborList belongs to another AtomVec"); return PARM_ERR_INVALID; }
+    if (kind < 0 || kind > 3) {
+        parm_set_error("parm_inter_create: pair type %d is outside the hot-path scope (supported: LJRepulsePair, "
+                       "RepulsionPair, LJAttractRepulsePair, LennardJonesCutPair)", kind);
+        return PARM_ERR_UNSUPPORTED;
+    }
+    CK(cudaSetDevice(c->device));
+    parm_inter *it = new parm_inter();
+    it->ctx = c;
+    it->nl = nl;
+    it->kind = kind;
+    it->h_spec_id.assign(c->n, 0);
+    CK(cudaMalloc(&it->d_spec_id, c->npad));
+    CK(cudaMalloc(&it->d_spec, c->npad));
+    CK(cudaMemsetAsync(it->d_spec_id, 0, c->npad, c->stream));
+    CK(cudaMemsetAsync(it->d_spec, 0, c->npad, c->stream));
+    CK(cudaMalloc(&it->d_table, sizeof(PairConst) * PARM_MAX_SPECIES * PARM_MAX_SPECIES));
+    c->inters.push_back(it);
+    *out = it;
+    return 0;
+}
+
+extern "C" int parm_inter_destroy(parm_inter *it) {
+    if (!it) return 0;
+    parm_ctx *c = it->ctx;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    if (it->d_spec_id) cudaFree(it->d_spec_id);
+    if (it->d_spec) cudaFree(it->d_spec);
+    if (it->d_table) cudaFree(it->d_table);
+    if (it->d_partials) cudaFree(it->d_partials);
+    c->inters.erase(std::remove(c->inters.begin(), c->inters.end(), it), c->inters.end());
+    delete it;
+    return 0;
+}
+
+__global__ void k_gather_spec(const uint8_t *__restrict__ spec_id, const uint32_t *__restrict__ order, uint32_t n, uint8_t *spec) {
+    for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < n; s += gridDim.x * blockDim.x) spec[s] = spec_id[order[s]];
+}
+
+int parm_inter_regather(parm_inter *it) {
+    parm_ctx *c = it->ctx;
+    if (!c->n) return 0;
+    unsigned nb = (c->n + 255) / 256;
+    unsigned cap = (unsigned)c->num_sms * 8;
+    k_gather_spec<<<nb < cap ? nb : cap, 256, 0, c->stream>>>(it->d_spec_id, c->order, c->n, it->d_spec);
+    CK_LAUNCH(c);
+    return 0;
+}
+
+// Pair constructors of the reference, evaluated once per species pair on the host.
+static PairConst mix(int kind, const double *p1, uint32_t t1, const double *p2, uint32_t t2, const double *tab, int nt) {
+    PairConst P;
+    memset(&P, 0, sizeof(P));
+    if (kind == PARM_PAIR_LJREPULSE) { // :878-883
+        P.eps = sqrt(p1[0] * p2[0]);
+        P.sig = (p1[1] + p2[1]) / 2;
+        P.cut2 = 1.0;
+    } else if (kind == PARM_PAIR_REPULSION) { // :1531-1536
+        P.eps = sqrt(p1[0] * p2[0]);
+        P.sig = (p1[1] + p2[1]) / 2.0;
+        P.expo = (p1[2] + p2[2]) / 2.0;
+    } else if (kind == PARM_PAIR_LJATTRACTREPULSE) { // :1255-1270
+        double eps = tab[(size_t)t1 * nt + t2];
+        P.sig = (p1[1] + p2[1]) / 2.0;
+        double cut = std::max(p1[2], p2[2]);
+        if (eps <= 0) {
+            cut = 1;
+            P.cutE = 0;
+            eps = fabs(eps);
+        } else {
+            double mid = (1 - pow(cut, -6));
+            P.cutE = eps * (mid * mid);
+        }
+        P.eps = eps;
+        P.cut2 = cut * cut;
+    } else { // :970-974, :247-252
+        P.eps = sqrt(p1[0] * p2[0]);
+        P.sig = (p1[1] + p2[1]) / 2;
+        double cut = std::max(p1[2], p2[2]);
+        double rsix = pow(cut, 6);
+        double mid = (1 - 1 / rsix);
+        P.cutE = P.eps * (mid * mid - 1);
+        P.cut2 = cut * cut;
+    }
+    P.sig2 = P.sig * P.sig;
+    P.inv_sig2 = 1.0 / P.sig2;
+    return P;
+}
+
+extern "C" int parm_inter_set_params(parm_inter *it, const double *params, const uint32_t *type, const double *eps_table,
+                                     int ntypes, const uint8_t *member, int set_diameters) {
+    if (!it || !params) { parm_set_error("parm_inter_set_params: NULL argument"); return PARM_ERR_INVALID; }
+    parm_ctx *c = it->ctx;
+    CK(cudaSetDevice(c->device));
+    const int kind = it->kind;
+    if (kind == PARM_PAIR_LJATTRACTREPULSE) {
+        if (!eps_table || ntypes < 1) { parm_set_error("LJAttractRepulsePair needs the epsilon table (IEpsSigCutAtom::epsilons)"); return PARM_ERR_INVALID; }
+        for (int a = 0; a < ntypes; a++)
+            for (int b = 0; b < ntypes; b++)
+                if (eps_table[a * ntypes + b] != eps_table[b * ntypes + a]) { // assert at interaction.hpp:1013-1014
+                    parm_set_error("LJAttractRepulsePair: epsilon table must be symmetric");
+                    return PARM_ERR_INVALID;
+                }
+    }
+    typedef std::tuple<double, double, double, uint32_t> Key;
+    std::map<Key, int> ids;
+    std::vector<Key> keys;
+    std::vector<double> diam(c->n, -1.0);
+    for (uint32_t i = 0; i < c->n; i++) {
+        if (member && !member[i]) { it->h_spec_id[i] = 0; continue; }
+        const double *p = params + 3 * (size_t)i;
+        uint32_t t = (kind == PARM_PAIR_LJATTRACTREPULSE && type) ? type[i] : 0;
+        if (kind == PARM_PAIR_LJATTRACTREPULSE && (int)t >= ntypes) { parm_set_error("atom %u: type %u >= ntypes %d", i, t, ntypes); return PARM_ERR_INVALID; }
+        Key k(kind == PARM_PAIR_LJATTRACTREPULSE ? 0.0 : p[0], p[1], kind == PARM_PAIR_LJREPULSE ? 0.0 : p[2], t);
+        auto f = ids.find(k);
+        int id;
+        if (f == ids.end()) {
+            id = (int)keys.size();
+            if (id >= PARM_MAX_SPECIES) {
+                parm_set_error("NListed: more than %d distinct per-atom parameter tuples (continuous polydispersity) "
+                               "is outside the current scope; see DESIGN.md", PARM_MAX_SPECIES);
+                return PARM_ERR_UNSUPPORTED;
+            }
+            ids[k] = id;
+            keys.push_back(k);
+        } else
+            id = f->second;
+        it->h_spec_id[i] = (uint8_t)id;
+        // A::max_size(): sigma (:864, :1464) or sigma*sigcut (:905, :1017)
+        diam[i] = (kind == PARM_PAIR_LJREPULSE || kind == PARM_PAIR_REPULSION) ? p[1] : p[1] * p[2];
+    }
+    int S = (int)keys.size();
+    if (S == 0) { S = 1; keys.push_back(Key(1.0, 1.0, 1.0, 0)); }
+    it->nspecies = S;
+    it->h_table.assign((size_t)S * S, PairConst());
+    for (int a = 0; a < S; a++)
+        for (int b = 0; b < S; b++) {
+            double p1[3] = {std::get<0>(keys[a]), std::get<1>(keys[a]), std::get<2>(keys[a])};
+            double p2[3] = {std::get<0>(keys[b]), std::get<1>(keys[b]), std::get<2>(keys[b])};
+            it->h_table[(size_t)a * S + b] = mix(kind, p1, std::get<3>(keys[a]), p2, std::get<3>(keys[b]), eps_table, ntypes);
+        }
+    CK(cudaMemcpyAsync(it->d_table, it->h_table.data(), sizeof(PairConst) * S * S, cudaMemcpyHostToDevice, c->stream));
+    if (c->n) CK(cudaMemcpyAsync(it->d_spec_id, it->h_spec_id.data(), c->n, cudaMemcpyHostToDevice, c->stream));
+    PTRY(parm_inter_regather(it));
+    CK(cudaStreamSynchronize(c->stream));
+    it->have_params = true;
+    if (set_diameters) PTRY(parm_nlist_set_diameters(it->nl, diam.data()));
+    return 0;
+}
+
+static int fetch(parm_inter *it, int mode, bool accumulate, double *host13) {
+    parm_ctx *c = it->ctx;
+    CK(cudaSetDevice(c->device));
+    PTRY(parm_ctx_ensure_red(c, 64));
+    PTRY(launch_forces(it, mode, accumulate, c->d_red));
+    CK(cudaMemcpyAsync(c->h_red, c->d_red, NPART * 8, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    memcpy(host13, c->h_red, NPART * 8);
+    return 0;
+}
+
+extern "C" int parm_inter_set_forces(parm_inter *it, unsigned want, double *out) {
+    if (!it) { parm_set_error("parm_inter_set_forces: NULL interaction"); return PARM_ERR_INVALID; }
+    parm_ctx *c = it->ctx;
+    CK(cudaSetDevice(c->device));
+    if (!want) return launch_forces(it, MODE_F, true, nullptr);
+    if (!out) { parm_set_error("parm_inter_set_forces: out is NULL"); return PARM_ERR_INVALID; }
+    double r[NPART];
+    PTRY(fetch(it, MODE_FALL, true, r));
+    int k = 0;
+    const int D = c->D;
+    if (want & PARM_WANT_ENERGY) out[k++] = r[0];
+    if (want & PARM_WANT_VIRIAL) out[k++] = r[1];
+    if (want & PARM_WANT_STRESS)
+        for (int a = 0; a < D; a++)
+            for (int b = 0; b < D; b++) out[k++] = r[2 + a * 3 + b];
+    return 0;
+}
+extern "C" int parm_inter_energy(parm_inter *it, double *E) {
+    double r[NPART];
+    PTRY(fetch(it, MODE_OBS, false, r));
+    *E = r[0];
+    return 0;
+}
+extern "C" int parm_inter_pressure(parm_inter *it, double *p) {
+    double r[NPART];
+    PTRY(fetch(it, MODE_OBS, false, r));
+    *p = r[1];
+    return 0;
+}
+extern "C" int parm_inter_stress(parm_inter *it, double *st) {
+    double r[NPART];
+    PTRY(fetch(it, MODE_OBS, false, r));
+    const int D = it->ctx->D;
+    for (int a = 0; a < D; a++)
+        for (int b = 0; b < D; b++) st[a * D + b] = r[2 + a * 3 + b];
+    return 0;
+}
+extern "C" int parm_inter_contacts(parm_inter *it, uint64_t *contacts, uint64_t *overlaps) {
+    double r[NPART];
+    PTRY(fetch(it, MODE_OBS, false, r));
+    if (contacts) *contacts = (uint64_t)llround(r[11]);
+    if (overlaps) *overlaps = (uint64_t)llround(r[12]);
+    return 0;
+}

@@ -1,0 +1,494 @@
+// Collection / CollectionVerlet / CollectionSol on the device.
+//   CollectionVerlet::timestep   collection.cpp:442-469
+//   CollectionSol::timestep      collection.cpp:265-322, set_constants :230-263,
+//                                BivariateGauss::{set,gen_vecs} vecrand.cpp:48-85
+//   Collection::{initialize,update_trackers,set_forces,potential_energy,virial}
+//                                collection.cpp:13-19, 45-50, 159-179, 98-108, 73-80
+// Each step is: K1 (first half-kick + drift of positions) -> force kernel(s) -> K3 (a = f/m,
+// second half-kick, fused with the NeighborList skin-drift reduction). The streaming kernels
+// reproduce the reference's expression order without FMA contraction so that, given the same
+// forces, positions and velocities are bit-identical to the CPU path.
+#include <math.h>
+#include <string.h>
+
+#include <algorithm>
+
+#include "drift.cuh"
+#include "internal.cuh"
+
+#define I_BLOCK 256
+
+static inline unsigned grid_for(const parm_ctx *ctx, uint32_t n, unsigned block, unsigned per_sm = 8) {
+    unsigned need = (n + block - 1) / block;
+    unsigned cap = (unsigned)ctx->num_sms * per_sm;
+    if (need < 1) need = 1;
+    return need < cap ? need : cap;
+}
+
+// ---- K1: x += v*dt + a*(dt*dt/2); v += a*(dt/2)   (collection.cpp:443-451) -------------
+template <int D>
+__global__ void __launch_bounds__(I_BLOCK)
+k_verlet1(double4 *__restrict__ pos, double *__restrict__ v, const double *__restrict__ a, uint32_t n, uint32_t npad,
+          double dt, double hdt2, double hdt) {
+    for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < n; s += gridDim.x * blockDim.x) {
+        double4 p = pos[s];
+        if (frozen_le(p.w)) { // m <= 0 || isinf(m): v = 0, position untouched
+#pragma unroll
+            for (int d = 0; d < D; d++) v[(size_t)d * npad + s] = 0.0;
+            continue;
+        }
+        double x[3] = {p.x, p.y, p.z};
+#pragma unroll
+        for (int d = 0; d < D; d++) {
+            const size_t q = (size_t)d * npad + s;
+            const double vd = v[q], ad = a[q];
+            x[d] = __dadd_rn(x[d], __dadd_rn(__dmul_rn(vd, dt), __dmul_rn(ad, hdt2)));
+            v[q] = __dadd_rn(vd, __dmul_rn(ad, hdt));
+        }
+        p.x = x[0];
+        p.y = x[1];
+        if (D == 3) p.z = x[2];
+        pos[s] = p;
+    }
+}
+
+// ---- K3: a = f/m; v += a*(dt/2)  (collection.cpp:457-465) fused with the drift check ------
+template <int D, bool DRIFT>
+__global__ void __launch_bounds__(I_BLOCK)
+k_verlet2(const double4 *__restrict__ pos, double *__restrict__ v, double *__restrict__ a, const double *__restrict__ f,
+          uint32_t n, uint32_t npad, double hdt, const double *__restrict__ xlast, const double *__restrict__ diam,
+          double skin, double *d_top2, unsigned int *counter, NlistFlags *dflags, NlistFlags *hflags) {
+    double b1 = 0.0, b2 = 0.0;
+    for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < n; s += gridDim.x * blockDim.x) {
+        const double4 p = pos[s];
+        if (frozen_le(p.w)) {
+#pragma unroll
+            for (int d = 0; d < D; d++) a[(size_t)d * npad + s] = 0.0;
+        } else {
+#pragma unroll
+            for (int d = 0; d < D; d++) {
+                const size_t q = (size_t)d * npad + s;
+                const double ad = __ddiv_rn(f[q], p.w);
+                a[q] = ad;
+                v[q] = __dadd_rn(v[q], __dmul_rn(ad, hdt));
+            }
+        }
+        if (DRIFT) {
+            if (diam[s] >= 0.0) top2_push(b1, b2, drift_dist(p, xlast[s], xlast[npad + s], xlast[2 * (size_t)npad + s]));
+        }
+    }
+    if (DRIFT) drift_finish(b1, b2, skin, d_top2, counter, dflags, hflags);
+}
+
+// ---- Philox4x32-10 counter RNG + Box-Muller (production noise of CollectionSol) ---------
+__device__ __forceinline__ void philox4x32(uint32_t c[4], uint32_t k0, uint32_t k1) {
+#pragma unroll
+    for (int r = 0; r < 10; r++) {
+        uint32_t hi0 = __umulhi(0xD2511F53u, c[0]), lo0 = 0xD2511F53u * c[0];
+        uint32_t hi1 = __umulhi(0xCD9E8D57u, c[2]), lo1 = 0xCD9E8D57u * c[2];
+        uint32_t n0 = hi1 ^ c[1] ^ k0, n2 = hi0 ^ c[3] ^ k1;
+        c[0] = n0;
+        c[1] = lo1;
+        c[2] = n2;
+        c[3] = lo0;
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+}
+__device__ __forceinline__ void normal_pair(uint32_t id, uint64_t step, uint32_t stream, uint64_t seed, double &z0, double &z1) {
+    uint32_t c[4] = {id, (uint32_t)step, (uint32_t)(step >> 32), stream};
+    philox4x32(c, (uint32_t)seed, (uint32_t)(seed >> 32));
+    // 53-bit uniforms: u1 in (0,1], u2 in [0,1)
+    double u1 = ((double)(((uint64_t)c[0] << 21) ^ (c[1] >> 11)) + 1.0) * (1.0 / 9007199254740992.0);
+    double u2 = (double)(((uint64_t)c[2] << 21) ^ (c[3] >> 11)) * (1.0 / 9007199254740992.0);
+    double r = sqrt(-2.0 * log(u1));
+    double sn, cs;
+    sincospi(2.0 * u2, &sn, &cs);
+    z0 = r * cs;
+    z1 = r * sn;
+}
+
+struct SolConst {
+    double dt, c0, c1dt, c2dtdt, dtc1mc2, dtc2, x11, x21, x22, desT, damping;
+};
+
+// ---- Sol K1 (collection.cpp:276-298) ----------------------------------------------------------
+template <int D>
+__global__ void __launch_bounds__(I_BLOCK)
+k_sol1(double4 *__restrict__ pos, double *__restrict__ v, const double *__restrict__ a, const uint32_t *__restrict__ order,
+       uint32_t n, uint32_t npad, SolConst K, const double *__restrict__ noise, const uint32_t *__restrict__ mobile_rank,
+       uint64_t step, uint64_t seed) {
+    for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < n; s += gridDim.x * blockDim.x) {
+        double4 p = pos[s];
+        if (frozen_le(p.w)) {
+#pragma unroll
+            for (int d = 0; d < D; d++) v[(size_t)d * npad + s] = 0.0;
+            continue;
+        }
+        const double v0 = __dsqrt_rn(__ddiv_rn(K.desT, p.w));
+        const double r0 = __dmul_rn(K.dt, v0);
+        double x1[3] = {0, 0, 0}, x2[3] = {0, 0, 0};
+        if (K.damping > 0) {
+            const uint32_t id = order[s];
+            if (noise) {
+                const double *z = noise + (size_t)mobile_rank[id] * 2 * D;
+#pragma unroll
+                for (int d = 0; d < D; d++) {
+                    x1[d] = z[d];
+                    x2[d] = z[D + d];
+                }
+            } else {
+                double za, zb;
+                normal_pair(id, step, 0, seed, x1[0], x1[1]);
+                normal_pair(id, step, 1, seed, x2[0], x2[1]);
+                normal_pair(id, step, 2, seed, za, zb);
+                if (D == 3) {
+                    x1[2] = za;
+                    x2[2] = zb;
+                }
+            }
+        }
+        double x[3] = {p.x, p.y, p.z};
+#pragma unroll
+        for (int d = 0; d < D; d++) {
+            const size_t q = (size_t)d * npad + s;
+            const double vd = v[q], ad = a[q];
+            const double drG = __dmul_rn(x1[d], K.x11);                                           // x1 * x11
+            const double dvG = __dadd_rn(__dmul_rn(x1[d], K.x21), __dmul_rn(x2[d], K.x22));       // x1*x21 + x2*x22
+            x[d] = __dadd_rn(x[d], __dadd_rn(__dadd_rn(__dmul_rn(vd, K.c1dt), __dmul_rn(ad, K.c2dtdt)), __dmul_rn(drG, r0)));
+            v[q] = __dadd_rn(__dadd_rn(__dmul_rn(vd, K.c0), __dmul_rn(ad, K.dtc1mc2)), __dmul_rn(dvG, v0));
+        }
+        p.x = x[0];
+        p.y = x[1];
+        if (D == 3) p.z = x[2];
+        pos[s] = p;
+    }
+}
+
+// ---- Sol K3 (collection.cpp:303-318): note the m == 0 (not m <= 0) tests ---------------------
+template <int D, bool DRIFT>
+__global__ void __launch_bounds__(I_BLOCK)
+k_sol2(const double4 *__restrict__ pos, double *__restrict__ v, double *__restrict__ a, const double *__restrict__ f,
+       uint32_t n, uint32_t npad, double dtc2, const double *__restrict__ xlast, const double *__restrict__ diam,
+       double skin, double *d_top2, unsigned int *counter, NlistFlags *dflags, NlistFlags *hflags) {
+    double b1 = 0.0, b2 = 0.0;
+    for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < n; s += gridDim.x * blockDim.x) {
+        const double4 p = pos[s];
+        if (frozen_eq(p.w)) {
+#pragma unroll
+            for (int d = 0; d < D; d++) {
+                a[(size_t)d * npad + s] = 0.0;
+                v[(size_t)d * npad + s] = 0.0;
+            }
+        } else {
+#pragma unroll
+            for (int d = 0; d < D; d++) {
+                const size_t q = (size_t)d * npad + s;
+                const double ad = __ddiv_rn(f[q], p.w);
+                a[q] = ad;
+                v[q] = __dadd_rn(v[q], __dmul_rn(ad, dtc2));
+            }
+        }
+        if (DRIFT) {
+            if (diam[s] >= 0.0) top2_push(b1, b2, drift_dist(p, xlast[s], xlast[npad + s], xlast[2 * (size_t)npad + s]));
+        }
+    }
+    if (DRIFT) drift_finish(b1, b2, skin, d_top2, counter, dflags, hflags);
+}
+
+// ---- a = f/m of Collection::set_forces(true) (collection.cpp:171-178) -----------------------
+template <int D>
+__global__ void k_accel(const double4 *__restrict__ pos, double *__restrict__ a, const double *__restrict__ f, uint32_t n, uint32_t npad) {
+    for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < n; s += gridDim.x * blockDim.x) {
+        const double m = pos[s].w;
+        const bool fr = frozen_le(m);
+#pragma unroll
+        for (int d = 0; d < D; d++) {
+            const size_t q = (size_t)d * npad + s;
+            a[q] = fr ? 0.0 : __ddiv_rn(f[q], m);
+        }
+    }
+}
+
+// ---- host ---------------------------------------------------------------------------------------
+static int sol_set_constants(parm_integ *g) { // collection.cpp:230-263 + vecrand.cpp:48-63
+    if (g->force_mag <= 0.0) {
+        g->c0 = 1; g->c1 = 1; g->c2 = .5; g->sigmar = 0; g->sigmav = 0; g->corr = 1;
+    } else {
+        double dampdt = g->force_mag * g->dt;
+        g->c0 = exp(-dampdt);
+        g->c1 = (-expm1(-dampdt)) / dampdt;
+        g->c2 = (1 - g->c1) / dampdt;
+        if (dampdt > 1e-4)
+            g->sigmar = sqrt((1 / dampdt) * (2 - (-4 * expm1(-dampdt) + expm1(-2 * dampdt)) / dampdt));
+        else
+            g->sigmar = sqrt(2 * dampdt / 3 - dampdt * dampdt / 2 + 7 * dampdt * dampdt * dampdt / 30);
+        g->sigmav = sqrt(-expm1(-2 * dampdt));
+        double exdpdt = (-expm1(-dampdt));
+        g->corr = exdpdt * exdpdt / dampdt / g->sigmar / g->sigmav;
+    }
+    if (!(g->sigmar >= 0)) { parm_set_error("BivariateGauss::set: s1 >= 0"); return PARM_ERR_INVALID; }
+    if (!(g->sigmav >= 0)) { parm_set_error("BivariateGauss::set: s2 >= 0"); return PARM_ERR_INVALID; }
+    if (!(g->corr >= 0)) { parm_set_error("BivariateGauss::set: corr >= 0"); return PARM_ERR_INVALID; }
+    if (!(g->corr <= 1)) { parm_set_error("BivariateGauss::set: corr <= 1"); return PARM_ERR_INVALID; }
+    g->x11 = g->sigmar;
+    g->x21 = g->sigmav * g->corr;
+    g->x22 = g->sigmav * sqrt(1 - g->corr * g->corr);
+    return 0;
+}
+
+extern "C" int parm_verlet_create(parm_ctx *c, double dt, parm_integ **out) {
+    if (!c || !out) { parm_set_error("parm_verlet_create: NULL argument"); return PARM_ERR_INVALID; }
+    parm_integ *g = new parm_integ();
+    g->ctx = c;
+    g->type = 0;
+    g->dt = dt;
+    *out = g;
+    return 0;
+}
+
+extern "C" int parm_sol_create(parm_ctx *c, double dt, double damping, double T, uint64_t seed, parm_integ **out) {
+    if (!c || !out) { parm_set_error("parm_sol_create: NULL argument"); return PARM_ERR_INVALID; }
+    *out = 0;
+    if (dt <= 0) { parm_set_error("Collection::CollectionSol: dt >= 0"); return PARM_ERR_INVALID; } // collection.cpp:222-224
+    parm_integ *g = new parm_integ();
+    g->ctx = c;
+    g->type = 1;
+    g->dt = dt;
+    g->damping = damping;
+    g->force_mag = damping;
+    g->desT = T;
+    g->seed = seed;
+    int r = sol_set_constants(g);
+    if (r) { delete g; return r; }
+    *out = g;
+    return 0;
+}
+
+extern "C" int parm_integ_destroy(parm_integ *g) {
+    if (!g) return 0;
+    cudaSetDevice(g->ctx->device);
+    cudaStreamSynchronize(g->ctx->stream);
+    if (g->d_noise) cudaFree(g->d_noise);
+    if (g->d_mobile_rank) cudaFree(g->d_mobile_rank);
+    delete g;
+    return 0;
+}
+
+extern "C" int parm_integ_update_trackers(parm_integ *g) {
+    for (parm_nlist *nl : g->trackers) {
+        int rebuilt = 0;
+        PTRY(parm_nlist_update(nl, 0, &rebuilt));
+        if (rebuilt) g->rebuilds++;
+    }
+    return 0;
+}
+
+extern "C" int parm_integ_register_interaction(parm_integ *g, parm_inter *it) {
+    if (!g || !it) { parm_set_error("parm_integ_register_interaction: NULL argument"); return PARM_ERR_INVALID; }
+    if (it->ctx != g->ctx) { parm_set_error("interaction belongs to another AtomVec"); return PARM_ERR_INVALID; }
+    g->inters.push_back(it);
+    return 0;
+}
+extern "C" int parm_integ_register_tracker(parm_integ *g, parm_nlist *nl) {
+    if (!g || !nl) { parm_set_error("parm_integ_register_tracker: NULL argument"); return PARM_ERR_INVALID; }
+    if (nl->ctx != g->ctx) { parm_set_error("tracker belongs to another AtomVec"); return PARM_ERR_INVALID; }
+    g->trackers.push_back(nl);
+    return 0;
+}
+extern "C" int parm_integ_add_interaction(parm_integ *g, parm_inter *it) {
+    PTRY(parm_integ_register_interaction(g, it));
+    return parm_integ_update_trackers(g); // collection.hpp:113-116
+}
+extern "C" int parm_integ_add_tracker(parm_integ *g, parm_nlist *nl) {
+    PTRY(parm_integ_register_tracker(g, nl));
+    return parm_integ_update_trackers(g); // collection.hpp:117-120
+}
+
+static int launch_all_forces(parm_integ *g) {
+    parm_ctx *c = g->ctx;
+    // atoms->reset_forces(); for each interaction: set_forces(box)   (collection.cpp:160-166)
+    if (g->inters.empty()) return parm_reset_forces(c);
+    bool first = true;
+    for (parm_inter *it : g->inters) {
+        PTRY(parm_inter_launch_forces(it, 0, !first, nullptr)); // first interaction overwrites f == reset + add
+        first = false;
+    }
+    return 0;
+}
+
+extern "C" int parm_integ_set_forces(parm_integ *g, int constraints_and_a) {
+    parm_ctx *c = g->ctx;
+    CK(cudaSetDevice(c->device));
+    PTRY(launch_all_forces(g));
+    if (!constraints_and_a || c->n == 0) return 0;
+    if (c->D == 3) k_accel<3><<<grid_for(c, c->n, 256), 256, 0, c->stream>>>(c->pos, c->a, c->f, c->n, c->npad);
+    else k_accel<2><<<grid_for(c, c->n, 256), 256, 0, c->stream>>>(c->pos, c->a, c->f, c->n, c->npad);
+    CK_LAUNCH(c);
+    return 0;
+}
+
+extern "C" int parm_integ_initialize(parm_integ *g) { // collection.cpp:13-19
+    PTRY(parm_integ_update_trackers(g));
+    PTRY(parm_integ_set_forces(g, 1));
+    return parm_integ_update_trackers(g);
+}
+
+extern "C" int parm_integ_set_dt(parm_integ *g, double dt) {
+    g->dt = dt;
+    if (g->type == 1) return sol_set_constants(g);
+    return 0;
+}
+extern "C" int parm_integ_set_temperature(parm_integ *g, double damping, double T) {
+    if (g->type != 1) { parm_set_error("change_temperature: not a CollectionSol"); return PARM_ERR_INVALID; }
+    g->damping = damping;
+    g->force_mag = damping;
+    g->desT = T;
+    return sol_set_constants(g);
+}
+extern "C" int parm_integ_get_sol_constants(parm_integ *g, double *cst) {
+    cst[0] = g->c0; cst[1] = g->c1; cst[2] = g->c2; cst[3] = g->x11; cst[4] = g->x21; cst[5] = g->x22;
+    return 0;
+}
+
+extern "C" int parm_integ_inject_noise(parm_integ *g, const double *z, size_t len) {
+    parm_ctx *c = g->ctx;
+    CK(cudaSetDevice(c->device));
+    CK(cudaStreamSynchronize(c->stream));
+    if (g->d_noise) cudaFree(g->d_noise);
+    g->d_noise = 0;
+    g->noise_len = g->noise_pos = 0;
+    if (!z || !len) return 0;
+    // rank of every mobile atom in AtomVec order (the reference draws in atom order, skipping frozen ones)
+    std::vector<double> m(c->n);
+    PTRY(parm_download_atoms(c, PARM_M, 0, 0, 0, 0, m.data(), (size_t)c->D * 8, 8));
+    std::vector<uint32_t> rank(c->npad, 0);
+    uint32_t r = 0;
+    for (uint32_t i = 0; i < c->n; i++) {
+        rank[i] = r;
+        if (!(m[i] <= 0 || isinf(m[i]))) r++;
+    }
+    g->n_mobile = r;
+    if (!g->d_mobile_rank) CK(cudaMalloc(&g->d_mobile_rank, (size_t)c->npad * 4));
+    CK(cudaMemcpy(g->d_mobile_rank, rank.data(), (size_t)c->npad * 4, cudaMemcpyHostToDevice));
+    CK(cudaMalloc(&g->d_noise, len * 8));
+    CK(cudaMemcpy(g->d_noise, z, len * 8, cudaMemcpyHostToDevice));
+    g->noise_len = len;
+    return 0;
+}
+
+static int one_step(parm_integ *g) {
+    parm_ctx *c = g->ctx;
+    const uint32_t n = c->n;
+    parm_nlist *nl = g->trackers.empty() ? nullptr : g->trackers[0];
+    const unsigned grid = grid_for(c, n, I_BLOCK, 8);
+    const unsigned grid2 = std::min(grid, 2048u); // drift_finish: d_top2 holds 4096 block entries
+    const double dt = g->dt;
+    if (g->type == 0) {
+        const double hdt2 = dt * dt / 2, hdt = dt / 2;
+        if (c->D == 3) k_verlet1<3><<<grid, I_BLOCK, 0, c->stream>>>(c->pos, c->v, c->a, n, c->npad, dt, hdt2, hdt);
+        else k_verlet1<2><<<grid, I_BLOCK, 0, c->stream>>>(c->pos, c->v, c->a, n, c->npad, dt, hdt2, hdt);
+        CK_LAUNCH(c);
+        PTRY(launch_all_forces(g));
+#define V2ARGS c->pos, c->v, c->a, c->f, n, c->npad, hdt, nl ? nl->xlast : nullptr, nl ? nl->d_diam : nullptr, \
+               nl ? nl->skin : 0.0, nl ? nl->d_top2 : nullptr, nl ? nl->d_counter : nullptr, nl ? nl->d_flags : nullptr, \
+               nl ? nl->h_flags : nullptr
+        if (c->D == 3) {
+            if (nl) k_verlet2<3, true><<<grid2, I_BLOCK, 0, c->stream>>>(V2ARGS);
+            else k_verlet2<3, false><<<grid2, I_BLOCK, 0, c->stream>>>(V2ARGS);
+        } else {
+            if (nl) k_verlet2<2, true><<<grid2, I_BLOCK, 0, c->stream>>>(V2ARGS);
+            else k_verlet2<2, false><<<grid2, I_BLOCK, 0, c->stream>>>(V2ARGS);
+        }
+#undef V2ARGS
+        CK_LAUNCH(c);
+    } else {
+        SolConst K;
+        K.dt = dt;
+        K.c0 = g->c0;
+        K.c1dt = g->c1 * dt;
+        K.c2dtdt = g->c2 * dt * dt;
+        K.dtc1mc2 = dt * (g->c1 - g->c2);
+        K.dtc2 = dt * g->c2;
+        K.x11 = g->x11;
+        K.x21 = g->x21;
+        K.x22 = g->x22;
+        K.desT = g->desT;
+        K.damping = g->damping;
+        const double *noise = nullptr;
+        if (g->d_noise) {
+            size_t per = (size_t)g->n_mobile * 2 * c->D;
+            if (g->noise_pos + per > g->noise_len) { parm_set_error("CollectionSol: injected noise exhausted"); return PARM_ERR_INVALID; }
+            noise = g->d_noise + g->noise_pos;
+            g->noise_pos += per;
+        }
+        if (c->D == 3) k_sol1<3><<<grid, I_BLOCK, 0, c->stream>>>(c->pos, c->v, c->a, c->order, n, c->npad, K, noise, g->d_mobile_rank, g->steps, g->seed);
+        else k_sol1<2><<<grid, I_BLOCK, 0, c->stream>>>(c->pos, c->v, c->a, c->order, n, c->npad, K, noise, g->d_mobile_rank, g->steps, g->seed);
+        CK_LAUNCH(c);
+        PTRY(launch_all_forces(g));
+#define S2ARGS c->pos, c->v, c->a, c->f, n, c->npad, K.dtc2, nl ? nl->xlast : nullptr, nl ? nl->d_diam : nullptr, \
+               nl ? nl->skin : 0.0, nl ? nl->d_top2 : nullptr, nl ? nl->d_counter : nullptr, nl ? nl->d_flags : nullptr, \
+               nl ? nl->h_flags : nullptr
+        if (c->D == 3) {
+            if (nl) k_sol2<3, true><<<grid2, I_BLOCK, 0, c->stream>>>(S2ARGS);
+            else k_sol2<3, false><<<grid2, I_BLOCK, 0, c->stream>>>(S2ARGS);
+        } else {
+            if (nl) k_sol2<2, true><<<grid2, I_BLOCK, 0, c->stream>>>(S2ARGS);
+            else k_sol2<2, false><<<grid2, I_BLOCK, 0, c->stream>>>(S2ARGS);
+        }
+#undef S2ARGS
+        CK_LAUNCH(c);
+    }
+    g->steps++;
+    // update_trackers(): NeighborList::update -> update_list(false)  (collection.cpp:468, trackers.hpp:173-176)
+    if (nl) {
+        bool rebuild = nl->ignorechanged;
+        if (!rebuild) {
+            CK(cudaStreamSynchronize(c->stream));
+            rebuild = nl->h_flags->need_rebuild != 0;
+        }
+        if (rebuild) {
+            PTRY(parm_nlist_rebuild(nl));
+            g->rebuilds++;
+        }
+    }
+    return 0;
+}
+
+extern "C" int parm_integ_timestep(parm_integ *g, int nsteps) {
+    if (!g) { parm_set_error("parm_integ_timestep: NULL integrator"); return PARM_ERR_INVALID; }
+    parm_ctx *c = g->ctx;
+    CK(cudaSetDevice(c->device));
+    if (c->n == 0) { g->steps += nsteps > 0 ? nsteps : 0; return 0; }
+    for (size_t k = 1; k < g->trackers.size(); k++)
+        if (g->trackers[k] != g->trackers[0]) { parm_set_error("one NeighborList per Collection is supported"); return PARM_ERR_UNSUPPORTED; }
+    for (int s = 0; s < nsteps; s++) PTRY(one_step(g));
+    return 0;
+}
+
+extern "C" int parm_integ_potential_energy(parm_integ *g, double *E) {
+    double tot = 0;
+    for (parm_inter *it : g->inters) {
+        double e;
+        PTRY(parm_inter_energy(it, &e));
+        tot += e;
+    }
+    *E = tot;
+    return 0;
+}
+extern "C" int parm_integ_virial(parm_integ *g, double *w) {
+    double tot = 0;
+    for (parm_inter *it : g->inters) {
+        double p;
+        PTRY(parm_inter_pressure(it, &p));
+        tot += p;
+    }
+    *w = tot;
+    return 0;
+}
+extern "C" int parm_integ_stats(parm_integ *g, uint64_t *steps, uint64_t *rebuilds, uint64_t *launches) {
+    if (steps) *steps = g->steps;
+    if (rebuilds) *rebuilds = g->rebuilds;
+    if (launches) *launches = g->ctx->launches;
+    return 0;
+}

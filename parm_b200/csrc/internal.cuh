@@ -1,0 +1,199 @@
+// parm_b200 internal declarations shared by the .cu translation units.
+// Device data layout (DESIGN.md "Data layout in HBM"):
+//   pos   double4[npad]      (x, y, z, m) per SLOT; z == 0 in 2-D builds. Canonical
+//                            storage of Atom::x and Atom::m (box.hpp:234-249).
+//   v,a,f double[3][npad]    SoA per slot, component-major.
+//   order uint32[npad]       order[slot] = AtomVec index; slot_of is the inverse.
+// Slots are re-ordered by cell index at every neighbour-list rebuild so that the
+// force kernel's gathers of pos[j] stay cache-local.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/parm_b200.h"
+
+#define PARM_TILE 32u         // atoms per neighbour-list tile (= warp)
+#define PARM_MAX_SPECIES 32   // distinct per-atom parameter tuples per interaction
+
+void parm_set_error(const char *fmt, ...);
+void parm_count_launch(parm_ctx *ctx, unsigned n = 1);
+
+#define CK(call)                                                                              \
+    do {                                                                                      \
+        cudaError_t e_ = (call);                                                              \
+        if (e_ != cudaSuccess) {                                                              \
+            parm_set_error("CUDA error %s at %s:%d: %s", cudaGetErrorName(e_), __FILE__, __LINE__, \
+                           cudaGetErrorString(e_));                                           \
+            return PARM_ERR_CUDA;                                                             \
+        }                                                                                     \
+    } while (0)
+#define PTRY(expr)             \
+    do {                       \
+        int r_ = (expr);       \
+        if (r_) return r_;     \
+    } while (0)
+#define CK_LAUNCH(ctx)        \
+    do {                      \
+        parm_count_launch(ctx); \
+        CK(cudaGetLastError()); \
+    } while (0)
+
+struct BoxDev {
+    double L[3], invL[3], halfL[3];
+};
+
+// Per species-pair constants, mixed on the host exactly as the reference's pair
+// constructors do (interaction.hpp:878-883, 1531-1536, 1255-1270, 970-974 + 247-252).
+struct PairConst {
+    double eps;      // epsilon_ij (>= 0 after the eps<=0 rule of LJAttractRepulsePair)
+    double sig;      // sigma_ij
+    double sig2;     // sig*sig
+    double inv_sig2; // 1/(sig*sig)
+    double cut2;     // cut_distance^2 in units of sigma (kinds 0: 1, 2, 3)
+    double cutE;     // cut_energy
+    double expo;     // exponent (kind 1)
+    double pad;
+};
+
+struct parm_ctx {
+    int D;
+    uint32_t n, npad;
+    int device;
+    cudaStream_t stream;
+    BoxDev box;
+    bool box_set;
+    double4 *pos, *pos_alt;
+    double *v, *a, *f, *v_alt, *a_alt, *f_alt; // [3][npad]
+    uint32_t *order, *order_alt, *slot_of;
+    // transfer staging
+    void *d_stage;
+    size_t d_stage_bytes;
+    // small results
+    double *d_red;      // device scratch for reductions (partials + finals)
+    size_t d_red_doubles;
+    double *h_red;      // pinned host mirror
+    uint64_t launches;
+    std::vector<parm_nlist *> nlists;
+    std::vector<parm_inter *> inters;
+    int num_sms;
+};
+
+struct NlistFlags { // pinned, device-written
+    int need_rebuild;
+    uint32_t overflow_max;
+    unsigned long long total;
+    uint32_t maxcnt;
+    double top2[2];
+};
+
+struct parm_nlist {
+    parm_ctx *ctx;
+    double skin;
+    std::vector<double> h_diam; // by AtomVec index; < 0: not a member
+    bool have_diam;
+    double maxdiam;
+    double *d_diam_id;   // by AtomVec index
+    double *d_diam;      // by slot
+    double *xlast;       // [3][npad] by slot: lastlocs (trackers.hpp:165)
+    uint32_t updatenum;
+    bool ignorechanged;
+    // cell grid
+    int nc[3];
+    uint32_t ncell;
+    uint32_t *cell_id, *cell_id_sorted, *perm, *iota, *cell_start;
+    uint32_t cell_start_cap;
+    void *sort_temp;
+    size_t sort_temp_bytes;
+    // list: nbr[tile][k][lane], cnt[slot]
+    uint32_t kmax;
+    uint32_t *nbr;
+    size_t nbr_cap_entries;
+    uint32_t *cnt;
+    unsigned long long total_full; // sum of cnt
+    uint32_t maxcnt;
+    // drift / build flags
+    double *d_top2;      // per-block top-2
+    unsigned int *d_counter;
+    NlistFlags *d_flags;
+    NlistFlags *h_flags; // pinned
+    uint64_t rebuilds;
+};
+
+struct parm_inter {
+    parm_ctx *ctx;
+    parm_nlist *nl;
+    int kind;
+    bool have_params;
+    int nspecies;
+    std::vector<uint8_t> h_spec_id; // by AtomVec index
+    uint8_t *d_spec_id;             // by AtomVec index
+    uint8_t *d_spec;                // by slot
+    PairConst *d_table;             // nspecies x nspecies
+    std::vector<PairConst> h_table;
+    bool uniform_expo2;             // kind 1: all exponents == 2
+    double *d_partials;
+    size_t partial_doubles;
+};
+
+struct parm_integ {
+    parm_ctx *ctx;
+    int type; // 0 verlet, 1 sol
+    double dt, damping, force_mag, desT;
+    double c0, c1, c2, sigmar, sigmav, corr, x11, x21, x22;
+    uint64_t seed;
+    std::vector<parm_inter *> inters;
+    std::vector<parm_nlist *> trackers;
+    double *d_noise;
+    size_t noise_len, noise_pos;
+    uint32_t *d_mobile_rank; // by AtomVec index (noise injection addressing)
+    uint32_t n_mobile;
+    uint64_t steps, rebuilds;
+};
+
+// ---- cross-TU host functions ----
+int parm_nlist_rebuild(parm_nlist *nl);
+int parm_nlist_drift_check_async(parm_nlist *nl);   // standalone drift kernel (update_list(false) outside timestep)
+int parm_inter_regather(parm_inter *inter);          // re-gather per-slot species after a re-sort
+int parm_inter_launch_forces(parm_inter *inter, unsigned want, bool accumulate, double *d_out /*device, 11 doubles*/);
+int parm_ctx_ensure_red(parm_ctx *ctx, size_t doubles);
+
+// ---- device helpers ----
+#ifdef __CUDACC__
+// IEEE remainder(dx, L) (box.hpp:69-72) without the libm loop: exact whenever rint picks
+// the nearest integer; the fix-up restores exactness when dx*invL was mis-rounded next to a
+// half-integer; exact ties follow remainder()'s round-half-even rule.
+__device__ __forceinline__ double min_image_exact(double dx, double L, double invL, double halfL) {
+    double q = rint(__dmul_rn(dx, invL));
+    double r = __fma_rn(-q, L, dx);
+    if (r > halfL) {
+        r -= L;
+        q += 1.0;
+    } else if (r < -halfL) {
+        r += L;
+        q -= 1.0;
+    }
+    if (fabs(r) == halfL) {
+        // tie: remainder() picks the even quotient
+        double h = q * 0.5;
+        if (h != rint(h)) r = -r;
+    }
+    return r;
+}
+// hot-loop form: same value as min_image_exact except on exact ties / mis-rounded
+// half-integers (|r| ~ L/2, never inside a cutoff when L > 2 r_cut)
+__device__ __forceinline__ double min_image_fast(double dx, double L, double invL) {
+    double q = rint(dx * invL);
+    return fma(-q, L, dx);
+}
+// 256-bit read-only gather of one (x,y,z,m) record: a single LDG.E.256 (one 32-byte sector)
+__device__ __forceinline__ double4 ld_pos4(const double4 *p) {
+    double4 r;
+    asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(r.x), "=d"(r.y), "=d"(r.z), "=d"(r.w) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ bool frozen_le(double m) { return m <= 0.0 || isinf(m); }
+__device__ __forceinline__ bool frozen_eq(double m) { return m == 0.0 || isinf(m); }
+#endif

@@ -1,0 +1,684 @@
+"""Host-side mirror of ParM's public classes over the parm_b200 C ABI.
+
+Same class names, argument meaning and error behaviour as the reference's SWIG
+modules pyparm.d2 / pyparm.d3 (src/sim.i:616-670) for the hot path:
+
+  OriginBox            box.hpp:97-158
+  AtomVec / Atom       box.hpp:234-249, 441-479   (+ AtomGroup reductions box.cpp:239-260, 401-431)
+  NeighborList         trackers.hpp:157-214
+  LJRepulse            NListed<EpsSigAtom, LJRepulsePair>          sim.i:621
+  Repulsion            NListed<EpsSigExpAtom, RepulsionPair>       sim.i:636
+  LJAttractRepulse     NListed<IEpsSigCutAtom, LJAttractRepulsePair>  sim.i:629
+  LJCut                NListed<EpsSigCutAtom, LennardJonesCutPair> (LJatoms.cpp:37-38; no SWIG name)
+  CollectionVerlet     collection.hpp:360-374
+  CollectionSol        collection.hpp:205-263
+
+All numerical work happens in libparm_b200.so on the GPU; this module only keeps the
+host mirror of `Atom` (AoS, identical layout to the reference's struct) coherent with the
+device copy using coarse dirty flags (SURVEY 8b "Mutation model").
+"""
+import numpy as np
+
+from . import capi
+from .capi import C, call, dp, u32p, u8p, u64p
+
+
+def _dptr(a):
+    return None if a is None else a.ctypes.data_as(dp)
+
+
+def atom_dtype(ndim):
+    """struct Atom {Vec x, v, a, f; flt m;} (box.hpp:234-249): 104 bytes in 3-D, 72 in 2-D."""
+    return np.dtype([("x", np.float64, (ndim,)), ("v", np.float64, (ndim,)), ("a", np.float64, (ndim,)),
+                     ("f", np.float64, (ndim,)), ("m", np.float64)])
+
+
+class OriginBox:
+    """Rectilinear periodic box (box.hpp:97-158)."""
+
+    def __init__(self, L, ndim=None):
+        L = np.atleast_1d(np.asarray(L, dtype=np.float64))
+        if L.size == 1:
+            L = np.full(3 if ndim is None else ndim, float(L[0]))
+        self.boxsize = np.ascontiguousarray(L)
+        self.ndim = self.boxsize.size
+        if self.ndim not in (2, 3):
+            raise ValueError("OriginBox: NDIM must be 2 or 3")
+        self._ctxs = []
+
+    def box_shape(self):
+        return self.boxsize.copy()
+
+    def V(self):  # box.hpp:122,127
+        b = self.boxsize
+        return float(b[0] * b[1] * b[2]) if self.ndim == 3 else float(b[0] * b[1])
+
+    def L(self):  # box.hpp:123,128
+        b = self.boxsize
+        return float((b[0] + b[1] + b[2]) / 3.0) if self.ndim == 3 else float((b[0] + b[1]) / 2.0)
+
+    def _attach(self, atoms):
+        if atoms not in self._ctxs:
+            self._ctxs.append(atoms)
+            call("parm_set_box", atoms._h, _dptr(self.boxsize))
+
+    def resize_to(self, newsize):  # box.cpp:21-25 (does not move atoms)
+        self.boxsize = np.ascontiguousarray(np.broadcast_to(np.asarray(newsize, dtype=np.float64), (self.ndim,)))
+        for a in self._ctxs:
+            call("parm_set_box", a._h, _dptr(self.boxsize))
+        return self.V()
+
+    def diff(self, r1, r2, atoms=None):
+        """OriginBox::diff evaluated ON THE DEVICE (box.hpp:103). r1, r2: (..., ndim)."""
+        if atoms is None:
+            if not self._ctxs:
+                raise capi.ParmInvalid("OriginBox.diff needs an AtomVec context")
+            atoms = self._ctxs[0]
+        r1 = np.ascontiguousarray(r1, dtype=np.float64)
+        r2 = np.ascontiguousarray(r2, dtype=np.float64)
+        out = np.empty_like(r1)
+        call("parm_box_diff", atoms._h, r1.size // self.ndim, _dptr(r1), _dptr(r2), _dptr(out))
+        return out
+
+
+class Atom:
+    """Proxy for one `Atom&` of an AtomVec (reads/writes go to the host mirror)."""
+    __slots__ = ("_av", "_i")
+
+    def __init__(self, av, i):
+        object.__setattr__(self, "_av", av)
+        object.__setattr__(self, "_i", i)
+
+    def __getattr__(self, k):
+        if k in ("x", "v", "a", "f", "m"):
+            return self._av._host()[k][self._i]
+        raise AttributeError(k)
+
+    def __setattr__(self, k, val):
+        if k not in ("x", "v", "a", "f", "m"):
+            raise AttributeError(k)
+        self._av._host()[k][self._i] = val
+
+
+class AtomID:
+    def __init__(self, av, n):
+        self.atoms, self._n = av, n
+
+    def n(self):
+        return self._n
+
+
+class AtomVec:
+    """AtomVec(N, mass) / AtomVec(masses) (box.hpp:441-479). Owns the device context."""
+
+    def __init__(self, N_or_masses, mass=None, ndim=3, device=0):
+        if mass is None:
+            masses = np.asarray(N_or_masses, dtype=np.float64).ravel()
+        else:
+            masses = np.full(int(N_or_masses), float(mass))
+        self.ndim = ndim
+        self.n = masses.size
+        self.atoms = np.zeros(self.n, dtype=atom_dtype(ndim))  # zero(): x=v=a=f=0 (box.hpp:445-452)
+        self.atoms["m"] = masses
+        h = C.c_void_p()
+        call("parm_ctx_create", ndim, self.n, device, C.byref(h))
+        self._h = h
+        self._registered = False
+        if self.n:
+            try:
+                call("parm_host_register", self.atoms.ctypes.data, self.atoms.nbytes)
+                self._registered = True
+            except capi.ParmError:
+                pass
+        self._host_dirty = True   # host mirror holds data the device has not seen
+        self._dev_newer = False   # device holds data the host mirror has not seen
+
+    # -- coherence ---------------------------------------------------------------
+    def _field_ptrs(self):
+        base = self.atoms.ctypes.data
+        vec = self.ndim * 8
+        return [C.cast(base + k * vec, dp) for k in range(5)]
+
+    def _host(self):
+        """Host mirror, current, and assumed modified by the caller (a mutable view escapes)."""
+        self.sync_to_host()
+        self._host_dirty = True
+        return self.atoms
+
+    def sync_to_host(self):
+        if self._dev_newer and self.n:
+            p = self._field_ptrs()
+            call("parm_download_atoms", self._h, capi.ALL, p[0], p[1], p[2], p[3], p[4], self.atoms.itemsize, self.atoms.itemsize)
+        self._dev_newer = False
+
+    def sync_to_device(self):
+        if self._host_dirty and self.n:
+            p = self._field_ptrs()
+            call("parm_upload_atoms", self._h, capi.ALL, p[0], p[1], p[2], p[3], p[4], self.atoms.itemsize, self.atoms.itemsize)
+        self._host_dirty = False
+
+    def _device_op(self, modifies=True):
+        self.sync_to_device()
+        if modifies:
+            self._dev_newer = True
+
+    # -- element access ----------------------------------------------------------------
+    def __len__(self):
+        return self.n
+
+    def size(self):
+        return self.n
+
+    def __getitem__(self, i):
+        if not -self.n <= i < self.n:
+            raise IndexError(i)
+        return Atom(self, i % self.n)
+
+    def __iter__(self):
+        return (Atom(self, i) for i in range(self.n))
+
+    def get_id(self, n):
+        return AtomID(self, n)
+
+    x = property(lambda self: self._host()["x"])
+    v = property(lambda self: self._host()["v"])
+    a = property(lambda self: self._host()["a"])
+    f = property(lambda self: self._host()["f"])
+    m = property(lambda self: self._host()["m"])
+
+    def peek(self, field):
+        """Read-only copy of a field without marking the host mirror modified."""
+        self.sync_to_host()
+        return self.atoms[field].copy()
+
+    # -- AtomGroup reductions, computed on the device (box.cpp:239-260, 401-431) ----------
+    def _reduce(self, what, v0=None, nout=1):
+        self._device_op(modifies=False)
+        out = np.zeros(4)
+        z = None if v0 is None else np.ascontiguousarray(v0, dtype=np.float64)
+        call("parm_reduce", self._h, what, _dptr(z), _dptr(out))
+        return float(out[0]) if nout == 1 else out[:nout].copy()
+
+    def mass(self):
+        return self._reduce(capi.RED_MASS)
+
+    def momentum(self):
+        return self._reduce(capi.RED_MOMENTUM, nout=self.ndim)
+
+    def com(self):
+        return self._reduce(capi.RED_COM, nout=self.ndim)
+
+    def com_force(self):
+        return self._reduce(capi.RED_COMFORCE, nout=self.ndim)
+
+    def com_velocity(self):
+        return self.momentum() / self.mass()
+
+    def kinetic_energy(self, originvelocity=None):
+        return self._reduce(capi.RED_KE, originvelocity)
+
+    def add_velocity(self, dv):
+        self._device_op()
+        dv = np.ascontiguousarray(dv, dtype=np.float64)
+        call("parm_add_velocity", self._h, _dptr(dv))
+
+    def reset_com_velocity(self):
+        self.add_velocity(-self.com_velocity())
+
+    def reset_forces(self):
+        self._device_op()
+        call("parm_reset_forces", self._h)
+
+    def close(self):
+        if self._h:
+            if self._registered:
+                try:
+                    call("parm_host_unregister", self.atoms.ctypes.data)
+                except Exception:
+                    pass
+            capi.lib().parm_ctx_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class NeighborList:
+    """NeighborList(box, atoms, skin) (trackers.hpp:157-214)."""
+
+    def __init__(self, box, atoms, skin):
+        self.box, self.atoms, self.skin = box, atoms, float(skin)
+        box._attach(atoms)
+        h = C.c_void_p()
+        call("parm_nlist_create", atoms._h, self.skin, C.byref(h))
+        self._h = h
+        self._diam = np.full(atoms.n, -1.0)
+        self._diam_dirty = False
+
+    def add(self, atom_id, diameter):
+        i = atom_id.n() if hasattr(atom_id, "n") else int(atom_id)
+        if self._diam[i] >= 0:  # SubGroup::add (box.hpp:495-501)
+            raise ValueError("Cannot add AtomID to SubGroup: it already exists.")
+        self._diam[i] = diameter
+        self._diam_dirty = True
+
+    def _flush(self):
+        if self._diam_dirty:
+            call("parm_nlist_set_diameters", self._h, _dptr(self._diam))
+            self._diam_dirty = False
+
+    def _set_diameters_from_inter(self, diam):
+        self._diam = np.array(diam, dtype=np.float64)
+        self._diam_dirty = False
+
+    def update_list(self, force=True):
+        self._flush()
+        self.atoms._device_op()  # a rebuild re-orders the device arrays but not their AtomVec-indexed content
+        r = C.c_int(0)
+        call("parm_nlist_update", self._h, int(force), C.byref(r))
+        return bool(r.value)
+
+    def update(self, box=None):
+        return self.update_list(False)
+
+    def which(self):
+        u = C.c_uint32(0)
+        call("parm_nlist_which", self._h, C.byref(u))
+        return u.value
+
+    def numpairs(self):
+        u = C.c_uint64(0)
+        call("parm_nlist_numpairs", self._h, C.byref(u))
+        return u.value
+
+    def size(self):
+        return int((self._diam >= 0).sum())
+
+    def pairs(self):
+        """curpairs as two uint32 arrays (first, last) in the reference's order (trackers.cpp:59-68)."""
+        n = self.numpairs()
+        a = np.empty(n, np.uint32)
+        b = np.empty(n, np.uint32)
+        if n:
+            call("parm_nlist_download_pairs", self._h, a.ctypes.data_as(u32p), b.ctypes.data_as(u32p), n)
+        return a, b
+
+    def __iter__(self):
+        a, b = self.pairs()
+        return iter(zip(a.tolist(), b.tolist()))
+
+    def stats(self):
+        mean = C.c_double(0)
+        mx = C.c_uint32(0)
+        call("parm_nlist_stats", self._h, C.byref(mean), C.byref(mx))
+        return mean.value, mx.value
+
+
+class EpsSigAtom:  # interaction.hpp:857-865
+    def __init__(self, a, epsilon, sigma):
+        self.id, self.p = a, (epsilon, sigma, 0.0)
+        self.type = 0
+
+
+class EpsSigExpAtom:  # interaction.hpp:1454-1465
+    def __init__(self, a, eps, sigma, exponent):
+        self.id, self.p = a, (eps, sigma, exponent)
+        self.type = 0
+
+
+class EpsSigCutAtom:  # interaction.hpp:897-905
+    def __init__(self, a, epsilon, sigma, cut):
+        self.id, self.p = a, (epsilon, sigma, cut)
+        self.type = 0
+
+
+class IEpsSigCutAtom:  # interaction.hpp:989-1018
+    def __init__(self, a, epsilons, indx, sigma, cut):
+        self.id, self.p = a, (0.0, sigma, cut)
+        self.type = int(indx)
+        self.epsilons = list(epsilons)
+
+
+class _NListed:
+    kind = None
+
+    def __init__(self, *args):
+        # NListed(box, atoms, skin) or NListed(atoms, neighbors)  (interaction.hpp:1903-1914)
+        if len(args) == 3:
+            box, atoms, skin = args
+            self.neighbors = NeighborList(box, atoms, skin)
+        elif len(args) == 2:
+            atoms, self.neighbors = args
+        else:
+            raise TypeError("NListed(box, atoms, skin) or NListed(atoms, neighbors)")
+        self.atoms = atoms
+        h = C.c_void_p()
+        call("parm_inter_create", atoms._h, self.neighbors._h, self.kind, C.byref(h))
+        self._h = h
+        n = atoms.n
+        self._params = np.zeros((n, 3))
+        self._types = np.zeros(n, np.uint32)
+        self._member = np.zeros(n, np.uint8)
+        self._eps_rows = {}
+        self._dirty = False
+
+    def add(self, atm):
+        i = atm.id.n() if hasattr(atm.id, "n") else int(atm.id)
+        if self._member[i]:
+            raise ValueError("Cannot add AtomID to SubGroup: it already exists.")
+        self._params[i] = atm.p
+        self._types[i] = atm.type
+        self._member[i] = 1
+        if hasattr(atm, "epsilons"):
+            self._eps_rows[atm.type] = atm.epsilons
+        self._dirty = True
+
+    def add_many(self, params, types=None, eps_table=None, member=None):
+        """Bulk form of add(): params (n,3) as in include/parm_b200.h."""
+        n = self.atoms.n
+        self._params = np.ascontiguousarray(params, dtype=np.float64).reshape(n, 3)
+        self._types = np.zeros(n, np.uint32) if types is None else np.ascontiguousarray(types, dtype=np.uint32)
+        self._member = np.ones(n, np.uint8) if member is None else np.ascontiguousarray(member, dtype=np.uint8)
+        self._eps_table = None if eps_table is None else np.ascontiguousarray(eps_table, dtype=np.float64)
+        self._dirty = True
+
+    def _flush(self):
+        if not self._dirty:
+            return
+        tab = getattr(self, "_eps_table", None)
+        if tab is None and self._eps_rows:
+            nt = max(len(r) for r in self._eps_rows.values())
+            tab = np.zeros((nt, nt))
+            for t, row in self._eps_rows.items():
+                tab[t, :len(row)] = row
+        nt = 0 if tab is None else tab.shape[0]
+        diam_src = self._params[:, 1] * (1.0 if self.kind in (capi.PAIR_LJREPULSE, capi.PAIR_REPULSION) else self._params[:, 2])
+        diam = np.where(self._member > 0, diam_src, -1.0)
+        shared = self.neighbors._diam
+        # NListed::add forwards max_size() to the (possibly shared) NeighborList
+        newdiam = np.where(self._member > 0, diam, shared)
+        call("parm_inter_set_params", self._h, _dptr(self._params), self._types.ctypes.data_as(u32p), _dptr(tab), nt,
+             self._member.ctypes.data_as(u8p), 0)
+        call("parm_nlist_set_diameters", self.neighbors._h, _dptr(np.ascontiguousarray(newdiam)))
+        self.neighbors._set_diameters_from_inter(newdiam)
+        self._dirty = False
+
+    def neighbor_list(self):
+        self._flush()
+        return self.neighbors
+
+    def _ready(self, modifies):
+        self._flush()
+        self.neighbors._flush()
+        self.atoms._device_op(modifies)
+
+    def energy(self, box=None):
+        self._ready(False)
+        e = C.c_double(0)
+        call("parm_inter_energy", self._h, C.byref(e))
+        return e.value
+
+    def pressure(self, box=None):
+        self._ready(False)
+        e = C.c_double(0)
+        call("parm_inter_pressure", self._h, C.byref(e))
+        return e.value
+
+    def stress(self, box=None):
+        self._ready(False)
+        D = self.atoms.ndim
+        out = np.zeros((D, D))
+        call("parm_inter_stress", self._h, _dptr(out))
+        return out
+
+    def set_forces(self, box=None):
+        self._ready(True)
+        call("parm_inter_set_forces", self._h, 0, None)
+
+    def set_forces_get_pressure(self, box=None):
+        self._ready(True)
+        out = np.zeros(1)
+        call("parm_inter_set_forces", self._h, capi.WANT_VIRIAL, _dptr(out))
+        return float(out[0])
+
+    def set_forces_get_stress(self, box=None):
+        self._ready(True)
+        D = self.atoms.ndim
+        out = np.zeros((D, D))
+        call("parm_inter_set_forces", self._h, capi.WANT_STRESS, _dptr(out))
+        return out
+
+    def contacts(self, box=None):
+        self._ready(False)
+        a, b = C.c_uint64(0), C.c_uint64(0)
+        call("parm_inter_contacts", self._h, C.byref(a), C.byref(b))
+        return a.value
+
+    def overlaps(self, box=None):
+        self._ready(False)
+        a, b = C.c_uint64(0), C.c_uint64(0)
+        call("parm_inter_contacts", self._h, C.byref(a), C.byref(b))
+        return b.value
+
+
+class LJRepulse(_NListed):
+    kind = capi.PAIR_LJREPULSE
+
+
+LJRepulsive = LJRepulse  # planned rename, src/namereplacements.txt:181
+
+
+class Repulsion(_NListed):
+    kind = capi.PAIR_REPULSION
+
+
+class LJAttractRepulse(_NListed):
+    kind = capi.PAIR_LJATTRACTREPULSE
+
+
+class LJCut(_NListed):
+    kind = capi.PAIR_LJCUT
+
+
+class Collection:
+    """Collection base (collection.hpp:23-130, collection.cpp:3-208)."""
+
+    def __init__(self, box, atoms, interactions=(), trackers=(), constraints=()):
+        if constraints:
+            raise capi.ParmUnsupported("Constraints are outside the hot-path scope (DESIGN.md)")
+        self.box, self.atoms = box, atoms
+        box._attach(atoms)
+        self.interactions, self.trackers = [], []
+        for t in trackers:
+            self._push_tracker(t)
+        for i in interactions:
+            self._push_interaction(i)
+
+    def _push_interaction(self, inter):
+        if not isinstance(inter, _NListed):
+            raise capi.ParmUnsupported("only NListed interactions of the four in-scope pair types run on the device")
+        inter._flush()
+        self.interactions.append(inter)
+
+    def _push_tracker(self, t):
+        if not isinstance(t, NeighborList):
+            raise capi.ParmUnsupported("only NeighborList trackers run on the device")
+        self.trackers.append(t)
+
+    def _ready(self, modifies=True):
+        for i in self.interactions:
+            i._flush()
+        for t in self.trackers:
+            t._flush()
+        self.atoms._device_op(modifies)
+
+    def add_interaction(self, inter):
+        self._push_interaction(inter)
+        self._ready()
+        call("parm_integ_add_interaction", self._h, inter._h)
+
+    def add_tracker(self, t):
+        self._push_tracker(t)
+        self._ready()
+        call("parm_integ_add_tracker", self._h, t._h)
+
+    def add(self, obj):
+        return self.add_tracker(obj) if isinstance(obj, NeighborList) else self.add_interaction(obj)
+
+    def initialize(self):
+        self._ready()
+        call("parm_integ_initialize", self._h)
+
+    def set_forces(self, constraints_and_a=True):
+        self._ready()
+        call("parm_integ_set_forces", self._h, int(constraints_and_a))
+
+    def timestep(self, nsteps=1):
+        self._ready()
+        call("parm_integ_timestep", self._h, int(nsteps))
+
+    def update_trackers(self):
+        self._ready()
+        call("parm_integ_update_trackers", self._h)
+
+    def potential_energy(self):
+        self._ready(False)
+        e = C.c_double(0)
+        call("parm_integ_potential_energy", self._h, C.byref(e))
+        return e.value
+
+    def kinetic_energy(self):
+        return self.atoms.kinetic_energy()
+
+    def energy(self):
+        return self.potential_energy() + self.kinetic_energy()
+
+    def virial(self):
+        self._ready(False)
+        e = C.c_double(0)
+        call("parm_integ_virial", self._h, C.byref(e))
+        return e.value
+
+    def pressure(self):  # collection.cpp:85-96
+        return (2.0 * self.kinetic_energy() + self.virial()) / self.box.V() / float(self.atoms.ndim)
+
+    def degrees_of_freedom(self):
+        return self.atoms._reduce(capi.RED_NDOF)
+
+    def com_velocity(self):
+        return self.atoms.com_velocity()
+
+    def temp(self, minuscomv=True):  # collection.cpp:135-142
+        v = self.atoms.com_velocity() if minuscomv else None
+        ndof = int(self.degrees_of_freedom())
+        if minuscomv:
+            ndof -= self.atoms.ndim
+        return self.atoms.kinetic_energy(v) * 2 / ndof
+
+    def reset_com_velocity(self):
+        self.atoms.reset_com_velocity()
+
+    def scale_velocities(self, scaleby):
+        self.atoms._device_op()
+        call("parm_scale_velocities", self.atoms._h, float(scaleby))
+
+    def scale_velocities_to_temp(self, T, minuscomv=True):  # collection.cpp:31-35
+        t = self.temp(minuscomv)
+        self.scale_velocities(np.sqrt(T / t))
+
+    def scale_velocities_to_energy(self, E):  # collection.cpp:37-43
+        E0 = self.energy()
+        k0 = self.kinetic_energy()
+        goalkinetic = k0 + (E - E0)
+        self.scale_velocities(np.sqrt(goalkinetic / k0))
+
+    def stats(self):
+        a, b, c = C.c_uint64(0), C.c_uint64(0), C.c_uint64(0)
+        call("parm_integ_stats", self._h, C.byref(a), C.byref(b), C.byref(c))
+        return dict(steps=a.value, rebuilds=b.value, launches=c.value)
+
+
+class CollectionVerlet(Collection):
+    def __init__(self, box, atoms, dt, interactions=(), trackers=(), constraints=()):
+        Collection.__init__(self, box, atoms, interactions, trackers, constraints)
+        h = C.c_void_p()
+        call("parm_verlet_create", atoms._h, float(dt), C.byref(h))
+        self._h = h
+        self.dt = float(dt)
+        _construct(self)
+
+    def set_dt(self, dt):
+        self.dt = float(dt)
+        call("parm_integ_set_dt", self._h, self.dt)
+
+
+class CollectionSol(Collection):
+    def __init__(self, box, atoms, dt, damping, desired_temperature, interactions=(), trackers=(), constraints=(), seed=0):
+        Collection.__init__(self, box, atoms, interactions, trackers, constraints)
+        h = C.c_void_p()
+        call("parm_sol_create", atoms._h, float(dt), float(damping), float(desired_temperature), int(seed), C.byref(h))
+        self._h = h
+        self.dt = float(dt)
+        _construct(self)
+
+    def set_dt(self, dt):
+        self.dt = float(dt)
+        call("parm_integ_set_dt", self._h, self.dt)
+
+    def change_temperature(self, damping, desired_temperature):
+        call("parm_integ_set_temperature", self._h, float(damping), float(desired_temperature))
+
+    def inject_noise(self, z):
+        """Exact-parity hook: z (steps, n_mobile, 2, ndim) standard normals (see parm_integ_inject_noise)."""
+        self._ready()
+        if z is None:
+            call("parm_integ_inject_noise", self._h, None, 0)
+            return
+        z = np.ascontiguousarray(z, dtype=np.float64)
+        call("parm_integ_inject_noise", self._h, _dptr(z), z.size)
+
+    def sol_constants(self):
+        out = np.zeros(6)
+        call("parm_integ_get_sol_constants", self._h, _dptr(out))
+        return out
+
+
+def _construct(collec):
+    """Collection constructor tail: the vectors were stored as passed (no per-add update_trackers),
+    then Collection::initialize() runs (collection.cpp:3-19)."""
+    collec._ready()
+    lib = capi.lib()
+    for t in collec.trackers:
+        capi.check(lib.parm_integ_register_tracker(collec._h, t._h))
+    for i in collec.interactions:
+        capi.check(lib.parm_integ_register_interaction(collec._h, i._h))
+    call("parm_integ_initialize", collec._h)
+
+
+def from_workload(w, device=0, collection=True):
+    """Build (box, atoms, interaction, neighbor list, collection) from a parm_b200.workloads dict,
+    following LJatoms.cpp:30-83: NListed(box, atoms, skin); add atoms; update_list(true);
+    Collection(box, atoms, dt); add_tracker(nl); add_interaction(I)."""
+    ndim = w["ndim"]
+    box = OriginBox(w["L"], ndim)
+    atoms = AtomVec(w["m"], ndim=ndim, device=device)
+    atoms.atoms["x"] = w["x"]
+    atoms.atoms["v"] = w["v"]
+    cls = {capi.PAIR_LJREPULSE: LJRepulse, capi.PAIR_REPULSION: Repulsion,
+           capi.PAIR_LJATTRACTREPULSE: LJAttractRepulse, capi.PAIR_LJCUT: LJCut}[w["kind"]]
+    inter = cls(box, atoms, w["skin"])
+    inter.add_many(w["params"], w.get("types"), w.get("eps_table"), w.get("member"))
+    nl = inter.neighbor_list()
+    nl.update_list(True)
+    collec = None
+    if collection:
+        if w.get("integrator", 0) == 0:
+            collec = CollectionVerlet(box, atoms, w["dt"])
+        else:
+            collec = CollectionSol(box, atoms, w["dt"], w["damping"], w["T"], seed=w.get("seed", 0))
+        collec.add_tracker(nl)
+        collec.add_interaction(inter)
+    return box, atoms, inter, nl, collec

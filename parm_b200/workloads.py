@@ -119,8 +119,12 @@ def hertzian12(seed=131):
     Vs = (np.pi / 6 * sig ** 3).sum()
     L = (Vs / 0.3) ** (1.0 / 3.0)
     rs = np.random.RandomState(seed)
-    x = rs.uniform(0, L, (n, 3))
-    v = rs.normal(size=(n, 3)) / np.sqrt(m)[:, None]
+    x = np.empty((n, 3))
+    v = np.empty((n, 3))
+    for i in range(n):  # tests.py:266-271 draws x, v, f per atom, interleaved
+        x[i] = rs.uniform(0., L, size=(3,))
+        v[i] = rs.normal(size=(3,)) / m[i]
+        rs.normal(size=(3,))  # a.f, overwritten by set_forces
     params = np.stack([np.full(n, 1.2), sig, np.full(n, 2.0)], axis=1)
     return dict(ndim=3, L=np.full(3, L), x=x, v=v, m=m, kind=KIND_REPULSION, params=params,
                 types=np.zeros(n, np.uint32), eps_table=np.ones((1, 1)), skin=0.4, dt=0.01, integrator=VERLET,
@@ -147,8 +151,9 @@ def random_system(n, ndim, kind, seed, rho=0.9, ntypes=2, polydisperse=True, T=1
         m[rng.choice(n, frozen, replace=False)] = 0.0
     mm = np.where(m > 0, m, 1.0)
     v = rng.standard_normal((n, ndim)) * np.sqrt(T / mm)[:, None]
-    sig = rng.uniform(0.8, 1.4, n) if polydisperse else np.ones(n)
-    eps = rng.uniform(0.5, 1.5, n)
+    # discrete species (the device path tabulates pair constants per species pair)
+    sig = rng.choice([0.8, 1.0, 1.2, 1.4], n) if polydisperse else np.ones(n)
+    eps = rng.choice([0.5, 1.5], n)
     third = {KIND_LJREPULSE: np.zeros(n), KIND_REPULSION: rng.choice([2.0, 2.5, 1.5], n),
              KIND_LJATTRACTREPULSE: rng.choice([2.0, 2.5], n), KIND_LJCUT: rng.choice([2.0, 2.5], n)}[kind]
     params = np.stack([eps, sig, third], axis=1)
