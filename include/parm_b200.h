@@ -73,6 +73,18 @@ int parm_download_atoms(parm_ctx *ctx, unsigned mask, double *x, double *v, doub
 int parm_host_register(void *ptr, size_t bytes);
 int parm_host_unregister(void *ptr);
 int parm_sync(parm_ctx *ctx);
+/* the CUDA stream (cudaStream_t) every kernel of this context is launched on, so a caller
+ * can bracket calls with its own CUDA events */
+int parm_get_stream(parm_ctx *ctx, void **cuda_stream);
+/* per-kernel-class device timing with CUDA events on that stream (bench.py rooflines) */
+#define PARM_PROF_INTEG1 0  /* K1 first half step */
+#define PARM_PROF_FORCE 1   /* pair force kernel(s) */
+#define PARM_PROF_INTEG2 2  /* K3 second half step + drift reduction */
+#define PARM_PROF_REBUILD 3 /* bin + sort + permute + neighbour build */
+#define PARM_PROF_N 4
+int parm_profile_enable(parm_ctx *ctx, int enable);
+/* waits for the stream, adds up the recorded intervals per class since the last read */
+int parm_profile_read(parm_ctx *ctx, double *ms /*[PARM_PROF_N]*/, uint64_t *intervals /*[PARM_PROF_N]*/);
 
 /* ---- AtomGroup reductions box.cpp:239-260, 401-431; Collection collection.cpp:21-29,116-133 ---- */
 #define PARM_RED_MASS 0      /* out[1]      AtomGroup::mass,  skips m<=0||inf */

@@ -38,6 +38,9 @@ SIGNATURES = {
     "parm_host_register": (C.c_int, [vp, C.c_size_t]),
     "parm_host_unregister": (C.c_int, [vp]),
     "parm_sync": (C.c_int, [vp]),
+    "parm_get_stream": (C.c_int, [vp, vpp]),
+    "parm_profile_enable": (C.c_int, [vp, C.c_int]),
+    "parm_profile_read": (C.c_int, [vp, dp, u64p]),
     "parm_reduce": (C.c_int, [vp, C.c_int, dp, dp]),
     "parm_scale_velocities": (C.c_int, [vp, C.c_double]),
     "parm_add_velocity": (C.c_int, [vp, dp]),

@@ -386,10 +386,15 @@ static int one_step(parm_integ *g) {
     const double dt = g->dt;
     if (g->type == 0) {
         const double hdt2 = dt * dt / 2, hdt = dt / 2;
+        PTRY(parm_prof_begin(c, PARM_PROF_INTEG1));
         if (c->D == 3) k_verlet1<3><<<grid, I_BLOCK, 0, c->stream>>>(c->pos, c->v, c->a, n, c->npad, dt, hdt2, hdt);
         else k_verlet1<2><<<grid, I_BLOCK, 0, c->stream>>>(c->pos, c->v, c->a, n, c->npad, dt, hdt2, hdt);
         CK_LAUNCH(c);
+        PTRY(parm_prof_end(c));
+        PTRY(parm_prof_begin(c, PARM_PROF_FORCE));
         PTRY(launch_all_forces(g));
+        PTRY(parm_prof_end(c));
+        PTRY(parm_prof_begin(c, PARM_PROF_INTEG2));
 #define V2ARGS c->pos, c->v, c->a, c->f, n, c->npad, hdt, nl ? nl->xlast : nullptr, nl ? nl->d_diam : nullptr, \
                nl ? nl->skin : 0.0, nl ? nl->d_top2 : nullptr, nl ? nl->d_counter : nullptr, nl ? nl->d_flags : nullptr, \
                nl ? nl->h_flags : nullptr
@@ -402,6 +407,7 @@ static int one_step(parm_integ *g) {
         }
 #undef V2ARGS
         CK_LAUNCH(c);
+        PTRY(parm_prof_end(c));
     } else {
         SolConst K;
         K.dt = dt;
@@ -422,10 +428,15 @@ static int one_step(parm_integ *g) {
             noise = g->d_noise + g->noise_pos;
             g->noise_pos += per;
         }
+        PTRY(parm_prof_begin(c, PARM_PROF_INTEG1));
         if (c->D == 3) k_sol1<3><<<grid, I_BLOCK, 0, c->stream>>>(c->pos, c->v, c->a, c->order, n, c->npad, K, noise, g->d_mobile_rank, g->steps, g->seed);
         else k_sol1<2><<<grid, I_BLOCK, 0, c->stream>>>(c->pos, c->v, c->a, c->order, n, c->npad, K, noise, g->d_mobile_rank, g->steps, g->seed);
         CK_LAUNCH(c);
+        PTRY(parm_prof_end(c));
+        PTRY(parm_prof_begin(c, PARM_PROF_FORCE));
         PTRY(launch_all_forces(g));
+        PTRY(parm_prof_end(c));
+        PTRY(parm_prof_begin(c, PARM_PROF_INTEG2));
 #define S2ARGS c->pos, c->v, c->a, c->f, n, c->npad, K.dtc2, nl ? nl->xlast : nullptr, nl ? nl->d_diam : nullptr, \
                nl ? nl->skin : 0.0, nl ? nl->d_top2 : nullptr, nl ? nl->d_counter : nullptr, nl ? nl->d_flags : nullptr, \
                nl ? nl->h_flags : nullptr
@@ -438,6 +449,7 @@ static int one_step(parm_integ *g) {
         }
 #undef S2ARGS
         CK_LAUNCH(c);
+        PTRY(parm_prof_end(c));
     }
     g->steps++;
     // update_trackers(): NeighborList::update -> update_list(false)  (collection.cpp:468, trackers.hpp:173-176)

@@ -79,7 +79,16 @@ struct parm_ctx {
     std::vector<parm_nlist *> nlists;
     std::vector<parm_inter *> inters;
     int num_sms;
+    // optional per-class CUDA-event timing
+    bool prof_on;
+    struct ProfRec { int cls; cudaEvent_t a, b; };
+    std::vector<ProfRec> prof_pending;
+    std::vector<cudaEvent_t> prof_pool;
+    double prof_ms[PARM_PROF_N];
+    uint64_t prof_cnt[PARM_PROF_N];
 };
+int parm_prof_begin(parm_ctx *c, int cls);
+int parm_prof_end(parm_ctx *c);
 
 struct NlistFlags { // pinned, device-written
     int need_rebuild;

@@ -326,6 +326,7 @@ int parm_nlist_rebuild(parm_nlist *nl) {
         CK(cudaMalloc(&nl->cell_start, (size_t)nl->cell_start_cap * 4));
     }
 
+    PTRY(parm_prof_begin(c, PARM_PROF_REBUILD));
     // --- bin, sort by cell index (stable LSD radix sort), re-order every per-slot array
     k_cell_id<<<grid_for(c, n, 256), 256, 0, c->stream>>>(c->pos, n, c->box, g, nl->cell_id, nl->iota);
     CK_LAUNCH(c);
@@ -372,6 +373,7 @@ int parm_nlist_rebuild(parm_nlist *nl) {
         k_build<<<(n + 127) / 128, 128, 0, c->stream>>>(c->pos, nl->d_diam, nl->cell_id_sorted, nl->cell_start, n, c->box, g,
                                                        st, nl->skin, nl->kmax, nl->nbr, nl->cnt, nl->d_flags);
         CK_LAUNCH(c);
+        if (attempt == 0) PTRY(parm_prof_end(c));
         CK(cudaMemcpyAsync(nl->h_flags, nl->d_flags, sizeof(NlistFlags), cudaMemcpyDeviceToHost, c->stream));
         CK(cudaStreamSynchronize(c->stream));
         nl->total_full = nl->h_flags->total;

@@ -110,6 +110,8 @@ extern "C" int parm_ctx_destroy(parm_ctx *c) {
     for (void *p : ptrs)
         if (p) cudaFree(p);
     if (c->h_red) cudaFreeHost(c->h_red);
+    for (auto &r : c->prof_pending) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+    for (auto e : c->prof_pool) cudaEventDestroy(e);
     cudaStreamDestroy(c->stream);
     delete c;
     return 0;
@@ -138,6 +140,61 @@ extern "C" int parm_get_box(parm_ctx *c, double *L) {
 extern "C" int parm_sync(parm_ctx *c) {
     CK(cudaSetDevice(c->device));
     CK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+extern "C" int parm_get_stream(parm_ctx *c, void **st) {
+    *st = (void *)c->stream;
+    return 0;
+}
+
+static int prof_event(parm_ctx *c, cudaEvent_t *e) {
+    if (!c->prof_pool.empty()) {
+        *e = c->prof_pool.back();
+        c->prof_pool.pop_back();
+        return 0;
+    }
+    CK(cudaEventCreate(e));
+    return 0;
+}
+int parm_prof_begin(parm_ctx *c, int cls) {
+    if (!c->prof_on) return 0;
+    parm_ctx::ProfRec r;
+    r.cls = cls;
+    PTRY(prof_event(c, &r.a));
+    PTRY(prof_event(c, &r.b));
+    CK(cudaEventRecord(r.a, c->stream));
+    c->prof_pending.push_back(r);
+    return 0;
+}
+int parm_prof_end(parm_ctx *c) {
+    if (!c->prof_on || c->prof_pending.empty()) return 0;
+    CK(cudaEventRecord(c->prof_pending.back().b, c->stream));
+    return 0;
+}
+extern "C" int parm_profile_enable(parm_ctx *c, int enable) {
+    CK(cudaSetDevice(c->device));
+    c->prof_on = enable != 0;
+    return 0;
+}
+extern "C" int parm_profile_read(parm_ctx *c, double *ms, uint64_t *cnt) {
+    CK(cudaSetDevice(c->device));
+    CK(cudaStreamSynchronize(c->stream));
+    for (auto &r : c->prof_pending) {
+        float t = 0;
+        CK(cudaEventElapsedTime(&t, r.a, r.b));
+        c->prof_ms[r.cls] += t;
+        c->prof_cnt[r.cls]++;
+        c->prof_pool.push_back(r.a);
+        c->prof_pool.push_back(r.b);
+    }
+    c->prof_pending.clear();
+    for (int k = 0; k < PARM_PROF_N; k++) {
+        if (ms) ms[k] = c->prof_ms[k];
+        if (cnt) cnt[k] = c->prof_cnt[k];
+        c->prof_ms[k] = 0;
+        c->prof_cnt[k] = 0;
+    }
     return 0;
 }
 
