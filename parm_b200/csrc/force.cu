@@ -9,6 +9,7 @@
 // shuffles, then per block, then by one folding block (deterministic), and halved because
 // every pair is visited from both ends.
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -63,7 +64,12 @@ __device__ __forceinline__ void pair_eval(const PairConst &P, double dsq, bool w
     }
 }
 
-template <int KIND, bool ONE_SPECIES, int MODE>
+// TEAM lanes share one atom: lane t of the team takes row entries t, t+TEAM, ... (the team reads
+// TEAM consecutive indices = one or more full 32-byte sectors of the row), U entries per lane are
+// in flight at once (index loads first, then the pos[j] gathers, then the arithmetic), and the
+// team folds its partial force with xor-shuffles. TEAM*U divides 32 so rows (kmax % 32 == 0)
+// are always readable up to the padded end.
+template <int KIND, bool ONE_SPECIES, int MODE, int TEAM, int U>
 __global__ void __launch_bounds__(F_BLOCK)
 k_force(const double4 *__restrict__ pos, const uint32_t *__restrict__ nbr, const uint32_t *__restrict__ cnt, uint32_t kmax,
         const uint8_t *__restrict__ spec, const PairConst *__restrict__ table, int nspecies, PairConst P1, double *f,
@@ -73,33 +79,49 @@ k_force(const double4 *__restrict__ pos, const uint32_t *__restrict__ nbr, const
         for (int q = threadIdx.x; q < nspecies * nspecies; q += blockDim.x) s_table[q] = table[q];
         __syncthreads();
     }
-    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t s = (blockIdx.x * blockDim.x + threadIdx.x) / TEAM;
+    const uint32_t tl = threadIdx.x % TEAM;
     const bool want_obs = MODE != MODE_F;
     double fx = 0, fy = 0, fz = 0;
     double acc[NPART];
     if (want_obs)
 #pragma unroll
         for (int q = 0; q < NPART; q++) acc[q] = 0.0;
-    if (s < n) {
-        const uint32_t my = cnt[s];
-        const double4 pi = pos[s];
-        const uint32_t *col = nbr + ((size_t)(s >> 5) * kmax) * PARM_TILE + (s & 31u);
-        const PairConst *row = ONE_SPECIES ? nullptr : s_table + (int)spec[s] * nspecies;
-#pragma unroll 2
-        for (uint32_t k = 0; k < my; k++) {
-            const uint32_t j = __ldg(col + (size_t)k * PARM_TILE);
-            const double4 pj = ld_pos4(pos + j);
+    const bool valid = s < n;
+    const uint32_t sc = valid ? s : 0;
+    const uint32_t my = valid ? cnt[sc] : 0;
+    const double4 pi = pos[sc];
+    const uint32_t *row = nbr + (size_t)sc * kmax;
+    const PairConst *prow = ONE_SPECIES ? nullptr : s_table + (int)spec[sc] * nspecies;
+    for (uint32_t k0 = tl; k0 < my; k0 += TEAM * U) {
+        uint32_t j[U];
+        bool ok[U];
+        double4 pj[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const uint32_t k = k0 + u * TEAM;
+            ok[u] = k < my;
+            j[u] = ok[u] ? __ldg(row + k) : sc;
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) pj[u] = ld_pos4(pos + j[u]);
+#pragma unroll
+        for (int u = 0; u < U; u++) {
             // OriginBox::diff(atom1->x, atom2->x), box.hpp:103
-            double dx = min_image_fast(pi.x - pj.x, box.L[0], box.invL[0]);
-            double dy = min_image_fast(pi.y - pj.y, box.L[1], box.invL[1]);
-            double dz = min_image_fast(pi.z - pj.z, box.L[2], box.invL[2]);
+            double dx = min_image_fast(pi.x - pj[u].x, box.L[0], box.invL[0]);
+            double dy = min_image_fast(pi.y - pj[u].y, box.L[1], box.invL[1]);
+            double dz = min_image_fast(pi.z - pj[u].z, box.L[2], box.invL[2]);
             double dsq = dx * dx + (dy * dy + dz * dz);
             double scal, e;
             if (ONE_SPECIES) {
                 pair_eval<KIND>(P1, dsq, want_obs, scal, e);
             } else {
-                const PairConst &P = row[__ldg(spec + j)];
+                const PairConst &P = prow[__ldg(spec + j[u])];
                 pair_eval<KIND>(P, dsq, want_obs, scal, e);
+            }
+            if (!ok[u]) { // padding lane (j == self, dsq == 0): contributes nothing
+                scal = 0.0;
+                e = 0.0;
             }
             double gx = dx * scal, gy = dy * scal, gz = dz * scal;
             fx += gx;
@@ -115,7 +137,15 @@ k_force(const double4 *__restrict__ pos, const uint32_t *__restrict__ nbr, const
                 acc[12] += (e > 0.0) ? 1.0 : 0.0;  // overlaps :2140-2151
             }
         }
-        if (MODE != MODE_OBS) {
+    }
+    if (MODE != MODE_OBS) {
+#pragma unroll
+        for (int o = TEAM / 2; o; o >>= 1) {
+            fx += __shfl_xor_sync(0xffffffffu, fx, o);
+            fy += __shfl_xor_sync(0xffffffffu, fy, o);
+            fz += __shfl_xor_sync(0xffffffffu, fz, o);
+        }
+        if (valid && tl == 0) {
             if (accumulate) {
                 f[s] += fx;
                 f[npad + s] += fy;
@@ -165,31 +195,40 @@ __global__ void k_force_fold(const double *__restrict__ partials, uint32_t nbloc
     }
 }
 
-template <int KIND, bool ONE>
+#define FARGS pos, nbr, cnt, kmax, spec, table, nsp, P1, f, n, npad, box, acc, partials
+template <int KIND, bool ONE, int TEAM, int U>
 static cudaError_t launch_mode(int mode, dim3 grid, size_t smem, cudaStream_t st, const double4 *pos, const uint32_t *nbr,
                                const uint32_t *cnt, uint32_t kmax, const uint8_t *spec, const PairConst *table, int nsp,
                                PairConst P1, double *f, uint32_t n, uint32_t npad, BoxDev box, int acc, double *partials) {
     if (mode == MODE_F) {
-        if (smem > 48 * 1024) cudaFuncSetAttribute(k_force<KIND, ONE, MODE_F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        k_force<KIND, ONE, MODE_F><<<grid, F_BLOCK, smem, st>>>(pos, nbr, cnt, kmax, spec, table, nsp, P1, f, n, npad, box, acc, partials);
+        if (smem > 48 * 1024) cudaFuncSetAttribute(k_force<KIND, ONE, MODE_F, TEAM, U>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        k_force<KIND, ONE, MODE_F, TEAM, U><<<grid, F_BLOCK, smem, st>>>(FARGS);
     } else if (mode == MODE_FALL) {
-        if (smem > 48 * 1024) cudaFuncSetAttribute(k_force<KIND, ONE, MODE_FALL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        k_force<KIND, ONE, MODE_FALL><<<grid, F_BLOCK, smem, st>>>(pos, nbr, cnt, kmax, spec, table, nsp, P1, f, n, npad, box, acc, partials);
+        if (smem > 48 * 1024) cudaFuncSetAttribute(k_force<KIND, ONE, MODE_FALL, TEAM, U>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        k_force<KIND, ONE, MODE_FALL, TEAM, U><<<grid, F_BLOCK, smem, st>>>(FARGS);
     } else {
-        if (smem > 48 * 1024) cudaFuncSetAttribute(k_force<KIND, ONE, MODE_OBS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        k_force<KIND, ONE, MODE_OBS><<<grid, F_BLOCK, smem, st>>>(pos, nbr, cnt, kmax, spec, table, nsp, P1, f, n, npad, box, acc, partials);
+        if (smem > 48 * 1024) cudaFuncSetAttribute(k_force<KIND, ONE, MODE_OBS, TEAM, U>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        k_force<KIND, ONE, MODE_OBS, TEAM, U><<<grid, F_BLOCK, smem, st>>>(FARGS);
     }
     return cudaGetLastError();
 }
 
 template <int KIND>
-static cudaError_t launch_kind(bool one, int mode, dim3 grid, size_t smem, cudaStream_t st, const double4 *pos,
+static cudaError_t launch_kind(bool one, int team, int mode, uint32_t natoms, size_t smem, cudaStream_t st, const double4 *pos,
                                const uint32_t *nbr, const uint32_t *cnt, uint32_t kmax, const uint8_t *spec,
                                const PairConst *table, int nsp, PairConst P1, double *f, uint32_t n, uint32_t npad,
                                BoxDev box, int acc, double *partials) {
-    if (one) return launch_mode<KIND, true>(mode, grid, 0, st, pos, nbr, cnt, kmax, spec, table, nsp, P1, f, n, npad, box, acc, partials);
-    return launch_mode<KIND, false>(mode, grid, smem, st, pos, nbr, cnt, kmax, spec, table, nsp, P1, f, n, npad, box, acc, partials);
+    const dim3 grid((unsigned)(((size_t)natoms * team + F_BLOCK - 1) / F_BLOCK));
+    if (one) {
+        if (team == 4) return launch_mode<KIND, true, 4, 2>(mode, grid, 0, st, FARGS);
+        if (team == 16) return launch_mode<KIND, true, 16, 2>(mode, grid, 0, st, FARGS);
+        return launch_mode<KIND, true, 8, 2>(mode, grid, 0, st, FARGS);
+    }
+    if (team == 4) return launch_mode<KIND, false, 4, 2>(mode, grid, smem, st, FARGS);
+    if (team == 16) return launch_mode<KIND, false, 16, 2>(mode, grid, smem, st, FARGS);
+    return launch_mode<KIND, false, 8, 2>(mode, grid, smem, st, FARGS);
 }
+#undef FARGS
 
 // d_out: device pointer to NPART doubles (E, virial, stress[9], contacts, overlaps) or NULL
 static int launch_forces(parm_inter *it, int mode, bool accumulate, double *d_out) {
@@ -202,7 +241,16 @@ static int launch_forces(parm_inter *it, int mode, bool accumulate, double *d_ou
         if (d_out) CK(cudaMemsetAsync(d_out, 0, NPART * 8, c->stream));
         return 0;
     }
-    const uint32_t nblocks = (c->n + F_BLOCK - 1) / F_BLOCK;
+    // lanes per atom: enough entries per lane to keep its loop busy, few enough to fill the last pass
+    int team = 8;
+    {
+        double mean = (double)nl->total_full / (double)(c->n ? c->n : 1);
+        if (mean < 24) team = 4;
+        static int forced = -1;
+        if (forced < 0) { const char *e = getenv("PARM_B200_TEAM"); forced = e ? atoi(e) : 0; }
+        if (forced == 4 || forced == 8 || forced == 16) team = forced;
+    }
+    const uint32_t nblocks = (uint32_t)(((size_t)c->n * team + F_BLOCK - 1) / F_BLOCK);
     if (c->n == 0) {
         if (d_out) CK(cudaMemsetAsync(d_out, 0, NPART * 8, c->stream));
         return 0;
@@ -217,7 +265,7 @@ static int launch_forces(parm_inter *it, int mode, bool accumulate, double *d_ou
     size_t smem = one ? 0 : (size_t)it->nspecies * it->nspecies * sizeof(PairConst);
     PairConst P1 = it->h_table[0];
     cudaError_t e;
-#define ARGS one, mode, dim3(nblocks), smem, c->stream, c->pos, nl->nbr, nl->cnt, nl->kmax, it->d_spec, it->d_table, \
+#define ARGS one, team, mode, c->n, smem, c->stream, c->pos, nl->nbr, nl->cnt, nl->kmax, it->d_spec, it->d_table, \
              it->nspecies, P1, c->f, c->n, c->npad, c->box, accumulate ? 1 : 0, it->d_partials
     switch (it->kind) {
         case PARM_PAIR_LJREPULSE: e = launch_kind<PARM_PAIR_LJREPULSE>(ARGS); break;

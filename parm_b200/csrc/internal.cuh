@@ -15,7 +15,6 @@
 
 #include "../../include/parm_b200.h"
 
-#define PARM_TILE 32u         // atoms per neighbour-list tile (= warp)
 #define PARM_MAX_SPECIES 32   // distinct per-atom parameter tuples per interaction
 
 void parm_set_error(const char *fmt, ...);
@@ -90,11 +89,11 @@ struct parm_ctx {
 int parm_prof_begin(parm_ctx *c, int cls);
 int parm_prof_end(parm_ctx *c);
 
-struct NlistFlags { // pinned, device-written
+struct NlistFlags { // device-written; a pinned host mirror receives need_rebuild / top2
     int need_rebuild;
-    uint32_t overflow_max;
-    unsigned long long total;
-    uint32_t maxcnt;
+    uint32_t maxcnt;              // longest row of the last build
+    unsigned long long total;     // sum of row lengths of the last build
+    unsigned long long xmax_bits; // bit pattern of max |coordinate| seen by the last binning pass
     double top2[2];
 };
 
@@ -103,10 +102,12 @@ struct parm_nlist {
     double skin;
     std::vector<double> h_diam; // by AtomVec index; < 0: not a member
     bool have_diam;
-    double maxdiam;
+    double maxdiam, mindiam;
     double *d_diam_id;   // by AtomVec index
     double *d_diam;      // by slot
     double *xlast;       // [3][npad] by slot: lastlocs (trackers.hpp:165)
+    double4 *pw;         // wrapped copy (x,y,z in [0,L)) + conservative half threshold, rebuilt with the list
+    int cell_sub;        // cells per r_list (1 or 2)
     uint32_t updatenum;
     bool ignorechanged;
     // cell grid
@@ -116,7 +117,7 @@ struct parm_nlist {
     uint32_t cell_start_cap;
     void *sort_temp;
     size_t sort_temp_bytes;
-    // list: nbr[tile][k][lane], cnt[slot]
+    // list: row-major nbr[slot * kmax + k], cnt[slot]; kmax is a multiple of 32
     uint32_t kmax;
     uint32_t *nbr;
     size_t nbr_cap_entries;

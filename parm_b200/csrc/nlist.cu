@@ -1,14 +1,19 @@
 // NeighborList on the device: skin-drift trigger + cell-list pair build.
-// Replaces NeighborList::update_list (trackers.cpp:19-85), which is an O(N^2) double
-// loop on the CPU, with: cell binning -> radix sort by cell index -> slot re-ordering ->
-// per-atom scan of the 3^D cell stencil with the reference's exact predicate
-//     box->diff(x_i, x_j).norm() < (diam_i + diam_j)/2 + skin     (trackers.cpp:65-66)
-// evaluated bit-for-bit (no FMA contraction, e0+(e1+e2) association, IEEE sqrt), so the
-// pair SET equals the reference's. The device list is a FULL list (both i->j and j->i)
-// stored in warp tiles nbr[tile][k][lane] so the force kernel needs no atomics.
+// Replaces NeighborList::update_list (trackers.cpp:19-85), an O(N^2) double loop on the CPU, with
+//   cell binning -> radix sort by cell index -> slot re-ordering -> warp-cooperative stencil scan.
+// The pair SET equals the reference's bit for bit: a pair is listed iff
+//     box->diff(x_i, x_j).norm() < (diam_i + diam_j)/2 + skin            (trackers.cpp:65-66)
+// evaluated with the reference's arithmetic (no FMA contraction, e0+(e1+e2), IEEE sqrt, IEEE
+// remainder). To keep that off the hot loop, candidates are first classified on wrapped
+// coordinates in plain fp64: clearly inside / clearly outside / within a relative band delta of
+// the threshold; only the band (a ~1e-9 fraction of the tests) runs the exact predicate.
+// The device list is a FULL list (i->j and j->i), row-major: nbr[slot * kmax + k], so the force
+// kernel needs no atomics and reads its rows coalesced.
 #include <algorithm>
 #include <cub/device/device_radix_sort.cuh>
 #include <math.h>
+#include <stddef.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "drift.cuh"
@@ -26,25 +31,38 @@ struct GridDev {
     double scale[3]; // nc / L
 };
 
-// ---- K4a: cell index from the wrapped coordinate --------------------------------
+// ---- K4a: cell index from the wrapped coordinate; also max |x| (bounds the wrap rounding) ----
 // (nearest reference analogue: Grid::get_loc, trackers.cpp:192-219)
 __global__ void k_cell_id(const double4 *__restrict__ pos, uint32_t n, BoxDev box, GridDev g, uint32_t *cell_id,
-                          uint32_t *iota) {
+                          uint32_t *iota, NlistFlags *flags) {
+    double xm = 0.0;
     for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < n; s += gridDim.x * blockDim.x) {
         double4 p = pos[s];
         double x[3] = {p.x, p.y, p.z};
         uint32_t c = 0;
 #pragma unroll
         for (int d = 0; d < 3; d++) {
-            double w = x[d] - box.L[d] * floor(x[d] * box.invL[d]); // ~[0, L)
+            double w = x[d] - box.L[d] * floor(x[d] * box.invL[d]); // ~[0, L]
             int k = (int)floor(w * g.scale[d]);
             if (!(k >= 0)) k = 0; // also catches NaN
             if (k >= g.nc[d]) k = g.nc[d] - 1;
             c = c * (uint32_t)g.nc[d] + (uint32_t)k;
+            double ax = fabs(x[d]);
+            if (ax > xm && ax < 1e300) xm = ax;
         }
         cell_id[s] = c;
         iota[s] = s;
     }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) xm = fmax(xm, __shfl_xor_sync(0xffffffffu, xm, o));
+    if ((threadIdx.x & 31) == 0 && xm > 0.0) atomicMax(&flags->xmax_bits, (unsigned long long)__double_as_longlong(xm));
+}
+
+// relative half-width of the "evaluate exactly" band around the threshold: rounding of the wrapped
+// coordinates (~ulp(xmax + L)) relative to the smallest threshold, plus slack for the arithmetic
+__device__ __forceinline__ double band_delta(const NlistFlags *flags, double lmax, double thr_min) {
+    double xmax = __longlong_as_double((long long)flags->xmax_bits);
+    return 1e-9 + 2e-14 * (xmax + lmax) / thr_min;
 }
 
 // ---- K4b: apply the sort permutation to every per-slot array -----------------------
@@ -52,7 +70,9 @@ __global__ void k_permute(const uint32_t *__restrict__ perm, uint32_t n, uint32_
                           const double *__restrict__ v, const double *__restrict__ a, const double *__restrict__ f,
                           const uint32_t *__restrict__ order, double4 *pos_o, double *v_o, double *a_o, double *f_o,
                           uint32_t *order_o, uint32_t *slot_of, const double *__restrict__ diam_id, double *diam,
-                          double *xlast) {
+                          double *xlast, double4 *pw, BoxDev box, double half_skin, double lmax, double thr_min,
+                          const NlistFlags *flags) {
+    const double delta = band_delta(flags, lmax, thr_min);
     for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < n; s += gridDim.x * blockDim.x) {
         uint32_t o = perm[s];
         double4 p = pos[o];
@@ -67,7 +87,17 @@ __global__ void k_permute(const uint32_t *__restrict__ perm, uint32_t n, uint32_
         uint32_t id = order[o];
         order_o[s] = id;
         slot_of[id] = s;
-        diam[s] = diam_id[id];
+        const double dm = diam_id[id];
+        diam[s] = dm;
+        // wrapped copy for the build (same formula as k_cell_id, so it lies in the atom's cell);
+        // w = upper half threshold g_i (1 + delta): g_i + g_j = ((d_i + d_j)/2 + skin)(1 + delta);
+        // NaN marks atoms that were never add()ed to the list
+        double4 q;
+        q.x = p.x - box.L[0] * floor(p.x * box.invL[0]);
+        q.y = p.y - box.L[1] * floor(p.y * box.invL[1]);
+        q.z = p.z - box.L[2] * floor(p.z * box.invL[2]);
+        q.w = dm >= 0.0 ? (0.5 * dm + half_skin) * (1.0 + delta) : __longlong_as_double(0x7ff8000000000000LL);
+        pw[s] = q;
         // lastlocs[i] = a1->x (trackers.cpp:61)
         xlast[s] = p.x;
         xlast[npad + s] = p.y;
@@ -86,64 +116,133 @@ __global__ void k_cell_start(const uint32_t *__restrict__ cid, uint32_t n, uint3
 }
 
 // ---- K5: neighbour build ----------------------------------------------------------
+// Cells have edge >= r_list/sub, the stencil is (2 sub + 1)^D cells.
 struct StencilDev {
-    int noff[3];
-    int off[3][3];
+    int sub;     // cells per r_list
+    int full[3]; // 1: nc >= 2 sub + 1 (offsets -sub..sub, unique images); 0: visit every cell of that axis once
 };
 
-// One thread per atom (slot). Lanes of a warp are consecutive slots, i.e. atoms of the same
-// or adjacent cells, so the candidate loads pos[j], diam[j] are warp-wide broadcasts; each
-// lane appends to its own column of the tile, so appends of a warp coalesce.
-__global__ void __launch_bounds__(128)
-k_build(const double4 *__restrict__ pos, const double *__restrict__ diam, const uint32_t *__restrict__ cid,
-        const uint32_t *__restrict__ cell_start, uint32_t n, BoxDev box, GridDev g, StencilDev st, double skin,
-        uint32_t kmax, uint32_t *__restrict__ nbr, uint32_t *__restrict__ cnt, NlistFlags *flags) {
-    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+// Exact reference predicate (trackers.cpp:65-66) on the UNWRAPPED coordinates.
+__device__ __noinline__ bool pair_pred_exact(const double4 *__restrict__ pos, const double *__restrict__ diam,
+                                             uint32_t i, uint32_t j, BoxDev box, double skin) {
+    const double4 pi = pos[i], pj = pos[j];
+    const double di = diam[i], dj = diam[j];
+    // box->diff(a1->x, a2->x): remainder(r1 - r2, L) per component (box.hpp:69-72,103)
+    double rx = min_image_exact(__dsub_rn(pi.x, pj.x), box.L[0], box.invL[0], box.halfL[0]);
+    double ry = min_image_exact(__dsub_rn(pi.y, pj.y), box.L[1], box.invL[1], box.halfL[1]);
+    double rz = min_image_exact(__dsub_rn(pi.z, pj.z), box.L[2], box.invL[2], box.halfL[2]);
+    // .norm(): sqrt(e0 + (e1 + e2)), no contraction
+    double dsq = __dadd_rn(__dmul_rn(rx, rx), __dadd_rn(__dmul_rn(ry, ry), __dmul_rn(rz, rz)));
+    // flt diam = (diameters[i] + diameters[j]) / 2;  ... < (diam + skin)
+    double thr = __dadd_rn(__dmul_rn(__dadd_rn(di, dj), 0.5), skin);
+    return __dsqrt_rn(dsq) < thr;
+}
+
+#define BUILD_WARPS 4
+// Warp-cooperative build: one warp owns a tile of 32 consecutive slots (atoms of one or two
+// neighbouring cells). For every distinct cell in the tile it walks that cell's stencil; the 32
+// lanes load 32 consecutive candidates at once (coalesced), then the warp loops over the tile's
+// atoms of that cell (their wrapped coordinates are broadcast from shared memory), each lane tests
+// its candidate, and the survivors are compacted with ballot + popc into the atom's row.
+template <bool SMALLBOX>
+__global__ void __launch_bounds__(BUILD_WARPS * 32)
+k_build(const double4 *__restrict__ pos, const double4 *__restrict__ pw, const double *__restrict__ diam,
+        const uint32_t *__restrict__ cid, const uint32_t *__restrict__ cell_start, uint32_t n, BoxDev box, GridDev g,
+        StencilDev st, double skin, double lmax, double thr_min, uint32_t kmax, uint32_t *__restrict__ nbr,
+        uint32_t *__restrict__ cnt, NlistFlags *flags) {
+    __shared__ double4 s_w[BUILD_WARPS][32];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const uint32_t tile = blockIdx.x * BUILD_WARPS + wib;
+    const uint32_t base_i = tile * 32u;
+    const uint32_t i = base_i + lane;
+    const double nan = __longlong_as_double(0x7ff8000000000000LL);
+    double4 wi = make_double4(0, 0, 0, nan);
+    uint32_t ci = 0xffffffffu;
+    if (i < n) {
+        wi = pw[i];
+        ci = cid[i];
+    }
+    const bool member = wi.w == wi.w;
+    s_w[wib][lane] = wi;
+    __syncwarp();
+    // a test is decided by the fast arithmetic when dsq is outside [lo, 1) * thr_hi^2
+    const double delta = band_delta(flags, lmax, thr_min);
+    const double lo = ((1.0 - delta) / (1.0 + delta)) * ((1.0 - delta) / (1.0 + delta));
+    const unsigned lt = (1u << lane) - 1u;
     uint32_t count = 0;
-    if (s < n) {
-        const double4 pi = pos[s];
-        const double di = diam[s];
-        if (di >= 0.0) {
-            uint32_t c = cid[s];
-            int cz = (int)(c % (uint32_t)g.nc[2]);
-            uint32_t t = c / (uint32_t)g.nc[2];
-            int cy = (int)(t % (uint32_t)g.nc[1]);
-            int cx = (int)(t / (uint32_t)g.nc[1]);
-            uint32_t *col = nbr + ((size_t)(s >> 5) * kmax) * PARM_TILE + (s & 31u);
-            for (int ix = 0; ix < st.noff[0]; ix++) {
-                int x2 = cx + st.off[0][ix];
-                x2 += x2 < 0 ? g.nc[0] : (x2 >= g.nc[0] ? -g.nc[0] : 0);
-                for (int iy = 0; iy < st.noff[1]; iy++) {
-                    int y2 = cy + st.off[1][iy];
-                    y2 += y2 < 0 ? g.nc[1] : (y2 >= g.nc[1] ? -g.nc[1] : 0);
-                    for (int iz = 0; iz < st.noff[2]; iz++) {
-                        int z2 = cz + st.off[2][iz];
-                        z2 += z2 < 0 ? g.nc[2] : (z2 >= g.nc[2] ? -g.nc[2] : 0);
-                        uint32_t c2 = ((uint32_t)x2 * (uint32_t)g.nc[1] + (uint32_t)y2) * (uint32_t)g.nc[2] + (uint32_t)z2;
-                        uint32_t jb = cell_start[c2], je = cell_start[c2 + 1];
-                        for (uint32_t j = jb; j < je; j++) {
-                            const double4 pj = pos[j];
-                            const double dj = diam[j];
-                            if (j == s || !(dj >= 0.0)) continue;
-                            // box->diff(a1->x, a2->x): remainder(r1 - r2, L) per component (box.hpp:69-72,103)
-                            double rx = min_image_exact(__dsub_rn(pi.x, pj.x), box.L[0], box.invL[0], box.halfL[0]);
-                            double ry = min_image_exact(__dsub_rn(pi.y, pj.y), box.L[1], box.invL[1], box.halfL[1]);
-                            double rz = min_image_exact(__dsub_rn(pi.z, pj.z), box.L[2], box.invL[2], box.halfL[2]);
-                            // .norm(): sqrt(e0 + (e1 + e2)), no contraction
-                            double dsq = __dadd_rn(__dmul_rn(rx, rx), __dadd_rn(__dmul_rn(ry, ry), __dmul_rn(rz, rz)));
-                            // flt diam = (diameters[i] + diameters[j]) / 2;  ... < (diam + skin)
-                            double thr = __dadd_rn(__dmul_rn(__dadd_rn(di, dj), 0.5), skin);
-                            if (__dsqrt_rn(dsq) < thr) {
-                                if (count < kmax) col[(size_t)count * PARM_TILE] = j;
-                                count++;
+    unsigned done = __ballot_sync(0xffffffffu, !member);
+    while (done != 0xffffffffu) {
+        const int leader = __ffs(~done) - 1;
+        const uint32_t cur = __shfl_sync(0xffffffffu, ci, leader);
+        const unsigned same = __ballot_sync(0xffffffffu, ci == cur);
+        const unsigned act = same & ~done; // tile atoms of this cell that are list members
+        done |= same;
+        const int cz = (int)(cur % (uint32_t)g.nc[2]);
+        const uint32_t t = cur / (uint32_t)g.nc[2];
+        const int cy = (int)(t % (uint32_t)g.nc[1]);
+        const int cx = (int)(t / (uint32_t)g.nc[1]);
+        const int x0 = st.full[0] ? cx - st.sub : 0, x1 = st.full[0] ? cx + st.sub : g.nc[0] - 1;
+        const int y0 = st.full[1] ? cy - st.sub : 0, y1 = st.full[1] ? cy + st.sub : g.nc[1] - 1;
+        const int z0 = st.full[2] ? cz - st.sub : 0, z1 = st.full[2] ? cz + st.sub : g.nc[2] - 1;
+        for (int xx = x0; xx <= x1; xx++) {
+            int x2 = xx;
+            double sx = 0.0; // image shift of the candidates of this cell relative to the tile atoms
+            if (x2 < 0) { x2 += g.nc[0]; sx = -box.L[0]; }
+            else if (x2 >= g.nc[0]) { x2 -= g.nc[0]; sx = box.L[0]; }
+            for (int yy = y0; yy <= y1; yy++) {
+                int y2 = yy;
+                double sy = 0.0;
+                if (y2 < 0) { y2 += g.nc[1]; sy = -box.L[1]; }
+                else if (y2 >= g.nc[1]) { y2 -= g.nc[1]; sy = box.L[1]; }
+                const uint32_t rowbase = ((uint32_t)x2 * (uint32_t)g.nc[1] + (uint32_t)y2) * (uint32_t)g.nc[2];
+                // cells along z are contiguous in slot order: at most 3 segments (below 0, inside, above nc-1)
+                for (int seg = 0; seg < 3; seg++) {
+                    int za, zb;
+                    double sz = 0.0;
+                    if (seg == 0) { za = z0 < 0 ? z0 + g.nc[2] : 1; zb = z0 < 0 ? g.nc[2] - 1 : 0; sz = -box.L[2]; }
+                    else if (seg == 1) { za = z0 < 0 ? 0 : z0; zb = z1 >= g.nc[2] ? g.nc[2] - 1 : z1; }
+                    else { za = z1 >= g.nc[2] ? 0 : 1; zb = z1 >= g.nc[2] ? z1 - g.nc[2] : 0; sz = box.L[2]; }
+                    if (za > zb) continue;
+                    const uint32_t jb = cell_start[rowbase + (uint32_t)za], je = cell_start[rowbase + (uint32_t)zb + 1];
+                    for (uint32_t jbase = jb; jbase < je; jbase += 32) {
+                        const uint32_t j = jbase + lane;
+                        double4 wj = make_double4(0, 0, 0, nan);
+                        if (j < je) wj = pw[j];
+                        wj.x += sx;
+                        wj.y += sy;
+                        wj.z += sz;
+                        unsigned m = act;
+                        while (m) {
+                            const int b = __ffs(m) - 1;
+                            m &= m - 1;
+                            const double4 a = s_w[wib][b];
+                            double dx = a.x - wj.x, dy = a.y - wj.y, dz = a.z - wj.z;
+                            if (SMALLBOX) { // some axis has too few cells for unique images: fold explicitly
+                                dx = min_image_fast(dx, box.L[0], box.invL[0]);
+                                dy = min_image_fast(dy, box.L[1], box.invL[1]);
+                                dz = min_image_fast(dz, box.L[2], box.invL[2]);
+                            }
+                            const double dsq = fma(dx, dx, fma(dy, dy, dz * dz));
+                            const double thr = a.w + wj.w; // NaN for non-members / padding lanes
+                            const double thr2 = thr * thr;
+                            bool pass = dsq < thr2 && j != base_i + (uint32_t)b;
+                            if (pass && !(dsq < thr2 * lo)) pass = pair_pred_exact(pos, diam, base_i + b, j, box, skin);
+                            const unsigned bal = __ballot_sync(0xffffffffu, pass);
+                            if (bal) {
+                                const uint32_t cb = __shfl_sync(0xffffffffu, count, b);
+                                if (pass) {
+                                    const uint32_t k = cb + __popc(bal & lt);
+                                    if (k < kmax) nbr[(size_t)(base_i + b) * kmax + k] = j;
+                                }
+                                if (lane == b) count += __popc(bal);
                             }
                         }
                     }
                 }
             }
         }
-        cnt[s] = count;
     }
+    if (i < n) cnt[i] = count;
     // totals: integer atomics are order independent, so the result is deterministic
     unsigned long long wsum = count;
     uint32_t wmax = count;
@@ -152,7 +251,7 @@ k_build(const double4 *__restrict__ pos, const double *__restrict__ diam, const 
         wsum += __shfl_xor_sync(0xffffffffu, wsum, o);
         wmax = max(wmax, __shfl_xor_sync(0xffffffffu, wmax, o));
     }
-    if ((threadIdx.x & 31) == 0 && wmax) {
+    if (lane == 0 && wmax) {
         atomicAdd(&flags->total, wsum);
         atomicMax(&flags->maxcnt, wmax);
     }
@@ -192,6 +291,9 @@ extern "C" int parm_nlist_create(parm_ctx *c, double skin, parm_nlist **out) {
     CK(cudaMalloc(&nl->d_diam_id, np * 8));
     CK(cudaMalloc(&nl->d_diam, np * 8));
     CK(cudaMalloc(&nl->xlast, 3 * np * 8));
+    CK(cudaMalloc(&nl->pw, np * sizeof(double4)));
+    nl->cell_sub = 1;
+    if (const char *e = getenv("PARM_B200_CELL_SUB")) nl->cell_sub = atoi(e) == 2 ? 2 : 1;
     CK(cudaMemsetAsync(nl->xlast, 0, 3 * np * 8, c->stream));
     CK(cudaMalloc(&nl->cell_id, np * 4));
     CK(cudaMalloc(&nl->cell_id_sorted, np * 4));
@@ -221,7 +323,7 @@ extern "C" int parm_nlist_destroy(parm_nlist *nl) {
     parm_ctx *c = nl->ctx;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
-    void *ptrs[] = {nl->d_diam_id, nl->d_diam, nl->xlast, nl->cell_id, nl->cell_id_sorted, nl->perm, nl->iota,
+    void *ptrs[] = {nl->pw, nl->d_diam_id, nl->d_diam, nl->xlast, nl->cell_id, nl->cell_id_sorted, nl->perm, nl->iota,
                     nl->cell_start, nl->sort_temp, nl->nbr, nl->cnt, nl->d_top2, nl->d_counter, nl->d_flags};
     for (void *p : ptrs)
         if (p) cudaFree(p);
@@ -239,7 +341,7 @@ extern "C" int parm_nlist_set_diameters(parm_nlist *nl, const double *diam) {
     if (!nl || !diam) { parm_set_error("parm_nlist_set_diameters: NULL argument"); return PARM_ERR_INVALID; }
     parm_ctx *c = nl->ctx;
     CK(cudaSetDevice(c->device));
-    double maxd = 0;
+    double maxd = 0, mind = INFINITY;
     bool any = false;
     for (uint32_t i = 0; i < c->n; i++) {
         double d = diam[i];
@@ -247,11 +349,13 @@ extern "C" int parm_nlist_set_diameters(parm_nlist *nl, const double *diam) {
             nl->h_diam[i] = d;
             any = true;
             if (d > maxd) maxd = d;
+            if (d < mind) mind = d;
         } else
             nl->h_diam[i] = -1.0;
     }
     nl->have_diam = any;
     nl->maxdiam = maxd;
+    nl->mindiam = any ? mind : 0.0;
     if (c->n) {
         CK(cudaMemcpyAsync(nl->d_diam_id, nl->h_diam.data(), (size_t)c->n * 8, cudaMemcpyHostToDevice, c->stream));
         k_gather_by_order_d<<<grid_for(c, c->n, 256), 256, 0, c->stream>>>(nl->d_diam_id, c->order, c->n, nl->d_diam);
@@ -264,8 +368,8 @@ extern "C" int parm_nlist_set_diameters(parm_nlist *nl, const double *diam) {
 
 static int alloc_nbr(parm_nlist *nl, uint32_t kmax) {
     parm_ctx *c = nl->ctx;
-    size_t ntiles = c->npad / PARM_TILE;
-    size_t need = ntiles * (size_t)kmax * PARM_TILE;
+    kmax = (kmax + 31u) & ~31u; // rows start on 128-byte boundaries
+    size_t need = (size_t)c->npad * kmax;
     if (need > nl->nbr_cap_entries) {
         if (nl->nbr) cudaFree(nl->nbr);
         nl->nbr = 0;
@@ -281,23 +385,24 @@ int parm_nlist_rebuild(parm_nlist *nl) {
     parm_ctx *c = nl->ctx;
     CK(cudaSetDevice(c->device));
     if (!c->box_set) { parm_set_error("NeighborList update before the box was set"); return PARM_ERR_INVALID; }
-    nl->updatenum++;          // trackers.cpp:56-57
+    nl->updatenum++; // trackers.cpp:56-57
     nl->ignorechanged = false;
     nl->rebuilds++;
     const uint32_t n = c->n;
     if (n == 0) { nl->total_full = 0; nl->maxcnt = 0; return 0; }
 
-    // --- cell grid: cells no smaller than the largest possible pair threshold
-    const double rlist = (nl->maxdiam + nl->skin) * (1.0 + 1e-9) + 1e-12;
+    // --- cell grid: cells no smaller than the largest possible pair threshold / sub
+    const double rlist = (nl->maxdiam + nl->skin) * (1.0 + 1e-6) + 1e-12;
     GridDev g;
     StencilDev st;
     uint64_t ncell = 1;
     const uint64_t cell_cap = std::max<uint64_t>(64, 4ull * n);
+    const int sub = nl->cell_sub;
     for (int d = 0; d < 3; d++) {
         int k = 1;
         if (d < c->D) {
-            double q = floor(c->box.L[d] / rlist);
-            k = q < 1 ? 1 : (q > 1024 ? 1024 : (int)q);
+            double q = floor(c->box.L[d] * sub / rlist);
+            k = q < 1 ? 1 : (q > 2048 ? 2048 : (int)q);
         }
         g.nc[d] = k;
     }
@@ -310,13 +415,15 @@ int parm_nlist_rebuild(parm_nlist *nl) {
             if (g.nc[d] > g.nc[big]) big = d;
         g.nc[big] = (g.nc[big] + 1) / 2;
     }
+    st.sub = sub;
+    bool smallbox = false;
+    double lmax = 0;
     for (int d = 0; d < 3; d++) {
         g.scale[d] = g.nc[d] / c->box.L[d];
-        int k = g.nc[d];
-        if (k >= 3) { st.noff[d] = 3; st.off[d][0] = -1; st.off[d][1] = 0; st.off[d][2] = 1; }
-        else if (k == 2) { st.noff[d] = 2; st.off[d][0] = 0; st.off[d][1] = 1; st.off[d][2] = 0; }
-        else { st.noff[d] = 1; st.off[d][0] = 0; st.off[d][1] = 0; st.off[d][2] = 0; }
-        nl->nc[d] = k;
+        st.full[d] = (g.nc[d] >= 2 * sub + 1) ? 1 : 0;
+        if (!st.full[d] && d < c->D) smallbox = true;
+        nl->nc[d] = g.nc[d];
+        if (d < c->D) lmax = std::max(lmax, c->box.L[d]);
     }
     nl->ncell = (uint32_t)ncell;
     if (nl->ncell + 2 > nl->cell_start_cap) {
@@ -325,10 +432,13 @@ int parm_nlist_rebuild(parm_nlist *nl) {
         nl->cell_start_cap = nl->ncell + 2 + nl->ncell / 4;
         CK(cudaMalloc(&nl->cell_start, (size_t)nl->cell_start_cap * 4));
     }
+    double thr_min = nl->mindiam + nl->skin;
+    if (!(thr_min > 1e-300)) thr_min = 1e-300;
 
     PTRY(parm_prof_begin(c, PARM_PROF_REBUILD));
+    CK(cudaMemsetAsync(nl->d_flags, 0, sizeof(NlistFlags), c->stream));
     // --- bin, sort by cell index (stable LSD radix sort), re-order every per-slot array
-    k_cell_id<<<grid_for(c, n, 256), 256, 0, c->stream>>>(c->pos, n, c->box, g, nl->cell_id, nl->iota);
+    k_cell_id<<<grid_for(c, n, 256), 256, 0, c->stream>>>(c->pos, n, c->box, g, nl->cell_id, nl->iota, nl->d_flags);
     CK_LAUNCH(c);
     int end_bit = 1;
     while ((1ull << end_bit) < ncell) end_bit++;
@@ -347,7 +457,8 @@ int parm_nlist_rebuild(parm_nlist *nl) {
     parm_count_launch(c, 3);
     k_permute<<<grid_for(c, n, 256), 256, 0, c->stream>>>(nl->perm, n, c->npad, c->pos, c->v, c->a, c->f, c->order,
                                                           c->pos_alt, c->v_alt, c->a_alt, c->f_alt, c->order_alt,
-                                                          c->slot_of, nl->d_diam_id, nl->d_diam, nl->xlast);
+                                                          c->slot_of, nl->d_diam_id, nl->d_diam, nl->xlast, nl->pw,
+                                                          c->box, 0.5 * nl->skin, lmax, thr_min, nl->d_flags);
     CK_LAUNCH(c);
     std::swap(c->pos, c->pos_alt);
     std::swap(c->v, c->v_alt);
@@ -365,13 +476,22 @@ int parm_nlist_rebuild(parm_nlist *nl) {
         double rl = nl->maxdiam + nl->skin;
         double sphere = c->D == 3 ? 4.18879020478639 * rl * rl * rl : 3.14159265358979 * rl * rl;
         double est = (double)n / vol * sphere;
-        uint32_t k0 = (uint32_t)std::min<double>(std::max(16.0, 1.3 * est + 16.0), (double)std::max<uint32_t>(n, 2u) - 1.0);
+        uint32_t k0 = (uint32_t)std::min<double>(std::max(16.0, 1.25 * est + 12.0), (double)std::max<uint32_t>(n, 2u) - 1.0);
         PTRY(alloc_nbr(nl, std::max<uint32_t>(k0, 1u)));
     }
+    const unsigned ntiles = (n + 31) / 32;
+    const unsigned nblocks = (ntiles + BUILD_WARPS - 1) / BUILD_WARPS;
     for (int attempt = 0; attempt < 8; attempt++) {
-        CK(cudaMemsetAsync(nl->d_flags, 0, sizeof(NlistFlags), c->stream));
-        k_build<<<(n + 127) / 128, 128, 0, c->stream>>>(c->pos, nl->d_diam, nl->cell_id_sorted, nl->cell_start, n, c->box, g,
-                                                       st, nl->skin, nl->kmax, nl->nbr, nl->cnt, nl->d_flags);
+        if (attempt) CK(cudaMemsetAsync((char *)nl->d_flags + offsetof(NlistFlags, maxcnt), 0,
+                                        offsetof(NlistFlags, xmax_bits) - offsetof(NlistFlags, maxcnt), c->stream));
+        if (smallbox)
+            k_build<true><<<nblocks, BUILD_WARPS * 32, 0, c->stream>>>(c->pos, nl->pw, nl->d_diam, nl->cell_id_sorted,
+                                                                      nl->cell_start, n, c->box, g, st, nl->skin, lmax,
+                                                                      thr_min, nl->kmax, nl->nbr, nl->cnt, nl->d_flags);
+        else
+            k_build<false><<<nblocks, BUILD_WARPS * 32, 0, c->stream>>>(c->pos, nl->pw, nl->d_diam, nl->cell_id_sorted,
+                                                                       nl->cell_start, n, c->box, g, st, nl->skin, lmax,
+                                                                       thr_min, nl->kmax, nl->nbr, nl->cnt, nl->d_flags);
         CK_LAUNCH(c);
         if (attempt == 0) PTRY(parm_prof_end(c));
         CK(cudaMemcpyAsync(nl->h_flags, nl->d_flags, sizeof(NlistFlags), cudaMemcpyDeviceToHost, c->stream));
@@ -429,8 +549,7 @@ extern "C" int parm_nlist_download_pairs(parm_nlist *nl, uint32_t *first, uint32
     if (cap < np) { parm_set_error("parm_nlist_download_pairs: capacity %llu < %llu pairs", (unsigned long long)cap, (unsigned long long)np); return PARM_ERR_INVALID; }
     if (np == 0 || nl->updatenum == 0) return 0;
     const uint32_t n = c->n;
-    size_t ntiles = c->npad / PARM_TILE;
-    std::vector<uint32_t> h_cnt(c->npad), h_order(c->npad), h_slot(c->npad), h_nbr(ntiles * nl->kmax * PARM_TILE);
+    std::vector<uint32_t> h_cnt(c->npad), h_order(c->npad), h_slot(c->npad), h_nbr((size_t)n * nl->kmax);
     CK(cudaMemcpyAsync(h_cnt.data(), nl->cnt, (size_t)c->npad * 4, cudaMemcpyDeviceToHost, c->stream));
     CK(cudaMemcpyAsync(h_order.data(), c->order, (size_t)c->npad * 4, cudaMemcpyDeviceToHost, c->stream));
     CK(cudaMemcpyAsync(h_slot.data(), c->slot_of, (size_t)c->npad * 4, cudaMemcpyDeviceToHost, c->stream));
@@ -441,9 +560,9 @@ extern "C" int parm_nlist_download_pairs(parm_nlist *nl, uint32_t *first, uint32
     for (uint32_t i = 0; i < n; i++) { // reference order: i ascending, j < i ascending (trackers.cpp:59-68)
         uint32_t s = h_slot[i];
         js.clear();
-        const uint32_t *col = h_nbr.data() + ((size_t)(s >> 5) * nl->kmax) * PARM_TILE + (s & 31u);
+        const uint32_t *row = h_nbr.data() + (size_t)s * nl->kmax;
         for (uint32_t q = 0; q < h_cnt[s]; q++) {
-            uint32_t j = h_order[col[(size_t)q * PARM_TILE]];
+            uint32_t j = h_order[row[q]];
             if (j < i) js.push_back(j);
         }
         std::sort(js.begin(), js.end());
