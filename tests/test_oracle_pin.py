@@ -1,0 +1,124 @@
+"""CPU-only: pins the oracles.
+
+1. oracle/parm_oracle.c (the plain-C restatement) must reproduce, bit for bit, every golden
+   fixture in tests/golden/ -- those were produced by the UNMODIFIED reference sources compiled
+   into oracle/_ref (tests/golden/make_golden.py).
+2. Where the compiled reference is present (this container, and the GPU box via the prebuilt .so)
+   it is re-run and must reproduce the fixtures too, and agree with the port on fresh inputs.
+3. The cell-list pair finder used for large N equals NeighborList::update_list(true).
+4. The reference's own hot-path test (pyparm/tests.py:284-317) holds on the oracle.
+"""
+import glob
+import math
+import os
+
+import numpy as np
+import pytest
+
+from parm_b200 import workloads as W
+from parity_util import backends, cpu_system
+
+GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
+
+
+def load(path):
+    d = dict(np.load(path))
+    w = {k: d[k] for k in ("L", "x", "v", "m", "params", "types", "eps_table")}
+    for k in ("ndim", "kind", "integrator"):
+        w[k] = int(d[k])
+    for k in ("skin", "dt"):
+        w[k] = float(d[k])
+    for k in ("damping", "T"):
+        if k in d:
+            w[k] = float(d[k])
+    return w, d
+
+
+def replay(backend, w, d):
+    s = cpu_system(backend, w, collection=True)
+    out = {}
+    out["pairs_first"], out["pairs_last"] = s.pairs()
+    f, p = s.forces_and_pressure()
+    out["forces"], out["virial"] = f, np.asarray(p)
+    out["energy"] = np.asarray(s.inter_energy())
+    out["stress"] = s.inter_stress()
+    s.set_forces(True)
+    if "noise" in d:
+        s.inject_noise(d["noise"])
+    s.timestep(int(d["steps"]))
+    x, v, a, ff = s.get_atoms()
+    out.update(x_end=x, v_end=v, a_end=a, f_end=ff, which_end=np.asarray(s.which()), E_end=np.asarray(s.energy()),
+               K_end=np.asarray(s.kinetic_energy()), P_end=np.asarray(s.pressure()), T_end=np.asarray(s.temp()))
+    out["pairs_first_end"], out["pairs_last_end"] = s.pairs()
+    return out
+
+
+@pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p)[:-4] for p in GOLDEN])
+def test_golden_bit_exact(oracle_built, path):
+    assert GOLDEN, "golden fixtures missing"
+    w, d = load(path)
+    for be in backends(oracle_built):
+        out = replay(be, w, d)
+        for k, v in out.items():
+            assert np.array_equal(np.asarray(v), d[k]), "%s: %s differs from the reference fixture" % (be, k)
+
+
+@pytest.mark.parametrize("ndim,kind", [(3, 2), (2, 1), (3, 0), (3, 3), (2, 2)])
+def test_cell_list_equals_reference_rebuild(oracle_built, ndim, kind):
+    """InjectedNeighborList / port cell list == NeighborList::update_list(true) (trackers.cpp:55-69)."""
+    w = W.random_system(2500, ndim, kind, seed=3 + kind, ntypes=2)
+    for be in backends(oracle_built):
+        a = cpu_system(be, w, injected=False, collection=False).pairs()
+        b = cpu_system(be, w, injected=True, collection=False).pairs()
+        assert len(a[0]) > 1000
+        assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+
+
+def test_port_equals_reference_fresh_inputs(oracle_built):
+    if "ref" not in backends(oracle_built):
+        pytest.skip("compiled reference not present")
+    w = W.lj_lattice((7, 7, 7), seed=123)
+    r, p = cpu_system("ref", w), cpu_system("port", w)
+    for s in (r, p):
+        s.set_forces(True)
+        s.timestep(120)
+    for a, b in zip(r.get_atoms(), p.get_atoms()):
+        assert np.array_equal(a, b)
+    assert r.which() == p.which() and r.energy() == p.energy() and r.pressure() == p.pressure()
+
+
+def test_box_diff_is_ieee_remainder(oracle_built):
+    rng = np.random.default_rng(0)
+    L = np.array([3.0, 4.5, 7.25])
+    s = cpu_system("port", dict(L=L, x=np.zeros((2, 3)), v=np.zeros((2, 3)), m=np.ones(2), kind=0, skin=0.1,
+                                params=np.ones((2, 3))), collection=False)
+    for _ in range(200):
+        r1, r2 = rng.uniform(-30, 30, 3), rng.uniform(-30, 30, 3)
+        assert np.array_equal(s.box_diff(r1, r2), np.array([math.remainder(a, b) for a, b in zip(r1 - r2, L)]))
+
+
+def test_reference_hertzian_verlet_test(oracle_built):
+    """pyparm/tests.py:284-317 RandomHertzianVerletTest.testEnergy, on the oracle: warm up with a
+    thermostat for 1000 steps, then 10^4 NVE steps: |dE|/E < 1e-2 per step, <T> = 1 +- 10 %, std(E)/mean(E) < 1e-2."""
+    w = W.hertzian12()
+    be = backends(oracle_built)[-1]
+    s = cpu_system(be, w, collection=False)
+    s.make_collection(0, w["dt"])
+    # constructor with interactions/trackers given -> initialize(): set_forces(true)
+    s.set_forces(True)
+    s.scale_velocities_to_temp(1.0)
+    for _ in range(1000):
+        s.timestep(1)
+        s.scale_velocities_to_temp(1.0)
+    lastE = s.energy()
+    Es, Ts = [], []
+    for _ in range(1000):
+        for _ in range(10):
+            s.timestep(1)
+            E = s.energy()
+            assert abs(E - lastE) <= 1e-2 * abs(lastE)
+            lastE = E
+        Es.append(E)
+        Ts.append(s.temp())
+    assert abs(np.mean(Ts) - 1.0) < 0.1
+    assert abs(np.std(Es) / np.mean(Es)) < 1e-2
