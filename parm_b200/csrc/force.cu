@@ -234,9 +234,8 @@ static cudaError_t launch_kind(bool one, int team, int mode, uint32_t natoms, si
 static int launch_forces(parm_inter *it, int mode, bool accumulate, double *d_out) {
     parm_ctx *c = it->ctx;
     parm_nlist *nl = it->nl;
-    if (!it->have_params) { parm_set_error("NListed: no atoms were added (parm_inter_set_params not called)"); return PARM_ERR_INVALID; }
-    if (nl->updatenum == 0) {
-        // the reference would iterate an empty pair vector (update_pairs with which()==0)
+    if (!it->have_params || nl->updatenum == 0) {
+        // no atoms add()ed yet, or the list was never built: the reference iterates an empty pair vector
         if (mode != MODE_OBS && !accumulate) CK(cudaMemsetAsync(c->f, 0, 3 * (size_t)c->npad * 8, c->stream));
         if (d_out) CK(cudaMemsetAsync(d_out, 0, NPART * 8, c->stream));
         return 0;
