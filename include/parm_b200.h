@@ -170,6 +170,27 @@ int parm_integ_get_sol_constants(parm_integ *integ, double *c /* c0,c1,c2,x11,x2
 /* steps / rebuilds executed so far, kernels launched by this integrator */
 int parm_integ_stats(parm_integ *integ, uint64_t *steps, uint64_t *rebuilds, uint64_t *launches);
 
+/* ---- slab decomposition over the GPUs of one box (new; the reference is single-core) ----
+ * One process per GPU. The slab axis is x: rank r owns the atoms whose wrapped x lies in
+ * [r L_x / nranks, (r+1) L_x / nranks) and keeps ghost copies of its neighbours' boundary layers.
+ * Atom ids are GLOBAL AtomVec indices; per-atom parameter / diameter arrays passed to
+ * parm_inter_set_params / parm_nlist_set_diameters have n_global entries on every rank.
+ * Everything else (NeighborList, NListed, Collection* calls) is used unchanged and collectively:
+ * every rank makes the same calls in the same order; scalars come back all-reduced. */
+int parm_nccl_unique_id(void *id128);  /* rank 0 creates it, the caller broadcasts the 128 bytes */
+int parm_ctx_create_sharded(int ndim, uint32_t n_global, uint32_t cap_slots, int device, int rank, int nranks,
+                            const void *id128, parm_ctx **out);
+/* replace this rank's local atoms: dense row-major arrays (n_local x NDIM), gid = global indices;
+ * atoms must lie in, or within one cell layer of, this rank's slab (v, a, f may be NULL = 0) */
+int parm_shard_set_atoms(parm_ctx *ctx, uint32_t n_local, const uint32_t *gid, const double *x, const double *v,
+                         const double *a, const double *f, const double *m);
+/* current local atoms in slot order; gid == NULL only queries n_local */
+int parm_shard_get_atoms(parm_ctx *ctx, uint32_t cap, uint32_t *n_local, uint32_t *gid, double *x, double *v, double *a,
+                         double *f, double *m);
+/* overwrite fields of the local atoms in the order parm_shard_get_atoms returned them (NULL = keep) */
+int parm_shard_put_atoms(parm_ctx *ctx, uint32_t n_local, const double *x, const double *v, const double *a, const double *f);
+int parm_shard_info(parm_ctx *ctx, uint32_t *out6 /* n_local, ghosts_down, ghosts_up, send_down, send_up, slots */);
+
 #ifdef __cplusplus
 }
 #endif

@@ -79,6 +79,12 @@ SIGNATURES = {
     "parm_integ_inject_noise": (C.c_int, [vp, dp, C.c_size_t]),
     "parm_integ_get_sol_constants": (C.c_int, [vp, dp]),
     "parm_integ_stats": (C.c_int, [vp, u64p, u64p, u64p]),
+    "parm_nccl_unique_id": (C.c_int, [vp]),
+    "parm_ctx_create_sharded": (C.c_int, [C.c_int, C.c_uint32, C.c_uint32, C.c_int, C.c_int, C.c_int, vp, vpp]),
+    "parm_shard_set_atoms": (C.c_int, [vp, C.c_uint32, u32p, dp, dp, dp, dp, dp]),
+    "parm_shard_get_atoms": (C.c_int, [vp, C.c_uint32, u32p, u32p, dp, dp, dp, dp, dp]),
+    "parm_shard_put_atoms": (C.c_int, [vp, C.c_uint32, dp, dp, dp, dp]),
+    "parm_shard_info": (C.c_int, [vp, u32p]),
 }
 
 

@@ -302,10 +302,10 @@ extern "C" int parm_inter_create(parm_ctx *c, parm_nlist *nl, int kind, parm_int
     it->ctx = c;
     it->nl = nl;
     it->kind = kind;
-    it->h_spec_id.assign(c->n, 0);
-    CK(cudaMalloc(&it->d_spec_id, c->npad));
+    it->h_spec_id.assign(c->nid, 0);
+    CK(cudaMalloc(&it->d_spec_id, std::max(c->npad, c->nid_pad)));
     CK(cudaMalloc(&it->d_spec, c->npad));
-    CK(cudaMemsetAsync(it->d_spec_id, 0, c->npad, c->stream));
+    CK(cudaMemsetAsync(it->d_spec_id, 0, std::max(c->npad, c->nid_pad), c->stream));
     CK(cudaMemsetAsync(it->d_spec, 0, c->npad, c->stream));
     CK(cudaMalloc(&it->d_table, sizeof(PairConst) * PARM_MAX_SPECIES * PARM_MAX_SPECIES));
     c->inters.push_back(it);
@@ -399,8 +399,8 @@ extern "C" int parm_inter_set_params(parm_inter *it, const double *params, const
     typedef std::tuple<double, double, double, uint32_t> Key;
     std::map<Key, int> ids;
     std::vector<Key> keys;
-    std::vector<double> diam(c->n, -1.0);
-    for (uint32_t i = 0; i < c->n; i++) {
+    std::vector<double> diam(c->nid, -1.0);
+    for (uint32_t i = 0; i < c->nid; i++) {
         if (member && !member[i]) { it->h_spec_id[i] = 0; continue; }
         const double *p = params + 3 * (size_t)i;
         uint32_t t = (kind == PARM_PAIR_LJATTRACTREPULSE && type) ? type[i] : 0;
@@ -434,7 +434,7 @@ extern "C" int parm_inter_set_params(parm_inter *it, const double *params, const
             it->h_table[(size_t)a * S + b] = mix(kind, p1, std::get<3>(keys[a]), p2, std::get<3>(keys[b]), eps_table, ntypes);
         }
     CK(cudaMemcpyAsync(it->d_table, it->h_table.data(), sizeof(PairConst) * S * S, cudaMemcpyHostToDevice, c->stream));
-    if (c->n) CK(cudaMemcpyAsync(it->d_spec_id, it->h_spec_id.data(), c->n, cudaMemcpyHostToDevice, c->stream));
+    if (c->nid) CK(cudaMemcpyAsync(it->d_spec_id, it->h_spec_id.data(), c->nid, cudaMemcpyHostToDevice, c->stream));
     PTRY(parm_inter_regather(it));
     CK(cudaStreamSynchronize(c->stream));
     it->have_params = true;
@@ -447,6 +447,7 @@ static int fetch(parm_inter *it, int mode, bool accumulate, double *host13) {
     CK(cudaSetDevice(c->device));
     PTRY(parm_ctx_ensure_red(c, 64));
     PTRY(launch_forces(it, mode, accumulate, c->d_red));
+    if (c->sh.on) PTRY(parm_shard_allreduce_sum(c, c->d_red, NPART));
     CK(cudaMemcpyAsync(c->h_red, c->d_red, NPART * 8, cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
     memcpy(host13, c->h_red, NPART * 8);

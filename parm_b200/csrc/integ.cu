@@ -354,6 +354,7 @@ extern "C" int parm_integ_get_sol_constants(parm_integ *g, double *cst) {
 extern "C" int parm_integ_inject_noise(parm_integ *g, const double *z, size_t len) {
     parm_ctx *c = g->ctx;
     CK(cudaSetDevice(c->device));
+    if (c->sh.on) { parm_set_error("noise injection is a single-GPU parity hook"); return PARM_ERR_UNSUPPORTED; }
     CK(cudaStreamSynchronize(c->stream));
     if (g->d_noise) cudaFree(g->d_noise);
     g->d_noise = 0;
@@ -391,6 +392,7 @@ static int one_step(parm_integ *g) {
         else k_verlet1<2><<<grid, I_BLOCK, 0, c->stream>>>(c->pos, c->v, c->a, n, c->npad, dt, hdt2, hdt);
         CK_LAUNCH(c);
         PTRY(parm_prof_end(c));
+        if (c->sh.on) PTRY(parm_shard_halo_exchange(c)); // ghost positions for x(t+dt)
         PTRY(parm_prof_begin(c, PARM_PROF_FORCE));
         PTRY(launch_all_forces(g));
         PTRY(parm_prof_end(c));
@@ -433,6 +435,7 @@ static int one_step(parm_integ *g) {
         else k_sol1<2><<<grid, I_BLOCK, 0, c->stream>>>(c->pos, c->v, c->a, c->order, n, c->npad, K, noise, g->d_mobile_rank, g->steps, g->seed);
         CK_LAUNCH(c);
         PTRY(parm_prof_end(c));
+        if (c->sh.on) PTRY(parm_shard_halo_exchange(c)); // ghost positions for x(t+dt)
         PTRY(parm_prof_begin(c, PARM_PROF_FORCE));
         PTRY(launch_all_forces(g));
         PTRY(parm_prof_end(c));
@@ -456,8 +459,12 @@ static int one_step(parm_integ *g) {
     if (nl) {
         bool rebuild = nl->ignorechanged;
         if (!rebuild) {
-            CK(cudaStreamSynchronize(c->stream));
-            rebuild = nl->h_flags->need_rebuild != 0;
+            if (c->sh.on) {
+                PTRY(parm_shard_drift_decision(nl, &rebuild));
+            } else {
+                CK(cudaStreamSynchronize(c->stream));
+                rebuild = nl->h_flags->need_rebuild != 0;
+            }
         }
         if (rebuild) {
             PTRY(parm_nlist_rebuild(nl));
@@ -471,7 +478,7 @@ extern "C" int parm_integ_timestep(parm_integ *g, int nsteps) {
     if (!g) { parm_set_error("parm_integ_timestep: NULL integrator"); return PARM_ERR_INVALID; }
     parm_ctx *c = g->ctx;
     CK(cudaSetDevice(c->device));
-    if (c->n == 0) { g->steps += nsteps > 0 ? nsteps : 0; return 0; }
+    if (c->n == 0 && !c->sh.on) { g->steps += nsteps > 0 ? nsteps : 0; return 0; }
     for (size_t k = 1; k < g->trackers.size(); k++)
         if (g->trackers[k] != g->trackers[0]) { parm_set_error("one NeighborList per Collection is supported"); return PARM_ERR_UNSUPPORTED; }
     for (int s = 0; s < nsteps; s++) PTRY(one_step(g));

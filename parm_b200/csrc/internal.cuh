@@ -57,9 +57,26 @@ struct PairConst {
     double pad;
 };
 
+// Slab decomposition state (one process per GPU; csrc/shard.cu). The slab axis is x (axis 0, the
+// slowest index of the cell id), rank r owns wrapped x in [lo, lo + Ls). Slot layout after a
+// rebuild: [ghosts from the lower neighbour | local atoms | ghosts from the upper neighbour].
+struct ShardState {
+    bool on;
+    int rank, nranks, up, down;
+    double lo, Ls;
+    void *comm;                       // ncclComm_t
+    uint32_t n_local, g_dn, g_up;     // local atoms, ghosts received from down / up
+    uint32_t s_dn, s_up;              // boundary-layer atoms sent to down / up every step
+    uint32_t *d_counts, *h_counts;    // small exchange buffers (device, pinned host)
+    double *d_gather, *h_gather;      // drift top-2 of every rank
+};
+
 struct parm_ctx {
     int D;
-    uint32_t n, npad;
+    uint32_t n, npad;      // slots in use (local + ghost atoms), allocated slots
+    uint32_t nid, nid_pad; // atom ids (AtomVec indices; global ids when sharded), allocated id entries
+    ShardState sh;
+    uint8_t *ghost, *ghost_alt; // per slot: 1 = ghost copy of a remote atom (sharded contexts only)
     int device;
     cudaStream_t stream;
     BoxDev box;
@@ -89,6 +106,22 @@ struct parm_ctx {
 int parm_prof_begin(parm_ctx *c, int cls);
 int parm_prof_end(parm_ctx *c);
 
+struct GridDev {
+    int nc[3];
+    double scale[3]; // nc / L
+};
+// Cells have edge >= r_list/sub, the stencil is (2 sub + 1)^D cells.
+struct StencilDev {
+    int sub;     // cells per r_list
+    int full[3]; // 1: nc >= 2 sub + 1 (offsets -sub..sub, unique images); 0: visit every cell of that axis once
+    int open0;   // axis 0 is the slab axis of a sharded context: no wrap, halo layers at both ends
+};
+struct ShardDev {
+    int on;
+    double lo, Ls, L;
+    int nci; // interior cell layers along the slab axis
+};
+
 struct NlistFlags { // device-written; a pinned host mirror receives need_rebuild / top2
     int need_rebuild;
     uint32_t maxcnt;              // longest row of the last build
@@ -112,6 +145,11 @@ struct parm_nlist {
     bool ignorechanged;
     // cell grid
     int nc[3];
+    GridDev g;
+    StencilDev st;
+    ShardDev sd;
+    bool smallbox;
+    double lmax, thr_min;
     uint32_t ncell;
     uint32_t *cell_id, *cell_id_sorted, *perm, *iota, *cell_start;
     uint32_t cell_start_cap;
@@ -164,6 +202,16 @@ struct parm_integ {
 };
 
 // ---- cross-TU host functions ----
+int parm_ctx_alloc(int ndim, uint32_t nid, uint32_t cap_slots, int device, parm_ctx **out);
+int parm_shard_halo_exchange(parm_ctx *c);                 // per step, after K1
+int parm_shard_drift_decision(parm_nlist *nl, bool *rebuild); // after K3: global top-2 rule
+int parm_shard_rebuild(parm_nlist *nl);                    // migration + ghost selection + build
+int parm_shard_allreduce_sum(parm_ctx *c, double *d_buf, int count);
+int parm_shard_destroy(parm_ctx *c);
+// rebuild steps shared by the single-GPU and the sharded path (csrc/nlist.cu)
+int parm_nlist_prepare_grid(parm_nlist *nl);
+int parm_nlist_sort_permute(parm_nlist *nl, const uint32_t *d_src, uint32_t nsrc); // d_src NULL: slots 0..nsrc-1
+int parm_nlist_build_rows(parm_nlist *nl);
 int parm_nlist_rebuild(parm_nlist *nl);
 int parm_nlist_drift_check_async(parm_nlist *nl);   // standalone drift kernel (update_list(false) outside timestep)
 int parm_inter_regather(parm_inter *inter);          // re-gather per-slot species after a re-sort

@@ -26,32 +26,49 @@ static inline unsigned grid_for(const parm_ctx *ctx, uint32_t n, unsigned block,
     return need < cap ? need : cap;
 }
 
-struct GridDev {
-    int nc[3];
-    double scale[3]; // nc / L
-};
-
 // ---- K4a: cell index from the wrapped coordinate; also max |x| (bounds the wrap rounding) ----
 // (nearest reference analogue: Grid::get_loc, trackers.cpp:192-219)
-__global__ void k_cell_id(const double4 *__restrict__ pos, uint32_t n, BoxDev box, GridDev g, uint32_t *cell_id,
-                          uint32_t *iota, NlistFlags *flags) {
+__device__ __forceinline__ double shard_rel(double x, const ShardDev &sd) {
+    // coordinate along the slab axis relative to the slab's lower face, continuous across both halos
+    double w = x - sd.L * floor(x / sd.L);
+    double rel = w - sd.lo;
+    if (rel < 0.0) rel += sd.L;
+    if (rel >= sd.Ls + 0.5 * (sd.L - sd.Ls)) rel -= sd.L;
+    return rel;
+}
+
+__global__ void k_cell_id(const double4 *__restrict__ pos, const uint32_t *__restrict__ src, uint32_t n, BoxDev box,
+                          GridDev g, ShardDev sd, uint32_t *cell_id, uint32_t *iota, NlistFlags *flags) {
     double xm = 0.0;
-    for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < n; s += gridDim.x * blockDim.x) {
+    for (uint32_t q = blockIdx.x * blockDim.x + threadIdx.x; q < n; q += gridDim.x * blockDim.x) {
+        const uint32_t s = src ? src[q] : q;
         double4 p = pos[s];
         double x[3] = {p.x, p.y, p.z};
         uint32_t c = 0;
 #pragma unroll
         for (int d = 0; d < 3; d++) {
-            double w = x[d] - box.L[d] * floor(x[d] * box.invL[d]); // ~[0, L]
-            int k = (int)floor(w * g.scale[d]);
-            if (!(k >= 0)) k = 0; // also catches NaN
-            if (k >= g.nc[d]) k = g.nc[d] - 1;
+            int k;
+            if (d == 0 && sd.on) {
+                // slab axis: [halo below | nci interior layers | halo above], no periodic wrap
+                double rel = shard_rel(x[0], sd);
+                if (rel < 0.0) k = 0;
+                else if (rel >= sd.Ls) k = g.nc[0] - 1;
+                else {
+                    k = 1 + (int)floor(rel * sd.nci / sd.Ls);
+                    if (k > sd.nci) k = sd.nci;
+                }
+            } else {
+                double w = x[d] - box.L[d] * floor(x[d] * box.invL[d]); // ~[0, L]
+                k = (int)floor(w * g.scale[d]);
+                if (!(k >= 0)) k = 0; // also catches NaN
+                if (k >= g.nc[d]) k = g.nc[d] - 1;
+            }
             c = c * (uint32_t)g.nc[d] + (uint32_t)k;
             double ax = fabs(x[d]);
             if (ax > xm && ax < 1e300) xm = ax;
         }
-        cell_id[s] = c;
-        iota[s] = s;
+        cell_id[q] = c;
+        iota[q] = s;
     }
 #pragma unroll
     for (int o = 16; o; o >>= 1) xm = fmax(xm, __shfl_xor_sync(0xffffffffu, xm, o));
@@ -71,7 +88,7 @@ __global__ void k_permute(const uint32_t *__restrict__ perm, uint32_t n, uint32_
                           const uint32_t *__restrict__ order, double4 *pos_o, double *v_o, double *a_o, double *f_o,
                           uint32_t *order_o, uint32_t *slot_of, const double *__restrict__ diam_id, double *diam,
                           double *xlast, double4 *pw, BoxDev box, double half_skin, double lmax, double thr_min,
-                          const NlistFlags *flags) {
+                          const NlistFlags *flags, ShardDev sd, const uint8_t *__restrict__ ghost, uint8_t *ghost_o) {
     const double delta = band_delta(flags, lmax, thr_min);
     for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < n; s += gridDim.x * blockDim.x) {
         uint32_t o = perm[s];
@@ -93,15 +110,18 @@ __global__ void k_permute(const uint32_t *__restrict__ perm, uint32_t n, uint32_
         // w = upper half threshold g_i (1 + delta): g_i + g_j = ((d_i + d_j)/2 + skin)(1 + delta);
         // NaN marks atoms that were never add()ed to the list
         double4 q;
-        q.x = p.x - box.L[0] * floor(p.x * box.invL[0]);
+        q.x = sd.on ? shard_rel(p.x, sd) : p.x - box.L[0] * floor(p.x * box.invL[0]);
         q.y = p.y - box.L[1] * floor(p.y * box.invL[1]);
         q.z = p.z - box.L[2] * floor(p.z * box.invL[2]);
         q.w = dm >= 0.0 ? (0.5 * dm + half_skin) * (1.0 + delta) : __longlong_as_double(0x7ff8000000000000LL);
         pw[s] = q;
-        // lastlocs[i] = a1->x (trackers.cpp:61)
-        xlast[s] = p.x;
-        xlast[npad + s] = p.y;
-        xlast[2 * (size_t)npad + s] = p.z;
+        // lastlocs[i] = a1->x (trackers.cpp:61); ghosts never take part in the drift rule (NaN never wins a >)
+        const bool gh = ghost ? ghost[o] != 0 : false;
+        if (ghost_o) ghost_o[s] = gh ? 1 : 0;
+        const double nanv = __longlong_as_double(0x7ff8000000000000LL);
+        xlast[s] = gh ? nanv : p.x;
+        xlast[npad + s] = gh ? nanv : p.y;
+        xlast[2 * (size_t)npad + s] = gh ? nanv : p.z;
     }
 }
 
@@ -116,12 +136,6 @@ __global__ void k_cell_start(const uint32_t *__restrict__ cid, uint32_t n, uint3
 }
 
 // ---- K5: neighbour build ----------------------------------------------------------
-// Cells have edge >= r_list/sub, the stencil is (2 sub + 1)^D cells.
-struct StencilDev {
-    int sub;     // cells per r_list
-    int full[3]; // 1: nc >= 2 sub + 1 (offsets -sub..sub, unique images); 0: visit every cell of that axis once
-};
-
 // Exact reference predicate (trackers.cpp:65-66) on the UNWRAPPED coordinates.
 __device__ __noinline__ bool pair_pred_exact(const double4 *__restrict__ pos, const double *__restrict__ diam,
                                              uint32_t i, uint32_t j, BoxDev box, double skin) {
@@ -149,7 +163,7 @@ __global__ void __launch_bounds__(BUILD_WARPS * 32)
 k_build(const double4 *__restrict__ pos, const double4 *__restrict__ pw, const double *__restrict__ diam,
         const uint32_t *__restrict__ cid, const uint32_t *__restrict__ cell_start, uint32_t n, BoxDev box, GridDev g,
         StencilDev st, double skin, double lmax, double thr_min, uint32_t kmax, uint32_t *__restrict__ nbr,
-        uint32_t *__restrict__ cnt, NlistFlags *flags) {
+        uint32_t *__restrict__ cnt, NlistFlags *flags, const uint8_t *__restrict__ ghost) {
     __shared__ double4 s_w[BUILD_WARPS][32];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const uint32_t tile = blockIdx.x * BUILD_WARPS + wib;
@@ -162,7 +176,8 @@ k_build(const double4 *__restrict__ pos, const double4 *__restrict__ pw, const d
         wi = pw[i];
         ci = cid[i];
     }
-    const bool member = wi.w == wi.w;
+    // rows are built for list members that this rank owns; ghosts are candidates only
+    const bool member = wi.w == wi.w && !(ghost && i < n && ghost[i]);
     s_w[wib][lane] = wi;
     __syncwarp();
     // a test is decided by the fast arithmetic when dsq is outside [lo, 1) * thr_hi^2
@@ -181,7 +196,11 @@ k_build(const double4 *__restrict__ pos, const double4 *__restrict__ pw, const d
         const uint32_t t = cur / (uint32_t)g.nc[2];
         const int cy = (int)(t % (uint32_t)g.nc[1]);
         const int cx = (int)(t / (uint32_t)g.nc[1]);
-        const int x0 = st.full[0] ? cx - st.sub : 0, x1 = st.full[0] ? cx + st.sub : g.nc[0] - 1;
+        int x0 = st.full[0] ? cx - st.sub : 0, x1 = st.full[0] ? cx + st.sub : g.nc[0] - 1;
+        if (st.open0) { // slab axis of a sharded context: halo layers instead of periodic wrap
+            x0 = max(cx - st.sub, 0);
+            x1 = min(cx + st.sub, g.nc[0] - 1);
+        }
         const int y0 = st.full[1] ? cy - st.sub : 0, y1 = st.full[1] ? cy + st.sub : g.nc[1] - 1;
         const int z0 = st.full[2] ? cz - st.sub : 0, z1 = st.full[2] ? cz + st.sub : g.nc[2] - 1;
         for (int xx = x0; xx <= x1; xx++) {
@@ -218,7 +237,7 @@ k_build(const double4 *__restrict__ pos, const double4 *__restrict__ pw, const d
                             const double4 a = s_w[wib][b];
                             double dx = a.x - wj.x, dy = a.y - wj.y, dz = a.z - wj.z;
                             if (SMALLBOX) { // some axis has too few cells for unique images: fold explicitly
-                                dx = min_image_fast(dx, box.L[0], box.invL[0]);
+                                if (!st.open0) dx = min_image_fast(dx, box.L[0], box.invL[0]);
                                 dy = min_image_fast(dy, box.L[1], box.invL[1]);
                                 dz = min_image_fast(dz, box.L[2], box.invL[2]);
                             }
@@ -286,9 +305,10 @@ extern "C" int parm_nlist_create(parm_ctx *c, double skin, parm_nlist **out) {
     nl->ctx = c;
     nl->skin = skin;
     nl->ignorechanged = true; // trackers.cpp:17
-    nl->h_diam.assign(c->n, -1.0);
+    nl->h_diam.assign(c->nid, -1.0);
     size_t np = c->npad;
-    CK(cudaMalloc(&nl->d_diam_id, np * 8));
+    const size_t nidp = std::max(c->npad, c->nid_pad);
+    CK(cudaMalloc(&nl->d_diam_id, nidp * 8));
     CK(cudaMalloc(&nl->d_diam, np * 8));
     CK(cudaMalloc(&nl->xlast, 3 * np * 8));
     CK(cudaMalloc(&nl->pw, np * sizeof(double4)));
@@ -309,8 +329,8 @@ extern "C" int parm_nlist_create(parm_ctx *c, double skin, parm_nlist **out) {
     CK(cudaHostAlloc(&nl->h_flags, sizeof(NlistFlags), cudaHostAllocMapped));
     memset(nl->h_flags, 0, sizeof(NlistFlags));
     // all atoms start as non-members
-    std::vector<double> neg(np, -1.0);
-    CK(cudaMemcpyAsync(nl->d_diam_id, neg.data(), np * 8, cudaMemcpyHostToDevice, c->stream));
+    std::vector<double> neg(nidp, -1.0);
+    CK(cudaMemcpyAsync(nl->d_diam_id, neg.data(), nidp * 8, cudaMemcpyHostToDevice, c->stream));
     CK(cudaMemcpyAsync(nl->d_diam, neg.data(), np * 8, cudaMemcpyHostToDevice, c->stream));
     CK(cudaStreamSynchronize(c->stream));
     c->nlists.push_back(nl);
@@ -343,7 +363,7 @@ extern "C" int parm_nlist_set_diameters(parm_nlist *nl, const double *diam) {
     CK(cudaSetDevice(c->device));
     double maxd = 0, mind = INFINITY;
     bool any = false;
-    for (uint32_t i = 0; i < c->n; i++) {
+    for (uint32_t i = 0; i < c->nid; i++) {
         double d = diam[i];
         if (d >= 0 && !isinf(d)) {
             nl->h_diam[i] = d;
@@ -356,8 +376,8 @@ extern "C" int parm_nlist_set_diameters(parm_nlist *nl, const double *diam) {
     nl->have_diam = any;
     nl->maxdiam = maxd;
     nl->mindiam = any ? mind : 0.0;
+    if (c->nid) CK(cudaMemcpyAsync(nl->d_diam_id, nl->h_diam.data(), (size_t)c->nid * 8, cudaMemcpyHostToDevice, c->stream));
     if (c->n) {
-        CK(cudaMemcpyAsync(nl->d_diam_id, nl->h_diam.data(), (size_t)c->n * 8, cudaMemcpyHostToDevice, c->stream));
         k_gather_by_order_d<<<grid_for(c, c->n, 256), 256, 0, c->stream>>>(nl->d_diam_id, c->order, c->n, nl->d_diam);
         CK_LAUNCH(c);
         CK(cudaStreamSynchronize(c->stream)); // h_diam may be re-written by the caller's next call
@@ -381,22 +401,19 @@ static int alloc_nbr(parm_nlist *nl, uint32_t kmax) {
     return 0;
 }
 
-int parm_nlist_rebuild(parm_nlist *nl) {
+// ---- rebuild steps (shared by the single-GPU path below and csrc/shard.cu) -------------------
+// Cell grid for the current box: cells no smaller than the largest possible pair threshold / sub.
+int parm_nlist_prepare_grid(parm_nlist *nl) {
     parm_ctx *c = nl->ctx;
-    CK(cudaSetDevice(c->device));
-    if (!c->box_set) { parm_set_error("NeighborList update before the box was set"); return PARM_ERR_INVALID; }
-    nl->updatenum++; // trackers.cpp:56-57
-    nl->ignorechanged = false;
-    nl->rebuilds++;
     const uint32_t n = c->n;
-    if (n == 0) { nl->total_full = 0; nl->maxcnt = 0; return 0; }
-
-    // --- cell grid: cells no smaller than the largest possible pair threshold / sub
     const double rlist = (nl->maxdiam + nl->skin) * (1.0 + 1e-6) + 1e-12;
-    GridDev g;
-    StencilDev st;
+    GridDev &g = nl->g;
+    StencilDev &st = nl->st;
+    ShardDev &sd = nl->sd;
+    memset(&sd, 0, sizeof(sd));
     uint64_t ncell = 1;
-    const uint64_t cell_cap = std::max<uint64_t>(64, 4ull * n);
+    // identical on every rank of a sharded context (the ranks must agree on the y/z grid)
+    const uint64_t cell_cap = std::max<uint64_t>(64, c->sh.on ? 8ull * (c->nid / c->sh.nranks + 1) : 4ull * std::max<uint32_t>(n, 1u));
     const int sub = nl->cell_sub;
     for (int d = 0; d < 3; d++) {
         int k = 1;
@@ -406,24 +423,41 @@ int parm_nlist_rebuild(parm_nlist *nl) {
         }
         g.nc[d] = k;
     }
-    // keep the cell table within a few entries per atom
+    if (c->sh.on) {
+        // slab axis: interior layers of width Ls/nci >= r_list plus one halo layer on each side
+        int nci = (int)floor(c->sh.Ls / rlist);
+        if (nci < 2) {
+            parm_set_error("slab decomposition: slab width %g must be at least 2 x (max diameter + skin) = %g", c->sh.Ls, 2 * rlist);
+            return PARM_ERR_INVALID;
+        }
+        if (nci > 2046) nci = 2046;
+        sd.on = 1;
+        sd.lo = c->sh.lo;
+        sd.Ls = c->sh.Ls;
+        sd.L = c->box.L[0];
+        sd.nci = nci;
+        g.nc[0] = nci + 2;
+    }
+    // keep the cell table within a few entries per atom (never shrink the slab axis)
     for (;;) {
         ncell = (uint64_t)g.nc[0] * g.nc[1] * g.nc[2];
         if (ncell <= cell_cap) break;
-        int big = 0;
-        for (int d = 1; d < 3; d++)
+        int big = c->sh.on ? 1 : 0;
+        for (int d = big + 1; d < 3; d++)
             if (g.nc[d] > g.nc[big]) big = d;
+        if (g.nc[big] <= 1) break;
         g.nc[big] = (g.nc[big] + 1) / 2;
     }
-    st.sub = sub;
-    bool smallbox = false;
-    double lmax = 0;
+    st.sub = c->sh.on ? 1 : sub;
+    st.open0 = c->sh.on ? 1 : 0;
+    nl->smallbox = false;
+    nl->lmax = 0;
     for (int d = 0; d < 3; d++) {
         g.scale[d] = g.nc[d] / c->box.L[d];
-        st.full[d] = (g.nc[d] >= 2 * sub + 1) ? 1 : 0;
-        if (!st.full[d] && d < c->D) smallbox = true;
+        st.full[d] = (g.nc[d] >= 2 * st.sub + 1) ? 1 : 0;
+        if (!st.full[d] && d < c->D && !(d == 0 && st.open0)) nl->smallbox = true;
         nl->nc[d] = g.nc[d];
-        if (d < c->D) lmax = std::max(lmax, c->box.L[d]);
+        if (d < c->D) nl->lmax = std::max(nl->lmax, c->box.L[d]);
     }
     nl->ncell = (uint32_t)ncell;
     if (nl->ncell + 2 > nl->cell_start_cap) {
@@ -432,16 +466,26 @@ int parm_nlist_rebuild(parm_nlist *nl) {
         nl->cell_start_cap = nl->ncell + 2 + nl->ncell / 4;
         CK(cudaMalloc(&nl->cell_start, (size_t)nl->cell_start_cap * 4));
     }
-    double thr_min = nl->mindiam + nl->skin;
-    if (!(thr_min > 1e-300)) thr_min = 1e-300;
+    nl->thr_min = nl->mindiam + nl->skin;
+    if (!(nl->thr_min > 1e-300)) nl->thr_min = 1e-300;
+    return 0;
+}
 
-    PTRY(parm_prof_begin(c, PARM_PROF_REBUILD));
-    CK(cudaMemsetAsync(nl->d_flags, 0, sizeof(NlistFlags), c->stream));
-    // --- bin, sort by cell index (stable LSD radix sort), re-order every per-slot array
-    k_cell_id<<<grid_for(c, n, 256), 256, 0, c->stream>>>(c->pos, n, c->box, g, nl->cell_id, nl->iota, nl->d_flags);
+// Bin the atoms in slots d_src[0..nsrc) (NULL: slots 0..nsrc-1), sort them by cell index (stable LSD
+// radix sort) and re-order every per-slot array; afterwards the context holds exactly those nsrc atoms
+// in slots 0..nsrc-1, cell-sorted, and cell_start is valid.
+int parm_nlist_sort_permute(parm_nlist *nl, const uint32_t *d_src, uint32_t nsrc) {
+    parm_ctx *c = nl->ctx;
+    const uint32_t n = nsrc;
+    c->n = nsrc;
+    if (n == 0) {
+        CK(cudaMemsetAsync(nl->cell_start, 0, (size_t)(nl->ncell + 1) * 4, c->stream));
+        return 0;
+    }
+    k_cell_id<<<grid_for(c, n, 256), 256, 0, c->stream>>>(c->pos, d_src, n, c->box, nl->g, nl->sd, nl->cell_id, nl->iota, nl->d_flags);
     CK_LAUNCH(c);
     int end_bit = 1;
-    while ((1ull << end_bit) < ncell) end_bit++;
+    while ((1ull << end_bit) < (uint64_t)nl->ncell) end_bit++;
     size_t need = 0;
     CK(cub::DeviceRadixSort::SortPairs(nullptr, need, nl->cell_id, nl->cell_id_sorted, nl->iota, nl->perm, (int)n, 0,
                                         end_bit, c->stream));
@@ -458,40 +502,51 @@ int parm_nlist_rebuild(parm_nlist *nl) {
     k_permute<<<grid_for(c, n, 256), 256, 0, c->stream>>>(nl->perm, n, c->npad, c->pos, c->v, c->a, c->f, c->order,
                                                           c->pos_alt, c->v_alt, c->a_alt, c->f_alt, c->order_alt,
                                                           c->slot_of, nl->d_diam_id, nl->d_diam, nl->xlast, nl->pw,
-                                                          c->box, 0.5 * nl->skin, lmax, thr_min, nl->d_flags);
+                                                          c->box, 0.5 * nl->skin, nl->lmax, nl->thr_min, nl->d_flags,
+                                                          nl->sd, c->ghost, c->ghost_alt);
     CK_LAUNCH(c);
     std::swap(c->pos, c->pos_alt);
     std::swap(c->v, c->v_alt);
     std::swap(c->a, c->a_alt);
     std::swap(c->f, c->f_alt);
     std::swap(c->order, c->order_alt);
-    for (parm_inter *it : c->inters) PTRY(parm_inter_regather(it));
+    std::swap(c->ghost, c->ghost_alt);
     k_cell_start<<<grid_for(c, n + 1, 256), 256, 0, c->stream>>>(nl->cell_id_sorted, n, nl->ncell, nl->cell_start);
     CK_LAUNCH(c);
+    return 0;
+}
 
-    // --- build, growing the per-atom capacity if some row overflowed
+// Build the rows for the atoms now in slots 0..n-1, growing the per-atom capacity if a row overflowed.
+int parm_nlist_build_rows(parm_nlist *nl) {
+    parm_ctx *c = nl->ctx;
+    const uint32_t n = c->n;
+    for (parm_inter *it : c->inters) PTRY(parm_inter_regather(it));
+    if (n == 0) { nl->total_full = 0; nl->maxcnt = 0; return 0; }
     if (nl->kmax == 0) {
         double vol = 1;
         for (int d = 0; d < c->D; d++) vol *= c->box.L[d];
         double rl = nl->maxdiam + nl->skin;
         double sphere = c->D == 3 ? 4.18879020478639 * rl * rl * rl : 3.14159265358979 * rl * rl;
-        double est = (double)n / vol * sphere;
-        uint32_t k0 = (uint32_t)std::min<double>(std::max(16.0, 1.25 * est + 12.0), (double)std::max<uint32_t>(n, 2u) - 1.0);
+        double ntot = c->sh.on ? (double)c->nid : (double)n;
+        double est = ntot / vol * sphere;
+        uint32_t k0 = (uint32_t)std::min<double>(std::max(16.0, 1.25 * est + 12.0), std::max(ntot, 2.0) - 1.0);
         PTRY(alloc_nbr(nl, std::max<uint32_t>(k0, 1u)));
     }
     const unsigned ntiles = (n + 31) / 32;
     const unsigned nblocks = (ntiles + BUILD_WARPS - 1) / BUILD_WARPS;
     for (int attempt = 0; attempt < 8; attempt++) {
-        if (attempt) CK(cudaMemsetAsync((char *)nl->d_flags + offsetof(NlistFlags, maxcnt), 0,
-                                        offsetof(NlistFlags, xmax_bits) - offsetof(NlistFlags, maxcnt), c->stream));
-        if (smallbox)
+        CK(cudaMemsetAsync((char *)nl->d_flags + offsetof(NlistFlags, maxcnt), 0,
+                           offsetof(NlistFlags, xmax_bits) - offsetof(NlistFlags, maxcnt), c->stream));
+        if (nl->smallbox)
             k_build<true><<<nblocks, BUILD_WARPS * 32, 0, c->stream>>>(c->pos, nl->pw, nl->d_diam, nl->cell_id_sorted,
-                                                                      nl->cell_start, n, c->box, g, st, nl->skin, lmax,
-                                                                      thr_min, nl->kmax, nl->nbr, nl->cnt, nl->d_flags);
+                                                                      nl->cell_start, n, c->box, nl->g, nl->st, nl->skin,
+                                                                      nl->lmax, nl->thr_min, nl->kmax, nl->nbr, nl->cnt,
+                                                                      nl->d_flags, c->sh.on ? c->ghost : nullptr);
         else
             k_build<false><<<nblocks, BUILD_WARPS * 32, 0, c->stream>>>(c->pos, nl->pw, nl->d_diam, nl->cell_id_sorted,
-                                                                       nl->cell_start, n, c->box, g, st, nl->skin, lmax,
-                                                                       thr_min, nl->kmax, nl->nbr, nl->cnt, nl->d_flags);
+                                                                       nl->cell_start, n, c->box, nl->g, nl->st, nl->skin,
+                                                                       nl->lmax, nl->thr_min, nl->kmax, nl->nbr, nl->cnt,
+                                                                       nl->d_flags, c->sh.on ? c->ghost : nullptr);
         CK_LAUNCH(c);
         if (attempt == 0) PTRY(parm_prof_end(c));
         CK(cudaMemcpyAsync(nl->h_flags, nl->d_flags, sizeof(NlistFlags), cudaMemcpyDeviceToHost, c->stream));
@@ -504,6 +559,22 @@ int parm_nlist_rebuild(parm_nlist *nl) {
     }
     parm_set_error("neighbour list capacity did not converge");
     return PARM_ERR_RUNTIME;
+}
+
+int parm_nlist_rebuild(parm_nlist *nl) {
+    parm_ctx *c = nl->ctx;
+    CK(cudaSetDevice(c->device));
+    if (!c->box_set) { parm_set_error("NeighborList update before the box was set"); return PARM_ERR_INVALID; }
+    nl->updatenum++; // trackers.cpp:56-57
+    nl->ignorechanged = false;
+    nl->rebuilds++;
+    if (c->sh.on) return parm_shard_rebuild(nl);
+    if (c->n == 0) { nl->total_full = 0; nl->maxcnt = 0; return 0; }
+    PTRY(parm_nlist_prepare_grid(nl));
+    PTRY(parm_prof_begin(c, PARM_PROF_REBUILD));
+    CK(cudaMemsetAsync(nl->d_flags, 0, sizeof(NlistFlags), c->stream));
+    PTRY(parm_nlist_sort_permute(nl, nullptr, c->n));
+    return parm_nlist_build_rows(nl);
 }
 
 int parm_nlist_drift_check_async(parm_nlist *nl) {
@@ -521,10 +592,16 @@ extern "C" int parm_nlist_update(parm_nlist *nl, int force, int *rebuilt) {
     CK(cudaSetDevice(c->device));
     if (rebuilt) *rebuilt = 0;
     if (!force && !nl->ignorechanged) {
-        if (c->n == 0) return 0;
+        if (c->n == 0 && !c->sh.on) return 0;
         PTRY(parm_nlist_drift_check_async(nl));
-        CK(cudaStreamSynchronize(c->stream));
-        if (!nl->h_flags->need_rebuild) return 0;
+        if (c->sh.on) {
+            bool rb = false;
+            PTRY(parm_shard_drift_decision(nl, &rb));
+            if (!rb) return 0;
+        } else {
+            CK(cudaStreamSynchronize(c->stream));
+            if (!nl->h_flags->need_rebuild) return 0;
+        }
     }
     PTRY(parm_nlist_rebuild(nl));
     if (rebuilt) *rebuilt = 1;
@@ -532,47 +609,67 @@ extern "C" int parm_nlist_update(parm_nlist *nl, int force, int *rebuilt) {
 }
 
 extern "C" int parm_nlist_which(parm_nlist *nl, uint32_t *u) { *u = nl->updatenum; return 0; }
-extern "C" int parm_nlist_numpairs(parm_nlist *nl, uint64_t *np) { *np = nl->total_full / 2; return 0; }
+
+// Host copy of the pair list in the reference's order (trackers.cpp:59-68): first = later atom i,
+// last = earlier atom j < i, sorted by (i, j). Sharded contexts return the pairs whose `first`
+// atom is local to this rank (the union over ranks is the global list, each pair exactly once).
+static int collect_pairs(parm_nlist *nl, std::vector<std::pair<uint32_t, uint32_t> > &out) {
+    parm_ctx *c = nl->ctx;
+    out.clear();
+    const uint32_t n = c->n;
+    if (n == 0 || nl->updatenum == 0) return 0;
+    std::vector<uint32_t> h_cnt(n), h_order(n), h_nbr((size_t)n * nl->kmax);
+    std::vector<uint8_t> h_ghost(n, 0);
+    CK(cudaMemcpyAsync(h_cnt.data(), nl->cnt, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(h_order.data(), c->order, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(h_nbr.data(), nl->nbr, h_nbr.size() * 4, cudaMemcpyDeviceToHost, c->stream));
+    if (c->sh.on) CK(cudaMemcpyAsync(h_ghost.data(), c->ghost, n, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    out.reserve(nl->total_full / 2 + 16);
+    for (uint32_t s = 0; s < n; s++) {
+        if (h_ghost[s]) continue;
+        const uint32_t i = h_order[s];
+        const uint32_t *row = h_nbr.data() + (size_t)s * nl->kmax;
+        for (uint32_t q = 0; q < h_cnt[s]; q++) {
+            uint32_t j = h_order[row[q]];
+            if (j < i) out.push_back(std::make_pair(i, j));
+        }
+    }
+    std::sort(out.begin(), out.end());
+    if (!c->sh.on && out.size() != nl->total_full / 2) {
+        parm_set_error("neighbour list is not symmetric (%llu canonical pairs vs %llu row entries / 2)",
+                       (unsigned long long)out.size(), (unsigned long long)(nl->total_full / 2));
+        return PARM_ERR_RUNTIME;
+    }
+    return 0;
+}
+
+extern "C" int parm_nlist_numpairs(parm_nlist *nl, uint64_t *np) {
+    if (!nl->ctx->sh.on) { *np = nl->total_full / 2; return 0; }
+    std::vector<std::pair<uint32_t, uint32_t> > pr;
+    CK(cudaSetDevice(nl->ctx->device));
+    PTRY(collect_pairs(nl, pr));
+    *np = pr.size();
+    return 0;
+}
 
 extern "C" int parm_nlist_stats(parm_nlist *nl, double *mean_full, uint32_t *max_full) {
-    uint32_t members = 0;
-    for (double d : nl->h_diam) members += d >= 0;
+    uint64_t members = 0;
+    if (nl->ctx->sh.on) members = nl->ctx->sh.n_local;
+    else for (double d : nl->h_diam) members += d >= 0;
     if (mean_full) *mean_full = members ? (double)nl->total_full / members : 0.0;
     if (max_full) *max_full = nl->maxcnt;
     return 0;
 }
 
 extern "C" int parm_nlist_download_pairs(parm_nlist *nl, uint32_t *first, uint32_t *last, uint64_t cap) {
-    parm_ctx *c = nl->ctx;
-    CK(cudaSetDevice(c->device));
-    uint64_t np = nl->total_full / 2;
-    if (cap < np) { parm_set_error("parm_nlist_download_pairs: capacity %llu < %llu pairs", (unsigned long long)cap, (unsigned long long)np); return PARM_ERR_INVALID; }
-    if (np == 0 || nl->updatenum == 0) return 0;
-    const uint32_t n = c->n;
-    std::vector<uint32_t> h_cnt(c->npad), h_order(c->npad), h_slot(c->npad), h_nbr((size_t)n * nl->kmax);
-    CK(cudaMemcpyAsync(h_cnt.data(), nl->cnt, (size_t)c->npad * 4, cudaMemcpyDeviceToHost, c->stream));
-    CK(cudaMemcpyAsync(h_order.data(), c->order, (size_t)c->npad * 4, cudaMemcpyDeviceToHost, c->stream));
-    CK(cudaMemcpyAsync(h_slot.data(), c->slot_of, (size_t)c->npad * 4, cudaMemcpyDeviceToHost, c->stream));
-    CK(cudaMemcpyAsync(h_nbr.data(), nl->nbr, h_nbr.size() * 4, cudaMemcpyDeviceToHost, c->stream));
-    CK(cudaStreamSynchronize(c->stream));
-    uint64_t k = 0;
-    std::vector<uint32_t> js;
-    for (uint32_t i = 0; i < n; i++) { // reference order: i ascending, j < i ascending (trackers.cpp:59-68)
-        uint32_t s = h_slot[i];
-        js.clear();
-        const uint32_t *row = h_nbr.data() + (size_t)s * nl->kmax;
-        for (uint32_t q = 0; q < h_cnt[s]; q++) {
-            uint32_t j = h_order[row[q]];
-            if (j < i) js.push_back(j);
-        }
-        std::sort(js.begin(), js.end());
-        for (uint32_t j : js) {
-            if (k >= np) { parm_set_error("parm_nlist_download_pairs: device list is not symmetric"); return PARM_ERR_RUNTIME; }
-            first[k] = i;
-            last[k] = j;
-            k++;
-        }
+    CK(cudaSetDevice(nl->ctx->device));
+    std::vector<std::pair<uint32_t, uint32_t> > pr;
+    PTRY(collect_pairs(nl, pr));
+    if (cap < pr.size()) { parm_set_error("parm_nlist_download_pairs: capacity %llu < %llu pairs", (unsigned long long)cap, (unsigned long long)pr.size()); return PARM_ERR_INVALID; }
+    for (size_t k = 0; k < pr.size(); k++) {
+        first[k] = pr[k].first;
+        last[k] = pr[k].second;
     }
-    if (k != np) { parm_set_error("parm_nlist_download_pairs: device list is not symmetric (%llu vs %llu)", (unsigned long long)k, (unsigned long long)np); return PARM_ERR_RUNTIME; }
     return 0;
 }

@@ -5,6 +5,7 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <algorithm>
 #include <atomic>
 
 #include "internal.cuh"
@@ -56,6 +57,11 @@ __global__ void k_init_order(uint32_t *order, uint32_t *slot_of, uint32_t n) {
 }
 
 extern "C" int parm_ctx_create(int ndim, uint32_t n_atoms, int device, parm_ctx **out) {
+    return parm_ctx_alloc(ndim, n_atoms, n_atoms, device, out);
+}
+
+// nid atom ids, cap_slots slots (== nid for a single-GPU context; local + ghost capacity when sharded)
+int parm_ctx_alloc(int ndim, uint32_t n_atoms, uint32_t cap_slots, int device, parm_ctx **out) {
     if (!out) { parm_set_error("parm_ctx_create: out is NULL"); return PARM_ERR_INVALID; }
     *out = 0;
     if (ndim != 2 && ndim != 3) { parm_set_error("parm_ctx_create: ndim must be 2 or 3 (got %d)", ndim); return PARM_ERR_INVALID; }
@@ -72,8 +78,12 @@ extern "C" int parm_ctx_create(int ndim, uint32_t n_atoms, int device, parm_ctx 
     parm_ctx *c = new parm_ctx();
     c->D = ndim;
     c->n = n_atoms;
-    c->npad = ((n_atoms + 127u) / 128u) * 128u;
+    c->nid = n_atoms;
+    c->npad = ((cap_slots + 127u) / 128u) * 128u;
     if (c->npad == 0) c->npad = 128;
+    c->nid_pad = ((n_atoms + 127u) / 128u) * 128u;
+    if (c->nid_pad == 0) c->nid_pad = 128;
+    if (c->nid_pad < c->npad && cap_slots == n_atoms) c->nid_pad = c->npad;
     c->device = device;
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, device));
@@ -91,7 +101,7 @@ extern "C" int parm_ctx_create(int ndim, uint32_t n_atoms, int device, parm_ctx 
     CK(cudaMemsetAsync(c->pos_alt, 0, np * sizeof(double4), c->stream));
     CK(cudaMalloc(&c->order, np * 4));
     CK(cudaMalloc(&c->order_alt, np * 4));
-    CK(cudaMalloc(&c->slot_of, np * 4));
+    CK(cudaMalloc(&c->slot_of, (size_t)std::max(c->nid_pad, c->npad) * 4));
     k_init_order<<<grid_for(c, c->npad, 256), 256, 0, c->stream>>>(c->order, c->slot_of, c->npad);
     CK_LAUNCH(c);
     PTRY(parm_ctx_ensure_red(c, 4096));
@@ -105,8 +115,9 @@ extern "C" int parm_ctx_destroy(parm_ctx *c) {
     if (!c) return 0;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
+    parm_shard_destroy(c);
     void *ptrs[] = {c->pos, c->pos_alt, c->v, c->a, c->f, c->v_alt, c->a_alt, c->f_alt, c->order, c->order_alt,
-                    c->slot_of, c->d_stage, c->d_red};
+                    c->slot_of, c->d_stage, c->d_red, c->ghost, c->ghost_alt};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     if (c->h_red) cudaFreeHost(c->h_red);
@@ -298,6 +309,7 @@ static bool aos_block(const parm_ctx *c, unsigned mask, const double *const p[5]
 
 static int transfer(parm_ctx *c, bool upload, unsigned mask, const double *const p[5], size_t sv, size_t sm) {
     CK(cudaSetDevice(c->device));
+    if (c->sh.on) { parm_set_error("sharded context: use parm_shard_set_atoms / parm_shard_get_atoms"); return PARM_ERR_INVALID; }
     mask &= PARM_ALL;
     if (!mask || c->n == 0) return 0;
     const size_t vec = (size_t)c->D * 8;
@@ -489,6 +501,7 @@ extern "C" int parm_reduce(parm_ctx *c, int what, const double *v0, double *out)
     CK_LAUNCH(c);
     k_reduce_final<<<1, RED_BLOCK, 0, c->stream>>>(c->d_red + RED_MAXQ, nb, c->d_red);
     CK_LAUNCH(c);
+    if (c->sh.on) PTRY(parm_shard_allreduce_sum(c, c->d_red, RED_MAXQ));
     CK(cudaMemcpyAsync(c->h_red, c->d_red, RED_MAXQ * 8, cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
     switch (what) {
