@@ -1,0 +1,28 @@
+"""N > 1 path: host-side logic on CPU with world_size-2 gloo; full parity on 2 GPUs when the box has them."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _torchrun(script, nproc, port, timeout):
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(nproc),
+           "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.join(ROOT, "tests", script)]
+    return subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, cwd=ROOT)
+
+
+def test_slab_host_logic_gloo_world2(oracle_built):
+    r = _torchrun("_gloo_worker.py", 2, 29541, 300)
+    assert r.returncode == 0 and "GLOO_WORKER_PASSED" in r.stdout, r.stdout[-2000:] + r.stderr[-3000:]
+
+
+@pytest.mark.gpu
+def test_two_gpu_parity_vs_oracle(oracle_built):
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (run with gpurun --gpus 2)")
+    r = _torchrun("mgpu_check.py", 2, 29542, 600)
+    assert r.returncode == 0 and "MGPU_CHECK_PASSED" in r.stdout, r.stdout[-2000:] + r.stderr[-3000:]
