@@ -136,6 +136,7 @@ struct parm_nlist {
     std::vector<double> h_diam; // by AtomVec index; < 0: not a member
     bool have_diam;
     double maxdiam, mindiam;
+    bool uniform;        // every atom a member, one common diameter
     double *d_diam_id;   // by AtomVec index
     double *d_diam;      // by slot
     double *xlast;       // [3][npad] by slot: lastlocs (trackers.hpp:165)

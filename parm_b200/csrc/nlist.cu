@@ -158,11 +158,12 @@ __device__ __noinline__ bool pair_pred_exact(const double4 *__restrict__ pos, co
 // lanes load 32 consecutive candidates at once (coalesced), then the warp loops over the tile's
 // atoms of that cell (their wrapped coordinates are broadcast from shared memory), each lane tests
 // its candidate, and the survivors are compacted with ballot + popc into the atom's row.
-template <bool SMALLBOX>
+// UNIFORM: every atom is a list member and all diameters are equal, so the threshold is a constant.
+template <bool SMALLBOX, bool UNIFORM>
 __global__ void __launch_bounds__(BUILD_WARPS * 32)
 k_build(const double4 *__restrict__ pos, const double4 *__restrict__ pw, const double *__restrict__ diam,
         const uint32_t *__restrict__ cid, const uint32_t *__restrict__ cell_start, uint32_t n, BoxDev box, GridDev g,
-        StencilDev st, double skin, double lmax, double thr_min, uint32_t kmax, uint32_t *__restrict__ nbr,
+        StencilDev st, double skin, double lmax, double thr_min, double uthr, uint32_t kmax, uint32_t *__restrict__ nbr,
         uint32_t *__restrict__ cnt, NlistFlags *flags, const uint8_t *__restrict__ ghost) {
     __shared__ double4 s_w[BUILD_WARPS][32];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -183,6 +184,7 @@ k_build(const double4 *__restrict__ pos, const double4 *__restrict__ pw, const d
     // a test is decided by the fast arithmetic when dsq is outside [lo, 1) * thr_hi^2
     const double delta = band_delta(flags, lmax, thr_min);
     const double lo = ((1.0 - delta) / (1.0 + delta)) * ((1.0 - delta) / (1.0 + delta));
+    const double uthr2 = uthr * (1.0 + delta) * (uthr * (1.0 + delta)), uthr2lo = uthr2 * lo;
     const unsigned lt = (1u << lane) - 1u;
     uint32_t count = 0;
     unsigned done = __ballot_sync(0xffffffffu, !member);
@@ -225,7 +227,7 @@ k_build(const double4 *__restrict__ pos, const double4 *__restrict__ pw, const d
                     const uint32_t jb = cell_start[rowbase + (uint32_t)za], je = cell_start[rowbase + (uint32_t)zb + 1];
                     for (uint32_t jbase = jb; jbase < je; jbase += 32) {
                         const uint32_t j = jbase + lane;
-                        double4 wj = make_double4(0, 0, 0, nan);
+                        double4 wj = make_double4(nan, nan, nan, nan);
                         if (j < je) wj = pw[j];
                         wj.x += sx;
                         wj.y += sy;
@@ -242,10 +244,17 @@ k_build(const double4 *__restrict__ pos, const double4 *__restrict__ pw, const d
                                 dz = min_image_fast(dz, box.L[2], box.invL[2]);
                             }
                             const double dsq = fma(dx, dx, fma(dy, dy, dz * dz));
-                            const double thr = a.w + wj.w; // NaN for non-members / padding lanes
-                            const double thr2 = thr * thr;
-                            bool pass = dsq < thr2 && j != base_i + (uint32_t)b;
-                            if (pass && !(dsq < thr2 * lo)) pass = pair_pred_exact(pos, diam, base_i + b, j, box, skin);
+                            double thr2, thr2lo;
+                            if (UNIFORM) {
+                                thr2 = uthr2;
+                                thr2lo = uthr2lo;
+                            } else {
+                                const double thr = a.w + wj.w; // NaN for non-members / padding lanes
+                                thr2 = thr * thr;
+                                thr2lo = thr2 * lo;
+                            }
+                            bool pass = dsq < thr2 && j != base_i + (uint32_t)b; // padding lanes: dsq is NaN
+                            if (pass && !(dsq < thr2lo)) pass = pair_pred_exact(pos, diam, base_i + b, j, box, skin);
                             const unsigned bal = __ballot_sync(0xffffffffu, pass);
                             if (bal) {
                                 const uint32_t cb = __shfl_sync(0xffffffffu, count, b);
@@ -375,6 +384,10 @@ extern "C" int parm_nlist_set_diameters(parm_nlist *nl, const double *diam) {
     }
     nl->have_diam = any;
     nl->maxdiam = maxd;
+    nl->uniform = any && mind == maxd;
+    if (nl->uniform)
+        for (uint32_t i = 0; i < c->nid; i++)
+            if (!(nl->h_diam[i] >= 0)) { nl->uniform = false; break; }
     nl->mindiam = any ? mind : 0.0;
     if (c->nid) CK(cudaMemcpyAsync(nl->d_diam_id, nl->h_diam.data(), (size_t)c->nid * 8, cudaMemcpyHostToDevice, c->stream));
     if (c->n) {
@@ -534,19 +547,20 @@ int parm_nlist_build_rows(parm_nlist *nl) {
     }
     const unsigned ntiles = (n + 31) / 32;
     const unsigned nblocks = (ntiles + BUILD_WARPS - 1) / BUILD_WARPS;
+    const double uthr = nl->maxdiam + nl->skin;
     for (int attempt = 0; attempt < 8; attempt++) {
         CK(cudaMemsetAsync((char *)nl->d_flags + offsetof(NlistFlags, maxcnt), 0,
                            offsetof(NlistFlags, xmax_bits) - offsetof(NlistFlags, maxcnt), c->stream));
-        if (nl->smallbox)
-            k_build<true><<<nblocks, BUILD_WARPS * 32, 0, c->stream>>>(c->pos, nl->pw, nl->d_diam, nl->cell_id_sorted,
-                                                                      nl->cell_start, n, c->box, nl->g, nl->st, nl->skin,
-                                                                      nl->lmax, nl->thr_min, nl->kmax, nl->nbr, nl->cnt,
-                                                                      nl->d_flags, c->sh.on ? c->ghost : nullptr);
-        else
-            k_build<false><<<nblocks, BUILD_WARPS * 32, 0, c->stream>>>(c->pos, nl->pw, nl->d_diam, nl->cell_id_sorted,
-                                                                       nl->cell_start, n, c->box, nl->g, nl->st, nl->skin,
-                                                                       nl->lmax, nl->thr_min, nl->kmax, nl->nbr, nl->cnt,
-                                                                       nl->d_flags, c->sh.on ? c->ghost : nullptr);
+#define BARGS c->pos, nl->pw, nl->d_diam, nl->cell_id_sorted, nl->cell_start, n, c->box, nl->g, nl->st, nl->skin, nl->lmax, \
+              nl->thr_min, uthr, nl->kmax, nl->nbr, nl->cnt, nl->d_flags, c->sh.on ? c->ghost : nullptr
+        if (nl->smallbox) {
+            if (nl->uniform) k_build<true, true><<<nblocks, BUILD_WARPS * 32, 0, c->stream>>>(BARGS);
+            else k_build<true, false><<<nblocks, BUILD_WARPS * 32, 0, c->stream>>>(BARGS);
+        } else {
+            if (nl->uniform) k_build<false, true><<<nblocks, BUILD_WARPS * 32, 0, c->stream>>>(BARGS);
+            else k_build<false, false><<<nblocks, BUILD_WARPS * 32, 0, c->stream>>>(BARGS);
+        }
+#undef BARGS
         CK_LAUNCH(c);
         if (attempt == 0) PTRY(parm_prof_end(c));
         CK(cudaMemcpyAsync(nl->h_flags, nl->d_flags, sizeof(NlistFlags), cudaMemcpyDeviceToHost, c->stream));
