@@ -49,7 +49,7 @@ __device__ __forceinline__ void pair_eval(const PairConst &P, double dsq, bool w
     } else {
         // rsq = dsq/(sig*sig); if (rsq > cut*cut) -> 0; rsix = sigma^6/r^6
         // f = rij * (12 eps rsix (rsix - 1) / dsq)      (:135-151, :259-267, :1289-1298)
-        if (dsq * P.inv_sig2 > P.cut2) return;
+        if (dsq > P.rc2) return;
         double w = 1.0 / dsq;
         double s2 = P.sig2 * w;
         double ir6 = s2 * s2 * s2;
@@ -69,13 +69,60 @@ __device__ __forceinline__ void pair_eval(const PairConst &P, double dsq, bool w
 // in flight at once (index loads first, then the pos[j] gathers, then the arithmetic), and the
 // team folds its partial force with xor-shuffles. TEAM*U divides 32 so rows (kmax % 32 == 0)
 // are always readable up to the padded end.
-template <int KIND, bool ONE_SPECIES, int MODE, int TEAM, int U>
+// Per-pair mixing on the device for continuously polydisperse systems; same rules as mix() below
+// (sqrt(e1 e2) is formed as sqrt(e1) sqrt(e2): identical to ~1 ulp).
+template <int KIND>
+__device__ __forceinline__ PairConst mix_dev(const double4 &qi, const double4 &qj, const double *__restrict__ tab, int nt,
+                                             bool want_e) {
+    PairConst P;
+    P.sig = (qi.y + qj.y) * 0.5;
+    P.sig2 = P.sig * P.sig;
+    P.inv_sig2 = 0.0;
+    P.cutE = 0.0;
+    P.expo = 0.0;
+    P.cut2 = 1.0;
+    if (KIND == PARM_PAIR_LJREPULSE) {
+        P.eps = qi.x * qj.x;
+        P.rc2 = P.sig2;
+    } else if (KIND == PARM_PAIR_REPULSION) {
+        P.eps = qi.x * qj.x;
+        P.expo = (qi.z + qj.z) * 0.5;
+        P.rc2 = P.sig2;
+    } else {
+        double cut = fmax(qi.z, qj.z);
+        double e;
+        bool shifted = true;
+        if (KIND == PARM_PAIR_LJATTRACTREPULSE) {
+            e = __ldg(tab + (int)qi.w * nt + (int)qj.w);
+            if (e <= 0) { // purely repulsive (interaction.hpp:1261-1266)
+                cut = 1.0;
+                e = fabs(e);
+                shifted = false;
+            }
+        } else {
+            e = qi.x * qj.x;
+        }
+        P.eps = e;
+        P.cut2 = cut * cut;
+        P.rc2 = P.cut2 * P.sig2;
+        if (want_e && shifted) {
+            const double ic6 = 1.0 / (P.cut2 * P.cut2 * P.cut2);
+            const double mid = 1.0 - ic6;
+            P.cutE = KIND == PARM_PAIR_LJCUT ? e * (mid * mid - 1.0) : e * (mid * mid);
+        }
+    }
+    return P;
+}
+
+// SPEC: 0 one species (constants in registers), 1 species table in shared memory, 2 per-atom parameters
+template <int KIND, int SPEC, int MODE, int TEAM, int U>
 __global__ void __launch_bounds__(F_BLOCK)
 k_force(const double4 *__restrict__ pos, const uint32_t *__restrict__ nbr, const uint32_t *__restrict__ cnt, uint32_t kmax,
         const uint8_t *__restrict__ spec, const PairConst *__restrict__ table, int nspecies, PairConst P1, double *f,
-        uint32_t n, uint32_t npad, BoxDev box, int accumulate, double *partials) {
+        uint32_t n, uint32_t npad, BoxDev box, int accumulate, double *partials, const double4 *__restrict__ par,
+        const double *__restrict__ eps_tab, int ntypes) {
     extern __shared__ PairConst s_table[];
-    if (!ONE_SPECIES) {
+    if (SPEC == 1) {
         for (int q = threadIdx.x; q < nspecies * nspecies; q += blockDim.x) s_table[q] = table[q];
         __syncthreads();
     }
@@ -92,7 +139,9 @@ k_force(const double4 *__restrict__ pos, const uint32_t *__restrict__ nbr, const
     const uint32_t my = valid ? cnt[sc] : 0;
     const double4 pi = pos[sc];
     const uint32_t *row = nbr + (size_t)sc * kmax;
-    const PairConst *prow = ONE_SPECIES ? nullptr : s_table + (int)spec[sc] * nspecies;
+    const PairConst *prow = SPEC == 1 ? s_table + (int)spec[sc] * nspecies : nullptr;
+    double4 qi = make_double4(0, 0, 0, 0);
+    if (SPEC == 2) qi = par[sc];
     for (uint32_t k0 = tl; k0 < my; k0 += TEAM * U) {
         uint32_t j[U];
         bool ok[U];
@@ -113,10 +162,13 @@ k_force(const double4 *__restrict__ pos, const uint32_t *__restrict__ nbr, const
             double dz = min_image_fast(pi.z - pj[u].z, box.L[2], box.invL[2]);
             double dsq = dx * dx + (dy * dy + dz * dz);
             double scal, e;
-            if (ONE_SPECIES) {
+            if (SPEC == 0) {
                 pair_eval<KIND>(P1, dsq, want_obs, scal, e);
-            } else {
+            } else if (SPEC == 1) {
                 const PairConst &P = prow[__ldg(spec + j[u])];
+                pair_eval<KIND>(P, dsq, want_obs, scal, e);
+            } else {
+                const PairConst P = mix_dev<KIND>(qi, ld_pos4(par + j[u]), eps_tab, ntypes, want_obs);
                 pair_eval<KIND>(P, dsq, want_obs, scal, e);
             }
             if (!ok[u]) { // padding lane (j == self, dsq == 0): contributes nothing
@@ -195,40 +247,41 @@ __global__ void k_force_fold(const double *__restrict__ partials, uint32_t nbloc
     }
 }
 
-#define FARGS pos, nbr, cnt, kmax, spec, table, nsp, P1, f, n, npad, box, acc, partials
-template <int KIND, bool ONE, int TEAM, int U>
-static cudaError_t launch_mode(int mode, dim3 grid, size_t smem, cudaStream_t st, const double4 *pos, const uint32_t *nbr,
-                               const uint32_t *cnt, uint32_t kmax, const uint8_t *spec, const PairConst *table, int nsp,
-                               PairConst P1, double *f, uint32_t n, uint32_t npad, BoxDev box, int acc, double *partials) {
+#define FARGS pos, nbr, cnt, kmax, spec, table, nsp, P1, f, n, npad, box, acc, partials, par, eps_tab, ntypes
+#define FPARAMS const double4 *pos, const uint32_t *nbr, const uint32_t *cnt, uint32_t kmax, const uint8_t *spec, \
+                const PairConst *table, int nsp, PairConst P1, double *f, uint32_t n, uint32_t npad, BoxDev box, int acc, \
+                double *partials, const double4 *par, const double *eps_tab, int ntypes
+template <int KIND, int SPEC, int TEAM, int U>
+static cudaError_t launch_mode(int mode, dim3 grid, size_t smem, cudaStream_t st, FPARAMS) {
     if (mode == MODE_F) {
-        if (smem > 48 * 1024) cudaFuncSetAttribute(k_force<KIND, ONE, MODE_F, TEAM, U>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        k_force<KIND, ONE, MODE_F, TEAM, U><<<grid, F_BLOCK, smem, st>>>(FARGS);
+        if (smem > 48 * 1024) cudaFuncSetAttribute(k_force<KIND, SPEC, MODE_F, TEAM, U>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        k_force<KIND, SPEC, MODE_F, TEAM, U><<<grid, F_BLOCK, smem, st>>>(FARGS);
     } else if (mode == MODE_FALL) {
-        if (smem > 48 * 1024) cudaFuncSetAttribute(k_force<KIND, ONE, MODE_FALL, TEAM, U>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        k_force<KIND, ONE, MODE_FALL, TEAM, U><<<grid, F_BLOCK, smem, st>>>(FARGS);
+        if (smem > 48 * 1024) cudaFuncSetAttribute(k_force<KIND, SPEC, MODE_FALL, TEAM, U>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        k_force<KIND, SPEC, MODE_FALL, TEAM, U><<<grid, F_BLOCK, smem, st>>>(FARGS);
     } else {
-        if (smem > 48 * 1024) cudaFuncSetAttribute(k_force<KIND, ONE, MODE_OBS, TEAM, U>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        k_force<KIND, ONE, MODE_OBS, TEAM, U><<<grid, F_BLOCK, smem, st>>>(FARGS);
+        if (smem > 48 * 1024) cudaFuncSetAttribute(k_force<KIND, SPEC, MODE_OBS, TEAM, U>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        k_force<KIND, SPEC, MODE_OBS, TEAM, U><<<grid, F_BLOCK, smem, st>>>(FARGS);
     }
     return cudaGetLastError();
 }
 
+template <int KIND, int SPEC>
+static cudaError_t launch_team(int team, int mode, dim3 grid, size_t smem, cudaStream_t st, FPARAMS) {
+    if (team == 4) return launch_mode<KIND, SPEC, 4, 2>(mode, grid, smem, st, FARGS);
+    if (team == 16) return launch_mode<KIND, SPEC, 16, 2>(mode, grid, smem, st, FARGS);
+    return launch_mode<KIND, SPEC, 8, 2>(mode, grid, smem, st, FARGS);
+}
+
 template <int KIND>
-static cudaError_t launch_kind(bool one, int team, int mode, uint32_t natoms, size_t smem, cudaStream_t st, const double4 *pos,
-                               const uint32_t *nbr, const uint32_t *cnt, uint32_t kmax, const uint8_t *spec,
-                               const PairConst *table, int nsp, PairConst P1, double *f, uint32_t n, uint32_t npad,
-                               BoxDev box, int acc, double *partials) {
+static cudaError_t launch_kind(int specmode, int team, int mode, uint32_t natoms, size_t smem, cudaStream_t st, FPARAMS) {
     const dim3 grid((unsigned)(((size_t)natoms * team + F_BLOCK - 1) / F_BLOCK));
-    if (one) {
-        if (team == 4) return launch_mode<KIND, true, 4, 2>(mode, grid, 0, st, FARGS);
-        if (team == 16) return launch_mode<KIND, true, 16, 2>(mode, grid, 0, st, FARGS);
-        return launch_mode<KIND, true, 8, 2>(mode, grid, 0, st, FARGS);
-    }
-    if (team == 4) return launch_mode<KIND, false, 4, 2>(mode, grid, smem, st, FARGS);
-    if (team == 16) return launch_mode<KIND, false, 16, 2>(mode, grid, smem, st, FARGS);
-    return launch_mode<KIND, false, 8, 2>(mode, grid, smem, st, FARGS);
+    if (specmode == 0) return launch_team<KIND, 0>(team, mode, grid, 0, st, FARGS);
+    if (specmode == 1) return launch_team<KIND, 1>(team, mode, grid, smem, st, FARGS);
+    return launch_team<KIND, 2>(team, mode, grid, 0, st, FARGS);
 }
 #undef FARGS
+#undef FPARAMS
 
 // d_out: device pointer to NPART doubles (E, virial, stress[9], contacts, overlaps) or NULL
 static int launch_forces(parm_inter *it, int mode, bool accumulate, double *d_out) {
@@ -241,10 +294,10 @@ static int launch_forces(parm_inter *it, int mode, bool accumulate, double *d_ou
         return 0;
     }
     // lanes per atom: enough entries per lane to keep its loop busy, few enough to fill the last pass
-    int team = 8;
+    int team = 4; // measured at n ~ 110 (N=1e6 LJ): TEAM=4 0.368 ms, TEAM=8 0.385 ms, TEAM=16 0.476 ms
     {
         double mean = (double)nl->total_full / (double)(c->n ? c->n : 1);
-        if (mean < 24) team = 4;
+        if (mean > 400) team = 8;
         static int forced = -1;
         if (forced < 0) { const char *e = getenv("PARM_B200_TEAM"); forced = e ? atoi(e) : 0; }
         if (forced == 4 || forced == 8 || forced == 16) team = forced;
@@ -260,12 +313,13 @@ static int launch_forces(parm_inter *it, int mode, bool accumulate, double *d_ou
         it->partial_doubles = (size_t)nblocks * NPART;
         CK(cudaMalloc(&it->d_partials, it->partial_doubles * 8));
     }
-    const bool one = it->nspecies == 1;
-    size_t smem = one ? 0 : (size_t)it->nspecies * it->nspecies * sizeof(PairConst);
+    const int specmode = it->generic ? 2 : (it->nspecies == 1 ? 0 : 1);
+    size_t smem = specmode == 1 ? (size_t)it->nspecies * it->nspecies * sizeof(PairConst) : 0;
     PairConst P1 = it->h_table[0];
     cudaError_t e;
-#define ARGS one, team, mode, c->n, smem, c->stream, c->pos, nl->nbr, nl->cnt, nl->kmax, it->d_spec, it->d_table, \
-             it->nspecies, P1, c->f, c->n, c->npad, c->box, accumulate ? 1 : 0, it->d_partials
+#define ARGS specmode, team, mode, c->n, smem, c->stream, c->pos, nl->nbr, nl->cnt, nl->kmax, it->d_spec, it->d_table, \
+             it->nspecies, P1, c->f, c->n, c->npad, c->box, accumulate ? 1 : 0, it->d_partials, it->d_par, it->d_eps_table, \
+             it->ntypes
     switch (it->kind) {
         case PARM_PAIR_LJREPULSE: e = launch_kind<PARM_PAIR_LJREPULSE>(ARGS); break;
         case PARM_PAIR_REPULSION: e = launch_kind<PARM_PAIR_REPULSION>(ARGS); break;
@@ -322,11 +376,17 @@ extern "C" int parm_inter_destroy(parm_inter *it) {
     if (it->d_spec) cudaFree(it->d_spec);
     if (it->d_table) cudaFree(it->d_table);
     if (it->d_partials) cudaFree(it->d_partials);
+    if (it->d_par_id) cudaFree(it->d_par_id);
+    if (it->d_par) cudaFree(it->d_par);
+    if (it->d_eps_table) cudaFree(it->d_eps_table);
     c->inters.erase(std::remove(c->inters.begin(), c->inters.end(), it), c->inters.end());
     delete it;
     return 0;
 }
 
+__global__ void k_gather_par(const double4 *__restrict__ par_id, const uint32_t *__restrict__ order, uint32_t n, double4 *par) {
+    for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < n; s += gridDim.x * blockDim.x) par[s] = par_id[order[s]];
+}
 __global__ void k_gather_spec(const uint8_t *__restrict__ spec_id, const uint32_t *__restrict__ order, uint32_t n, uint8_t *spec) {
     for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < n; s += gridDim.x * blockDim.x) spec[s] = spec_id[order[s]];
 }
@@ -336,7 +396,8 @@ int parm_inter_regather(parm_inter *it) {
     if (!c->n) return 0;
     unsigned nb = (c->n + 255) / 256;
     unsigned cap = (unsigned)c->num_sms * 8;
-    k_gather_spec<<<nb < cap ? nb : cap, 256, 0, c->stream>>>(it->d_spec_id, c->order, c->n, it->d_spec);
+    if (it->generic) k_gather_par<<<nb < cap ? nb : cap, 256, 0, c->stream>>>(it->d_par_id, c->order, c->n, it->d_par);
+    else k_gather_spec<<<nb < cap ? nb : cap, 256, 0, c->stream>>>(it->d_spec_id, c->order, c->n, it->d_spec);
     CK_LAUNCH(c);
     return 0;
 }
@@ -378,6 +439,7 @@ static PairConst mix(int kind, const double *p1, uint32_t t1, const double *p2, 
     }
     P.sig2 = P.sig * P.sig;
     P.inv_sig2 = 1.0 / P.sig2;
+    P.rc2 = kind == PARM_PAIR_REPULSION ? P.sig2 : P.cut2 * P.sig2;
     return P;
 }
 
@@ -397,6 +459,7 @@ extern "C" int parm_inter_set_params(parm_inter *it, const double *params, const
                 }
     }
     typedef std::tuple<double, double, double, uint32_t> Key;
+    bool too_many = false;
     std::map<Key, int> ids;
     std::vector<Key> keys;
     std::vector<double> diam(c->nid, -1.0);
@@ -411,17 +474,39 @@ extern "C" int parm_inter_set_params(parm_inter *it, const double *params, const
         if (f == ids.end()) {
             id = (int)keys.size();
             if (id >= PARM_MAX_SPECIES) {
-                parm_set_error("NListed: more than %d distinct per-atom parameter tuples (continuous polydispersity) "
-                               "is outside the current scope; see DESIGN.md", PARM_MAX_SPECIES);
-                return PARM_ERR_UNSUPPORTED;
+                too_many = true; // continuous polydispersity: per-atom parameters, mixed per pair on the device
+                id = 0;
+            } else {
+                ids[k] = id;
+                keys.push_back(k);
             }
-            ids[k] = id;
-            keys.push_back(k);
         } else
             id = f->second;
         it->h_spec_id[i] = (uint8_t)id;
         // A::max_size(): sigma (:864, :1464) or sigma*sigcut (:905, :1017)
         diam[i] = (kind == PARM_PAIR_LJREPULSE || kind == PARM_PAIR_REPULSION) ? p[1] : p[1] * p[2];
+    }
+    it->generic = too_many;
+    it->ntypes = ntypes > 0 ? ntypes : 1;
+    if (too_many) {
+        keys.resize(1);
+        it->h_par_id.assign(4 * (size_t)std::max(c->npad, c->nid_pad), 0.0);
+        for (uint32_t i = 0; i < c->nid; i++) {
+            if (member && !member[i]) continue;
+            const double *p = params + 3 * (size_t)i;
+            double *q = &it->h_par_id[4 * (size_t)i];
+            q[0] = kind == PARM_PAIR_LJATTRACTREPULSE ? 0.0 : sqrt(p[0]);
+            q[1] = p[1];
+            q[2] = kind == PARM_PAIR_LJREPULSE ? 0.0 : p[2];
+            q[3] = (kind == PARM_PAIR_LJATTRACTREPULSE && type) ? (double)type[i] : 0.0;
+        }
+        const size_t npar = std::max(c->npad, c->nid_pad);
+        if (!it->d_par_id) CK(cudaMalloc(&it->d_par_id, npar * sizeof(double4)));
+        if (!it->d_par) CK(cudaMalloc(&it->d_par, (size_t)c->npad * sizeof(double4)));
+        CK(cudaMemcpyAsync(it->d_par_id, it->h_par_id.data(), npar * sizeof(double4), cudaMemcpyHostToDevice, c->stream));
+        if (it->d_eps_table) { cudaFree(it->d_eps_table); it->d_eps_table = 0; }
+        CK(cudaMalloc(&it->d_eps_table, sizeof(double) * it->ntypes * it->ntypes));
+        if (eps_table) CK(cudaMemcpyAsync(it->d_eps_table, eps_table, sizeof(double) * it->ntypes * it->ntypes, cudaMemcpyHostToDevice, c->stream));
     }
     int S = (int)keys.size();
     if (S == 0) { S = 1; keys.push_back(Key(1.0, 1.0, 1.0, 0)); }

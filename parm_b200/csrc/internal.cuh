@@ -52,9 +52,9 @@ struct PairConst {
     double sig2;     // sig*sig
     double inv_sig2; // 1/(sig*sig)
     double cut2;     // cut_distance^2 in units of sigma (kinds 0: 1, 2, 3)
+    double rc2;      // cutoff in distance units squared: cut2 * sig2 (kind 1: sig2)
     double cutE;     // cut_energy
     double expo;     // exponent (kind 1)
-    double pad;
 };
 
 // Slab decomposition state (one process per GPU; csrc/shard.cu). The slab axis is x (axis 0, the
@@ -182,7 +182,13 @@ struct parm_inter {
     uint8_t *d_spec;                // by slot
     PairConst *d_table;             // nspecies x nspecies
     std::vector<PairConst> h_table;
-    bool uniform_expo2;             // kind 1: all exponents == 2
+    // more than PARM_MAX_SPECIES distinct tuples (continuous polydispersity): per-atom parameters are
+    // gathered with the neighbour and mixed per pair on the device
+    bool generic;
+    std::vector<double> h_par_id;   // 4 doubles per AtomVec index: sqrt(eps), sigma, exponent|sigcut, type
+    double4 *d_par_id, *d_par;      // by AtomVec index / by slot
+    double *d_eps_table;            // kind 2: ntypes x ntypes
+    int ntypes;
     double *d_partials;
     size_t partial_doubles;
 };

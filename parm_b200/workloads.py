@@ -131,7 +131,8 @@ def hertzian12(seed=131):
                 name="hertzian12")
 
 
-def random_system(n, ndim, kind, seed, rho=0.9, ntypes=2, polydisperse=True, T=1.0, skin=0.3, frozen=0):
+def random_system(n, ndim, kind, seed, rho=0.9, ntypes=2, polydisperse=True, T=1.0, skin=0.3, frozen=0,
+                  continuous=False):
     """Small ragged random systems for parity tests: jittered lattice with vacancies, shifted by
     random whole box images, non-cubic box, per-atom eps/sigma/exponent/sigcut, several
     types with negative / zero table entries (LJAttractRepulsePair's repulsive-only and off branches)."""
@@ -154,6 +155,9 @@ def random_system(n, ndim, kind, seed, rho=0.9, ntypes=2, polydisperse=True, T=1
     # discrete species (the device path tabulates pair constants per species pair)
     sig = rng.choice([0.8, 1.0, 1.2, 1.4], n) if polydisperse else np.ones(n)
     eps = rng.choice([0.5, 1.5], n)
+    if continuous:  # every atom its own (eps, sigma): exercises the per-pair mixing path on the device
+        sig = rng.uniform(0.8, 1.4, n)
+        eps = rng.uniform(0.5, 1.5, n)
     third = {KIND_LJREPULSE: np.zeros(n), KIND_REPULSION: rng.choice([2.0, 2.5, 1.5], n),
              KIND_LJATTRACTREPULSE: rng.choice([2.0, 2.5], n), KIND_LJCUT: rng.choice([2.0, 2.5], n)}[kind]
     params = np.stack([eps, sig, third], axis=1)

@@ -64,3 +64,30 @@ def test_verlet_trajectory(oracle_built, ndim, kind):
     ga, gb = nl.pairs()
     ca_, cb_ = c.pairs()
     assert np.array_equal(ga, ca_) and np.array_equal(gb, cb_)
+
+
+@pytest.mark.parametrize("ndim,kind", CASES)
+def test_continuous_polydispersity(oracle_built, ndim, kind):
+    """More distinct (eps, sigma, ...) tuples than the species table holds: parameters are gathered per
+    neighbour and mixed per pair on the device (interaction.hpp:878-883, 1531-1536, 1255-1270, 970-974)."""
+    from parm_b200 import sim
+    w = W.random_system(600, ndim, kind, seed=70 + kind + 10 * ndim, ntypes=3, frozen=3, continuous=True, T=0.5)
+    box, atoms, inter, nl, collec = sim.from_workload(w)
+    c = cpu_system(backends(oracle_built)[-1], w)
+    ga, gb = nl.pairs()
+    ca, cb = c.pairs()
+    assert np.array_equal(ga, ca) and np.array_equal(gb, cb)
+    atoms.reset_forces()
+    gp = inter.set_forces_get_pressure(box)
+    cf, cp = c.forces_and_pressure()
+    assert rel_err_vec(atoms.peek("f"), cf) < TOL
+    assert rel_err(gp, cp) < TOL
+    assert rel_err(inter.energy(box), c.inter_energy()) < TOL
+    assert rel_err(inter.stress(box), c.inter_stress()) < TOL
+    collec.set_forces(True)
+    c.set_forces(True)
+    collec.timestep(40)
+    c.timestep(40)
+    assert nl.which() == c.which()
+    assert rel_err_vec(atoms.peek("x") - w["x"], c.get_atoms()[0] - w["x"]) < 1e-9
+    assert rel_err(collec.energy(), c.energy()) < 1e-10
