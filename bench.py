@@ -258,7 +258,7 @@ def run_ours(args):
 
     cpu = None
     if not args.no_cpu:
-        cs, cw = 40, 3
+        cs, cw = 100, 3   # ~15 s of single-core work
         val, dt, ncpu, kind = time_cpu(cs, cw)
         cpu = {"value": val, "unit": UNIT, "cores": 1, "kind": "reference" if kind == "ref" else "port",
                "sample": cpu_sample_desc(ncpu, cs, kind)}
