@@ -285,6 +285,179 @@ k_build(const double4 *__restrict__ pos, const double4 *__restrict__ pw, const d
     }
 }
 
+// ---- K5b: cell-per-warp build (default) ------------------------------------------------------
+// One warp owns one cell; lane l owns the cell's l-th atom (cells with more than 32 atoms are walked
+// in chunks). For every block of 32 consecutive candidates of the stencil the warp stages the block
+// in shared memory (one coalesced load), then every lane tests ITS atom against the 32 candidates
+// (broadcast shared-memory reads, no shuffles or ballots) and collects a 32-bit pass mask. Survivors
+// are appended to the lane's own row through an 8-entry shared-memory buffer that is written out as
+// one full 32-byte sector, so the row stores cost one L2 transaction per 8 neighbours. Same banded
+// classification / exact predicate as k_build; ~2.4x fewer instructions per candidate test.
+#define CB_WARPS 4
+template <bool SMALLBOX, bool UNIFORM>
+__global__ void __launch_bounds__(CB_WARPS * 32)
+k_build_cell(const double4 *__restrict__ pos, const double4 *__restrict__ pw, const double *__restrict__ diam,
+             const uint32_t *__restrict__ cell_start, uint32_t ncell, uint32_t n, BoxDev box, GridDev g, StencilDev st,
+             double skin, double lmax, double thr_min, double uthr, uint32_t kmax, uint32_t *__restrict__ nbr,
+             uint32_t *__restrict__ cnt, NlistFlags *flags, const uint8_t *__restrict__ ghost) {
+    __shared__ double4 s_c[CB_WARPS][32];
+    __shared__ uint32_t s_buf[CB_WARPS][8][32];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const uint32_t cur = blockIdx.x * CB_WARPS + wib;
+    if (cur >= ncell) return;
+    const uint32_t a0 = cell_start[cur], a1 = cell_start[cur + 1];
+    if (a0 == a1) return;
+    const double nan = __longlong_as_double(0x7ff8000000000000LL);
+    const double delta = band_delta(flags, lmax, thr_min);
+    const double lo = ((1.0 - delta) / (1.0 + delta)) * ((1.0 - delta) / (1.0 + delta));
+    const double uthr2 = uthr * (1.0 + delta) * (uthr * (1.0 + delta)), uthr2lo = uthr2 * lo;
+    const int cz = (int)(cur % (uint32_t)g.nc[2]);
+    const uint32_t t = cur / (uint32_t)g.nc[2];
+    const int cy = (int)(t % (uint32_t)g.nc[1]);
+    const int cx = (int)(t / (uint32_t)g.nc[1]);
+    int x0 = st.full[0] ? cx - st.sub : 0, x1 = st.full[0] ? cx + st.sub : g.nc[0] - 1;
+    if (st.open0) {
+        x0 = max(cx - st.sub, 0);
+        x1 = min(cx + st.sub, g.nc[0] - 1);
+    }
+    const int y0 = st.full[1] ? cy - st.sub : 0, y1 = st.full[1] ? cy + st.sub : g.nc[1] - 1;
+    const int z0 = st.full[2] ? cz - st.sub : 0, z1 = st.full[2] ? cz + st.sub : g.nc[2] - 1;
+    unsigned long long wsum_tot = 0;
+    uint32_t wmax_tot = 0;
+    for (uint32_t chunk = a0; chunk < a1; chunk += 32) {
+        const uint32_t i = chunk + lane;
+        const bool valid = i < a1;
+        double4 wi = make_double4(0, 0, 0, nan);
+        if (valid) wi = pw[i];
+        const bool member = valid && wi.w == wi.w && !(ghost && ghost[i]);
+        if (!__any_sync(0xffffffffu, member)) {
+            if (valid) cnt[i] = 0;
+            continue;
+        }
+        uint32_t count = 0;
+        uint32_t *row = nbr + (size_t)(valid ? i : a0) * kmax;
+        for (int xx = x0; xx <= x1; xx++) {
+            int x2 = xx;
+            double sx = 0.0;
+            if (x2 < 0) { x2 += g.nc[0]; sx = -box.L[0]; }
+            else if (x2 >= g.nc[0]) { x2 -= g.nc[0]; sx = box.L[0]; }
+            for (int yy = y0; yy <= y1; yy++) {
+                int y2 = yy;
+                double sy = 0.0;
+                if (y2 < 0) { y2 += g.nc[1]; sy = -box.L[1]; }
+                else if (y2 >= g.nc[1]) { y2 -= g.nc[1]; sy = box.L[1]; }
+                const uint32_t rowbase = ((uint32_t)x2 * (uint32_t)g.nc[1] + (uint32_t)y2) * (uint32_t)g.nc[2];
+                for (int seg = 0; seg < 3; seg++) {
+                    int za, zb;
+                    double sz = 0.0;
+                    if (seg == 0) { za = z0 < 0 ? z0 + g.nc[2] : 1; zb = z0 < 0 ? g.nc[2] - 1 : 0; sz = -box.L[2]; }
+                    else if (seg == 1) { za = z0 < 0 ? 0 : z0; zb = z1 >= g.nc[2] ? g.nc[2] - 1 : z1; }
+                    else { za = z1 >= g.nc[2] ? 0 : 1; zb = z1 >= g.nc[2] ? z1 - g.nc[2] : 0; sz = box.L[2]; }
+                    if (za > zb) continue;
+                    const uint32_t jb = cell_start[rowbase + (uint32_t)za], je = cell_start[rowbase + (uint32_t)zb + 1];
+                    for (uint32_t jbase = jb; jbase < je; jbase += 32) {
+                        {   // stage 32 candidates (image shift applied once per candidate)
+                            const uint32_t j = jbase + lane;
+                            double4 wj = make_double4(nan, nan, nan, nan);
+                            if (j < je) wj = pw[j];
+                            wj.x += sx;
+                            wj.y += sy;
+                            wj.z += sz;
+                            __syncwarp();
+                            s_c[wib][lane] = wj;
+                            __syncwarp();
+                        }
+                        const int nb = (int)min(32u, je - jbase);
+                        const uint32_t iself = i - jbase; // candidate index of this lane's own atom, if in the block
+                        uint32_t m = 0;
+                        bool near_any = false;
+                        // fully unrolled: the bit position is an immediate; lanes past the end of the run hold NaN
+#pragma unroll
+                        for (int c = 0; c < 32; c++) {
+                            const double4 q = s_c[wib][c];
+                            double dx = wi.x - q.x, dy = wi.y - q.y, dz = wi.z - q.z;
+                            if (SMALLBOX) {
+                                if (!st.open0) dx = min_image_fast(dx, box.L[0], box.invL[0]);
+                                dy = min_image_fast(dy, box.L[1], box.invL[1]);
+                                dz = min_image_fast(dz, box.L[2], box.invL[2]);
+                            }
+                            const double dsq = fma(dx, dx, fma(dy, dy, dz * dz));
+                            double thr2, thr2lo;
+                            if (UNIFORM) {
+                                thr2 = uthr2;
+                                thr2lo = uthr2lo;
+                            } else {
+                                const double thr = wi.w + q.w; // NaN for non-members
+                                thr2 = thr * thr;
+                                thr2lo = thr2 * lo;
+                            }
+                            const bool pass = dsq < thr2;
+                            near_any |= pass && !(dsq < thr2lo);
+                            if (pass) m |= 1u << c;
+                        }
+                        if (iself < 32u) m &= ~(1u << iself); // never its own neighbour
+                        if (__any_sync(0xffffffffu, near_any && member)) {
+                            // some test fell inside the band (~1e-9 of them): decide with the reference's exact predicate
+                            if (near_any && member) {
+                                m = 0;
+                                for (int c = 0; c < nb; c++) {
+                                    const double4 q = s_c[wib][c];
+                                    double dx = wi.x - q.x, dy = wi.y - q.y, dz = wi.z - q.z;
+                                    if (SMALLBOX) {
+                                        if (!st.open0) dx = min_image_fast(dx, box.L[0], box.invL[0]);
+                                        dy = min_image_fast(dy, box.L[1], box.invL[1]);
+                                        dz = min_image_fast(dz, box.L[2], box.invL[2]);
+                                    }
+                                    const double dsq = fma(dx, dx, fma(dy, dy, dz * dz));
+                                    const double thr = UNIFORM ? uthr * (1.0 + delta) : wi.w + q.w;
+                                    const double thr2 = thr * thr;
+                                    bool pass = dsq < thr2 && iself != (uint32_t)c;
+                                    if (pass && !(dsq < thr2 * lo)) pass = pair_pred_exact(pos, diam, i, jbase + c, box, skin);
+                                    m |= (pass ? 1u : 0u) << c;
+                                }
+                            }
+                        }
+                        if (!member) m = 0;
+                        while (m) { // append this lane's survivors; a full 8-entry buffer leaves as one 32-byte sector
+                            const int bit = __ffs(m) - 1;
+                            m &= m - 1;
+                            s_buf[wib][count & 7u][lane] = jbase + (uint32_t)bit;
+                            count++;
+                            if ((count & 7u) == 0 && count <= kmax) {
+                                uint4 u0, u1;
+                                u0.x = s_buf[wib][0][lane]; u0.y = s_buf[wib][1][lane]; u0.z = s_buf[wib][2][lane]; u0.w = s_buf[wib][3][lane];
+                                u1.x = s_buf[wib][4][lane]; u1.y = s_buf[wib][5][lane]; u1.z = s_buf[wib][6][lane]; u1.w = s_buf[wib][7][lane];
+                                uint4 *dst = reinterpret_cast<uint4 *>(row + (count - 8));
+                                dst[0] = u0;
+                                dst[1] = u1;
+                            }
+                        }
+                    }
+                }
+            }
+        }
+        if (member) { // tail of the row
+            const uint32_t done = count & ~7u;
+            for (uint32_t k = done; k < count && k < kmax; k++) row[k] = s_buf[wib][k & 7u][lane];
+        }
+        if (valid) cnt[i] = count;
+        wsum_tot += count;
+        wmax_tot = max(wmax_tot, count);
+    }
+    // totals: integer atomics are order independent, so the result is deterministic
+    unsigned long long wsum = wsum_tot;
+    uint32_t wmax = wmax_tot;
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+        wsum += __shfl_xor_sync(0xffffffffu, wsum, o);
+        wmax = max(wmax, __shfl_xor_sync(0xffffffffu, wmax, o));
+    }
+    if (lane == 0 && wmax) {
+        atomicAdd(&flags->total, wsum);
+        atomicMax(&flags->maxcnt, wmax);
+    }
+}
+
 // ---- standalone drift check (update_list(false) outside timestep()) -------------------
 __global__ void __launch_bounds__(256)
 k_drift(const double4 *__restrict__ pos, const double *__restrict__ xlast, const double *__restrict__ diam, uint32_t n,
@@ -551,9 +724,22 @@ int parm_nlist_build_rows(parm_nlist *nl) {
     for (int attempt = 0; attempt < 8; attempt++) {
         CK(cudaMemsetAsync((char *)nl->d_flags + offsetof(NlistFlags, maxcnt), 0,
                            offsetof(NlistFlags, xmax_bits) - offsetof(NlistFlags, maxcnt), c->stream));
+#define CARGS c->pos, nl->pw, nl->d_diam, nl->cell_start, nl->ncell, n, c->box, nl->g, nl->st, nl->skin, nl->lmax, \
+              nl->thr_min, uthr, nl->kmax, nl->nbr, nl->cnt, nl->d_flags, c->sh.on ? c->ghost : nullptr
 #define BARGS c->pos, nl->pw, nl->d_diam, nl->cell_id_sorted, nl->cell_start, n, c->box, nl->g, nl->st, nl->skin, nl->lmax, \
               nl->thr_min, uthr, nl->kmax, nl->nbr, nl->cnt, nl->d_flags, c->sh.on ? c->ghost : nullptr
-        if (nl->smallbox) {
+        static int per_cell = -1;
+        if (per_cell < 0) { const char *e = getenv("PARM_B200_BUILD_PER_CELL"); per_cell = e ? atoi(e) : 1; }
+        if (per_cell) {
+            const unsigned cblocks = (nl->ncell + CB_WARPS - 1) / CB_WARPS;
+            if (nl->smallbox) {
+                if (nl->uniform) k_build_cell<true, true><<<cblocks, CB_WARPS * 32, 0, c->stream>>>(CARGS);
+                else k_build_cell<true, false><<<cblocks, CB_WARPS * 32, 0, c->stream>>>(CARGS);
+            } else {
+                if (nl->uniform) k_build_cell<false, true><<<cblocks, CB_WARPS * 32, 0, c->stream>>>(CARGS);
+                else k_build_cell<false, false><<<cblocks, CB_WARPS * 32, 0, c->stream>>>(CARGS);
+            }
+        } else if (nl->smallbox) {
             if (nl->uniform) k_build<true, true><<<nblocks, BUILD_WARPS * 32, 0, c->stream>>>(BARGS);
             else k_build<true, false><<<nblocks, BUILD_WARPS * 32, 0, c->stream>>>(BARGS);
         } else {
@@ -561,6 +747,7 @@ int parm_nlist_build_rows(parm_nlist *nl) {
             else k_build<false, false><<<nblocks, BUILD_WARPS * 32, 0, c->stream>>>(BARGS);
         }
 #undef BARGS
+#undef CARGS
         CK_LAUNCH(c);
         if (attempt == 0) PTRY(parm_prof_end(c));
         CK(cudaMemcpyAsync(nl->h_flags, nl->d_flags, sizeof(NlistFlags), cudaMemcpyDeviceToHost, c->stream));
