@@ -268,6 +268,10 @@ static cudaError_t launch_mode(int mode, dim3 grid, size_t smem, cudaStream_t st
 
 template <int KIND, int SPEC>
 static cudaError_t launch_team(int team, int mode, dim3 grid, size_t smem, cudaStream_t st, FPARAMS) {
+    static int u4 = -1;
+    if (u4 < 0) { const char *e = getenv("PARM_B200_U"); u4 = e ? atoi(e) : 2; }
+    if (team == 4 && u4 == 4) return launch_mode<KIND, SPEC, 4, 4>(mode, grid, smem, st, FARGS);
+    if (team == 4 && u4 == 1) return launch_mode<KIND, SPEC, 4, 1>(mode, grid, smem, st, FARGS);
     if (team == 4) return launch_mode<KIND, SPEC, 4, 2>(mode, grid, smem, st, FARGS);
     if (team == 16) return launch_mode<KIND, SPEC, 16, 2>(mode, grid, smem, st, FARGS);
     return launch_mode<KIND, SPEC, 8, 2>(mode, grid, smem, st, FARGS);

@@ -152,3 +152,57 @@ def test_errors():
         lj.add(sim.IEpsSigCutAtom(atoms.get_id(1), [0.5, 1.0], 1, 1.0, 2.5))  # duplicate add
     with pytest.raises(capi.ParmUnsupported):
         sim.NeighborList(box, atoms, 0.2)  # second list on the same AtomVec
+
+
+def test_drift_trigger_matches_reference_rule(oracle_built):
+    """NeighborList::update_list(false) (trackers.cpp:23-53): rebuild iff the two largest displacements since the
+    last rebuild sum to >= skin -- including the equality case and moves by whole box images."""
+    from parm_b200 import sim
+    w = W.lj_lattice((7, 7, 7), seed=9)
+    w["skin"] = 0.25  # exactly representable, so 0.125 + 0.125 == skin tests the >=
+    box, atoms, inter, nl, _ = sim.from_workload(w, collection=False)
+    c = cpu_system("port", w, collection=False)
+
+    def move(dx_list):
+        x = w["x"].copy()
+        for k, d in enumerate(dx_list):
+            x[3 + 5 * k] += d
+        atoms.x[:] = x
+        c.set_atoms(x=x)
+        return nl.update_list(False), c.update_list(False)
+
+    base = nl.which()
+    assert move([[0.1, 0, 0], [0, 0.1, 0]]) == (False, False)
+    assert move([[0.125, 0, 0], [0, 0, 0.125]]) == (True, True)          # equality rebuilds
+    assert nl.which() == base + 1 == c.which()
+    # lastlocs were reset by the rebuild: the same positions no longer trigger
+    assert (nl.update_list(False), c.update_list(False)) == (False, False)
+    assert move([[0.125, 0, 0], [0, 0, 0.125], [0.2, 0, 0]]) == (False, False)   # only one atom moved since
+    assert move([[0.125, 0, 0], [0, 0, 0.125], [0.2, 0, 0], [0, 0.06, 0]]) == (True, True)
+    # a single atom moved by a whole box image: displacement L alone is >= skin (raw unwrapped positions)
+    x = atoms.peek("x")
+    x[0, 1] += w["L"][1]
+    atoms.x[:] = x
+    c.set_atoms(x=x)
+    assert (nl.update_list(False), c.update_list(False)) == (True, True)
+    a, b = nl.pairs()
+    ca, cb = c.pairs()
+    assert np.array_equal(a, ca) and np.array_equal(b, cb)
+
+
+def test_row_capacity_growth(oracle_built):
+    """Strongly non-uniform density: rows overflow the initial capacity estimate and the build retries."""
+    from parm_b200 import sim
+    w = W.lj_lattice((9, 9, 9), seed=12)
+    x = w["x"].copy()
+    x[:, 0] = x[:, 0] * 0.35  # squeeze everything into a third of the box along x
+    w["x"] = x
+    box, atoms, inter, nl, _ = sim.from_workload(w, collection=False)
+    c = cpu_system("port", w, collection=False)
+    a, b = nl.pairs()
+    ca, cb = c.pairs()
+    assert nl.stats()[1] > 200
+    assert np.array_equal(a, ca) and np.array_equal(b, cb)
+    atoms.reset_forces()
+    inter.set_forces(box)
+    assert rel_err_vec(atoms.peek("f"), c.forces()) < 1e-10
