@@ -34,8 +34,11 @@ __device__ __forceinline__ void top2_warp(double &b1, double &b2) {
 // Block top-2, publish per-block result, and let the last block to arrive fold all blocks
 // and write the rebuild flag (to device memory and to the pinned host mirror).
 // Must be called by every thread of every block of the grid (blockDim.x <= 1024).
+// d_slot / h_slot (optional): per-step decision words read by the NEXT step's kernels (abort guard) and by
+// the host, so the host can enqueue step s+1 before it has seen the decision of step s.
 __device__ __forceinline__ void drift_finish(double b1, double b2, double skin, double *d_top2, unsigned int *counter,
-                                             NlistFlags *dflags, NlistFlags *hflags) {
+                                             NlistFlags *dflags, NlistFlags *hflags, int *d_slot = nullptr,
+                                             int *h_slot = nullptr) {
     __shared__ double s1[32], s2[32];
     __shared__ int s_last;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
@@ -82,6 +85,8 @@ __device__ __forceinline__ void drift_finish(double b1, double b2, double skin, 
             hflags->top2[0] = b1;
             hflags->top2[1] = b2;
             hflags->need_rebuild = need;
+            if (d_slot) *d_slot = need;
+            if (h_slot) *h_slot = need;
             __threadfence_system();
         }
     }

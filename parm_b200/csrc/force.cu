@@ -120,7 +120,8 @@ __global__ void __launch_bounds__(F_BLOCK)
 k_force(const double4 *__restrict__ pos, const uint32_t *__restrict__ nbr, const uint32_t *__restrict__ cnt, uint32_t kmax,
         const uint8_t *__restrict__ spec, const PairConst *__restrict__ table, int nspecies, PairConst P1, double *f,
         uint32_t n, uint32_t npad, BoxDev box, int accumulate, double *partials, const double4 *__restrict__ par,
-        const double *__restrict__ eps_tab, int ntypes) {
+        const double *__restrict__ eps_tab, int ntypes, const int *__restrict__ abort_flag) {
+    if (abort_flag && *abort_flag) return; // speculatively enqueued step whose predecessor asked for a rebuild
     extern __shared__ PairConst s_table[];
     if (SPEC == 1) {
         for (int q = threadIdx.x; q < nspecies * nspecies; q += blockDim.x) s_table[q] = table[q];
@@ -247,10 +248,10 @@ __global__ void k_force_fold(const double *__restrict__ partials, uint32_t nbloc
     }
 }
 
-#define FARGS pos, nbr, cnt, kmax, spec, table, nsp, P1, f, n, npad, box, acc, partials, par, eps_tab, ntypes
+#define FARGS pos, nbr, cnt, kmax, spec, table, nsp, P1, f, n, npad, box, acc, partials, par, eps_tab, ntypes, abortf
 #define FPARAMS const double4 *pos, const uint32_t *nbr, const uint32_t *cnt, uint32_t kmax, const uint8_t *spec, \
                 const PairConst *table, int nsp, PairConst P1, double *f, uint32_t n, uint32_t npad, BoxDev box, int acc, \
-                double *partials, const double4 *par, const double *eps_tab, int ntypes
+                double *partials, const double4 *par, const double *eps_tab, int ntypes, const int *abortf
 template <int KIND, int SPEC, int TEAM, int U>
 static cudaError_t launch_mode(int mode, dim3 grid, size_t smem, cudaStream_t st, FPARAMS) {
     if (mode == MODE_F) {
@@ -288,7 +289,7 @@ static cudaError_t launch_kind(int specmode, int team, int mode, uint32_t natoms
 #undef FPARAMS
 
 // d_out: device pointer to NPART doubles (E, virial, stress[9], contacts, overlaps) or NULL
-static int launch_forces(parm_inter *it, int mode, bool accumulate, double *d_out) {
+static int launch_forces(parm_inter *it, int mode, bool accumulate, double *d_out, const int *abort_flag = nullptr) {
     parm_ctx *c = it->ctx;
     parm_nlist *nl = it->nl;
     if (!it->have_params || nl->updatenum == 0) {
@@ -323,7 +324,7 @@ static int launch_forces(parm_inter *it, int mode, bool accumulate, double *d_ou
     cudaError_t e;
 #define ARGS specmode, team, mode, c->n, smem, c->stream, c->pos, nl->nbr, nl->cnt, nl->kmax, it->d_spec, it->d_table, \
              it->nspecies, P1, c->f, c->n, c->npad, c->box, accumulate ? 1 : 0, it->d_partials, it->d_par, it->d_eps_table, \
-             it->ntypes
+             it->ntypes, abort_flag
     switch (it->kind) {
         case PARM_PAIR_LJREPULSE: e = launch_kind<PARM_PAIR_LJREPULSE>(ARGS); break;
         case PARM_PAIR_REPULSION: e = launch_kind<PARM_PAIR_REPULSION>(ARGS); break;
@@ -341,8 +342,8 @@ static int launch_forces(parm_inter *it, int mode, bool accumulate, double *d_ou
     return 0;
 }
 
-int parm_inter_launch_forces(parm_inter *it, unsigned want, bool accumulate, double *d_out) {
-    return launch_forces(it, want ? MODE_FALL : MODE_F, accumulate, d_out);
+int parm_inter_launch_forces(parm_inter *it, unsigned want, bool accumulate, double *d_out, const int *abort_flag) {
+    return launch_forces(it, want ? MODE_FALL : MODE_F, accumulate, d_out, abort_flag);
 }
 
 // ---- host API ---------------------------------------------------------------------------

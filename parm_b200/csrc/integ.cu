@@ -29,7 +29,8 @@ static inline unsigned grid_for(const parm_ctx *ctx, uint32_t n, unsigned block,
 template <int D>
 __global__ void __launch_bounds__(I_BLOCK)
 k_verlet1(double4 *__restrict__ pos, double *__restrict__ v, const double *__restrict__ a, uint32_t n, uint32_t npad,
-          double dt, double hdt2, double hdt) {
+          double dt, double hdt2, double hdt, const int *__restrict__ abort_flag) {
+    if (abort_flag && *abort_flag) return; // speculative step behind a rebuild request: leave the state alone
     for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < n; s += gridDim.x * blockDim.x) {
         double4 p = pos[s];
         if (frozen_le(p.w)) { // m <= 0 || isinf(m): v = 0, position untouched
@@ -57,7 +58,9 @@ template <int D, bool DRIFT>
 __global__ void __launch_bounds__(I_BLOCK)
 k_verlet2(const double4 *__restrict__ pos, double *__restrict__ v, double *__restrict__ a, const double *__restrict__ f,
           uint32_t n, uint32_t npad, double hdt, const double *__restrict__ xlast, const double *__restrict__ diam,
-          double skin, double *d_top2, unsigned int *counter, NlistFlags *dflags, NlistFlags *hflags) {
+          double skin, double *d_top2, unsigned int *counter, NlistFlags *dflags, NlistFlags *hflags,
+          const int *__restrict__ abort_flag, int *d_slot, int *h_slot) {
+    if (abort_flag && *abort_flag) return;
     double b1 = 0.0, b2 = 0.0;
     for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < n; s += gridDim.x * blockDim.x) {
         const double4 p = pos[s];
@@ -77,7 +80,7 @@ k_verlet2(const double4 *__restrict__ pos, double *__restrict__ v, double *__res
             if (diam[s] >= 0.0) top2_push(b1, b2, drift_dist(p, xlast[s], xlast[npad + s], xlast[2 * (size_t)npad + s]));
         }
     }
-    if (DRIFT) drift_finish(b1, b2, skin, d_top2, counter, dflags, hflags);
+    if (DRIFT) drift_finish(b1, b2, skin, d_top2, counter, dflags, hflags, d_slot, h_slot);
 }
 
 // ---- Philox4x32-10 counter RNG + Box-Muller (production noise of CollectionSol) ---------
@@ -117,7 +120,8 @@ template <int D>
 __global__ void __launch_bounds__(I_BLOCK)
 k_sol1(double4 *__restrict__ pos, double *__restrict__ v, const double *__restrict__ a, const uint32_t *__restrict__ order,
        uint32_t n, uint32_t npad, SolConst K, const double *__restrict__ noise, const uint32_t *__restrict__ mobile_rank,
-       uint64_t step, uint64_t seed) {
+       uint64_t step, uint64_t seed, const int *__restrict__ abort_flag) {
+    if (abort_flag && *abort_flag) return;
     for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < n; s += gridDim.x * blockDim.x) {
         double4 p = pos[s];
         if (frozen_le(p.w)) {
@@ -170,7 +174,9 @@ template <int D, bool DRIFT>
 __global__ void __launch_bounds__(I_BLOCK)
 k_sol2(const double4 *__restrict__ pos, double *__restrict__ v, double *__restrict__ a, const double *__restrict__ f,
        uint32_t n, uint32_t npad, double dtc2, const double *__restrict__ xlast, const double *__restrict__ diam,
-       double skin, double *d_top2, unsigned int *counter, NlistFlags *dflags, NlistFlags *hflags) {
+       double skin, double *d_top2, unsigned int *counter, NlistFlags *dflags, NlistFlags *hflags,
+       const int *__restrict__ abort_flag, int *d_slot, int *h_slot) {
+    if (abort_flag && *abort_flag) return;
     double b1 = 0.0, b2 = 0.0;
     for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < n; s += gridDim.x * blockDim.x) {
         const double4 p = pos[s];
@@ -193,7 +199,7 @@ k_sol2(const double4 *__restrict__ pos, double *__restrict__ v, double *__restri
             if (diam[s] >= 0.0) top2_push(b1, b2, drift_dist(p, xlast[s], xlast[npad + s], xlast[2 * (size_t)npad + s]));
         }
     }
-    if (DRIFT) drift_finish(b1, b2, skin, d_top2, counter, dflags, hflags);
+    if (DRIFT) drift_finish(b1, b2, skin, d_top2, counter, dflags, hflags, d_slot, h_slot);
 }
 
 // ---- a = f/m of Collection::set_forces(true) (collection.cpp:171-178) -----------------------
@@ -271,6 +277,7 @@ extern "C" int parm_integ_destroy(parm_integ *g) {
     cudaStreamSynchronize(g->ctx->stream);
     if (g->d_noise) cudaFree(g->d_noise);
     if (g->d_mobile_rank) cudaFree(g->d_mobile_rank);
+    if (g->ev_ok) { cudaEventDestroy(g->ev[0]); cudaEventDestroy(g->ev[1]); }
     delete g;
     return 0;
 }
@@ -305,13 +312,13 @@ extern "C" int parm_integ_add_tracker(parm_integ *g, parm_nlist *nl) {
     return parm_integ_update_trackers(g); // collection.hpp:117-120
 }
 
-static int launch_all_forces(parm_integ *g) {
+static int launch_all_forces(parm_integ *g, const int *abort_flag = nullptr) {
     parm_ctx *c = g->ctx;
     // atoms->reset_forces(); for each interaction: set_forces(box)   (collection.cpp:160-166)
     if (g->inters.empty()) return parm_reset_forces(c);
     bool first = true;
     for (parm_inter *it : g->inters) {
-        PTRY(parm_inter_launch_forces(it, 0, !first, nullptr)); // first interaction overwrites f == reset + add
+        PTRY(parm_inter_launch_forces(it, 0, !first, nullptr, abort_flag)); // first interaction overwrites f == reset + add
         first = false;
     }
     return 0;
@@ -375,39 +382,46 @@ extern "C" int parm_integ_inject_noise(parm_integ *g, const double *z, size_t le
     CK(cudaMalloc(&g->d_noise, len * 8));
     CK(cudaMemcpy(g->d_noise, z, len * 8, cudaMemcpyHostToDevice));
     g->noise_len = len;
+    g->noise_step0 = g->steps;
     return 0;
 }
 
-static int one_step(parm_integ *g) {
+// Enqueue the kernels of step number `step` (K1 -> halo exchange -> forces -> K3 + drift). With a
+// tracker, the rebuild decision of the step is left in decision slot `slot` (device word + pinned host
+// word). abort_flag (device, may be NULL) is the decision word of the PREVIOUS step: when it is set the
+// kernels of this step return immediately, so a step can be enqueued before the host has seen whether
+// its predecessor asked for a rebuild.
+static int enqueue_step(parm_integ *g, uint64_t step, const int *abort_flag, int slot) {
     parm_ctx *c = g->ctx;
     const uint32_t n = c->n;
     parm_nlist *nl = g->trackers.empty() ? nullptr : g->trackers[0];
     const unsigned grid = grid_for(c, n, I_BLOCK, 8);
     const unsigned grid2 = std::min(grid, 2048u); // drift_finish: d_top2 holds 4096 block entries
     const double dt = g->dt;
+    // sharded: K3 only leaves the local top-2; the global decision is folded after the all-gather
+    int *d_slot = nl && !c->sh.on ? nl->d_slot + slot : nullptr;
+    int *h_slot = nl && !c->sh.on ? nl->h_slot + slot : nullptr;
+#define DRIFTARGS nl ? nl->xlast : nullptr, nl ? nl->d_diam : nullptr, nl ? nl->skin : 0.0, nl ? nl->d_top2 : nullptr, \
+                  nl ? nl->d_counter : nullptr, nl ? nl->d_flags : nullptr, nl ? nl->h_flags : nullptr, abort_flag, d_slot, h_slot
     if (g->type == 0) {
         const double hdt2 = dt * dt / 2, hdt = dt / 2;
         PTRY(parm_prof_begin(c, PARM_PROF_INTEG1));
-        if (c->D == 3) k_verlet1<3><<<grid, I_BLOCK, 0, c->stream>>>(c->pos, c->v, c->a, n, c->npad, dt, hdt2, hdt);
-        else k_verlet1<2><<<grid, I_BLOCK, 0, c->stream>>>(c->pos, c->v, c->a, n, c->npad, dt, hdt2, hdt);
+        if (c->D == 3) k_verlet1<3><<<grid, I_BLOCK, 0, c->stream>>>(c->pos, c->v, c->a, n, c->npad, dt, hdt2, hdt, abort_flag);
+        else k_verlet1<2><<<grid, I_BLOCK, 0, c->stream>>>(c->pos, c->v, c->a, n, c->npad, dt, hdt2, hdt, abort_flag);
         CK_LAUNCH(c);
         PTRY(parm_prof_end(c));
         if (c->sh.on) PTRY(parm_shard_halo_exchange(c)); // ghost positions for x(t+dt)
         PTRY(parm_prof_begin(c, PARM_PROF_FORCE));
-        PTRY(launch_all_forces(g));
+        PTRY(launch_all_forces(g, abort_flag));
         PTRY(parm_prof_end(c));
         PTRY(parm_prof_begin(c, PARM_PROF_INTEG2));
-#define V2ARGS c->pos, c->v, c->a, c->f, n, c->npad, hdt, nl ? nl->xlast : nullptr, nl ? nl->d_diam : nullptr, \
-               nl ? nl->skin : 0.0, nl ? nl->d_top2 : nullptr, nl ? nl->d_counter : nullptr, nl ? nl->d_flags : nullptr, \
-               nl ? nl->h_flags : nullptr
         if (c->D == 3) {
-            if (nl) k_verlet2<3, true><<<grid2, I_BLOCK, 0, c->stream>>>(V2ARGS);
-            else k_verlet2<3, false><<<grid2, I_BLOCK, 0, c->stream>>>(V2ARGS);
+            if (nl) k_verlet2<3, true><<<grid2, I_BLOCK, 0, c->stream>>>(c->pos, c->v, c->a, c->f, n, c->npad, hdt, DRIFTARGS);
+            else k_verlet2<3, false><<<grid2, I_BLOCK, 0, c->stream>>>(c->pos, c->v, c->a, c->f, n, c->npad, hdt, DRIFTARGS);
         } else {
-            if (nl) k_verlet2<2, true><<<grid2, I_BLOCK, 0, c->stream>>>(V2ARGS);
-            else k_verlet2<2, false><<<grid2, I_BLOCK, 0, c->stream>>>(V2ARGS);
+            if (nl) k_verlet2<2, true><<<grid2, I_BLOCK, 0, c->stream>>>(c->pos, c->v, c->a, c->f, n, c->npad, hdt, DRIFTARGS);
+            else k_verlet2<2, false><<<grid2, I_BLOCK, 0, c->stream>>>(c->pos, c->v, c->a, c->f, n, c->npad, hdt, DRIFTARGS);
         }
-#undef V2ARGS
         CK_LAUNCH(c);
         PTRY(parm_prof_end(c));
     } else {
@@ -425,52 +439,33 @@ static int one_step(parm_integ *g) {
         K.damping = g->damping;
         const double *noise = nullptr;
         if (g->d_noise) {
-            size_t per = (size_t)g->n_mobile * 2 * c->D;
-            if (g->noise_pos + per > g->noise_len) { parm_set_error("CollectionSol: injected noise exhausted"); return PARM_ERR_INVALID; }
-            noise = g->d_noise + g->noise_pos;
-            g->noise_pos += per;
+            const size_t per = (size_t)g->n_mobile * 2 * c->D;
+            const size_t off = (size_t)(step - g->noise_step0) * per;
+            if (off + per > g->noise_len) { parm_set_error("CollectionSol: injected noise exhausted"); return PARM_ERR_INVALID; }
+            noise = g->d_noise + off;
         }
         PTRY(parm_prof_begin(c, PARM_PROF_INTEG1));
-        if (c->D == 3) k_sol1<3><<<grid, I_BLOCK, 0, c->stream>>>(c->pos, c->v, c->a, c->order, n, c->npad, K, noise, g->d_mobile_rank, g->steps, g->seed);
-        else k_sol1<2><<<grid, I_BLOCK, 0, c->stream>>>(c->pos, c->v, c->a, c->order, n, c->npad, K, noise, g->d_mobile_rank, g->steps, g->seed);
+        if (c->D == 3) k_sol1<3><<<grid, I_BLOCK, 0, c->stream>>>(c->pos, c->v, c->a, c->order, n, c->npad, K, noise, g->d_mobile_rank, step, g->seed, abort_flag);
+        else k_sol1<2><<<grid, I_BLOCK, 0, c->stream>>>(c->pos, c->v, c->a, c->order, n, c->npad, K, noise, g->d_mobile_rank, step, g->seed, abort_flag);
         CK_LAUNCH(c);
         PTRY(parm_prof_end(c));
         if (c->sh.on) PTRY(parm_shard_halo_exchange(c)); // ghost positions for x(t+dt)
         PTRY(parm_prof_begin(c, PARM_PROF_FORCE));
-        PTRY(launch_all_forces(g));
+        PTRY(launch_all_forces(g, abort_flag));
         PTRY(parm_prof_end(c));
         PTRY(parm_prof_begin(c, PARM_PROF_INTEG2));
-#define S2ARGS c->pos, c->v, c->a, c->f, n, c->npad, K.dtc2, nl ? nl->xlast : nullptr, nl ? nl->d_diam : nullptr, \
-               nl ? nl->skin : 0.0, nl ? nl->d_top2 : nullptr, nl ? nl->d_counter : nullptr, nl ? nl->d_flags : nullptr, \
-               nl ? nl->h_flags : nullptr
         if (c->D == 3) {
-            if (nl) k_sol2<3, true><<<grid2, I_BLOCK, 0, c->stream>>>(S2ARGS);
-            else k_sol2<3, false><<<grid2, I_BLOCK, 0, c->stream>>>(S2ARGS);
+            if (nl) k_sol2<3, true><<<grid2, I_BLOCK, 0, c->stream>>>(c->pos, c->v, c->a, c->f, n, c->npad, K.dtc2, DRIFTARGS);
+            else k_sol2<3, false><<<grid2, I_BLOCK, 0, c->stream>>>(c->pos, c->v, c->a, c->f, n, c->npad, K.dtc2, DRIFTARGS);
         } else {
-            if (nl) k_sol2<2, true><<<grid2, I_BLOCK, 0, c->stream>>>(S2ARGS);
-            else k_sol2<2, false><<<grid2, I_BLOCK, 0, c->stream>>>(S2ARGS);
+            if (nl) k_sol2<2, true><<<grid2, I_BLOCK, 0, c->stream>>>(c->pos, c->v, c->a, c->f, n, c->npad, K.dtc2, DRIFTARGS);
+            else k_sol2<2, false><<<grid2, I_BLOCK, 0, c->stream>>>(c->pos, c->v, c->a, c->f, n, c->npad, K.dtc2, DRIFTARGS);
         }
-#undef S2ARGS
         CK_LAUNCH(c);
         PTRY(parm_prof_end(c));
     }
-    g->steps++;
-    // update_trackers(): NeighborList::update -> update_list(false)  (collection.cpp:468, trackers.hpp:173-176)
-    if (nl) {
-        bool rebuild = nl->ignorechanged;
-        if (!rebuild) {
-            if (c->sh.on) {
-                PTRY(parm_shard_drift_decision(nl, &rebuild));
-            } else {
-                CK(cudaStreamSynchronize(c->stream));
-                rebuild = nl->h_flags->need_rebuild != 0;
-            }
-        }
-        if (rebuild) {
-            PTRY(parm_nlist_rebuild(nl));
-            g->rebuilds++;
-        }
-    }
+#undef DRIFTARGS
+    if (nl && c->sh.on) PTRY(parm_shard_drift_enqueue(nl, nl->d_slot + slot, nl->h_slot + slot));
     return 0;
 }
 
@@ -481,7 +476,50 @@ extern "C" int parm_integ_timestep(parm_integ *g, int nsteps) {
     if (c->n == 0 && !c->sh.on) { g->steps += nsteps > 0 ? nsteps : 0; return 0; }
     for (size_t k = 1; k < g->trackers.size(); k++)
         if (g->trackers[k] != g->trackers[0]) { parm_set_error("one NeighborList per Collection is supported"); return PARM_ERR_UNSUPPORTED; }
-    for (int s = 0; s < nsteps; s++) PTRY(one_step(g));
+    if (nsteps <= 0) return 0;
+    parm_nlist *nl = g->trackers.empty() ? nullptr : g->trackers[0];
+    if (!nl) { // no tracker: nothing to decide, the steps just queue up
+        for (int s = 0; s < nsteps; s++) {
+            PTRY(enqueue_step(g, g->steps, nullptr, 0));
+            g->steps++;
+        }
+        return 0;
+    }
+    if (!g->ev_ok) {
+        CK(cudaEventCreateWithFlags(&g->ev[0], cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&g->ev[1], cudaEventDisableTiming));
+        g->ev_ok = true;
+    }
+    static int speculate = -1;
+    if (speculate < 0) { const char *e = getenv("PARM_B200_SPECULATE"); speculate = e ? atoi(e) : 1; }
+    // update_trackers() ends every step (collection.cpp:468): NeighborList::update -> update_list(false).
+    // The host runs one step ahead of the decisions: step s+1 is enqueued (guarded by the decision word
+    // of step s) before the host waits for step s. A rebuild request makes the guarded kernels no-ops;
+    // the host then rebuilds and enqueues step s+1 again.
+    PTRY(enqueue_step(g, g->steps, nullptr, 0));
+    CK(cudaEventRecord(g->ev[0], c->stream));
+    for (int s = 0; s < nsteps; s++) {
+        const int p = s & 1;
+        // (per-class event timing counts launches, so it runs without speculation)
+        const bool spec = speculate && !c->prof_on && s + 1 < nsteps && !nl->ignorechanged;
+        if (spec) {
+            PTRY(enqueue_step(g, g->steps + 1, nl->d_slot + p, p ^ 1));
+            CK(cudaEventRecord(g->ev[p ^ 1], c->stream));
+        }
+        CK(cudaEventSynchronize(g->ev[p]));
+        const bool rebuild = nl->ignorechanged || nl->h_slot[p] != 0;
+        g->steps++;
+        if (rebuild) {
+            PTRY(parm_nlist_rebuild(nl)); // synchronises the stream: the guarded kernels of step s+1 have returned
+            g->rebuilds++;
+            CK(cudaMemsetAsync(nl->d_slot, 0, 2 * sizeof(int), c->stream));
+            nl->h_slot[0] = nl->h_slot[1] = 0;
+        }
+        if (s + 1 < nsteps && (rebuild || !spec)) {
+            PTRY(enqueue_step(g, g->steps, nullptr, p ^ 1));
+            CK(cudaEventRecord(g->ev[p ^ 1], c->stream));
+        }
+    }
     return 0;
 }
 

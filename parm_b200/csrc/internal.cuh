@@ -168,6 +168,7 @@ struct parm_nlist {
     unsigned int *d_counter;
     NlistFlags *d_flags;
     NlistFlags *h_flags; // pinned
+    int *d_slot, *h_slot; // [2] per-step rebuild decisions (device / pinned): see parm_integ_timestep
     uint64_t rebuilds;
 };
 
@@ -206,12 +207,16 @@ struct parm_integ {
     uint32_t *d_mobile_rank; // by AtomVec index (noise injection addressing)
     uint32_t n_mobile;
     uint64_t steps, rebuilds;
+    uint64_t noise_step0;    // g->steps when the noise was injected
+    cudaEvent_t ev[2];
+    bool ev_ok;
 };
 
 // ---- cross-TU host functions ----
 int parm_ctx_alloc(int ndim, uint32_t nid, uint32_t cap_slots, int device, parm_ctx **out);
 int parm_shard_halo_exchange(parm_ctx *c);                 // per step, after K1
-int parm_shard_drift_decision(parm_nlist *nl, bool *rebuild); // after K3: global top-2 rule
+int parm_shard_drift_decision(parm_nlist *nl, bool *rebuild); // after K3: global top-2 rule (synchronous)
+int parm_shard_drift_enqueue(parm_nlist *nl, int *d_slot, int *h_slot); // same, decision left in the step slot
 int parm_shard_rebuild(parm_nlist *nl);                    // migration + ghost selection + build
 int parm_shard_allreduce_sum(parm_ctx *c, double *d_buf, int count);
 int parm_shard_destroy(parm_ctx *c);
@@ -222,7 +227,8 @@ int parm_nlist_build_rows(parm_nlist *nl);
 int parm_nlist_rebuild(parm_nlist *nl);
 int parm_nlist_drift_check_async(parm_nlist *nl);   // standalone drift kernel (update_list(false) outside timestep)
 int parm_inter_regather(parm_inter *inter);          // re-gather per-slot species after a re-sort
-int parm_inter_launch_forces(parm_inter *inter, unsigned want, bool accumulate, double *d_out /*device, 11 doubles*/);
+int parm_inter_launch_forces(parm_inter *inter, unsigned want, bool accumulate, double *d_out /*device, 13 doubles*/,
+                             const int *abort_flag = nullptr);
 int parm_ctx_ensure_red(parm_ctx *ctx, size_t doubles);
 
 // ---- device helpers ----

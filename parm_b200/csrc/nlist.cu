@@ -510,6 +510,10 @@ extern "C" int parm_nlist_create(parm_ctx *c, double skin, parm_nlist **out) {
     CK(cudaMemsetAsync(nl->d_flags, 0, sizeof(NlistFlags), c->stream));
     CK(cudaHostAlloc(&nl->h_flags, sizeof(NlistFlags), cudaHostAllocMapped));
     memset(nl->h_flags, 0, sizeof(NlistFlags));
+    CK(cudaMalloc(&nl->d_slot, 2 * sizeof(int)));
+    CK(cudaMemsetAsync(nl->d_slot, 0, 2 * sizeof(int), c->stream));
+    CK(cudaHostAlloc(&nl->h_slot, 2 * sizeof(int), cudaHostAllocMapped));
+    nl->h_slot[0] = nl->h_slot[1] = 0;
     // all atoms start as non-members
     std::vector<double> neg(nidp, -1.0);
     CK(cudaMemcpyAsync(nl->d_diam_id, neg.data(), nidp * 8, cudaMemcpyHostToDevice, c->stream));
@@ -526,10 +530,11 @@ extern "C" int parm_nlist_destroy(parm_nlist *nl) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     void *ptrs[] = {nl->pw, nl->d_diam_id, nl->d_diam, nl->xlast, nl->cell_id, nl->cell_id_sorted, nl->perm, nl->iota,
-                    nl->cell_start, nl->sort_temp, nl->nbr, nl->cnt, nl->d_top2, nl->d_counter, nl->d_flags};
+                    nl->cell_start, nl->sort_temp, nl->nbr, nl->cnt, nl->d_top2, nl->d_counter, nl->d_flags, nl->d_slot};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     if (nl->h_flags) cudaFreeHost(nl->h_flags);
+    if (nl->h_slot) cudaFreeHost(nl->h_slot);
     c->nlists.erase(std::remove(c->nlists.begin(), c->nlists.end(), nl), c->nlists.end());
     delete nl;
     return 0;

@@ -337,6 +337,31 @@ int parm_shard_drift_decision(parm_nlist *nl, bool *rebuild) {
     return 0;
 }
 
+// device-side fold of the gathered top-2 values: identical arithmetic on every rank
+__global__ void k_fold_decision(const double *__restrict__ gathered, int nvals, double skin, int *d_slot, int *h_slot) {
+    if (threadIdx.x || blockIdx.x) return;
+    double b1 = 0, b2 = 0;
+    for (int k = 0; k < nvals; k++) {
+        double d = gathered[k];
+        if (d > b1) { b2 = b1; b1 = d; }
+        else if (d > b2) b2 = d;
+    }
+    const int need = (__dadd_rn(b2, b1) >= skin) ? 1 : 0; // bigdist + biggestdist >= skin
+    *d_slot = need;
+    *h_slot = need;
+    __threadfence_system();
+}
+
+int parm_shard_drift_enqueue(parm_nlist *nl, int *d_slot, int *h_slot) {
+    parm_ctx *c = nl->ctx;
+    ShardState &sh = c->sh;
+    NcclApi *n = nccl_api();
+    NCK(n->AllGather(nl->d_flags->top2, sh.d_gather, 2, ncclFloat64, (ncclComm_t)sh.comm, c->stream));
+    k_fold_decision<<<1, 32, 0, c->stream>>>(sh.d_gather, 2 * sh.nranks, nl->skin, d_slot, h_slot);
+    CK_LAUNCH(c);
+    return 0;
+}
+
 __global__ void k_iota2(uint32_t *dst, uint32_t a0, uint32_t na, uint32_t b0, uint32_t nb) {
     for (uint32_t q = blockIdx.x * blockDim.x + threadIdx.x; q < na + nb; q += gridDim.x * blockDim.x)
         dst[q] = q < na ? a0 + q : b0 + (q - na);
