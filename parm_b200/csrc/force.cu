@@ -301,14 +301,15 @@ static int launch_forces(parm_inter *it, int mode, bool accumulate, double *d_ou
     // lanes per atom: enough entries per lane to keep its loop busy, few enough to fill the last pass
     int team = 4; // measured at n ~ 110 (N=1e6 LJ): TEAM=4 0.368 ms, TEAM=8 0.385 ms, TEAM=16 0.476 ms
     {
-        double mean = (double)nl->total_full / (double)(c->n ? c->n : 1);
+        double mean = (double)nl->total_full / (double)(parm_owned(c) ? parm_owned(c) : 1);
         if (mean > 400) team = 8;
         static int forced = -1;
         if (forced < 0) { const char *e = getenv("PARM_B200_TEAM"); forced = e ? atoi(e) : 0; }
         if (forced == 4 || forced == 8 || forced == 16) team = forced;
     }
-    const uint32_t nblocks = (uint32_t)(((size_t)c->n * team + F_BLOCK - 1) / F_BLOCK);
-    if (c->n == 0) {
+    const uint32_t nown = parm_owned(c); // rows exist for owned atoms only
+    const uint32_t nblocks = (uint32_t)(((size_t)nown * team + F_BLOCK - 1) / F_BLOCK);
+    if (nown == 0) {
         if (d_out) CK(cudaMemsetAsync(d_out, 0, NPART * 8, c->stream));
         return 0;
     }
@@ -322,8 +323,8 @@ static int launch_forces(parm_inter *it, int mode, bool accumulate, double *d_ou
     size_t smem = specmode == 1 ? (size_t)it->nspecies * it->nspecies * sizeof(PairConst) : 0;
     PairConst P1 = it->h_table[0];
     cudaError_t e;
-#define ARGS specmode, team, mode, c->n, smem, c->stream, c->pos, nl->nbr, nl->cnt, nl->kmax, it->d_spec, it->d_table, \
-             it->nspecies, P1, c->f, c->n, c->npad, c->box, accumulate ? 1 : 0, it->d_partials, it->d_par, it->d_eps_table, \
+#define ARGS specmode, team, mode, nown, smem, c->stream, c->pos, nl->nbr, nl->cnt, nl->kmax, it->d_spec, it->d_table, \
+             it->nspecies, P1, c->f, nown, c->npad, c->box, accumulate ? 1 : 0, it->d_partials, it->d_par, it->d_eps_table, \
              it->ntypes, abort_flag
     switch (it->kind) {
         case PARM_PAIR_LJREPULSE: e = launch_kind<PARM_PAIR_LJREPULSE>(ARGS); break;

@@ -328,9 +328,10 @@ extern "C" int parm_integ_set_forces(parm_integ *g, int constraints_and_a) {
     parm_ctx *c = g->ctx;
     CK(cudaSetDevice(c->device));
     PTRY(launch_all_forces(g));
-    if (!constraints_and_a || c->n == 0) return 0;
-    if (c->D == 3) k_accel<3><<<grid_for(c, c->n, 256), 256, 0, c->stream>>>(c->pos, c->a, c->f, c->n, c->npad);
-    else k_accel<2><<<grid_for(c, c->n, 256), 256, 0, c->stream>>>(c->pos, c->a, c->f, c->n, c->npad);
+    const uint32_t no = parm_owned(c);
+    if (!constraints_and_a || no == 0) return 0;
+    if (c->D == 3) k_accel<3><<<grid_for(c, no, 256), 256, 0, c->stream>>>(c->pos, c->a, c->f, no, c->npad);
+    else k_accel<2><<<grid_for(c, no, 256), 256, 0, c->stream>>>(c->pos, c->a, c->f, no, c->npad);
     CK_LAUNCH(c);
     return 0;
 }
@@ -393,7 +394,7 @@ extern "C" int parm_integ_inject_noise(parm_integ *g, const double *z, size_t le
 // its predecessor asked for a rebuild.
 static int enqueue_step(parm_integ *g, uint64_t step, const int *abort_flag, int slot) {
     parm_ctx *c = g->ctx;
-    const uint32_t n = c->n;
+    const uint32_t n = parm_owned(c); // ghost copies are never integrated
     parm_nlist *nl = g->trackers.empty() ? nullptr : g->trackers[0];
     const unsigned grid = grid_for(c, n, I_BLOCK, 8);
     const unsigned grid2 = std::min(grid, 2048u); // drift_finish: d_top2 holds 4096 block entries

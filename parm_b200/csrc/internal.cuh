@@ -212,6 +212,9 @@ struct parm_integ {
     bool ev_ok;
 };
 
+// slots [0, parm_owned(c)) hold the atoms this context integrates; ghost copies (sharded) follow them
+static inline uint32_t parm_owned(const parm_ctx *c) { return c->sh.on ? c->sh.n_local : c->n; }
+
 // ---- cross-TU host functions ----
 int parm_ctx_alloc(int ndim, uint32_t nid, uint32_t cap_slots, int device, parm_ctx **out);
 int parm_shard_halo_exchange(parm_ctx *c);                 // per step, after K1
@@ -224,6 +227,7 @@ int parm_shard_destroy(parm_ctx *c);
 int parm_nlist_prepare_grid(parm_nlist *nl);
 int parm_nlist_sort_permute(parm_nlist *nl, const uint32_t *d_src, uint32_t nsrc); // d_src NULL: slots 0..nsrc-1
 int parm_nlist_build_rows(parm_nlist *nl);
+int parm_nlist_append_ghosts(parm_nlist *nl, uint32_t first, uint32_t count);
 int parm_nlist_rebuild(parm_nlist *nl);
 int parm_nlist_drift_check_async(parm_nlist *nl);   // standalone drift kernel (update_list(false) outside timestep)
 int parm_inter_regather(parm_inter *inter);          // re-gather per-slot species after a re-sort

@@ -49,13 +49,14 @@ __global__ void k_cell_id(const double4 *__restrict__ pos, const uint32_t *__res
         for (int d = 0; d < 3; d++) {
             int k;
             if (d == 0 && sd.on) {
-                // slab axis: [halo below | nci interior layers | halo above], no periodic wrap
+                // slab axis, no periodic wrap: interior layers 0..nci-1, then the halo layer above (nci), then
+                // the halo layer below (nci+1) -- so a sort by cell id puts owned atoms first, ghosts last
                 double rel = shard_rel(x[0], sd);
-                if (rel < 0.0) k = 0;
-                else if (rel >= sd.Ls) k = g.nc[0] - 1;
+                if (rel < 0.0) k = sd.nci + 1;
+                else if (rel >= sd.Ls) k = sd.nci;
                 else {
-                    k = 1 + (int)floor(rel * sd.nci / sd.Ls);
-                    if (k > sd.nci) k = sd.nci;
+                    k = (int)floor(rel * sd.nci / sd.Ls);
+                    if (k > sd.nci - 1) k = sd.nci - 1;
                 }
             } else {
                 double w = x[d] - box.L[d] * floor(x[d] * box.invL[d]); // ~[0, L]
@@ -122,6 +123,45 @@ __global__ void k_permute(const uint32_t *__restrict__ perm, uint32_t n, uint32_
         xlast[s] = gh ? nanv : p.x;
         xlast[npad + s] = gh ? nanv : p.y;
         xlast[2 * (size_t)npad + s] = gh ? nanv : p.z;
+    }
+}
+
+// ---- K4b': ghost copies appended behind the (already cell-sorted) owned atoms ------------------
+// The sender's boundary layer arrives in the sender's cell order, which is this rank's cell order for its
+// halo layer (same y,z grid, stable sorts), so the ghosts only need their per-slot data, not a sort.
+__global__ void k_append_ghosts(uint32_t first, uint32_t count, uint32_t npad, const double4 *__restrict__ pos,
+                                const uint32_t *__restrict__ order, uint32_t *slot_of, const double *__restrict__ diam_id,
+                                double *diam, double *xlast, double4 *pw, uint8_t *ghost, uint32_t *cell_id_sorted,
+                                uint32_t *cnt, BoxDev box, GridDev g, ShardDev sd, double half_skin, double lmax,
+                                double thr_min, const NlistFlags *flags) {
+    const double delta = band_delta(flags, lmax, thr_min);
+    const double nanv = __longlong_as_double(0x7ff8000000000000LL);
+    for (uint32_t q = blockIdx.x * blockDim.x + threadIdx.x; q < count; q += gridDim.x * blockDim.x) {
+        const uint32_t s = first + q;
+        const double4 p = pos[s];
+        const uint32_t id = order[s];
+        const double rel = shard_rel(p.x, sd);
+        const int k0 = rel < 0.0 ? sd.nci + 1 : (rel >= sd.Ls ? sd.nci : min((int)floor(rel * sd.nci / sd.Ls), sd.nci - 1));
+        double4 q4;
+        q4.x = rel;
+        q4.y = p.y - box.L[1] * floor(p.y * box.invL[1]);
+        q4.z = p.z - box.L[2] * floor(p.z * box.invL[2]);
+        int k1 = (int)floor(q4.y * g.scale[1]), k2 = (int)floor(q4.z * g.scale[2]);
+        if (!(k1 >= 0)) k1 = 0;
+        if (k1 >= g.nc[1]) k1 = g.nc[1] - 1;
+        if (!(k2 >= 0)) k2 = 0;
+        if (k2 >= g.nc[2]) k2 = g.nc[2] - 1;
+        cell_id_sorted[s] = ((uint32_t)k0 * (uint32_t)g.nc[1] + (uint32_t)k1) * (uint32_t)g.nc[2] + (uint32_t)k2;
+        const double dm = diam_id[id];
+        diam[s] = dm;
+        q4.w = dm >= 0.0 ? (0.5 * dm + half_skin) * (1.0 + delta) : nanv;
+        pw[s] = q4;
+        xlast[s] = nanv;
+        xlast[npad + s] = nanv;
+        xlast[2 * (size_t)npad + s] = nanv;
+        ghost[s] = 1;
+        slot_of[id] = s;
+        cnt[s] = 0;
     }
 }
 
@@ -200,15 +240,17 @@ k_build(const double4 *__restrict__ pos, const double4 *__restrict__ pw, const d
         const int cx = (int)(t / (uint32_t)g.nc[1]);
         int x0 = st.full[0] ? cx - st.sub : 0, x1 = st.full[0] ? cx + st.sub : g.nc[0] - 1;
         if (st.open0) { // slab axis of a sharded context: halo layers instead of periodic wrap
-            x0 = max(cx - st.sub, 0);
-            x1 = min(cx + st.sub, g.nc[0] - 1);
+            x0 = cx - 1; // layer -1 is the halo below (stored as layer nc-1), layer nc-2 is the halo above
+            x1 = cx + 1;
         }
         const int y0 = st.full[1] ? cy - st.sub : 0, y1 = st.full[1] ? cy + st.sub : g.nc[1] - 1;
         const int z0 = st.full[2] ? cz - st.sub : 0, z1 = st.full[2] ? cz + st.sub : g.nc[2] - 1;
         for (int xx = x0; xx <= x1; xx++) {
             int x2 = xx;
             double sx = 0.0; // image shift of the candidates of this cell relative to the tile atoms
-            if (x2 < 0) { x2 += g.nc[0]; sx = -box.L[0]; }
+            if (st.open0) {
+                if (x2 < 0) x2 = g.nc[0] - 1; // halo below; relative coordinates are continuous, no image shift
+            } else if (x2 < 0) { x2 += g.nc[0]; sx = -box.L[0]; }
             else if (x2 >= g.nc[0]) { x2 -= g.nc[0]; sx = box.L[0]; }
             for (int yy = y0; yy <= y1; yy++) {
                 int y2 = yy;
@@ -316,9 +358,9 @@ k_build_cell(const double4 *__restrict__ pos, const double4 *__restrict__ pw, co
     const int cy = (int)(t % (uint32_t)g.nc[1]);
     const int cx = (int)(t / (uint32_t)g.nc[1]);
     int x0 = st.full[0] ? cx - st.sub : 0, x1 = st.full[0] ? cx + st.sub : g.nc[0] - 1;
-    if (st.open0) {
-        x0 = max(cx - st.sub, 0);
-        x1 = min(cx + st.sub, g.nc[0] - 1);
+    if (st.open0) { // slab axis: layer -1 is the halo below (stored as layer nc-1), layer nc-2 the halo above
+        x0 = cx - 1;
+        x1 = cx + 1;
     }
     const int y0 = st.full[1] ? cy - st.sub : 0, y1 = st.full[1] ? cy + st.sub : g.nc[1] - 1;
     const int z0 = st.full[2] ? cz - st.sub : 0, z1 = st.full[2] ? cz + st.sub : g.nc[2] - 1;
@@ -339,7 +381,9 @@ k_build_cell(const double4 *__restrict__ pos, const double4 *__restrict__ pw, co
         for (int xx = x0; xx <= x1; xx++) {
             int x2 = xx;
             double sx = 0.0;
-            if (x2 < 0) { x2 += g.nc[0]; sx = -box.L[0]; }
+            if (st.open0) {
+                if (x2 < 0) x2 = g.nc[0] - 1; // halo below; relative coordinates are continuous, no image shift
+            } else if (x2 < 0) { x2 += g.nc[0]; sx = -box.L[0]; }
             else if (x2 >= g.nc[0]) { x2 -= g.nc[0]; sx = box.L[0]; }
             for (int yy = y0; yy <= y1; yy++) {
                 int y2 = yy;
@@ -703,6 +747,23 @@ int parm_nlist_sort_permute(parm_nlist *nl, const uint32_t *d_src, uint32_t nsrc
     std::swap(c->order, c->order_alt);
     std::swap(c->ghost, c->ghost_alt);
     k_cell_start<<<grid_for(c, n + 1, 256), 256, 0, c->stream>>>(nl->cell_id_sorted, n, nl->ncell, nl->cell_start);
+    CK_LAUNCH(c);
+    return 0;
+}
+
+// Sharded contexts: `count` ghost copies (pos + id already in slots [first, first+count), in the sender's
+// cell order) become part of the cell structure without another sort.
+int parm_nlist_append_ghosts(parm_nlist *nl, uint32_t first, uint32_t count) {
+    parm_ctx *c = nl->ctx;
+    c->n = first + count;
+    if (count) {
+        k_append_ghosts<<<grid_for(c, count, 256), 256, 0, c->stream>>>(first, count, c->npad, c->pos, c->order, c->slot_of,
+                                                                        nl->d_diam_id, nl->d_diam, nl->xlast, nl->pw, c->ghost,
+                                                                        nl->cell_id_sorted, nl->cnt, c->box, nl->g, nl->sd,
+                                                                        0.5 * nl->skin, nl->lmax, nl->thr_min, nl->d_flags);
+        CK_LAUNCH(c);
+    }
+    k_cell_start<<<grid_for(c, c->n + 1, 256), 256, 0, c->stream>>>(nl->cell_id_sorted, c->n, nl->ncell, nl->cell_start);
     CK_LAUNCH(c);
     return 0;
 }

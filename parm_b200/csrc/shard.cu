@@ -9,8 +9,9 @@
 //                              the identical rebuild decision (trackers.cpp:23-53 semantics);
 //   * on rebuild:             migrates atoms that left the slab, re-selects ghosts, then runs the
 //                              ordinary bin/sort/build over local + ghost atoms.
-// Slot layout after a rebuild (cell ids have the slab axis as slowest index, so a sort by cell id
-// produces it): [ghosts from below | local atoms, boundary layers first/last | ghosts from above].
+// Slot layout after a rebuild (cell ids have the slab axis as slowest index with the two halo layers
+// numbered last, so a sort by cell id produces it):
+//   [owned atoms, lowest layer first ... highest layer last | ghosts from above | ghosts from below].
 // Full neighbour rows mean no reverse (force) communication.
 #include <dlfcn.h>
 #include <nccl.h>
@@ -211,8 +212,8 @@ extern "C" int parm_shard_get_atoms(parm_ctx *c, uint32_t cap, uint32_t *n_local
     double *dm = (double *)(s + 4 * nv);
     uint32_t *dg = (uint32_t *)(s + 4 * nv + (size_t)n * 8);
     unsigned grid = std::min<unsigned>((n + 255) / 256, (unsigned)c->num_sms * 8);
-    if (D == 3) k_shard_get<3><<<grid, 256, 0, c->stream>>>(c->sh.g_dn, n, c->npad, c->pos, c->v, c->a, c->f, c->order, dg, dx, dv, da, df, dm);
-    else k_shard_get<2><<<grid, 256, 0, c->stream>>>(c->sh.g_dn, n, c->npad, c->pos, c->v, c->a, c->f, c->order, dg, dx, dv, da, df, dm);
+    if (D == 3) k_shard_get<3><<<grid, 256, 0, c->stream>>>(0, n, c->npad, c->pos, c->v, c->a, c->f, c->order, dg, dx, dv, da, df, dm);
+    else k_shard_get<2><<<grid, 256, 0, c->stream>>>(0, n, c->npad, c->pos, c->v, c->a, c->f, c->order, dg, dx, dv, da, df, dm);
     CK_LAUNCH(c);
     if (x) CK(cudaMemcpyAsync(x, dx, nv, cudaMemcpyDeviceToHost, c->stream));
     if (v) CK(cudaMemcpyAsync(v, dv, nv, cudaMemcpyDeviceToHost, c->stream));
@@ -265,8 +266,8 @@ extern "C" int parm_shard_put_atoms(parm_ctx *c, uint32_t n_local, const double 
     if (a) CK(cudaMemcpyAsync(da, a, nv, cudaMemcpyHostToDevice, c->stream));
     if (f) CK(cudaMemcpyAsync(df, f, nv, cudaMemcpyHostToDevice, c->stream));
     unsigned grid = std::min<unsigned>((n_local + 255) / 256, (unsigned)c->num_sms * 8);
-    if (D == 3) k_shard_put<3><<<grid, 256, 0, c->stream>>>(c->sh.g_dn, n_local, c->npad, x ? dx : nullptr, v ? dv : nullptr, a ? da : nullptr, f ? df : nullptr, c->pos, c->v, c->a, c->f);
-    else k_shard_put<2><<<grid, 256, 0, c->stream>>>(c->sh.g_dn, n_local, c->npad, x ? dx : nullptr, v ? dv : nullptr, a ? da : nullptr, f ? df : nullptr, c->pos, c->v, c->a, c->f);
+    if (D == 3) k_shard_put<3><<<grid, 256, 0, c->stream>>>(0, n_local, c->npad, x ? dx : nullptr, v ? dv : nullptr, a ? da : nullptr, f ? df : nullptr, c->pos, c->v, c->a, c->f);
+    else k_shard_put<2><<<grid, 256, 0, c->stream>>>(0, n_local, c->npad, x ? dx : nullptr, v ? dv : nullptr, a ? da : nullptr, f ? df : nullptr, c->pos, c->v, c->a, c->f);
     CK_LAUNCH(c);
     CK(cudaStreamSynchronize(c->stream));
     return 0;
@@ -288,34 +289,20 @@ int parm_shard_allreduce_sum(parm_ctx *c, double *d_buf, int count) {
     return 0;
 }
 
-// ghost copies take no part in the integrators or the group reductions: mass 0 = frozen
-// (collection.cpp:445,458; box.cpp:406)
-__global__ void k_ghost_fix(double4 *pos, uint32_t a0, uint32_t na, uint32_t b0, uint32_t nb) {
-    for (uint32_t q = blockIdx.x * blockDim.x + threadIdx.x; q < na + nb; q += gridDim.x * blockDim.x) {
-        const uint32_t s = q < na ? a0 + q : b0 + (q - na);
-        pos[s].w = 0.0;
-    }
-}
-
 int parm_shard_halo_exchange(parm_ctx *c) {
     ShardState &sh = c->sh;
     if (!sh.on) return 0;
     NcclApi *n = nccl_api();
     ncclComm_t comm = (ncclComm_t)sh.comm;
-    const uint32_t l0 = sh.g_dn, l1 = sh.g_dn + sh.n_local;
+    const uint32_t nl = sh.n_local;
     NCK(n->GroupStart());
     // sends: [to down, to up]; receives: [from up, from down] -- with 2 ranks both neighbours are the same
-    // peer and NCCL matches same-peer messages in issue order
-    if (sh.s_dn) NCK(n->Send(c->pos + l0, (size_t)sh.s_dn * 4, ncclFloat64, sh.down, comm, c->stream));
-    if (sh.s_up) NCK(n->Send(c->pos + (l1 - sh.s_up), (size_t)sh.s_up * 4, ncclFloat64, sh.up, comm, c->stream));
-    if (sh.g_up) NCK(n->Recv(c->pos + l1, (size_t)sh.g_up * 4, ncclFloat64, sh.up, comm, c->stream));
-    if (sh.g_dn) NCK(n->Recv(c->pos, (size_t)sh.g_dn * 4, ncclFloat64, sh.down, comm, c->stream));
+    // peer and NCCL matches same-peer messages in issue order. Every range is contiguous in `pos`.
+    if (sh.s_dn) NCK(n->Send(c->pos, (size_t)sh.s_dn * 4, ncclFloat64, sh.down, comm, c->stream));
+    if (sh.s_up) NCK(n->Send(c->pos + (nl - sh.s_up), (size_t)sh.s_up * 4, ncclFloat64, sh.up, comm, c->stream));
+    if (sh.g_up) NCK(n->Recv(c->pos + nl, (size_t)sh.g_up * 4, ncclFloat64, sh.up, comm, c->stream));
+    if (sh.g_dn) NCK(n->Recv(c->pos + nl + sh.g_up, (size_t)sh.g_dn * 4, ncclFloat64, sh.down, comm, c->stream));
     NCK(n->GroupEnd());
-    if (sh.g_dn + sh.g_up) {
-        unsigned grid = std::min<unsigned>((sh.g_dn + sh.g_up + 255) / 256, (unsigned)c->num_sms * 4);
-        k_ghost_fix<<<grid, 256, 0, c->stream>>>(c->pos, 0, sh.g_dn, l1, sh.g_up);
-        CK_LAUNCH(c);
-    }
     return 0;
 }
 
@@ -437,59 +424,48 @@ int parm_shard_rebuild(parm_nlist *nl) {
     PTRY(parm_prof_begin(c, PARM_PROF_REBUILD));
     CK(cudaMemsetAsync(nl->d_flags, 0, sizeof(NlistFlags), c->stream));
     const uint32_t plane = (uint32_t)nl->g.nc[1] * (uint32_t)nl->g.nc[2];
-    const uint32_t nc0 = (uint32_t)nl->g.nc[0];
+    const uint32_t nci = (uint32_t)nl->sd.nci; // layers 0..nci-1 interior, nci = halo above, nci+1 = halo below
     auto grid = [&](uint32_t n) { return std::max(1u, std::min<unsigned>((n + 255) / 256, (unsigned)c->num_sms * 8)); };
-    uint32_t bounds[4];
 
-    // ---- phase 1: sort the local atoms; the ones binned into the halo layers have left the slab
-    k_iota2<<<grid(sh.n_local), 256, 0, c->stream>>>(nl->cell_id_sorted, sh.g_dn, sh.n_local, 0, 0);
-    CK_LAUNCH(c);
-    PTRY(parm_nlist_sort_permute(nl, nl->cell_id_sorted, sh.n_local));
-    CK(cudaMemcpyAsync(&sh.h_counts[8], nl->cell_start + plane, 4, cudaMemcpyDeviceToHost, c->stream));
-    CK(cudaMemcpyAsync(&sh.h_counts[9], nl->cell_start + (size_t)(nc0 - 1) * plane, 4, cudaMemcpyDeviceToHost, c->stream));
+    // ---- phase 1: sort the owned atoms; the ones binned into a halo layer have left the slab:
+    //      [interior | left upwards | left downwards], every range contiguous
+    PTRY(parm_nlist_sort_permute(nl, nullptr, sh.n_local));
+    CK(cudaMemcpyAsync(&sh.h_counts[8], nl->cell_start + (size_t)nci * plane, 4, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(&sh.h_counts[9], nl->cell_start + (size_t)(nci + 1) * plane, 4, cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
-    const uint32_t m_dn = sh.h_counts[8], up_begin = sh.h_counts[9], m_up = sh.n_local - up_begin;
+    const uint32_t keep = sh.h_counts[8], dn_begin = sh.h_counts[9];
+    const uint32_t m_up = dn_begin - keep, m_dn = sh.n_local - dn_begin;
     uint32_t r_up = 0, r_dn = 0;
     PTRY(exchange_counts(c, m_dn, m_up, &r_up, &r_dn));
     if ((uint64_t)sh.n_local + r_up + r_dn > c->npad) { parm_set_error("slab rank %d: slot capacity %u too small for migration", sh.rank, c->npad); return PARM_ERR_RUNTIME; }
-    PTRY(exchange_ranges(c, true, 0, m_dn, up_begin, m_up, sh.n_local, r_up, r_dn));
+    PTRY(exchange_ranges(c, true, dn_begin, m_dn, keep, m_up, sh.n_local, r_up, r_dn));
     if (r_up + r_dn) {
         k_fill_u8<<<grid(r_up + r_dn), 256, 0, c->stream>>>(c->ghost + sh.n_local, r_up + r_dn, 0);
         CK_LAUNCH(c);
     }
-    const uint32_t keep = up_begin - m_dn;
     const uint32_t n_local = keep + r_up + r_dn;
 
-    // ---- phase 2: sort the new local set; its first / last interior layers are the neighbours' ghosts
-    k_iota2<<<grid(n_local), 256, 0, c->stream>>>(nl->cell_id_sorted, m_dn, keep, sh.n_local, r_up + r_dn);
+    // ---- phase 2: sort the new owned set; its lowest / highest layers are the neighbours' ghosts
+    k_iota2<<<grid(n_local), 256, 0, c->stream>>>(nl->cell_id_sorted, 0, keep, sh.n_local, r_up + r_dn);
     CK_LAUNCH(c);
     PTRY(parm_nlist_sort_permute(nl, nl->cell_id_sorted, n_local));
-    const size_t idx[4] = {(size_t)plane, (size_t)2 * plane, (size_t)(nc0 - 2) * plane, (size_t)(nc0 - 1) * plane};
-    for (int k = 0; k < 4; k++) CK(cudaMemcpyAsync(&sh.h_counts[8 + k], nl->cell_start + idx[k], 4, cudaMemcpyDeviceToHost, c->stream));
+    const size_t idx[3] = {(size_t)plane, (size_t)(nci - 1) * plane, (size_t)nci * plane};
+    for (int k = 0; k < 3; k++) CK(cudaMemcpyAsync(&sh.h_counts[8 + k], nl->cell_start + idx[k], 4, cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
-    for (int k = 0; k < 4; k++) bounds[k] = sh.h_counts[8 + k];
-    if (bounds[0] != 0 || bounds[3] != n_local) {
+    if (sh.h_counts[10] != n_local) {
         parm_set_error("slab rank %d: %u atoms are more than one layer outside the slab after migration "
-                       "(atoms must start in, or next to, their slab)", sh.rank, bounds[0] + (n_local - bounds[3]));
+                       "(atoms must start in, or next to, their slab)", sh.rank, n_local - sh.h_counts[10]);
         return PARM_ERR_RUNTIME;
     }
-    const uint32_t s_dn = bounds[1], s_up = n_local - bounds[2];
+    const uint32_t s_dn = sh.h_counts[8], s_up = n_local - sh.h_counts[9];
     uint32_t g_up = 0, g_dn = 0;
     PTRY(exchange_counts(c, s_dn, s_up, &g_up, &g_dn));
     if ((uint64_t)n_local + g_up + g_dn > c->npad) { parm_set_error("slab rank %d: slot capacity %u too small for %u ghosts", sh.rank, c->npad, g_up + g_dn); return PARM_ERR_RUNTIME; }
-    PTRY(exchange_ranges(c, false, 0, s_dn, bounds[2], s_up, n_local, g_up, g_dn));
-    if (g_up + g_dn) {
-        k_fill_u8<<<grid(g_up + g_dn), 256, 0, c->stream>>>(c->ghost + n_local, g_up + g_dn, 1);
-        CK_LAUNCH(c);
-        CK(cudaMemsetAsync(c->f + n_local, 0, (size_t)(g_up + g_dn) * 8, c->stream)); // ghost forces stay 0
-        CK(cudaMemsetAsync(c->f + c->npad + n_local, 0, (size_t)(g_up + g_dn) * 8, c->stream));
-        CK(cudaMemsetAsync(c->f + 2 * (size_t)c->npad + n_local, 0, (size_t)(g_up + g_dn) * 8, c->stream));
-        k_ghost_fix<<<grid(g_up + g_dn), 256, 0, c->stream>>>(c->pos, n_local, g_up + g_dn, 0, 0);
-        CK_LAUNCH(c);
-    }
+    // ghosts land behind the owned atoms: first the upper neighbour's lowest layer, then the lower neighbour's highest
+    PTRY(exchange_ranges(c, false, 0, s_dn, n_local - s_up, s_up, n_local, g_up, g_dn));
 
-    // ---- phase 3: final order [ghosts below | locals | ghosts above] and the rows of the local atoms
-    PTRY(parm_nlist_sort_permute(nl, nullptr, n_local + g_up + g_dn));
+    // ---- phase 3: per-slot data of the ghosts (no third sort) and the rows of the owned atoms
+    PTRY(parm_nlist_append_ghosts(nl, n_local, g_up + g_dn));
     sh.n_local = n_local;
     sh.g_dn = g_dn;
     sh.g_up = g_up;

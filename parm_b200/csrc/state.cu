@@ -491,13 +491,14 @@ extern "C" int parm_reduce(parm_ctx *c, int what, const double *v0, double *out)
     if (!c || !out) { parm_set_error("parm_reduce: NULL argument"); return PARM_ERR_INVALID; }
     if (what < 0 || what > PARM_RED_COMFORCE) { parm_set_error("parm_reduce: unknown quantity %d", what); return PARM_ERR_INVALID; }
     CK(cudaSetDevice(c->device));
-    int nb = (int)grid_for(c, c->n, RED_BLOCK, 4);
+    const uint32_t no = parm_owned(c);
+    int nb = (int)grid_for(c, no, RED_BLOCK, 4);
     PTRY(parm_ctx_ensure_red(c, (size_t)(nb + 1) * RED_MAXQ));
     double z[3] = {0, 0, 0};
     if (v0)
         for (int k = 0; k < c->D; k++) z[k] = v0[k];
-    if (c->D == 3) k_reduce<3><<<nb, RED_BLOCK, 0, c->stream>>>(what, c->pos, c->v, c->f, c->n, c->npad, z[0], z[1], z[2], c->d_red + RED_MAXQ);
-    else k_reduce<2><<<nb, RED_BLOCK, 0, c->stream>>>(what, c->pos, c->v, c->f, c->n, c->npad, z[0], z[1], z[2], c->d_red + RED_MAXQ);
+    if (c->D == 3) k_reduce<3><<<nb, RED_BLOCK, 0, c->stream>>>(what, c->pos, c->v, c->f, no, c->npad, z[0], z[1], z[2], c->d_red + RED_MAXQ);
+    else k_reduce<2><<<nb, RED_BLOCK, 0, c->stream>>>(what, c->pos, c->v, c->f, no, c->npad, z[0], z[1], z[2], c->d_red + RED_MAXQ);
     CK_LAUNCH(c);
     k_reduce_final<<<1, RED_BLOCK, 0, c->stream>>>(c->d_red + RED_MAXQ, nb, c->d_red);
     CK_LAUNCH(c);
@@ -527,8 +528,9 @@ __global__ void k_scale_v(const double4 *__restrict__ pos, double *v, uint32_t n
 }
 extern "C" int parm_scale_velocities(parm_ctx *c, double s) {
     CK(cudaSetDevice(c->device));
-    if (c->D == 3) k_scale_v<3><<<grid_for(c, c->n, 256), 256, 0, c->stream>>>(c->pos, c->v, c->n, c->npad, s);
-    else k_scale_v<2><<<grid_for(c, c->n, 256), 256, 0, c->stream>>>(c->pos, c->v, c->n, c->npad, s);
+    const uint32_t no = parm_owned(c);
+    if (c->D == 3) k_scale_v<3><<<grid_for(c, no, 256), 256, 0, c->stream>>>(c->pos, c->v, no, c->npad, s);
+    else k_scale_v<2><<<grid_for(c, no, 256), 256, 0, c->stream>>>(c->pos, c->v, no, c->npad, s);
     CK_LAUNCH(c);
     return 0;
 }
@@ -542,7 +544,7 @@ __global__ void k_add_v(double *v, uint32_t n, uint32_t npad, double dx, double 
 }
 extern "C" int parm_add_velocity(parm_ctx *c, const double *dv) {
     CK(cudaSetDevice(c->device));
-    k_add_v<<<grid_for(c, c->n, 256), 256, 0, c->stream>>>(c->v, c->n, c->npad, dv[0], dv[1], c->D == 3 ? dv[2] : 0.0, c->D);
+    k_add_v<<<grid_for(c, parm_owned(c), 256), 256, 0, c->stream>>>(c->v, parm_owned(c), c->npad, dv[0], dv[1], c->D == 3 ? dv[2] : 0.0, c->D);
     CK_LAUNCH(c);
     return 0;
 }
