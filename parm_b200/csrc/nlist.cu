@@ -336,34 +336,45 @@ k_build(const double4 *__restrict__ pos, const double4 *__restrict__ pw, const d
 // one full 32-byte sector, so the row stores cost one L2 transaction per 8 neighbours. Same banded
 // classification / exact predicate as k_build; ~2.4x fewer instructions per candidate test.
 #define CB_WARPS 4
-template <bool SMALLBOX, bool UNIFORM>
+// RUN2D: in 2-D the cells that are contiguous in slot order run along y (z is a single layer), so y takes the
+// role of the run axis. zg: consecutive cells of the run axis handled by one warp (sparse systems have only a
+// few atoms per cell; grouping keeps the lanes busy and shares the stencil between the group's cells).
+template <bool SMALLBOX, bool UNIFORM, bool RUN2D>
 __global__ void __launch_bounds__(CB_WARPS * 32)
 k_build_cell(const double4 *__restrict__ pos, const double4 *__restrict__ pw, const double *__restrict__ diam,
-             const uint32_t *__restrict__ cell_start, uint32_t ncell, uint32_t n, BoxDev box, GridDev g, StencilDev st,
+             const uint32_t *__restrict__ cell_start, uint32_t ngroups, int zg, uint32_t n, BoxDev box, GridDev g, StencilDev st,
              double skin, double lmax, double thr_min, double uthr, uint32_t kmax, uint32_t *__restrict__ nbr,
              uint32_t *__restrict__ cnt, NlistFlags *flags, const uint8_t *__restrict__ ghost) {
     __shared__ double4 s_c[CB_WARPS][32];
     __shared__ uint32_t s_buf[CB_WARPS][8][32];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const uint32_t cur = blockIdx.x * CB_WARPS + wib;
-    if (cur >= ncell) return;
-    const uint32_t a0 = cell_start[cur], a1 = cell_start[cur + 1];
+    if (cur >= ngroups) return;
+    constexpr int RAX = RUN2D ? 1 : 2;                 // physical axis of the run
+    const int ncr = g.nc[RAX], ncm = RUN2D ? 1 : g.nc[1];
+    const uint32_t gpc = (uint32_t)((ncr + zg - 1) / zg); // groups per column
+    const int cr0 = (int)(cur % gpc) * zg, cr1 = min(cr0 + zg, ncr) - 1;
+    const uint32_t tcol = cur / gpc;
+    const int cy = RUN2D ? 0 : (int)(tcol % (uint32_t)ncm); // mid-axis cell (3-D only)
+    const int cx = (int)(tcol / (uint32_t)ncm);
+    // cell id of (slow x, mid m, run r)
+    auto cell_of = [&](int x, int m, int r) -> uint32_t {
+        return RUN2D ? ((uint32_t)x * (uint32_t)g.nc[1] + (uint32_t)r) * (uint32_t)g.nc[2]
+                     : ((uint32_t)x * (uint32_t)g.nc[1] + (uint32_t)m) * (uint32_t)g.nc[2] + (uint32_t)r;
+    };
+    const uint32_t a0 = cell_start[cell_of(cx, cy, cr0)], a1 = cell_start[cell_of(cx, cy, cr1) + 1];
     if (a0 == a1) return;
     const double nan = __longlong_as_double(0x7ff8000000000000LL);
     const double delta = band_delta(flags, lmax, thr_min);
     const double lo = ((1.0 - delta) / (1.0 + delta)) * ((1.0 - delta) / (1.0 + delta));
     const double uthr2 = uthr * (1.0 + delta) * (uthr * (1.0 + delta)), uthr2lo = uthr2 * lo;
-    const int cz = (int)(cur % (uint32_t)g.nc[2]);
-    const uint32_t t = cur / (uint32_t)g.nc[2];
-    const int cy = (int)(t % (uint32_t)g.nc[1]);
-    const int cx = (int)(t / (uint32_t)g.nc[1]);
     int x0 = st.full[0] ? cx - st.sub : 0, x1 = st.full[0] ? cx + st.sub : g.nc[0] - 1;
     if (st.open0) { // slab axis: layer -1 is the halo below (stored as layer nc-1), layer nc-2 the halo above
         x0 = cx - 1;
         x1 = cx + 1;
     }
-    const int y0 = st.full[1] ? cy - st.sub : 0, y1 = st.full[1] ? cy + st.sub : g.nc[1] - 1;
-    const int z0 = st.full[2] ? cz - st.sub : 0, z1 = st.full[2] ? cz + st.sub : g.nc[2] - 1;
+    const int y0 = RUN2D ? 0 : (st.full[1] ? cy - st.sub : 0), y1 = RUN2D ? 0 : (st.full[1] ? cy + st.sub : g.nc[1] - 1);
+    const int z0 = st.full[RAX] ? cr0 - st.sub : 0, z1 = st.full[RAX] ? cr1 + st.sub : ncr - 1; // run-axis range
     unsigned long long wsum_tot = 0;
     uint32_t wmax_tot = 0;
     for (uint32_t chunk = a0; chunk < a1; chunk += 32) {
@@ -390,22 +401,23 @@ k_build_cell(const double4 *__restrict__ pos, const double4 *__restrict__ pw, co
                 double sy = 0.0;
                 if (y2 < 0) { y2 += g.nc[1]; sy = -box.L[1]; }
                 else if (y2 >= g.nc[1]) { y2 -= g.nc[1]; sy = box.L[1]; }
-                const uint32_t rowbase = ((uint32_t)x2 * (uint32_t)g.nc[1] + (uint32_t)y2) * (uint32_t)g.nc[2];
                 for (int seg = 0; seg < 3; seg++) {
                     int za, zb;
-                    double sz = 0.0;
-                    if (seg == 0) { za = z0 < 0 ? z0 + g.nc[2] : 1; zb = z0 < 0 ? g.nc[2] - 1 : 0; sz = -box.L[2]; }
-                    else if (seg == 1) { za = z0 < 0 ? 0 : z0; zb = z1 >= g.nc[2] ? g.nc[2] - 1 : z1; }
-                    else { za = z1 >= g.nc[2] ? 0 : 1; zb = z1 >= g.nc[2] ? z1 - g.nc[2] : 0; sz = box.L[2]; }
+                    double sr = 0.0; // image shift along the run axis
+                    if (seg == 0) { za = z0 < 0 ? z0 + ncr : 1; zb = z0 < 0 ? ncr - 1 : 0; sr = -box.L[RAX]; }
+                    else if (seg == 1) { za = z0 < 0 ? 0 : z0; zb = z1 >= ncr ? ncr - 1 : z1; }
+                    else { za = z1 >= ncr ? 0 : 1; zb = z1 >= ncr ? z1 - ncr : 0; sr = box.L[RAX]; }
                     if (za > zb) continue;
-                    const uint32_t jb = cell_start[rowbase + (uint32_t)za], je = cell_start[rowbase + (uint32_t)zb + 1];
+                    const double sz = RUN2D ? 0.0 : sr;
+                    const double syy = RUN2D ? sr : sy;
+                    const uint32_t jb = cell_start[cell_of(x2, y2, za)], je = cell_start[cell_of(x2, y2, zb) + 1];
                     for (uint32_t jbase = jb; jbase < je; jbase += 32) {
                         {   // stage 32 candidates (image shift applied once per candidate)
                             const uint32_t j = jbase + lane;
                             double4 wj = make_double4(nan, nan, nan, nan);
                             if (j < je) wj = pw[j];
                             wj.x += sx;
-                            wj.y += sy;
+                            wj.y += syy;
                             wj.z += sz;
                             __syncwarp();
                             s_c[wib][lane] = wj;
@@ -790,21 +802,34 @@ int parm_nlist_build_rows(parm_nlist *nl) {
     for (int attempt = 0; attempt < 8; attempt++) {
         CK(cudaMemsetAsync((char *)nl->d_flags + offsetof(NlistFlags, maxcnt), 0,
                            offsetof(NlistFlags, xmax_bits) - offsetof(NlistFlags, maxcnt), c->stream));
-#define CARGS c->pos, nl->pw, nl->d_diam, nl->cell_start, nl->ncell, n, c->box, nl->g, nl->st, nl->skin, nl->lmax, \
+#define CARGS c->pos, nl->pw, nl->d_diam, nl->cell_start, ngroups, zg, n, c->box, nl->g, nl->st, nl->skin, nl->lmax, \
               nl->thr_min, uthr, nl->kmax, nl->nbr, nl->cnt, nl->d_flags, c->sh.on ? c->ghost : nullptr
 #define BARGS c->pos, nl->pw, nl->d_diam, nl->cell_id_sorted, nl->cell_start, n, c->box, nl->g, nl->st, nl->skin, nl->lmax, \
               nl->thr_min, uthr, nl->kmax, nl->nbr, nl->cnt, nl->d_flags, c->sh.on ? c->ghost : nullptr
         static int per_cell = -1;
         if (per_cell < 0) { const char *e = getenv("PARM_B200_BUILD_PER_CELL"); per_cell = e ? atoi(e) : 1; }
         if (per_cell) {
-            const unsigned cblocks = (nl->ncell + CB_WARPS - 1) / CB_WARPS;
-            if (nl->smallbox) {
-                if (nl->uniform) k_build_cell<true, true><<<cblocks, CB_WARPS * 32, 0, c->stream>>>(CARGS);
-                else k_build_cell<true, false><<<cblocks, CB_WARPS * 32, 0, c->stream>>>(CARGS);
-            } else {
-                if (nl->uniform) k_build_cell<false, true><<<cblocks, CB_WARPS * 32, 0, c->stream>>>(CARGS);
-                else k_build_cell<false, false><<<cblocks, CB_WARPS * 32, 0, c->stream>>>(CARGS);
+            // one warp per group of zg consecutive cells along the run axis, ~28 atoms per group
+            const bool run2d = c->D == 2;
+            const int rax = run2d ? 1 : 2;
+            const int ncr = nl->g.nc[rax];
+            int zg = 1;
+            if (nl->st.full[rax]) {
+                const double per_cell_atoms = (double)n / (double)nl->ncell;
+                zg = (int)floor(28.0 / std::max(per_cell_atoms, 0.05) + 0.5);
+                zg = std::max(1, std::min(zg, std::min(64, ncr - 2 * nl->st.sub)));
             }
+            const uint32_t gpc = (uint32_t)((ncr + zg - 1) / zg);
+            const uint32_t ngroups = (uint32_t)nl->g.nc[0] * (run2d ? 1u : (uint32_t)nl->g.nc[1]) * gpc;
+            const unsigned cblocks = (ngroups + CB_WARPS - 1) / CB_WARPS;
+#define CLAUNCH(SB, UN)                                                                                         \
+    do {                                                                                                        \
+        if (run2d) k_build_cell<SB, UN, true><<<cblocks, CB_WARPS * 32, 0, c->stream>>>(CARGS);                    \
+        else k_build_cell<SB, UN, false><<<cblocks, CB_WARPS * 32, 0, c->stream>>>(CARGS);                         \
+    } while (0)
+            if (nl->smallbox) { if (nl->uniform) CLAUNCH(true, true); else CLAUNCH(true, false); }
+            else { if (nl->uniform) CLAUNCH(false, true); else CLAUNCH(false, false); }
+#undef CLAUNCH
         } else if (nl->smallbox) {
             if (nl->uniform) k_build<true, true><<<nblocks, BUILD_WARPS * 32, 0, c->stream>>>(BARGS);
             else k_build<true, false><<<nblocks, BUILD_WARPS * 32, 0, c->stream>>>(BARGS);
