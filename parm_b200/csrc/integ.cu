@@ -77,7 +77,8 @@ k_verlet2(const double4 *__restrict__ pos, double *__restrict__ v, double *__res
             }
         }
         if (DRIFT) {
-            if (diam[s] >= 0.0) top2_push(b1, b2, drift_dist(p, xlast[s], xlast[npad + s], xlast[2 * (size_t)npad + s]));
+            // atoms that were never add()ed have NaN lastlocs (set at rebuild): NaN never wins a '>' comparison
+            top2_push(b1, b2, drift_dist(p, xlast[s], xlast[npad + s], xlast[2 * (size_t)npad + s]));
         }
     }
     if (DRIFT) drift_finish(b1, b2, skin, d_top2, counter, dflags, hflags, d_slot, h_slot);
@@ -196,7 +197,8 @@ k_sol2(const double4 *__restrict__ pos, double *__restrict__ v, double *__restri
             }
         }
         if (DRIFT) {
-            if (diam[s] >= 0.0) top2_push(b1, b2, drift_dist(p, xlast[s], xlast[npad + s], xlast[2 * (size_t)npad + s]));
+            // atoms that were never add()ed have NaN lastlocs (set at rebuild): NaN never wins a '>' comparison
+            top2_push(b1, b2, drift_dist(p, xlast[s], xlast[npad + s], xlast[2 * (size_t)npad + s]));
         }
     }
     if (DRIFT) drift_finish(b1, b2, skin, d_top2, counter, dflags, hflags, d_slot, h_slot);
@@ -396,8 +398,8 @@ static int enqueue_step(parm_integ *g, uint64_t step, const int *abort_flag, int
     parm_ctx *c = g->ctx;
     const uint32_t n = parm_owned(c); // ghost copies are never integrated
     parm_nlist *nl = g->trackers.empty() ? nullptr : g->trackers[0];
-    const unsigned grid = grid_for(c, n, I_BLOCK, 8);
-    const unsigned grid2 = std::min(grid, 2048u); // drift_finish: d_top2 holds 4096 block entries
+    const unsigned grid = grid_for(c, n, I_BLOCK, 16);
+    const unsigned grid2 = std::min(grid, 4096u); // drift_finish: d_top2 holds 4096 block entries
     const double dt = g->dt;
     // sharded: K3 only leaves the local top-2; the global decision is folded after the all-gather
     int *d_slot = nl && !c->sh.on ? nl->d_slot + slot : nullptr;

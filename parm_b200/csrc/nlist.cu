@@ -119,10 +119,11 @@ __global__ void k_permute(const uint32_t *__restrict__ perm, uint32_t n, uint32_
         // lastlocs[i] = a1->x (trackers.cpp:61); ghosts never take part in the drift rule (NaN never wins a >)
         const bool gh = ghost ? ghost[o] != 0 : false;
         if (ghost_o) ghost_o[s] = gh ? 1 : 0;
+        const bool skip = gh || !(dm >= 0.0); // ghosts and atoms never add()ed take no part in the drift rule
         const double nanv = __longlong_as_double(0x7ff8000000000000LL);
-        xlast[s] = gh ? nanv : p.x;
-        xlast[npad + s] = gh ? nanv : p.y;
-        xlast[2 * (size_t)npad + s] = gh ? nanv : p.z;
+        xlast[s] = skip ? nanv : p.x;
+        xlast[npad + s] = skip ? nanv : p.y;
+        xlast[2 * (size_t)npad + s] = skip ? nanv : p.z;
     }
 }
 
