@@ -153,9 +153,8 @@ struct parm_nlist {
     double lmax, thr_min;
     uint32_t ncell;
     uint32_t *cell_id, *cell_id_sorted, *perm, *iota, *cell_start;
+    uint32_t *cell_fill, *scan_sums, *sort_tmp; // counting-sort scratch
     uint32_t cell_start_cap;
-    void *sort_temp;
-    size_t sort_temp_bytes;
     // list: row-major nbr[slot * kmax + k], cnt[slot]; kmax is a multiple of 32
     uint32_t kmax;
     uint32_t *nbr;

@@ -10,7 +10,6 @@
 // The device list is a FULL list (i->j and j->i), row-major: nbr[slot * kmax + k], so the force
 // kernel needs no atomics and reads its rows coalesced.
 #include <algorithm>
-#include <cub/device/device_radix_sort.cuh>
 #include <math.h>
 #include <stddef.h>
 #include <stdlib.h>
@@ -38,7 +37,8 @@ __device__ __forceinline__ double shard_rel(double x, const ShardDev &sd) {
 }
 
 __global__ void k_cell_id(const double4 *__restrict__ pos, const uint32_t *__restrict__ src, uint32_t n, BoxDev box,
-                          GridDev g, ShardDev sd, uint32_t *cell_id, uint32_t *iota, NlistFlags *flags) {
+                          GridDev g, ShardDev sd, uint32_t *cell_id, uint32_t *iota, NlistFlags *flags,
+                          uint32_t *cell_count) {
     double xm = 0.0;
     for (uint32_t q = blockIdx.x * blockDim.x + threadIdx.x; q < n; q += gridDim.x * blockDim.x) {
         const uint32_t s = src ? src[q] : q;
@@ -70,6 +70,7 @@ __global__ void k_cell_id(const double4 *__restrict__ pos, const uint32_t *__res
         }
         cell_id[q] = c;
         iota[q] = s;
+        atomicAdd(cell_count + c, 1u); // histogram of the one-digit radix (counting) sort; integer, order independent
     }
 #pragma unroll
     for (int o = 16; o; o >>= 1) xm = fmax(xm, __shfl_xor_sync(0xffffffffu, xm, o));
@@ -81,6 +82,92 @@ __global__ void k_cell_id(const double4 *__restrict__ pos, const uint32_t *__res
 __device__ __forceinline__ double band_delta(const NlistFlags *flags, double lmax, double thr_min) {
     double xmax = __longlong_as_double((long long)flags->xmax_bits);
     return 1e-9 + 2e-14 * (xmax + lmax) / thr_min;
+}
+
+// ---- K4s: radix sort by cell index -------------------------------------------------------------
+// The key is the cell index itself, so one counting pass (a radix sort with a single digit as wide as
+// the key) is enough: histogram (fused into k_cell_id) -> exclusive scan = cell_start -> every atom
+// claims a place in its cell's range -> each atom's final rank inside the cell is the number of cell
+// mates that came earlier in the source order, which makes the sort STABLE and hence deterministic
+// although the places were claimed with atomics.
+#define SCAN_ITEMS 1024
+__global__ void __launch_bounds__(256) k_scan_blocks(uint32_t *data, uint32_t n, uint32_t *bsum) {
+    __shared__ uint32_t s_warp[8];
+    const uint32_t base = blockIdx.x * SCAN_ITEMS + threadIdx.x * 4;
+    uint32_t v[4], tot = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        v[k] = base + k < n ? data[base + k] : 0u;
+        tot += v[k];
+    }
+    uint32_t incl = tot;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    if (lane == 31) s_warp[w] = incl;
+    __syncthreads();
+    uint32_t woff = 0;
+    for (int k = 0; k < w; k++) woff += s_warp[k];
+    uint32_t run = woff + incl - tot; // exclusive prefix of this thread's 4 items
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        if (base + k < n) data[base + k] = run;
+        run += v[k];
+    }
+    if (threadIdx.x == 255) bsum[blockIdx.x] = woff + incl;
+}
+__global__ void __launch_bounds__(1024) k_scan_sums(uint32_t *bsum, uint32_t nb) {
+    __shared__ uint32_t s_warp[32];
+    __shared__ uint32_t s_carry;
+    if (threadIdx.x == 0) s_carry = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    for (uint32_t b0 = 0; b0 < nb; b0 += 1024) {
+        const uint32_t i = b0 + threadIdx.x;
+        const uint32_t v = i < nb ? bsum[i] : 0u;
+        uint32_t incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        if (lane == 31) s_warp[w] = incl;
+        __syncthreads();
+        uint32_t woff = 0;
+        for (int k = 0; k < w; k++) woff += s_warp[k];
+        const uint32_t carry = s_carry;
+        if (i < nb) bsum[i] = carry + woff + incl - v;
+        __syncthreads();
+        if (threadIdx.x == 1023) s_carry = carry + woff + incl;
+        __syncthreads();
+    }
+}
+__global__ void k_scan_add(uint32_t *data, uint32_t n, const uint32_t *__restrict__ bsum, uint32_t total_at, uint32_t total) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) data[i] += bsum[i / SCAN_ITEMS];
+    if (blockIdx.x == 0 && threadIdx.x == 0) data[total_at] = total;
+}
+__global__ void k_sort_place(const uint32_t *__restrict__ cell_id, uint32_t n, const uint32_t *__restrict__ cell_start,
+                             uint32_t *cell_fill, uint32_t *tmp_q) {
+    for (uint32_t q = blockIdx.x * blockDim.x + threadIdx.x; q < n; q += gridDim.x * blockDim.x) {
+        const uint32_t c = cell_id[q];
+        tmp_q[cell_start[c] + atomicAdd(cell_fill + c, 1u)] = q;
+    }
+}
+__global__ void k_sort_rank(const uint32_t *__restrict__ cell_id, const uint32_t *__restrict__ iota, uint32_t n,
+                            const uint32_t *__restrict__ cell_start, const uint32_t *__restrict__ tmp_q, uint32_t *perm,
+                            uint32_t *cell_id_sorted) {
+    for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) {
+        const uint32_t q = tmp_q[t];
+        const uint32_t c = cell_id[q];
+        const uint32_t lo = cell_start[c], hi = cell_start[c + 1];
+        uint32_t rank = 0;
+        for (uint32_t k = lo; k < hi; k++) rank += tmp_q[k] < q;
+        perm[lo + rank] = iota[q];
+        cell_id_sorted[lo + rank] = c;
+    }
 }
 
 // ---- K4b: apply the sort permutation to every per-slot array -----------------------
@@ -557,6 +644,7 @@ extern "C" int parm_nlist_create(parm_ctx *c, double skin, parm_nlist **out) {
     CK(cudaMalloc(&nl->cell_id, np * 4));
     CK(cudaMalloc(&nl->cell_id_sorted, np * 4));
     CK(cudaMalloc(&nl->perm, np * 4));
+    CK(cudaMalloc(&nl->sort_tmp, np * 4));
     CK(cudaMalloc(&nl->iota, np * 4));
     CK(cudaMalloc(&nl->cnt, np * 4));
     CK(cudaMemsetAsync(nl->cnt, 0, np * 4, c->stream));
@@ -587,7 +675,7 @@ extern "C" int parm_nlist_destroy(parm_nlist *nl) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     void *ptrs[] = {nl->pw, nl->d_diam_id, nl->d_diam, nl->xlast, nl->cell_id, nl->cell_id_sorted, nl->perm, nl->iota,
-                    nl->cell_start, nl->sort_temp, nl->nbr, nl->cnt, nl->d_top2, nl->d_counter, nl->d_flags, nl->d_slot};
+                    nl->cell_start, nl->cell_fill, nl->scan_sums, nl->sort_tmp, nl->nbr, nl->cnt, nl->d_top2, nl->d_counter, nl->d_flags, nl->d_slot};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     if (nl->h_flags) cudaFreeHost(nl->h_flags);
@@ -713,6 +801,11 @@ int parm_nlist_prepare_grid(parm_nlist *nl) {
         nl->cell_start = 0;
         nl->cell_start_cap = nl->ncell + 2 + nl->ncell / 4;
         CK(cudaMalloc(&nl->cell_start, (size_t)nl->cell_start_cap * 4));
+        if (nl->cell_fill) cudaFree(nl->cell_fill);
+        if (nl->scan_sums) cudaFree(nl->scan_sums);
+        nl->cell_fill = nl->scan_sums = 0;
+        CK(cudaMalloc(&nl->cell_fill, (size_t)nl->cell_start_cap * 4));
+        CK(cudaMalloc(&nl->scan_sums, ((size_t)nl->cell_start_cap / SCAN_ITEMS + 2) * 4));
     }
     nl->thr_min = nl->mindiam + nl->skin;
     if (!(nl->thr_min > 1e-300)) nl->thr_min = 1e-300;
@@ -730,23 +823,25 @@ int parm_nlist_sort_permute(parm_nlist *nl, const uint32_t *d_src, uint32_t nsrc
         CK(cudaMemsetAsync(nl->cell_start, 0, (size_t)(nl->ncell + 1) * 4, c->stream));
         return 0;
     }
-    k_cell_id<<<grid_for(c, n, 256), 256, 0, c->stream>>>(c->pos, d_src, n, c->box, nl->g, nl->sd, nl->cell_id, nl->iota, nl->d_flags);
+    // one-digit radix (counting) sort by cell index; cell_start falls out of the scan
+    const uint32_t nce = nl->ncell;
+    CK(cudaMemsetAsync(nl->cell_start, 0, (size_t)(nce + 1) * 4, c->stream));
+    CK(cudaMemsetAsync(nl->cell_fill, 0, (size_t)(nce + 1) * 4, c->stream));
+    k_cell_id<<<grid_for(c, n, 256), 256, 0, c->stream>>>(c->pos, d_src, n, c->box, nl->g, nl->sd, nl->cell_id, nl->iota,
+                                                          nl->d_flags, nl->cell_start);
     CK_LAUNCH(c);
-    int end_bit = 1;
-    while ((1ull << end_bit) < (uint64_t)nl->ncell) end_bit++;
-    size_t need = 0;
-    CK(cub::DeviceRadixSort::SortPairs(nullptr, need, nl->cell_id, nl->cell_id_sorted, nl->iota, nl->perm, (int)n, 0,
-                                        end_bit, c->stream));
-    if (need > nl->sort_temp_bytes) {
-        if (nl->sort_temp) cudaFree(nl->sort_temp);
-        nl->sort_temp = 0;
-        CK(cudaMalloc(&nl->sort_temp, need + need / 8 + 256));
-        nl->sort_temp_bytes = need + need / 8 + 256;
-    }
-    size_t tb = nl->sort_temp_bytes;
-    CK(cub::DeviceRadixSort::SortPairs(nl->sort_temp, tb, nl->cell_id, nl->cell_id_sorted, nl->iota, nl->perm, (int)n, 0,
-                                        end_bit, c->stream));
-    parm_count_launch(c, 3);
+    const uint32_t nsb = (nce + SCAN_ITEMS - 1) / SCAN_ITEMS;
+    k_scan_blocks<<<nsb, 256, 0, c->stream>>>(nl->cell_start, nce, nl->scan_sums);
+    CK_LAUNCH(c);
+    k_scan_sums<<<1, 1024, 0, c->stream>>>(nl->scan_sums, nsb);
+    CK_LAUNCH(c);
+    k_scan_add<<<grid_for(c, nce, 256), 256, 0, c->stream>>>(nl->cell_start, nce, nl->scan_sums, nce, n);
+    CK_LAUNCH(c);
+    k_sort_place<<<grid_for(c, n, 256), 256, 0, c->stream>>>(nl->cell_id, n, nl->cell_start, nl->cell_fill, nl->sort_tmp);
+    CK_LAUNCH(c);
+    k_sort_rank<<<grid_for(c, n, 256, 16), 256, 0, c->stream>>>(nl->cell_id, nl->iota, n, nl->cell_start, nl->sort_tmp, nl->perm,
+                                                                nl->cell_id_sorted);
+    CK_LAUNCH(c);
     k_permute<<<grid_for(c, n, 256), 256, 0, c->stream>>>(nl->perm, n, c->npad, c->pos, c->v, c->a, c->f, c->order,
                                                           c->pos_alt, c->v_alt, c->a_alt, c->f_alt, c->order_alt,
                                                           c->slot_of, nl->d_diam_id, nl->d_diam, nl->xlast, nl->pw,
@@ -759,8 +854,6 @@ int parm_nlist_sort_permute(parm_nlist *nl, const uint32_t *d_src, uint32_t nsrc
     std::swap(c->f, c->f_alt);
     std::swap(c->order, c->order_alt);
     std::swap(c->ghost, c->ghost_alt);
-    k_cell_start<<<grid_for(c, n + 1, 256), 256, 0, c->stream>>>(nl->cell_id_sorted, n, nl->ncell, nl->cell_start);
-    CK_LAUNCH(c);
     return 0;
 }
 
