@@ -120,14 +120,14 @@ __global__ void __launch_bounds__(F_BLOCK)
 k_force(const double4 *__restrict__ pos, const uint32_t *__restrict__ nbr, const uint32_t *__restrict__ cnt, uint32_t kmax,
         const uint8_t *__restrict__ spec, const PairConst *__restrict__ table, int nspecies, PairConst P1, double *f,
         uint32_t n, uint32_t npad, BoxDev box, int accumulate, double *partials, const double4 *__restrict__ par,
-        const double *__restrict__ eps_tab, int ntypes, const int *__restrict__ abort_flag) {
+        const double *__restrict__ eps_tab, int ntypes, const int *__restrict__ abort_flag, uint32_t first) {
     if (abort_flag && *abort_flag) return; // speculatively enqueued step whose predecessor asked for a rebuild
     extern __shared__ PairConst s_table[];
     if (SPEC == 1) {
         for (int q = threadIdx.x; q < nspecies * nspecies; q += blockDim.x) s_table[q] = table[q];
         __syncthreads();
     }
-    const uint32_t s = (blockIdx.x * blockDim.x + threadIdx.x) / TEAM;
+    const uint32_t s = first + (blockIdx.x * blockDim.x + threadIdx.x) / TEAM; // slots [first, n)
     const uint32_t tl = threadIdx.x % TEAM;
     const bool want_obs = MODE != MODE_F;
     double fx = 0, fy = 0, fz = 0;
@@ -248,10 +248,10 @@ __global__ void k_force_fold(const double *__restrict__ partials, uint32_t nbloc
     }
 }
 
-#define FARGS pos, nbr, cnt, kmax, spec, table, nsp, P1, f, n, npad, box, acc, partials, par, eps_tab, ntypes, abortf
+#define FARGS pos, nbr, cnt, kmax, spec, table, nsp, P1, f, n, npad, box, acc, partials, par, eps_tab, ntypes, abortf, first
 #define FPARAMS const double4 *pos, const uint32_t *nbr, const uint32_t *cnt, uint32_t kmax, const uint8_t *spec, \
                 const PairConst *table, int nsp, PairConst P1, double *f, uint32_t n, uint32_t npad, BoxDev box, int acc, \
-                double *partials, const double4 *par, const double *eps_tab, int ntypes, const int *abortf
+                double *partials, const double4 *par, const double *eps_tab, int ntypes, const int *abortf, uint32_t first
 template <int KIND, int SPEC, int TEAM, int U>
 static cudaError_t launch_mode(int mode, dim3 grid, size_t smem, cudaStream_t st, FPARAMS) {
     if (mode == MODE_F) {
@@ -289,7 +289,8 @@ static cudaError_t launch_kind(int specmode, int team, int mode, uint32_t natoms
 #undef FPARAMS
 
 // d_out: device pointer to NPART doubles (E, virial, stress[9], contacts, overlaps) or NULL
-static int launch_forces(parm_inter *it, int mode, bool accumulate, double *d_out, const int *abort_flag = nullptr) {
+static int launch_forces(parm_inter *it, int mode, bool accumulate, double *d_out, const int *abort_flag = nullptr,
+                         uint32_t first = 0, uint32_t count = 0xffffffffu) {
     parm_ctx *c = it->ctx;
     parm_nlist *nl = it->nl;
     if (!it->have_params || nl->updatenum == 0) {
@@ -307,9 +308,12 @@ static int launch_forces(parm_inter *it, int mode, bool accumulate, double *d_ou
         if (forced < 0) { const char *e = getenv("PARM_B200_TEAM"); forced = e ? atoi(e) : 0; }
         if (forced == 4 || forced == 8 || forced == 16) team = forced;
     }
-    const uint32_t nown = parm_owned(c); // rows exist for owned atoms only
-    const uint32_t nblocks = (uint32_t)(((size_t)nown * team + F_BLOCK - 1) / F_BLOCK);
-    if (nown == 0) {
+    uint32_t nown = parm_owned(c); // rows exist for owned atoms only
+    if (first > nown) first = nown;
+    nown = count == 0xffffffffu ? nown : std::min(nown, first + count); // slots [first, nown)
+    const uint32_t nrange = nown - first;
+    const uint32_t nblocks = (uint32_t)(((size_t)nrange * team + F_BLOCK - 1) / F_BLOCK);
+    if (nrange == 0) {
         if (d_out) CK(cudaMemsetAsync(d_out, 0, NPART * 8, c->stream));
         return 0;
     }
@@ -323,9 +327,9 @@ static int launch_forces(parm_inter *it, int mode, bool accumulate, double *d_ou
     size_t smem = specmode == 1 ? (size_t)it->nspecies * it->nspecies * sizeof(PairConst) : 0;
     PairConst P1 = it->h_table[0];
     cudaError_t e;
-#define ARGS specmode, team, mode, nown, smem, c->stream, c->pos, nl->nbr, nl->cnt, nl->kmax, it->d_spec, it->d_table, \
+#define ARGS specmode, team, mode, nrange, smem, c->stream, c->pos, nl->nbr, nl->cnt, nl->kmax, it->d_spec, it->d_table, \
              it->nspecies, P1, c->f, nown, c->npad, c->box, accumulate ? 1 : 0, it->d_partials, it->d_par, it->d_eps_table, \
-             it->ntypes, abort_flag
+             it->ntypes, abort_flag, first
     switch (it->kind) {
         case PARM_PAIR_LJREPULSE: e = launch_kind<PARM_PAIR_LJREPULSE>(ARGS); break;
         case PARM_PAIR_REPULSION: e = launch_kind<PARM_PAIR_REPULSION>(ARGS); break;
@@ -343,8 +347,9 @@ static int launch_forces(parm_inter *it, int mode, bool accumulate, double *d_ou
     return 0;
 }
 
-int parm_inter_launch_forces(parm_inter *it, unsigned want, bool accumulate, double *d_out, const int *abort_flag) {
-    return launch_forces(it, want ? MODE_FALL : MODE_F, accumulate, d_out, abort_flag);
+int parm_inter_launch_forces(parm_inter *it, unsigned want, bool accumulate, double *d_out, const int *abort_flag,
+                             uint32_t first, uint32_t count) {
+    return launch_forces(it, want ? MODE_FALL : MODE_F, accumulate, d_out, abort_flag, first, count);
 }
 
 // ---- host API ---------------------------------------------------------------------------

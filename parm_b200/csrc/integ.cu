@@ -4,8 +4,8 @@
 //                                BivariateGauss::{set,gen_vecs} vecrand.cpp:48-85
 //   Collection::{initialize,update_trackers,set_forces,potential_energy,virial}
 //                                collection.cpp:13-19, 45-50, 159-179, 98-108, 73-80
-// Each step is: K1 (first half-kick + drift of positions) -> force kernel(s) -> K3 (a = f/m,
-// second half-kick, fused with the NeighborList skin-drift reduction). The streaming kernels
+// Each step is: K1 (first half-kick + drift of positions, fused with the NeighborList skin-drift
+// reduction) -> force kernel(s) -> K3 (a = f/m, second half-kick). The streaming kernels
 // reproduce the reference's expression order without FMA contraction so that, given the same
 // forces, positions and velocities are bit-identical to the CPU path.
 #include <math.h>
@@ -26,62 +26,63 @@ static inline unsigned grid_for(const parm_ctx *ctx, uint32_t n, unsigned block,
 }
 
 // ---- K1: x += v*dt + a*(dt*dt/2); v += a*(dt/2)   (collection.cpp:443-451) -------------
-template <int D>
+// fused with the NeighborList skin-drift reduction (trackers.cpp:23-53): the displacement only depends on
+// x(t+dt), which this kernel produces, so the rebuild decision of the step is known while the forces of the
+// step are still being computed (and, sharded, its all-gather overlaps the force kernel).
+template <int D, bool DRIFT>
 __global__ void __launch_bounds__(I_BLOCK)
 k_verlet1(double4 *__restrict__ pos, double *__restrict__ v, const double *__restrict__ a, uint32_t n, uint32_t npad,
-          double dt, double hdt2, double hdt, const int *__restrict__ abort_flag) {
+          double dt, double hdt2, double hdt, const int *__restrict__ abort_flag, const double *__restrict__ xlast,
+          double skin, double *d_top2, unsigned int *counter, NlistFlags *dflags, NlistFlags *hflags, int *d_slot,
+          int *h_slot) {
     if (abort_flag && *abort_flag) return; // speculative step behind a rebuild request: leave the state alone
+    double b1 = 0.0, b2 = 0.0;
     for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < n; s += gridDim.x * blockDim.x) {
         double4 p = pos[s];
         if (frozen_le(p.w)) { // m <= 0 || isinf(m): v = 0, position untouched
 #pragma unroll
             for (int d = 0; d < D; d++) v[(size_t)d * npad + s] = 0.0;
-            continue;
-        }
-        double x[3] = {p.x, p.y, p.z};
+        } else {
+            double x[3] = {p.x, p.y, p.z};
 #pragma unroll
-        for (int d = 0; d < D; d++) {
-            const size_t q = (size_t)d * npad + s;
-            const double vd = v[q], ad = a[q];
-            x[d] = __dadd_rn(x[d], __dadd_rn(__dmul_rn(vd, dt), __dmul_rn(ad, hdt2)));
-            v[q] = __dadd_rn(vd, __dmul_rn(ad, hdt));
+            for (int d = 0; d < D; d++) {
+                const size_t q = (size_t)d * npad + s;
+                const double vd = v[q], ad = a[q];
+                x[d] = __dadd_rn(x[d], __dadd_rn(__dmul_rn(vd, dt), __dmul_rn(ad, hdt2)));
+                v[q] = __dadd_rn(vd, __dmul_rn(ad, hdt));
+            }
+            p.x = x[0];
+            p.y = x[1];
+            if (D == 3) p.z = x[2];
+            pos[s] = p;
         }
-        p.x = x[0];
-        p.y = x[1];
-        if (D == 3) p.z = x[2];
-        pos[s] = p;
+        // atoms that were never add()ed have NaN lastlocs (set at rebuild): NaN never wins a '>' comparison
+        if (DRIFT) top2_push(b1, b2, drift_dist(p, xlast[s], xlast[npad + s], xlast[2 * (size_t)npad + s]));
     }
+    if (DRIFT) drift_finish(b1, b2, skin, d_top2, counter, dflags, hflags, d_slot, h_slot);
 }
 
-// ---- K3: a = f/m; v += a*(dt/2)  (collection.cpp:457-465) fused with the drift check ------
-template <int D, bool DRIFT>
+// ---- K3: a = f/m; v += a*(dt/2)  (collection.cpp:457-465) -----------------------------------
+template <int D>
 __global__ void __launch_bounds__(I_BLOCK)
 k_verlet2(const double4 *__restrict__ pos, double *__restrict__ v, double *__restrict__ a, const double *__restrict__ f,
-          uint32_t n, uint32_t npad, double hdt, const double *__restrict__ xlast, const double *__restrict__ diam,
-          double skin, double *d_top2, unsigned int *counter, NlistFlags *dflags, NlistFlags *hflags,
-          const int *__restrict__ abort_flag, int *d_slot, int *h_slot) {
+          uint32_t n, uint32_t npad, double hdt, const int *__restrict__ abort_flag) {
     if (abort_flag && *abort_flag) return;
-    double b1 = 0.0, b2 = 0.0;
     for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < n; s += gridDim.x * blockDim.x) {
-        const double4 p = pos[s];
-        if (frozen_le(p.w)) {
+        const double m = pos[s].w;
+        if (frozen_le(m)) {
 #pragma unroll
             for (int d = 0; d < D; d++) a[(size_t)d * npad + s] = 0.0;
         } else {
 #pragma unroll
             for (int d = 0; d < D; d++) {
                 const size_t q = (size_t)d * npad + s;
-                const double ad = __ddiv_rn(f[q], p.w);
+                const double ad = __ddiv_rn(f[q], m);
                 a[q] = ad;
                 v[q] = __dadd_rn(v[q], __dmul_rn(ad, hdt));
             }
         }
-        if (DRIFT) {
-            // atoms that were never add()ed have NaN lastlocs (set at rebuild): NaN never wins a '>' comparison
-            top2_push(b1, b2, drift_dist(p, xlast[s], xlast[npad + s], xlast[2 * (size_t)npad + s]));
-        }
     }
-    if (DRIFT) drift_finish(b1, b2, skin, d_top2, counter, dflags, hflags, d_slot, h_slot);
 }
 
 // ---- Philox4x32-10 counter RNG + Box-Muller (production noise of CollectionSol) ---------
@@ -116,72 +117,73 @@ struct SolConst {
     double dt, c0, c1dt, c2dtdt, dtc1mc2, dtc2, x11, x21, x22, desT, damping;
 };
 
-// ---- Sol K1 (collection.cpp:276-298) ----------------------------------------------------------
-template <int D>
+// ---- Sol K1 (collection.cpp:276-298), fused with the drift reduction like k_verlet1 --------------
+template <int D, bool DRIFT>
 __global__ void __launch_bounds__(I_BLOCK)
 k_sol1(double4 *__restrict__ pos, double *__restrict__ v, const double *__restrict__ a, const uint32_t *__restrict__ order,
        uint32_t n, uint32_t npad, SolConst K, const double *__restrict__ noise, const uint32_t *__restrict__ mobile_rank,
-       uint64_t step, uint64_t seed, const int *__restrict__ abort_flag) {
+       uint64_t step, uint64_t seed, const int *__restrict__ abort_flag, const double *__restrict__ xlast, double skin,
+       double *d_top2, unsigned int *counter, NlistFlags *dflags, NlistFlags *hflags, int *d_slot, int *h_slot) {
     if (abort_flag && *abort_flag) return;
+    double b1 = 0.0, b2 = 0.0;
     for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < n; s += gridDim.x * blockDim.x) {
         double4 p = pos[s];
         if (frozen_le(p.w)) {
 #pragma unroll
             for (int d = 0; d < D; d++) v[(size_t)d * npad + s] = 0.0;
-            continue;
-        }
-        const double v0 = __dsqrt_rn(__ddiv_rn(K.desT, p.w));
-        const double r0 = __dmul_rn(K.dt, v0);
-        double x1[3] = {0, 0, 0}, x2[3] = {0, 0, 0};
-        if (K.damping > 0) {
-            const uint32_t id = order[s];
-            if (noise) {
-                const double *z = noise + (size_t)mobile_rank[id] * 2 * D;
+        } else {
+            const double v0 = __dsqrt_rn(__ddiv_rn(K.desT, p.w));
+            const double r0 = __dmul_rn(K.dt, v0);
+            double x1[3] = {0, 0, 0}, x2[3] = {0, 0, 0};
+            if (K.damping > 0) {
+                const uint32_t id = order[s];
+                if (noise) {
+                    const double *z = noise + (size_t)mobile_rank[id] * 2 * D;
 #pragma unroll
-                for (int d = 0; d < D; d++) {
-                    x1[d] = z[d];
-                    x2[d] = z[D + d];
-                }
-            } else {
-                double za, zb;
-                normal_pair(id, step, 0, seed, x1[0], x1[1]);
-                normal_pair(id, step, 1, seed, x2[0], x2[1]);
-                normal_pair(id, step, 2, seed, za, zb);
-                if (D == 3) {
-                    x1[2] = za;
-                    x2[2] = zb;
+                    for (int d = 0; d < D; d++) {
+                        x1[d] = z[d];
+                        x2[d] = z[D + d];
+                    }
+                } else {
+                    double za, zb;
+                    normal_pair(id, step, 0, seed, x1[0], x1[1]);
+                    normal_pair(id, step, 1, seed, x2[0], x2[1]);
+                    normal_pair(id, step, 2, seed, za, zb);
+                    if (D == 3) {
+                        x1[2] = za;
+                        x2[2] = zb;
+                    }
                 }
             }
-        }
-        double x[3] = {p.x, p.y, p.z};
+            double x[3] = {p.x, p.y, p.z};
 #pragma unroll
-        for (int d = 0; d < D; d++) {
-            const size_t q = (size_t)d * npad + s;
-            const double vd = v[q], ad = a[q];
-            const double drG = __dmul_rn(x1[d], K.x11);                                           // x1 * x11
-            const double dvG = __dadd_rn(__dmul_rn(x1[d], K.x21), __dmul_rn(x2[d], K.x22));       // x1*x21 + x2*x22
-            x[d] = __dadd_rn(x[d], __dadd_rn(__dadd_rn(__dmul_rn(vd, K.c1dt), __dmul_rn(ad, K.c2dtdt)), __dmul_rn(drG, r0)));
-            v[q] = __dadd_rn(__dadd_rn(__dmul_rn(vd, K.c0), __dmul_rn(ad, K.dtc1mc2)), __dmul_rn(dvG, v0));
+            for (int d = 0; d < D; d++) {
+                const size_t q = (size_t)d * npad + s;
+                const double vd = v[q], ad = a[q];
+                const double drG = __dmul_rn(x1[d], K.x11);                                           // x1 * x11
+                const double dvG = __dadd_rn(__dmul_rn(x1[d], K.x21), __dmul_rn(x2[d], K.x22));       // x1*x21 + x2*x22
+                x[d] = __dadd_rn(x[d], __dadd_rn(__dadd_rn(__dmul_rn(vd, K.c1dt), __dmul_rn(ad, K.c2dtdt)), __dmul_rn(drG, r0)));
+                v[q] = __dadd_rn(__dadd_rn(__dmul_rn(vd, K.c0), __dmul_rn(ad, K.dtc1mc2)), __dmul_rn(dvG, v0));
+            }
+            p.x = x[0];
+            p.y = x[1];
+            if (D == 3) p.z = x[2];
+            pos[s] = p;
         }
-        p.x = x[0];
-        p.y = x[1];
-        if (D == 3) p.z = x[2];
-        pos[s] = p;
+        if (DRIFT) top2_push(b1, b2, drift_dist(p, xlast[s], xlast[npad + s], xlast[2 * (size_t)npad + s]));
     }
+    if (DRIFT) drift_finish(b1, b2, skin, d_top2, counter, dflags, hflags, d_slot, h_slot);
 }
 
 // ---- Sol K3 (collection.cpp:303-318): note the m == 0 (not m <= 0) tests ---------------------
-template <int D, bool DRIFT>
+template <int D>
 __global__ void __launch_bounds__(I_BLOCK)
 k_sol2(const double4 *__restrict__ pos, double *__restrict__ v, double *__restrict__ a, const double *__restrict__ f,
-       uint32_t n, uint32_t npad, double dtc2, const double *__restrict__ xlast, const double *__restrict__ diam,
-       double skin, double *d_top2, unsigned int *counter, NlistFlags *dflags, NlistFlags *hflags,
-       const int *__restrict__ abort_flag, int *d_slot, int *h_slot) {
+       uint32_t n, uint32_t npad, double dtc2, const int *__restrict__ abort_flag) {
     if (abort_flag && *abort_flag) return;
-    double b1 = 0.0, b2 = 0.0;
     for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < n; s += gridDim.x * blockDim.x) {
-        const double4 p = pos[s];
-        if (frozen_eq(p.w)) {
+        const double m = pos[s].w;
+        if (frozen_eq(m)) {
 #pragma unroll
             for (int d = 0; d < D; d++) {
                 a[(size_t)d * npad + s] = 0.0;
@@ -191,17 +193,12 @@ k_sol2(const double4 *__restrict__ pos, double *__restrict__ v, double *__restri
 #pragma unroll
             for (int d = 0; d < D; d++) {
                 const size_t q = (size_t)d * npad + s;
-                const double ad = __ddiv_rn(f[q], p.w);
+                const double ad = __ddiv_rn(f[q], m);
                 a[q] = ad;
                 v[q] = __dadd_rn(v[q], __dmul_rn(ad, dtc2));
             }
         }
-        if (DRIFT) {
-            // atoms that were never add()ed have NaN lastlocs (set at rebuild): NaN never wins a '>' comparison
-            top2_push(b1, b2, drift_dist(p, xlast[s], xlast[npad + s], xlast[2 * (size_t)npad + s]));
-        }
     }
-    if (DRIFT) drift_finish(b1, b2, skin, d_top2, counter, dflags, hflags, d_slot, h_slot);
 }
 
 // ---- a = f/m of Collection::set_forces(true) (collection.cpp:171-178) -----------------------
@@ -314,14 +311,14 @@ extern "C" int parm_integ_add_tracker(parm_integ *g, parm_nlist *nl) {
     return parm_integ_update_trackers(g); // collection.hpp:117-120
 }
 
-static int launch_all_forces(parm_integ *g, const int *abort_flag = nullptr) {
+static int launch_all_forces(parm_integ *g, const int *abort_flag = nullptr, uint32_t first = 0, uint32_t count = 0xffffffffu) {
     parm_ctx *c = g->ctx;
     // atoms->reset_forces(); for each interaction: set_forces(box)   (collection.cpp:160-166)
     if (g->inters.empty()) return parm_reset_forces(c);
-    bool first = true;
+    bool first_inter = true;
     for (parm_inter *it : g->inters) {
-        PTRY(parm_inter_launch_forces(it, 0, !first, nullptr, abort_flag)); // first interaction overwrites f == reset + add
-        first = false;
+        PTRY(parm_inter_launch_forces(it, 0, !first_inter, nullptr, abort_flag, first, count)); // first interaction overwrites f == reset + add
+        first_inter = false;
     }
     return 0;
 }
@@ -399,36 +396,25 @@ static int enqueue_step(parm_integ *g, uint64_t step, const int *abort_flag, int
     const uint32_t n = parm_owned(c); // ghost copies are never integrated
     parm_nlist *nl = g->trackers.empty() ? nullptr : g->trackers[0];
     const unsigned grid = grid_for(c, n, I_BLOCK, 16);
-    const unsigned grid2 = std::min(grid, 4096u); // drift_finish: d_top2 holds 4096 block entries
+    const unsigned grid1 = std::min(grid, 4096u); // drift_finish: d_top2 holds 4096 block entries
     const double dt = g->dt;
-    // sharded: K3 only leaves the local top-2; the global decision is folded after the all-gather
+    // sharded: K1 only leaves the local top-2; the global decision is folded after the all-gather
     int *d_slot = nl && !c->sh.on ? nl->d_slot + slot : nullptr;
     int *h_slot = nl && !c->sh.on ? nl->h_slot + slot : nullptr;
-#define DRIFTARGS nl ? nl->xlast : nullptr, nl ? nl->d_diam : nullptr, nl ? nl->skin : 0.0, nl ? nl->d_top2 : nullptr, \
-                  nl ? nl->d_counter : nullptr, nl ? nl->d_flags : nullptr, nl ? nl->h_flags : nullptr, abort_flag, d_slot, h_slot
+#define DRIFTARGS abort_flag, nl ? nl->xlast : nullptr, nl ? nl->skin : 0.0, nl ? nl->d_top2 : nullptr, \
+                  nl ? nl->d_counter : nullptr, nl ? nl->d_flags : nullptr, nl ? nl->h_flags : nullptr, d_slot, h_slot
+    SolConst K;
+    PTRY(parm_prof_begin(c, PARM_PROF_INTEG1));
     if (g->type == 0) {
         const double hdt2 = dt * dt / 2, hdt = dt / 2;
-        PTRY(parm_prof_begin(c, PARM_PROF_INTEG1));
-        if (c->D == 3) k_verlet1<3><<<grid, I_BLOCK, 0, c->stream>>>(c->pos, c->v, c->a, n, c->npad, dt, hdt2, hdt, abort_flag);
-        else k_verlet1<2><<<grid, I_BLOCK, 0, c->stream>>>(c->pos, c->v, c->a, n, c->npad, dt, hdt2, hdt, abort_flag);
-        CK_LAUNCH(c);
-        PTRY(parm_prof_end(c));
-        if (c->sh.on) PTRY(parm_shard_halo_exchange(c)); // ghost positions for x(t+dt)
-        PTRY(parm_prof_begin(c, PARM_PROF_FORCE));
-        PTRY(launch_all_forces(g, abort_flag));
-        PTRY(parm_prof_end(c));
-        PTRY(parm_prof_begin(c, PARM_PROF_INTEG2));
         if (c->D == 3) {
-            if (nl) k_verlet2<3, true><<<grid2, I_BLOCK, 0, c->stream>>>(c->pos, c->v, c->a, c->f, n, c->npad, hdt, DRIFTARGS);
-            else k_verlet2<3, false><<<grid2, I_BLOCK, 0, c->stream>>>(c->pos, c->v, c->a, c->f, n, c->npad, hdt, DRIFTARGS);
+            if (nl) k_verlet1<3, true><<<grid1, I_BLOCK, 0, c->stream>>>(c->pos, c->v, c->a, n, c->npad, dt, hdt2, hdt, DRIFTARGS);
+            else k_verlet1<3, false><<<grid1, I_BLOCK, 0, c->stream>>>(c->pos, c->v, c->a, n, c->npad, dt, hdt2, hdt, DRIFTARGS);
         } else {
-            if (nl) k_verlet2<2, true><<<grid2, I_BLOCK, 0, c->stream>>>(c->pos, c->v, c->a, c->f, n, c->npad, hdt, DRIFTARGS);
-            else k_verlet2<2, false><<<grid2, I_BLOCK, 0, c->stream>>>(c->pos, c->v, c->a, c->f, n, c->npad, hdt, DRIFTARGS);
+            if (nl) k_verlet1<2, true><<<grid1, I_BLOCK, 0, c->stream>>>(c->pos, c->v, c->a, n, c->npad, dt, hdt2, hdt, DRIFTARGS);
+            else k_verlet1<2, false><<<grid1, I_BLOCK, 0, c->stream>>>(c->pos, c->v, c->a, n, c->npad, dt, hdt2, hdt, DRIFTARGS);
         }
-        CK_LAUNCH(c);
-        PTRY(parm_prof_end(c));
     } else {
-        SolConst K;
         K.dt = dt;
         K.c0 = g->c0;
         K.c1dt = g->c1 * dt;
@@ -447,28 +433,45 @@ static int enqueue_step(parm_integ *g, uint64_t step, const int *abort_flag, int
             if (off + per > g->noise_len) { parm_set_error("CollectionSol: injected noise exhausted"); return PARM_ERR_INVALID; }
             noise = g->d_noise + off;
         }
-        PTRY(parm_prof_begin(c, PARM_PROF_INTEG1));
-        if (c->D == 3) k_sol1<3><<<grid, I_BLOCK, 0, c->stream>>>(c->pos, c->v, c->a, c->order, n, c->npad, K, noise, g->d_mobile_rank, step, g->seed, abort_flag);
-        else k_sol1<2><<<grid, I_BLOCK, 0, c->stream>>>(c->pos, c->v, c->a, c->order, n, c->npad, K, noise, g->d_mobile_rank, step, g->seed, abort_flag);
-        CK_LAUNCH(c);
-        PTRY(parm_prof_end(c));
-        if (c->sh.on) PTRY(parm_shard_halo_exchange(c)); // ghost positions for x(t+dt)
-        PTRY(parm_prof_begin(c, PARM_PROF_FORCE));
-        PTRY(launch_all_forces(g, abort_flag));
-        PTRY(parm_prof_end(c));
-        PTRY(parm_prof_begin(c, PARM_PROF_INTEG2));
+#define S1ARGS c->pos, c->v, c->a, c->order, n, c->npad, K, noise, g->d_mobile_rank, step, g->seed, DRIFTARGS
         if (c->D == 3) {
-            if (nl) k_sol2<3, true><<<grid2, I_BLOCK, 0, c->stream>>>(c->pos, c->v, c->a, c->f, n, c->npad, K.dtc2, DRIFTARGS);
-            else k_sol2<3, false><<<grid2, I_BLOCK, 0, c->stream>>>(c->pos, c->v, c->a, c->f, n, c->npad, K.dtc2, DRIFTARGS);
+            if (nl) k_sol1<3, true><<<grid1, I_BLOCK, 0, c->stream>>>(S1ARGS);
+            else k_sol1<3, false><<<grid1, I_BLOCK, 0, c->stream>>>(S1ARGS);
         } else {
-            if (nl) k_sol2<2, true><<<grid2, I_BLOCK, 0, c->stream>>>(c->pos, c->v, c->a, c->f, n, c->npad, K.dtc2, DRIFTARGS);
-            else k_sol2<2, false><<<grid2, I_BLOCK, 0, c->stream>>>(c->pos, c->v, c->a, c->f, n, c->npad, K.dtc2, DRIFTARGS);
+            if (nl) k_sol1<2, true><<<grid1, I_BLOCK, 0, c->stream>>>(S1ARGS);
+            else k_sol1<2, false><<<grid1, I_BLOCK, 0, c->stream>>>(S1ARGS);
         }
-        CK_LAUNCH(c);
-        PTRY(parm_prof_end(c));
+#undef S1ARGS
     }
 #undef DRIFTARGS
-    if (nl && c->sh.on) PTRY(parm_shard_drift_enqueue(nl, nl->d_slot + slot, nl->h_slot + slot));
+    CK_LAUNCH(c);
+    PTRY(parm_prof_end(c));
+
+    PTRY(parm_prof_begin(c, PARM_PROF_FORCE));
+    if (c->sh.on) {
+        // communication stream: ghost positions for x(t+dt) and the global drift decision, overlapped with the
+        // forces of the atoms whose neighbours are all owned (everything but the two boundary layers)
+        PTRY(parm_shard_step_comm(c, nl, nl ? nl->d_slot + slot : nullptr, nl ? nl->h_slot + slot : nullptr));
+        const uint32_t lo = c->sh.s_dn, hi = n - c->sh.s_up;
+        if (hi > lo) PTRY(launch_all_forces(g, abort_flag, lo, hi - lo));
+        PTRY(parm_shard_step_join(c));
+        if (lo) PTRY(launch_all_forces(g, abort_flag, 0, lo));
+        if (n > hi) PTRY(launch_all_forces(g, abort_flag, std::max(hi, lo), n - std::max(hi, lo)));
+    } else {
+        PTRY(launch_all_forces(g, abort_flag));
+    }
+    PTRY(parm_prof_end(c));
+
+    PTRY(parm_prof_begin(c, PARM_PROF_INTEG2));
+    if (g->type == 0) {
+        if (c->D == 3) k_verlet2<3><<<grid, I_BLOCK, 0, c->stream>>>(c->pos, c->v, c->a, c->f, n, c->npad, dt / 2, abort_flag);
+        else k_verlet2<2><<<grid, I_BLOCK, 0, c->stream>>>(c->pos, c->v, c->a, c->f, n, c->npad, dt / 2, abort_flag);
+    } else {
+        if (c->D == 3) k_sol2<3><<<grid, I_BLOCK, 0, c->stream>>>(c->pos, c->v, c->a, c->f, n, c->npad, K.dtc2, abort_flag);
+        else k_sol2<2><<<grid, I_BLOCK, 0, c->stream>>>(c->pos, c->v, c->a, c->f, n, c->npad, K.dtc2, abort_flag);
+    }
+    CK_LAUNCH(c);
+    PTRY(parm_prof_end(c));
     return 0;
 }
 

@@ -67,6 +67,8 @@ struct ShardState {
     void *comm;                       // ncclComm_t
     uint32_t n_local, g_dn, g_up;     // local atoms, ghosts received from down / up
     uint32_t s_dn, s_up;              // boundary-layer atoms sent to down / up every step
+    cudaStream_t comm_stream;         // per-step exchanges run here, overlapped with the interior forces
+    cudaEvent_t ev_k1, ev_comm;
     uint32_t *d_counts, *h_counts;    // small exchange buffers (device, pinned host)
     double *d_gather, *h_gather;      // drift top-2 of every rank
 };
@@ -219,6 +221,10 @@ int parm_ctx_alloc(int ndim, uint32_t nid, uint32_t cap_slots, int device, parm_
 int parm_shard_halo_exchange(parm_ctx *c);                 // per step, after K1
 int parm_shard_drift_decision(parm_nlist *nl, bool *rebuild); // after K3: global top-2 rule (synchronous)
 int parm_shard_drift_enqueue(parm_nlist *nl, int *d_slot, int *h_slot); // same, decision left in the step slot
+// per step: halo exchange + drift all-gather on the communication stream (after what is queued on the main
+// stream so far), and the point where the main stream waits for them
+int parm_shard_step_comm(parm_ctx *c, parm_nlist *nl, int *d_slot, int *h_slot);
+int parm_shard_step_join(parm_ctx *c);
 int parm_shard_rebuild(parm_nlist *nl);                    // migration + ghost selection + build
 int parm_shard_allreduce_sum(parm_ctx *c, double *d_buf, int count);
 int parm_shard_destroy(parm_ctx *c);
@@ -231,7 +237,7 @@ int parm_nlist_rebuild(parm_nlist *nl);
 int parm_nlist_drift_check_async(parm_nlist *nl);   // standalone drift kernel (update_list(false) outside timestep)
 int parm_inter_regather(parm_inter *inter);          // re-gather per-slot species after a re-sort
 int parm_inter_launch_forces(parm_inter *inter, unsigned want, bool accumulate, double *d_out /*device, 13 doubles*/,
-                             const int *abort_flag = nullptr);
+                             const int *abort_flag = nullptr, uint32_t first = 0, uint32_t count = 0xffffffffu);
 int parm_ctx_ensure_red(parm_ctx *ctx, size_t doubles);
 
 // ---- device helpers ----

@@ -97,6 +97,13 @@ extern "C" int parm_ctx_create_sharded(int ndim, uint32_t n_global, uint32_t cap
     CK(cudaMallocHost(&sh.h_counts, 16 * 4));
     CK(cudaMalloc(&sh.d_gather, 2 * 8 * (size_t)nranks));
     CK(cudaMallocHost(&sh.h_gather, 2 * 8 * (size_t)nranks));
+    {   // highest priority: the small exchange kernels must get SM slots while the force kernel fills the GPU
+        int lo_prio = 0, hi_prio = 0;
+        CK(cudaDeviceGetStreamPriorityRange(&lo_prio, &hi_prio));
+        CK(cudaStreamCreateWithPriority(&sh.comm_stream, cudaStreamNonBlocking, hi_prio));
+    }
+    CK(cudaEventCreateWithFlags(&sh.ev_k1, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&sh.ev_comm, cudaEventDisableTiming));
     ncclUniqueId id;
     memcpy(&id, id128, 128);
     ncclComm_t comm;
@@ -289,7 +296,10 @@ int parm_shard_allreduce_sum(parm_ctx *c, double *d_buf, int count) {
     return 0;
 }
 
-int parm_shard_halo_exchange(parm_ctx *c) {
+static int halo_exchange_on(parm_ctx *c, cudaStream_t st);
+int parm_shard_halo_exchange(parm_ctx *c) { return halo_exchange_on(c, c->stream); }
+
+static int halo_exchange_on(parm_ctx *c, cudaStream_t st) {
     ShardState &sh = c->sh;
     if (!sh.on) return 0;
     NcclApi *n = nccl_api();
@@ -298,10 +308,10 @@ int parm_shard_halo_exchange(parm_ctx *c) {
     NCK(n->GroupStart());
     // sends: [to down, to up]; receives: [from up, from down] -- with 2 ranks both neighbours are the same
     // peer and NCCL matches same-peer messages in issue order. Every range is contiguous in `pos`.
-    if (sh.s_dn) NCK(n->Send(c->pos, (size_t)sh.s_dn * 4, ncclFloat64, sh.down, comm, c->stream));
-    if (sh.s_up) NCK(n->Send(c->pos + (nl - sh.s_up), (size_t)sh.s_up * 4, ncclFloat64, sh.up, comm, c->stream));
-    if (sh.g_up) NCK(n->Recv(c->pos + nl, (size_t)sh.g_up * 4, ncclFloat64, sh.up, comm, c->stream));
-    if (sh.g_dn) NCK(n->Recv(c->pos + nl + sh.g_up, (size_t)sh.g_dn * 4, ncclFloat64, sh.down, comm, c->stream));
+    if (sh.s_dn) NCK(n->Send(c->pos, (size_t)sh.s_dn * 4, ncclFloat64, sh.down, comm, st));
+    if (sh.s_up) NCK(n->Send(c->pos + (nl - sh.s_up), (size_t)sh.s_up * 4, ncclFloat64, sh.up, comm, st));
+    if (sh.g_up) NCK(n->Recv(c->pos + nl, (size_t)sh.g_up * 4, ncclFloat64, sh.up, comm, st));
+    if (sh.g_dn) NCK(n->Recv(c->pos + nl + sh.g_up, (size_t)sh.g_dn * 4, ncclFloat64, sh.down, comm, st));
     NCK(n->GroupEnd());
     return 0;
 }
@@ -339,13 +349,31 @@ __global__ void k_fold_decision(const double *__restrict__ gathered, int nvals, 
     __threadfence_system();
 }
 
-int parm_shard_drift_enqueue(parm_nlist *nl, int *d_slot, int *h_slot) {
+static int drift_enqueue_on(parm_nlist *nl, int *d_slot, int *h_slot, cudaStream_t st) {
     parm_ctx *c = nl->ctx;
     ShardState &sh = c->sh;
     NcclApi *n = nccl_api();
-    NCK(n->AllGather(nl->d_flags->top2, sh.d_gather, 2, ncclFloat64, (ncclComm_t)sh.comm, c->stream));
-    k_fold_decision<<<1, 32, 0, c->stream>>>(sh.d_gather, 2 * sh.nranks, nl->skin, d_slot, h_slot);
+    NCK(n->AllGather(nl->d_flags->top2, sh.d_gather, 2, ncclFloat64, (ncclComm_t)sh.comm, st));
+    k_fold_decision<<<1, 32, 0, st>>>(sh.d_gather, 2 * sh.nranks, nl->skin, d_slot, h_slot);
     CK_LAUNCH(c);
+    return 0;
+}
+int parm_shard_drift_enqueue(parm_nlist *nl, int *d_slot, int *h_slot) { return drift_enqueue_on(nl, d_slot, h_slot, nl->ctx->stream); }
+
+// After K1 (queued on the main stream): exchange the boundary-layer positions and, with a tracker, all-gather
+// the per-rank top-2 displacements and fold them into the step's decision word -- all on the communication
+// stream, so the main stream can meanwhile compute the forces of the interior atoms.
+int parm_shard_step_comm(parm_ctx *c, parm_nlist *nl, int *d_slot, int *h_slot) {
+    ShardState &sh = c->sh;
+    CK(cudaEventRecord(sh.ev_k1, c->stream));
+    CK(cudaStreamWaitEvent(sh.comm_stream, sh.ev_k1, 0));
+    PTRY(halo_exchange_on(c, sh.comm_stream));
+    if (nl) PTRY(drift_enqueue_on(nl, d_slot, h_slot, sh.comm_stream));
+    CK(cudaEventRecord(sh.ev_comm, sh.comm_stream));
+    return 0;
+}
+int parm_shard_step_join(parm_ctx *c) {
+    CK(cudaStreamWaitEvent(c->stream, c->sh.ev_comm, 0));
     return 0;
 }
 
@@ -478,6 +506,7 @@ int parm_shard_destroy(parm_ctx *c) {
     if (!c->sh.on) return 0;
     NcclApi *n = nccl_api();
     if (n && c->sh.comm) n->CommDestroy((ncclComm_t)c->sh.comm);
+    if (c->sh.comm_stream) { cudaStreamDestroy(c->sh.comm_stream); cudaEventDestroy(c->sh.ev_k1); cudaEventDestroy(c->sh.ev_comm); }
     if (c->sh.d_counts) cudaFree(c->sh.d_counts);
     if (c->sh.h_counts) cudaFreeHost(c->sh.h_counts);
     if (c->sh.d_gather) cudaFree(c->sh.d_gather);
