@@ -515,29 +515,35 @@ k_build_cell(const double4 *__restrict__ pos, const double4 *__restrict__ pw, co
                         const uint32_t iself = i - jbase; // candidate index of this lane's own atom, if in the block
                         uint32_t m = 0;
                         bool near_any = false;
-                        // fully unrolled: the bit position is an immediate; lanes past the end of the run hold NaN
+                        // 4 x 8: the inner 8 tests are unrolled (bit position = immediate + c0); lanes past the end of the
+                        // run hold NaN and fail every test
+                        for (int c0 = 0; c0 < 32; c0 += 8) {
+                            uint32_t m8 = 0;
 #pragma unroll
-                        for (int c = 0; c < 32; c++) {
-                            const double4 q = s_c[wib][c];
-                            double dx = wi.x - q.x, dy = wi.y - q.y, dz = wi.z - q.z;
-                            if (SMALLBOX) {
-                                if (!st.open0) dx = min_image_fast(dx, box.L[0], box.invL[0]);
-                                dy = min_image_fast(dy, box.L[1], box.invL[1]);
-                                dz = min_image_fast(dz, box.L[2], box.invL[2]);
+                            for (int k = 0; k < 8; k++) {
+                                const double4 q = s_c[wib][c0 + k];
+                                double dx = wi.x - q.x, dy = wi.y - q.y, dz = wi.z - q.z;
+                                if (SMALLBOX) {
+                                    if (!st.open0) dx = min_image_fast(dx, box.L[0], box.invL[0]);
+                                    dy = min_image_fast(dy, box.L[1], box.invL[1]);
+                                    dz = min_image_fast(dz, box.L[2], box.invL[2]);
+                                }
+                                const double dsq = fma(dx, dx, fma(dy, dy, dz * dz));
+                                double thr2, thr2lo;
+                                if (UNIFORM) {
+                                    thr2 = uthr2;
+                                    thr2lo = uthr2lo;
+                                } else {
+                                    const double thr = wi.w + q.w; // NaN for non-members
+                                    thr2 = thr * thr;
+                                    thr2lo = thr2 * lo;
+                                }
+                                const bool pass = dsq < thr2;
+                                near_any |= pass && !(dsq < thr2lo);
+                                if (pass) m8 |= 1u << k;
                             }
-                            const double dsq = fma(dx, dx, fma(dy, dy, dz * dz));
-                            double thr2, thr2lo;
-                            if (UNIFORM) {
-                                thr2 = uthr2;
-                                thr2lo = uthr2lo;
-                            } else {
-                                const double thr = wi.w + q.w; // NaN for non-members
-                                thr2 = thr * thr;
-                                thr2lo = thr2 * lo;
-                            }
-                            const bool pass = dsq < thr2;
-                            near_any |= pass && !(dsq < thr2lo);
-                            if (pass) m |= 1u << c;
+                            m |= m8 << c0;
+                            if (c0 + 8 >= nb) break;
                         }
                         if (iself < 32u) m &= ~(1u << iself); // never its own neighbour
                         if (__any_sync(0xffffffffu, near_any && member)) {
