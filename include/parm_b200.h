@@ -119,6 +119,19 @@ int parm_nlist_stats(parm_nlist *nl, double *mean_full_neighbors, uint32_t *max_
 #define PARM_PAIR_REPULSION 1        /* NListed<EpsSigExpAtom, RepulsionPair>    :1454-1465, 1528-1550 */
 #define PARM_PAIR_LJATTRACTREPULSE 2 /* NListed<IEpsSigCutAtom, LJAttractRepulsePair> :989-1018, 1251-1299 */
 #define PARM_PAIR_LJCUT 3            /* NListed<EpsSigCutAtom, LennardJonesCutPair>   :897-905, 967-987, 238-281 */
+/* the remaining NListed functors of sim.i:621-643 */
+#define PARM_PAIR_LJATTRACTCUT 4           /* LJAttractCutPair :1020-1049 + LJAttractCut :197-236 */
+#define PARM_PAIR_LJATTRACTFIXEDREPULSE 5  /* NListed<IEpsRepsSigCutAtom, LJAttractFixedRepulsePair> :1307-1413 */
+#define PARM_PAIR_EISMCLACHLAN 6           /* NListed<EisMclachlanAtom, EisMclachlanPair> :1415-1452 */
+#define PARM_PAIR_LJISH 7                  /* NListed<IEpsRepsSigExpCutAtom, LJishPair> :1051-1142 */
+#define PARM_PAIR_LJATTRACTREPULSESIGS 8   /* NListed<EpsEpsSigSigCutAtom, LJAttractRepulseSigsPair> :1149-1244 */
+#define PARM_PAIR_REPULSIONDRAG 9          /* NListed<EpsSigExpDragAtom, RepulsionDragPair> :1598-1642 */
+#define PARM_PAIR_LOISOHERN 10             /* NListed<LoisOhernAtom, LoisOhernPair> :1679-1744 */
+#define PARM_PAIR_LOISLIN 11               /* NListed<LoisLinAtom, LoisLinPair> :1764-1829 */
+#define PARM_PAIR_LOISOHERNMIN 12          /* NListed<LoisOhernAtom, LoisOhernPairMinCLs> :1746-1752 */
+#define PARM_PAIR_LOISLINMIN 13            /* NListed<LoisLinAtom, LoisLinPairMin> :1831-1837 */
+#define PARM_PAIR_NKINDS 14
+#define PARM_PAIR_MAXPARAMS 5
 int parm_inter_create(parm_ctx *ctx, parm_nlist *nl, int pair_kind, parm_inter **out);
 int parm_inter_destroy(parm_inter *inter);
 /* per-atom A structs for all atoms at once. params is n x 3 doubles:
@@ -130,6 +143,29 @@ int parm_inter_destroy(parm_inter *inter);
  * interaction.hpp:1906-1910) when set_diameters != 0. member: optional n bytes. */
 int parm_inter_set_params(parm_inter *inter, const double *params, const uint32_t *type, const double *eps_table,
                           int ntypes, const uint8_t *member, int set_diameters);
+/* General form: params is n x nper doubles (nper <= PARM_PAIR_MAXPARAMS), per kind
+ *   0  LJREPULSE              EpsSigAtom             (epsilon, sigma)
+ *   1  REPULSION              EpsSigExpAtom          (eps, sigma, exponent)
+ *                             IEpsISigExpAtom        (-, -, exponent) + eps_table + sig_table   [RepulsionII]
+ *   2  LJATTRACTREPULSE       IEpsSigCutAtom         (-, sigma, sigcut) + eps_table
+ *   3  LJCUT                  EpsSigCutAtom          (epsilon, sigma, sigcut)
+ *                             IEpsISigCutAtom        (-, -, sigcut) + eps_table + sig_table     [LJIICut]
+ *   4  LJATTRACTCUT           EpsSigCutAtom          (epsilon, sigma, sigcut)                   [LJAttractCut]
+ *                             IEpsSigCutAtom         (-, sigma, sigcut) + eps_table             [LJAttractICut]
+ *                             IEpsISigCutAtom        (-, -, sigcut) + eps_table + sig_table     [LJAttractIICut]
+ *   5  LJATTRACTFIXEDREPULSE  IEpsRepsSigCutAtom     (-, sig, sigcut, repeps) + eps_table
+ *   6  EISMCLACHLAN           EisMclachlanAtom       (sigmai, dist)
+ *   7  LJISH                  IEpsRepsSigExpCutAtom  (-, sigma, sigcut, repeps, exponent) + eps_table
+ *   8  LJATTRACTREPULSESIGS   EpsEpsSigSigCutAtom    (eps_r, sig_r, sigcut, eps_a, sig_a)
+ *   9  REPULSIONDRAG          EpsSigExpDragAtom      (eps, sigma, exponent, gamma)
+ *   10 LOISOHERN / 12 ..MIN   LoisOhernAtom          (eps, sigma, C, l)
+ *   11 LOISLIN / 13 ..MIN     LoisLinAtom            (eps, sigma, f, l)   f = depth/width as the ctor stores it
+ * type[i] is the atom's `indx`; eps_table / sig_table are ntypes x ntypes, row t = the `epsilons` / `sigmas`
+ * vector carried by atoms of indx t, and must be symmetric (the reference asserts it for IEpsSigCutAtom,
+ * :1013-1014; for the other indexed structs an asymmetric table would make the result depend on pair order). */
+int parm_inter_set_params_ex(parm_inter *inter, const double *params, int nper, const uint32_t *type,
+                             const double *eps_table, const double *sig_table, int ntypes, const uint8_t *member,
+                             int set_diameters);
 #define PARM_WANT_ENERGY 1u
 #define PARM_WANT_VIRIAL 2u
 #define PARM_WANT_STRESS 4u

@@ -17,6 +17,8 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 
 KIND_LJREPULSE, KIND_REPULSION, KIND_LJATTRACTREPULSE, KIND_LJCUT = 0, 1, 2, 3
+(KIND_LJATTRACTCUT, KIND_LJATTRACTFIXEDREPULSE, KIND_EISMCLACHLAN, KIND_LJISH, KIND_LJATTRACTREPULSESIGS,
+ KIND_REPULSIONDRAG, KIND_LOISOHERN, KIND_LOISLIN, KIND_LOISOHERNMIN, KIND_LOISLINMIN) = range(4, 14)
 VERLET, SOL = 0, 1
 
 _dp = C.POINTER(C.c_double)
@@ -78,6 +80,9 @@ def _load(backend, ndim):
     api["sys_destroy"] = sig("sys_destroy", None, [vp])
     api["add_interaction"] = sig("add_interaction", C.c_int,
                                  [vp, C.c_int, C.c_double, _dp, _u32p, _dp, C.c_int, _u8p, C.c_int, C.c_int])
+    api["add_interaction_ex"] = sig("add_interaction_ex", C.c_int,
+                                    [vp, C.c_int, C.c_double, _dp, C.c_int, _u32p, _dp, _dp, C.c_int, _u8p, C.c_int, C.c_int])
+    api["inter_contacts"] = sig("inter_contacts", C.c_int, [vp, C.c_int, C.POINTER(C.c_ulonglong), C.POINTER(C.c_ulonglong)])
     api["make_collection"] = sig("make_collection", C.c_int, [vp, C.c_int, C.c_double, C.c_double, C.c_double])
     api["update_list"] = sig("update_list", C.c_int, [vp, C.c_int, C.c_int])
     api["which"] = sig("which", C.c_uint32, [vp, C.c_int])
@@ -142,15 +147,19 @@ class CpuSystem:
         except Exception:
             pass
 
-    def add_interaction(self, kind, skin, params, types=None, eps_table=None, member=None, injected=False, share_nl=-1):
-        params = np.ascontiguousarray(params, dtype=np.float64).reshape(self.n, 3)
+    def add_interaction(self, kind, skin, params, types=None, eps_table=None, member=None, injected=False, share_nl=-1,
+                        sig_table=None):
+        """params: n x nper (nper <= 5), layout per kind as in include/parm_b200.h."""
+        params = np.ascontiguousarray(params, dtype=np.float64)
+        params = params.reshape(self.n, params.size // self.n if self.n else 3)
         t = None if types is None else np.ascontiguousarray(types, dtype=np.uint32)
         e = None if eps_table is None else np.ascontiguousarray(eps_table, dtype=np.float64)
+        sg = None if sig_table is None else np.ascontiguousarray(sig_table, dtype=np.float64)
         nt = 0 if e is None else e.shape[0]
         mem = None if member is None else np.ascontiguousarray(member, dtype=np.uint8)
-        r = self.api["add_interaction"](
-            self.h, kind, float(skin), _d(params),
-            None if t is None else t.ctypes.data_as(_u32p), _d(e), nt,
+        r = self.api["add_interaction_ex"](
+            self.h, kind, float(skin), _d(params), params.shape[1],
+            None if t is None else t.ctypes.data_as(_u32p), _d(e), _d(sg), nt,
             None if mem is None else mem.ctypes.data_as(_u8p), int(injected), share_nl)
         if r < 0:
             raise RuntimeError("oracle add_interaction failed: %d" % r)
@@ -213,6 +222,13 @@ class CpuSystem:
         out = np.empty((self.ndim, self.ndim))
         self.api["inter_stress"](self.h, k, _d(out))
         return out
+
+    def inter_contacts(self, k=0):
+        """(contacts, overlaps) of NListed<A,P> (interaction.hpp:2126-2151)."""
+        c, o = C.c_ulonglong(0), C.c_ulonglong(0)
+        if self.api["inter_contacts"](self.h, k, C.byref(c), C.byref(o)):
+            raise RuntimeError("oracle inter_contacts failed")
+        return c.value, o.value
 
     def timestep(self, n=1):
         self.api["timestep"](self.h, n)

@@ -18,19 +18,23 @@
  */
 #include <math.h>
 #include <stdint.h>
+#ifndef M_PI
+#define M_PI 3.14159265358979323846 /* glibc math.h value; hidden by -std=c11 */
+#endif
 #include <stdlib.h>
 #include <string.h>
 
 typedef struct {
-    double eps, sig, c, cutE; /* c: exponent (kind 1) or cut_distance (2,3) */
+    double eps, sig, c, cutE; /* c: exponent (kinds 1, 9) or cut_distance (2,3,4,5,7,8) */
+    double e2, s2, x, y;      /* second epsilon / sigma and functor-specific members (see update_pairs) */
     uint32_t i, j;            /* atom1 = first() = i (later atom), atom2 = j */
 } Pair;
 
 typedef struct {
     int kind;
-    double *params; /* n x 3 */
+    double *params; /* n x NPER, layout per kind: include/parm_b200.h (parm_inter_set_params_ex) */
     uint32_t *type;
-    double *eps_table;
+    double *eps_table, *sig_table; /* ntypes x ntypes; NULL = not indexed */
     int ntypes;
     int nl;
     uint32_t last_update;
@@ -106,6 +110,7 @@ void port_sys_destroy(void *h) {
         free(s->inters[k].params);
         free(s->inters[k].type);
         free(s->inters[k].eps_table);
+        free(s->inters[k].sig_table);
         free(s->inters[k].pairs);
     }
     for (int k = 0; k < s->nnls; k++) {
@@ -117,15 +122,35 @@ void port_sys_destroy(void *h) {
     free(s);
 }
 
-/* A::max_size(): interaction.hpp:864 (sigma), :1464 (sigma), :1017 and :905 (sigma*sigcut) */
-static double max_size(int kind, const double *p) { return (kind == 0 || kind == 1) ? p[1] : p[1] * p[2]; }
+#define NPER 5
+/* A::max_size(): interaction.hpp:864, :905, :953-959, :1017, :1091, :1168, :1340, :1422, :1464, :1517-1523,
+ * :1610, :1690, :1779 */
+static double max_size(const Inter *I, uint32_t i) {
+    const double *p = I->params + (size_t)NPER * i;
+    double sigma = p[1];
+    if (I->sig_table) {
+        const double *row = I->sig_table + (size_t)I->type[i] * I->ntypes;
+        sigma = row[0];
+        for (int k = 1; k < I->ntypes; k++)
+            if (sigma < row[k]) sigma = row[k];
+    }
+    switch (I->kind) {
+        case 0: case 1: case 9: return sigma;
+        case 6: return p[1];
+        case 8: return p[1] + p[4] * (p[2] - 1);
+        case 10: case 12: return p[1] * (1 + p[2] + p[3]);
+        case 11: case 13: return p[1] * (1 + p[3]);
+        default: return sigma * p[2];
+    }
+}
 
 static void collection_update_trackers(Sys *s);
 
-int port_add_interaction(void *h, int kind, double skin, const double *params, const uint32_t *type,
-                         const double *eps_table, int ntypes, const uint8_t *member, int injected, int share_nl) {
+int port_add_interaction_ex(void *h, int kind, double skin, const double *params, int nper, const uint32_t *type,
+                            const double *eps_table, const double *sig_table, int ntypes, const uint8_t *member,
+                            int injected, int share_nl) {
     Sys *s = (Sys *)h;
-    if (kind < 0 || kind > 3) return -1;
+    if (kind < 0 || kind > 13 || nper < 1 || nper > NPER) return -1;
     int nl = share_nl;
     if (nl < 0) { /* NeighborList ctor, trackers.cpp:10-17 */
         s->nls = (NList *)realloc(s->nls, sizeof(NList) * (s->nnls + 1));
@@ -145,25 +170,37 @@ int port_add_interaction(void *h, int kind, double skin, const double *params, c
     memset(I, 0, sizeof(Inter));
     I->kind = kind;
     I->nl = nl;
-    I->params = (double *)malloc((size_t)(s->n ? s->n : 1) * 3 * 8);
-    memcpy(I->params, params, (size_t)s->n * 3 * 8);
+    I->params = (double *)calloc((size_t)(s->n ? s->n : 1) * NPER, 8);
+    for (uint32_t i = 0; i < s->n; i++) memcpy(I->params + (size_t)NPER * i, params + (size_t)nper * i, 8 * (size_t)nper);
     I->type = (uint32_t *)calloc(s->n ? s->n : 1, 4);
     if (type) memcpy(I->type, type, (size_t)s->n * 4);
     I->ntypes = ntypes > 0 ? ntypes : 1;
-    I->eps_table = (double *)calloc((size_t)I->ntypes * I->ntypes, 8);
-    if (eps_table) memcpy(I->eps_table, eps_table, (size_t)I->ntypes * I->ntypes * 8);
+    if (eps_table) {
+        I->eps_table = (double *)calloc((size_t)I->ntypes * I->ntypes, 8);
+        memcpy(I->eps_table, eps_table, (size_t)I->ntypes * I->ntypes * 8);
+    }
+    if (sig_table) {
+        I->sig_table = (double *)calloc((size_t)I->ntypes * I->ntypes, 8);
+        memcpy(I->sig_table, sig_table, (size_t)I->ntypes * I->ntypes * 8);
+    }
     NList *l = &s->nls[nl];
     for (uint32_t i = 0; i < s->n; i++) { /* NListed::add -> NeighborList::add, interaction.hpp:1906-1910, trackers.hpp:194-201 */
         if (member && !member[i]) continue;
         if (l->member[i]) return -3; /* SubGroup::add throws on duplicates, box.hpp:495-501 */
         l->member[i] = 1;
         l->ids[l->nids] = i;
-        l->diam[l->nids] = max_size(kind, params + 3 * (size_t)i);
+        l->diam[l->nids] = max_size(I, i);
         memcpy(l->lastlocs + (size_t)l->nids * s->D, s->x + (size_t)i * s->D, 8 * s->D);
         l->nids++;
         l->ignorechanged = 1;
     }
     return s->ninters++;
+}
+
+int port_add_interaction(void *h, int kind, double skin, const double *params, const uint32_t *type,
+                         const double *eps_table, int ntypes, const uint8_t *member, int injected, int share_nl) {
+    return port_add_interaction_ex(h, kind, skin, params, 3, type, kind == 2 ? eps_table : NULL, NULL, ntypes, member,
+                                   injected, share_nl);
 }
 
 static void push_pair(NList *l, uint32_t a, uint32_t b) {
@@ -290,9 +327,36 @@ static int nl_update_list(Sys *s, NList *l, int force) {
     return 1;
 }
 
+static double dmax(double a, double b) { return a < b ? b : a; } /* std::max */
+static double dmin(double a, double b) { return a < b ? a : b; } /* (a1.C < a2.C ? a1.C : a2.C) */
+
+/* LJAttract::energy(rsig), interaction.hpp:170-177 */
+static double ljattract_energy_rsig(double rsig) {
+    if (rsig < 1) return -1;
+    double rsq = rsig * rsig;
+    double rsix = rsq * rsq * rsq;
+    double mid = (1 - 1 / rsix);
+    return mid * mid - 1;
+}
+
+/* LJAttractRepulseSigsPair::attract_energy / repulse_energy :1195-1205 (eps_r = eps, eps_a = e2, sig_r = sig, sig_a = s2) */
+static double sigs_attract_energy(const Pair *P, double r) {
+    double r_over_sig = (r - P->sig + P->s2) / P->s2;
+    double mid = (1 - pow(r_over_sig, -6));
+    return P->e2 * (mid * mid) - P->e2;
+}
+static double sigs_repulse_energy(const Pair *P, double r) {
+    double r_over_sig = r / P->sig;
+    double mid = (1 - pow(r_over_sig, -6));
+    return P->eps * (mid * mid) - P->e2;
+}
+
 /* NListed<A,P>::update_pairs, interaction.hpp:2102-2115; pair constructors:
- * LJRepulsePair :878-883, RepulsionPair :1531-1536, LJAttractRepulsePair :1255-1270,
- * LennardJonesCutPair :970-974 + LennardJonesCut ctor :247-252 */
+ * LJRepulsePair :878-883, RepulsionPair :1531-1542, LJAttractRepulsePair :1255-1270,
+ * LennardJonesCutPair :970-979 + LennardJonesCut ctor :247-252, LJAttractCutPair :1023-1040 + LJAttractCut ctor
+ * :205-209, LJAttractFixedRepulsePair :1347-1364, EisMclachlanPair :1430-1439, LJishPair :1098-1114,
+ * LJAttractRepulseSigsPair :1175-1193, RepulsionDragPair :1617-1623, LoisOhernPair :1696-1712 (+MinCLs :1747-1751),
+ * LoisLinPair :1785-1801 (+Min :1832-1836) */
 static void update_pairs(Sys *s, Inter *I) {
     NList *l = &s->nls[I->nl];
     if (I->last_update == l->updatenum) return;
@@ -302,22 +366,31 @@ static void update_pairs(Sys *s, Inter *I) {
         I->pairs = (Pair *)realloc(I->pairs, I->cappairs * sizeof(Pair));
     }
     I->npairs = l->npairs;
+    const int nt = I->ntypes;
     for (size_t k = 0; k < l->npairs; k++) {
         uint32_t i = l->first[k], j = l->last[k];
-        const double *p1 = I->params + 3 * (size_t)i, *p2 = I->params + 3 * (size_t)j;
+        const double *p1 = I->params + (size_t)NPER * i, *p2 = I->params + (size_t)NPER * j;
+        const size_t tij = (size_t)I->type[i] * nt + I->type[j]; /* a1.epsilons[a2.indx] */
         Pair P;
-        P.i = i; P.j = j; P.c = 0; P.cutE = 0;
-        if (I->kind == 0) {
+        memset(&P, 0, sizeof(P));
+        P.i = i; P.j = j;
+        const int kind = I->kind;
+        if (kind == 0) {
             P.eps = sqrt(p1[0] * p2[0]);
             P.sig = (p1[1] + p2[1]) / 2;
-        } else if (I->kind == 1) {
-            P.eps = sqrt(p1[0] * p2[0]);
-            P.sig = (p1[1] + p2[1]) / 2.0;
+        } else if (kind == 1) {
+            if (I->eps_table) {
+                P.eps = I->eps_table[tij];
+                P.sig = I->sig_table[tij];
+            } else {
+                P.eps = sqrt(p1[0] * p2[0]);
+                P.sig = (p1[1] + p2[1]) / 2.0;
+            }
             P.c = (p1[2] + p2[2]) / 2.0;
-        } else if (I->kind == 2) {
-            P.eps = I->eps_table[(size_t)I->type[i] * I->ntypes + I->type[j]];
+        } else if (kind == 2) {
+            P.eps = I->eps_table[tij];
             P.sig = (p1[1] + p2[1]) / 2.0;
-            P.c = p1[2] > p2[2] ? p1[2] : p2[2]; /* max(a1.sigcut, a2.sigcut) */
+            P.c = dmax(p1[2], p2[2]); /* max(a1.sigcut, a2.sigcut) */
             if (P.eps <= 0) {
                 P.c = 1;
                 P.cutE = 0;
@@ -326,84 +399,291 @@ static void update_pairs(Sys *s, Inter *I) {
                 double mid = (1 - pow(P.c, -6));
                 P.cutE = P.eps * (mid * mid);
             }
-        } else {
+        } else if (kind == 3 || kind == 4) {
+            if (I->eps_table && I->sig_table) {
+                P.eps = I->eps_table[tij];
+                P.sig = I->sig_table[tij];
+            } else if (I->eps_table) { /* LJAttractCutPair(IEpsSigCutAtom, IEpsSigCutAtom) :1035-1040 */
+                P.eps = I->eps_table[tij];
+                P.sig = (p1[1] + p2[1]) / 2;
+            } else {
+                P.eps = sqrt(p1[0] * p2[0]);
+                P.sig = (p1[1] + p2[1]) / 2;
+            }
+            P.c = dmax(p1[2], p2[2]);
+            if (kind == 3) {
+                double rsix = pow(P.c, 6);
+                double mid = (1 - 1 / rsix);
+                P.cutE = P.eps * (mid * mid - 1);
+            } else {
+                P.cutE = ljattract_energy_rsig(P.c) * P.eps;
+            }
+        } else if (kind == 5) {
+            double e12 = I->eps_table[tij];
+            P.eps = fabs(e12);
+            P.e2 = sqrt(p1[3] * p2[3]); /* repeps */
+            P.sig = (p1[1] + p2[1]) / 2.0;
+            P.c = dmax(p1[2], p2[2]);
+            if (!(e12 > 0) || P.eps == 0) {
+                P.c = 1;
+                P.cutE = 0;
+                P.eps = 0;
+            } else {
+                double mid = (1 - pow(P.c, -6.0));
+                P.cutE = P.eps * (mid * mid);
+            }
+        } else if (kind == 6) { /* p = (sigmai, dist): c0 = eps, c1 = x, c2 = y, cutoff = sig */
+            P.eps = -M_PI * (p1[0] * p2[1] - p2[0] * p1[1]) * (p1[1] * p1[1] - p2[1] * p2[1]);
+            P.x = -2 * M_PI * (p1[0] * p2[1] * p2[1] + p2[0] * p1[1] * p1[1]);
+            P.y = M_PI * (p1[0] * p2[1] + p2[0] * p1[1]);
+            P.sig = p1[1] + p2[1];
+        } else if (kind == 7) { /* n = x */
+            P.eps = I->eps_table[tij];
+            P.e2 = sqrt(p1[3] * p2[3]);
+            P.sig = (p1[1] + p2[1]) / 2.0;
+            P.x = (p1[4] + p2[4]) / 2;
+            P.c = dmax(p1[2], p2[2]);
+            if (P.eps <= 0) {
+                P.c = 1;
+                P.cutE = 0;
+                P.eps = 0;
+            } else {
+                double mid = (1 - pow(P.c, -P.x));
+                P.cutE = P.eps * (mid * mid);
+            }
+        } else if (kind == 8) {
             P.eps = sqrt(p1[0] * p2[0]);
-            P.sig = (p1[1] + p2[1]) / 2;
-            P.c = p1[2] > p2[2] ? p1[2] : p2[2];
-            double rsix = pow(P.c, 6);
-            double mid = (1 - 1 / rsix);
-            P.cutE = P.eps * (mid * mid - 1);
+            P.e2 = sqrt(p1[3] * p2[3]);
+            P.sig = (p1[1] + p2[1]) / 2.0;
+            P.s2 = (p1[4] + p2[4]) / 2.0;
+            P.c = dmax(p1[2], p2[2]);
+            if (P.c > 0) { /* (cut_energy stays uninitialised in the reference when cut_distance <= 0; 0 here) */
+                double cdu = P.sig + P.s2 * (P.c - 1);
+                if (P.c >= 1)
+                    P.cutE = sigs_attract_energy(&P, cdu);
+                else
+                    P.cutE = sigs_repulse_energy(&P, cdu);
+            }
+        } else if (kind == 9) { /* gamma = x */
+            P.eps = sqrt(p1[0] * p2[0]);
+            P.sig = (p1[1] + p2[1]) / 2.0;
+            P.c = (p1[2] + p2[2]) / 2.0;
+            P.x = (p1[3] + p2[3]) / 2;
+        } else if (kind == 10 || kind == 12) { /* C = x, l = y, sigcut = s2 */
+            P.eps = sqrt(p1[0] * p2[0]);
+            P.sig = (p1[1] + p2[1]) / 2.0;
+            P.x = kind == 10 ? (p1[2] + p2[2]) / 2.0 : dmin(p1[2], p2[2]);
+            P.y = kind == 10 ? (p1[3] + p2[3]) / 2.0 : dmin(p1[3], p2[3]);
+            P.s2 = P.sig * (1 + P.x + P.y);
+        } else { /* 11, 13: f = x, l = y, sigcut = s2 */
+            P.eps = sqrt(p1[0] * p2[0]);
+            P.sig = (p1[1] + p2[1]) / 2.0;
+            P.x = kind == 11 ? (p1[2] + p2[2]) / 2.0 : dmin(p1[2], p2[2]);
+            P.y = kind == 11 ? (p1[3] + p2[3]) / 2.0 : dmin(p1[3], p2[3]);
+            P.s2 = P.sig + P.y;
         }
         I->pairs[k] = P;
     }
 }
 
 /* P::forces(box): LJRepulsive::forces interaction.hpp:135-151; RepulsionPair::forces :1544-1550;
- * LJAttractRepulsePair::forces :1289-1298; LennardJonesCut::forces :259-267.
+ * LJAttractRepulsePair::forces :1289-1298; LennardJonesCut::forces :259-267; LJAttractCut::forces :222-232;
+ * LJAttractFixedRepulsePair::forces :1388-1394; EisMclachlanPair::forces :1446-1452; LJishPair::forces :1130-1141;
+ * LJAttractRepulseSigsPair::forces :1222-1243; RepulsionDragPair::forces :1631-1641; LoisOhernPair::forces
+ * :1729-1743; LoisLinPair::forces :1816-1828.
  * Returns 0 when the force is exactly Vec::Zero(). rij = diff(atom1->x, atom2->x). */
 static int pair_forces(const Sys *s, const Inter *I, const Pair *P, double *rij, double *f) {
     const int D = s->D;
+    const int kind = I->kind;
     rij[2] = 0;
     f[0] = f[1] = f[2] = 0;
-    if (I->kind == 2 && P->eps == 0) return 0;
+    if (kind == 2 && P->eps == 0) return 0;
     box_diff(s, s->x + (size_t)P->i * D, s->x + (size_t)P->j * D, rij);
     double dsq = sum3(D, rij[0] * rij[0], rij[1] * rij[1], rij[2] * rij[2]);
     double scal;
-    if (I->kind == 0) {
+    if (kind == 0) {
         double rsq = dsq / (P->sig * P->sig);
         if (rsq > 1) return 0;
         double rsix = rsq * rsq * rsq;
         double fmagTimesR = 12 * P->eps / rsix * (1 / rsix - 1);
         scal = fmagTimesR / dsq;
-    } else if (I->kind == 1) {
+    } else if (kind == 1) {
         if (dsq > P->sig * P->sig) return 0;
         double R = sqrt(dsq);
         scal = P->eps * pow(1.0 - (R / P->sig), P->c - 1) / P->sig / R;
-    } else if (I->kind == 2) {
+    } else if (kind == 2) {
         double rsq = dsq / (P->sig * P->sig);
         if (rsq > (P->c * P->c)) return 0;
         double rsix = pow(rsq, -3);
         double fmagTimesR = 12 * P->eps * rsix * (rsix - 1);
         scal = fmagTimesR / dsq;
-    } else {
+    } else if (kind == 3) {
         double rsq = dsq / (P->sig * P->sig);
         if (rsq > (P->c * P->c)) return 0;
         double rsix = rsq * rsq * rsq;
         double fmagTimesR = 12 * P->eps / rsix * (1 / rsix - 1);
         scal = fmagTimesR / dsq;
+    } else if (kind == 4) {
+        if (P->eps == 0) return 0;
+        double rsq = dsq / (P->sig * P->sig);
+        if (rsq < 1 || rsq > (P->c * P->c)) return 0;
+        double rsix = rsq * rsq * rsq;
+        double fmagTimesR = 12 * P->eps / rsix * (1 / rsix - 1);
+        scal = fmagTimesR / dsq;
+    } else if (kind == 5) {
+        double rsq = dsq / (P->sig * P->sig);
+        if (rsq > (P->c * P->c)) return 0;
+        double rsix = pow(rsq, -3);
+        double fmagTimesR = 12 * rsix * (rsix - 1);
+        scal = rsq < 1 ? P->e2 * fmagTimesR / dsq : P->eps * fmagTimesR / dsq;
+    } else if (kind == 6) {
+        if (dsq > (P->sig * P->sig)) return 0;
+        double R = sqrt(dsq);
+        scal = (P->eps / dsq - P->y) / R;
+    } else if (kind == 7) {
+        double rsq = dsq / (P->sig * P->sig);
+        if (rsq > P->c * P->c) return 0;
+        double rmid = pow(rsq, -P->x / 2);
+        double fmagTimesR = 2 * P->x * rmid * (rmid - 1);
+        scal = rsq < 1 ? P->e2 * fmagTimesR / dsq : P->eps * fmagTimesR / dsq;
+    } else if (kind == 8) {
+        double cdu = P->sig + P->s2 * (P->c - 1);
+        if (P->c > 0 && dsq > cdu * cdu) return 0;
+        if (dsq > P->sig * P->sig) {
+            double dist = sqrt(dsq);
+            double rminus = dist - P->sig + P->s2;
+            double r_over_sig = rminus / P->s2;
+            double rsix = pow(r_over_sig, -6);
+            double fmag_over_r = 12 * rsix * (rsix - 1) / (dist * rminus);
+            scal = P->e2 * fmag_over_r;
+        } else {
+            double r_over_sigsq = dsq / (P->sig * P->sig);
+            double rsix = pow(r_over_sigsq, -3);
+            double fmagTimesR = 12 * rsix * (rsix - 1);
+            scal = P->eps * fmagTimesR / dsq;
+        }
+    } else if (kind == 9) {
+        if (dsq > P->sig * P->sig) return 0;
+        double vij[3] = {0, 0, 0};
+        for (int k = 0; k < D; k++) vij[k] = s->v[(size_t)P->i * D + k] - s->v[(size_t)P->j * D + k];
+        double R = sqrt(dsq);
+        double vr = sum3(D, vij[0] * rij[0], vij[1] * rij[1], vij[2] * rij[2]);
+        double el = P->eps * pow(1.0 - (R / P->sig), P->c - 1) / P->sig / R;
+        for (int k = 0; k < D; k++) { /* rij * el - (rij * vr / dsq) * gamma */
+            double v_perp = rij[k] * vr / dsq;
+            f[k] = rij[k] * el - v_perp * P->x;
+        }
+        return 1;
+    } else if (kind == 10 || kind == 12) {
+        if (dsq >= P->s2 * P->s2) return 0;
+        double R = sqrt(dsq);
+        double rsig = R / P->sig;
+        if (rsig <= 1 + P->x) {
+            double dR = rsig - 1;
+            scal = -P->eps * dR / R;
+        } else {
+            double dR2 = rsig - (P->x + P->y + 1);
+            scal = P->x * P->eps / P->y * dR2 / R;
+        }
+    } else {
+        if (dsq >= P->s2 * P->s2) return 0;
+        double R = sqrt(dsq);
+        if (R <= P->sig) {
+            double dR = 1.0 - (R / P->sig);
+            scal = P->eps * dR / P->sig / R;
+        } else {
+            for (int k = 0; k < D; k++) f[k] = -rij[k] * (P->x / R);
+            return 1;
+        }
     }
     for (int k = 0; k < D; k++) f[k] = rij[k] * scal;
     return 1;
 }
 
 /* P::energy(box): LJRepulsive::energy :126-133; RepulsionPair::energy :1537-1543;
- * LJAttractRepulsePair::energy :1271-1288; LennardJonesCut::energy :253-258 */
+ * LJAttractRepulsePair::energy :1271-1288; LennardJonesCut::energy :253-258; LJAttractCut::energy :216-221;
+ * LJAttractFixedRepulsePair::energy :1365-1387; EisMclachlanPair::energy :1440-1445; LJishPair::energy :1115-1129;
+ * LJAttractRepulseSigsPair::energy :1207-1220; RepulsionDragPair::energy :1624-1630; LoisOhernPair::energy
+ * :1714-1727; LoisLinPair::energy :1802-1814 */
 static double pair_energy(const Sys *s, const Inter *I, const Pair *P) {
     const int D = s->D;
+    const int kind = I->kind;
     double rij[3] = {0, 0, 0};
     box_diff(s, s->x + (size_t)P->i * D, s->x + (size_t)P->j * D, rij);
     double dsq = sum3(D, rij[0] * rij[0], rij[1] * rij[1], rij[2] * rij[2]);
-    if (I->kind == 0) {
+    if (kind == 0) {
         double rsq = dsq / (P->sig * P->sig);
         if (rsq > 1) return 0;
         double rsix = rsq * rsq * rsq;
         double mid = (1 - 1 / rsix);
         return P->eps * (mid * mid);
-    } else if (I->kind == 1) {
+    } else if (kind == 1 || kind == 9) {
         if (dsq > P->sig * P->sig) return 0.0;
         double R = sqrt(dsq);
         return P->eps * pow(1.0 - (R / P->sig), P->c) / P->c;
-    } else if (I->kind == 2) {
+    } else if (kind == 2) {
         double rsq = dsq / (P->sig * P->sig);
         if (rsq > P->c * P->c) return 0;
         double mid = (1 - pow(rsq, -3));
         return P->eps * (mid * mid) - P->cutE;
-    } else {
+    } else if (kind == 3) {
         double rsq = dsq / (P->sig * P->sig);
         if (rsq > (P->c * P->c)) return 0;
         double rsix = rsq * rsq * rsq;
         double mid = (1 - 1 / rsix);
         return P->eps * (mid * mid - 1) - P->cutE;
+    } else if (kind == 4) {
+        if (P->eps == 0) return 0;
+        if (dsq > (P->c * P->c * P->sig * P->sig)) return 0;
+        double rsq = dsq / (P->sig * P->sig); /* LJAttract::energy(diff, eps, sig) :161-168 */
+        double lj;
+        if (rsq < 1)
+            lj = -P->eps;
+        else {
+            double rsix = rsq * rsq * rsq;
+            double mid = (1 - 1 / rsix);
+            lj = P->eps * (mid * mid - 1);
+        }
+        return lj - P->cutE;
+    } else if (kind == 5) {
+        double rsq = dsq / (P->sig * P->sig);
+        if (rsq > P->c * P->c) return 0;
+        double mid = (1 - pow(rsq, -3));
+        if (rsq > 1) return P->eps * (mid * mid) - P->cutE;
+        return P->e2 * (mid * mid) - P->cutE;
+    } else if (kind == 6) {
+        double R = sqrt(dsq);
+        if (R > P->sig) return 0;
+        return P->eps / R + P->x + P->y * R;
+    } else if (kind == 7) {
+        double rsq = dsq / (P->sig * P->sig);
+        if (rsq > P->c * P->c) return 0;
+        double mid = (1 - pow(rsq, -P->x / 2));
+        if (rsq > 1) return P->eps * (mid * mid) - P->cutE;
+        return P->e2 * (mid * mid) - P->cutE;
+    } else if (kind == 8) {
+        double dist = sqrt(dsq);
+        double cdu = P->sig + P->s2 * (P->c - 1);
+        if (P->c > 0 && dist > cdu) return 0;
+        if (dist <= P->sig) return sigs_repulse_energy(P, dist) - P->cutE;
+        return sigs_attract_energy(P, dist) - P->cutE;
+    } else if (kind == 10 || kind == 12) {
+        if (dsq >= P->s2 * P->s2) return 0.0;
+        double R = sqrt(dsq) / P->sig;
+        if (R <= 1 + P->x) {
+            double dR = R - 1;
+            return -P->eps * P->sig / 2 * (P->x * (P->x + P->y) - dR * dR);
+        }
+        double dR2 = P->x + P->y + 1 - R;
+        return -P->x * P->eps * P->sig / 2 / P->y * dR2 * dR2;
+    } else {
+        if (dsq >= P->s2 * P->s2) return 0.0;
+        double R = sqrt(dsq);
+        if (R <= P->sig) {
+            double dR = 1.0 - (R / P->sig);
+            return P->eps / 2 * dR * dR - P->x * P->y;
+        }
+        return -P->x * (P->sig + P->y - R);
     }
 }
 
@@ -440,6 +720,17 @@ static double inter_energy(Sys *s, Inter *I) { /* NListed::energy :2154-2163 */
     double E = 0;
     for (size_t k = 0; k < I->npairs; k++) E += pair_energy(s, I, &I->pairs[k]);
     return E;
+}
+
+/* NListed::contacts :2126-2137 (E != 0), ::overlaps :2140-2151 (E > 0) */
+static void inter_contacts(Sys *s, Inter *I, unsigned long long *c, unsigned long long *o) {
+    update_pairs(s, I);
+    *c = *o = 0;
+    for (size_t k = 0; k < I->npairs; k++) {
+        double E = pair_energy(s, I, &I->pairs[k]);
+        if (E != 0.0) (*c)++;
+        if (E > 0.0) (*o)++;
+    }
 }
 
 /* ---- AtomGroup reductions, box.cpp:239-260, 401-431 ---- */
@@ -677,6 +968,7 @@ void port_inter_set_forces(void *h, int k) { Sys *s = (Sys *)h; inter_loop(s, &s
 double port_inter_set_forces_get_pressure(void *h, int k) { Sys *s = (Sys *)h; double p; inter_loop(s, &s->inters[k], 1, &p, NULL); return p; }
 double port_inter_energy(void *h, int k) { Sys *s = (Sys *)h; return inter_energy(s, &s->inters[k]); }
 double port_inter_pressure(void *h, int k) { Sys *s = (Sys *)h; double p; inter_loop(s, &s->inters[k], 0, &p, NULL); return p; }
+int port_inter_contacts(void *h, int k, unsigned long long *c, unsigned long long *o) { Sys *s = (Sys *)h; inter_contacts(s, &s->inters[k], c, o); return 0; }
 void port_inter_stress(void *h, int k, double *out) { Sys *s = (Sys *)h; inter_loop(s, &s->inters[k], 0, NULL, out); }
 
 void port_set_forces(void *h, int constraints_and_a) { collection_set_forces((Sys *)h, constraints_and_a); }

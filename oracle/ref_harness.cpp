@@ -217,18 +217,29 @@ void *ref_sys_create(uint32_t n, const double *L, const double *x, const double 
 
 void ref_sys_destroy(void *h) { delete static_cast<Sys *>(h); }
 
-// kind: 0 NListed<EpsSigAtom,LJRepulsePair>            params (eps, sigma)
-//       1 NListed<EpsSigExpAtom,RepulsionPair>         params (eps, sigma, exponent)
-//       2 NListed<IEpsSigCutAtom,LJAttractRepulsePair> params (-, sigma, sigcut) + type + eps_table
-//       3 NListed<EpsSigCutAtom,LennardJonesCutPair>   params (eps, sigma, sigcut)
-// params: n x 3 row-major. member: optional n bytes, 0 = atom not added.
+}  // extern "C"
+// Adds every (member) atom i as A(make(i)) to a new FastNListed<A,P>.
+template <class A, class P, class MK>
+static void add_all(Sys *s, sptr<NeighborList> nlbase, InjectedNeighborList *nl, const uint8_t *member, MK make) {
+    sptr<FastNListed<A, P> > I(new FastNListed<A, P>(s->atoms, nlbase));
+    const uint n = s->atoms->size();
+    for (uint i = 0; i < n; i++)
+        if (!member || member[i]) I->add_fast(make(i), nl);
+    s->inters.push_back(I);
+}
+
+extern "C" {
+// kind and per-atom parameter layout: include/parm_b200.h (parm_inter_set_params_ex). params: n x nper
+// row-major; type[i] = indx; eps_table / sig_table: ntypes x ntypes, row t = the `epsilons` / `sigmas`
+// vector of atoms with indx t (NULL = that quantity is not indexed, which selects the A struct).
+// member: optional n bytes, 0 = atom not added.
 // injected: 0 = reference O(N^2) NeighborList, 1 = cell-list InjectedNeighborList
 // share_nl: -1 = new NeighborList, else index of an existing list to share
-int ref_add_interaction(void *h, int kind, double skin, const double *params, const uint32_t *type,
-                        const double *eps_table, int ntypes, const uint8_t *member, int injected, int share_nl) {
+int ref_add_interaction_ex(void *h, int kind, double skin, const double *params, int nper, const uint32_t *type,
+                           const double *eps_table, const double *sig_table, int ntypes, const uint8_t *member,
+                           int injected, int share_nl) {
     Sys *s = static_cast<Sys *>(h);
     AtomVec &av = *s->atoms;
-    const uint n = av.size();
     sptr<InjectedNeighborList> nl;
     if (share_nl >= 0)
         nl = s->nls[share_nl];
@@ -237,35 +248,65 @@ int ref_add_interaction(void *h, int kind, double skin, const double *params, co
         s->nls.push_back(nl);
     }
     sptr<NeighborList> nlbase = boost::static_pointer_cast<NeighborList>(nl);
+    InjectedNeighborList *inl = nl.get();
+    auto P = [&](uint i, int q) { return params[(size_t)nper * i + q]; };
+    auto T = [&](uint i) { return type ? type[i] : 0u; };
+    auto row = [&](const double *tab, uint t) { return vector<flt>(tab + (size_t)t * ntypes, tab + (size_t)(t + 1) * ntypes); };
     try {
         if (kind == 0) {
-            sptr<FastNListed<EpsSigAtom, LJRepulsePair> > I(new FastNListed<EpsSigAtom, LJRepulsePair>(s->atoms, nlbase));
-            for (uint i = 0; i < n; i++)
-                if (!member || member[i]) I->add_fast(EpsSigAtom(av.get_id(i), params[3 * i], params[3 * i + 1]), nl.get());
-            s->inters.push_back(I);
+            add_all<EpsSigAtom, LJRepulsePair>(s, nlbase, inl, member, [&](uint i) { return EpsSigAtom(av.get_id(i), P(i, 0), P(i, 1)); });
+        } else if (kind == 1 && !eps_table) {
+            add_all<EpsSigExpAtom, RepulsionPair>(s, nlbase, inl, member, [&](uint i) { return EpsSigExpAtom(av.get_id(i), P(i, 0), P(i, 1), P(i, 2)); });
         } else if (kind == 1) {
-            sptr<FastNListed<EpsSigExpAtom, RepulsionPair> > I(new FastNListed<EpsSigExpAtom, RepulsionPair>(s->atoms, nlbase));
-            for (uint i = 0; i < n; i++)
-                if (!member || member[i])
-                    I->add_fast(EpsSigExpAtom(av.get_id(i), params[3 * i], params[3 * i + 1], params[3 * i + 2]), nl.get());
-            s->inters.push_back(I);
+            add_all<IEpsISigExpAtom, RepulsionPair>(s, nlbase, inl, member, [&](uint i) {
+                return IEpsISigExpAtom(av.get_id(i), row(eps_table, T(i)), row(sig_table, T(i)), T(i), P(i, 2)); });
         } else if (kind == 2) {
-            sptr<FastNListed<IEpsSigCutAtom, LJAttractRepulsePair> > I(
-                new FastNListed<IEpsSigCutAtom, LJAttractRepulsePair>(s->atoms, nlbase));
-            for (uint i = 0; i < n; i++) {
-                if (member && !member[i]) continue;
-                uint t = type ? type[i] : 0;
-                vector<flt> eps(eps_table + (size_t)t * ntypes, eps_table + (size_t)(t + 1) * ntypes);
-                I->add_fast(IEpsSigCutAtom(av.get_id(i), eps, t, params[3 * i + 1], params[3 * i + 2]), nl.get());
-            }
-            s->inters.push_back(I);
+            add_all<IEpsSigCutAtom, LJAttractRepulsePair>(s, nlbase, inl, member, [&](uint i) {
+                return IEpsSigCutAtom(av.get_id(i), row(eps_table, T(i)), T(i), P(i, 1), P(i, 2)); });
+        } else if (kind == 3 && !eps_table) {
+            add_all<EpsSigCutAtom, LennardJonesCutPair>(s, nlbase, inl, member, [&](uint i) { return EpsSigCutAtom(av.get_id(i), P(i, 0), P(i, 1), P(i, 2)); });
         } else if (kind == 3) {
-            sptr<FastNListed<EpsSigCutAtom, LennardJonesCutPair> > I(
-                new FastNListed<EpsSigCutAtom, LennardJonesCutPair>(s->atoms, nlbase));
-            for (uint i = 0; i < n; i++)
-                if (!member || member[i])
-                    I->add_fast(EpsSigCutAtom(av.get_id(i), params[3 * i], params[3 * i + 1], params[3 * i + 2]), nl.get());
-            s->inters.push_back(I);
+            add_all<IEpsISigCutAtom, LennardJonesCutPair>(s, nlbase, inl, member, [&](uint i) {
+                return IEpsISigCutAtom(av.get_id(i), row(eps_table, T(i)), row(sig_table, T(i)), T(i), P(i, 2)); });
+        } else if (kind == 4 && !eps_table) {
+            add_all<EpsSigCutAtom, LJAttractCutPair>(s, nlbase, inl, member, [&](uint i) { return EpsSigCutAtom(av.get_id(i), P(i, 0), P(i, 1), P(i, 2)); });
+        } else if (kind == 4 && !sig_table) {
+            add_all<IEpsSigCutAtom, LJAttractCutPair>(s, nlbase, inl, member, [&](uint i) {
+                return IEpsSigCutAtom(av.get_id(i), row(eps_table, T(i)), T(i), P(i, 1), P(i, 2)); });
+        } else if (kind == 4) {
+            add_all<IEpsISigCutAtom, LJAttractCutPair>(s, nlbase, inl, member, [&](uint i) {
+                return IEpsISigCutAtom(av.get_id(i), row(eps_table, T(i)), row(sig_table, T(i)), T(i), P(i, 2)); });
+        } else if (kind == 5) {
+            add_all<IEpsRepsSigCutAtom, LJAttractFixedRepulsePair>(s, nlbase, inl, member, [&](uint i) {
+                return IEpsRepsSigCutAtom(av.get_id(i), row(eps_table, T(i)), P(i, 3), P(i, 1), T(i), P(i, 2)); });
+        } else if (kind == 6) {
+            add_all<EisMclachlanAtom, EisMclachlanPair>(s, nlbase, inl, member, [&](uint i) { return EisMclachlanAtom(av.get_id(i), P(i, 1), P(i, 0)); });
+        } else if (kind == 7) {
+            add_all<IEpsRepsSigExpCutAtom, LJishPair>(s, nlbase, inl, member, [&](uint i) {
+                return IEpsRepsSigExpCutAtom(av.get_id(i), row(eps_table, T(i)), P(i, 3), P(i, 1), P(i, 4), T(i), P(i, 2)); });
+        } else if (kind == 8) {
+            add_all<EpsEpsSigSigCutAtom, LJAttractRepulseSigsPair>(s, nlbase, inl, member, [&](uint i) {
+                return EpsEpsSigSigCutAtom(av.get_id(i), P(i, 0), P(i, 3), P(i, 1), P(i, 4), P(i, 2)); });
+        } else if (kind == 9) {
+            add_all<EpsSigExpDragAtom, RepulsionDragPair>(s, nlbase, inl, member, [&](uint i) {
+                return EpsSigExpDragAtom(av.get_id(i), P(i, 0), P(i, 1), P(i, 3), P(i, 2)); });
+        } else if (kind == 10 || kind == 12) {
+            // the LoisOhernAtom ctor stores its arguments unchanged
+            if (kind == 10)
+                add_all<LoisOhernAtom, LoisOhernPair>(s, nlbase, inl, member, [&](uint i) { return LoisOhernAtom(av.get_id(i), P(i, 0), P(i, 1), P(i, 2), P(i, 3)); });
+            else
+                add_all<LoisOhernAtom, LoisOhernPairMinCLs>(s, nlbase, inl, member, [&](uint i) { return LoisOhernAtom(av.get_id(i), P(i, 0), P(i, 1), P(i, 2), P(i, 3)); });
+        } else if (kind == 11 || kind == 13) {
+            // LoisLinAtom(a, eps, sigma, depth, width) stores f = depth/width: pass depth = f*width back in
+            auto mk = [&](uint i) {
+                LoisLinAtom a(av.get_id(i), P(i, 0), P(i, 1), 0.0, P(i, 3));
+                a.f = P(i, 2);
+                return a;
+            };
+            if (kind == 11)
+                add_all<LoisLinAtom, LoisLinPair>(s, nlbase, inl, member, mk);
+            else
+                add_all<LoisLinAtom, LoisLinPairMin>(s, nlbase, inl, member, mk);
         } else
             return -1;
     } catch (std::exception &e) {
@@ -273,6 +314,41 @@ int ref_add_interaction(void *h, int kind, double skin, const double *params, co
         return -2;
     }
     return (int)s->inters.size() - 1;
+}
+
+int ref_add_interaction(void *h, int kind, double skin, const double *params, const uint32_t *type,
+                        const double *eps_table, int ntypes, const uint8_t *member, int injected, int share_nl) {
+    return ref_add_interaction_ex(h, kind, skin, params, 3, type, kind == 2 ? eps_table : 0, 0, ntypes, member, injected, share_nl);
+}
+
+}  // extern "C"
+// NListed<A,P>::contacts / overlaps (interaction.hpp:2126-2151) are not virtuals of Interaction: dispatch on the type
+template <class A, class P>
+static bool try_contacts(Interaction *I, Box &box, unsigned long long *c, unsigned long long *o) {
+    NListed<A, P> *n = dynamic_cast<NListed<A, P> *>(I);
+    if (!n) return false;
+    *c = n->contacts(box);
+    *o = n->overlaps(box);
+    return true;
+}
+extern "C" {
+int ref_inter_contacts(void *h, int k, unsigned long long *c, unsigned long long *o) {
+    Sys *s = static_cast<Sys *>(h);
+    Interaction *I = s->inters[k].get();
+    Box &b = *s->box;
+    return (try_contacts<EpsSigAtom, LJRepulsePair>(I, b, c, o) || try_contacts<EpsSigExpAtom, RepulsionPair>(I, b, c, o) ||
+            try_contacts<IEpsISigExpAtom, RepulsionPair>(I, b, c, o) || try_contacts<IEpsSigCutAtom, LJAttractRepulsePair>(I, b, c, o) ||
+            try_contacts<EpsSigCutAtom, LennardJonesCutPair>(I, b, c, o) || try_contacts<IEpsISigCutAtom, LennardJonesCutPair>(I, b, c, o) ||
+            try_contacts<EpsSigCutAtom, LJAttractCutPair>(I, b, c, o) || try_contacts<IEpsSigCutAtom, LJAttractCutPair>(I, b, c, o) ||
+            try_contacts<IEpsISigCutAtom, LJAttractCutPair>(I, b, c, o) ||
+            try_contacts<IEpsRepsSigCutAtom, LJAttractFixedRepulsePair>(I, b, c, o) ||
+            try_contacts<EisMclachlanAtom, EisMclachlanPair>(I, b, c, o) || try_contacts<IEpsRepsSigExpCutAtom, LJishPair>(I, b, c, o) ||
+            try_contacts<EpsEpsSigSigCutAtom, LJAttractRepulseSigsPair>(I, b, c, o) ||
+            try_contacts<EpsSigExpDragAtom, RepulsionDragPair>(I, b, c, o) || try_contacts<LoisOhernAtom, LoisOhernPair>(I, b, c, o) ||
+            try_contacts<LoisOhernAtom, LoisOhernPairMinCLs>(I, b, c, o) || try_contacts<LoisLinAtom, LoisLinPair>(I, b, c, o) ||
+            try_contacts<LoisLinAtom, LoisLinPairMin>(I, b, c, o))
+               ? 0
+               : -1;
 }
 
 // integrator: 0 CollectionVerlet(dt), 1 CollectionSol(dt, damping, T).

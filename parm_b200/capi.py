@@ -14,6 +14,8 @@ OK, ERR_INVALID, ERR_RUNTIME, ERR_CUDA, ERR_UNSUPPORTED = 0, 1, 2, 3, 4
 X, V, A, F, M, ALL = 1, 2, 4, 8, 16, 31
 RED_MASS, RED_MOMENTUM, RED_KE, RED_COM, RED_NDOF, RED_COMFORCE = range(6)
 PAIR_LJREPULSE, PAIR_REPULSION, PAIR_LJATTRACTREPULSE, PAIR_LJCUT = range(4)
+(PAIR_LJATTRACTCUT, PAIR_LJATTRACTFIXEDREPULSE, PAIR_EISMCLACHLAN, PAIR_LJISH, PAIR_LJATTRACTREPULSESIGS,
+ PAIR_REPULSIONDRAG, PAIR_LOISOHERN, PAIR_LOISLIN, PAIR_LOISOHERNMIN, PAIR_LOISLINMIN) = range(4, 14)
 WANT_ENERGY, WANT_VIRIAL, WANT_STRESS = 1, 2, 4
 
 dp = C.POINTER(C.c_double)
@@ -56,6 +58,7 @@ SIGNATURES = {
     "parm_inter_create": (C.c_int, [vp, vp, C.c_int, vpp]),
     "parm_inter_destroy": (C.c_int, [vp]),
     "parm_inter_set_params": (C.c_int, [vp, dp, u32p, dp, C.c_int, u8p, C.c_int]),
+    "parm_inter_set_params_ex": (C.c_int, [vp, dp, C.c_int, u32p, dp, dp, C.c_int, u8p, C.c_int]),
     "parm_inter_set_forces": (C.c_int, [vp, C.c_uint, dp]),
     "parm_inter_energy": (C.c_int, [vp, dp]),
     "parm_inter_pressure": (C.c_int, [vp, dp]),

@@ -44,17 +44,14 @@ struct BoxDev {
     double L[3], invL[3], halfL[3];
 };
 
-// Per species-pair constants, mixed on the host exactly as the reference's pair
-// constructors do (interaction.hpp:878-883, 1531-1536, 1255-1270, 970-974 + 247-252).
+// Per species-pair constants: the state of one pair functor P after its constructor ran (csrc/pairs.cuh).
 struct PairConst {
-    double eps;      // epsilon_ij (>= 0 after the eps<=0 rule of LJAttractRepulsePair)
-    double sig;      // sigma_ij
-    double sig2;     // sig*sig
-    double inv_sig2; // 1/(sig*sig)
-    double cut2;     // cut_distance^2 in units of sigma (kinds 0: 1, 2, 3)
-    double rc2;      // cutoff in distance units squared: cut2 * sig2 (kind 1: sig2)
-    double cutE;     // cut_energy
-    double expo;     // exponent (kind 1)
+    double eps;  // epsilon_ij (EisMclachlan: c0)
+    double sig;  // sigma_ij (LJAttractRepulseSigs: sig_r; EisMclachlan: cutoff)
+    double sig2; // sig*sig
+    double rc2;  // square of the distance beyond which P::forces and P::energy are exactly zero
+    double cutE; // cut_energy
+    double a, b, c; // functor-specific: exponent, repeps, gamma, C, l, f, c1, c2, eps_a, sig_a, sigcut ...
 };
 
 // Slab decomposition state (one process per GPU; csrc/shard.cu). The slab axis is x (axis 0, the
@@ -185,11 +182,13 @@ struct parm_inter {
     PairConst *d_table;             // nspecies x nspecies
     std::vector<PairConst> h_table;
     // more than PARM_MAX_SPECIES distinct tuples (continuous polydispersity): per-atom parameters are
-    // gathered with the neighbour and mixed per pair on the device
+    // gathered with the neighbour and the pair constructor runs per pair on the device
     bool generic;
-    std::vector<double> h_par_id;   // 4 doubles per AtomVec index: sqrt(eps), sigma, exponent|sigcut, type
-    double4 *d_par_id, *d_par;      // by AtomVec index / by slot
-    double *d_eps_table;            // kind 2: ntypes x ntypes
+    bool minmix;                    // LoisOhernPairMinCLs / LoisLinPairMin constructors
+    std::vector<double> h_par_id;   // 8 doubles per AtomVec index: p0 p1 p2 type | p3 p4 - - (geometric ones as sqrt)
+    double4 *d_par_id, *d_par;      // by AtomVec index / by slot; two double4 per atom: [lo | hi] halves
+    double *d_eps_table;            // ntypes x ntypes or NULL
+    double *d_sig_table;            // ntypes x ntypes or NULL
     int ntypes;
     double *d_partials;
     size_t partial_doubles;

@@ -317,29 +317,106 @@ class NeighborList:
         return mean.value, mx.value
 
 
-class EpsSigAtom:  # interaction.hpp:857-865
+# ---- per-atom parameter structs; .p follows the table in include/parm_b200.h (parm_inter_set_params_ex) ----
+class _PairAtom:
+    type = 0
+
+    def _set(self, a, *p):
+        self.id = a
+        self.p = tuple(p) + (0.0,) * (5 - len(p))
+
+
+class EpsSigAtom(_PairAtom):  # interaction.hpp:857-865
     def __init__(self, a, epsilon, sigma):
-        self.id, self.p = a, (epsilon, sigma, 0.0)
-        self.type = 0
+        self._set(a, epsilon, sigma)
 
 
-class EpsSigExpAtom:  # interaction.hpp:1454-1465
+class EpsSigExpAtom(_PairAtom):  # interaction.hpp:1454-1465
     def __init__(self, a, eps, sigma, exponent):
-        self.id, self.p = a, (eps, sigma, exponent)
-        self.type = 0
+        self._set(a, eps, sigma, exponent)
 
 
-class EpsSigCutAtom:  # interaction.hpp:897-905
+class EpsSigCutAtom(_PairAtom):  # interaction.hpp:897-905
     def __init__(self, a, epsilon, sigma, cut):
-        self.id, self.p = a, (epsilon, sigma, cut)
-        self.type = 0
+        self._set(a, epsilon, sigma, cut)
 
 
-class IEpsSigCutAtom:  # interaction.hpp:989-1018
+class IEpsSigCutAtom(_PairAtom):  # interaction.hpp:989-1018
     def __init__(self, a, epsilons, indx, sigma, cut):
-        self.id, self.p = a, (0.0, sigma, cut)
+        self._set(a, 0.0, sigma, cut)
         self.type = int(indx)
         self.epsilons = list(epsilons)
+
+
+class IEpsISigCutAtom(_PairAtom):  # interaction.hpp:911-960
+    def __init__(self, a, epsilons, sigmas, indx, cut):
+        assert len(epsilons) == len(sigmas)
+        self._set(a, 0.0, 0.0, cut)
+        self.type = int(indx)
+        self.epsilons, self.sigmas = list(epsilons), list(sigmas)
+
+
+class IEpsISigExpAtom(_PairAtom):  # interaction.hpp:1477-1524
+    def __init__(self, a, epsilons, sigmas, indx, exponent=2.5):
+        assert len(epsilons) == len(sigmas)
+        self._set(a, 0.0, 0.0, exponent)
+        self.type = int(indx)
+        self.epsilons, self.sigmas = list(epsilons), list(sigmas)
+
+
+class IEpsRepsSigCutAtom(_PairAtom):  # interaction.hpp:1307-1341
+    def __init__(self, a, epsilons, repeps, sigma, indx, cut):
+        self._set(a, 0.0, sigma, cut, repeps)
+        self.type = int(indx)
+        self.epsilons = list(epsilons)
+
+
+class IEpsRepsSigExpCutAtom(_PairAtom):  # interaction.hpp:1051-1093
+    def __init__(self, a, epsilons, repeps, sigma, n, indx, cut):
+        self._set(a, 0.0, sigma, cut, repeps, n)
+        self.type = int(indx)
+        self.epsilons = list(epsilons)
+
+
+class EisMclachlanAtom(_PairAtom):  # interaction.hpp:1415-1423
+    def __init__(self, a, dist, sigmai):
+        self._set(a, sigmai, dist)
+
+
+class EpsEpsSigSigCutAtom(_PairAtom):  # interaction.hpp:1149-1169
+    def __init__(self, a, eps_r, eps_a, sigma_r, sigma_a, cut):
+        self._set(a, eps_r, sigma_r, cut, eps_a, sigma_a)
+
+
+class EpsSigExpDragAtom(_PairAtom):  # interaction.hpp:1598-1611
+    def __init__(self, a, eps, sigma, gamma, exponent=2.5):
+        self._set(a, eps, sigma, exponent, gamma)
+
+
+class LoisOhernAtom(_PairAtom):  # interaction.hpp:1679-1691
+    def __init__(self, a, eps, sigma, C, l):
+        self._set(a, eps, sigma, C, l)
+
+
+class LoisLinAtom(_PairAtom):  # interaction.hpp:1764-1780
+    def __init__(self, a, eps, sigma, depth, width):
+        self._set(a, eps, sigma, (depth / width) if width > 0 else 0.0, width)
+
+
+def _max_sizes(kind, p, types, sig_table):
+    """A::max_size() per atom (what NListed::add hands to NeighborList::add, interaction.hpp:1906-1910)."""
+    sigma = p[:, 1] if sig_table is None else sig_table.max(axis=1)[types]
+    if kind in (capi.PAIR_LJREPULSE, capi.PAIR_REPULSION, capi.PAIR_REPULSIONDRAG):
+        return sigma
+    if kind == capi.PAIR_EISMCLACHLAN:
+        return p[:, 1]
+    if kind == capi.PAIR_LJATTRACTREPULSESIGS:
+        return p[:, 1] + p[:, 4] * (p[:, 2] - 1)
+    if kind in (capi.PAIR_LOISOHERN, capi.PAIR_LOISOHERNMIN):
+        return p[:, 1] * (1 + p[:, 2] + p[:, 3])
+    if kind in (capi.PAIR_LOISLIN, capi.PAIR_LOISLINMIN):
+        return p[:, 1] * (1 + p[:, 3])
+    return sigma * p[:, 2]
 
 
 class _NListed:
@@ -359,10 +436,11 @@ class _NListed:
         call("parm_inter_create", atoms._h, self.neighbors._h, self.kind, C.byref(h))
         self._h = h
         n = atoms.n
-        self._params = np.zeros((n, 3))
+        self._params = np.zeros((n, 5))
         self._types = np.zeros(n, np.uint32)
         self._member = np.zeros(n, np.uint8)
-        self._eps_rows = {}
+        self._eps_rows, self._sig_rows = {}, {}
+        self._eps_table = self._sig_table = None
         self._dirty = False
 
     def add(self, atm):
@@ -374,34 +452,44 @@ class _NListed:
         self._member[i] = 1
         if hasattr(atm, "epsilons"):
             self._eps_rows[atm.type] = atm.epsilons
+        if hasattr(atm, "sigmas"):
+            self._sig_rows[atm.type] = atm.sigmas
         self._dirty = True
 
-    def add_many(self, params, types=None, eps_table=None, member=None):
-        """Bulk form of add(): params (n,3) as in include/parm_b200.h."""
+    def add_many(self, params, types=None, eps_table=None, member=None, sig_table=None):
+        """Bulk form of add(): params (n, nper <= 5) as in include/parm_b200.h."""
         n = self.atoms.n
-        self._params = np.ascontiguousarray(params, dtype=np.float64).reshape(n, 3)
+        params = np.asarray(params, dtype=np.float64)
+        params = params.reshape(n, params.size // n if n else 5)
+        self._params = np.zeros((n, 5))
+        self._params[:, :params.shape[1]] = params
         self._types = np.zeros(n, np.uint32) if types is None else np.ascontiguousarray(types, dtype=np.uint32)
         self._member = np.ones(n, np.uint8) if member is None else np.ascontiguousarray(member, dtype=np.uint8)
         self._eps_table = None if eps_table is None else np.ascontiguousarray(eps_table, dtype=np.float64)
+        self._sig_table = None if sig_table is None else np.ascontiguousarray(sig_table, dtype=np.float64)
         self._dirty = True
+
+    @staticmethod
+    def _table(tab, rows):
+        if tab is None and rows:
+            nt = max(max(len(r) for r in rows.values()), max(rows) + 1)
+            tab = np.zeros((nt, nt))
+            for t, row in rows.items():
+                tab[t, :len(row)] = row
+        return tab
 
     def _flush(self):
         if not self._dirty:
             return
-        tab = getattr(self, "_eps_table", None)
-        if tab is None and self._eps_rows:
-            nt = max(len(r) for r in self._eps_rows.values())
-            tab = np.zeros((nt, nt))
-            for t, row in self._eps_rows.items():
-                tab[t, :len(row)] = row
+        tab = self._table(self._eps_table, self._eps_rows)
+        stab = self._table(self._sig_table, self._sig_rows)
         nt = 0 if tab is None else tab.shape[0]
-        diam_src = self._params[:, 1] * (1.0 if self.kind in (capi.PAIR_LJREPULSE, capi.PAIR_REPULSION) else self._params[:, 2])
-        diam = np.where(self._member > 0, diam_src, -1.0)
+        diam = np.where(self._member > 0, _max_sizes(self.kind, self._params, self._types, stab), -1.0)
         shared = self.neighbors._diam
         # NListed::add forwards max_size() to the (possibly shared) NeighborList
         newdiam = np.where(self._member > 0, diam, shared)
-        call("parm_inter_set_params", self._h, _dptr(self._params), self._types.ctypes.data_as(u32p), _dptr(tab), nt,
-             self._member.ctypes.data_as(u8p), 0)
+        call("parm_inter_set_params_ex", self._h, _dptr(self._params), 5, self._types.ctypes.data_as(u32p), _dptr(tab),
+             _dptr(stab), nt, self._member.ctypes.data_as(u8p), 0)
         call("parm_nlist_set_diameters", self.neighbors._h, _dptr(np.ascontiguousarray(newdiam)))
         self.neighbors._set_diameters_from_inter(newdiam)
         self._dirty = False
@@ -464,23 +552,88 @@ class _NListed:
         return b.value
 
 
-class LJRepulse(_NListed):
+# the NListed instantiations of sim.i:621-643, under the same names
+class LJRepulse(_NListed):  # NListed<EpsSigAtom, LJRepulsePair>
     kind = capi.PAIR_LJREPULSE
 
 
 LJRepulsive = LJRepulse  # planned rename, src/namereplacements.txt:181
 
 
-class Repulsion(_NListed):
+class Repulsion(_NListed):  # NListed<EpsSigExpAtom, RepulsionPair>
     kind = capi.PAIR_REPULSION
 
 
-class LJAttractRepulse(_NListed):
+class RepulsionII(_NListed):  # NListed<IEpsISigExpAtom, RepulsionPair>
+    kind = capi.PAIR_REPULSION
+
+
+class LJAttractRepulse(_NListed):  # NListed<IEpsSigCutAtom, LJAttractRepulsePair>
     kind = capi.PAIR_LJATTRACTREPULSE
 
 
-class LJCut(_NListed):
+class LJCut(_NListed):  # NListed<EpsSigCutAtom, LennardJonesCutPair>
     kind = capi.PAIR_LJCUT
+
+
+class LJIICut(_NListed):  # NListed<IEpsISigCutAtom, LennardJonesCutPair>
+    kind = capi.PAIR_LJCUT
+
+
+class LJAttractCut(_NListed):  # NListed<EpsSigCutAtom, LJAttractCutPair>
+    kind = capi.PAIR_LJATTRACTCUT
+
+
+class LJAttractICut(_NListed):  # NListed<IEpsSigCutAtom, LJAttractCutPair>
+    kind = capi.PAIR_LJATTRACTCUT
+
+
+class LJAttractIICut(_NListed):  # NListed<IEpsISigCutAtom, LJAttractCutPair>
+    kind = capi.PAIR_LJATTRACTCUT
+
+
+class LJAttractFixedRepulse(_NListed):  # NListed<IEpsRepsSigCutAtom, LJAttractFixedRepulsePair>
+    kind = capi.PAIR_LJATTRACTFIXEDREPULSE
+
+
+class EisMclachlan(_NListed):  # NListed<EisMclachlanAtom, EisMclachlanPair>
+    kind = capi.PAIR_EISMCLACHLAN
+
+
+class LJish(_NListed):  # NListed<IEpsRepsSigExpCutAtom, LJishPair>
+    kind = capi.PAIR_LJISH
+
+
+class LJAttractRepulseSigs(_NListed):  # NListed<EpsEpsSigSigCutAtom, LJAttractRepulseSigsPair>
+    kind = capi.PAIR_LJATTRACTREPULSESIGS
+
+
+class HertzianDrag(_NListed):  # NListed<EpsSigExpDragAtom, RepulsionDragPair>
+    kind = capi.PAIR_REPULSIONDRAG
+
+
+class LoisOhern(_NListed):  # NListed<LoisOhernAtom, LoisOhernPair>
+    kind = capi.PAIR_LOISOHERN
+
+
+class LoisLin(_NListed):  # NListed<LoisLinAtom, LoisLinPair>
+    kind = capi.PAIR_LOISLIN
+
+
+class LoisOhernMin(_NListed):  # NListed<LoisOhernAtom, LoisOhernPairMinCLs>
+    kind = capi.PAIR_LOISOHERNMIN
+
+
+class LoisLinMin(_NListed):  # NListed<LoisLinAtom, LoisLinPairMin>
+    kind = capi.PAIR_LOISLINMIN
+
+
+PAIR_CLASSES = {
+    capi.PAIR_LJREPULSE: LJRepulse, capi.PAIR_REPULSION: Repulsion, capi.PAIR_LJATTRACTREPULSE: LJAttractRepulse,
+    capi.PAIR_LJCUT: LJCut, capi.PAIR_LJATTRACTCUT: LJAttractCut, capi.PAIR_LJATTRACTFIXEDREPULSE: LJAttractFixedRepulse,
+    capi.PAIR_EISMCLACHLAN: EisMclachlan, capi.PAIR_LJISH: LJish, capi.PAIR_LJATTRACTREPULSESIGS: LJAttractRepulseSigs,
+    capi.PAIR_REPULSIONDRAG: HertzianDrag, capi.PAIR_LOISOHERN: LoisOhern, capi.PAIR_LOISLIN: LoisLin,
+    capi.PAIR_LOISOHERNMIN: LoisOhernMin, capi.PAIR_LOISLINMIN: LoisLinMin}
 
 
 class Collection:
@@ -667,10 +820,10 @@ def from_workload(w, device=0, collection=True):
     atoms = AtomVec(w["m"], ndim=ndim, device=device)
     atoms.atoms["x"] = w["x"]
     atoms.atoms["v"] = w["v"]
-    cls = {capi.PAIR_LJREPULSE: LJRepulse, capi.PAIR_REPULSION: Repulsion,
-           capi.PAIR_LJATTRACTREPULSE: LJAttractRepulse, capi.PAIR_LJCUT: LJCut}[w["kind"]]
-    inter = cls(box, atoms, w["skin"])
-    inter.add_many(w["params"], w.get("types"), w.get("eps_table"), w.get("member"))
+    inter = PAIR_CLASSES[w["kind"]](box, atoms, w["skin"])
+    from . import workloads
+    eps_table, sig_table = workloads.tables(w)
+    inter.add_many(w["params"], w.get("types"), eps_table, w.get("member"), sig_table)
     nl = inter.neighbor_list()
     nl.update_list(True)
     collec = None

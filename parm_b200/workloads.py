@@ -12,7 +12,18 @@ gives exactly T.
 import numpy as np
 
 KIND_LJREPULSE, KIND_REPULSION, KIND_LJATTRACTREPULSE, KIND_LJCUT = 0, 1, 2, 3
+(KIND_LJATTRACTCUT, KIND_LJATTRACTFIXEDREPULSE, KIND_EISMCLACHLAN, KIND_LJISH, KIND_LJATTRACTREPULSESIGS,
+ KIND_REPULSIONDRAG, KIND_LOISOHERN, KIND_LOISLIN, KIND_LOISOHERNMIN, KIND_LOISLINMIN) = range(4, 14)
 VERLET, SOL = 0, 1
+
+
+def tables(w):
+    """(eps_table, sig_table) to hand to the interaction: the epsilon table only for the functors whose A struct
+    carries `epsilons` (always for kinds 2, 5, 7; for kinds 1, 3, 4 when variant is "I" or "II"), the sigma table
+    only for the doubly indexed A structs (variant "II": IEpsISigCutAtom / IEpsISigExpAtom)."""
+    variant = str(w.get("variant", ""))
+    indexed = int(w["kind"]) in (KIND_LJATTRACTREPULSE, KIND_LJATTRACTFIXEDREPULSE, KIND_LJISH) or variant in ("I", "II")
+    return (w.get("eps_table") if indexed else None), (w.get("sig_table") if variant == "II" else None)
 
 
 def _velocities(rng, n, ndim, T, m):
@@ -170,3 +181,70 @@ def random_system(n, ndim, kind, seed, rho=0.9, ntypes=2, polydisperse=True, T=1
         tab[0, 2] = tab[2, 0] = 0.0    # eps==0 -> no force, interaction.hpp:1290
     return dict(ndim=ndim, L=L, x=x, v=v, m=m, kind=kind, params=params, types=types, eps_table=tab,
                 skin=skin, dt=0.002, integrator=VERLET, name="random_%d_%dd_k%d" % (n, ndim, kind))
+
+
+FUNCTOR_CASES = [  # (kind, variant): every NListed instantiation of sim.i:621-643 beyond the four hot-path ones
+    (KIND_REPULSION, "II"), (KIND_LJCUT, "II"), (KIND_LJATTRACTCUT, ""), (KIND_LJATTRACTCUT, "I"),
+    (KIND_LJATTRACTCUT, "II"), (KIND_LJATTRACTFIXEDREPULSE, ""), (KIND_EISMCLACHLAN, ""), (KIND_LJISH, ""),
+    (KIND_LJATTRACTREPULSESIGS, ""), (KIND_REPULSIONDRAG, ""), (KIND_LOISOHERN, ""), (KIND_LOISLIN, ""),
+    (KIND_LOISOHERNMIN, ""), (KIND_LOISLINMIN, "")]
+
+
+def functor_system(kind, variant="", ndim=3, n=400, seed=0, continuous=False, T=0.2):
+    """Ragged random system for one NListed functor. params columns follow
+    include/parm_b200.h (parm_inter_set_params_ex). continuous=True gives every atom its own parameter
+    tuple (> 32 species: the per-pair constructor then runs on the device)."""
+    rng = np.random.default_rng(seed)
+    side = int(np.ceil(n ** (1.0 / ndim)))
+    a = 1.12
+    shape = [side] * ndim
+    shape[-1] = side + 1
+    L = np.array(shape, dtype=np.float64) * a
+    sites = _lattice(shape, a)
+    pick = rng.permutation(len(sites))[:n]
+    x = sites[pick] + rng.uniform(-0.13, 0.13, (n, ndim)) * a + 0.5 * a
+    x += rng.integers(-1, 2, (n, ndim)) * L
+    m = rng.uniform(0.5, 2.0, n)
+    v = rng.standard_normal((n, ndim)) * np.sqrt(T / m)[:, None]
+    nt = 3
+    types = rng.integers(0, nt, n).astype(np.uint32)
+
+    def pick2(lo, hi, choices):
+        return rng.uniform(lo, hi, n) if continuous else rng.choice(choices, n)
+
+    sig = pick2(0.9, 1.25, [1.0, 1.2])
+    eps = pick2(0.5, 1.5, [0.6, 1.4])
+    cut = rng.choice([1.8, 2.2], n)
+    p = np.zeros((n, 5))
+    p[:, 0], p[:, 1] = eps, sig
+    tab = np.array([[1.0, -0.5, 0.0], [-0.5, 0.8, 0.3], [0.0, 0.3, 0.6]])
+    stab = np.array([[1.0, 1.1, 1.2], [1.1, 1.25, 0.95], [1.2, 0.95, 1.05]])
+    if kind == KIND_REPULSION:
+        p[:, 2] = rng.choice([2.0, 2.5, 1.5], n)
+        tab = np.abs(tab) + 0.2
+    elif kind in (KIND_LJCUT, KIND_LJATTRACTCUT):
+        p[:, 2] = cut
+        if kind == KIND_LJCUT:
+            stab = stab * 0.82  # full r^-12 core: keep sigma_ij below the lattice spacing or the trajectory is chaotic
+        if kind == KIND_LJATTRACTCUT:
+            tab = np.abs(tab)  # one zero entry: the eps == 0 early-out (interaction.hpp:214, :224)
+    elif kind == KIND_LJATTRACTFIXEDREPULSE:
+        p[:, 2], p[:, 3] = cut, pick2(0.8, 2.0, [1.0, 2.0])
+    elif kind == KIND_EISMCLACHLAN:
+        p[:, 0], p[:, 1] = pick2(-0.3, 0.4, [0.35, -0.2]), pick2(0.95, 1.35, [1.0, 1.3])
+    elif kind == KIND_LJISH:
+        p[:, 2], p[:, 3], p[:, 4] = cut, pick2(0.8, 2.0, [1.0, 2.0]), rng.choice([6.0, 4.0, 5.0], n)
+    elif kind == KIND_LJATTRACTREPULSESIGS:
+        p[:, 2], p[:, 3], p[:, 4] = cut, pick2(0.3, 0.9, [0.4, 0.8]), pick2(0.4, 0.7, [0.5, 0.6])
+    elif kind == KIND_REPULSIONDRAG:
+        p[:, 2], p[:, 3] = rng.choice([2.0, 2.5], n), pick2(0.1, 0.6, [0.2, 0.5])
+    elif kind in (KIND_LOISOHERN, KIND_LOISOHERNMIN):
+        p[:, 2], p[:, 3] = pick2(0.05, 0.25, [0.1, 0.2]), pick2(0.03, 0.15, [0.05, 0.1])
+    elif kind in (KIND_LOISLIN, KIND_LOISLINMIN):
+        width = pick2(0.1, 0.35, [0.2, 0.3])
+        depth = pick2(0.02, 0.08, [0.03, 0.06])
+        p[:, 2], p[:, 3] = depth / width, width
+    w = dict(ndim=ndim, L=L, x=x, v=v, m=m, kind=kind, variant=variant, params=p, types=types, eps_table=tab,
+             sig_table=stab, skin=0.3, dt=0.002, integrator=VERLET,
+             name="functor_k%d%s_%dd%s" % (kind, variant, ndim, "_cont" if continuous else ""))
+    return w

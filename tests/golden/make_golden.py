@@ -23,12 +23,13 @@ from parm_b200 import workloads as W  # noqa: E402
 from parity_util import cpu_system  # noqa: E402
 
 INPUT_KEYS = ("ndim", "L", "x", "v", "m", "kind", "params", "types", "eps_table", "skin", "dt", "integrator")
+OPTIONAL_KEYS = ("damping", "T", "variant", "sig_table")
 
 
 def record(w, steps=40, noise=None):
     s = cpu_system("ref", w, collection=True)
     out = {k: np.asarray(w[k]) for k in INPUT_KEYS}
-    for k in ("damping", "T"):
+    for k in OPTIONAL_KEYS:
         if k in w:
             out[k] = np.asarray(w[k])
     a, b = s.pairs()
@@ -37,6 +38,7 @@ def record(w, steps=40, noise=None):
     out["forces"], out["virial"] = f, np.asarray(p)
     out["energy"] = np.asarray(s.inter_energy())
     out["stress"] = s.inter_stress()
+    out["contacts"] = np.asarray(s.inter_contacts(), dtype=np.uint64)
     s.set_forces(True)
     if noise is not None:
         s.inject_noise(noise)
@@ -72,6 +74,11 @@ def main():
     nm = int((w["m"] > 0).sum())
     z = np.random.default_rng(5).standard_normal((steps, nm, 2, 2))
     cases["sol_harmonic2d"] = record(w, steps=steps, noise=z)
+    # the remaining NListed functors of sim.i:621-643
+    for k, (kind, variant) in enumerate(W.FUNCTOR_CASES):
+        ndim = 2 if k % 4 == 3 else 3
+        w = W.functor_system(kind, variant, ndim=ndim, n=90 if ndim == 3 else 70, seed=500 + k)
+        cases["functor_k%d%s_%dd" % (kind, variant, ndim)] = record(w, steps=30)
     for name, d in cases.items():
         np.savez_compressed(os.path.join(HERE, name + ".npz"), **d)
         print(name, "pairs", len(d["pairs_first"]), "E", float(d["energy"]), "which_end", int(d["which_end"]))

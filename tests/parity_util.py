@@ -15,8 +15,10 @@ def backends(cpu):
 def cpu_system(backend, w, injected=False, collection=True):
     """Oracle twin of parm_b200.sim.from_workload (same call order as LJatoms.cpp:30-83)."""
     s = CpuSystem(backend, w["L"], w["x"], w["v"], w["m"])
-    s.add_interaction(w["kind"], w["skin"], w["params"], w.get("types"), w.get("eps_table"), w.get("member"),
-                      injected=injected)
+    from parm_b200.workloads import tables
+    eps_table, sig_table = tables(w)
+    s.add_interaction(w["kind"], w["skin"], w["params"], w.get("types"), eps_table, w.get("member"),
+                      injected=injected, sig_table=sig_table)
     s.update_list(True)
     if collection:
         if w.get("integrator", 0) == 0:

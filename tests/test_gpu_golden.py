@@ -25,6 +25,8 @@ def test_gpu_reproduces_reference_fixture(path):
     assert rel_err(p, d["virial"]) < 1e-10
     assert rel_err(inter.energy(box), d["energy"]) < 1e-10
     assert rel_err(inter.stress(box), d["stress"]) < 1e-10
+    if "contacts" in d:
+        assert (inter.contacts(box), inter.overlaps(box)) == tuple(int(q) for q in d["contacts"])
     collec.set_forces(True)
     if "noise" in d:
         collec.inject_noise(d["noise"])

@@ -1,0 +1,89 @@
+"""every NListed functor of sim.i:621-643 on the GPU against the oracle (the compiled reference when
+present, else its C restatement): pair set bit-exact, forces / energy / virial / stress to 1e-10, contact and
+overlap counts exact, and a short NVE trajectory -- with tabulated species and with per-atom continuous
+parameters (pair constructor on the device), in 3-D and 2-D."""
+import numpy as np
+import pytest
+
+from parm_b200 import workloads as W
+from parity_util import backends, cpu_system, rel_err, rel_err_vec
+
+pytestmark = pytest.mark.gpu
+IDS = ["k%d%s" % c for c in W.FUNCTOR_CASES]
+
+
+def check_static(w, be):
+    from parm_b200 import sim
+    box, atoms, inter, nl, collec = sim.from_workload(w)
+    s = cpu_system(be, w, injected=True)
+    a, b = nl.pairs()
+    ra, rb = s.pairs()
+    assert len(ra) > 0 and np.array_equal(a, ra) and np.array_equal(b, rb)
+    atoms.reset_forces()
+    p = inter.set_forces_get_pressure(box)
+    f_ref, p_ref = s.forces_and_pressure()
+    assert np.abs(f_ref).max() > 0
+    assert rel_err_vec(atoms.peek("f"), f_ref) < 1e-10
+    assert rel_err(p, p_ref) < 1e-10
+    assert rel_err(inter.energy(box), s.inter_energy()) < 1e-10
+    assert rel_err(inter.pressure(box), s.inter_pressure()) < 1e-10
+    assert rel_err(inter.stress(box), s.inter_stress()) < 1e-10
+    atoms.reset_forces()
+    st = inter.set_forces_get_stress(box)
+    assert rel_err(st, s.inter_stress()) < 1e-10
+    assert rel_err_vec(atoms.peek("f"), f_ref) < 1e-10
+    assert (inter.contacts(box), inter.overlaps(box)) == s.inter_contacts()
+    return box, atoms, inter, nl, collec, s
+
+
+@pytest.mark.parametrize("kind,variant", W.FUNCTOR_CASES, ids=IDS)
+def test_functor_matches_oracle_3d(oracle_built, kind, variant):
+    w = W.functor_system(kind, variant, ndim=3, n=3000, seed=40 + kind)
+    for be in backends(oracle_built)[-1:]:
+        box, atoms, inter, nl, collec, s = check_static(w, be)
+        collec.set_forces(True)
+        s.set_forces(True)
+        collec.timestep(150)
+        s.timestep(150)
+        x, v, a, f = s.get_atoms()
+        assert nl.which() == s.which()
+        assert rel_err_vec(atoms.peek("x") - w["x"], x - w["x"]) < 1e-8
+        assert rel_err_vec(atoms.peek("v"), v) < 1e-8
+        assert rel_err(collec.energy(), s.energy()) < 1e-9
+        assert rel_err(collec.pressure(), s.pressure()) < 1e-8
+
+
+@pytest.mark.parametrize("kind,variant", W.FUNCTOR_CASES, ids=IDS)
+def test_functor_continuous_parameters_2d(oracle_built, kind, variant):
+    """> 32 distinct parameter tuples: the pair constructor runs per pair on the device (pairs.cuh mix_pair)."""
+    w = W.functor_system(kind, variant, ndim=2, n=2500, seed=70 + kind, continuous=True)
+    for be in backends(oracle_built)[-1:]:
+        box, atoms, inter, nl, collec, s = check_static(w, be)
+        collec.set_forces(True)
+        s.set_forces(True)
+        collec.timestep(60)
+        s.timestep(60)
+        x, v, a, f = s.get_atoms()
+        assert rel_err_vec(atoms.peek("x") - w["x"], x - w["x"]) < 1e-8
+        assert rel_err(collec.energy(), s.energy()) < 1e-9
+
+
+def test_unknown_functor_and_bad_tables_fail_loudly():
+    from parm_b200 import capi, sim
+    w = W.functor_system(W.KIND_LJISH, n=64, seed=1)
+    box = sim.OriginBox(w["L"], 3)
+    atoms = sim.AtomVec(w["m"], ndim=3)
+    nl = sim.NeighborList(box, atoms, 0.3)
+    import ctypes as C
+    h = C.c_void_p()
+    with pytest.raises(Exception):
+        capi.call("parm_inter_create", atoms._h, nl._h, 99, C.byref(h))
+    inter = sim.LJish(atoms, nl)
+    inter.add_many(w["params"], w["types"], None)  # LJishPair needs the epsilon table
+    with pytest.raises(Exception):
+        inter.energy(box)
+    bad = w["eps_table"].copy()
+    bad[0, 1] += 1.0  # asymmetric
+    inter.add_many(w["params"], w["types"], bad)
+    with pytest.raises(Exception):
+        inter.energy(box)

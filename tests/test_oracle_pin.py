@@ -31,6 +31,10 @@ def load(path):
     for k in ("damping", "T"):
         if k in d:
             w[k] = float(d[k])
+    if "variant" in d:
+        w["variant"] = str(d["variant"])
+    if "sig_table" in d:
+        w["sig_table"] = d["sig_table"]
     return w, d
 
 
@@ -42,6 +46,7 @@ def replay(backend, w, d):
     out["forces"], out["virial"] = f, np.asarray(p)
     out["energy"] = np.asarray(s.inter_energy())
     out["stress"] = s.inter_stress()
+    out["contacts"] = np.asarray(s.inter_contacts(), dtype=np.uint64)
     s.set_forces(True)
     if "noise" in d:
         s.inject_noise(d["noise"])
@@ -85,6 +90,32 @@ def test_port_equals_reference_fresh_inputs(oracle_built):
     for a, b in zip(r.get_atoms(), p.get_atoms()):
         assert np.array_equal(a, b)
     assert r.which() == p.which() and r.energy() == p.energy() and r.pressure() == p.pressure()
+
+
+@pytest.mark.parametrize("kind,variant", W.FUNCTOR_CASES, ids=["k%d%s" % c for c in W.FUNCTOR_CASES])
+def test_port_equals_reference_all_functors(oracle_built, kind, variant):
+    """the C restatement of every NListed functor is bit-equal to the compiled reference, with
+    discrete species and with per-atom continuous parameters, in 2-D and 3-D."""
+    if "ref" not in backends(oracle_built):
+        pytest.skip("compiled reference not present")
+    for ndim, cont in ((3, False), (2, True)):
+        w = W.functor_system(kind, variant, ndim=ndim, n=150, seed=900 + kind, continuous=cont)
+        r, p = cpu_system("ref", w), cpu_system("port", w)
+        assert len(r.pairs()[0]) > 200
+        for s in (r, p):
+            s.set_forces(True)
+        fr, pr = r.forces_and_pressure()
+        fp, pp = p.forces_and_pressure()
+        assert np.abs(fr).max() > 0 and np.array_equal(fr, fp) and pr == pp
+        assert r.inter_energy() == p.inter_energy() and r.inter_energy() != 0
+        assert np.array_equal(r.inter_stress(), p.inter_stress())
+        assert r.inter_contacts() == p.inter_contacts() and r.inter_contacts()[0] > 0
+        for s in (r, p):
+            s.set_forces(True)
+            s.timestep(50)
+        for a, b in zip(r.get_atoms(), p.get_atoms()):
+            assert np.array_equal(a, b)
+        assert r.energy() == p.energy()
 
 
 def test_box_diff_is_ieee_remainder(oracle_built):
