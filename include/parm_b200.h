@@ -107,6 +107,10 @@ int parm_nlist_set_diameters(parm_nlist *nl, const double *diam);
 /* NeighborList::update_list(force) trackers.cpp:19-85: drift rule then pair build. */
 int parm_nlist_update(parm_nlist *nl, int force, int *rebuilt);
 int parm_nlist_which(parm_nlist *nl, uint32_t *updatenum);  /* which() */
+/* ignore(AtomID a, AtomID b) for npairs pairs of AtomVec indices (trackers.hpp:190-193): the pair never enters
+ * the list (trackers.cpp:64); sets ignorechanged, so the next update_list() rebuilds. ignore_size(): :204 */
+int parm_nlist_ignore(parm_nlist *nl, const uint32_t *a, const uint32_t *b, uint64_t npairs);
+int parm_nlist_ignore_size(parm_nlist *nl, uint64_t *n);
 int parm_nlist_numpairs(parm_nlist *nl, uint64_t *npairs);  /* numpairs() */
 /* curpairs in the reference's order (trackers.cpp:59-68): first = later atom i,
  * last = earlier atom j < i, sorted by (i, j).  cap = capacity of both arrays. */

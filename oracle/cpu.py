@@ -86,6 +86,8 @@ def _load(backend, ndim):
     api["make_collection"] = sig("make_collection", C.c_int, [vp, C.c_int, C.c_double, C.c_double, C.c_double])
     api["update_list"] = sig("update_list", C.c_int, [vp, C.c_int, C.c_int])
     api["which"] = sig("which", C.c_uint32, [vp, C.c_int])
+    api["ignore"] = sig("ignore", None, [vp, C.c_int, _u32p, _u32p, C.c_uint64])
+    api["ignore_size"] = sig("ignore_size", C.c_uint32, [vp, C.c_int])
     api["numpairs"] = sig("numpairs", C.c_uint32, [vp, C.c_int])
     api["get_pairs"] = sig("get_pairs", None, [vp, C.c_int, _u32p, _u32p])
     api["set_atoms"] = sig("set_atoms", None, [vp, _dp, _dp, _dp, _dp])
@@ -175,6 +177,15 @@ class CpuSystem:
 
     def which(self, nl=0):
         return self.api["which"](self.h, nl)
+
+    def ignore(self, a, b, nl=0):
+        """NeighborList::ignore for equal-length arrays of AtomVec indices (trackers.hpp:190-193)."""
+        a = np.ascontiguousarray(np.atleast_1d(a), dtype=np.uint32)
+        b = np.ascontiguousarray(np.atleast_1d(b), dtype=np.uint32)
+        self.api["ignore"](self.h, nl, a.ctypes.data_as(_u32p), b.ctypes.data_as(_u32p), a.size)
+
+    def ignore_size(self, nl=0):
+        return self.api["ignore_size"](self.h, nl)
 
     def pairs(self, nl=0):
         """Pairs in the reference's own order: (first, last) = (later atom i, earlier atom j<i)."""

@@ -54,6 +54,8 @@ typedef struct {
     uint32_t updatenum;
     int ignorechanged;
     int injected;
+    uint64_t *ignored; /* PairList ignorepairs: sorted keys (larger index << 32 | smaller index), trackers.hpp:41-128 */
+    size_t nignored;
 } NList;
 
 typedef struct {
@@ -115,7 +117,7 @@ void port_sys_destroy(void *h) {
     }
     for (int k = 0; k < s->nnls; k++) {
         NList *l = &s->nls[k];
-        free(l->member); free(l->ids); free(l->diam); free(l->lastlocs); free(l->first); free(l->last);
+        free(l->member); free(l->ids); free(l->diam); free(l->lastlocs); free(l->first); free(l->last); free(l->ignored);
     }
     free(s->inters); free(s->nls);
     free(s->x); free(s->v); free(s->a); free(s->f); free(s->m);
@@ -220,7 +222,19 @@ static int cmp_u32(const void *a, const void *b) {
 }
 
 /* predicate of trackers.cpp:65-66 on SubGroup slots i, j */
+static int cmp_u64(const void *a, const void *b) {
+    uint64_t x = *(const uint64_t *)a, y = *(const uint64_t *)b;
+    return x < y ? -1 : x > y;
+}
+/* PairList::has_pair, trackers.hpp:66-71 */
+static int nl_ignored(const NList *l, uint32_t a, uint32_t b) {
+    if (!l->nignored) return 0;
+    uint64_t key = a > b ? ((uint64_t)a << 32 | b) : ((uint64_t)b << 32 | a);
+    return bsearch(&key, l->ignored, l->nignored, 8, cmp_u64) != NULL;
+}
+
 static inline int nl_pred(const Sys *s, const NList *l, uint32_t i, uint32_t j) {
+    if (nl_ignored(l, l->ids[i], l->ids[j])) return 0; /* trackers.cpp:64 */
     double d[3] = {0, 0, 0};
     double diam = (l->diam[i] + l->diam[j]) / 2;
     box_diff(s, s->x + (size_t)l->ids[i] * s->D, s->x + (size_t)l->ids[j] * s->D, d);
@@ -935,6 +949,22 @@ void port_timestep(void *h, int nsteps) {
 }
 
 int port_update_list(void *h, int nl, int force) { Sys *s = (Sys *)h; return nl_update_list(s, &s->nls[nl], force); }
+/* NeighborList::ignore, trackers.hpp:190-193 (PairList::add_pair :76-83: a set, duplicates collapse) */
+void port_ignore(void *h, int nl, const uint32_t *a, const uint32_t *b, uint64_t npairs) {
+    NList *l = &((Sys *)h)->nls[nl];
+    l->ignored = (uint64_t *)realloc(l->ignored, (l->nignored + npairs + 1) * 8);
+    for (uint64_t k = 0; k < npairs; k++) {
+        uint64_t key = a[k] > b[k] ? ((uint64_t)a[k] << 32 | b[k]) : ((uint64_t)b[k] << 32 | a[k]);
+        l->ignored[l->nignored++] = key;
+    }
+    qsort(l->ignored, l->nignored, 8, cmp_u64);
+    size_t w = 0;
+    for (size_t k = 0; k < l->nignored; k++)
+        if (w == 0 || l->ignored[w - 1] != l->ignored[k]) l->ignored[w++] = l->ignored[k];
+    l->nignored = w;
+    l->ignorechanged = 1;
+}
+uint32_t port_ignore_size(void *h, int nl) { return (uint32_t)((Sys *)h)->nls[nl].nignored; }
 uint32_t port_which(void *h, int nl) { return ((Sys *)h)->nls[nl].updatenum; }
 uint32_t port_numpairs(void *h, int nl) { return (uint32_t)((Sys *)h)->nls[nl].npairs; }
 void port_get_pairs(void *h, int nl, uint32_t *first, uint32_t *last) {

@@ -102,6 +102,7 @@ class InjectedNeighborList : public NeighborList {
                 lastlocs[i] = a1->x;
                 for (uint j = 0; j < i; j++) {
                     AtomID a2 = atoms.get_id(j);
+                    if (ignorepairs.has_pair(a1, a2)) continue;
                     flt diam = (diameters[i] + diameters[j]) / 2;
                     if (box->diff(a1->x, a2->x).norm() < (diam + skin)) curpairs.push_back(IDPair(a1, a2));
                 }
@@ -132,6 +133,7 @@ class InjectedNeighborList : public NeighborList {
             for (uint i = 0; i < N; i++) cellatoms[fill[cellof[i]]++] = i;  // ascending i inside a cell
         }
         vector<uint> js;
+        const bool has_ignored = ignorepairs.size() > 0;  // has_pair() inserts map nodes: skip it when nothing is ignored
         int nst = 1;
         for (uint d = 0; d < NDIM; d++) nst *= 3;
         for (uint i = 0; i < N; i++) {
@@ -150,6 +152,7 @@ class InjectedNeighborList : public NeighborList {
                     uint j = cellatoms[q];
                     if (j >= i) break;  // ascending within a cell
                     AtomID a2 = atoms.get_id(j);
+                    if (has_ignored && ignorepairs.has_pair(a1, a2)) continue;
                     flt diam = (diameters[i] + diameters[j]) / 2;
                     if (box->diff(a1->x, a2->x).norm() < (diam + skin)) js.push_back(j);
                 }
@@ -376,6 +379,12 @@ int ref_make_collection(void *h, int integrator, double dt, double damping, doub
 const char *ref_last_error(void *h) { return static_cast<Sys *>(h)->err.c_str(); }
 
 int ref_update_list(void *h, int nl, int force) { return static_cast<Sys *>(h)->nls[nl]->update_list_cells(force != 0) ? 1 : 0; }
+// NeighborList::ignore(AtomID, AtomID), trackers.hpp:190-193
+void ref_ignore(void *h, int nl, const uint32_t *a, const uint32_t *b, uint64_t npairs) {
+    Sys *s = static_cast<Sys *>(h);
+    for (uint64_t k = 0; k < npairs; k++) s->nls[nl]->ignore(s->atoms->get_id(a[k]), s->atoms->get_id(b[k]));
+}
+uint32_t ref_ignore_size(void *h, int nl) { return static_cast<Sys *>(h)->nls[nl]->ignore_size(); }
 uint32_t ref_which(void *h, int nl) { return static_cast<Sys *>(h)->nls[nl]->which(); }
 uint32_t ref_numpairs(void *h, int nl) { return static_cast<Sys *>(h)->nls[nl]->numpairs(); }
 // pairs in the reference's own order; first() is the later atom (trackers.cpp:59-68)

@@ -10,7 +10,9 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <set>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "../../include/parm_b200.h"
@@ -143,6 +145,11 @@ struct parm_nlist {
     int cell_sub;        // cells per r_list (1 or 2)
     uint32_t updatenum;
     bool ignorechanged;
+    // NeighborList::ignore (trackers.hpp:190-193): excluded pairs, canonical (larger index, smaller index)
+    std::set<std::pair<uint32_t, uint32_t> > ignored;
+    bool ignore_dirty;           // the device CSR is older than `ignored`
+    uint32_t *d_excl_start;      // by AtomVec index, nid + 1 entries
+    uint32_t *d_excl;            // both directions: the excluded partners of each atom
     // cell grid
     int nc[3];
     GridDev g;

@@ -684,6 +684,8 @@ extern "C" int parm_nlist_destroy(parm_nlist *nl) {
                     nl->cell_start, nl->cell_fill, nl->scan_sums, nl->sort_tmp, nl->nbr, nl->cnt, nl->d_top2, nl->d_counter, nl->d_flags, nl->d_slot};
     for (void *p : ptrs)
         if (p) cudaFree(p);
+    if (nl->d_excl_start) cudaFree(nl->d_excl_start);
+    if (nl->d_excl) cudaFree(nl->d_excl);
     if (nl->h_flags) cudaFreeHost(nl->h_flags);
     if (nl->h_slot) cudaFreeHost(nl->h_slot);
     c->nlists.erase(std::remove(c->nlists.begin(), c->nlists.end(), nl), c->nlists.end());
@@ -880,6 +882,71 @@ int parm_nlist_append_ghosts(parm_nlist *nl, uint32_t first, uint32_t count) {
     return 0;
 }
 
+// NeighborList::ignore (trackers.cpp:64 `if (ignorepairs.has_pair(a1, a2)) continue;`): excluded pairs are
+// removed from the finished rows. One warp per slot whose atom has exclusions; the row is compacted in place
+// (stable), 32 entries at a time.
+__global__ void k_apply_ignore(const uint32_t *__restrict__ order, const uint32_t *__restrict__ excl_start,
+                               const uint32_t *__restrict__ excl, uint32_t nown, uint32_t kmax, uint32_t *nbr, uint32_t *cnt,
+                               NlistFlags *flags) {
+    const uint32_t s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t lane = threadIdx.x & 31;
+    if (s >= nown) return;
+    const uint32_t id = order[s];
+    const uint32_t e0 = excl_start[id], e1 = excl_start[id + 1];
+    if (e0 == e1) return;
+    const uint32_t my = min(cnt[s], kmax);
+    uint32_t *row = nbr + (size_t)s * kmax;
+    uint32_t kept = 0;
+    for (uint32_t k0 = 0; k0 < my; k0 += 32) {
+        const uint32_t k = k0 + lane;
+        const bool valid = k < my;
+        const uint32_t j = valid ? row[k] : 0;
+        bool keep = valid;
+        if (valid) {
+            const uint32_t jid = order[j];
+            for (uint32_t e = e0; e < e1; e++) keep = keep && excl[e] != jid;
+        }
+        const uint32_t m = __ballot_sync(0xffffffffu, keep);
+        __syncwarp();
+        if (keep) row[kept + __popc(m & ((1u << lane) - 1))] = j;
+        kept += __popc(m);
+        __syncwarp();
+    }
+    if (lane == 0 && kept != my) {
+        cnt[s] = kept;
+        atomicAdd(&flags->total, (unsigned long long)0 - (unsigned long long)(my - kept));
+    }
+}
+
+static int apply_ignore(parm_nlist *nl) {
+    parm_ctx *c = nl->ctx;
+    if (nl->ignored.empty()) return 0;
+    if (nl->ignore_dirty) { // CSR by AtomVec index, both directions
+        std::vector<uint32_t> start(c->nid + 1, 0), list(2 * nl->ignored.size());
+        for (const auto &pr : nl->ignored) { start[pr.first + 1]++; start[pr.second + 1]++; }
+        for (uint32_t i = 0; i < c->nid; i++) start[i + 1] += start[i];
+        std::vector<uint32_t> fill(start.begin(), start.end() - 1);
+        for (const auto &pr : nl->ignored) { list[fill[pr.first]++] = pr.second; list[fill[pr.second]++] = pr.first; }
+        if (nl->d_excl) cudaFree(nl->d_excl);
+        nl->d_excl = 0;
+        if (!nl->d_excl_start) CK(cudaMalloc(&nl->d_excl_start, ((size_t)c->nid + 1) * 4));
+        CK(cudaMalloc(&nl->d_excl, list.size() * 4));
+        CK(cudaMemcpyAsync(nl->d_excl_start, start.data(), start.size() * 4, cudaMemcpyHostToDevice, c->stream));
+        CK(cudaMemcpyAsync(nl->d_excl, list.data(), list.size() * 4, cudaMemcpyHostToDevice, c->stream));
+        CK(cudaStreamSynchronize(c->stream)); // the host vectors go out of scope
+        nl->ignore_dirty = false;
+    }
+    const uint32_t nown = parm_owned(c);
+    if (!nown) return 0;
+    k_apply_ignore<<<(unsigned)(((size_t)nown * 32 + 255) / 256), 256, 0, c->stream>>>(c->order, nl->d_excl_start, nl->d_excl, nown,
+                                                                                      nl->kmax, nl->nbr, nl->cnt, nl->d_flags);
+    CK_LAUNCH(c);
+    CK(cudaMemcpyAsync(nl->h_flags, nl->d_flags, sizeof(NlistFlags), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    nl->total_full = nl->h_flags->total;
+    return 0;
+}
+
 // Build the rows for the atoms now in slots 0..n-1, growing the per-atom capacity if a row overflowed.
 int parm_nlist_build_rows(parm_nlist *nl) {
     parm_ctx *c = nl->ctx;
@@ -945,7 +1012,7 @@ int parm_nlist_build_rows(parm_nlist *nl) {
         CK(cudaStreamSynchronize(c->stream));
         nl->total_full = nl->h_flags->total;
         nl->maxcnt = nl->h_flags->maxcnt;
-        if (nl->maxcnt <= nl->kmax) return 0;
+        if (nl->maxcnt <= nl->kmax) return apply_ignore(nl);
         uint32_t k2 = nl->maxcnt + nl->maxcnt / 8 + 8;
         PTRY(alloc_nbr(nl, k2));
     }
@@ -1001,6 +1068,24 @@ extern "C" int parm_nlist_update(parm_nlist *nl, int force, int *rebuilt) {
 }
 
 extern "C" int parm_nlist_which(parm_nlist *nl, uint32_t *u) { *u = nl->updatenum; return 0; }
+
+extern "C" int parm_nlist_ignore(parm_nlist *nl, const uint32_t *a, const uint32_t *b, uint64_t npairs) {
+    if (!nl || (npairs && (!a || !b))) { parm_set_error("parm_nlist_ignore: NULL argument"); return PARM_ERR_INVALID; }
+    parm_ctx *c = nl->ctx;
+    for (uint64_t k = 0; k < npairs; k++) {
+        if (a[k] >= c->nid || b[k] >= c->nid) { parm_set_error("parm_nlist_ignore: atom index out of range"); return PARM_ERR_INVALID; }
+        if (a[k] == b[k]) continue; // an atom never pairs with itself
+        nl->ignored.insert(std::make_pair(std::max(a[k], b[k]), std::min(a[k], b[k])));
+    }
+    nl->ignore_dirty = true;
+    nl->ignorechanged = true; // trackers.hpp:192
+    return 0;
+}
+extern "C" int parm_nlist_ignore_size(parm_nlist *nl, uint64_t *n) {
+    if (!nl || !n) { parm_set_error("parm_nlist_ignore_size: NULL argument"); return PARM_ERR_INVALID; }
+    *n = nl->ignored.size();
+    return 0;
+}
 
 // Host copy of the pair list in the reference's order (trackers.cpp:59-68): first = later atom i,
 // last = earlier atom j < i, sorted by (i, j). Sharded contexts return the pairs whose `first`

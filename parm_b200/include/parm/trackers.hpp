@@ -78,8 +78,9 @@ class NeighborList : public StateTracker {
         parm_b200::check(parm_nlist_numpairs(nl, &np));
         return (uint)np;
     }
-    inline void ignore(AtomID, AtomID) {
-        throw std::runtime_error("parm_b200: NeighborList::ignore is outside the hot-path scope (DESIGN.md, next)");
+    inline void ignore(AtomID a, AtomID b) {  // trackers.hpp:190-193
+        uint32_t ia = a.n(), ib = b.n();
+        parm_b200::check(parm_nlist_ignore(nl, &ia, &ib, 1));
     }
     void add(AtomID a, flt diameter) {
         if (a.n() >= diameters.size()) throw std::invalid_argument("NeighborList::add: AtomID is not from this AtomVec");
@@ -88,7 +89,11 @@ class NeighborList : public StateTracker {
         diameters[a.n()] = diameter;
         diam_dirty = true;
     }
-    inline uint ignore_size() const { return 0; }
+    inline uint ignore_size() const {
+        uint64_t k = 0;
+        parm_b200::check(parm_nlist_ignore_size(nl, &k));
+        return (uint)k;
+    }
     inline uint size() const {
         uint k = 0;
         for (size_t i = 0; i < diameters.size(); i++) k += diameters[i] >= 0;

@@ -297,6 +297,19 @@ class NeighborList:
     def size(self):
         return int((self._diam >= 0).sum())
 
+    def ignore(self, a, b):
+        """ignore(AtomID a, AtomID b) (trackers.hpp:190-193); a and b may also be equal-length index arrays."""
+        ia = np.atleast_1d(np.asarray([q.n() if hasattr(q, "n") else q for q in np.atleast_1d(a)], dtype=np.uint32))
+        ib = np.atleast_1d(np.asarray([q.n() if hasattr(q, "n") else q for q in np.atleast_1d(b)], dtype=np.uint32))
+        if ia.shape != ib.shape:
+            raise ValueError("ignore: a and b must have the same length")
+        call("parm_nlist_ignore", self._h, ia.ctypes.data_as(u32p), ib.ctypes.data_as(u32p), ia.size)
+
+    def ignore_size(self):
+        u = C.c_uint64(0)
+        call("parm_nlist_ignore_size", self._h, C.byref(u))
+        return u.value
+
     def pairs(self):
         """curpairs as two uint32 arrays (first, last) in the reference's order (trackers.cpp:59-68)."""
         n = self.numpairs()

@@ -66,6 +66,41 @@ def test_facade_program_matches_oracle(oracle_built, tmp_path, case):
     assert rel_err_vec(f, cf) < 1e-8
 
 
+@pytest.mark.parametrize("kind,variant", W.FUNCTOR_CASES, ids=["k%d%s" % c for c in W.FUNCTOR_CASES])
+def test_facade_every_functor_instantiation(oracle_built, tmp_path, kind, variant):
+    """examples/facade_functors.cpp builds each NListed<A,P> of sim.i:621-643 from the reference's own per-atom
+    structs through the C++ facade; energy, virial, stress, contacts, overlaps and forces against the oracle."""
+    import __graft_entry__ as g
+    g.build()
+    nd = 2 if kind % 3 == 0 else 3
+    w = W.functor_system(kind, variant, ndim=nd, n=700, seed=300 + kind)
+    n = w["x"].shape[0]
+    fin, fout = str(tmp_path / "in.bin"), str(tmp_path / "out.bin")
+    with open(fin, "wb") as fh:
+        fh.write(struct.pack("4i", n, int(kind), {"": 0, "I": 1, "II": 2}[variant], w["eps_table"].shape[0]))
+        fh.write(np.asarray(w["L"], np.float64).tobytes())
+        fh.write(struct.pack("d", w["skin"]))
+        for k in ("x", "v", "m", "params"):
+            fh.write(np.ascontiguousarray(w[k], np.float64).tobytes())
+        fh.write(np.ascontiguousarray(w["types"], np.uint32).tobytes())
+        fh.write(np.ascontiguousarray(w["eps_table"], np.float64).tobytes())
+        fh.write(np.ascontiguousarray(w["sig_table"], np.float64).tobytes())
+    r = subprocess.run([os.path.join(BIN, "facade_functors%dd" % nd), fin, fout], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    raw = open(fout, "rb").read()
+    o = 16 + 8 * nd * nd
+    E, vir = np.frombuffer(raw[:16], np.float64)
+    st = np.frombuffer(raw[16:o], np.float64).reshape(nd, nd)
+    contacts, overlaps, npairs = (int(q) for q in np.frombuffer(raw[o:o + 24], np.uint64))
+    f = np.frombuffer(raw[o + 24:], np.float64).reshape(n, nd)
+    c = cpu_system("port", w, collection=False)
+    assert npairs == len(c.pairs()[0]) > 0
+    f_ref, p_ref = c.forces_and_pressure()
+    assert rel_err_vec(f, f_ref) < 1e-10 and rel_err(vir, p_ref) < 1e-10
+    assert rel_err(E, c.inter_energy()) < 1e-10 and rel_err(st, c.inter_stress()) < 1e-10
+    assert (contacts, overlaps) == c.inter_contacts()
+
+
 def test_unmodified_ljatoms_runs_on_the_dropin(tmp_path):
     """src/bin/LJatoms.cpp compiled, unmodified, against parm_b200/include/parm (examples/Makefile `ref`).
     It is a 5e5-step NVE run of 400 LJ atoms with random insertion; we let it run for a bounded time and

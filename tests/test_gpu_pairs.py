@@ -87,3 +87,41 @@ def test_unknown_functor_and_bad_tables_fail_loudly():
     inter.add_many(w["params"], w["types"], bad)
     with pytest.raises(Exception):
         inter.energy(box)
+
+
+@pytest.mark.parametrize("ndim", [3, 2])
+def test_neighborlist_ignore(oracle_built, ndim):
+    """NeighborList::ignore (trackers.hpp:190-193): pair set bit-exact against the oracle with bonded-style
+    exclusions, the rebuild it forces, and the trajectory that follows."""
+    from parm_b200 import sim
+    from test_oracle_pin import chain_ignores
+    n = 4000
+    w = W.random_system(n, ndim, 2, seed=21 + ndim, ntypes=2)
+    a, b = chain_ignores(n, np.random.default_rng(3))
+    box, atoms, inter, nl, collec = sim.from_workload(w)
+    s = cpu_system(backends(oracle_built)[-1], w, injected=True)
+    n0 = nl.numpairs()
+    w0 = nl.which()
+    nl.ignore(a, b)
+    s.ignore(a, b)
+    assert nl.ignore_size() == s.ignore_size() > 0
+    assert nl.update_list(False) and s.update_list(False)  # ignorechanged forces the rebuild (trackers.cpp:23)
+    collec.set_forces(True)
+    s.set_forces(True)
+    assert nl.which() == w0 + 1 == s.which()
+    pa, pb = nl.pairs()
+    ra, rb = s.pairs()
+    assert 0 < len(ra) < n0 and np.array_equal(pa, ra) and np.array_equal(pb, rb)
+    assert rel_err_vec(atoms.peek("f"), s.get_atoms()[3]) < 1e-10
+    assert rel_err(inter.energy(box), s.inter_energy()) < 1e-10
+    collec.timestep(120)
+    s.timestep(120)
+    assert nl.which() == s.which() > w0 + 1
+    pa, pb = nl.pairs()
+    ra, rb = s.pairs()
+    assert np.array_equal(pa, ra) and np.array_equal(pb, rb)
+    assert rel_err_vec(atoms.peek("x") - w["x"], s.get_atoms()[0] - w["x"]) < 1e-8
+    assert rel_err(collec.energy(), s.energy()) < 1e-9
+    # AtomID form, one pair at a time
+    nl.ignore(sim.AtomID(atoms, 10), sim.AtomID(atoms, 500))
+    assert nl.ignore_size() == s.ignore_size() + 1

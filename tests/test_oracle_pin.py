@@ -118,6 +118,46 @@ def test_port_equals_reference_all_functors(oracle_built, kind, variant):
         assert r.energy() == p.energy()
 
 
+def chain_ignores(n, rng, extra=40):
+    """Bonded-neighbour style exclusions (i,i+1), (i,i+2) plus a few random pairs, duplicates and both orders."""
+    a = np.concatenate([np.arange(n - 1), np.arange(n - 2), rng.integers(0, n, extra), np.arange(5)])
+    b = np.concatenate([np.arange(1, n), np.arange(2, n), rng.integers(0, n, extra), np.arange(1, 6)])
+    keep = a != b
+    flip = rng.random(a.size) < 0.5
+    a, b = np.where(flip, b, a)[keep], np.where(flip, a, b)[keep]
+    return a.astype(np.uint32), b.astype(np.uint32)
+
+
+def test_ignore_port_equals_reference(oracle_built):
+    """NeighborList::ignore (trackers.hpp:190-193, trackers.cpp:64): excluded pairs never enter the list, the
+    next update_list(false) rebuilds; O(N^2) reference loop == cell-list finder == C port."""
+    if "ref" not in backends(oracle_built):
+        pytest.skip("compiled reference not present")
+    rng = np.random.default_rng(5)
+    w = W.random_system(900, 3, 2, seed=77, ntypes=2)
+    a, b = chain_ignores(900, rng)
+    lists = []
+    for be, inj in (("ref", False), ("ref", True), ("port", False), ("port", True)):
+        s = cpu_system(be, w, injected=inj)
+        n0 = len(s.pairs()[0])
+        w0 = s.which()
+        s.ignore(a, b)
+        assert s.update_list(False) and s.which() == w0 + 1  # ignorechanged forces the rebuild
+        pa, pb = s.pairs()
+        assert 0 < len(pa) < n0
+        key = set(zip(np.maximum(a, b).tolist(), np.minimum(a, b).tolist()))
+        assert s.ignore_size() == len(key)
+        assert not (set(zip(pa.tolist(), pb.tolist())) & key)
+        s.set_forces(True)
+        s.timestep(40)
+        lists.append((pa, pb, s.get_atoms(), s.energy()))
+    for other in lists[1:]:
+        assert np.array_equal(lists[0][0], other[0]) and np.array_equal(lists[0][1], other[1])
+        for x, y in zip(lists[0][2], other[2]):
+            assert np.array_equal(x, y)
+        assert lists[0][3] == other[3]
+
+
 def test_box_diff_is_ieee_remainder(oracle_built):
     rng = np.random.default_rng(0)
     L = np.array([3.0, 4.5, 7.25])
