@@ -185,6 +185,31 @@ int parm_inter_contacts(parm_inter *inter, uint64_t *contacts, uint64_t *overlap
 /* ---- Collection / CollectionVerlet / CollectionSol collection.hpp:23-130,205-263,360-374 ---- */
 int parm_verlet_create(parm_ctx *ctx, double dt, parm_integ **out);
 int parm_sol_create(parm_ctx *ctx, double dt, double damping, double T, uint64_t seed, parm_integ **out);
+/* the other fixed-box integrators that only need set_forces(). params per type:
+ *   PARM_INTEG_DAMPED      CollectionDamped      (dt, damping)        collection.cpp:324-381
+ *   PARM_INTEG_SOLHT       CollectionSolHT       (dt, damping, T)     :383-440  (seed: Gaussian stream)
+ *   PARM_INTEG_OVERDAMPED  CollectionOverdamped  (dt, gamma)          :471-492
+ *   PARM_INTEG_NOSEHOOVER  CollectionNoseHoover  (dt, Q, T)           :1170-1249
+ *   PARM_INTEG_GAUSSIANT   CollectionGaussianT   (dt)                 :1251-1299
+ *   PARM_INTEG_GEAR3A      CollectionGear3A      (dt)                 :1301-1322
+ *   PARM_INTEG_GEAR4A/5A/6A CollectionGear4A/5A/6A (dt, ncorrec)      :1324-1496
+ * Single-GPU contexts only (the correctors move atoms between force evaluations). */
+#define PARM_INTEG_VERLET 0
+#define PARM_INTEG_SOL 1
+#define PARM_INTEG_DAMPED 2
+#define PARM_INTEG_SOLHT 3
+#define PARM_INTEG_OVERDAMPED 4
+#define PARM_INTEG_NOSEHOOVER 5
+#define PARM_INTEG_GAUSSIANT 6
+#define PARM_INTEG_GEAR3A 7
+#define PARM_INTEG_GEAR4A 8
+#define PARM_INTEG_GEAR5A 9
+#define PARM_INTEG_GEAR6A 10
+int parm_integ_create(parm_ctx *ctx, int type, const double *params, int nparams, uint64_t seed, parm_integ **out);
+/* thermostat state: out[0] = xi, out[1] = lns (CollectionNoseHoover::get_xi/get_lns; GaussianT: xi) */
+int parm_integ_get_scalars(parm_integ *integ, double *out2);
+int parm_integ_reset_bath(parm_integ *integ);        /* CollectionNoseHoover::reset_bath, collection.hpp:589-592 */
+int parm_integ_set_param(parm_integ *integ, int which, double value); /* 1: Q (set_Q), 2: T, 3: damping, 4: gamma */
 int parm_integ_destroy(parm_integ *integ);
 /* add_interaction / add_tracker (collection.hpp:113-120): append, then update_trackers() */
 int parm_integ_add_interaction(parm_integ *integ, parm_inter *inter);

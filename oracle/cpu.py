@@ -84,6 +84,8 @@ def _load(backend, ndim):
                                     [vp, C.c_int, C.c_double, _dp, C.c_int, _u32p, _dp, _dp, C.c_int, _u8p, C.c_int, C.c_int])
     api["inter_contacts"] = sig("inter_contacts", C.c_int, [vp, C.c_int, C.POINTER(C.c_ulonglong), C.POINTER(C.c_ulonglong)])
     api["make_collection"] = sig("make_collection", C.c_int, [vp, C.c_int, C.c_double, C.c_double, C.c_double])
+    api["make_collection_ex"] = sig("make_collection_ex", C.c_int, [vp, C.c_int, _dp, C.c_int])
+    api["get_scalars"] = sig("get_scalars", None, [vp, _dp])
     api["update_list"] = sig("update_list", C.c_int, [vp, C.c_int, C.c_int])
     api["which"] = sig("which", C.c_uint32, [vp, C.c_int])
     api["ignore"] = sig("ignore", None, [vp, C.c_int, _u32p, _u32p, C.c_uint64])
@@ -167,10 +169,20 @@ class CpuSystem:
             raise RuntimeError("oracle add_interaction failed: %d" % r)
         return r
 
-    def make_collection(self, integrator, dt, damping=0.0, T=0.0):
-        r = self.api["make_collection"](self.h, integrator, dt, damping, T)
+    def make_collection(self, integrator, dt, damping=0.0, T=0.0, params=None):
+        """integrator: PARM_INTEG_* (include/parm_b200.h); params: the constructor arguments after dt."""
+        if params is None:
+            params = (damping, T)
+        p = np.ascontiguousarray((dt,) + tuple(params), dtype=np.float64)
+        r = self.api["make_collection_ex"](self.h, integrator, _d(p), p.size)
         if r:
             raise ValueError("oracle make_collection failed: %d" % r)
+
+    def get_scalars(self):
+        """(xi, lns) of CollectionNoseHoover."""
+        out = np.zeros(2)
+        self.api["get_scalars"](self.h, _d(out))
+        return out
 
     def update_list(self, force=True, nl=0):
         return bool(self.api["update_list"](self.h, nl, int(force)))

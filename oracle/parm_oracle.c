@@ -67,8 +67,11 @@ typedef struct {
     int ninters;
     NList *nls;
     int nnls;
-    int integrator; /* -1 none, 0 verlet, 1 sol */
+    int integrator; /* -1 none, else PARM_INTEG_* of include/parm_b200.h */
     double dt, damping, force_mag, desT;
+    double gamma, Q, xi, lns; /* Overdamped; NoseHoover / GaussianT */
+    unsigned ncorrec;         /* Gear4A-6A */
+    double *bs, *cs, *ds;
     double c0, c1, c2, sigmar, sigmav, corr, x11, x21, x22;
     const double *noise;
     size_t noise_len, noise_pos;
@@ -121,6 +124,7 @@ void port_sys_destroy(void *h) {
     }
     free(s->inters); free(s->nls);
     free(s->x); free(s->v); free(s->a); free(s->f); free(s->m);
+    free(s->bs); free(s->cs); free(s->ds);
     free(s);
 }
 
@@ -822,17 +826,48 @@ static int sol_set_constants(Sys *s) {
 }
 
 /* Collection ctor + initialize, collection.cpp:3-19; add_tracker/add_interaction collection.hpp:113-120 */
-int port_make_collection(void *h, int integrator, double dt, double damping, double T) {
+static void damped_set_constants(Sys *s) { /* CollectionDamped::set_constants, collection.cpp:342-354 */
+    if (s->damping <= 0.0) {
+        s->c0 = 1; s->c1 = 1; s->c2 = .5;
+        return;
+    }
+    double dampdt = s->damping * s->dt;
+    s->c0 = exp(-dampdt);
+    s->c1 = (-expm1(-dampdt)) / dampdt;
+    s->c2 = (1 - s->c1) / dampdt;
+}
+
+int port_make_collection_ex(void *h, int integrator, const double *p, int np) {
     Sys *s = (Sys *)h;
-    if (integrator != 0 && integrator != 1) return -1;
+    if (integrator < 0 || integrator > 10 || np < 1) return -1;
     s->integrator = integrator;
-    s->dt = dt;
+    s->dt = p[0];
+    s->xi = s->lns = 0;
+    const size_t nd = (size_t)(s->n ? s->n : 1) * s->D;
     if (integrator == 1) {
-        if (dt <= 0) return -2;
-        s->damping = damping;
-        s->force_mag = damping;
-        s->desT = T;
+        if (s->dt <= 0) return -2;
+        s->damping = p[1];
+        s->force_mag = p[1];
+        s->desT = p[2];
         if (sol_set_constants(s)) return -2;
+    } else if (integrator == 2) {
+        if (s->dt <= 0) return -2;
+        s->damping = p[1];
+        damped_set_constants(s);
+    } else if (integrator == 3) {
+        s->damping = p[1];
+        s->desT = p[2];
+    } else if (integrator == 4) {
+        s->gamma = np > 1 ? p[1] : 1.0;
+    } else if (integrator == 5) {
+        s->Q = p[1];
+        s->desT = p[2];
+    } else if (integrator >= 8) {
+        s->ncorrec = (unsigned)(np > 1 ? p[1] : 1);
+        free(s->bs); free(s->cs); free(s->ds);
+        s->bs = (double *)calloc(nd, 8); /* resetbs / resetbcs / resetbcds, collection.hpp:645, :679-683, :717-725 */
+        s->cs = (double *)calloc(nd, 8);
+        s->ds = (double *)calloc(nd, 8);
     }
     /* initialize() with empty interaction/tracker vectors: set_forces(true) zeroes f, a = f/m */
     memset(s->f, 0, (size_t)s->n * s->D * 8);
@@ -857,6 +892,13 @@ void port_inject_noise(void *h, const double *z, size_t len) {
     s->noise_len = len;
     s->noise_pos = 0;
 }
+
+int port_make_collection(void *h, int integrator, double dt, double damping, double T) {
+    double p[3] = {dt, damping, T};
+    if (integrator != 0 && integrator != 1) return -1;
+    return port_make_collection_ex(h, integrator, p, 3);
+}
+void port_get_scalars(void *h, double *out) { out[0] = ((Sys *)h)->xi; out[1] = ((Sys *)h)->lns; }
 
 /* CollectionVerlet::timestep, collection.cpp:442-469 */
 static void verlet_timestep(Sys *s) {
@@ -940,11 +982,279 @@ static void sol_timestep(Sys *s) {
     collection_update_trackers(s);
 }
 
+/* CollectionDamped::timestep, collection.cpp:356-381 */
+static void damped_timestep(Sys *s) {
+    const int D = s->D;
+    const double dt = s->dt, c0 = s->c0, c1 = s->c1, c2 = s->c2;
+    for (uint32_t i = 0; i < s->n; i++) {
+        double *x = s->x + (size_t)i * D, *v = s->v + (size_t)i * D, *a = s->a + (size_t)i * D;
+        if (frozen_le(s->m[i])) {
+            for (int d = 0; d < D; d++) v[d] = 0;
+            continue;
+        }
+        for (int d = 0; d < D; d++) {
+            x[d] += v[d] * (c1 * dt) + a[d] * (c2 * dt * dt);
+            v[d] = v[d] * c0 + a[d] * (dt * (c1 - c2));
+        }
+    }
+    collection_set_forces(s, 1);
+    for (uint32_t i = 0; i < s->n; i++) {
+        if (frozen_le(s->m[i])) continue;
+        for (int d = 0; d < D; d++) s->v[(size_t)i * D + d] += s->a[(size_t)i * D + d] * (dt * c2);
+    }
+    collection_update_trackers(s);
+}
+
+/* CollectionSolHT::timestep, collection.cpp:401-440; GaussVec(sqrt(2 T damping / dt)) :393, vecrand.hpp:227-240.
+ * The Gaussian stream is injected (port_inject_noise): D standard normals per mobile atom per step, component order. */
+static void solht_timestep(Sys *s) {
+    const int D = s->D;
+    const double dt = s->dt, damping = s->damping;
+    double keepv = 1 - (damping * dt);
+    double xpartfromv = dt - (dt * dt * damping / 2);
+    double sigma = sqrt(2.0 * s->desT * damping / dt);
+    for (uint32_t i = 0; i < s->n; i++) {
+        double *x = s->x + (size_t)i * D, *v = s->v + (size_t)i * D, *a = s->a + (size_t)i * D;
+        if (frozen_le(s->m[i])) {
+            for (int d = 0; d < D; d++) v[d] = 0;
+            continue;
+        }
+        for (int d = 0; d < D; d++) {
+            x[d] += (v[d] * xpartfromv) + (a[d] * (.5 * dt * dt));
+            v[d] = v[d] * keepv + a[d] * (dt / 2);
+        }
+    }
+    collection_set_forces(s, 1);
+    for (uint32_t i = 0; i < s->n; i++) {
+        double *v = s->v + (size_t)i * D, *a = s->a + (size_t)i * D, *f = s->f + (size_t)i * D;
+        if (frozen_le(s->m[i])) {
+            for (int d = 0; d < D; d++) a[d] = 0;
+            continue;
+        }
+        for (int d = 0; d < D; d++) {
+            double z = 0;
+            if (s->noise && s->noise_pos < s->noise_len) z = s->noise[s->noise_pos++];
+            double g = z * sigma + 0.0; /* normal_distribution(0, sigma) */
+            a[d] = (f[d] + g) / s->m[i];
+            v[d] += a[d] * (dt / 2);
+        }
+    }
+    collection_update_trackers(s);
+}
+
+/* CollectionOverdamped::timestep, collection.cpp:471-492 */
+static void overdamped_timestep(Sys *s) {
+    const int D = s->D;
+    collection_set_forces(s, 0);
+    for (uint32_t i = 0; i < s->n; i++) {
+        double *v = s->v + (size_t)i * D, *a = s->a + (size_t)i * D, *f = s->f + (size_t)i * D;
+        if (frozen_le(s->m[i])) {
+            for (int d = 0; d < D; d++) v[d] = a[d] = 0;
+            continue;
+        }
+        for (int d = 0; d < D; d++) {
+            a[d] = f[d] / s->m[i];
+            v[d] = a[d] * s->gamma;
+        }
+    }
+    for (size_t q = 0; q < (size_t)s->n * D; q++) s->x[q] += s->v[q] * s->dt;
+    collection_update_trackers(s);
+}
+
+/* solve_cubic, collection.cpp:2304-2353 */
+static double solve_cubic(double a1, double a2, double a3, double closeto) {
+    double Q = (a1 * a1 - 3 * a2) / 9;
+    double Q3 = Q * Q * Q;
+    double R = ((2 * a1 * a1 * a1) - (9 * a1 * a2) + 27 * a3) / 54;
+    double R2 = R * R;
+    if (Q3 >= R2) {
+        double theta = acos(R / sqrt(Q3));
+        double sqQ = -2 * sqrt(Q);
+        double x1 = sqQ * cos(theta / 3) - (a1 / 3);
+        double x2 = sqQ * cos((theta + (2 * M_PI)) / 3) - (a1 / 3);
+        double x3 = sqQ * cos((theta + (4 * M_PI)) / 3) - (a1 / 3);
+        double d1 = fabs(x1 - closeto), d2 = fabs(x2 - closeto), d3 = fabs(x3 - closeto);
+        if (d1 < d2 && d1 < d3) return x1;
+        if (d2 < d1 && d2 < d3) return x2;
+        return x3;
+    }
+    double R2Q3 = cbrt(sqrt(R2 - Q3) + fabs(R));
+    int sgn = (0 < R) - (R < 0);
+    return -(sgn * (R2Q3 + (Q / R2Q3))) - (a1 / 3);
+}
+
+static double collection_ndof(const Sys *s) { /* collection.cpp:116-133 */
+    int ndof = 0;
+    for (uint32_t i = 0; i < s->n; i++)
+        if (!frozen_le(s->m[i])) ndof += s->D;
+    return ndof;
+}
+
+/* CollectionNoseHoover::timestep, collection.cpp:1170-1242 */
+static void nosehoover_timestep(Sys *s) {
+    const int D = s->D;
+    const double dt = s->dt, Q = s->Q, T = s->desT;
+    double z3[3] = {0, 0, 0};
+    double ndof = collection_ndof(s);
+    double Kt = 2 * group_ke(s, z3);
+    for (uint32_t i = 0; i < s->n; i++) {
+        double *x = s->x + (size_t)i * D, *v = s->v + (size_t)i * D, *a = s->a + (size_t)i * D;
+        for (int d = 0; d < D; d++) {
+            double Ftilde = (a[d] - (v[d] * s->xi));
+            x[d] += v[d] * dt + Ftilde * (dt * dt / 2);
+            v[d] += Ftilde * (dt / 2);
+        }
+    }
+    s->lns += s->xi * dt + (Kt - ndof * T) * (dt * dt / 2 / Q);
+    collection_set_forces(s, 0);
+    for (uint32_t i = 0; i < s->n; i++)
+        for (int d = 0; d < D; d++) {
+            size_t q = (size_t)i * D + d;
+            s->a[q] = s->f[q] / s->m[i];
+            s->v[q] += s->a[q] * (dt / 2);
+        }
+    double Ky = 2 * group_ke(s, z3);
+    double z0 = s->xi + (Kt - 2 * ndof * T) * (dt / 2 / Q);
+    double z1 = Ky * 2 / dt / Q;
+    s->xi = solve_cubic(4 / dt - z0, 4 / dt / dt - 4 * z0 / dt, -(z0 * 4 / dt / dt) - z1, s->xi);
+    double ytov = 1 + s->xi * dt / 2;
+    for (size_t q = 0; q < (size_t)s->n * D; q++) s->v[q] /= ytov;
+    collection_update_trackers(s);
+}
+
+/* CollectionGaussianT::set_xi, collection.cpp:1251-1260 */
+static double gaussiant_set_xi(Sys *s) {
+    const int D = s->D;
+    double num = 0, den = 0;
+    for (uint32_t i = 0; i < s->n; i++) {
+        const double *v = s->v + (size_t)i * D, *f = s->f + (size_t)i * D;
+        num += dotD(D, f, v);
+        den += dotD(D, v, v) * s->m[i];
+    }
+    s->xi = num / den;
+    return s->xi;
+}
+
+/* CollectionGaussianT::timestep, collection.cpp:1268-1299 */
+static void gaussiant_timestep(Sys *s) {
+    const int D = s->D;
+    const double dt = s->dt;
+    for (uint32_t i = 0; i < s->n; i++) {
+        double *x = s->x + (size_t)i * D, *v = s->v + (size_t)i * D, *a = s->a + (size_t)i * D;
+        for (int d = 0; d < D; d++) {
+            x[d] += v[d] * dt + a[d] * (dt * dt / 2);
+            v[d] += (a[d] - (v[d] * s->xi)) * (dt / 2);
+        }
+    }
+    collection_set_forces(s, 0);
+    for (uint32_t i = 0; i < s->n; i++)
+        for (int d = 0; d < D; d++) {
+            size_t q = (size_t)i * D + d;
+            s->a[q] = s->f[q] / s->m[i];
+            s->v[q] += s->a[q] * (dt / 2);
+        }
+    double z = gaussiant_set_xi(s);
+    s->xi = z / (1 - z * dt / 2);
+    double ytov = 1 + s->xi * dt / 2;
+    for (size_t q = 0; q < (size_t)s->n * D; q++) s->v[q] /= ytov;
+    collection_update_trackers(s);
+}
+
+/* CollectionGear3A::timestep, collection.cpp:1301-1322 */
+static void gear3a_timestep(Sys *s) {
+    const int D = s->D;
+    const double dt = s->dt;
+    for (size_t q = 0; q < (size_t)s->n * D; q++) {
+        s->x[q] += s->v[q] * dt + s->a[q] * (dt * dt / 2);
+        s->v[q] += s->a[q] * dt;
+    }
+    collection_set_forces(s, 0);
+    for (uint32_t i = 0; i < s->n; i++)
+        for (int d = 0; d < D; d++) {
+            size_t q = (size_t)i * D + d;
+            double a = s->f[q] / s->m[i];
+            double correction = a - s->a[q];
+            s->v[q] += correction * (dt / 2);
+            s->a[q] = a;
+        }
+    collection_update_trackers(s);
+}
+
+/* CollectionGear4A / 5A / 6A::timestep, collection.cpp:1324-1364, 1366-1407, 1409-1496 */
+static void gear_timestep(Sys *s, int order) {
+    const int D = s->D;
+    const double dt = s->dt;
+    const size_t nd = (size_t)s->n * D;
+    double c0, c1, c3 = 0, c4 = 0, c5 = 0;
+    if (order == 4) {
+        for (size_t q = 0; q < nd; q++) {
+            s->x[q] += s->v[q] * dt + s->a[q] * (dt * dt / 2) + s->bs[q] * (dt * dt * dt / 6);
+            s->v[q] += s->a[q] * dt + s->bs[q] * (dt * dt / 2);
+            s->a[q] += s->bs[q] * dt;
+        }
+        c0 = dt * dt / 12;
+        c1 = 5 * dt / 12;
+    } else {
+        double dt2 = dt * dt / 2;
+        double dt3 = dt * dt2 / 3;
+        double dt4 = dt * dt3 / 4;
+        double dt5 = dt * dt4 / 5;
+        if (order == 5) {
+            for (size_t q = 0; q < nd; q++) {
+                s->x[q] += s->v[q] * dt + s->a[q] * dt2 + s->bs[q] * dt3 + s->cs[q] * dt4;
+                s->v[q] += s->a[q] * dt + s->bs[q] * dt2 + s->cs[q] * dt3;
+                s->a[q] += s->bs[q] * dt + s->cs[q] * dt2;
+                s->bs[q] += s->cs[q] * dt;
+            }
+            c0 = 19 * dt * dt / 240; c1 = 3 * dt / 8;
+            c3 = 3 / (2 * dt); c4 = 1 / (dt * dt);
+        } else {
+            for (size_t q = 0; q < nd; q++) {
+                s->x[q] += s->v[q] * dt + s->a[q] * dt2 + s->bs[q] * dt3 + s->cs[q] * dt4 + s->ds[q] * dt5;
+                s->v[q] += s->a[q] * dt + s->bs[q] * dt2 + s->cs[q] * dt3 + s->ds[q] * dt4;
+                s->a[q] += s->bs[q] * dt + s->cs[q] * dt2 + s->ds[q] * dt3;
+                s->bs[q] += s->cs[q] * dt + s->ds[q] * dt2;
+                s->cs[q] += s->ds[q] * dt;
+            }
+            c0 = 3 * dt * dt / 40; c1 = 251 * dt / 720;
+            c3 = 11 / (6 * dt); c4 = 2 / (dt * dt); c5 = 1 / (dt * dt * dt);
+        }
+    }
+    for (unsigned m = 0; m < s->ncorrec; m++) {
+        collection_set_forces(s, 0);
+        for (uint32_t i = 0; i < s->n; i++)
+            for (int d = 0; d < D; d++) {
+                size_t q = (size_t)i * D + d;
+                double a = s->f[q] / s->m[i];
+                double correction = a - s->a[q];
+                s->x[q] += correction * c0;
+                s->v[q] += correction * c1;
+                s->a[q] = a;
+                if (order == 4) s->bs[q] += correction / dt;
+                else s->bs[q] += correction * c3;
+                if (order >= 5) s->cs[q] += correction * c4;
+                if (order >= 6) s->ds[q] += correction * c5;
+            }
+    }
+    collection_update_trackers(s);
+}
+
 void port_timestep(void *h, int nsteps) {
     Sys *s = (Sys *)h;
     for (int k = 0; k < nsteps; k++) {
-        if (s->integrator == 0) verlet_timestep(s);
-        else if (s->integrator == 1) sol_timestep(s);
+        switch (s->integrator) {
+            case 0: verlet_timestep(s); break;
+            case 1: sol_timestep(s); break;
+            case 2: damped_timestep(s); break;
+            case 3: solht_timestep(s); break;
+            case 4: overdamped_timestep(s); break;
+            case 5: nosehoover_timestep(s); break;
+            case 6: gaussiant_timestep(s); break;
+            case 7: gear3a_timestep(s); break;
+            case 8: gear_timestep(s, 4); break;
+            case 9: gear_timestep(s, 5); break;
+            case 10: gear_timestep(s, 6); break;
+        }
     }
 }
 
@@ -1001,7 +1311,15 @@ double port_inter_pressure(void *h, int k) { Sys *s = (Sys *)h; double p; inter_
 int port_inter_contacts(void *h, int k, unsigned long long *c, unsigned long long *o) { Sys *s = (Sys *)h; inter_contacts(s, &s->inters[k], c, o); return 0; }
 void port_inter_stress(void *h, int k, double *out) { Sys *s = (Sys *)h; inter_loop(s, &s->inters[k], 0, NULL, out); }
 
-void port_set_forces(void *h, int constraints_and_a) { collection_set_forces((Sys *)h, constraints_and_a); }
+void port_set_forces(void *h, int constraints_and_a) {
+    Sys *s = (Sys *)h;
+    if (s->integrator == 6) { /* CollectionGaussianT::set_forces(bool) -> set_forces(true, true), collection.hpp:618 */
+        collection_set_forces(s, 1);
+        gaussiant_set_xi(s);
+        return;
+    }
+    collection_set_forces(s, constraints_and_a);
+}
 double port_kinetic_energy(void *h) { double z[3] = {0, 0, 0}; return group_ke((Sys *)h, z); }
 double port_potential_energy(void *h) { /* collection.cpp:98-108 */
     Sys *s = (Sys *)h;

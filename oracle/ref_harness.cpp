@@ -376,6 +376,52 @@ int ref_make_collection(void *h, int integrator, double dt, double damping, doub
     return 0;
 }
 
+// integrator types and parameter order: include/parm_b200.h (PARM_INTEG_*, parm_integ_create)
+int ref_make_collection_ex(void *h, int type, const double *p, int np) {
+    Sys *s = static_cast<Sys *>(h);
+    if (type == 0) return ref_make_collection(h, 0, p[0], 0, 0);
+    if (type == 1) return ref_make_collection(h, 1, p[0], p[1], p[2]);
+    try {
+        sptr<Box> b = boost::static_pointer_cast<Box>(s->box);
+        sptr<AtomGroup> ag = boost::static_pointer_cast<AtomGroup>(s->atoms);
+        switch (type) {
+            case 2: s->collec.reset(new CollectionDamped(b, ag, p[0], p[1])); break;
+            case 3: s->collec.reset(new CollectionSolHT(b, ag, p[0], p[1], p[2])); break;
+            case 4: s->collec.reset(new CollectionOverdamped(b, ag, p[0], np > 1 ? p[1] : 1.0)); break;
+            case 5: s->collec.reset(new CollectionNoseHoover(b, ag, p[0], p[1], p[2])); break;
+            case 6: s->collec.reset(new CollectionGaussianT(b, ag, p[0])); break;
+            case 7: s->collec.reset(new CollectionGear3A(b, ag, p[0])); break;
+            case 8: s->collec.reset(new CollectionGear4A(b, ag, p[0], (uint)(np > 1 ? p[1] : 1))); break;
+            case 9: s->collec.reset(new CollectionGear5A(b, ag, p[0], (uint)(np > 1 ? p[1] : 1))); break;
+            case 10: s->collec.reset(new CollectionGear6A(b, ag, p[0], (uint)(np > 1 ? p[1] : 1))); break;
+            default: return -1;
+        }
+        for (size_t k = 0; k < s->nls.size(); k++) s->collec->add_tracker(boost::static_pointer_cast<StateTracker>(s->nls[k]));
+        for (size_t k = 0; k < s->inters.size(); k++) s->collec->add_interaction(s->inters[k]);
+    } catch (std::exception &e) {
+        s->err = e.what();
+        return -2;
+    }
+    return 0;
+}
+}  // extern "C"
+// CollectionGaussianT::xi is protected and has no getter: read it through a pointer to member
+struct GaussianTXi : public CollectionGaussianT {
+    static flt get(CollectionGaussianT &c) { return c.*(&GaussianTXi::xi); }
+};
+extern "C" {
+// thermostat state: out[0] = xi, out[1] = lns (CollectionNoseHoover), out[0] = xi (CollectionGaussianT)
+void ref_get_scalars(void *h, double *out) {
+    out[0] = out[1] = 0;
+    Collection *c = static_cast<Sys *>(h)->collec.get();
+    if (CollectionNoseHoover *nh = dynamic_cast<CollectionNoseHoover *>(c)) {
+        out[0] = nh->get_xi();
+        out[1] = nh->get_lns();
+    } else if (CollectionGaussianT *gt = dynamic_cast<CollectionGaussianT *>(c)) {
+        out[0] = GaussianTXi::get(*gt);
+    }
+}
+
 const char *ref_last_error(void *h) { return static_cast<Sys *>(h)->err.c_str(); }
 
 int ref_update_list(void *h, int nl, int force) { return static_cast<Sys *>(h)->nls[nl]->update_list_cells(force != 0) ? 1 : 0; }

@@ -13,6 +13,8 @@ LIB_PATH = os.path.join(HERE, "libparm_b200.so")
 OK, ERR_INVALID, ERR_RUNTIME, ERR_CUDA, ERR_UNSUPPORTED = 0, 1, 2, 3, 4
 X, V, A, F, M, ALL = 1, 2, 4, 8, 16, 31
 RED_MASS, RED_MOMENTUM, RED_KE, RED_COM, RED_NDOF, RED_COMFORCE = range(6)
+(INTEG_VERLET, INTEG_SOL, INTEG_DAMPED, INTEG_SOLHT, INTEG_OVERDAMPED, INTEG_NOSEHOOVER, INTEG_GAUSSIANT, INTEG_GEAR3A,
+ INTEG_GEAR4A, INTEG_GEAR5A, INTEG_GEAR6A) = range(11)
 PAIR_LJREPULSE, PAIR_REPULSION, PAIR_LJATTRACTREPULSE, PAIR_LJCUT = range(4)
 (PAIR_LJATTRACTCUT, PAIR_LJATTRACTFIXEDREPULSE, PAIR_EISMCLACHLAN, PAIR_LJISH, PAIR_LJATTRACTREPULSESIGS,
  PAIR_REPULSIONDRAG, PAIR_LOISOHERN, PAIR_LOISLIN, PAIR_LOISOHERNMIN, PAIR_LOISLINMIN) = range(4, 14)
@@ -68,6 +70,10 @@ SIGNATURES = {
     "parm_inter_contacts": (C.c_int, [vp, u64p, u64p]),
     "parm_verlet_create": (C.c_int, [vp, C.c_double, vpp]),
     "parm_sol_create": (C.c_int, [vp, C.c_double, C.c_double, C.c_double, C.c_uint64, vpp]),
+    "parm_integ_create": (C.c_int, [vp, C.c_int, dp, C.c_int, C.c_uint64, vpp]),
+    "parm_integ_get_scalars": (C.c_int, [vp, dp]),
+    "parm_integ_reset_bath": (C.c_int, [vp]),
+    "parm_integ_set_param": (C.c_int, [vp, C.c_int, C.c_double]),
     "parm_integ_destroy": (C.c_int, [vp]),
     "parm_integ_add_interaction": (C.c_int, [vp, vp]),
     "parm_integ_add_tracker": (C.c_int, [vp, vp]),

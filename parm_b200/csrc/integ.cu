@@ -14,6 +14,7 @@
 #include <algorithm>
 
 #include "drift.cuh"
+#include "rng.cuh"
 #include "internal.cuh"
 
 #define I_BLOCK 256
@@ -83,34 +84,6 @@ k_verlet2(const double4 *__restrict__ pos, double *__restrict__ v, double *__res
             }
         }
     }
-}
-
-// ---- Philox4x32-10 counter RNG + Box-Muller (production noise of CollectionSol) ---------
-__device__ __forceinline__ void philox4x32(uint32_t c[4], uint32_t k0, uint32_t k1) {
-#pragma unroll
-    for (int r = 0; r < 10; r++) {
-        uint32_t hi0 = __umulhi(0xD2511F53u, c[0]), lo0 = 0xD2511F53u * c[0];
-        uint32_t hi1 = __umulhi(0xCD9E8D57u, c[2]), lo1 = 0xCD9E8D57u * c[2];
-        uint32_t n0 = hi1 ^ c[1] ^ k0, n2 = hi0 ^ c[3] ^ k1;
-        c[0] = n0;
-        c[1] = lo1;
-        c[2] = n2;
-        c[3] = lo0;
-        k0 += 0x9E3779B9u;
-        k1 += 0xBB67AE85u;
-    }
-}
-__device__ __forceinline__ void normal_pair(uint32_t id, uint64_t step, uint32_t stream, uint64_t seed, double &z0, double &z1) {
-    uint32_t c[4] = {id, (uint32_t)step, (uint32_t)(step >> 32), stream};
-    philox4x32(c, (uint32_t)seed, (uint32_t)(seed >> 32));
-    // 53-bit uniforms: u1 in (0,1], u2 in [0,1)
-    double u1 = ((double)(((uint64_t)c[0] << 21) ^ (c[1] >> 11)) + 1.0) * (1.0 / 9007199254740992.0);
-    double u2 = (double)(((uint64_t)c[2] << 21) ^ (c[3] >> 11)) * (1.0 / 9007199254740992.0);
-    double r = sqrt(-2.0 * log(u1));
-    double sn, cs;
-    sincospi(2.0 * u2, &sn, &cs);
-    z0 = r * cs;
-    z1 = r * sn;
 }
 
 struct SolConst {
@@ -276,6 +249,9 @@ extern "C" int parm_integ_destroy(parm_integ *g) {
     cudaStreamSynchronize(g->ctx->stream);
     if (g->d_noise) cudaFree(g->d_noise);
     if (g->d_mobile_rank) cudaFree(g->d_mobile_rank);
+    if (g->d_gear) cudaFree(g->d_gear);
+    if (g->d_scal) cudaFree(g->d_scal);
+    if (g->d_xpart) cudaFree(g->d_xpart);
     if (g->ev_ok) { cudaEventDestroy(g->ev[0]); cudaEventDestroy(g->ev[1]); }
     delete g;
     return 0;
@@ -323,7 +299,10 @@ static int launch_all_forces(parm_integ *g, const int *abort_flag = nullptr, uin
     return 0;
 }
 
-extern "C" int parm_integ_set_forces(parm_integ *g, int constraints_and_a) {
+int parm_integ_launch_all_forces(parm_integ *g, const int *abort_flag) { return launch_all_forces(g, abort_flag); }
+
+// Collection::set_forces (collection.cpp:159-179), non-virtual part
+static int base_set_forces(parm_integ *g, int constraints_and_a) {
     parm_ctx *c = g->ctx;
     CK(cudaSetDevice(c->device));
     PTRY(launch_all_forces(g));
@@ -335,15 +314,24 @@ extern "C" int parm_integ_set_forces(parm_integ *g, int constraints_and_a) {
     return 0;
 }
 
+extern "C" int parm_integ_set_forces(parm_integ *g, int constraints_and_a) {
+    if (g->type == PARM_INTEG_GAUSSIANT) { // CollectionGaussianT::set_forces(bool) -> set_forces(true, true), collection.hpp:618
+        PTRY(base_set_forces(g, 1));
+        return parm_integ_extra_after_set_forces(g);
+    }
+    return base_set_forces(g, constraints_and_a);
+}
+
 extern "C" int parm_integ_initialize(parm_integ *g) { // collection.cpp:13-19
     PTRY(parm_integ_update_trackers(g));
-    PTRY(parm_integ_set_forces(g, 1));
+    // called from the base-class constructor in the reference: the base set_forces, not a derived override
+    PTRY(base_set_forces(g, 1));
     return parm_integ_update_trackers(g);
 }
 
 extern "C" int parm_integ_set_dt(parm_integ *g, double dt) {
     g->dt = dt;
-    if (g->type == 1) return sol_set_constants(g);
+    if (g->type == PARM_INTEG_SOL) return sol_set_constants(g);
     return 0;
 }
 extern "C" int parm_integ_set_temperature(parm_integ *g, double damping, double T) {
@@ -392,6 +380,7 @@ extern "C" int parm_integ_inject_noise(parm_integ *g, const double *z, size_t le
 // kernels of this step return immediately, so a step can be enqueued before the host has seen whether
 // its predecessor asked for a rebuild.
 static int enqueue_step(parm_integ *g, uint64_t step, const int *abort_flag, int slot) {
+    if (g->type >= PARM_INTEG_DAMPED) return parm_integ_extra_enqueue(g, step, abort_flag, slot);
     parm_ctx *c = g->ctx;
     const uint32_t n = parm_owned(c); // ghost copies are never integrated
     parm_nlist *nl = g->trackers.empty() ? nullptr : g->trackers[0];
@@ -483,6 +472,11 @@ extern "C" int parm_integ_timestep(parm_integ *g, int nsteps) {
     for (size_t k = 1; k < g->trackers.size(); k++)
         if (g->trackers[k] != g->trackers[0]) { parm_set_error("one NeighborList per Collection is supported"); return PARM_ERR_UNSUPPORTED; }
     if (nsteps <= 0) return 0;
+    if (g->type == PARM_INTEG_NOSEHOOVER) { // Collection::degrees_of_freedom(), collection.cpp:116-133
+        double out[4];
+        PTRY(parm_reduce(c, PARM_RED_NDOF, nullptr, out));
+        g->ndof_cached = out[0];
+    }
     parm_nlist *nl = g->trackers.empty() ? nullptr : g->trackers[0];
     if (!nl) { // no tracker: nothing to decide, the steps just queue up
         for (int s = 0; s < nsteps; s++) {

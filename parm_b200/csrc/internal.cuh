@@ -203,7 +203,14 @@ struct parm_inter {
 
 struct parm_integ {
     parm_ctx *ctx;
-    int type; // 0 verlet, 1 sol
+    int type; // PARM_INTEG_*
+    // integ_extra.cu: gamma (Overdamped), Q (NoseHoover), corrector passes and derivative arrays (Gear4A-6A, by
+    // AtomVec index: [3 arrays][3 components][nid_pad]), thermostat scalars on the device
+    double gamma, Q, ndof_cached;
+    int ncorrec;
+    double *d_gear;
+    struct IntegScalars *d_scal;
+    double *d_xpart; // per-block partials of the thermostat reductions
     double dt, damping, force_mag, desT;
     double c0, c1, c2, sigmar, sigmav, corr, x11, x21, x22;
     uint64_t seed;
@@ -222,7 +229,15 @@ struct parm_integ {
 // slots [0, parm_owned(c)) hold the atoms this context integrates; ghost copies (sharded) follow them
 static inline uint32_t parm_owned(const parm_ctx *c) { return c->sh.on ? c->sh.n_local : c->n; }
 
+// thermostat state of CollectionNoseHoover / CollectionGaussianT, kept on the device so that steps queue up
+struct IntegScalars {
+    double xi, lns, Kt, ytov;
+};
+
 // ---- cross-TU host functions ----
+int parm_integ_extra_enqueue(parm_integ *g, uint64_t step, const int *abort_flag, int slot); // integ_extra.cu
+int parm_integ_extra_after_set_forces(parm_integ *g);  // CollectionGaussianT::set_forces -> set_xi
+int parm_integ_launch_all_forces(parm_integ *g, const int *abort_flag);
 int parm_ctx_alloc(int ndim, uint32_t nid, uint32_t cap_slots, int device, parm_ctx **out);
 int parm_shard_halo_exchange(parm_ctx *c);                 // per step, after K1
 int parm_shard_drift_decision(parm_nlist *nl, bool *rebuild); // after K3: global top-2 rule (synchronous)

@@ -665,7 +665,7 @@ class Collection:
 
     def _push_interaction(self, inter):
         if not isinstance(inter, _NListed):
-            raise capi.ParmUnsupported("only NListed interactions of the four in-scope pair types run on the device")
+            raise capi.ParmUnsupported("only NListed interactions run on the device")
         inter._flush()
         self.interactions.append(inter)
 
@@ -812,6 +812,124 @@ class CollectionSol(Collection):
         return out
 
 
+class _GenericCollection(Collection):
+    """The other fixed-box integrators (include/parm_b200.h PARM_INTEG_*)."""
+    integ_type = None
+
+    def _make(self, box, atoms, params, interactions, trackers, constraints, seed=0):
+        Collection.__init__(self, box, atoms, interactions, trackers, constraints)
+        h = C.c_void_p()
+        p = np.ascontiguousarray(params, dtype=np.float64)
+        call("parm_integ_create", atoms._h, self.integ_type, _dptr(p), p.size, int(seed), C.byref(h))
+        self._h = h
+        self.dt = float(params[0])
+        _construct(self)
+
+    def set_dt(self, dt):
+        self.dt = float(dt)
+        call("parm_integ_set_dt", self._h, self.dt)
+
+    def _scalars(self):
+        out = np.zeros(2)
+        call("parm_integ_get_scalars", self._h, _dptr(out))
+        return out
+
+
+class CollectionDamped(_GenericCollection):  # collection.hpp:273-295
+    integ_type = capi.INTEG_DAMPED
+
+    def __init__(self, box, atoms, dt, damping, interactions=(), trackers=(), constraints=()):
+        self._make(box, atoms, (dt, damping), interactions, trackers, constraints)
+
+    def change_damping(self, damp):
+        call("parm_integ_set_param", self._h, 3, float(damp))
+
+
+class CollectionSolHT(_GenericCollection):  # collection.hpp:328-353
+    integ_type = capi.INTEG_SOLHT
+    inject_noise = CollectionSol.inject_noise  # z: (steps, n_mobile, ndim) standard normals
+
+    def __init__(self, box, atoms, dt, damping, desired_temperature, interactions=(), trackers=(), constraints=(), seed=0):
+        self._make(box, atoms, (dt, damping, desired_temperature), interactions, trackers, constraints, seed)
+
+    def change_temperature(self, newdt, damp, desired_temperature):
+        self.set_dt(newdt)
+        call("parm_integ_set_param", self._h, 3, float(damp))
+        call("parm_integ_set_param", self._h, 2, float(desired_temperature))
+
+
+class CollectionOverdamped(_GenericCollection):  # collection.hpp:376-393
+    integ_type = capi.INTEG_OVERDAMPED
+
+    def __init__(self, box, atoms, dt, gamma=1.0, interactions=(), trackers=(), constraints=()):
+        self._make(box, atoms, (dt, gamma), interactions, trackers, constraints)
+
+
+class CollectionNoseHoover(_GenericCollection):  # collection.hpp:567-598
+    integ_type = capi.INTEG_NOSEHOOVER
+
+    def __init__(self, box, atoms, dt, Q, T, interactions=(), trackers=(), constraints=()):
+        self._make(box, atoms, (dt, Q, T), interactions, trackers, constraints)
+        self.Q, self.T = float(Q), float(T)
+
+    def set_Q(self, Q):
+        self.Q = float(Q)
+        call("parm_integ_set_param", self._h, 1, self.Q)
+
+    def reset_bath(self):
+        call("parm_integ_reset_bath", self._h)
+
+    def get_xi(self):
+        return float(self._scalars()[0])
+
+    def get_lns(self):
+        return float(self._scalars()[1])
+
+    def hamiltonian(self):  # collection.cpp:1244-1249
+        xi, lns = self._scalars()
+        return (self.kinetic_energy() + self.potential_energy() + (xi * xi * self.Q / 2) +
+                (self.degrees_of_freedom() * lns * self.T))
+
+
+class CollectionGaussianT(_GenericCollection):  # collection.hpp:600-621
+    integ_type = capi.INTEG_GAUSSIANT
+
+    def __init__(self, box, atoms, dt, interactions=(), trackers=(), constraints=()):
+        self._make(box, atoms, (dt,), interactions, trackers, constraints)
+
+
+class CollectionGear3A(_GenericCollection):  # collection.hpp:623-637
+    integ_type = capi.INTEG_GEAR3A
+
+    def __init__(self, box, atoms, dt, interactions=(), trackers=(), constraints=()):
+        self._make(box, atoms, (dt,), interactions, trackers, constraints)
+
+
+class _GearN(_GenericCollection):
+    def __init__(self, box, atoms, dt, ncorrectionsteps=1, interactions=(), trackers=(), constraints=()):
+        self._make(box, atoms, (dt, ncorrectionsteps), interactions, trackers, constraints)
+
+
+class CollectionGear4A(_GearN):  # collection.hpp:639-671
+    integ_type = capi.INTEG_GEAR4A
+
+
+class CollectionGear5A(_GearN):  # collection.hpp:673-709
+    integ_type = capi.INTEG_GEAR5A
+
+
+class CollectionGear6A(_GearN):  # collection.hpp:711-755
+    integ_type = capi.INTEG_GEAR6A
+
+
+INTEGRATOR_CLASSES = {
+    capi.INTEG_VERLET: CollectionVerlet, capi.INTEG_SOL: CollectionSol, capi.INTEG_DAMPED: CollectionDamped,
+    capi.INTEG_SOLHT: CollectionSolHT, capi.INTEG_OVERDAMPED: CollectionOverdamped,
+    capi.INTEG_NOSEHOOVER: CollectionNoseHoover, capi.INTEG_GAUSSIANT: CollectionGaussianT,
+    capi.INTEG_GEAR3A: CollectionGear3A, capi.INTEG_GEAR4A: CollectionGear4A, capi.INTEG_GEAR5A: CollectionGear5A,
+    capi.INTEG_GEAR6A: CollectionGear6A}
+
+
 def _construct(collec):
     """Collection constructor tail: the vectors were stored as passed (no per-add update_trackers),
     then Collection::initialize() runs (collection.cpp:3-19)."""
@@ -841,10 +959,13 @@ def from_workload(w, device=0, collection=True):
     nl.update_list(True)
     collec = None
     if collection:
-        if w.get("integrator", 0) == 0:
+        integ = int(w.get("integrator", 0))
+        if integ == 0:
             collec = CollectionVerlet(box, atoms, w["dt"])
-        else:
+        elif integ == 1:
             collec = CollectionSol(box, atoms, w["dt"], w["damping"], w["T"], seed=w.get("seed", 0))
+        else:  # w["integ_params"]: the constructor arguments after dt
+            collec = INTEGRATOR_CLASSES[integ](box, atoms, w["dt"], *w.get("integ_params", ()))
         collec.add_tracker(nl)
         collec.add_interaction(inter)
     return box, atoms, inter, nl, collec

@@ -248,3 +248,18 @@ def functor_system(kind, variant="", ndim=3, n=400, seed=0, continuous=False, T=
              sig_table=stab, skin=0.3, dt=0.002, integrator=VERLET,
              name="functor_k%d%s_%dd%s" % (kind, variant, ndim, "_cont" if continuous else ""))
     return w
+
+
+INTEGRATOR_CASES = {  # PARM_INTEG_* -> constructor arguments after dt
+    2: ("damped", (0.8,)), 3: ("solht", (0.7, 0.4)), 4: ("overdamped", (0.5,)), 5: ("nosehoover", (3.0, 0.5)),
+    6: ("gaussiant", ()), 7: ("gear3a", ()), 8: ("gear4a", (2,)), 9: ("gear5a", (2,)), 10: ("gear6a", (1,))}
+
+
+def integrator_system(integ, ndim=3, n=150, seed=0, kind=None):
+    """random_system + one of the (f)2 integrators; frozen atoms only where the integrator tests for them."""
+    name, params = INTEGRATOR_CASES[integ]
+    if kind is None:
+        kind = KIND_LJATTRACTREPULSE if integ % 2 else KIND_REPULSION
+    w = random_system(n, ndim, kind, seed=seed, ntypes=2, frozen=(2 if integ in (2, 3, 4) else 0), T=0.5)
+    w.update(integrator=integ, integ_params=params, name="integ_%s_%dd" % (name, ndim))
+    return w

@@ -23,7 +23,7 @@ from parm_b200 import workloads as W  # noqa: E402
 from parity_util import cpu_system  # noqa: E402
 
 INPUT_KEYS = ("ndim", "L", "x", "v", "m", "kind", "params", "types", "eps_table", "skin", "dt", "integrator")
-OPTIONAL_KEYS = ("damping", "T", "variant", "sig_table")
+OPTIONAL_KEYS = ("damping", "T", "variant", "sig_table", "integ_params")
 
 
 def record(w, steps=40, noise=None):
@@ -47,7 +47,7 @@ def record(w, steps=40, noise=None):
     x, v, acc, ff = s.get_atoms()
     out.update(steps=np.asarray(steps), x_end=x, v_end=v, a_end=acc, f_end=ff, which_end=np.asarray(s.which()),
                E_end=np.asarray(s.energy()), K_end=np.asarray(s.kinetic_energy()), P_end=np.asarray(s.pressure()),
-               T_end=np.asarray(s.temp()))
+               T_end=np.asarray(s.temp()), scalars_end=s.get_scalars())
     a, b = s.pairs()
     out["pairs_first_end"], out["pairs_last_end"] = a, b
     return out
@@ -79,6 +79,14 @@ def main():
         ndim = 2 if k % 4 == 3 else 3
         w = W.functor_system(kind, variant, ndim=ndim, n=90 if ndim == 3 else 70, seed=500 + k)
         cases["functor_k%d%s_%dd" % (kind, variant, ndim)] = record(w, steps=30)
+    # the other fixed-box integrators
+    for integ, (name, _) in W.INTEGRATOR_CASES.items():
+        ndim = 2 if integ % 3 == 0 else 3
+        w = W.integrator_system(integ, ndim=ndim, n=100 if ndim == 3 else 80, seed=700 + integ)
+        z = None
+        if integ == 3:
+            z = np.random.default_rng(integ).standard_normal((30, int((w["m"] > 0).sum()), ndim))
+        cases["integ_%s_%dd" % (name, ndim)] = record(w, steps=30, noise=z)
     for name, d in cases.items():
         np.savez_compressed(os.path.join(HERE, name + ".npz"), **d)
         print(name, "pairs", len(d["pairs_first"]), "E", float(d["energy"]), "which_end", int(d["which_end"]))

@@ -21,10 +21,13 @@ def cpu_system(backend, w, injected=False, collection=True):
                       injected=injected, sig_table=sig_table)
     s.update_list(True)
     if collection:
-        if w.get("integrator", 0) == 0:
+        integ = int(w.get("integrator", 0))
+        if integ == 0:
             s.make_collection(0, w["dt"])
-        else:
+        elif integ == 1:
             s.make_collection(1, w["dt"], w["damping"], w["T"])
+        else:
+            s.make_collection(integ, w["dt"], params=tuple(w.get("integ_params", ())))
     return s
 
 

@@ -1,0 +1,127 @@
+"""CollectionDamped, SolHT, Overdamped, NoseHoover, GaussianT and Gear3A-6A on the GPU against
+the oracle (the compiled reference when present, else its C restatement): trajectories, rebuild counts, energies
+and thermostat state, through multi-step calls (steps queued with the speculative rebuild guard) and one step
+at a time."""
+import numpy as np
+import pytest
+
+from parm_b200 import workloads as W
+from parity_util import backends, cpu_system, rel_err, rel_err_vec
+
+pytestmark = pytest.mark.gpu
+CASES = sorted(W.INTEGRATOR_CASES)
+IDS = [W.INTEGRATOR_CASES[k][0] for k in CASES]
+
+
+def lattice_case(integ, ndim):
+    """A few thousand atoms on a jittered lattice: enough steps for several neighbour-list rebuilds."""
+    if ndim == 3:
+        w = W.lj_lattice((12, 12, 12), seed=60 + integ, T=1.0)
+    else:
+        w = W.config2(nx=60, ny=60, seed=60 + integ)
+        w["v"] = w["v"] * 20.0
+    w.update(integrator=integ, integ_params=W.INTEGRATOR_CASES[integ][1])
+    return w
+
+
+def noise_for(w, steps, integ):
+    if integ != 3:
+        return None
+    return np.random.default_rng(9).standard_normal((steps, int((w["m"] > 0).sum()), w["ndim"]))
+
+
+def compare(collec, atoms, nl, s, w, tol_x=1e-8):
+    x, v, a, f = s.get_atoms()
+    assert nl.which() == s.which()
+    assert rel_err_vec(atoms.peek("x") - w["x"], x - w["x"]) < tol_x
+    assert rel_err_vec(atoms.peek("v"), v) < tol_x
+    assert rel_err_vec(atoms.peek("a"), a) < 1e-7
+    assert rel_err(collec.energy(), s.energy()) < 1e-9
+    assert rel_err(collec.pressure(), s.pressure()) < 1e-8
+
+
+@pytest.mark.parametrize("integ", CASES, ids=IDS)
+@pytest.mark.parametrize("ndim", [3, 2])
+def test_integrator_matches_oracle(oracle_built, integ, ndim):
+    from parm_b200 import sim
+    w = lattice_case(integ, ndim)
+    steps = 120
+    be = backends(oracle_built)[-1]
+    box, atoms, inter, nl, collec = sim.from_workload(w)
+    s = cpu_system(be, w, injected=True)
+    collec.set_forces(True)
+    s.set_forces(True)
+    z = noise_for(w, steps, integ)
+    if z is not None:
+        collec.inject_noise(z)
+        s.inject_noise(z)
+    collec.timestep(steps)
+    s.timestep(steps)
+    compare(collec, atoms, nl, s, w)
+    if integ != 4:  # (overdamped relaxation barely moves the atoms)
+        assert nl.which() > 1  # at least one rebuild went through the guarded pipeline
+    if integ == 5:
+        assert rel_err(collec._scalars(), s.get_scalars()) < 1e-9
+        assert abs(collec.get_xi()) > 0
+
+
+@pytest.mark.parametrize("integ", CASES, ids=IDS)
+def test_integrator_ragged_system_step_by_step(oracle_built, integ):
+    """Random ragged systems (vacancies, unwrapped coordinates, several species, frozen atoms where the integrator
+    tests for them), advanced one timestep() call at a time."""
+    from parm_b200 import sim
+    w = W.integrator_system(integ, ndim=3, n=1500, seed=90 + integ)
+    steps = 25
+    be = backends(oracle_built)[-1]
+    box, atoms, inter, nl, collec = sim.from_workload(w)
+    s = cpu_system(be, w, injected=True)
+    collec.set_forces(True)
+    s.set_forces(True)
+    z = noise_for(w, steps, integ)
+    if z is not None:
+        collec.inject_noise(z)
+        s.inject_noise(z)
+    for _ in range(steps):
+        collec.timestep()
+    s.timestep(steps)
+    compare(collec, atoms, nl, s, w, tol_x=1e-7)
+
+
+def test_solht_thermostat_reaches_temperature():
+    """Production noise (Philox, not injected): the Honeycutt-Thirumalai Langevin integrator equilibrates to T."""
+    from parm_b200 import sim
+    w = W.config4(shape=(14, 14, 14), seed=5)
+    w.update(integrator=3, integ_params=(2.0, 1.0), dt=0.002)
+    box, atoms, inter, nl, collec = sim.from_workload(w)
+    collec.set_forces(True)
+    collec.timestep(4000)
+    Ts = []
+    for _ in range(20):
+        collec.timestep(100)
+        Ts.append(collec.temp())
+    assert abs(np.mean(Ts) - 1.0) < 0.05
+
+
+def test_nosehoover_hamiltonian_is_conserved():
+    from parm_b200 import sim
+    w = W.lj_lattice((10, 10, 10), seed=11, T=1.0)
+    w.update(integrator=5, integ_params=(50.0, 1.0), dt=0.002)
+    box, atoms, inter, nl, collec = sim.from_workload(w)
+    collec.set_forces(True)
+    H0 = collec.hamiltonian()
+    collec.timestep(2000)
+    H1 = collec.hamiltonian()
+    assert abs(H1 - H0) / abs(H0) < 2e-3
+    assert collec.get_lns() != 0.0
+
+
+def test_extra_integrators_refuse_sharded_contexts_and_bad_types():
+    import ctypes as C
+    from parm_b200 import capi, sim
+    atoms = sim.AtomVec(np.ones(8), ndim=3)
+    h = C.c_void_p()
+    p = (C.c_double * 2)(0.01, 1.0)
+    with pytest.raises(Exception):
+        capi.call("parm_integ_create", atoms._h, 42, p, 2, 0, C.byref(h))
+    with pytest.raises(Exception):  # CollectionDamped: dt must be positive (collection.cpp:334-336)
+        sim.CollectionDamped(sim.OriginBox(np.full(3, 5.0), 3), atoms, -1.0, 0.5)

@@ -35,6 +35,8 @@ def load(path):
         w["variant"] = str(d["variant"])
     if "sig_table" in d:
         w["sig_table"] = d["sig_table"]
+    if "integ_params" in d:
+        w["integ_params"] = tuple(float(q) for q in d["integ_params"])
     return w, d
 
 
@@ -53,7 +55,8 @@ def replay(backend, w, d):
     s.timestep(int(d["steps"]))
     x, v, a, ff = s.get_atoms()
     out.update(x_end=x, v_end=v, a_end=a, f_end=ff, which_end=np.asarray(s.which()), E_end=np.asarray(s.energy()),
-               K_end=np.asarray(s.kinetic_energy()), P_end=np.asarray(s.pressure()), T_end=np.asarray(s.temp()))
+               K_end=np.asarray(s.kinetic_energy()), P_end=np.asarray(s.pressure()), T_end=np.asarray(s.temp()),
+               scalars_end=s.get_scalars())
     out["pairs_first_end"], out["pairs_last_end"] = s.pairs()
     return out
 
@@ -116,6 +119,28 @@ def test_port_equals_reference_all_functors(oracle_built, kind, variant):
         for a, b in zip(r.get_atoms(), p.get_atoms()):
             assert np.array_equal(a, b)
         assert r.energy() == p.energy()
+
+
+@pytest.mark.parametrize("integ", sorted(W.INTEGRATOR_CASES), ids=[W.INTEGRATOR_CASES[k][0] for k in sorted(W.INTEGRATOR_CASES)])
+def test_port_equals_reference_all_integrators(oracle_built, integ):
+    """the C restatement of every extra integrator is bit-equal to the compiled reference."""
+    if "ref" not in backends(oracle_built):
+        pytest.skip("compiled reference not present")
+    for ndim in (3, 2):
+        w = W.integrator_system(integ, ndim=ndim, n=160, seed=40 + integ)
+        outs = []
+        for be in ("ref", "port"):
+            s = cpu_system(be, w)
+            s.set_forces(True)
+            if integ == 3:
+                s.inject_noise(np.random.default_rng(1).standard_normal((40, int((w["m"] > 0).sum()), ndim)))
+            s.timestep(40)
+            outs.append((s.get_atoms(), s.energy(), s.which(), s.get_scalars()))
+        for a, b in zip(outs[0][0], outs[1][0]):
+            assert np.array_equal(a, b)
+        assert outs[0][1] == outs[1][1] and outs[0][2] == outs[1][2]
+        if integ == 5:
+            assert np.array_equal(outs[0][3], outs[1][3]) and outs[0][3][0] != 0
 
 
 def chain_ignores(n, rng, extra=40):
