@@ -1,5 +1,7 @@
 // parm_b200 drop-in for ParM's src/collection.hpp -- Collection, CollectionVerlet, CollectionSol
-// (collection.hpp:23-130, 205-263, 360-374; collection.cpp:3-208, 210-322, 442-469).
+// (collection.hpp:23-130, 205-263, 360-374; collection.cpp:3-208, 210-322, 442-469) and the other fixed-box
+// integrators that only need set_forces(): CollectionDamped, SolHT, Overdamped, NoseHoover, GaussianT,
+// Gear3A-6A (collection.hpp:273-353, 376-393, 567-755).
 // timestep() enqueues K1 -> force kernel(s) -> K3+drift on the device and returns; nothing is
 // copied to the host until user code touches an Atom or asks for a scalar.
 #ifndef PARM_B200_COLLECTION_H
@@ -194,5 +196,135 @@ class CollectionSol : public Collection {
         parm_b200::check(parm_integ_timestep(integ, 1));
     }
 };
+
+namespace parm_b200 {
+// Shared body of the integrators created through parm_integ_create (include/parm_b200.h PARM_INTEG_*).
+class DeviceCollection : public Collection {
+   protected:
+    flt dt;
+    void make(int type, const flt *params, int nparams, uint64_t seed = 0) {
+        check(parm_integ_create(av->context(), type, params, nparams, seed, &integ));
+        register_all(true);
+    }
+    void scalars(flt *out2) {
+        ready(false);
+        check(parm_integ_get_scalars(integ, out2));
+    }
+
+   public:
+    DeviceCollection(sptr<Box> box, sptr<AtomGroup> atoms, flt dt, vector<sptr<Interaction> > is, vector<sptr<StateTracker> > ts,
+                     vector<sptr<Constraint> > cs)
+        : Collection(box, atoms, is, ts, cs), dt(dt) {}
+    void timestep() {
+        ready();
+        check(parm_integ_timestep(integ, 1));
+    }
+    void set_dt(flt newdt) {
+        dt = newdt;
+        check(parm_integ_set_dt(integ, dt));
+    }
+};
+}  // namespace parm_b200
+
+#define PARM_B200_VECS                                                                    \
+    vector<sptr<Interaction> > interactions = vector<sptr<Interaction> >(),              \
+                               vector<sptr<StateTracker> > trackers = vector<sptr<StateTracker> >(), \
+                               vector<sptr<Constraint> > constraints = vector<sptr<Constraint> >()
+
+class CollectionDamped : public parm_b200::DeviceCollection {  // collection.hpp:273-295, collection.cpp:324-381
+   public:
+    CollectionDamped(sptr<Box> box, sptr<AtomGroup> atoms, const flt dt, const flt damping, PARM_B200_VECS)
+        : DeviceCollection(box, atoms, dt, interactions, trackers, constraints) {
+        flt p[2] = {dt, damping};
+        make(PARM_INTEG_DAMPED, p, 2);
+    }
+    void change_damping(const flt damp) { parm_b200::check(parm_integ_set_param(integ, 3, damp)); }
+};
+
+class CollectionSolHT : public parm_b200::DeviceCollection {  // collection.hpp:328-353, collection.cpp:383-440
+   public:
+    CollectionSolHT(sptr<Box> box, sptr<AtomGroup> atoms, const flt dt, const flt damping, const flt desired_temperature,
+                    PARM_B200_VECS)
+        : DeviceCollection(box, atoms, dt, interactions, trackers, constraints) {
+        flt p[3] = {dt, damping, desired_temperature};
+        make(PARM_INTEG_SOLHT, p, 3, (uint64_t)parm_b200::randengine()());
+    }
+    void change_temperature(const flt newdt, const flt damp, const flt desired_temperature) {
+        set_dt(newdt);
+        parm_b200::check(parm_integ_set_param(integ, 3, damp));
+        parm_b200::check(parm_integ_set_param(integ, 2, desired_temperature));
+    }
+};
+
+class CollectionOverdamped : public parm_b200::DeviceCollection {  // collection.hpp:376-393, collection.cpp:471-492
+   public:
+    CollectionOverdamped(sptr<Box> box, sptr<AtomGroup> atoms, const flt dt, const flt gamma = 1.0, PARM_B200_VECS)
+        : DeviceCollection(box, atoms, dt, interactions, trackers, constraints) {
+        flt p[2] = {dt, gamma};
+        make(PARM_INTEG_OVERDAMPED, p, 2);
+    }
+};
+
+class CollectionNoseHoover : public parm_b200::DeviceCollection {  // collection.hpp:567-598, collection.cpp:1170-1249
+   protected:
+    flt Q, T;
+
+   public:
+    CollectionNoseHoover(sptr<Box> box, sptr<AtomGroup> atoms, const flt dt, const flt Q, const flt T, PARM_B200_VECS)
+        : DeviceCollection(box, atoms, dt, interactions, trackers, constraints), Q(Q), T(T) {
+        flt p[3] = {dt, Q, T};
+        make(PARM_INTEG_NOSEHOOVER, p, 3);
+    }
+    void set_Q(flt newQ) {
+        Q = newQ;
+        parm_b200::check(parm_integ_set_param(integ, 1, Q));
+    }
+    void reset_bath() { parm_b200::check(parm_integ_reset_bath(integ)); }
+    flt get_xi() { flt s[2]; scalars(s); return s[0]; }
+    flt get_lns() { flt s[2]; scalars(s); return s[1]; }
+    flt hamiltonian() {
+        flt s[2];
+        scalars(s);
+        flt H = (kinetic_energy() + potential_energy() + (s[0] * s[0] * Q / 2) + (degrees_of_freedom() * s[1] * T));
+        assert(not isnan(H));
+        return H;
+    }
+};
+
+class CollectionGaussianT : public parm_b200::DeviceCollection {  // collection.hpp:600-621, collection.cpp:1251-1299
+   public:
+    CollectionGaussianT(sptr<Box> box, sptr<AtomGroup> atoms, const flt dt, PARM_B200_VECS)
+        : DeviceCollection(box, atoms, dt, interactions, trackers, constraints) {
+        make(PARM_INTEG_GAUSSIANT, &dt, 1);
+    }
+};
+
+class CollectionGear3A : public parm_b200::DeviceCollection {  // collection.hpp:623-637, collection.cpp:1301-1322
+   public:
+    CollectionGear3A(sptr<Box> box, sptr<AtomGroup> atoms, const flt dt, PARM_B200_VECS)
+        : DeviceCollection(box, atoms, dt, interactions, trackers, constraints) {
+        make(PARM_INTEG_GEAR3A, &dt, 1);
+    }
+};
+
+#define PARM_B200_GEAR(NAME, TYPE)                                                                               \
+    class NAME : public parm_b200::DeviceCollection {                                                            \
+       public:                                                                                                   \
+        NAME(sptr<Box> box, sptr<AtomGroup> atoms, const flt dt, uint ncorrectionsteps, PARM_B200_VECS)          \
+            : DeviceCollection(box, atoms, dt, interactions, trackers, constraints) {                            \
+            flt p[2] = {dt, (flt)ncorrectionsteps};                                                              \
+            make(TYPE, p, 2);                                                                                    \
+        }                                                                                                        \
+        NAME(sptr<Box> box, sptr<AtomGroup> atoms, const flt dt, PARM_B200_VECS)                                 \
+            : DeviceCollection(box, atoms, dt, interactions, trackers, constraints) {                            \
+            flt p[2] = {dt, 1.0};                                                                                \
+            make(TYPE, p, 2);                                                                                    \
+        }                                                                                                        \
+    }
+PARM_B200_GEAR(CollectionGear4A, PARM_INTEG_GEAR4A);  // collection.hpp:639-671, collection.cpp:1324-1364
+PARM_B200_GEAR(CollectionGear5A, PARM_INTEG_GEAR5A);  // collection.hpp:673-709, collection.cpp:1366-1407
+PARM_B200_GEAR(CollectionGear6A, PARM_INTEG_GEAR6A);  // collection.hpp:711-755, collection.cpp:1409-1496
+#undef PARM_B200_GEAR
+#undef PARM_B200_VECS
 
 #endif

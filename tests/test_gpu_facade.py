@@ -101,6 +101,49 @@ def test_facade_every_functor_instantiation(oracle_built, tmp_path, kind, varian
     assert (contacts, overlaps) == c.inter_contacts()
 
 
+@pytest.mark.parametrize("integ", sorted(W.INTEGRATOR_CASES), ids=[W.INTEGRATOR_CASES[k][0] for k in sorted(W.INTEGRATOR_CASES)])
+def test_facade_every_integrator(oracle_built, tmp_path, integ):
+    """examples/facade_integrators.cpp constructs each extra Collection with the reference's constructor
+    signature and steps it one timestep() at a time; trajectories against the oracle (CollectionSolHT draws its
+    own Gaussians there, so only its sanity is checked)."""
+    import __graft_entry__ as g
+    g.build()
+    nd = 2 if integ % 2 else 3
+    w = W.random_system(900, nd, W.KIND_REPULSION, seed=400 + integ, ntypes=1, frozen=0, T=0.05)
+    w["params"][:, 0] = 1.0
+    w["params"][:, 2] = 2.5
+    params = W.INTEGRATOR_CASES[integ][1]
+    w.update(integrator=integ, integ_params=params)
+    n, steps = w["x"].shape[0], 40
+    fin, fout = str(tmp_path / "in.bin"), str(tmp_path / "out.bin")
+    with open(fin, "wb") as fh:
+        fh.write(struct.pack("4i", n, integ, steps, len(params)))
+        fh.write(np.asarray(w["L"], np.float64).tobytes())
+        fh.write(struct.pack("2d", w["skin"], w["dt"]))
+        fh.write(np.asarray(params, np.float64).tobytes())
+        for k in ("x", "v", "m"):
+            fh.write(np.ascontiguousarray(w[k], np.float64).tobytes())
+        fh.write(np.ascontiguousarray(w["params"][:, 1], np.float64).tobytes())
+    r = subprocess.run([os.path.join(BIN, "facade_integrators%dd" % nd), fin, fout], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    raw = open(fout, "rb").read()
+    E, K, U, xi, lns = np.frombuffer(raw[:40], np.float64)
+    which = int(np.frombuffer(raw[40:44], np.uint32)[0])
+    x, v = np.frombuffer(raw[44:], np.float64).reshape(2, n, nd)
+    assert np.isfinite([E, K, U]).all() and np.isfinite(x).all()
+    if integ == 3:
+        return
+    c = cpu_system("port", w)
+    c.set_forces(True)
+    c.timestep(steps)
+    cx, cv, ca, cf = c.get_atoms()
+    assert which == c.which()
+    assert rel_err_vec(x - w["x"], cx - w["x"]) < 1e-8 and rel_err_vec(v, cv) < 1e-8
+    assert rel_err(E, c.energy()) < 1e-9 and rel_err(U, c.potential_energy()) < 1e-9
+    if integ == 5:
+        assert rel_err([xi, lns], c.get_scalars()) < 1e-9
+
+
 def test_unmodified_ljatoms_runs_on_the_dropin(tmp_path):
     """src/bin/LJatoms.cpp compiled, unmodified, against parm_b200/include/parm (examples/Makefile `ref`).
     It is a 5e5-step NVE run of 400 LJ atoms with random insertion; we let it run for a bounded time and

@@ -20,7 +20,10 @@ def lattice_case(integ, ndim):
     else:
         w = W.config2(nx=60, ny=60, seed=60 + integ)
         w["v"] = w["v"] * 20.0
-    w.update(integrator=integ, integ_params=W.INTEGRATOR_CASES[integ][1])
+    params = W.INTEGRATOR_CASES[integ][1]
+    if integ == 4 and ndim == 3:
+        params = (0.05,)  # explicit Euler on the LJ lattice: gamma*dt*stiffness must stay below 2 or it blows up
+    w.update(integrator=integ, integ_params=params)
     return w
 
 
