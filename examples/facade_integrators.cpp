@@ -23,7 +23,7 @@ int main(int argc, char **argv) {
     rd(fi, hdr, 4);
     const uint n = (uint)hdr[0];
     const int integ = hdr[1], steps = hdr[2], np = hdr[3];
-    double L[NDIM], skin, dt, par[4] = {0, 0, 0, 0};
+    double L[NDIM], skin, dt, par[6] = {0, 0, 0, 0, 0, 0};
     rd(fi, L, NDIM);
     rd(fi, &skin, 1);
     rd(fi, &dt, 1);
@@ -63,6 +63,16 @@ int main(int argc, char **argv) {
         case PARM_INTEG_GEAR4A: collec.reset(new CollectionGear4A(box, atomptr, dt, (uint)par[0])); break;
         case PARM_INTEG_GEAR5A: collec.reset(new CollectionGear5A(box, atomptr, dt, (uint)par[0])); break;
         case PARM_INTEG_GEAR6A: collec.reset(new CollectionGear6A(box, atomptr, dt, (uint)par[0])); break;
+        case PARM_INTEG_NLCG: {  // par = (P0, kappa, kmax, secmax, seceps), then packmin.py:73-76
+            CollectionNLCG *cg = new CollectionNLCG(obox, atomptr, dt, par[0], vector<sptr<Interaction> >(),
+                                                    vector<sptr<StateTracker> >(), vector<sptr<Constraint> >(), par[1], par[2],
+                                                    (uint)par[3], par[4]);
+            collec.reset(cg);
+            cg->set_max_alpha(2.0);
+            cg->set_max_dx(10.0);
+            cg->set_max_step(1e-3);
+            break;
+        }
         default: fprintf(stderr, "facade_integrators: type %d not handled here\n", integ); return 2;
     }
     collec->add_tracker(nl);
@@ -73,6 +83,10 @@ int main(int argc, char **argv) {
     if (nh) {
         out[3] = nh->get_xi();
         out[4] = nh->get_lns();
+    }
+    if (integ == PARM_INTEG_NLCG) {  // report the box the minimiser arrived at
+        out[3] = obox->V();
+        out[4] = obox->L();
     }
     uint32_t which = nl->which();
     vector<double> xo(n * NDIM), vo(n * NDIM);

@@ -205,6 +205,39 @@ int parm_sol_create(parm_ctx *ctx, double dt, double damping, double T, uint64_t
 #define PARM_INTEG_GEAR4A 8
 #define PARM_INTEG_GEAR5A 9
 #define PARM_INTEG_GEAR6A 10
+#define PARM_INTEG_NLCG 11
+/* CollectionNLCG (collection.hpp:400-474, collection.cpp:494-854): conjugate-gradient minimisation of
+ * H = U + P0 V over the atom coordinates and kappa ln V (the packer's minimiser, pyparm/packmin.py). The box
+ * of the context changes during timestep(): read it back with parm_get_box. */
+int parm_nlcg_create(parm_ctx *ctx, double dt, double P0, double kappa, double kmax, unsigned secmax, double seceps,
+                     parm_integ **out);
+#define PARM_NLCG_DT 0        /* set_dt (calls reset())            */
+#define PARM_NLCG_P0 1        /* set_pressure_goal (calls reset()) */
+#define PARM_NLCG_KAPPA 2     /* set_kappa (calls reset())         */
+#define PARM_NLCG_ALPHAMAX 3  /* set_max_alpha                     */
+#define PARM_NLCG_AFRAC 4     /* set_max_alpha_fraction            */
+#define PARM_NLCG_DXMAX 5     /* set_max_dx                        */
+#define PARM_NLCG_STEPMAX 6   /* set_max_step                      */
+#define PARM_NLCG_MAXDV 7     /* public member maxdV               */
+#define PARM_NLCG_KMAX 8
+#define PARM_NLCG_SECMAX 9
+#define PARM_NLCG_SECEPS 10
+int parm_nlcg_set(parm_integ *integ, int which, double value);
+/* out[16]: dt, P0, kappa, alphamax, afrac, dxmax, stepmax, maxdV, Knew, k, vl, fl, al, alpha, beta|betaused.. :
+ * [0] dt [1] P0 [2] kappa [3] Knew [4] k [5] vl [6] fl [7] al [8] alpha [9] beta [10] betaused [11] dxsum
+ * [12] alphavmax [13] sec [14] kmax [15] secmax */
+int parm_nlcg_get(parm_integ *integ, double *out16);
+int parm_nlcg_set_forces(parm_integ *integ, int constraints_and_a, int setV); /* set_forces(bool, bool) :534-568 */
+int parm_nlcg_reset(parm_integ *integ);    /* :525-532 */
+int parm_nlcg_descend(parm_integ *integ);  /* :837-854 */
+#define PARM_NLCG_FDOTF 0
+#define PARM_NLCG_FDOTA 1
+#define PARM_NLCG_FDOTV 2
+#define PARM_NLCG_VDOTV 3
+#define PARM_NLCG_KINETIC 4      /* CollectionNLCG::kinetic_energy :574-588 */
+#define PARM_NLCG_PRESSURE 5     /* CollectionNLCG::pressure :590-600       */
+#define PARM_NLCG_HAMILTONIAN 6  /* :570-572                                */
+int parm_nlcg_reduce(parm_integ *integ, int what, double *out);
 int parm_integ_create(parm_ctx *ctx, int type, const double *params, int nparams, uint64_t seed, parm_integ **out);
 /* thermostat state: out[0] = xi, out[1] = lns (CollectionNoseHoover::get_xi/get_lns; GaussianT: xi) */
 int parm_integ_get_scalars(parm_integ *integ, double *out2);

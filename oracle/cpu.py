@@ -86,6 +86,14 @@ def _load(backend, ndim):
     api["make_collection"] = sig("make_collection", C.c_int, [vp, C.c_int, C.c_double, C.c_double, C.c_double])
     api["make_collection_ex"] = sig("make_collection_ex", C.c_int, [vp, C.c_int, _dp, C.c_int])
     api["get_scalars"] = sig("get_scalars", None, [vp, _dp])
+    api["nlcg_set"] = sig("nlcg_set", C.c_int, [vp, C.c_int, C.c_double])
+    api["nlcg_get"] = sig("nlcg_get", C.c_int, [vp, _dp])
+    api["nlcg_set_forces"] = sig("nlcg_set_forces", C.c_int, [vp, C.c_int, C.c_int])
+    api["nlcg_reset"] = sig("nlcg_reset", C.c_int, [vp])
+    api["nlcg_descend"] = sig("nlcg_descend", C.c_int, [vp])
+    api["nlcg_reduce"] = sig("nlcg_reduce", C.c_double, [vp, C.c_int])
+    api["get_box"] = sig("get_box", None, [vp, _dp])
+    api["set_box"] = sig("set_box", None, [vp, _dp])
     api["update_list"] = sig("update_list", C.c_int, [vp, C.c_int, C.c_int])
     api["which"] = sig("which", C.c_uint32, [vp, C.c_int])
     api["ignore"] = sig("ignore", None, [vp, C.c_int, _u32p, _u32p, C.c_uint64])
@@ -177,6 +185,38 @@ class CpuSystem:
         r = self.api["make_collection_ex"](self.h, integrator, _d(p), p.size)
         if r:
             raise ValueError("oracle make_collection failed: %d" % r)
+
+    # ---- CollectionNLCG (selectors: include/parm_b200.h PARM_NLCG_*) ----
+    def nlcg_set(self, which, value):
+        if self.api["nlcg_set"](self.h, which, float(value)):
+            raise ValueError("not a CollectionNLCG / unknown parameter")
+
+    def nlcg_get(self):
+        out = np.zeros(16)
+        if self.api["nlcg_get"](self.h, _d(out)):
+            raise ValueError("not a CollectionNLCG")
+        return out
+
+    def nlcg_set_forces(self, constraints_and_a=True, setV=True):
+        self.api["nlcg_set_forces"](self.h, int(constraints_and_a), int(setV))
+
+    def nlcg_reset(self):
+        self.api["nlcg_reset"](self.h)
+
+    def nlcg_descend(self):
+        self.api["nlcg_descend"](self.h)
+
+    def nlcg_reduce(self, what):
+        return self.api["nlcg_reduce"](self.h, what)
+
+    def get_box(self):
+        out = np.zeros(self.ndim)
+        self.api["get_box"](self.h, _d(out))
+        return out
+
+    def set_box(self, L):
+        L = np.ascontiguousarray(np.broadcast_to(np.asarray(L, dtype=np.float64), (self.ndim,)))
+        self.api["set_box"](self.h, _d(L))
 
     def get_scalars(self):
         """(xi, lns) of CollectionNoseHoover."""

@@ -72,6 +72,10 @@ typedef struct {
     double gamma, Q, xi, lns; /* Overdamped; NoseHoover / GaussianT */
     unsigned ncorrec;         /* Gear4A-6A */
     double *bs, *cs, *ds;
+    /* CollectionNLCG members, collection.hpp:409-427 */
+    double seceps, kappa, alphamax, afrac, dxmax, stepmax, kmax, P0, Knew, k, vl, fl, al;
+    double alpha, beta, betaused, dxsum, alphavmax, maxdV;
+    unsigned secmax, sec;
     double c0, c1, c2, sigmar, sigmav, corr, x11, x21, x22;
     const double *noise;
     size_t noise_len, noise_pos;
@@ -839,7 +843,7 @@ static void damped_set_constants(Sys *s) { /* CollectionDamped::set_constants, c
 
 int port_make_collection_ex(void *h, int integrator, const double *p, int np) {
     Sys *s = (Sys *)h;
-    if (integrator < 0 || integrator > 10 || np < 1) return -1;
+    if (integrator < 0 || integrator > 11 || np < 1) return -1;
     s->integrator = integrator;
     s->dt = p[0];
     s->xi = s->lns = 0;
@@ -862,6 +866,15 @@ int port_make_collection_ex(void *h, int integrator, const double *p, int np) {
     } else if (integrator == 5) {
         s->Q = p[1];
         s->desT = p[2];
+    } else if (integrator == 11) { /* CollectionNLCG ctor, collection.cpp:494-523 */
+        s->P0 = p[1];
+        s->kappa = np > 2 ? p[2] : 10.0;
+        s->kmax = np > 3 ? p[3] : 1000;
+        s->secmax = (unsigned)(np > 4 ? p[4] : 40);
+        s->seceps = np > 5 ? p[5] : 1e-20;
+        s->alphamax = 2.0; s->afrac = 0; s->dxmax = 100; s->stepmax = 1e-3;
+        s->Knew = 0; s->k = 0; s->vl = 0; s->fl = 0; s->al = 0; s->alpha = 0; s->beta = 0; s->betaused = 0;
+        s->dxsum = 0; s->alphavmax = 0; s->maxdV = 0; s->sec = 0;
     } else if (integrator >= 8) {
         s->ncorrec = (unsigned)(np > 1 ? p[1] : 1);
         free(s->bs); free(s->cs); free(s->ds);
@@ -1239,6 +1252,230 @@ static void gear_timestep(Sys *s, int order) {
     collection_update_trackers(s);
 }
 
+/* ---- CollectionNLCG, collection.cpp:525-854 ---- */
+static double box_volume(const Sys *s) { return s->D == 3 ? s->L[0] * s->L[1] * s->L[2] : s->L[0] * s->L[1]; }
+static double nlcg_length_squared(const Sys *s) { return s->D == 3 ? pow(box_volume(s), 2.0 / 3.0) : box_volume(s); }
+static double nlcg_dot(const Sys *s, const double *p, const double *q) { /* sum over mobile atoms of p_i . q_i */
+    double r = 0;
+    for (uint32_t i = 0; i < s->n; i++) {
+        if (frozen_le(s->m[i])) continue;
+        r += dotD(s->D, p + (size_t)i * s->D, q + (size_t)i * s->D);
+    }
+    return r;
+}
+static double nlcg_fdotf(const Sys *s) { return nlcg_dot(s, s->f, s->f) / nlcg_length_squared(s) + s->fl * s->fl; }
+static double nlcg_fdota(const Sys *s) { return nlcg_dot(s, s->f, s->a) / nlcg_length_squared(s) + s->fl * s->al; }
+static double nlcg_fdotv(const Sys *s) { return nlcg_dot(s, s->f, s->v) / nlcg_length_squared(s) + s->fl * s->vl; }
+static double nlcg_vdotv(const Sys *s) { return nlcg_dot(s, s->v, s->v) / nlcg_length_squared(s) + s->vl * s->vl; }
+
+static void nlcg_stepx(Sys *s, double dx) { /* :602-618 */
+    double Lfac = exp(dx * s->vl / (s->kappa * s->D));
+    for (size_t q = 0; q < (size_t)s->n * s->D; q++) {
+        s->x[q] *= Lfac;
+        s->x[q] += s->v[q] * dx;
+    }
+    for (int d = 0; d < s->D; d++) s->L[d] *= Lfac; /* OriginBox::resize(factor), box.cpp:3-6 */
+}
+
+/* Collection::set_forces_get_pressure(false), collection.cpp:181-208 */
+static double collection_set_forces_get_pressure(Sys *s) {
+    memset(s->f, 0, (size_t)s->n * s->D * 8);
+    double p = 0;
+    for (int k = 0; k < s->ninters; k++) {
+        double pk;
+        inter_loop(s, &s->inters[k], 1, &pk, NULL);
+        p += pk;
+    }
+    for (uint32_t i = 0; i < s->n; i++)
+        if (frozen_le(s->m[i]))
+            for (int d = 0; d < s->D; d++) s->a[(size_t)i * s->D + d] = 0;
+    return p;
+}
+
+static void nlcg_set_forces(Sys *s, int constraints_and_a, int setV) { /* :534-568 */
+    double V = box_volume(s);
+    if (setV) {
+        double interacP = collection_set_forces_get_pressure(s);
+        s->fl = ((interacP / s->D) - (s->P0 * V)) / s->kappa;
+        if (constraints_and_a) {
+            s->al = s->fl;
+            s->vl = s->fl;
+        }
+    } else {
+        collection_set_forces(s, 0);
+    }
+    if (constraints_and_a) {
+        for (uint32_t i = 0; i < s->n; i++)
+            for (int d = 0; d < s->D; d++) {
+                size_t q = (size_t)i * s->D + d;
+                double t = frozen_le(s->m[i]) ? 0.0 : s->f[q];
+                s->a[q] = t;
+                s->v[q] = t;
+            }
+        s->Knew = nlcg_fdota(s);
+    }
+}
+
+static void nlcg_reset(Sys *s) { /* :525-532 */
+    s->k = 0;
+    nlcg_set_forces(s, 1, 1);
+    memcpy(s->v, s->a, (size_t)s->n * s->D * 8);
+    s->vl = s->al;
+}
+
+static void nlcg_descend(Sys *s) { /* :837-854 */
+    nlcg_set_forces(s, 0, 1);
+    for (uint32_t i = 0; i < s->n; i++) {
+        if (frozen_le(s->m[i])) continue;
+        for (int d = 0; d < s->D; d++) {
+            size_t q = (size_t)i * s->D + d;
+            s->v[q] = s->f[q];
+            s->a[q] = s->f[q];
+        }
+    }
+    s->al = s->fl;
+    s->vl = s->fl;
+    nlcg_stepx(s, s->dt);
+    collection_update_trackers(s);
+}
+
+static void nlcg_timestep(Sys *s) { /* :682-835 */
+    const double dt = s->dt;
+    const int NDIM = s->D;
+    nlcg_stepx(s, dt);
+    nlcg_set_forces(s, 0, 1);
+    double eta0 = -nlcg_fdotv(s);
+    double eta;
+    nlcg_stepx(s, -dt);
+    collection_update_trackers(s);
+    s->alpha = -dt;
+    nlcg_set_forces(s, 0, 1);
+    s->dxsum = 0;
+    double vdv = nlcg_vdotv(s);
+    for (s->sec = 0; s->sec < s->secmax; s->sec++) {
+        eta = -nlcg_fdotv(s);
+        double alphafac = -eta / fabs(eta0 - eta);
+        if (fabs(eta0 - eta) <= 1e-12 * fabs(eta)) {
+            alphafac = s->alphamax > 0 ? s->alphamax : 1.1;
+            s->sec = s->sec > 0 ? s->sec * 2 - 1 : 1;
+        }
+        if (s->alphamax > 0 && alphafac > s->alphamax) alphafac = s->alphamax;
+        if (s->alphamax > 0 && alphafac < -s->alphamax) alphafac = -s->alphamax;
+        s->alpha = fabs(s->alpha) * alphafac;
+        double newdxsum = fabs(s->dxsum + s->alpha);
+        if (s->dxmax > 0 && newdxsum > s->dxmax) {
+            s->k = 0;
+            break;
+        }
+        double dVoverV = expm1(fabs(s->dxsum + s->alpha) * s->vl / (s->kappa * NDIM));
+        if (s->maxdV > 0 && dVoverV > s->maxdV) {
+            s->k = 0;
+            break;
+        }
+        s->dxsum += s->alpha;
+        nlcg_stepx(s, s->alpha);
+        nlcg_set_forces(s, 0, 1);
+        eta0 = eta;
+        if (s->alpha * s->alpha * vdv < s->seceps * s->seceps) break;
+        if ((s->sec > 1) && (s->afrac > 0) && (fabs(s->alpha) < fabs(s->dxsum)) && (fabs(s->alpha) / fabs(s->dxsum) < s->afrac)) break;
+        if (s->stepmax > 0 && s->dxsum * s->dxsum * vdv > s->stepmax * s->stepmax) {
+            s->k = 0;
+            break;
+        }
+    }
+    s->alphavmax = sqrt(s->alpha * s->alpha * vdv);
+    double Kold = s->Knew;
+    double Kmid = nlcg_fdota(s);
+    for (uint32_t i = 0; i < s->n; i++)
+        for (int d = 0; d < s->D; d++) {
+            size_t q = (size_t)i * s->D + d;
+            s->a[q] = frozen_le(s->m[i]) ? 0.0 : s->f[q];
+        }
+    s->al = s->fl;
+    s->Knew = nlcg_fdota(s);
+    s->beta = (s->Knew - Kmid) / Kold;
+    s->betaused = s->beta;
+    s->k++;
+    if (s->k >= s->kmax || isinf(s->betaused) || isnan(s->betaused) || s->betaused <= 0) {
+        s->k = 0;
+        s->betaused = 0;
+    } else if (s->betaused > 1) {
+        s->betaused = 1;
+    }
+    for (uint32_t i = 0; i < s->n; i++)
+        for (int d = 0; d < s->D; d++) {
+            size_t q = (size_t)i * s->D + d;
+            s->v[q] = frozen_le(s->m[i]) ? 0.0 : s->a[q] + s->v[q] * s->betaused;
+        }
+    s->vl = s->al + s->betaused * s->vl;
+}
+
+int port_nlcg_set(void *h, int which, double v) {
+    Sys *s = (Sys *)h;
+    if (s->integrator != 11) return -1;
+    switch (which) {
+        case 0: s->dt = v; nlcg_reset(s); break;
+        case 1: s->P0 = v; nlcg_reset(s); break;
+        case 2: s->kappa = v; nlcg_reset(s); break;
+        case 3: s->alphamax = v; break;
+        case 4: s->afrac = v; break;
+        case 5: s->dxmax = v; break;
+        case 6: s->stepmax = v; break;
+        case 7: s->maxdV = v; break;
+        case 8: s->kmax = v; break;
+        case 9: s->secmax = (unsigned)v; break;
+        case 10: s->seceps = v; break;
+        default: return -1;
+    }
+    return 0;
+}
+int port_nlcg_get(void *h, double *o) {
+    Sys *s = (Sys *)h;
+    if (s->integrator != 11) return -1;
+    o[0] = s->dt; o[1] = s->P0; o[2] = s->kappa; o[3] = s->Knew; o[4] = s->k; o[5] = s->vl; o[6] = s->fl; o[7] = s->al;
+    o[8] = s->alpha; o[9] = s->beta; o[10] = s->betaused; o[11] = s->dxsum; o[12] = s->alphavmax; o[13] = s->sec;
+    o[14] = s->kmax; o[15] = s->secmax;
+    return 0;
+}
+int port_nlcg_set_forces(void *h, int caa, int setV) { Sys *s = (Sys *)h; if (s->integrator != 11) return -1; nlcg_set_forces(s, caa, setV); return 0; }
+int port_nlcg_reset(void *h) { Sys *s = (Sys *)h; if (s->integrator != 11) return -1; nlcg_reset(s); return 0; }
+int port_nlcg_descend(void *h) { Sys *s = (Sys *)h; if (s->integrator != 11) return -1; nlcg_descend(s); return 0; }
+double port_potential_energy(void *h);
+double port_nlcg_reduce(void *h, int what) {
+    Sys *s = (Sys *)h;
+    if (s->integrator != 11) return NAN;
+    switch (what) {
+        case 0: return nlcg_fdotf(s);
+        case 1: return nlcg_fdota(s);
+        case 2: return nlcg_fdotv(s);
+        case 3: return nlcg_vdotv(s);
+        case 4: { /* kinetic_energy :574-588 */
+            double E = 0;
+            double Lfac = exp(s->vl / (s->kappa * s->D));
+            for (uint32_t i = 0; i < s->n; i++) {
+                if (frozen_le(s->m[i])) continue;
+                double w[3] = {0, 0, 0};
+                for (int d = 0; d < s->D; d++) w[d] = s->v[(size_t)i * s->D + d] + (s->x[(size_t)i * s->D + d] * Lfac);
+                E += dotD(s->D, w, w);
+            }
+            return E / 2.0;
+        }
+        case 5: { /* pressure :590-600 */
+            double E = 0;
+            for (int k = 0; k < s->ninters; k++) {
+                double p;
+                inter_loop(s, &s->inters[k], 0, &p, NULL);
+                E += p;
+            }
+            return E / box_volume(s) / (double)s->D;
+        }
+        case 6: return port_potential_energy(h) + s->P0 * box_volume(s); /* :570-572 */
+    }
+    return NAN;
+}
+void port_get_box(void *h, double *L) { Sys *s = (Sys *)h; for (int d = 0; d < s->D; d++) L[d] = s->L[d]; }
+void port_set_box(void *h, const double *L) { Sys *s = (Sys *)h; for (int d = 0; d < s->D; d++) s->L[d] = L[d]; }
+
 void port_timestep(void *h, int nsteps) {
     Sys *s = (Sys *)h;
     for (int k = 0; k < nsteps; k++) {
@@ -1254,6 +1491,7 @@ void port_timestep(void *h, int nsteps) {
             case 8: gear_timestep(s, 4); break;
             case 9: gear_timestep(s, 5); break;
             case 10: gear_timestep(s, 6); break;
+            case 11: nlcg_timestep(s); break;
         }
     }
 }
@@ -1313,6 +1551,10 @@ void port_inter_stress(void *h, int k, double *out) { Sys *s = (Sys *)h; inter_l
 
 void port_set_forces(void *h, int constraints_and_a) {
     Sys *s = (Sys *)h;
+    if (s->integrator == 11) { /* CollectionNLCG::set_forces(bool) -> set_forces(constraints_and_a, true), collection.hpp:449-451 */
+        nlcg_set_forces(s, constraints_and_a, 1);
+        return;
+    }
     if (s->integrator == 6) { /* CollectionGaussianT::set_forces(bool) -> set_forces(true, true), collection.hpp:618 */
         collection_set_forces(s, 1);
         gaussiant_set_xi(s);
@@ -1320,7 +1562,12 @@ void port_set_forces(void *h, int constraints_and_a) {
     }
     collection_set_forces(s, constraints_and_a);
 }
-double port_kinetic_energy(void *h) { double z[3] = {0, 0, 0}; return group_ke((Sys *)h, z); }
+double port_nlcg_reduce(void *h, int what);
+double port_kinetic_energy(void *h) { /* virtual: CollectionNLCG overrides it, collection.cpp:574-588 */
+    double z[3] = {0, 0, 0};
+    if (((Sys *)h)->integrator == 11) return port_nlcg_reduce(h, 4);
+    return group_ke((Sys *)h, z);
+}
 double port_potential_energy(void *h) { /* collection.cpp:98-108 */
     Sys *s = (Sys *)h;
     double E = 0;
@@ -1354,6 +1601,7 @@ double port_virial(void *h) { /* :73-80 */
     return E;
 }
 double port_pressure(void *h) { /* :85-96 */
+    if (((Sys *)h)->integrator == 11) return port_nlcg_reduce(h, 5); /* CollectionNLCG::pressure :590-600 */
     Sys *s = (Sys *)h;
     double V = port_box_V(h);
     double E = 2.0 * port_kinetic_energy(h);

@@ -394,6 +394,12 @@ int ref_make_collection_ex(void *h, int type, const double *p, int np) {
             case 8: s->collec.reset(new CollectionGear4A(b, ag, p[0], (uint)(np > 1 ? p[1] : 1))); break;
             case 9: s->collec.reset(new CollectionGear5A(b, ag, p[0], (uint)(np > 1 ? p[1] : 1))); break;
             case 10: s->collec.reset(new CollectionGear6A(b, ag, p[0], (uint)(np > 1 ? p[1] : 1))); break;
+            case 11:  // CollectionNLCG(box, atoms, dt, P0, {}, {}, {}, kappa, kmax, secmax, seceps), collection.hpp:430-437
+                s->collec.reset(new CollectionNLCG(s->box, ag, p[0], p[1], vector<sptr<Interaction> >(),
+                                                   vector<sptr<StateTracker> >(), vector<sptr<Constraint> >(),
+                                                   np > 2 ? p[2] : 10.0, np > 3 ? p[3] : 1000, (uint)(np > 4 ? p[4] : 40),
+                                                   np > 5 ? p[5] : 1e-20));
+                break;
             default: return -1;
         }
         for (size_t k = 0; k < s->nls.size(); k++) s->collec->add_tracker(boost::static_pointer_cast<StateTracker>(s->nls[k]));
@@ -421,6 +427,63 @@ void ref_get_scalars(void *h, double *out) {
         out[0] = GaussianTXi::get(*gt);
     }
 }
+
+// ---- CollectionNLCG: selectors as in include/parm_b200.h (PARM_NLCG_*) ----
+static CollectionNLCG *nlcg_of(void *h) { return dynamic_cast<CollectionNLCG *>(static_cast<Sys *>(h)->collec.get()); }
+int ref_nlcg_set(void *h, int which, double v) {
+    CollectionNLCG *c = nlcg_of(h);
+    if (!c) return -1;
+    switch (which) {
+        case 0: c->set_dt(v); break;
+        case 1: c->set_pressure_goal(v); break;
+        case 2: c->set_kappa(v); break;
+        case 3: c->set_max_alpha(v); break;
+        case 4: c->set_max_alpha_fraction(v); break;
+        case 5: c->set_max_dx(v); break;
+        case 6: c->set_max_step(v); break;
+        case 7: c->maxdV = v; break;
+        case 8: c->kmax = v; break;
+        case 9: c->secmax = (uint)v; break;
+        case 10: c->seceps = v; break;
+        default: return -1;
+    }
+    return 0;
+}
+int ref_nlcg_get(void *h, double *o) {
+    CollectionNLCG *c = nlcg_of(h);
+    if (!c) return -1;
+    o[0] = c->dt; o[1] = c->P0; o[2] = c->kappa; o[3] = c->Knew; o[4] = c->k; o[5] = c->vl; o[6] = c->fl; o[7] = c->al;
+    o[8] = c->alpha; o[9] = c->beta; o[10] = c->betaused; o[11] = c->dxsum; o[12] = c->alphavmax; o[13] = c->sec;
+    o[14] = c->kmax; o[15] = c->secmax;
+    return 0;
+}
+int ref_nlcg_set_forces(void *h, int caa, int setV) {
+    CollectionNLCG *c = nlcg_of(h);
+    if (!c) return -1;
+    c->set_forces(caa != 0, setV != 0);
+    return 0;
+}
+int ref_nlcg_reset(void *h) { CollectionNLCG *c = nlcg_of(h); if (!c) return -1; c->reset(); return 0; }
+int ref_nlcg_descend(void *h) { CollectionNLCG *c = nlcg_of(h); if (!c) return -1; c->descend(); return 0; }
+double ref_nlcg_reduce(void *h, int what) {
+    CollectionNLCG *c = nlcg_of(h);
+    if (!c) return NAN;
+    switch (what) {
+        case 0: return c->fdotf();
+        case 1: return c->fdota();
+        case 2: return c->fdotv();
+        case 3: return c->vdotv();
+        case 4: return c->kinetic_energy();
+        case 5: return c->pressure();
+        case 6: return c->hamiltonian();
+    }
+    return NAN;
+}
+void ref_get_box(void *h, double *L) {
+    Vec s = static_cast<Sys *>(h)->box->box_shape();
+    for (uint d = 0; d < NDIM; d++) L[d] = s[d];
+}
+void ref_set_box(void *h, const double *L) { static_cast<Sys *>(h)->box->resize_to(vec_from(L)); }  // box.cpp:21-25
 
 const char *ref_last_error(void *h) { return static_cast<Sys *>(h)->err.c_str(); }
 

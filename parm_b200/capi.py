@@ -14,7 +14,7 @@ OK, ERR_INVALID, ERR_RUNTIME, ERR_CUDA, ERR_UNSUPPORTED = 0, 1, 2, 3, 4
 X, V, A, F, M, ALL = 1, 2, 4, 8, 16, 31
 RED_MASS, RED_MOMENTUM, RED_KE, RED_COM, RED_NDOF, RED_COMFORCE = range(6)
 (INTEG_VERLET, INTEG_SOL, INTEG_DAMPED, INTEG_SOLHT, INTEG_OVERDAMPED, INTEG_NOSEHOOVER, INTEG_GAUSSIANT, INTEG_GEAR3A,
- INTEG_GEAR4A, INTEG_GEAR5A, INTEG_GEAR6A) = range(11)
+ INTEG_GEAR4A, INTEG_GEAR5A, INTEG_GEAR6A, INTEG_NLCG) = range(12)
 PAIR_LJREPULSE, PAIR_REPULSION, PAIR_LJATTRACTREPULSE, PAIR_LJCUT = range(4)
 (PAIR_LJATTRACTCUT, PAIR_LJATTRACTFIXEDREPULSE, PAIR_EISMCLACHLAN, PAIR_LJISH, PAIR_LJATTRACTREPULSESIGS,
  PAIR_REPULSIONDRAG, PAIR_LOISOHERN, PAIR_LOISLIN, PAIR_LOISOHERNMIN, PAIR_LOISLINMIN) = range(4, 14)
@@ -71,6 +71,13 @@ SIGNATURES = {
     "parm_verlet_create": (C.c_int, [vp, C.c_double, vpp]),
     "parm_sol_create": (C.c_int, [vp, C.c_double, C.c_double, C.c_double, C.c_uint64, vpp]),
     "parm_integ_create": (C.c_int, [vp, C.c_int, dp, C.c_int, C.c_uint64, vpp]),
+    "parm_nlcg_create": (C.c_int, [vp, C.c_double, C.c_double, C.c_double, C.c_double, C.c_uint, C.c_double, vpp]),
+    "parm_nlcg_set": (C.c_int, [vp, C.c_int, C.c_double]),
+    "parm_nlcg_get": (C.c_int, [vp, dp]),
+    "parm_nlcg_set_forces": (C.c_int, [vp, C.c_int, C.c_int]),
+    "parm_nlcg_reset": (C.c_int, [vp]),
+    "parm_nlcg_descend": (C.c_int, [vp]),
+    "parm_nlcg_reduce": (C.c_int, [vp, C.c_int, dp]),
     "parm_integ_get_scalars": (C.c_int, [vp, dp]),
     "parm_integ_reset_bath": (C.c_int, [vp]),
     "parm_integ_set_param": (C.c_int, [vp, C.c_int, C.c_double]),

@@ -249,6 +249,7 @@ extern "C" int parm_integ_destroy(parm_integ *g) {
     cudaStreamSynchronize(g->ctx->stream);
     if (g->d_noise) cudaFree(g->d_noise);
     if (g->d_mobile_rank) cudaFree(g->d_mobile_rank);
+    if (g->nlcg) parm_nlcg_free(g);
     if (g->d_gear) cudaFree(g->d_gear);
     if (g->d_scal) cudaFree(g->d_scal);
     if (g->d_xpart) cudaFree(g->d_xpart);
@@ -315,6 +316,7 @@ static int base_set_forces(parm_integ *g, int constraints_and_a) {
 }
 
 extern "C" int parm_integ_set_forces(parm_integ *g, int constraints_and_a) {
+    if (g->type == PARM_INTEG_NLCG) return parm_nlcg_set_forces(g, constraints_and_a, 1); // collection.hpp:449-451
     if (g->type == PARM_INTEG_GAUSSIANT) { // CollectionGaussianT::set_forces(bool) -> set_forces(true, true), collection.hpp:618
         PTRY(base_set_forces(g, 1));
         return parm_integ_extra_after_set_forces(g);
@@ -472,6 +474,13 @@ extern "C" int parm_integ_timestep(parm_integ *g, int nsteps) {
     for (size_t k = 1; k < g->trackers.size(); k++)
         if (g->trackers[k] != g->trackers[0]) { parm_set_error("one NeighborList per Collection is supported"); return PARM_ERR_UNSUPPORTED; }
     if (nsteps <= 0) return 0;
+    if (g->type == PARM_INTEG_NLCG) { // host-driven secant / conjugate-gradient loop (nlcg.cu)
+        for (int s = 0; s < nsteps; s++) {
+            PTRY(parm_nlcg_timestep(g));
+            g->steps++;
+        }
+        return 0;
+    }
     if (g->type == PARM_INTEG_NOSEHOOVER) { // Collection::degrees_of_freedom(), collection.cpp:116-133
         double out[4];
         PTRY(parm_reduce(c, PARM_RED_NDOF, nullptr, out));

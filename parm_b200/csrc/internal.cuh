@@ -211,6 +211,7 @@ struct parm_integ {
     double *d_gear;
     struct IntegScalars *d_scal;
     double *d_xpart; // per-block partials of the thermostat reductions
+    struct NlcgState *nlcg; // CollectionNLCG (nlcg.cu)
     double dt, damping, force_mag, desT;
     double c0, c1, c2, sigmar, sigmav, corr, x11, x21, x22;
     uint64_t seed;
@@ -233,6 +234,18 @@ static inline uint32_t parm_owned(const parm_ctx *c) { return c->sh.on ? c->sh.n
 struct IntegScalars {
     double xi, lns, Kt, ytov;
 };
+
+// CollectionNLCG members (collection.hpp:409-427)
+struct NlcgState {
+    double seceps;
+    unsigned secmax;
+    double kappa, alphamax, afrac, dxmax, stepmax, kmax, P0;
+    double Knew, k, vl, fl, al;
+    double alpha, beta, betaused, dxsum, alphavmax, maxdV;
+    unsigned sec;
+};
+int parm_nlcg_timestep(parm_integ *g); // nlcg.cu
+void parm_nlcg_free(parm_integ *g);
 
 // ---- cross-TU host functions ----
 int parm_integ_extra_enqueue(parm_integ *g, uint64_t step, const int *abort_flag, int slot); // integ_extra.cu

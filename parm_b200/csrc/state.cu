@@ -138,8 +138,7 @@ extern "C" int parm_set_box(parm_ctx *c, const double *L) {
         c->box.invL[k] = 1.0 / l;
         c->box.halfL[k] = l * 0.5;
     }
-    c->box_set = true;
-    for (parm_nlist *nl : c->nlists) nl->ignorechanged = true; // geometry changed: cells are stale
+    c->box_set = true; // (the reference keeps its pair list across a resize: the grid is re-derived at every rebuild)
     return 0;
 }
 

@@ -86,6 +86,14 @@ class OriginBox : public Box {
         ctxs.push_back(c);
         parm_b200::check(parm_set_box(c, boxsize.data()));
     }
+    // the device changed the box of context c (CollectionNLCG::stepx): refresh boxsize and the other contexts
+    void pull(parm_ctx *c) {
+        flt L[3] = {0, 0, 0};
+        parm_b200::check(parm_get_box(c, L));
+        for (uint i = 0; i < NDIM; i++) boxsize[i] = L[i];
+        for (size_t k = 0; k < ctxs.size(); k++)
+            if (ctxs[k] != c) parm_b200::check(parm_set_box(ctxs[k], boxsize.data()));
+    }
     void detach(parm_ctx *c) {
         for (size_t k = 0; k < ctxs.size(); k++)
             if (ctxs[k] == c) { ctxs.erase(ctxs.begin() + k); return; }

@@ -307,6 +307,78 @@ class CollectionGear3A : public parm_b200::DeviceCollection {  // collection.hpp
     }
 };
 
+class CollectionNLCG : public Collection {  // collection.hpp:400-474, collection.cpp:494-854
+   protected:
+    sptr<OriginBox> obox;
+    flt state(int k) {
+        flt o[16];
+        parm_b200::check(parm_nlcg_get(integ, o));
+        return o[k];
+    }
+    void set(int which, flt v) {
+        ready();
+        parm_b200::check(parm_nlcg_set(integ, which, v));
+    }
+    flt reduce(int what) {
+        ready(false);
+        flt r = 0;
+        parm_b200::check(parm_nlcg_reduce(integ, what, &r));
+        return r;
+    }
+
+   public:
+    CollectionNLCG(sptr<OriginBox> box, sptr<AtomGroup> atoms, const flt dt, const flt P0,
+                   vector<sptr<Interaction> > interactions = vector<sptr<Interaction> >(),
+                   vector<sptr<StateTracker> > trackers = vector<sptr<StateTracker> >(),
+                   vector<sptr<Constraint> > constraints = vector<sptr<Constraint> >(), const flt kappa = 10.0,
+                   const flt kmax = 1000, const uint secmax = 40, const flt seceps = 1e-20)
+        : Collection(boost::static_pointer_cast<Box>(box), atoms, interactions, trackers, constraints), obox(box) {
+        parm_b200::check(parm_nlcg_create(av->context(), dt, P0, kappa, kmax, secmax, seceps, &integ));
+        register_all(true);
+    }
+    flt kinetic_energy() { return reduce(PARM_NLCG_KINETIC); }  // Note: masses are ignored
+    flt pressure() { return reduce(PARM_NLCG_PRESSURE); }
+    flt hamiltonian() { return reduce(PARM_NLCG_HAMILTONIAN); }
+    flt fdota() { return reduce(PARM_NLCG_FDOTA); }
+    flt fdotf() { return reduce(PARM_NLCG_FDOTF); }
+    flt fdotv() { return reduce(PARM_NLCG_FDOTV); }
+    flt vdotv() { return reduce(PARM_NLCG_VDOTV); }
+    void set_forces(bool constraints_and_a = true) { set_forces(constraints_and_a, true); }
+    void set_forces(bool constraints_and_a, bool setV) {
+        ready();
+        parm_b200::check(parm_nlcg_set_forces(integ, constraints_and_a ? 1 : 0, setV ? 1 : 0));
+    }
+    void timestep() {
+        ready();
+        parm_b200::check(parm_integ_timestep(integ, 1));
+        obox->pull(av->context());
+    }
+    void descend() {
+        ready();
+        parm_b200::check(parm_nlcg_descend(integ));
+        obox->pull(av->context());
+    }
+    void reset() {
+        ready();
+        parm_b200::check(parm_nlcg_reset(integ));
+    }
+    void set_dt(flt newdt) { set(PARM_NLCG_DT, newdt); }
+    void set_pressure_goal(flt P) { set(PARM_NLCG_P0, P); }
+    flt get_pressure_goal() { return state(1); }
+    void set_kappa(flt k) { set(PARM_NLCG_KAPPA, k); }
+    void set_max_alpha(flt a) { set(PARM_NLCG_ALPHAMAX, a); }
+    void set_max_alpha_fraction(flt a) { set(PARM_NLCG_AFRAC, a); }
+    void set_max_dx(flt d) { set(PARM_NLCG_DXMAX, d); }
+    void set_max_step(flt m) { set(PARM_NLCG_STEPMAX, m); }
+    // the reference's public tracking members, as accessors
+    flt get_alpha() { return state(8); }
+    flt get_beta() { return state(9); }
+    flt get_betaused() { return state(10); }
+    flt get_dxsum() { return state(11); }
+    flt get_alphavmax() { return state(12); }
+    uint get_sec() { return (uint)state(13); }
+};
+
 #define PARM_B200_GEAR(NAME, TYPE)                                                                               \
     class NAME : public parm_b200::DeviceCollection {                                                            \
        public:                                                                                                   \

@@ -68,6 +68,24 @@ class OriginBox:
             call("parm_set_box", a._h, _dptr(self.boxsize))
         return self.V()
 
+    def resize(self, factor):  # box.cpp:3-6
+        return self.resize_to(self.boxsize * factor)
+
+    def resize_to_V(self, newV):  # box.cpp:34-38
+        return self.resize((newV / self.V()) ** (1.0 / self.ndim))
+
+    def resize_to_L(self, newL):  # box.cpp:46-50
+        return self.resize(newL / self.V() ** (1.0 / self.ndim))
+
+    def _pull(self, atoms):
+        """The device changed the box (CollectionNLCG::stepx): refresh this object and the other contexts."""
+        L = np.zeros(self.ndim)
+        call("parm_get_box", atoms._h, _dptr(L))
+        self.boxsize = L
+        for a in self._ctxs:
+            if a is not atoms:
+                call("parm_set_box", a._h, _dptr(self.boxsize))
+
     def diff(self, r1, r2, atoms=None):
         """OriginBox::diff evaluated ON THE DEVICE (box.hpp:103). r1, r2: (..., ndim)."""
         if atoms is None:
@@ -922,12 +940,105 @@ class CollectionGear6A(_GearN):  # collection.hpp:711-755
     integ_type = capi.INTEG_GEAR6A
 
 
+class CollectionNLCG(Collection):
+    """CollectionNLCG (collection.hpp:400-474): the packer's conjugate-gradient minimiser of U + P0 V."""
+
+    def __init__(self, box, atoms, dt, P0, interactions=(), trackers=(), constraints=(), kappa=10.0, kmax=1000, secmax=40,
+                 seceps=1e-20):
+        Collection.__init__(self, box, atoms, interactions, trackers, constraints)
+        h = C.c_void_p()
+        call("parm_nlcg_create", atoms._h, float(dt), float(P0), float(kappa), float(kmax), int(secmax), float(seceps), C.byref(h))
+        self._h = h
+        self.dt = float(dt)
+        _construct(self)
+
+    def _state(self):
+        out = np.zeros(16)
+        call("parm_nlcg_get", self._h, _dptr(out))
+        return out
+
+    def _set(self, which, value):
+        self._ready()
+        call("parm_nlcg_set", self._h, which, float(value))
+
+    def _reduce(self, what):
+        self._ready(False)
+        out = C.c_double(0)
+        call("parm_nlcg_reduce", self._h, what, C.byref(out))
+        return out.value
+
+    def timestep(self, nsteps=1):
+        Collection.timestep(self, nsteps)
+        self.box._pull(self.atoms)
+
+    def set_forces(self, constraints_and_a=True, setV=True):
+        self._ready()
+        call("parm_nlcg_set_forces", self._h, int(constraints_and_a), int(setV))
+
+    def reset(self):
+        self._ready()
+        call("parm_nlcg_reset", self._h)
+
+    def descend(self):
+        self._ready()
+        call("parm_nlcg_descend", self._h)
+        self.box._pull(self.atoms)
+
+    def set_dt(self, dt):
+        self.dt = float(dt)
+        self._set(0, dt)
+
+    def set_pressure_goal(self, P):
+        self._set(1, P)
+
+    def get_pressure_goal(self):
+        return float(self._state()[1])
+
+    P0 = property(get_pressure_goal)
+
+    def set_kappa(self, k):
+        self._set(2, k)
+
+    def set_max_alpha(self, a):
+        self._set(3, a)
+
+    def set_max_alpha_fraction(self, a):
+        self._set(4, a)
+
+    def set_max_dx(self, d):
+        self._set(5, d)
+
+    def set_max_step(self, m):
+        self._set(6, m)
+
+    def fdotf(self):
+        return self._reduce(0)
+
+    def fdota(self):
+        return self._reduce(1)
+
+    def fdotv(self):
+        return self._reduce(2)
+
+    def vdotv(self):
+        return self._reduce(3)
+
+    def kinetic_energy(self):
+        return self._reduce(4)
+
+    def pressure(self):
+        return self._reduce(5)
+
+    def hamiltonian(self):
+        return self._reduce(6)
+
+
 INTEGRATOR_CLASSES = {
     capi.INTEG_VERLET: CollectionVerlet, capi.INTEG_SOL: CollectionSol, capi.INTEG_DAMPED: CollectionDamped,
     capi.INTEG_SOLHT: CollectionSolHT, capi.INTEG_OVERDAMPED: CollectionOverdamped,
     capi.INTEG_NOSEHOOVER: CollectionNoseHoover, capi.INTEG_GAUSSIANT: CollectionGaussianT,
     capi.INTEG_GEAR3A: CollectionGear3A, capi.INTEG_GEAR4A: CollectionGear4A, capi.INTEG_GEAR5A: CollectionGear5A,
-    capi.INTEG_GEAR6A: CollectionGear6A}
+    capi.INTEG_GEAR6A: CollectionGear6A, capi.INTEG_NLCG: CollectionNLCG}
 
 
 def _construct(collec):
@@ -964,6 +1075,9 @@ def from_workload(w, device=0, collection=True):
             collec = CollectionVerlet(box, atoms, w["dt"])
         elif integ == 1:
             collec = CollectionSol(box, atoms, w["dt"], w["damping"], w["T"], seed=w.get("seed", 0))
+        elif integ == capi.INTEG_NLCG:  # integ_params: (P0, kappa, kmax, secmax, seceps)
+            P0, kappa, kmax, secmax, seceps = w["integ_params"]
+            collec = CollectionNLCG(box, atoms, w["dt"], P0, kappa=kappa, kmax=kmax, secmax=int(secmax), seceps=seceps)
         else:  # w["integ_params"]: the constructor arguments after dt
             collec = INTEGRATOR_CLASSES[integ](box, atoms, w["dt"], *w.get("integ_params", ()))
         collec.add_tracker(nl)

@@ -263,3 +263,18 @@ def integrator_system(integ, ndim=3, n=150, seed=0, kind=None):
     w = random_system(n, ndim, kind, seed=seed, ntypes=2, frozen=(2 if integ in (2, 3, 4) else 0), T=0.5)
     w.update(integrator=integ, integ_params=params, name="integ_%s_%dd" % (name, ndim))
     return w
+
+
+def packer_system(ndim=3, n=200, seed=0, phi0=0.5, P0=1e-3):
+    """pyparm/packmin.py:60-80: bidisperse (1 : 1.4) harmonic spheres dropped at random in a box of packing
+    fraction phi0, masses sigma^ndim, NeighborList skin 0.4, CollectionNLCG(dt=0.1, P0, kappa=10, kmax=1000,
+    secmax=40, seceps=1e-20)."""
+    rng = np.random.default_rng(seed)
+    sig = np.where(np.arange(n) < n // 2, 1.0, 1.4)
+    Vs = (sig ** ndim).sum() * np.pi / (2 * ndim)
+    L = (Vs / phi0) ** (1.0 / ndim)
+    x = rng.random((n, ndim)) * L
+    p = np.stack([np.ones(n), sig, np.full(n, 2.0)], axis=1)
+    return dict(ndim=ndim, L=np.full(ndim, L), x=x, v=np.zeros((n, ndim)), m=sig ** ndim, kind=KIND_REPULSION, params=p,
+                types=np.zeros(n, np.uint32), eps_table=np.ones((1, 1)), skin=0.4, dt=0.1, integrator=11,
+                integ_params=(P0, 10.0, 1000, 40, 1e-20), name="packer_%dd_%d" % (ndim, n))

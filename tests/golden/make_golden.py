@@ -47,7 +47,9 @@ def record(w, steps=40, noise=None):
     x, v, acc, ff = s.get_atoms()
     out.update(steps=np.asarray(steps), x_end=x, v_end=v, a_end=acc, f_end=ff, which_end=np.asarray(s.which()),
                E_end=np.asarray(s.energy()), K_end=np.asarray(s.kinetic_energy()), P_end=np.asarray(s.pressure()),
-               T_end=np.asarray(s.temp()), scalars_end=s.get_scalars())
+               T_end=np.asarray(s.temp()), scalars_end=s.get_scalars(), L_end=s.get_box())
+    if int(w.get("integrator", 0)) == 11:
+        out["nlcg_end"] = s.nlcg_get()
     a, b = s.pairs()
     out["pairs_first_end"], out["pairs_last_end"] = a, b
     return out
@@ -87,6 +89,9 @@ def main():
         if integ == 3:
             z = np.random.default_rng(integ).standard_normal((30, int((w["m"] > 0).sum()), ndim))
         cases["integ_%s_%dd" % (name, ndim)] = record(w, steps=30, noise=z)
+    # CollectionNLCG, set up like pyparm/packmin.py
+    for ndim in (2, 3):
+        cases["nlcg_packer_%dd" % ndim] = record(W.packer_system(ndim=ndim, n=120, seed=30 + ndim), steps=40)
     for name, d in cases.items():
         np.savez_compressed(os.path.join(HERE, name + ".npz"), **d)
         print(name, "pairs", len(d["pairs_first"]), "E", float(d["energy"]), "which_end", int(d["which_end"]))

@@ -144,6 +144,41 @@ def test_facade_every_integrator(oracle_built, tmp_path, integ):
         assert rel_err([xi, lns], c.get_scalars()) < 1e-9
 
 
+def test_facade_nlcg_packer(oracle_built, tmp_path):
+    """CollectionNLCG through the C++ facade, set up like pyparm/packmin.py:60-80 (Hertzian exponent 2.5 here)."""
+    import __graft_entry__ as g
+    g.build()
+    w = W.packer_system(ndim=3, n=500, seed=12)
+    w["params"][:, 2] = 2.5
+    n, steps = w["x"].shape[0], 25
+    params = w["integ_params"]
+    fin, fout = str(tmp_path / "in.bin"), str(tmp_path / "out.bin")
+    with open(fin, "wb") as fh:
+        fh.write(struct.pack("4i", n, 11, steps, len(params)))
+        fh.write(np.asarray(w["L"], np.float64).tobytes())
+        fh.write(struct.pack("2d", w["skin"], w["dt"]))
+        fh.write(np.asarray(params, np.float64).tobytes())
+        for k in ("x", "v", "m"):
+            fh.write(np.ascontiguousarray(w[k], np.float64).tobytes())
+        fh.write(np.ascontiguousarray(w["params"][:, 1], np.float64).tobytes())
+    r = subprocess.run([os.path.join(BIN, "facade_integrators3d"), fin, fout], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    raw = open(fout, "rb").read()
+    E, K, U, V, Lbox = np.frombuffer(raw[:40], np.float64)
+    which = int(np.frombuffer(raw[40:44], np.uint32)[0])
+    x, v = np.frombuffer(raw[44:], np.float64).reshape(2, n, 3)
+    c = cpu_system("port", w)
+    c.nlcg_set(3, 2.0)
+    c.nlcg_set(5, 10.0)
+    c.nlcg_set(6, 1e-3)
+    c.set_forces(True)
+    c.timestep(steps)
+    assert which == c.which()
+    assert rel_err(V, np.prod(c.get_box())) < 1e-9 and rel_err(Lbox, c.get_box().mean()) < 1e-9
+    assert rel_err_vec(x - w["x"], c.get_atoms()[0] - w["x"]) < 1e-7
+    assert rel_err(U, c.potential_energy()) < 1e-6 and rel_err(K, c.nlcg_reduce(4)) < 1e-6
+
+
 def test_unmodified_ljatoms_runs_on_the_dropin(tmp_path):
     """src/bin/LJatoms.cpp compiled, unmodified, against parm_b200/include/parm (examples/Makefile `ref`).
     It is a 5e5-step NVE run of 400 LJ atoms with random insertion; we let it run for a bounded time and

@@ -39,5 +39,7 @@ def test_gpu_reproduces_reference_fixture(path):
     assert rel_err(collec.kinetic_energy(), d["K_end"]) < 1e-10
     assert rel_err(collec.pressure(), d["P_end"]) < 1e-9
     assert rel_err(collec.temp(), d["T_end"]) < 1e-10
+    if "L_end" in d:
+        assert rel_err(box.box_shape(), d["L_end"]) < 1e-10
     a, b = nl.pairs()
     assert np.array_equal(a, d["pairs_first_end"]) and np.array_equal(b, d["pairs_last_end"])

@@ -128,3 +128,70 @@ def test_extra_integrators_refuse_sharded_contexts_and_bad_types():
         capi.call("parm_integ_create", atoms._h, 42, p, 2, 0, C.byref(h))
     with pytest.raises(Exception):  # CollectionDamped: dt must be positive (collection.cpp:334-336)
         sim.CollectionDamped(sim.OriginBox(np.full(3, 5.0), 3), atoms, -1.0, 0.5)
+
+
+@pytest.mark.parametrize("ndim", [2, 3])
+def test_nlcg_packer_matches_oracle(oracle_built, ndim):
+    """CollectionNLCG as pyparm/packmin.py drives it: compress bidisperse harmonic spheres towards P0. The secant
+    loop branches on dot products, so device and CPU are compared over a stretch short enough that no branch sits
+    within rounding of its threshold, then the GPU run is continued to convergence on its own."""
+    from parm_b200 import sim
+    w = W.packer_system(ndim=ndim, n=600, seed=4 + ndim)
+    be = backends(oracle_built)[-1]
+    box, atoms, inter, nl, collec = sim.from_workload(w)
+    s = cpu_system(be, w, injected=True)
+    for c in (collec, ):
+        c.set_max_alpha(2.0)
+        c.set_max_dx(10.0)
+        c.set_max_step(1e-3)
+    s.nlcg_set(3, 2.0)
+    s.nlcg_set(5, 10.0)
+    s.nlcg_set(6, 1e-3)
+    collec.set_forces(True, True)
+    s.nlcg_set_forces(True, True)
+    for what in range(7):
+        assert rel_err(collec._reduce(what), s.nlcg_reduce(what)) < 1e-10
+    steps = 40
+    for _ in range(steps):
+        collec.timestep()
+    s.timestep(steps)
+    assert rel_err(box.box_shape(), s.get_box()) < 1e-9
+    assert nl.which() == s.which()
+    x = s.get_atoms()[0]
+    assert rel_err_vec(atoms.peek("x") - w["x"], x - w["x"]) < 1e-7
+    st, so = collec._state(), s.nlcg_get()
+    assert rel_err(st[:8], so[:8]) < 1e-6
+    for what in (4, 5, 6):
+        assert rel_err(collec._reduce(what), s.nlcg_reduce(what)) < 1e-6
+    # descend() and reset() (steepest-descent restart)
+    collec.descend()
+    s.nlcg_descend()
+    collec.reset()
+    s.nlcg_reset()
+    assert rel_err(box.box_shape(), s.get_box()) < 1e-9
+    assert rel_err(collec._state()[:8], s.nlcg_get()[:8]) < 1e-6
+    # on its own: the packing approaches the goal pressure, the box shrinks
+    V0 = box.V()
+    collec.set_max_step(1e-2)
+    collec.timestep(1500)
+    assert box.V() < V0
+    assert abs(collec.pressure() / collec.P0 - 1) < 0.2
+
+
+def test_box_resize_keeps_the_pair_list(oracle_built):
+    """OriginBox::resize_to does not touch the NeighborList (box.cpp:21-25): forces use the new box, the list is
+    only rebuilt when the drift rule fires."""
+    from parm_b200 import sim
+    w = W.lj_lattice((8, 8, 8), seed=2)
+    box, atoms, inter, nl, collec = sim.from_workload(w)
+    s = cpu_system(backends(oracle_built)[-1], w, injected=True)
+    box.resize(0.97)
+    s.set_box(np.asarray(w["L"]) * 0.97)
+    collec.set_forces(True)
+    s.set_forces(True)
+    assert nl.which() == s.which() == 1
+    assert rel_err_vec(atoms.peek("f"), s.get_atoms()[3]) < 1e-10
+    collec.timestep(50)
+    s.timestep(50)
+    assert nl.which() == s.which()
+    assert rel_err(collec.energy(), s.energy()) < 1e-9

@@ -56,7 +56,9 @@ def replay(backend, w, d):
     x, v, a, ff = s.get_atoms()
     out.update(x_end=x, v_end=v, a_end=a, f_end=ff, which_end=np.asarray(s.which()), E_end=np.asarray(s.energy()),
                K_end=np.asarray(s.kinetic_energy()), P_end=np.asarray(s.pressure()), T_end=np.asarray(s.temp()),
-               scalars_end=s.get_scalars())
+               scalars_end=s.get_scalars(), L_end=s.get_box())
+    if int(w.get("integrator", 0)) == 11:
+        out["nlcg_end"] = s.nlcg_get()
     out["pairs_first_end"], out["pairs_last_end"] = s.pairs()
     return out
 
