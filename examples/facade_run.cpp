@@ -4,7 +4,9 @@
 // feed the same numbers to the CPU oracle and compare.
 //   facade_run <in.bin> <out.bin>
 // in.bin : int32 n, kind, steps; double L[NDIM], skin, dt; double x[n][NDIM], v[n][NDIM], m[n], params[n][3]
-// out.bin: double E0, K0, U0, E1, K1, U1, P1, T1; uint32 numpairs0, which1; double x[n][NDIM], v[n][NDIM], f[n][NDIM]
+// out.bin: double E0, K0, U0, E1, K1, U1, P1, T1; uint32 numpairs0, which1; double x[n][NDIM], v[n][NDIM], f[n][NDIM];
+//          then the statistics trackers registered with the collection: double rsq_count[2], r2[2][n] (lags 1 and 5),
+//          r4[n] (lag 5), isf_re[n], isf_im[n] (k = 1.5, lag 3), et_n, et_E, et_U, et_K, et_Estd
 #include <cstdio>
 #include <cstdlib>
 
@@ -81,6 +83,16 @@ int main(int argc, char **argv) {
     CollectionVerlet collec = CollectionVerlet(boost::static_pointer_cast<Box>(obox), atomptr, dt);
     collec.add_tracker(nl);
     collec.add_interaction(inter);
+    // statistics trackers on the device (constraints.hpp:260-414), registered like any StateTracker
+    vector<unsigned long> lags;
+    lags.push_back(1);
+    lags.push_back(5);
+    sptr<RsqTracker> rsq(new RsqTracker(atomptr, lags, true));
+    sptr<ISFTracker> isf(new ISFTracker(atomptr, vector<flt>(1, 1.5), vector<unsigned long>(1, 3), false));
+    sptr<EnergyTracker> et(new EnergyTracker(atomptr, vector<sptr<Interaction> >(1, inter), 2));
+    collec.add_tracker(rsq);
+    collec.add_tracker(isf);
+    collec.add_tracker(et);
     collec.set_forces(true);
     double out[8];
     out[0] = collec.energy();
@@ -110,6 +122,21 @@ int main(int argc, char **argv) {
     fwrite(xo.data(), 8, xo.size(), fo_);
     fwrite(vo.data(), 8, vo.size(), fo_);
     fwrite(fo.data(), 8, fo.size(), fo_);
+    {
+        vector<flt> cnt = rsq->counts();
+        vector<vector<flt> > r2 = rsq->r2(), r4 = rsq->r4();
+        vector<vector<vector<cmplx> > > I = isf->ISFs();
+        vector<double> re(n), im(n);
+        for (uint i = 0; i < n; i++) { re[i] = I[0][0][i].real(); im[i] = I[0][0][i].imag(); }
+        double e5[5] = {(double)et->n(), et->E(), et->U(), et->K(), et->E_std()};
+        fwrite(cnt.data(), 8, 2, fo_);
+        fwrite(r2[0].data(), 8, n, fo_);
+        fwrite(r2[1].data(), 8, n, fo_);
+        fwrite(r4[1].data(), 8, n, fo_);
+        fwrite(re.data(), 8, n, fo_);
+        fwrite(im.data(), 8, n, fo_);
+        fwrite(e5, 8, 5, fo_);
+    }
     fclose(fo_);
     printf("facade_run ok: n=%u pairs=%u E0=%.12g E1=%.12g which=%u\n", n, np0, out[0], out[3], u[1]);
     return 0;

@@ -40,7 +40,8 @@ extern "C" {
 typedef struct parm_ctx parm_ctx;     /* OriginBox + AtomVec device state */
 typedef struct parm_nlist parm_nlist; /* NeighborList */
 typedef struct parm_inter parm_inter; /* NListed<A,P> */
-typedef struct parm_integ parm_integ; /* Collection{Verlet,Sol} */
+typedef struct parm_integ parm_integ;
+typedef struct parm_tracker parm_tracker; /* Collection{Verlet,Sol} */
 
 const char *parm_b200_last_error(void);
 /* number of kernels launched by this library since load (bench.py's gpu_launches) */
@@ -244,6 +245,29 @@ int parm_integ_get_scalars(parm_integ *integ, double *out2);
 int parm_integ_reset_bath(parm_integ *integ);        /* CollectionNoseHoover::reset_bath, collection.hpp:589-592 */
 int parm_integ_set_param(parm_integ *integ, int which, double value); /* 1: Q (set_Q), 2: T, 3: damping, 4: gamma */
 int parm_integ_destroy(parm_integ *integ);
+
+/* ---- statistics trackers: accumulators in device memory, read on demand ---- */
+/* RsqTracker(atoms, ns, usecom) constraints.hpp:342-368: per-atom <dx_j^2>, <dx_j^4>, <|dr|^4> over lags of ns[k] steps */
+int parm_rsq_create(parm_ctx *ctx, const uint64_t *ns, int nns, int usecom, parm_tracker **out);
+/* ISFTracker(atoms, ks, ns, usecom) constraints.hpp:393-414: per-atom, per-axis sums of exp(i k dx_j) */
+int parm_isf_create(parm_ctx *ctx, const double *ks, int nks, const uint64_t *ns, int nns, int usecom, parm_tracker **out);
+/* EnergyTracker(atoms, interactions, n_skip) constraints.hpp:260-316 */
+int parm_energy_tracker_create(parm_ctx *ctx, parm_inter **inters, int ninters, unsigned n_skip, parm_tracker **out);
+int parm_tracker_destroy(parm_tracker *t);
+int parm_tracker_update(parm_tracker *t);  /* StateTracker::update(Box&) */
+int parm_tracker_reset(parm_tracker *t);   /* reset() */
+int parm_tracker_counts(parm_tracker *t, uint64_t *counts, int cap);  /* counts() per lag */
+/* xyz2(), xyz4() (n x NDIM row-major) and r4() (n) of lag `single`, divided by its count; pointers may be NULL */
+int parm_rsq_read(parm_tracker *t, int single, double *xyz2, double *xyz4, double *r4);
+/* ISFxyz() of lag `single`: out[nks][n][NDIM][2] = (re, im) */
+int parm_isf_read(parm_tracker *t, int single, double *out);
+/* out[8] = N, Es, Us, Ks, Esq, Usq, Ksq, U0 (E() = Es/N, E_std() = sqrt(Esq/N - Es*Es/N/N) ...) */
+int parm_energy_tracker_read(parm_tracker *t, double *out8);
+int parm_energy_tracker_set_u0(parm_tracker *t, int from_box, double U0);  /* set_U0(flt) / set_U0(Box&) */
+/* Collection::add_tracker / constructor vector for these trackers (collection.hpp:117-120): they are updated at
+ * the end of every timestep(), after the NeighborList, without a host synchronisation */
+int parm_integ_add_stat_tracker(parm_integ *integ, parm_tracker *t);
+int parm_integ_register_stat_tracker(parm_integ *integ, parm_tracker *t);
 /* add_interaction / add_tracker (collection.hpp:113-120): append, then update_trackers() */
 int parm_integ_add_interaction(parm_integ *integ, parm_inter *inter);
 int parm_integ_add_tracker(parm_integ *integ, parm_nlist *nl);

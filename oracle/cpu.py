@@ -94,6 +94,17 @@ def _load(backend, ndim):
     api["nlcg_reduce"] = sig("nlcg_reduce", C.c_double, [vp, C.c_int])
     api["get_box"] = sig("get_box", None, [vp, _dp])
     api["set_box"] = sig("set_box", None, [vp, _dp])
+    ullp = C.POINTER(C.c_ulonglong)
+    api["add_rsq_tracker"] = sig("add_rsq_tracker", C.c_int, [vp, ullp, C.c_int, C.c_int])
+    api["add_isf_tracker"] = sig("add_isf_tracker", C.c_int, [vp, _dp, C.c_int, ullp, C.c_int, C.c_int])
+    api["add_energy_tracker"] = sig("add_energy_tracker", C.c_int, [vp, C.c_uint])
+    api["tracker_update"] = sig("tracker_update", None, [vp, C.c_int])
+    api["tracker_reset"] = sig("tracker_reset", None, [vp, C.c_int])
+    api["tracker_counts"] = sig("tracker_counts", None, [vp, C.c_int, ullp, C.c_int])
+    api["rsq_read"] = sig("rsq_read", None, [vp, C.c_int, C.c_int, _dp, _dp, _dp])
+    api["isf_read"] = sig("isf_read", None, [vp, C.c_int, C.c_int, _dp])
+    api["energy_tracker_read"] = sig("energy_tracker_read", None, [vp, C.c_int, _dp])
+    api["energy_tracker_set_U0"] = sig("energy_tracker_set_U0", None, [vp, C.c_int, C.c_int, C.c_double])
     api["update_list"] = sig("update_list", C.c_int, [vp, C.c_int, C.c_int])
     api["which"] = sig("which", C.c_uint32, [vp, C.c_int])
     api["ignore"] = sig("ignore", None, [vp, C.c_int, _u32p, _u32p, C.c_uint64])
@@ -217,6 +228,59 @@ class CpuSystem:
     def set_box(self, L):
         L = np.ascontiguousarray(np.broadcast_to(np.asarray(L, dtype=np.float64), (self.ndim,)))
         self.api["set_box"](self.h, _d(L))
+
+    # ---- statistics trackers (constraints.hpp:260-414); added to the collection like add_tracker() ----
+    def add_rsq_tracker(self, ns, usecom=True):
+        ns = np.ascontiguousarray(ns, dtype=np.uint64)
+        self._stat_meta = getattr(self, "_stat_meta", {})
+        t = self.api["add_rsq_tracker"](self.h, ns.ctypes.data_as(C.POINTER(C.c_ulonglong)), ns.size, int(usecom))
+        self._stat_meta[t] = (len(ns), 0)
+        return t
+
+    def add_isf_tracker(self, ks, ns, usecom=False):
+        ns = np.ascontiguousarray(ns, dtype=np.uint64)
+        ks = np.ascontiguousarray(ks, dtype=np.float64)
+        self._stat_meta = getattr(self, "_stat_meta", {})
+        t = self.api["add_isf_tracker"](self.h, _d(ks), ks.size, ns.ctypes.data_as(C.POINTER(C.c_ulonglong)), ns.size, int(usecom))
+        self._stat_meta[t] = (len(ns), len(ks))
+        return t
+
+    def add_energy_tracker(self, n_skip=1):
+        return self.api["add_energy_tracker"](self.h, int(n_skip))
+
+    def tracker_update(self, t):
+        self.api["tracker_update"](self.h, t)
+
+    def tracker_reset(self, t):
+        self.api["tracker_reset"](self.h, t)
+
+    def tracker_counts(self, t):
+        n = self._stat_meta[t][0]
+        out = (C.c_ulonglong * max(n, 1))()
+        self.api["tracker_counts"](self.h, t, out, n)
+        return [int(out[k]) for k in range(n)]
+
+    def rsq_read(self, t, single):
+        """(xyz2, xyz4, r4) means of lag `single`."""
+        a, b, c = np.zeros((self.n, self.ndim)), np.zeros((self.n, self.ndim)), np.zeros(self.n)
+        self.api["rsq_read"](self.h, t, single, _d(a), _d(b), _d(c))
+        return a, b, c
+
+    def isf_read(self, t, single):
+        """ISFxyz of lag `single` as a complex array (nks, n, ndim)."""
+        nks = self._stat_meta[t][1]
+        out = np.zeros((nks, self.n, self.ndim, 2))
+        self.api["isf_read"](self.h, t, single, _d(out))
+        return out[..., 0] + 1j * out[..., 1]
+
+    def energy_tracker_read(self, t):
+        """n(), E(), U(), K(), E_squared_mean(), U_squared_mean(), K_squared_mean(), get_U0()."""
+        out = np.zeros(8)
+        self.api["energy_tracker_read"](self.h, t, _d(out))
+        return out
+
+    def energy_tracker_set_U0(self, t, U0=None):
+        self.api["energy_tracker_set_U0"](self.h, t, int(U0 is None), 0.0 if U0 is None else float(U0))
 
     def get_scalars(self):
         """(xi, lns) of CollectionNoseHoover."""

@@ -58,7 +58,20 @@ typedef struct {
     size_t nignored;
 } NList;
 
+typedef struct { /* RsqTracker / ISFTracker / EnergyTracker, constraints.hpp:260-414 */
+    int kind; /* 0 Rsq, 1 ISF, 2 Energy */
+    int usecom, nskips, nks;
+    unsigned long long *skips, *counts, curt;
+    double *ks;
+    double **past; /* per lag: n x D */
+    double **acc;  /* per lag: Rsq xyz2 (n x D), xyz4 (n x D), r4 (n); ISF nks x n x D x 2 */
+    unsigned n_skip, n_skipped, N;
+    double U0, Es, Us, Ks, Esq, Usq, Ksq;
+} Stat;
+
 typedef struct {
+    Stat *stats;
+    int nstats;
     int D;
     uint32_t n;
     double L[3];
@@ -126,6 +139,12 @@ void port_sys_destroy(void *h) {
         NList *l = &s->nls[k];
         free(l->member); free(l->ids); free(l->diam); free(l->lastlocs); free(l->first); free(l->last); free(l->ignored);
     }
+    for (int k = 0; k < s->nstats; k++) {
+        Stat *t = &s->stats[k];
+        for (int q = 0; q < t->nskips; q++) { free(t->past[q]); free(t->acc[q]); }
+        free(t->past); free(t->acc); free(t->skips); free(t->counts); free(t->ks);
+    }
+    free(s->stats);
     free(s->inters); free(s->nls);
     free(s->x); free(s->v); free(s->a); free(s->f); free(s->m);
     free(s->bs); free(s->cs); free(s->ds);
@@ -786,8 +805,11 @@ static double group_ke(const Sys *s, const double *v0) {
 }
 
 /* Collection::update_trackers, collection.cpp:45-50 -> NeighborList::update, trackers.hpp:173-176 */
+static void stat_update(Sys *s, Stat *t);
 static void collection_update_trackers(Sys *s) {
     for (int k = 0; k < s->nnls; k++) nl_update_list(s, &s->nls[k], 0);
+    if (s->integrator >= 0) /* the statistics trackers are add_tracker()ed after the lists */
+        for (int k = 0; k < s->nstats; k++) stat_update(s, &s->stats[k]);
 }
 
 /* Collection::set_forces, collection.cpp:159-179 */
@@ -1475,6 +1497,192 @@ double port_nlcg_reduce(void *h, int what) {
 }
 void port_get_box(void *h, double *L) { Sys *s = (Sys *)h; for (int d = 0; d < s->D; d++) L[d] = s->L[d]; }
 void port_set_box(void *h, const double *L) { Sys *s = (Sys *)h; for (int d = 0; d < s->D; d++) s->L[d] = L[d]; }
+
+/* ---- statistics trackers ---- */
+static void group_com(const Sys *s, double *com) { /* AtomGroup::com, box.cpp:228-237 */
+    double v[3] = {0, 0, 0};
+    for (uint32_t i = 0; i < s->n; i++) {
+        if (frozen_le(s->m[i])) continue;
+        for (int d = 0; d < s->D; d++) v[d] += s->x[(size_t)i * s->D + d] * s->m[i];
+    }
+    double m = group_mass(s);
+    for (int d = 0; d < s->D; d++) com[d] = v[d] / m;
+}
+static void stat_com(const Sys *s, const Stat *t, double *com) {
+    com[0] = com[1] = com[2] = 0;
+    if (t->usecom) group_com(s, com);
+}
+static size_t stat_acc_doubles(const Sys *s, const Stat *t) {
+    return t->kind == 0 ? (size_t)(2 * s->D + 1) * s->n : (size_t)t->nks * s->n * s->D * 2;
+}
+static void stat_init_singles(Sys *s, Stat *t) { /* ctors constraints.cpp:404-416, 567-582; reset :418-427, :584-593 */
+    double com[3];
+    stat_com(s, t, com);
+    for (int k = 0; k < t->nskips; k++) {
+        memset(t->acc[k], 0, stat_acc_doubles(s, t) * 8);
+        for (uint32_t i = 0; i < s->n; i++)
+            for (int d = 0; d < s->D; d++) t->past[k][(size_t)i * s->D + d] = s->x[(size_t)i * s->D + d] - com[d];
+        t->counts[k] = 0;
+    }
+}
+static Stat *stat_new(Sys *s, int kind, const unsigned long long *ns, int nns, int usecom, const double *ks, int nks) {
+    s->stats = (Stat *)realloc(s->stats, sizeof(Stat) * (s->nstats + 1));
+    Stat *t = &s->stats[s->nstats++];
+    memset(t, 0, sizeof(Stat));
+    t->kind = kind;
+    t->usecom = usecom;
+    t->nskips = nns;
+    t->nks = nks;
+    t->skips = (unsigned long long *)calloc(nns ? nns : 1, 8);
+    t->counts = (unsigned long long *)calloc(nns ? nns : 1, 8);
+    if (nns) memcpy(t->skips, ns, 8 * (size_t)nns);
+    t->ks = (double *)calloc(nks ? nks : 1, 8);
+    if (nks) memcpy(t->ks, ks, 8 * (size_t)nks);
+    t->past = (double **)calloc(nns ? nns : 1, sizeof(double *));
+    t->acc = (double **)calloc(nns ? nns : 1, sizeof(double *));
+    for (int k = 0; k < nns; k++) {
+        t->past[k] = (double *)calloc((size_t)(s->n ? s->n : 1) * s->D, 8);
+        t->acc[k] = (double *)calloc(stat_acc_doubles(s, t) ? stat_acc_doubles(s, t) : 1, 8);
+    }
+    return t;
+}
+static int stat_added(Sys *s) { /* Collection::add_tracker -> update_trackers(), collection.hpp:117-120 */
+    if (s->integrator >= 0) collection_update_trackers(s);
+    return s->nstats - 1;
+}
+int port_add_rsq_tracker(void *h, const unsigned long long *ns, int nns, int usecom) {
+    Sys *s = (Sys *)h;
+    stat_init_singles(s, stat_new(s, 0, ns, nns, usecom, NULL, 0));
+    return stat_added(s);
+}
+int port_add_isf_tracker(void *h, const double *ks, int nks, const unsigned long long *ns, int nns, int usecom) {
+    Sys *s = (Sys *)h;
+    stat_init_singles(s, stat_new(s, 1, ns, nns, usecom, ks, nks));
+    return stat_added(s);
+}
+int port_add_energy_tracker(void *h, unsigned n_skip) {
+    Sys *s = (Sys *)h;
+    Stat *t = stat_new(s, 2, NULL, 0, 0, NULL, 0);
+    t->n_skip = n_skip > 1u ? n_skip : 1u;
+    return stat_added(s);
+}
+
+static void stat_update(Sys *s, Stat *t) {
+    const int D = s->D;
+    if (t->kind == 2) { /* EnergyTracker::update, constraints.cpp:366-393 */
+        if (t->n_skipped + 1 < t->n_skip) {
+            t->n_skipped += 1;
+            return;
+        }
+        t->n_skipped = 0;
+        double curU = 0, curK = 0;
+        for (uint32_t i = 0; i < s->n; i++) {
+            const double *v = s->v + (size_t)i * D;
+            curK += dotD(D, v, v) * s->m[i] / 2;
+        }
+        for (int k = 0; k < s->ninters; k++) curU += inter_energy(s, &s->inters[k]);
+        curU -= t->U0;
+        t->Ks += curK;
+        t->Us += curU;
+        t->Es += curK + curU;
+        t->Ksq += curK * curK;
+        t->Usq += curU * curU;
+        t->Esq += (curK + curU) * (curK + curU);
+        t->N++;
+        return;
+    }
+    t->curt++; /* RsqTracker::update :492-499, ISFTracker::update :662-669 */
+    double com[3];
+    stat_com(s, t, com);
+    for (int k = 0; k < t->nskips; k++) {
+        if (t->curt % t->skips[k] != 0) continue;
+        double *past = t->past[k], *acc = t->acc[k];
+        for (uint32_t i = 0; i < s->n; i++) {
+            double dr[3] = {0, 0, 0};
+            for (int j = 0; j < D; j++) {
+                double r = s->x[(size_t)i * D + j] - com[j];
+                dr[j] = r - past[(size_t)i * D + j];
+                past[(size_t)i * D + j] = r;
+            }
+            if (t->kind == 0) { /* RsqTracker1::update :429-455 */
+                double *xyz2 = acc, *xyz4 = acc + (size_t)D * s->n, *r4 = acc + 2 * (size_t)D * s->n;
+                double dist4 = 0;
+                for (int j = 0; j < D; j++) {
+                    double d2 = dr[j] * dr[j];
+                    double d4 = d2 * d2;
+                    dist4 += d2;
+                    xyz2[(size_t)i * D + j] += d2;
+                    xyz4[(size_t)i * D + j] += d4;
+                }
+                dist4 *= dist4;
+                r4[i] += dist4;
+            } else { /* ISFTracker1::update :595-619: += exp(i k dr_j) */
+                for (int ki = 0; ki < t->nks; ki++)
+                    for (int j = 0; j < D; j++) {
+                        double *a = acc + (((size_t)ki * s->n + i) * D + j) * 2;
+                        double arg = t->ks[ki] * dr[j];
+                        a[0] += cos(arg); /* std::exp(complex(0, y)) = polar(1, y) = (cos y, sin y) */
+                        a[1] += sin(arg);
+                    }
+            }
+        }
+        t->counts[k] += 1;
+    }
+}
+void port_tracker_update(void *h, int t) { Sys *s = (Sys *)h; stat_update(s, &s->stats[t]); }
+void port_tracker_reset(void *h, int k) {
+    Sys *s = (Sys *)h;
+    Stat *t = &s->stats[k];
+    if (t->kind == 2) { /* EnergyTracker::reset, constraints.hpp:284-293 */
+        t->n_skipped = 0; t->N = 0;
+        t->Es = t->Us = t->Ks = t->Esq = t->Usq = t->Ksq = 0;
+        return;
+    }
+    t->curt = 0;
+    stat_init_singles(s, t);
+}
+void port_tracker_counts(void *h, int k, unsigned long long *out, int cap) {
+    Stat *t = &((Sys *)h)->stats[k];
+    for (int q = 0; q < cap && q < t->nskips; q++) out[q] = t->counts[q];
+}
+void port_rsq_read(void *h, int k, int single, double *xyz2, double *xyz4, double *r4) { /* :457-481 */
+    Sys *s = (Sys *)h;
+    Stat *t = &s->stats[k];
+    const double *acc = t->acc[single];
+    const double cnt = (double)t->counts[single];
+    const size_t nd = (size_t)s->n * s->D;
+    for (size_t q = 0; q < nd; q++) {
+        if (xyz2) xyz2[q] = acc[q] / cnt;
+        if (xyz4) xyz4[q] = acc[nd + q] / cnt;
+    }
+    for (uint32_t i = 0; i < s->n && r4; i++) r4[i] = acc[2 * nd + i] / cnt;
+}
+void port_isf_read(void *h, int k, int single, double *out) { /* ISFxyz :637-650: complex / complex(count, 0) */
+    Sys *s = (Sys *)h;
+    Stat *t = &s->stats[k];
+    const double cnt = (double)t->counts[single];
+    const size_t tot = stat_acc_doubles(s, t);
+    for (size_t q = 0; q < tot; q++) out[q] = t->acc[single][q] / cnt;
+}
+void port_energy_tracker_read(void *h, int k, double *out) { /* accessors constraints.hpp:301-312 */
+    Stat *t = &((Sys *)h)->stats[k];
+    double N = (double)t->N;
+    out[0] = N;
+    out[1] = t->Es / N; out[2] = t->Us / N; out[3] = t->Ks / N;
+    out[4] = t->Esq / t->N; out[5] = t->Usq / t->N; out[6] = t->Ksq / t->N;
+    out[7] = t->U0;
+}
+void port_energy_tracker_set_U0(void *h, int k, int from_box, double U0) { /* :294-298, constraints.cpp:395-402 */
+    Sys *s = (Sys *)h;
+    Stat *t = &s->stats[k];
+    if (from_box) {
+        double curU = 0;
+        for (int q = 0; q < s->ninters; q++) curU += inter_energy(s, &s->inters[q]);
+        U0 = curU;
+    }
+    t->U0 = U0;
+    port_tracker_reset(h, k);
+}
 
 void port_timestep(void *h, int nsteps) {
     Sys *s = (Sys *)h;

@@ -184,6 +184,7 @@ class FastNListed : public NListed<A, P> {
 };
 
 struct Sys {
+    vector<sptr<StateTracker> > stats;  // RsqTracker / ISFTracker / EnergyTracker, in creation order
     sptr<OriginBox> box;
     sptr<AtomVec> atoms;
     vector<sptr<Interaction> > inters;
@@ -484,6 +485,82 @@ void ref_get_box(void *h, double *L) {
     for (uint d = 0; d < NDIM; d++) L[d] = s[d];
 }
 void ref_set_box(void *h, const double *L) { static_cast<Sys *>(h)->box->resize_to(vec_from(L)); }  // box.cpp:21-25
+
+// ---- statistics trackers (constraints.hpp:260-414); each is add_tracker()ed to the collection, which
+// calls update_trackers() once (collection.hpp:117-120) ----
+static int push_stat(Sys *s, sptr<StateTracker> t) {
+    s->stats.push_back(t);
+    if (s->collec) s->collec->add_tracker(t);
+    return (int)s->stats.size() - 1;
+}
+int ref_add_rsq_tracker(void *h, const unsigned long long *ns, int nns, int usecom) {
+    Sys *s = static_cast<Sys *>(h);
+    vector<unsigned long> v(ns, ns + nns);
+    return push_stat(s, sptr<StateTracker>(new RsqTracker(boost::static_pointer_cast<AtomGroup>(s->atoms), v, usecom != 0)));
+}
+int ref_add_isf_tracker(void *h, const double *ks, int nks, const unsigned long long *ns, int nns, int usecom) {
+    Sys *s = static_cast<Sys *>(h);
+    vector<unsigned long> v(ns, ns + nns);
+    vector<flt> kv(ks, ks + nks);
+    return push_stat(s, sptr<StateTracker>(new ISFTracker(boost::static_pointer_cast<AtomGroup>(s->atoms), kv, v, usecom != 0)));
+}
+int ref_add_energy_tracker(void *h, unsigned n_skip) {
+    Sys *s = static_cast<Sys *>(h);
+    return push_stat(s, sptr<StateTracker>(new EnergyTracker(boost::static_pointer_cast<AtomGroup>(s->atoms), s->inters, n_skip)));
+}
+void ref_tracker_update(void *h, int t) { Sys *s = static_cast<Sys *>(h); s->stats[t]->update(*s->box); }
+void ref_tracker_reset(void *h, int t) {
+    StateTracker *p = static_cast<Sys *>(h)->stats[t].get();
+    if (RsqTracker *r = dynamic_cast<RsqTracker *>(p)) r->reset();
+    else if (ISFTracker *i = dynamic_cast<ISFTracker *>(p)) i->reset();
+    else if (EnergyTracker *e = dynamic_cast<EnergyTracker *>(p)) e->reset();
+}
+void ref_tracker_counts(void *h, int t, unsigned long long *out, int cap) {
+    StateTracker *p = static_cast<Sys *>(h)->stats[t].get();
+    vector<flt> c;
+    if (RsqTracker *r = dynamic_cast<RsqTracker *>(p)) c = r->counts();
+    else if (ISFTracker *i = dynamic_cast<ISFTracker *>(p)) c = i->counts();
+    for (int k = 0; k < cap && k < (int)c.size(); k++) out[k] = (unsigned long long)c[k];
+}
+// xyz2(), xyz4() (n x NDIM row-major) and r4() (n) of lag `single`
+void ref_rsq_read(void *h, int t, int single, double *xyz2, double *xyz4, double *r4) {
+    RsqTracker *r = dynamic_cast<RsqTracker *>(static_cast<Sys *>(h)->stats[t].get());
+    Eigen::Matrix<flt, Eigen::Dynamic, NDIM> a = r->xyz2()[single], b = r->xyz4()[single];
+    vector<flt> c = r->r4()[single];
+    for (int i = 0; i < a.rows(); i++) {
+        for (uint j = 0; j < NDIM; j++) {
+            if (xyz2) xyz2[(size_t)i * NDIM + j] = a(i, j);
+            if (xyz4) xyz4[(size_t)i * NDIM + j] = b(i, j);
+        }
+        if (r4) r4[i] = c[i];
+    }
+}
+// ISFxyz() of lag `single`: out[nks][n][NDIM][2]
+void ref_isf_read(void *h, int t, int single, double *out) {
+    ISFTracker *r = dynamic_cast<ISFTracker *>(static_cast<Sys *>(h)->stats[t].get());
+    vector<vector<barray<cmplx, NDIM> > > v = r->ISFxyz()[single];
+    size_t q = 0;
+    for (size_t ki = 0; ki < v.size(); ki++)
+        for (size_t i = 0; i < v[ki].size(); i++)
+            for (uint j = 0; j < NDIM; j++) {
+                out[q++] = v[ki][i][j].real();
+                out[q++] = v[ki][i][j].imag();
+            }
+}
+// out[8] = n(), E(), U(), K(), E_squared_mean(), U_squared_mean(), K_squared_mean(), get_U0()
+void ref_energy_tracker_read(void *h, int t, double *out) {
+    EnergyTracker *e = dynamic_cast<EnergyTracker *>(static_cast<Sys *>(h)->stats[t].get());
+    out[0] = e->n();
+    out[1] = e->E(); out[2] = e->U(); out[3] = e->K();
+    out[4] = e->E_squared_mean(); out[5] = e->U_squared_mean(); out[6] = e->K_squared_mean();
+    out[7] = e->get_U0();
+}
+void ref_energy_tracker_set_U0(void *h, int t, int from_box, double U0) {
+    Sys *s = static_cast<Sys *>(h);
+    EnergyTracker *e = dynamic_cast<EnergyTracker *>(s->stats[t].get());
+    if (from_box) e->set_U0(*s->box);
+    else e->set_U0(U0);
+}
 
 const char *ref_last_error(void *h) { return static_cast<Sys *>(h)->err.c_str(); }
 

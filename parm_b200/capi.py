@@ -78,6 +78,19 @@ SIGNATURES = {
     "parm_nlcg_reset": (C.c_int, [vp]),
     "parm_nlcg_descend": (C.c_int, [vp]),
     "parm_nlcg_reduce": (C.c_int, [vp, C.c_int, dp]),
+    "parm_rsq_create": (C.c_int, [vp, u64p, C.c_int, C.c_int, vpp]),
+    "parm_isf_create": (C.c_int, [vp, dp, C.c_int, u64p, C.c_int, C.c_int, vpp]),
+    "parm_energy_tracker_create": (C.c_int, [vp, vpp, C.c_int, C.c_uint, vpp]),
+    "parm_tracker_destroy": (C.c_int, [vp]),
+    "parm_tracker_update": (C.c_int, [vp]),
+    "parm_tracker_reset": (C.c_int, [vp]),
+    "parm_tracker_counts": (C.c_int, [vp, u64p, C.c_int]),
+    "parm_rsq_read": (C.c_int, [vp, C.c_int, dp, dp, dp]),
+    "parm_isf_read": (C.c_int, [vp, C.c_int, dp]),
+    "parm_energy_tracker_read": (C.c_int, [vp, dp]),
+    "parm_energy_tracker_set_u0": (C.c_int, [vp, C.c_int, C.c_double]),
+    "parm_integ_add_stat_tracker": (C.c_int, [vp, vp]),
+    "parm_integ_register_stat_tracker": (C.c_int, [vp, vp]),
     "parm_integ_get_scalars": (C.c_int, [vp, dp]),
     "parm_integ_reset_bath": (C.c_int, [vp]),
     "parm_integ_set_param": (C.c_int, [vp, C.c_int, C.c_double]),

@@ -127,6 +127,11 @@ int parm_inter_launch_forces(parm_inter *it, unsigned want, bool accumulate, dou
     return launch_forces(it, want ? RUN_FALL : RUN_F, accumulate, d_out, abort_flag, first, count);
 }
 
+// energy / virial / stress / contact counts into device memory, no host round trip (EnergyTracker, trackers.cu)
+int parm_inter_launch_obs(parm_inter *it, double *d_out, const int *abort_flag) {
+    return launch_forces(it, RUN_OBS, false, d_out, abort_flag);
+}
+
 // ---- host API ---------------------------------------------------------------------------
 static const char *k_kind_names[PARM_PAIR_NKINDS] = {
     "LJRepulsePair", "RepulsionPair", "LJAttractRepulsePair", "LennardJonesCutPair", "LJAttractCutPair",

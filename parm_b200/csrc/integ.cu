@@ -264,7 +264,18 @@ extern "C" int parm_integ_update_trackers(parm_integ *g) {
         PTRY(parm_nlist_update(nl, 0, &rebuilt));
         if (rebuilt) g->rebuilds++;
     }
+    for (parm_tracker *t : g->stat_trackers) PTRY(parm_tracker_enqueue_update(t, nullptr));
     return 0;
+}
+
+extern "C" int parm_integ_register_stat_tracker(parm_integ *g, parm_tracker *t) {
+    if (!g || !t) { parm_set_error("parm_integ_register_stat_tracker: NULL argument"); return PARM_ERR_INVALID; }
+    g->stat_trackers.push_back(t);
+    return 0;
+}
+extern "C" int parm_integ_add_stat_tracker(parm_integ *g, parm_tracker *t) {
+    PTRY(parm_integ_register_stat_tracker(g, t));
+    return parm_integ_update_trackers(g); // collection.hpp:117-120
 }
 
 extern "C" int parm_integ_register_interaction(parm_integ *g, parm_inter *it) {
@@ -381,8 +392,15 @@ extern "C" int parm_integ_inject_noise(parm_integ *g, const double *z, size_t le
 // word). abort_flag (device, may be NULL) is the decision word of the PREVIOUS step: when it is set the
 // kernels of this step return immediately, so a step can be enqueued before the host has seen whether
 // its predecessor asked for a rebuild.
+static int enqueue_step_core(parm_integ *g, uint64_t step, const int *abort_flag, int slot);
 static int enqueue_step(parm_integ *g, uint64_t step, const int *abort_flag, int slot) {
-    if (g->type >= PARM_INTEG_DAMPED) return parm_integ_extra_enqueue(g, step, abort_flag, slot);
+    if (g->type >= PARM_INTEG_DAMPED) PTRY(parm_integ_extra_enqueue(g, step, abort_flag, slot));
+    else PTRY(enqueue_step_core(g, step, abort_flag, slot));
+    // update_trackers() ends every step: the statistics trackers follow the NeighborList
+    for (parm_tracker *t : g->stat_trackers) PTRY(parm_tracker_enqueue_update(t, abort_flag));
+    return 0;
+}
+static int enqueue_step_core(parm_integ *g, uint64_t step, const int *abort_flag, int slot) {
     parm_ctx *c = g->ctx;
     const uint32_t n = parm_owned(c); // ghost copies are never integrated
     parm_nlist *nl = g->trackers.empty() ? nullptr : g->trackers[0];
@@ -510,7 +528,8 @@ extern "C" int parm_integ_timestep(parm_integ *g, int nsteps) {
     for (int s = 0; s < nsteps; s++) {
         const int p = s & 1;
         // (per-class event timing counts launches, so it runs without speculation)
-        const bool spec = speculate && !c->prof_on && s + 1 < nsteps && !nl->ignorechanged;
+        // (statistics trackers keep host-side step counters: their steps are never enqueued speculatively)
+        const bool spec = speculate && !c->prof_on && s + 1 < nsteps && !nl->ignorechanged && g->stat_trackers.empty();
         if (spec) {
             PTRY(enqueue_step(g, g->steps + 1, nl->d_slot + p, p ^ 1));
             CK(cudaEventRecord(g->ev[p ^ 1], c->stream));

@@ -217,6 +217,7 @@ struct parm_integ {
     uint64_t seed;
     std::vector<parm_inter *> inters;
     std::vector<parm_nlist *> trackers;
+    std::vector<parm_tracker *> stat_trackers; // RsqTracker / ISFTracker / EnergyTracker (trackers.cu)
     double *d_noise;
     size_t noise_len, noise_pos;
     uint32_t *d_mobile_rank; // by AtomVec index (noise injection addressing)
@@ -246,6 +247,8 @@ struct NlcgState {
 };
 int parm_nlcg_timestep(parm_integ *g); // nlcg.cu
 void parm_nlcg_free(parm_integ *g);
+
+int parm_tracker_enqueue_update(parm_tracker *t, const int *abort_flag); // trackers.cu
 
 // ---- cross-TU host functions ----
 int parm_integ_extra_enqueue(parm_integ *g, uint64_t step, const int *abort_flag, int slot); // integ_extra.cu

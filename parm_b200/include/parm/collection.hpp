@@ -27,14 +27,19 @@ class Collection {
         if (!d) throw std::runtime_error("parm_b200: only NListed interactions of the in-scope pair types run on the device (no CPU fallback)");
         return d->device_handle();
     }
+    static parm_tracker *stat(sptr<StateTracker> &t) {  // RsqTracker / ISFTracker / EnergyTracker, else NULL
+        parm_b200::DeviceTracker *d = dynamic_cast<parm_b200::DeviceTracker *>(t.get());
+        return d ? d->tracker_handle() : NULL;
+    }
     static parm_nlist *dev(sptr<StateTracker> &t) {
         NeighborList *n = dynamic_cast<NeighborList *>(t.get());
-        if (!n) throw std::runtime_error("parm_b200: only NeighborList trackers run on the device (statistics trackers are out of scope)");
+        if (!n) throw std::runtime_error("parm_b200: only NeighborList, RsqTracker, ISFTracker and EnergyTracker run on the device");
         return n->handle();
     }
     parm_ctx *ready(bool modifies = true) {
         for (size_t k = 0; k < interactions.size(); k++) dev(interactions[k]);
-        for (size_t k = 0; k < trackers.size(); k++) dev(trackers[k]);
+        for (size_t k = 0; k < trackers.size(); k++)
+            if (!stat(trackers[k])) dev(trackers[k]);
         return av->device(modifies);
     }
     void bind() {  // common constructor tail: resolve the AtomVec, attach the box
@@ -46,7 +51,10 @@ class Collection {
         ob->attach(av->context());
     }
     void register_all(bool should_initialize) {  // collection.cpp:3-11
-        for (size_t k = 0; k < trackers.size(); k++) parm_b200::check(parm_integ_register_tracker(integ, dev(trackers[k])));
+        for (size_t k = 0; k < trackers.size(); k++) {
+            if (stat(trackers[k])) parm_b200::check(parm_integ_register_stat_tracker(integ, stat(trackers[k])));
+            else parm_b200::check(parm_integ_register_tracker(integ, dev(trackers[k])));
+        }
         for (size_t k = 0; k < interactions.size(); k++) parm_b200::check(parm_integ_register_interaction(integ, dev(interactions[k])));
         if (should_initialize) initialize();
     }
@@ -132,6 +140,12 @@ class Collection {
         parm_b200::check(parm_integ_add_interaction(integ, h));
     }
     virtual void add_tracker(sptr<StateTracker> track) {  // collection.hpp:117-120
+        if (parm_tracker *t = stat(track)) {
+            trackers.push_back(track);
+            ready();
+            parm_b200::check(parm_integ_add_stat_tracker(integ, t));
+            return;
+        }
         parm_nlist *h = dev(track);
         trackers.push_back(track);
         ready();

@@ -84,6 +84,12 @@ class Mat {
         for (int i = 0; i < R * C; i++) s += d[i] * o.d[i];
         return s;
     }
+    flt sum() const {
+        if (R * C == 3) return d[0] + (d[1] + d[2 % (R * C)]);
+        flt s = 0;
+        for (int i = 0; i < R * C; i++) s += d[i];
+        return s;
+    }
     flt squaredNorm() const { return dot(*this); }
     flt norm() const { return std::sqrt(squaredNorm()); }
     Mat normalized() const { return (*this) / norm(); }

@@ -667,6 +667,153 @@ PAIR_CLASSES = {
     capi.PAIR_LOISOHERNMIN: LoisOhernMin, capi.PAIR_LOISLINMIN: LoisLinMin}
 
 
+class _StatTracker:
+    """Statistics trackers with their accumulators in device memory (csrc/trackers.cu)."""
+
+    def update(self, box=None):
+        self.atoms._device_op(False)
+        call("parm_tracker_update", self._h)
+
+    def reset(self):
+        self.atoms._device_op(False)
+        call("parm_tracker_reset", self._h)
+
+    def counts(self):
+        out = (C.c_uint64 * max(self._nlags, 1))()
+        call("parm_tracker_counts", self._h, out, self._nlags)
+        return [float(out[k]) for k in range(self._nlags)]
+
+
+class RsqTracker(_StatTracker):  # constraints.hpp:342-368
+    def __init__(self, atoms, ns, usecom=True):
+        self.atoms = atoms
+        ns = np.ascontiguousarray(ns, dtype=np.uint64)
+        self._nlags = ns.size
+        atoms._device_op(False)
+        h = C.c_void_p()
+        call("parm_rsq_create", atoms._h, ns.ctypes.data_as(capi.u64p), ns.size, int(usecom), C.byref(h))
+        self._h = h
+
+    def _read(self, k):
+        n, D = self.atoms.n, self.atoms.ndim
+        a, b, c = np.zeros((n, D)), np.zeros((n, D)), np.zeros(n)
+        call("parm_rsq_read", self._h, k, _dptr(a), _dptr(b), _dptr(c))
+        return a, b, c
+
+    def xyz2(self):
+        return [self._read(k)[0] for k in range(self._nlags)]
+
+    def xyz4(self):
+        return [self._read(k)[1] for k in range(self._nlags)]
+
+    def r4(self):
+        return [self._read(k)[2] for k in range(self._nlags)]
+
+    def r2(self):  # constraints.cpp:520-535: row sums of xyz2
+        out = []
+        for a in self.xyz2():
+            out.append(a[:, 0] + (a[:, 1] + a[:, 2]) if a.shape[1] == 3 else a[:, 0] + a[:, 1])
+        return out
+
+
+class ISFTracker(_StatTracker):  # constraints.hpp:393-414
+    def __init__(self, atoms, ks, ns, usecom=False):
+        self.atoms = atoms
+        ns = np.ascontiguousarray(ns, dtype=np.uint64)
+        ks = np.ascontiguousarray(ks, dtype=np.float64)
+        self._nlags, self._nks = ns.size, ks.size
+        atoms._device_op(False)
+        h = C.c_void_p()
+        call("parm_isf_create", atoms._h, _dptr(ks), ks.size, ns.ctypes.data_as(capi.u64p), ns.size, int(usecom), C.byref(h))
+        self._h = h
+
+    def ISFxyz(self):
+        """per lag: complex array (nks, n, ndim)."""
+        out = []
+        for k in range(self._nlags):
+            buf = np.zeros((self._nks, self.atoms.n, self.atoms.ndim, 2))
+            call("parm_isf_read", self._h, k, _dptr(buf))
+            out.append(buf[..., 0] + 1j * buf[..., 1])
+        return out
+
+    def ISFs(self):  # constraints.cpp:621-635: mean over the axes
+        return [a.sum(axis=2) / a.shape[2] for a in self.ISFxyz()]
+
+
+class EnergyTracker(_StatTracker):  # constraints.hpp:260-316
+    _nlags = 0
+
+    def __init__(self, atoms, interactions, n_skip=1):
+        self.atoms = atoms
+        self.interactions = list(interactions)
+        for i in self.interactions:
+            i._flush()
+        atoms._device_op(False)
+        arr = (C.c_void_p * max(len(self.interactions), 1))(*[i._h for i in self.interactions])
+        h = C.c_void_p()
+        call("parm_energy_tracker_create", atoms._h, arr, len(self.interactions), int(n_skip), C.byref(h))
+        self._h = h
+
+    def update(self, box=None):
+        for i in self.interactions:
+            i._ready(False)
+        call("parm_tracker_update", self._h)
+
+    def _sums(self):
+        out = np.zeros(8)
+        call("parm_energy_tracker_read", self._h, _dptr(out))
+        return out
+
+    def set_U0(self, U0=None):
+        """set_U0(flt) or, with a Box / no argument, set_U0(Box&): the current potential energy."""
+        from_box = U0 is None or isinstance(U0, OriginBox)
+        for i in self.interactions:
+            i._ready(False)
+        call("parm_energy_tracker_set_u0", self._h, int(from_box), 0.0 if from_box else float(U0))
+
+    def get_U0(self):
+        return float(self._sums()[7])
+
+    def n(self):
+        return int(self._sums()[0])
+
+    def E(self):
+        s = self._sums()
+        return s[1] / s[0]
+
+    def U(self):
+        s = self._sums()
+        return s[2] / s[0]
+
+    def K(self):
+        s = self._sums()
+        return s[3] / s[0]
+
+    def E_squared_mean(self):
+        s = self._sums()
+        return s[4] / s[0]
+
+    def U_squared_mean(self):
+        s = self._sums()
+        return s[5] / s[0]
+
+    def K_squared_mean(self):
+        s = self._sums()
+        return s[6] / s[0]
+
+    def E_std(self):
+        s = self._sums()
+        return np.sqrt(s[4] / s[0] - s[1] * s[1] / s[0] / s[0])
+
+    def U_std(self):
+        s = self._sums()
+        return np.sqrt(s[5] / s[0] - s[2] * s[2] / s[0] / s[0])
+
+    def K_std(self):
+        s = self._sums()
+        return np.sqrt(s[6] / s[0] - s[3] * s[3] / s[0] / s[0])
+
+
 class Collection:
     """Collection base (collection.hpp:23-130, collection.cpp:3-208)."""
 
@@ -675,7 +822,7 @@ class Collection:
             raise capi.ParmUnsupported("Constraints are outside the hot-path scope (DESIGN.md)")
         self.box, self.atoms = box, atoms
         box._attach(atoms)
-        self.interactions, self.trackers = [], []
+        self.interactions, self.trackers, self.stat_trackers = [], [], []
         for t in trackers:
             self._push_tracker(t)
         for i in interactions:
@@ -688,8 +835,11 @@ class Collection:
         self.interactions.append(inter)
 
     def _push_tracker(self, t):
+        if isinstance(t, _StatTracker):
+            self.stat_trackers.append(t)
+            return
         if not isinstance(t, NeighborList):
-            raise capi.ParmUnsupported("only NeighborList trackers run on the device")
+            raise capi.ParmUnsupported("only NeighborList, RsqTracker, ISFTracker and EnergyTracker run on the device")
         self.trackers.append(t)
 
     def _ready(self, modifies=True):
@@ -707,10 +857,13 @@ class Collection:
     def add_tracker(self, t):
         self._push_tracker(t)
         self._ready()
-        call("parm_integ_add_tracker", self._h, t._h)
+        if isinstance(t, _StatTracker):
+            call("parm_integ_add_stat_tracker", self._h, t._h)
+        else:
+            call("parm_integ_add_tracker", self._h, t._h)
 
     def add(self, obj):
-        return self.add_tracker(obj) if isinstance(obj, NeighborList) else self.add_interaction(obj)
+        return self.add_tracker(obj) if isinstance(obj, (NeighborList, _StatTracker)) else self.add_interaction(obj)
 
     def initialize(self):
         self._ready()
@@ -1048,6 +1201,8 @@ def _construct(collec):
     lib = capi.lib()
     for t in collec.trackers:
         capi.check(lib.parm_integ_register_tracker(collec._h, t._h))
+    for t in collec.stat_trackers:
+        capi.check(lib.parm_integ_register_stat_tracker(collec._h, t._h))
     for i in collec.interactions:
         capi.check(lib.parm_integ_register_interaction(collec._h, i._h))
     call("parm_integ_initialize", collec._h)

@@ -35,7 +35,11 @@ def run_facade(w, steps, tmp_path):
     raw = open(fout, "rb").read()
     sc = np.frombuffer(raw[:64], np.float64)
     u = np.frombuffer(raw[64:72], np.uint32)
-    arr = np.frombuffer(raw[72:], np.float64).reshape(3, n, nd)
+    o = 72 + 3 * n * nd * 8
+    arr = np.frombuffer(raw[72:o], np.float64).reshape(3, n, nd)
+    t = np.frombuffer(raw[o:], np.float64)
+    run_facade.trackers = dict(counts=t[:2], r2=t[2:2 + 2 * n].reshape(2, n), r4=t[2 + 2 * n:2 + 3 * n],
+                               isf=t[2 + 3 * n:2 + 4 * n] + 1j * t[2 + 4 * n:2 + 5 * n], et=t[2 + 5 * n:])
     return sc, u, arr
 
 
@@ -54,9 +58,21 @@ def test_facade_program_matches_oracle(oracle_built, tmp_path, case):
     sc, u, (x, v, f) = run_facade(w, steps, tmp_path)
     c = cpu_system("port", w)
     np0 = len(c.pairs()[0])
+    tr = [c.add_rsq_tracker([1, 5], True), c.add_isf_tracker([1.5], [3], False), c.add_energy_tracker(2)]
     c.set_forces(True)
     E0, K0, U0 = c.energy(), c.kinetic_energy(), c.inter_energy()
     c.timestep(steps)
+    # the statistics trackers the C++ program registered (RsqTracker, ISFTracker, EnergyTracker)
+    T = run_facade.trackers
+    assert [int(q) for q in T["counts"]] == c.tracker_counts(tr[0])
+    for k in (0, 1):
+        assert rel_err(T["r2"][k], c.rsq_read(tr[0], k)[0].sum(axis=1)) < 1e-8
+    assert rel_err(T["r4"], c.rsq_read(tr[0], 1)[2]) < 1e-8
+    assert np.abs(T["isf"] - c.isf_read(tr[1], 0)[0].mean(axis=1)).max() < 1e-8
+    e = c.energy_tracker_read(tr[2])
+    assert int(T["et"][0]) == int(e[0]) and rel_err(T["et"][1:4], e[1:4]) < 1e-9
+    # E_std() = sqrt(<E^2> - <E>^2) cancels catastrophically for a conserved energy: only its scale is comparable
+    assert np.isnan(T["et"][4]) or T["et"][4] < 1e-2 * abs(e[1]) + 1e-6
     cx, cv, ca, cf = c.get_atoms()
     assert u[0] == np0 and u[1] == c.which()
     for got, want in zip(sc, (E0, K0, U0, c.energy(), c.kinetic_energy(), c.inter_energy(), c.pressure(), c.temp())):

@@ -145,6 +145,38 @@ def test_port_equals_reference_all_integrators(oracle_built, integ):
             assert np.array_equal(outs[0][3], outs[1][3]) and outs[0][3][0] != 0
 
 
+@pytest.mark.parametrize("ndim", [3, 2])
+def test_trackers_port_equals_reference(oracle_built, ndim):
+    """RsqTracker / ISFTracker / EnergyTracker of the C restatement against the reference's own
+    constraints.cpp (compiled in place), bit for bit -- including reset(), set_U0(box) and frozen atoms."""
+    if "ref" not in backends(oracle_built):
+        pytest.skip("compiled reference not present")
+    w = W.random_system(130, ndim, 2, seed=15, ntypes=2, frozen=2, T=0.5)
+    outs = []
+    for be in ("ref", "port"):
+        s = cpu_system(be, w)
+        s.set_forces(True)
+        r = s.add_rsq_tracker([1, 3, 10], True)
+        i = s.add_isf_tracker([0.7, 6.3], [2, 5], False)
+        e = s.add_energy_tracker(3)
+        s.timestep(37)
+        o = [s.tracker_counts(r), s.rsq_read(r, 0), s.rsq_read(r, 2), s.tracker_counts(i), s.isf_read(i, 1), s.energy_tracker_read(e)]
+        s.energy_tracker_set_U0(e)
+        s.tracker_reset(r)
+        s.tracker_update(i)
+        s.timestep(11)
+        o += [s.rsq_read(r, 1), s.isf_read(i, 0), s.energy_tracker_read(e), s.tracker_counts(r)]
+        outs.append(o)
+
+    def eq(a, b):
+        if isinstance(a, (tuple, list)):
+            return all(eq(x, y) for x, y in zip(a, b))
+        return np.array_equal(np.asarray(a), np.asarray(b))
+    assert outs[0][0] == [40, 13, 4] and outs[0][5][0] > 0
+    for a, b in zip(*outs):
+        assert eq(a, b)
+
+
 def chain_ignores(n, rng, extra=40):
     """Bonded-neighbour style exclusions (i,i+1), (i,i+2) plus a few random pairs, duplicates and both orders."""
     a = np.concatenate([np.arange(n - 1), np.arange(n - 2), rng.integers(0, n, extra), np.arange(5)])
