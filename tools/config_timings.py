@@ -37,10 +37,43 @@ def run(name, w, steps):
     atoms.close()
 
 
+def functor_lattice(kind, variant, side):
+    """1e6-atom 3-D lattice at the LJ bench density with the parameters of W.functor_system for one functor."""
+    import numpy as np
+    base = W.lj_lattice((side, side, side), seed=3003, T=0.3)
+    f = W.functor_system(kind, variant, ndim=3, n=base["x"].shape[0], seed=kind)
+    for k in ("params", "types", "eps_table", "sig_table"):
+        base[k] = f[k]
+    base["params"][:, 1] = np.where(base["params"][:, 1] > 1.1, 1.0, 0.9)  # keep sigma_ij below the lattice spacing
+    if kind == W.KIND_EISMCLACHLAN:
+        base["params"][:, 1] = 0.55
+    base.update(kind=kind, variant=variant, dt=0.001)
+    return base
+
+
+def widening(steps):
+    """every NListed functor under CollectionVerlet and every extra integrator on the LJ workload,
+    1e6 atoms each, same timing as the config table."""
+    side = 100
+    for kind, variant in [(W.KIND_LJATTRACTCUT, ""), (W.KIND_LJATTRACTFIXEDREPULSE, ""), (W.KIND_EISMCLACHLAN, ""),
+                          (W.KIND_LJISH, ""), (W.KIND_LJATTRACTREPULSESIGS, ""), (W.KIND_REPULSIONDRAG, ""),
+                          (W.KIND_LOISOHERN, ""), (W.KIND_LOISLIN, ""), (W.KIND_REPULSION, "II")]:
+        run("functor kind %d%s, CollectionVerlet, N=1M" % (kind, variant), functor_lattice(kind, variant, side), steps)
+    for integ, (name, params) in sorted(W.INTEGRATOR_CASES.items()):
+        w = W.config3(side)
+        if integ == 4:
+            params = (0.05,)
+        w.update(integrator=integ, integ_params=params, seed=1)
+        run("integrator %s, LJAttractRepulsePair, N=1M" % name, w, steps)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--widening", action="store_true", help="time the SURVEY 8(f) functors and integrators instead")
     a = ap.parse_args()
+    if a.widening:
+        return widening(a.steps)
     run("1: LJatoms-like LennardJonesCutPair N=1000", W.config1(), a.steps * 5)
     run("2: 2-D bidisperse harmonic RepulsionPair N=100k", W.config2(), a.steps * 2)
     run("3: 3-D LJAttractRepulsePair N=1M", W.config3(), a.steps)
