@@ -85,7 +85,9 @@ static int launch_forces(parm_inter *it, int run, bool accumulate, double *d_out
         it->partial_doubles = (size_t)nblocks * NPART;
         CK(cudaMalloc(&it->d_partials, it->partial_doubles * 8));
     }
-    const int specmode = it->generic ? 2 : (it->nspecies == 1 ? 0 : 1);
+    // 0 one species, 1 species table in shared memory, 2 per-atom parameters, 3 two species in registers
+    const bool long_rows = nl->total_full >= (uint64_t)PARM_PACK_MIN_NEIGHBORS * (parm_owned(c) ? parm_owned(c) : 1);
+    const int specmode = it->generic ? 2 : (it->nspecies == 1 ? 0 : (it->nspecies == 2 && long_rows ? 3 : 1));
     size_t smem = specmode == 1 ? (size_t)it->nspecies * it->nspecies * sizeof(PairConst) : 0;
     ForceArgs A;
     A.pos = c->pos;
@@ -96,6 +98,10 @@ static int launch_forces(parm_inter *it, int run, bool accumulate, double *d_out
     A.table = it->d_table;
     A.nspecies = it->nspecies;
     A.P1 = it->h_table[0];
+    if (specmode == 3)
+        for (int q = 0; q < 4; q++) A.P4[q] = it->h_table[q];
+    A.mask = nl->packed ? PARM_NBR_SLOT_MASK : 0xffffffffu;
+    A.packed = nl->packed_for == it && !it->spec_stale;
     A.f = c->f;
     A.vel = c->v;
     A.n = nown;
@@ -182,6 +188,7 @@ extern "C" int parm_inter_destroy(parm_inter *it) {
     if (it->d_eps_table) cudaFree(it->d_eps_table);
     if (it->d_sig_table) cudaFree(it->d_sig_table);
     c->inters.erase(std::remove(c->inters.begin(), c->inters.end(), it), c->inters.end());
+    if (it->nl->packed_for == it) it->nl->packed_for = nullptr; // (the entries stay packed until the next rebuild)
     delete it;
     return 0;
 }
@@ -317,6 +324,7 @@ extern "C" int parm_inter_set_params_ex(parm_inter *it, const double *params, in
         diam[i] = max_size(kind, k.data(), t, sig_table, ntypes);
     }
     it->generic = too_many;
+    it->spec_stale = true; // until the next rebuild re-packs the list entries
     it->ntypes = ntypes > 0 ? ntypes : 1;
     if (it->d_eps_table) { cudaFree(it->d_eps_table); it->d_eps_table = 0; }
     if (it->d_sig_table) { cudaFree(it->d_sig_table); it->d_sig_table = 0; }

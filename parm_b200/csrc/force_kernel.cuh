@@ -22,6 +22,9 @@ struct ForceArgs {
     const PairConst *table;  // SPEC 1: nspecies x nspecies
     int nspecies;
     PairConst P1;            // SPEC 0
+    PairConst P4[4];         // SPEC 3: the 2 x 2 species table
+    uint32_t mask;           // row entry & mask = neighbour slot (entries may carry a species id in their top bits)
+    int packed;              // the species id in the top bits is this interaction's
     double *f;
     const double *vel;       // RepulsionDragPair only: v[3][npad]
     uint32_t n, npad;
@@ -40,7 +43,8 @@ struct ForceArgs {
 // consecutive indices = one or more full 32-byte sectors of the row), U entries per lane are in flight at
 // once (index loads first, then the pos[j] gathers, then the arithmetic), and the team folds its partial
 // force with xor-shuffles. TEAM*U divides 32 so rows (kmax % 32 == 0) are always readable up to the padded end.
-// SPEC: 0 one species (constants in registers), 1 species table in shared memory, 2 per-atom parameters
+// SPEC: 0 one species (constants in registers), 1 species table in shared memory, 2 per-atom parameters,
+//       3 two species (this atom's table row in registers, selected per neighbour)
 template <int KIND, int SPEC, int MODE, int TEAM, int U>
 __global__ void __launch_bounds__(F_BLOCK) k_force(const ForceArgs A) {
     if (A.abort_flag && *A.abort_flag) return; // speculatively enqueued step whose predecessor asked for a rebuild
@@ -66,6 +70,12 @@ __global__ void __launch_bounds__(F_BLOCK) k_force(const ForceArgs A) {
     const double4 pi = pos[sc];
     const uint32_t *row = A.nbr + (size_t)sc * A.kmax;
     const PairConst *prow = SPEC == 1 ? s_table + (int)A.spec[sc] * A.nspecies : nullptr;
+    PairConst R0, R1; // SPEC 3: pair constants of this atom against species 0 and 1
+    if (SPEC == 3) {
+        const int si = (int)A.spec[sc];
+        R0 = A.P4[2 * si];
+        R1 = A.P4[2 * si + 1];
+    }
     double qi[5] = {0, 0, 0, 0, 0};
     int ti = 0;
     if (SPEC == 2) {
@@ -83,14 +93,16 @@ __global__ void __launch_bounds__(F_BLOCK) k_force(const ForceArgs A) {
         viz = A.vel[2 * (size_t)A.npad + sc];
     }
     for (uint32_t k0 = tl; k0 < my; k0 += TEAM * U) {
-        uint32_t j[U];
+        uint32_t j[U], sp[U];
         bool ok[U];
         double4 pj[U];
 #pragma unroll
         for (int u = 0; u < U; u++) {
             const uint32_t k = k0 + u * TEAM;
             ok[u] = k < my;
-            j[u] = ok[u] ? __ldg(row + k) : sc;
+            const uint32_t e = ok[u] ? __ldg(row + k) : sc;
+            j[u] = e & A.mask;
+            sp[u] = e >> PARM_NBR_SLOT_BITS;
         }
 #pragma unroll
         for (int u = 0; u < U; u++) pj[u] = ld_pos4(pos + j[u]);
@@ -112,7 +124,14 @@ __global__ void __launch_bounds__(F_BLOCK) k_force(const ForceArgs A) {
             if (SPEC == 0) {
                 pair_eval<KIND>(A.P1, dsq, vdotr, want_obs, scal, e);
             } else if (SPEC == 1) {
-                const PairConst &P = prow[__ldg(A.spec + j[u])];
+                const PairConst &P = prow[A.packed ? sp[u] : (uint32_t)__ldg(A.spec + j[u])];
+                pair_eval<KIND>(P, dsq, vdotr, want_obs, scal, e);
+            } else if (SPEC == 3) {
+                const uint32_t sj = A.packed ? sp[u] : (uint32_t)__ldg(A.spec + j[u]);
+                PairConst P;
+                P.eps = sj ? R1.eps : R0.eps; P.sig = sj ? R1.sig : R0.sig; P.sig2 = sj ? R1.sig2 : R0.sig2;
+                P.rc2 = sj ? R1.rc2 : R0.rc2; P.cutE = sj ? R1.cutE : R0.cutE;
+                P.a = sj ? R1.a : R0.a; P.b = sj ? R1.b : R0.b; P.c = sj ? R1.c : R0.c;
                 pair_eval<KIND>(P, dsq, vdotr, want_obs, scal, e);
             } else {
                 double qj[5] = {0, 0, 0, 0, 0};
@@ -202,10 +221,12 @@ cudaError_t parm_launch_force_kind(int specmode, int team, int mode, uint32_t na
     if (team == 8) {
         if (specmode == 0) return launch_mode<KIND, 0, 8>(mode, grid, 0, st, A);
         if (specmode == 1) return launch_mode<KIND, 1, 8>(mode, grid, smem, st, A);
+        if (specmode == 3) return launch_mode<KIND, 3, 8>(mode, grid, 0, st, A);
         return launch_mode<KIND, 2, 8>(mode, grid, 0, st, A);
     }
     if (specmode == 0) return launch_mode<KIND, 0, 4>(mode, grid, 0, st, A);
     if (specmode == 1) return launch_mode<KIND, 1, 4>(mode, grid, smem, st, A);
+    if (specmode == 3) return launch_mode<KIND, 3, 4>(mode, grid, 0, st, A);
     return launch_mode<KIND, 2, 4>(mode, grid, 0, st, A);
 }
 

@@ -18,6 +18,9 @@
 #include "../../include/parm_b200.h"
 
 #define PARM_MAX_SPECIES 32   // distinct per-atom parameter tuples per interaction
+#define PARM_NBR_SLOT_BITS 27  // neighbour-row entry = slot | species << 27 when packed (parm_nlist::packed_for)
+#define PARM_NBR_SLOT_MASK ((1u << PARM_NBR_SLOT_BITS) - 1u)
+#define PARM_PACK_MIN_NEIGHBORS 24 // mean row length from which packing / the two-species register path pay
 
 void parm_set_error(const char *fmt, ...);
 void parm_count_launch(parm_ctx *ctx, unsigned n = 1);
@@ -145,6 +148,10 @@ struct parm_nlist {
     int cell_sub;        // cells per r_list (1 or 2)
     uint32_t updatenum;
     bool ignorechanged;
+    // Species packing: when one interaction with 2..32 tabulated species uses this list, the top 5 bits of every
+    // row entry carry the neighbour's species id, so the force kernel needs no per-neighbour species gather.
+    bool packed;                 // row entries carry a species id in their top bits (mask them)
+    parm_inter *packed_for;      // whose species they are (NULL once that interaction is destroyed)
     // NeighborList::ignore (trackers.hpp:190-193): excluded pairs, canonical (larger index, smaller index)
     std::set<std::pair<uint32_t, uint32_t> > ignored;
     bool ignore_dirty;           // the device CSR is older than `ignored`
@@ -191,6 +198,7 @@ struct parm_inter {
     // more than PARM_MAX_SPECIES distinct tuples (continuous polydispersity): per-atom parameters are
     // gathered with the neighbour and the pair constructor runs per pair on the device
     bool generic;
+    bool spec_stale;                // species ids changed since the list entries were packed: gather them instead
     bool minmix;                    // LoisOhernPairMinCLs / LoisLinPairMin constructors
     std::vector<double> h_par_id;   // 8 doubles per AtomVec index: p0 p1 p2 type | p3 p4 - - (geometric ones as sqrt)
     double4 *d_par_id, *d_par;      // by AtomVec index / by slot; two double4 per atom: [lo | hi] halves

@@ -125,3 +125,55 @@ def test_neighborlist_ignore(oracle_built, ndim):
     # AtomID form, one pair at a time
     nl.ignore(sim.AtomID(atoms, 10), sim.AtomID(atoms, 500))
     assert nl.ignore_size() == s.ignore_size() + 1
+
+
+@pytest.mark.parametrize("nspecies", [2, 3])
+def test_species_packed_into_list_entries(oracle_built, nspecies):
+    """Long rows + 2..32 tabulated species: the neighbour's species id rides in the top bits of the row entries
+    (csrc/nlist.cu k_pack_species; two species use the register path of the force kernel). Covers the state
+    changes around it: parameters changed after the build (entries stale until the next rebuild), a second
+    interaction sharing the list (it must mask the entries and gather its own species), ignore()."""
+    from parm_b200 import sim
+    w = W.lj_lattice((14, 14, 14), seed=8)  # ~110 neighbours per atom
+    n = w["x"].shape[0]
+    rng = np.random.default_rng(nspecies)
+    types = rng.integers(0, nspecies, n).astype(np.uint32)
+    tab = np.array([[1.0, 1.5, 0.7], [1.5, 0.5, 1.2], [0.7, 1.2, 0.9]])[:nspecies, :nspecies]  # Kob-Andersen-like
+    w.update(types=types, eps_table=tab)
+    w["params"][:, 1] = np.where(types == 1, 0.88, 1.0)
+    box, atoms, inter, nl, collec = sim.from_workload(w)
+    s = cpu_system(backends(oracle_built)[-1], w, injected=True)
+
+    def same():
+        atoms.reset_forces()
+        p = inter.set_forces_get_pressure(box)
+        f_ref, p_ref = s.forces_and_pressure()
+        assert rel_err_vec(atoms.peek("f"), f_ref) < 1e-10 and rel_err(p, p_ref) < 1e-10
+        assert rel_err(inter.energy(box), s.inter_energy()) < 1e-10
+        a, b = nl.pairs()
+        ra, rb = s.pairs()
+        assert np.array_equal(a, ra) and np.array_equal(b, rb)
+
+    same()
+    collec.set_forces(True)
+    s.set_forces(True)
+    collec.timestep(80)
+    s.timestep(80)
+    assert nl.which() == s.which() > 1
+    assert rel_err_vec(atoms.peek("x") - w["x"], s.get_atoms()[0] - w["x"]) < 1e-8
+    same()
+    # a second interaction on the same list: soft repulsion with its own species (sigma classes)
+    p2 = np.zeros((n, 3))
+    p2[:, 0] = 2.0
+    p2[:, 1] = np.where(rng.random(n) < 0.5, 0.9, 1.05)
+    p2[:, 2] = 2.5
+    rep = sim.Repulsion(atoms, nl)
+    rep.add_many(p2)
+    k2 = s.add_interaction(W.KIND_REPULSION, 0.0, p2, share_nl=0)
+    atoms.reset_forces()
+    rep.set_forces(box)
+    s.api["reset_forces"](s.h)
+    s.api["inter_set_forces"](s.h, k2)
+    assert rel_err_vec(atoms.peek("f"), s.get_atoms()[3]) < 1e-10
+    assert rel_err(rep.energy(box), s.inter_energy(k2)) < 1e-10
+    same()
