@@ -175,10 +175,10 @@ def build_system(L, n_global, gid, x, v, m, kind, params, types, eps_table, skin
     box = sim.OriginBox(L, ndim)
     box._attach(atoms)
     atoms.set_local(gid, x, v, None, None, m)
-    cls = {capi.PAIR_LJREPULSE: sim.LJRepulse, capi.PAIR_REPULSION: sim.Repulsion,
-           capi.PAIR_LJATTRACTREPULSE: sim.LJAttractRepulse, capi.PAIR_LJCUT: sim.LJCut}[kind]
-    inter = cls(box, atoms, skin)
-    inter.add_many(params, types, eps_table)
+    inter = sim.PAIR_CLASSES[kind](box, atoms, skin)
+    # the epsilon table belongs to the functors whose atom struct carries `epsilons` (workloads.tables)
+    needs_table = kind in (capi.PAIR_LJATTRACTREPULSE, capi.PAIR_LJATTRACTFIXEDREPULSE, capi.PAIR_LJISH)
+    inter.add_many(params, types, eps_table if needs_table else None)
     nl = inter.neighbor_list()
     nl.update_list(True)
     if integrator == 0:

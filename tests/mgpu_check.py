@@ -85,6 +85,12 @@ def main():
     world = dist.get_world_size()
     # 3-D LJ (config 3/5 state point, small): hot enough that atoms migrate between slabs
     check("lj3d", W.lj_lattice((12 * world, 10, 10), seed=11), steps=60)
+    # binary LJ with long rows: the neighbour species ride in the list entries (ghost rows included)
+    wb = W.lj_lattice((12 * world, 10, 10), seed=13)
+    tb = (np.arange(wb["x"].shape[0]) % 3 == 0).astype(np.uint32)
+    wb.update(types=tb, eps_table=np.array([[1.0, 1.5], [1.5, 0.5]]))
+    wb["params"][:, 1] = np.where(tb == 1, 0.88, 1.0)
+    check("lj3d_binary", wb, steps=50)
     # 2-D bidisperse harmonic (config 2 functor)
     check("harm2d", W.config2(nx=30 * world, ny=30), steps=80)
     # binary WCA with Langevin dynamics (config 4): counter-based noise is decomposition independent
