@@ -118,6 +118,11 @@ int parm_nlist_numpairs(parm_nlist *nl, uint64_t *npairs);  /* numpairs() */
 int parm_nlist_download_pairs(parm_nlist *nl, uint32_t *first, uint32_t *last, uint64_t cap);
 /* mean / max neighbours per atom in the device (full) list, for bench rooflines */
 int parm_nlist_stats(parm_nlist *nl, double *mean_full_neighbors, uint32_t *max_full_neighbors);
+/* cell-tile layout of the last rebuild (the shared-memory staged pair kernel):
+ * active = 1 when single-species Lennard-Jones interactions on this list run on the tile kernel;
+ * chunks = blocks per launch, max_tile_atoms = largest number of positions one block stages,
+ * wide_chunks = chunks whose tile spans more than half the box (per-pair minimum image kept). */
+int parm_nlist_tile_stats(parm_nlist *nl, int *active, uint32_t *chunks, uint32_t *max_tile_atoms, uint32_t *wide_chunks);
 
 /* ---- NListed<A,P> interaction.hpp:1876-1945, 2102-2291 ---- */
 #define PARM_PAIR_LJREPULSE 0        /* NListed<EpsSigAtom, LJRepulsePair>       :857-891, 119-152 */

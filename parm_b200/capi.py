@@ -57,6 +57,7 @@ SIGNATURES = {
     "parm_nlist_numpairs": (C.c_int, [vp, u64p]),
     "parm_nlist_download_pairs": (C.c_int, [vp, u32p, u32p, C.c_uint64]),
     "parm_nlist_stats": (C.c_int, [vp, dp, u32p]),
+    "parm_nlist_tile_stats": (C.c_int, [vp, C.POINTER(C.c_int), u32p, u32p, u32p]),
     "parm_nlist_ignore": (C.c_int, [vp, u32p, u32p, C.c_uint64]),
     "parm_nlist_ignore_size": (C.c_int, [vp, u64p]),
     "parm_inter_create": (C.c_int, [vp, vp, C.c_int, vpp]),

@@ -12,7 +12,7 @@
 #include <array>
 #include <map>
 
-#include "force_kernel.cuh"
+#include "force_tile.cuh"
 
 // folds the per-block partials; every pair was visited from both ends -> * 0.5
 __global__ void k_force_fold(const double *__restrict__ partials, uint32_t nblocks, double *out) {
@@ -47,6 +47,19 @@ static const force_launcher k_launchers[PARM_NKERNEL_KINDS] = {
     parm_launch_force_kind<PARM_PAIR_LJATTRACTREPULSESIGS>, parm_launch_force_kind<PARM_PAIR_REPULSIONDRAG>,
     parm_launch_force_kind<PARM_PAIR_LOISOHERN>, parm_launch_force_kind<PARM_PAIR_LOISLIN>};
 
+typedef cudaError_t (*tile_launcher)(int, int, int, unsigned, size_t, cudaStream_t, const TileForceArgs &);
+#define DECL(K) extern template cudaError_t parm_launch_force_tile_kind<K>(int, int, int, unsigned, size_t, cudaStream_t, const TileForceArgs &);
+DECL(PARM_PAIR_LJREPULSE) DECL(PARM_PAIR_LJATTRACTREPULSE) DECL(PARM_PAIR_LJCUT)
+#undef DECL
+static tile_launcher tile_launcher_of(int kernel_kind) {
+    switch (kernel_kind) {
+        case PARM_PAIR_LJREPULSE: return parm_launch_force_tile_kind<PARM_PAIR_LJREPULSE>;
+        case PARM_PAIR_LJATTRACTREPULSE: return parm_launch_force_tile_kind<PARM_PAIR_LJATTRACTREPULSE>;
+        case PARM_PAIR_LJCUT: return parm_launch_force_tile_kind<PARM_PAIR_LJCUT>;
+        default: return nullptr;
+    }
+}
+
 enum { RUN_F = 0, RUN_FALL = 1, RUN_OBS = 2 }; // forces only / forces + observables / observables only
 
 // d_out: device pointer to NPART doubles (E, virial, stress[9], contacts, overlaps) or NULL
@@ -73,17 +86,50 @@ static int launch_forces(parm_inter *it, int run, bool accumulate, double *d_out
     if (first > nown) first = nown;
     nown = count == 0xffffffffu ? nown : std::min(nown, first + count); // slots [first, nown)
     const uint32_t nrange = nown - first;
-    const uint32_t nblocks = (uint32_t)(((size_t)nrange * team + F_BLOCK - 1) / F_BLOCK);
+    uint32_t nblocks = (uint32_t)(((size_t)nrange * team + F_BLOCK - 1) / F_BLOCK);
     if (nrange == 0) {
         if (d_out) CK(cudaMemsetAsync(d_out, 0, NPART * 8, c->stream));
         return 0;
     }
     const int mode = run == RUN_F ? MODE_F : MODE_FALL;
+    // cell-tile kernel (force_tile.cuh) when the list carries tile-local rows for this interaction and the slot
+    // range is made of whole cell columns; otherwise the gather kernel below
+    uint32_t chunk0 = 0, chunk1 = 0;
+    tile_launcher tl = parm_tile_usable(it) ? tile_launcher_of(PARM_KERNEL_KIND(it->kind)) : nullptr;
+    if (tl && !parm_tile_chunk_range(nl, first, nown, &chunk0, &chunk1)) tl = nullptr;
+    if (tl && chunk1 == chunk0) tl = nullptr;
+    if (tl) nblocks = chunk1 - chunk0;
     if (mode != MODE_F && (size_t)nblocks * NPART > it->partial_doubles) {
         if (it->d_partials) cudaFree(it->d_partials);
         it->d_partials = 0;
         it->partial_doubles = (size_t)nblocks * NPART;
         CK(cudaMalloc(&it->d_partials, it->partial_doubles * 8));
+    }
+    if (tl) {
+        TileForceArgs T;
+        T.pos = c->pos;
+        T.chunks = nl->tile.d_chunks + chunk0;
+        T.rows16 = nl->tile.rows16;
+        T.cnt = nl->cnt;
+        T.kmax = nl->kmax;
+        T.cap = (nl->tile.max_tile + 1 + 15u) & ~15u;
+        T.P1 = it->h_table[0];
+        T.f = c->f;
+        T.npad = c->npad;
+        T.box = c->box;
+        T.accumulate = accumulate ? 1 : 0;
+        T.store = run != RUN_OBS;
+        T.partials = it->d_partials;
+        T.abort_flag = abort_flag;
+        cudaError_t e = tl(nl->tile.team, nl->tile.v, mode, nblocks, 3 * (size_t)T.cap * 8, c->stream, T);
+        parm_count_launch(c);
+        CK(e);
+        if (mode != MODE_F) {
+            if (!d_out) { parm_set_error("internal: observables requested without an output buffer"); return PARM_ERR_RUNTIME; }
+            k_force_fold<<<1, 256, 0, c->stream>>>(it->d_partials, nblocks, d_out);
+            CK_LAUNCH(c);
+        }
+        return 0;
     }
     // 0 one species, 1 species table in shared memory, 2 per-atom parameters, 3 two species in registers
     const bool long_rows = nl->total_full >= (uint64_t)PARM_PACK_MIN_NEIGHBORS * (parm_owned(c) ? parm_owned(c) : 1);

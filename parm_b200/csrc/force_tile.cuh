@@ -1,0 +1,206 @@
+// Cell-tile variant of the NListed pair kernel (interaction.hpp:2154-2291) for single-species interactions
+// with long rows (the LJ configurations of BASELINE.json). One block per chunk (tile.cu):
+//   1. stage the chunk's tile: every position of the <= 18 contiguous slot runs is loaded ONCE, coalesced,
+//      reduced to min_image(x - origin) and stored SoA in shared memory (24 B per atom);
+//   2. TEAM lanes per atom walk the atom's 16-bit tile-local row: one vector load brings V entries per lane,
+//      every pair costs three LDS.64 instead of a 32-byte global gather, and there is no per-pair minimum
+//      image (OriginBox::diff, box.hpp:103, is applied once per staged atom) unless the tile is wider than
+//      half the box (small boxes), in which case the per-pair form runs on top.
+// Same FULL rows, same fixed summation order inside a lane, team and block as force_kernel.cuh: no atomics,
+// run-to-run deterministic.
+#pragma once
+#include "force_kernel.cuh"
+
+struct TileForceArgs {
+    const double4 *pos;
+    const TileChunk *chunks; // already offset to the first chunk of the launch
+    const uint16_t *rows16;
+    const uint32_t *cnt;
+    uint32_t kmax;
+    uint32_t cap;            // doubles per coordinate array in shared memory (> max tile size, sentinel included)
+    PairConst P1;
+    double *f;
+    uint32_t npad;
+    BoxDev box;
+    int accumulate, store;
+    double *partials;
+    const int *abort_flag;
+};
+
+// 1/x for normal positive x without the division's special-case path: MUFU.RCP64H seed (2^-23) and one
+// cubic Newton step, relative error ~2^-52 (the pair distance squared is never zero, subnormal or infinite)
+__device__ __forceinline__ double rcp_pos(double x) {
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    const double e = fma(-x, y, 1.0);
+    return fma(y, fma(e, e, e), y);
+}
+
+// Branch-free form of pair_eval (pairs.cuh) for the Lennard-Jones family, so that the V pairs of a pass can
+// be interleaved: LJRepulsePair::forces/energy :875-891 (:126-151), LJAttractRepulsePair :1271-1298,
+// LennardJonesCutPair :253-267. c12 = 12 epsilon.
+template <int KIND>
+__device__ __forceinline__ void lj_eval(const PairConst &P, double c12, double dsq, bool want_e, double &scal, double &e) {
+    const bool in = !(dsq > P.rc2);
+    const double w = rcp_pos(dsq);
+    const double s2 = P.sig2 * w;
+    const double ir6 = s2 * s2 * s2;
+    const double t = c12 * ir6 * (ir6 - 1.0) * w;
+    scal = in ? t : 0.0;
+    e = 0.0;
+    if (want_e) {
+        const double mid = 1.0 - ir6;
+        const double en = KIND == PARM_PAIR_LJCUT ? P.eps * (mid * mid - 1.0) - P.cutE : P.eps * (mid * mid) - P.cutE;
+        e = in ? en : 0.0;
+    }
+}
+
+template <int KIND, int MODE, int TEAM, int V, bool MI>
+__device__ __forceinline__ void tile_rows(const TileForceArgs &A, const TileChunk *C, const double *sx, const double *sy,
+                                          const double *sz, double (&acc)[NPART]) {
+    constexpr bool want_obs = MODE != MODE_F;
+    const uint32_t tl = threadIdx.x % TEAM;
+    const uint32_t na = C->n, s0 = C->s0;
+    const double ox = C->o[0], oy = C->o[1], oz = C->o[2];
+    const double c12 = 12.0 * A.P1.eps;
+    for (uint32_t a0 = 0; a0 < na; a0 += TILE_NT / TEAM) {
+        const uint32_t a = a0 + threadIdx.x / TEAM;
+        const bool valid = a < na;
+        const uint32_t s = s0 + (valid ? a : 0);
+        const uint32_t my = valid ? min(A.cnt[s], A.kmax) : 0;
+        const double4 pi = A.pos[s];
+        const double xi = min_image_fast(pi.x - ox, A.box.L[0], A.box.invL[0]);
+        const double yi = min_image_fast(pi.y - oy, A.box.L[1], A.box.invL[1]);
+        const double zi = min_image_fast(pi.z - oz, A.box.L[2], A.box.invL[2]);
+        const uint16_t *row = A.rows16 + (size_t)s * A.kmax;
+        double fx = 0, fy = 0, fz = 0;
+        for (uint32_t k0 = 0; k0 < my; k0 += TEAM * V) {
+            uint32_t w[V / 2];
+            if constexpr (V == 8) {
+                const uint4 q = __ldg(reinterpret_cast<const uint4 *>(row + k0 + tl * V));
+                w[0] = q.x; w[1] = q.y; w[2] = q.z; w[3] = q.w;
+            } else {
+                const uint2 q = __ldg(reinterpret_cast<const uint2 *>(row + k0 + tl * V));
+                w[0] = q.x; w[1] = q.y;
+            }
+#pragma unroll
+            for (int e = 0; e < V; e++) {
+                const uint32_t idx = (e & 1) ? (w[e >> 1] >> 16) : (w[e >> 1] & 0xffffu);
+                double dx = xi - sx[idx], dy = yi - sy[idx], dz = zi - sz[idx];
+                if (MI) {
+                    dx = min_image_fast(dx, A.box.L[0], A.box.invL[0]);
+                    dy = min_image_fast(dy, A.box.L[1], A.box.invL[1]);
+                    dz = min_image_fast(dz, A.box.L[2], A.box.invL[2]);
+                }
+                const double dsq = dx * dx + (dy * dy + dz * dz);
+                double scal, en;
+                lj_eval<KIND>(A.P1, c12, dsq, want_obs, scal, en); // sentinel pads: dsq ~ 1e200, beyond any cutoff
+                const double gx = dx * scal, gy = dy * scal, gz = dz * scal;
+                fx += gx;
+                fy += gy;
+                fz += gz;
+                if (want_obs) {
+                    acc[0] += en;
+                    acc[1] += dx * gx + (dy * gy + dz * gz); // r.dot(f), :2241
+                    acc[2] += dx * gx; acc[3] += dx * gy; acc[4] += dx * gz; // stress += r * f^T, :2274
+                    acc[5] += dy * gx; acc[6] += dy * gy; acc[7] += dy * gz;
+                    acc[8] += dz * gx; acc[9] += dz * gy; acc[10] += dz * gz;
+                    acc[11] += (en != 0.0) ? 1.0 : 0.0; // contacts :2126-2137
+                    acc[12] += (en > 0.0) ? 1.0 : 0.0;  // overlaps :2140-2151
+                }
+            }
+        }
+        if (MODE == MODE_F || A.store) {
+#pragma unroll
+            for (int o = TEAM / 2; o; o >>= 1) {
+                fx += __shfl_xor_sync(0xffffffffu, fx, o);
+                fy += __shfl_xor_sync(0xffffffffu, fy, o);
+                fz += __shfl_xor_sync(0xffffffffu, fz, o);
+            }
+            if (valid && tl == 0) {
+                double *f = A.f;
+                if (A.accumulate) {
+                    f[s] += fx;
+                    f[A.npad + s] += fy;
+                    f[2 * (size_t)A.npad + s] += fz;
+                } else {
+                    f[s] = fx;
+                    f[A.npad + s] = fy;
+                    f[2 * (size_t)A.npad + s] = fz;
+                }
+            }
+        }
+    }
+}
+
+template <int KIND, int MODE, int TEAM, int V>
+__global__ void __launch_bounds__(TILE_NT) k_force_tile(const TileForceArgs A) {
+    if (A.abort_flag && *A.abort_flag) return; // speculatively enqueued step whose predecessor asked for a rebuild
+    extern __shared__ double s_xyz[];
+    __shared__ uint32_t s_start[TILE_MAXSEG], s_off[TILE_MAXSEG + 1];
+    const TileChunk *C = A.chunks + blockIdx.x;
+    if (threadIdx.x < TILE_MAXSEG) s_start[threadIdx.x] = C->seg_start[threadIdx.x];
+    if (threadIdx.x <= TILE_MAXSEG) s_off[threadIdx.x] = C->seg_off[threadIdx.x];
+    double *sx = s_xyz, *sy = s_xyz + A.cap, *sz = s_xyz + 2 * (size_t)A.cap;
+    const uint32_t ntile = C->ntile;
+    const double ox = C->o[0], oy = C->o[1], oz = C->o[2];
+    __syncthreads();
+    {
+        uint32_t seg = 0;
+        for (uint32_t t = threadIdx.x; t < ntile; t += TILE_NT) {
+            while (t >= s_off[seg + 1]) seg++;
+            const double4 p = A.pos[s_start[seg] + (t - s_off[seg])];
+            sx[t] = min_image_fast(p.x - ox, A.box.L[0], A.box.invL[0]);
+            sy[t] = min_image_fast(p.y - oy, A.box.L[1], A.box.invL[1]);
+            sz[t] = min_image_fast(p.z - oz, A.box.L[2], A.box.invL[2]);
+        }
+        if (threadIdx.x == 0) sx[ntile] = sy[ntile] = sz[ntile] = 1e100; // the sentinel every row is padded with
+    }
+    __syncthreads();
+    double acc[NPART];
+    if (MODE != MODE_F)
+#pragma unroll
+        for (int q = 0; q < NPART; q++) acc[q] = 0.0;
+    if (C->flags & 1u) tile_rows<KIND, MODE, TEAM, V, true>(A, C, sx, sy, sz, acc);
+    else tile_rows<KIND, MODE, TEAM, V, false>(A, C, sx, sy, sz, acc);
+    if (MODE != MODE_F) {
+        __shared__ double red[NPART][TILE_NT / 32];
+        const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+        for (int q = 0; q < NPART; q++) {
+            double x = acc[q];
+#pragma unroll
+            for (int o = 16; o; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+            if (lane == 0) red[q][w] = x;
+        }
+        __syncthreads();
+        if (threadIdx.x < NPART) {
+            double x = 0;
+            for (int ww = 0; ww < TILE_NT / 32; ww++) x += red[threadIdx.x][ww];
+            A.partials[(size_t)blockIdx.x * NPART + threadIdx.x] = x;
+        }
+    }
+}
+
+template <int KIND, int TEAM, int V>
+static cudaError_t launch_tile_mode(int mode, unsigned nchunks, size_t smem, cudaStream_t st, const TileForceArgs &A) {
+    if (mode == MODE_F) {
+        if (smem > 48 * 1024) cudaFuncSetAttribute(k_force_tile<KIND, MODE_F, TEAM, V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        k_force_tile<KIND, MODE_F, TEAM, V><<<nchunks, TILE_NT, smem, st>>>(A);
+    } else {
+        if (smem > 48 * 1024) cudaFuncSetAttribute(k_force_tile<KIND, MODE_FALL, TEAM, V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        k_force_tile<KIND, MODE_FALL, TEAM, V><<<nchunks, TILE_NT, smem, st>>>(A);
+    }
+    return cudaGetLastError();
+}
+
+template <int KIND>
+cudaError_t parm_launch_force_tile_kind(int team, int v, int mode, unsigned nchunks, size_t smem, cudaStream_t st, const TileForceArgs &A) {
+    if (team == 8) return launch_tile_mode<KIND, 8, 4>(mode, nchunks, smem, st, A);
+    if (team == 2) return launch_tile_mode<KIND, 2, 8>(mode, nchunks, smem, st, A);
+    if (v == 4) return launch_tile_mode<KIND, 4, 4>(mode, nchunks, smem, st, A);
+    return launch_tile_mode<KIND, 4, 8>(mode, nchunks, smem, st, A);
+}
+
+#define PARM_INSTANTIATE_FORCE_TILE_KIND(K) \
+    template cudaError_t parm_launch_force_tile_kind<K>(int, int, int, unsigned, size_t, cudaStream_t, const TileForceArgs &);

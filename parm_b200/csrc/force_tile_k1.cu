@@ -1,0 +1,3 @@
+// Cell-tile pair kernel instantiations (force_tile.cuh), part 2
+#include "force_tile.cuh"
+PARM_INSTANTIATE_FORCE_TILE_KIND(PARM_PAIR_LJREPULSE)

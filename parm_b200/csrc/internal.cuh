@@ -134,8 +134,47 @@ struct NlistFlags { // device-written; a pinned host mirror receives need_rebuil
     double top2[2];
 };
 
+// ---- cell-tile staging for the pair kernel (csrc/tile.cu, csrc/force_tile.cuh) --------------------
+// The owned slots are cut into CHUNKS of at most `ch` consecutive slots that never straddle an (x,y)
+// cell column. The neighbours of a chunk's atoms all lie in <= TILE_MAXSEG contiguous slot runs (the
+// 3 x 3 surrounding columns, z range of the chunk +- one cell): the chunk's TILE. The pair kernel
+// stages the tile's positions in shared memory, relative to the chunk origin and minimum-imaged
+// once per staged atom, and walks 16-bit tile-local neighbour rows (rows16) written once per rebuild.
+#define TILE_MAXSEG 18
+#define TILE_NT 256            // threads per block of the tile kernels
+#define TILE_MAX_ATOMS 9000    // staged positions per tile that fit 227 KB of shared memory (24 B each)
+struct TileChunk {
+    uint32_t s0, n;            // first slot, number of atoms (<= ch)
+    uint32_t nseg, ntile;      // contiguous slot runs, staged atoms in total
+    double o[3];               // origin the staged coordinates are relative to
+    uint32_t flags, pad;       // bit 0: tile is wider than half the box on some axis: minimum image per pair as well
+    uint32_t seg_start[TILE_MAXSEG];
+    uint32_t seg_off[TILE_MAXSEG + 1]; // exclusive prefix of the run lengths
+};
+struct TileInfo { // device-written, copied to the host with the build flags
+    uint32_t nchunks, max_tile, bad, wide;
+};
+struct TileState {
+    int enabled;               // PARM_B200_TILE (default 1)
+    int min_nbrs;              // mean row length from which the tile kernel is used (PARM_B200_TILE_MIN_NEIGHBORS, 32)
+    int ch, team, v;           // chunk size; lanes per atom and row entries per lane and pass of the pair kernel
+    bool planned;              // chunk table matches the current cell structure
+    bool valid;                // rows16 match the current rows
+    uint32_t nchunks, max_tile;
+    uint32_t ncol;             // owned cell columns
+    TileChunk *d_chunks;
+    uint32_t chunk_cap;
+    uint16_t *rows16;          // [npad][kmax], permuted per (team, v) block, padded with the sentinel index
+    size_t rows16_cap;
+    uint32_t *d_col;           // [2][ncol + 1]: first slot / first chunk of every owned column
+    uint32_t col_cap;
+    uint32_t *h_col;           // pinned copy of d_col (same layout, stride col_cap)
+    TileInfo *d_info, *h_info; // h_info pinned
+};
+
 struct parm_nlist {
     parm_ctx *ctx;
+    TileState tile;
     double skin;
     std::vector<double> h_diam; // by AtomVec index; < 0: not a member
     bool have_diam;
@@ -284,6 +323,14 @@ int parm_inter_regather(parm_inter *inter);          // re-gather per-slot speci
 int parm_inter_launch_forces(parm_inter *inter, unsigned want, bool accumulate, double *d_out /*device, 13 doubles*/,
                              const int *abort_flag = nullptr, uint32_t first = 0, uint32_t count = 0xffffffffu);
 int parm_ctx_ensure_red(parm_ctx *ctx, size_t doubles);
+// cell-tile path (csrc/tile.cu)
+int parm_tile_plan_enqueue(parm_nlist *nl);   // chunk table from the cell structure (async, before the build's sync)
+int parm_tile_plan_fetch(parm_nlist *nl);     // queue the device->host copy of the plan summary (before that sync)
+int parm_tile_localize(parm_nlist *nl);       // after the rows are final: write rows16
+void parm_tile_invalidate(parm_nlist *nl);
+void parm_tile_free(parm_nlist *nl);
+bool parm_tile_usable(const parm_inter *it);  // this interaction can run on the tile kernel right now
+bool parm_tile_chunk_range(const parm_nlist *nl, uint32_t first, uint32_t end, uint32_t *c0, uint32_t *c1);
 
 // ---- device helpers ----
 #ifdef __CUDACC__

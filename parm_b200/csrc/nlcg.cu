@@ -153,6 +153,7 @@ static void box_resize(parm_ctx *c, double factor) { // OriginBox::resize(factor
         c->box.invL[k] = 1.0 / l;
         c->box.halfL[k] = l * 0.5;
     }
+    for (parm_nlist *nl : c->nlists) parm_tile_invalidate(nl);
 }
 
 #define ND(kern, ...)                                                                    \

@@ -688,6 +688,7 @@ extern "C" int parm_nlist_destroy(parm_nlist *nl) {
     if (nl->d_excl) cudaFree(nl->d_excl);
     if (nl->h_flags) cudaFreeHost(nl->h_flags);
     if (nl->h_slot) cudaFreeHost(nl->h_slot);
+    parm_tile_free(nl);
     c->nlists.erase(std::remove(c->nlists.begin(), c->nlists.end(), nl), c->nlists.end());
     delete nl;
     return 0;
@@ -985,7 +986,8 @@ static int pack_species(parm_nlist *nl) {
 
 static int finish_rows(parm_nlist *nl) {
     PTRY(apply_ignore(nl));
-    return pack_species(nl);
+    PTRY(pack_species(nl));
+    return parm_tile_localize(nl); // 16-bit tile-local rows for the cell-tile pair kernel (tile.cu)
 }
 
 // Build the rows for the atoms now in slots 0..n-1, growing the per-atom capacity if a row overflowed.
@@ -993,6 +995,7 @@ int parm_nlist_build_rows(parm_nlist *nl) {
     parm_ctx *c = nl->ctx;
     const uint32_t n = c->n;
     for (parm_inter *it : c->inters) PTRY(parm_inter_regather(it));
+    parm_tile_invalidate(nl);
     if (n == 0) { nl->total_full = 0; nl->maxcnt = 0; return 0; }
     if (nl->kmax == 0) {
         double vol = 1;
@@ -1007,6 +1010,7 @@ int parm_nlist_build_rows(parm_nlist *nl) {
     const unsigned ntiles = (n + 31) / 32;
     const unsigned nblocks = (ntiles + BUILD_WARPS - 1) / BUILD_WARPS;
     const double uthr = nl->maxdiam + nl->skin;
+    PTRY(parm_tile_plan_enqueue(nl)); // chunk table of the cell-tile pair kernel: needs the cell structure only
     for (int attempt = 0; attempt < 8; attempt++) {
         CK(cudaMemsetAsync((char *)nl->d_flags + offsetof(NlistFlags, maxcnt), 0,
                            offsetof(NlistFlags, xmax_bits) - offsetof(NlistFlags, maxcnt), c->stream));
@@ -1050,6 +1054,7 @@ int parm_nlist_build_rows(parm_nlist *nl) {
         CK_LAUNCH(c);
         if (attempt == 0) PTRY(parm_prof_end(c));
         CK(cudaMemcpyAsync(nl->h_flags, nl->d_flags, sizeof(NlistFlags), cudaMemcpyDeviceToHost, c->stream));
+        PTRY(parm_tile_plan_fetch(nl));
         CK(cudaStreamSynchronize(c->stream));
         nl->total_full = nl->h_flags->total;
         nl->maxcnt = nl->h_flags->maxcnt;

@@ -139,6 +139,7 @@ extern "C" int parm_set_box(parm_ctx *c, const double *L) {
         c->box.halfL[k] = l * 0.5;
     }
     c->box_set = true; // (the reference keeps its pair list across a resize: the grid is re-derived at every rebuild)
+    for (parm_nlist *nl : c->nlists) parm_tile_invalidate(nl); // tile origins belong to the old box: gather kernel until the next rebuild
     return 0;
 }
 

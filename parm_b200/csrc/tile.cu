@@ -1,0 +1,356 @@
+// Cell-tile staging for the NListed pair loop (interaction.hpp:2154-2291): per-rebuild planning.
+//
+// After the atoms are sorted by cell index (cells of one (x,y) column are contiguous in slot order), the
+// neighbours of any run of consecutive slots inside one column lie in at most 18 contiguous slot runs:
+// the 3 x 3 surrounding columns, each over the run's z range +- one cell (two runs where that range wraps).
+// k_tile_cols cuts every owned column into chunks of <= ch slots (deterministic prefix scan),
+// k_tile_chunks writes each chunk's run table, origin and size, and k_tile_localize rewrites the
+// 32-bit neighbour rows as 16-bit indices into the chunk's tile (rows16). The pair kernel
+// (force_tile.cuh) then stages the tile once per block in shared memory and never gathers positions
+// from global memory or evaluates a per-pair minimum image.
+#include <algorithm>
+#include <stdlib.h>
+#include <string.h>
+
+#include "pairs.cuh"
+
+// ---- K5a: chunks per owned column, exclusive scan (one block; a few thousand columns at most) ----
+__global__ void __launch_bounds__(1024)
+k_tile_cols(const uint32_t *__restrict__ cell_start, uint32_t nc2, uint32_t ncol, uint32_t ch, uint32_t *col_slot,
+            uint32_t *col_chunk, TileInfo *info) {
+    __shared__ uint32_t s_warp[32];
+    __shared__ uint32_t s_running;
+    const uint32_t lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (threadIdx.x == 0) s_running = 0;
+    __syncthreads();
+    for (uint32_t base = 0; base < ncol; base += 1024) {
+        const uint32_t q = base + threadIdx.x;
+        uint32_t a = 0, nch = 0;
+        if (q < ncol) {
+            a = cell_start[(size_t)q * nc2];
+            const uint32_t b = cell_start[(size_t)(q + 1) * nc2];
+            nch = (b - a + ch - 1) / ch;
+        }
+        uint32_t x = nch; // inclusive warp scan
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+            if (lane >= (uint32_t)o) x += y;
+        }
+        if (lane == 31) s_warp[w] = x;
+        __syncthreads();
+        if (w == 0) {
+            uint32_t t = s_warp[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t y = __shfl_up_sync(0xffffffffu, t, o);
+                if (lane >= (uint32_t)o) t += y;
+            }
+            s_warp[lane] = t; // inclusive over warps
+        }
+        __syncthreads();
+        const uint32_t before = s_running + (w ? s_warp[w - 1] : 0) + (x - nch);
+        if (q < ncol) {
+            col_slot[q] = a;
+            col_chunk[q] = before;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) s_running += s_warp[31];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        col_slot[ncol] = cell_start[(size_t)ncol * nc2];
+        col_chunk[ncol] = s_running;
+        info->nchunks = s_running;
+    }
+}
+
+// ---- K5b: one thread per chunk: run table, origin, size -----------------------------------------
+__global__ void __launch_bounds__(128)
+k_tile_chunks(const uint32_t *__restrict__ cell_start, const uint32_t *__restrict__ cell_id_sorted,
+              const uint32_t *__restrict__ col_slot, const uint32_t *__restrict__ col_chunk, uint32_t ncol, uint32_t ch,
+              BoxDev box, GridDev g, StencilDev st, ShardDev sd, double margin, TileChunk *chunks, TileInfo *info) {
+    const uint32_t cidx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (cidx >= col_chunk[ncol]) return;
+    uint32_t lo = 0, hi = ncol; // largest q with col_chunk[q] <= cidx (columns without atoms own no chunk)
+    while (hi - lo > 1) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (col_chunk[mid] <= cidx) lo = mid; else hi = mid;
+    }
+    const uint32_t q = lo;
+    const uint32_t k = cidx - col_chunk[q];
+    const uint32_t a = col_slot[q] + k * ch, b = min(a + ch, col_slot[q + 1]);
+    const int nc0 = g.nc[0], nc1 = g.nc[1], nc2 = g.nc[2];
+    const int cx = (int)(q / (uint32_t)nc1), cy = (int)(q % (uint32_t)nc1);
+    const int zlo = (int)(cell_id_sorted[a] % (uint32_t)nc2), zhi = (int)(cell_id_sorted[b - 1] % (uint32_t)nc2);
+    TileChunk C;
+    C.s0 = a;
+    C.n = b - a;
+    C.pad = 0;
+    // z pieces (run axis): the chunk's cells +- one, split where the range wraps; the whole column once when
+    // the range would overlap itself
+    int za[2], zb[2], npiece = 1;
+    bool wide = false;
+    if (zhi - zlo + 3 > nc2) {
+        za[0] = 0; zb[0] = nc2 - 1;
+        wide = true;
+    } else if (zlo - 1 < 0) {
+        za[0] = zlo - 1 + nc2; zb[0] = nc2 - 1;
+        za[1] = 0; zb[1] = zhi + 1;
+        npiece = 2;
+    } else if (zhi + 1 >= nc2) {
+        za[0] = zlo - 1; zb[0] = nc2 - 1;
+        za[1] = 0; zb[1] = zhi + 1 - nc2;
+        npiece = 2;
+    } else {
+        za[0] = zlo - 1; zb[0] = zhi + 1;
+    }
+    uint32_t nseg = 0, off = 0;
+    bool bad = false;
+    for (int xx = cx - 1; xx <= cx + 1; xx++) {
+        int x2 = xx;
+        if (st.open0) {
+            if (x2 < 0) x2 = nc0 - 1; // halo layer below (numbered last), halo above is layer nc0 - 2 = cx + 1
+        } else if (x2 < 0) x2 += nc0;
+        else if (x2 >= nc0) x2 -= nc0;
+        for (int yy = cy - 1; yy <= cy + 1; yy++) {
+            int y2 = yy;
+            if (y2 < 0) y2 += nc1; else if (y2 >= nc1) y2 -= nc1;
+            const uint32_t cbase = ((uint32_t)x2 * (uint32_t)nc1 + (uint32_t)y2) * (uint32_t)nc2;
+            for (int p = 0; p < npiece; p++) {
+                const uint32_t jb = cell_start[cbase + (uint32_t)za[p]], je = cell_start[cbase + (uint32_t)zb[p] + 1];
+                if (je == jb) continue;
+                if (nseg >= TILE_MAXSEG) { bad = true; continue; }
+                C.seg_start[nseg] = jb;
+                C.seg_off[nseg] = off;
+                off += je - jb;
+                nseg++;
+            }
+        }
+    }
+    for (uint32_t s = nseg; s < TILE_MAXSEG; s++) { C.seg_start[s] = 0; C.seg_off[s] = off; }
+    C.seg_off[TILE_MAXSEG] = off;
+    C.nseg = nseg;
+    C.ntile = off;
+    // origin: centre of the chunk's cells (wrapped frame); min_image(x - o) then picks the right image of every
+    // staged atom whatever multiple of L its unwrapped coordinate carries
+    double h[3];
+    C.o[0] = st.open0 ? sd.lo + (cx + 0.5) * (sd.Ls / sd.nci) : (cx + 0.5) / g.scale[0];
+    h[0] = st.open0 ? 0.5 * sd.Ls / sd.nci : 0.5 / g.scale[0];
+    C.o[1] = (cy + 0.5) / g.scale[1];
+    h[1] = 0.5 / g.scale[1];
+    C.o[2] = 0.5 * (zlo + zhi + 1) / g.scale[2];
+    h[2] = 0.5 * (zhi - zlo + 1) / g.scale[2];
+    // staged differences equal the minimum image iff |x_i - o| + r_list stays below L/2 (margin = r_list + 2 skin)
+    for (int d = 0; d < 3; d++)
+        if (!(h[d] + margin < 0.4999 * box.L[d])) wide = true;
+    C.flags = wide ? 1u : 0u;
+    chunks[cidx] = C;
+    atomicMax(&info->max_tile, off);
+    if (wide) atomicAdd(&info->wide, 1u);
+    if (bad || off > 65534u) atomicOr(&info->bad, 1u);
+}
+
+// ---- K5c: rows16 ----------------------------------------------------------------------------------
+// One block per chunk, one warp per atom (round robin). Entry k of the 32-bit row goes to position
+//   (k / (team v)) (team v) + (k % team) v + (k % (team v)) / team
+// so that lane t of a team finds entries t, t + team, ... of every pass in ONE vector load while the
+// team as a whole still reads consecutive entries (= near-consecutive tile slots, few bank conflicts)
+// at every step. The tail of the last pass is padded with the sentinel index ntile (staged far away).
+__global__ void __launch_bounds__(TILE_NT)
+k_tile_localize(const TileChunk *__restrict__ chunks, const uint32_t *__restrict__ nbr, const uint32_t *__restrict__ cnt,
+                uint32_t kmax, uint32_t mask, int team, int v, uint16_t *__restrict__ rows16, TileInfo *info) {
+    __shared__ uint32_t s_start[TILE_MAXSEG], s_off[TILE_MAXSEG + 1];
+    const TileChunk *C = chunks + blockIdx.x;
+    if (threadIdx.x < TILE_MAXSEG) s_start[threadIdx.x] = C->seg_start[threadIdx.x];
+    if (threadIdx.x <= TILE_MAXSEG) s_off[threadIdx.x] = C->seg_off[threadIdx.x];
+    __syncthreads();
+    const uint32_t nseg = C->nseg, ntile = C->ntile, s0 = C->s0, na = C->n;
+    const uint32_t lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const uint32_t tv = (uint32_t)(team * v);
+    bool lost = false;
+    for (uint32_t a = w; a < na; a += TILE_NT / 32) {
+        const uint32_t s = s0 + a;
+        const uint32_t my = min(cnt[s], kmax);
+        const uint32_t padded = (my + tv - 1) / tv * tv;
+        const uint32_t *row = nbr + (size_t)s * kmax;
+        uint16_t *out = rows16 + (size_t)s * kmax;
+        uint32_t seg = 0;
+        for (uint32_t k = lane; k < padded; k += 32) {
+            uint32_t loc = ntile;
+            if (k < my) {
+                const uint32_t j = row[k] & mask;
+                // rows are written run by run, so the previous hit is almost always still right
+                if (!(j >= s_start[seg] && j - s_start[seg] < s_off[seg + 1] - s_off[seg])) {
+                    seg = 0;
+                    while (seg < nseg && !(j >= s_start[seg] && j - s_start[seg] < s_off[seg + 1] - s_off[seg])) seg++;
+                }
+                if (seg < nseg) loc = s_off[seg] + (j - s_start[seg]);
+                else { lost = true; seg = 0; }
+            }
+            const uint32_t r = k % tv;
+            out[k - r + (r % (uint32_t)team) * (uint32_t)v + r / (uint32_t)team] = (uint16_t)loc;
+        }
+    }
+    if (lost) atomicOr(&info->bad, 2u);
+}
+
+// ---- host side -----------------------------------------------------------------------------------
+static bool kind_on_tile(int kind) {
+    const int kk = PARM_KERNEL_KIND(kind);
+    return kk == PARM_PAIR_LJREPULSE || kk == PARM_PAIR_LJATTRACTREPULSE || kk == PARM_PAIR_LJCUT; // the Lennard-Jones family
+}
+static bool inter_fits(const parm_inter *it) {
+    return it->have_params && !it->generic && it->nspecies == 1 && kind_on_tile(it->kind);
+}
+
+static void tile_config(parm_nlist *nl) {
+    TileState &t = nl->tile;
+    if (t.ch) return;
+    const char *e = getenv("PARM_B200_TILE");
+    t.enabled = e ? atoi(e) : 1;
+    e = getenv("PARM_B200_TILE_MIN_NEIGHBORS");
+    t.min_nbrs = e ? atoi(e) : 32;
+    e = getenv("PARM_B200_TILE_CH");
+    t.ch = e ? atoi(e) : 128;
+    if (t.ch < 32) t.ch = 32;
+    if (t.ch > 1024) t.ch = 1024;
+    e = getenv("PARM_B200_TILE_TEAM");
+    t.team = e ? atoi(e) : 4;
+    e = getenv("PARM_B200_TILE_V");
+    t.v = e ? atoi(e) : 8;
+    if (!((t.team == 4 && (t.v == 8 || t.v == 4)) || (t.team == 8 && t.v == 4) || (t.team == 2 && t.v == 8))) {
+        t.team = 4;
+        t.v = 8;
+    }
+}
+
+void parm_tile_invalidate(parm_nlist *nl) {
+    nl->tile.planned = false;
+    nl->tile.valid = false;
+}
+
+void parm_tile_free(parm_nlist *nl) {
+    TileState &t = nl->tile;
+    if (t.d_chunks) cudaFree(t.d_chunks);
+    if (t.rows16) cudaFree(t.rows16);
+    if (t.d_col) cudaFree(t.d_col);
+    if (t.d_info) cudaFree(t.d_info);
+    if (t.h_info) cudaFreeHost(t.h_info);
+    if (t.h_col) cudaFreeHost(t.h_col);
+    t.d_chunks = 0; t.rows16 = 0; t.d_col = 0; t.d_info = 0; t.h_info = 0; t.h_col = 0;
+}
+
+int parm_tile_plan_enqueue(parm_nlist *nl) {
+    parm_ctx *c = nl->ctx;
+    TileState &t = nl->tile;
+    tile_config(nl);
+    parm_tile_invalidate(nl);
+    if (!t.enabled || c->D != 3 || nl->smallbox || nl->st.sub != 1) return 0;
+    if (!(nl->st.full[1] && nl->st.full[2] && (nl->st.full[0] || nl->st.open0))) return 0;
+    bool any = false;
+    for (parm_inter *it : c->inters) any = any || (it->nl == nl && inter_fits(it));
+    const uint32_t nown = parm_owned(c);
+    if (!any || !nown) return 0;
+    const uint32_t ncol = (uint32_t)(c->sh.on ? nl->sd.nci : nl->g.nc[0]) * (uint32_t)nl->g.nc[1];
+    if (!t.d_info) {
+        CK(cudaMalloc(&t.d_info, sizeof(TileInfo)));
+        CK(cudaHostAlloc(&t.h_info, sizeof(TileInfo), cudaHostAllocDefault));
+    }
+    if (ncol + 1 > t.col_cap) {
+        if (t.d_col) cudaFree(t.d_col);
+        if (t.h_col) cudaFreeHost(t.h_col);
+        t.d_col = 0;
+        t.h_col = 0;
+        t.col_cap = ncol + 1 + ncol / 4;
+        CK(cudaMalloc(&t.d_col, 2 * (size_t)t.col_cap * 4));
+        CK(cudaHostAlloc(&t.h_col, 2 * (size_t)t.col_cap * 4, cudaHostAllocDefault));
+    }
+    const uint32_t maxchunks = nown / (uint32_t)t.ch + ncol + 1;
+    if (maxchunks > t.chunk_cap) {
+        if (t.d_chunks) cudaFree(t.d_chunks);
+        t.d_chunks = 0;
+        t.chunk_cap = maxchunks + maxchunks / 4;
+        CK(cudaMalloc(&t.d_chunks, (size_t)t.chunk_cap * sizeof(TileChunk)));
+    }
+    t.ncol = ncol;
+    CK(cudaMemsetAsync(t.d_info, 0, sizeof(TileInfo), c->stream));
+    k_tile_cols<<<1, 1024, 0, c->stream>>>(nl->cell_start, (uint32_t)nl->g.nc[2], ncol, (uint32_t)t.ch, t.d_col, t.d_col + t.col_cap, t.d_info);
+    CK_LAUNCH(c);
+    const double margin = (nl->maxdiam + nl->skin) * (1.0 + 1e-6) + 2.0 * nl->skin;
+    k_tile_chunks<<<(maxchunks + 127) / 128, 128, 0, c->stream>>>(nl->cell_start, nl->cell_id_sorted, t.d_col, t.d_col + t.col_cap, ncol,
+                                                                 (uint32_t)t.ch, c->box, nl->g, nl->st, nl->sd, margin, t.d_chunks, t.d_info);
+    CK_LAUNCH(c);
+    t.planned = true;
+    return 0;
+}
+
+int parm_tile_plan_fetch(parm_nlist *nl) {
+    parm_ctx *c = nl->ctx;
+    TileState &t = nl->tile;
+    if (!t.planned) return 0;
+    CK(cudaMemcpyAsync(t.h_info, t.d_info, sizeof(TileInfo), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(t.h_col, t.d_col, 2 * (size_t)t.col_cap * 4, cudaMemcpyDeviceToHost, c->stream));
+    return 0;
+}
+
+// Called when the rows are final (after ignore / species packing) and the plan summary is on the host.
+int parm_tile_localize(parm_nlist *nl) {
+    parm_ctx *c = nl->ctx;
+    TileState &t = nl->tile;
+    t.valid = false;
+    if (!t.planned) return 0;
+    const uint32_t nown = parm_owned(c);
+    t.nchunks = t.h_info->nchunks;
+    t.max_tile = t.h_info->max_tile;
+    if (t.h_info->bad || !t.nchunks || t.max_tile + 1 > TILE_MAX_ATOMS) return 0;
+    // short rows (contact-range potentials) are not gather bound: staging a tile per chunk would cost more than it saves
+    if (nl->total_full < (uint64_t)t.min_nbrs * nown) return 0;
+    const size_t need = (size_t)c->npad * nl->kmax;
+    if (need > t.rows16_cap) {
+        if (t.rows16) cudaFree(t.rows16);
+        t.rows16 = 0;
+        t.rows16_cap = 0;
+        CK(cudaMalloc(&t.rows16, need * 2));
+        t.rows16_cap = need;
+    }
+    k_tile_localize<<<t.nchunks, TILE_NT, 0, c->stream>>>(t.d_chunks, nl->nbr, nl->cnt, nl->kmax,
+                                                           nl->packed ? PARM_NBR_SLOT_MASK : 0xffffffffu, t.team, t.v, t.rows16, t.d_info);
+    CK_LAUNCH(c);
+    static int check = -1;
+    if (check < 0) { const char *e = getenv("PARM_B200_TILE_CHECK"); check = e ? atoi(e) : 0; }
+    if (check) { // debugging aid: every row entry must have been found in its chunk's tile
+        CK(cudaMemcpyAsync(t.h_info, t.d_info, sizeof(TileInfo), cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+        if (t.h_info->bad) { parm_set_error("cell-tile plan lost a neighbour (bad = %u)", t.h_info->bad); return PARM_ERR_RUNTIME; }
+    }
+    t.valid = true;
+    return 0;
+}
+
+bool parm_tile_usable(const parm_inter *it) {
+    const parm_nlist *nl = it->nl;
+    return nl->tile.valid && inter_fits(it);
+}
+
+// Owned slots [first, end) as a chunk range; false when the range does not start and end on column boundaries.
+bool parm_tile_chunk_range(const parm_nlist *nl, uint32_t first, uint32_t end, uint32_t *c0, uint32_t *c1) {
+    const TileState &t = nl->tile;
+    const uint32_t *slot = t.h_col, *chunk = t.h_col + t.col_cap;
+    const uint32_t *a = std::lower_bound(slot, slot + t.ncol + 1, first);
+    const uint32_t *b = std::lower_bound(slot, slot + t.ncol + 1, end);
+    if (a == slot + t.ncol + 1 || *a != first || b == slot + t.ncol + 1 || *b != end) return false;
+    *c0 = chunk[a - slot];
+    *c1 = chunk[b - slot];
+    return true;
+}
+
+extern "C" int parm_nlist_tile_stats(parm_nlist *nl, int *active, uint32_t *chunks, uint32_t *max_tile_atoms, uint32_t *wide_chunks) {
+    if (!nl) { parm_set_error("parm_nlist_tile_stats: NULL list"); return PARM_ERR_INVALID; }
+    const TileState &t = nl->tile;
+    if (active) *active = t.valid ? 1 : 0;
+    if (chunks) *chunks = t.valid ? t.nchunks : 0;
+    if (max_tile_atoms) *max_tile_atoms = t.valid ? t.max_tile : 0;
+    if (wide_chunks) *wide_chunks = t.valid && t.h_info ? t.h_info->wide : 0;
+    return 0;
+}

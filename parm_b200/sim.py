@@ -347,6 +347,13 @@ class NeighborList:
         call("parm_nlist_stats", self._h, C.byref(mean), C.byref(mx))
         return mean.value, mx.value
 
+    def tile_stats(self):
+        """(active, chunks, max_tile_atoms, wide_chunks) of the cell-tile pair kernel after the last rebuild."""
+        act = C.c_int(0)
+        nch, mt, wide = C.c_uint32(0), C.c_uint32(0), C.c_uint32(0)
+        call("parm_nlist_tile_stats", self._h, C.byref(act), C.byref(nch), C.byref(mt), C.byref(wide))
+        return bool(act.value), nch.value, mt.value, wide.value
+
 
 # ---- per-atom parameter structs; .p follows the table in include/parm_b200.h (parm_inter_set_params_ex) ----
 class _PairAtom:

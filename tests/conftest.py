@@ -3,6 +3,9 @@ import sys
 
 import pytest
 
+# every 16-bit tile-local neighbour row is verified against its chunk's tile after each rebuild (csrc/tile.cu)
+os.environ.setdefault("PARM_B200_TILE_CHECK", "1")
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 HERE = os.path.dirname(os.path.abspath(__file__))
 for p_ in (HERE, ROOT):

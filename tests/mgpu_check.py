@@ -54,6 +54,9 @@ def check(name, w, steps, tol_traj=1e-9):
     dist.all_gather_object(parts, (a, b))
     ga1, gb1 = sharded.merge_pairs(parts)
     info = atoms.info()
+    tile = nl.tile_stats()
+    if name == "lj3d_tile":
+        assert tile[0] and tile[3] == 0, "sharded run should use the cell-tile kernel without wide chunks: %r" % (tile,)
     if rank == 0:
         c = cpu_system("port", w, injected=n > 3000)
         ca, cb = c.pairs()
@@ -71,8 +74,8 @@ def check(name, w, steps, tol_traj=1e-9):
         assert rel_err(E1, c.energy()) < 1e-10
         ca, cb = c.pairs()
         assert np.array_equal(ga1, ca) and np.array_equal(gb1, cb), "%s: merged pair set after %d steps differs" % (name, steps)
-        print("mgpu ok: %s world=%d N=%d pairs=%d rebuilds=%d local %s -> %s, rank0 %s" %
-              (name, world, n, len(ca), which, counts, counts1, info), flush=True)
+        print("mgpu ok: %s world=%d N=%d pairs=%d rebuilds=%d local %s -> %s, rank0 %s tile %s" %
+              (name, world, n, len(ca), which, counts, counts1, info, tile), flush=True)
     dist.barrier()
     del collec, inter, nl
     atoms.close()
@@ -85,6 +88,8 @@ def main():
     world = dist.get_world_size()
     # 3-D LJ (config 3/5 state point, small): hot enough that atoms migrate between slabs
     check("lj3d", W.lj_lattice((12 * world, 10, 10), seed=11), steps=60)
+    # wide enough in y and z that the cell-tile pair kernel runs without the per-pair minimum image
+    check("lj3d_tile", W.lj_lattice((14 * world, 28, 28), seed=17), steps=25)
     # binary LJ with long rows: the neighbour species ride in the list entries (ghost rows included)
     wb = W.lj_lattice((12 * world, 10, 10), seed=13)
     tb = (np.arange(wb["x"].shape[0]) % 3 == 0).astype(np.uint32)
