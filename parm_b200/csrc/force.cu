@@ -146,7 +146,7 @@ static int launch_forces(parm_inter *it, int run, bool accumulate, double *d_out
     A.P1 = it->h_table[0];
     if (specmode == 3)
         for (int q = 0; q < 4; q++) A.P4[q] = it->h_table[q];
-    A.mask = nl->packed ? PARM_NBR_SLOT_MASK : 0xffffffffu;
+    A.mask = PARM_NBR_MASK_OF(nl);
     A.packed = nl->packed_for == it && !it->spec_stale;
     A.f = c->f;
     A.vel = c->v;

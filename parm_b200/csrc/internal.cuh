@@ -20,6 +20,7 @@
 #define PARM_MAX_SPECIES 32   // distinct per-atom parameter tuples per interaction
 #define PARM_NBR_SLOT_BITS 27  // neighbour-row entry = slot | species << 27 when packed (parm_nlist::packed_for)
 #define PARM_NBR_SLOT_MASK ((1u << PARM_NBR_SLOT_BITS) - 1u)
+#define PARM_NBR_MASK_OF(nl) (((nl)->packed || (nl)->tagged) ? PARM_NBR_SLOT_MASK : 0xffffffffu)
 #define PARM_PACK_MIN_NEIGHBORS 24 // mean row length from which packing / the two-species register path pay
 
 void parm_set_error(const char *fmt, ...);
@@ -190,6 +191,8 @@ struct parm_nlist {
     // Species packing: when one interaction with 2..32 tabulated species uses this list, the top 5 bits of every
     // row entry carry the neighbour's species id, so the force kernel needs no per-neighbour species gather.
     bool packed;                 // row entries carry a species id in their top bits (mask them)
+    bool tagged;                 // row entries carry the stencil column (0..8) they were found in in their top bits:
+                                 // written by the build kernel for tile.cu's localize pass, dropped by species packing
     parm_inter *packed_for;      // whose species they are (NULL once that interaction is destroyed)
     // NeighborList::ignore (trackers.hpp:190-193): excluded pairs, canonical (larger index, smaller index)
     std::set<std::pair<uint32_t, uint32_t> > ignored;
@@ -326,7 +329,7 @@ int parm_ctx_ensure_red(parm_ctx *ctx, size_t doubles);
 // cell-tile path (csrc/tile.cu)
 int parm_tile_plan_enqueue(parm_nlist *nl);   // chunk table from the cell structure (async, before the build's sync)
 int parm_tile_plan_fetch(parm_nlist *nl);     // queue the device->host copy of the plan summary (before that sync)
-int parm_tile_localize(parm_nlist *nl);       // after the rows are final: write rows16
+int parm_tile_localize(parm_nlist *nl);       // after the rows are final (ignore applied, before species packing): write rows16
 void parm_tile_invalidate(parm_nlist *nl);
 void parm_tile_free(parm_nlist *nl);
 bool parm_tile_usable(const parm_inter *it);  // this interaction can run on the tile kernel right now

@@ -432,7 +432,7 @@ __global__ void __launch_bounds__(CB_WARPS * 32)
 k_build_cell(const double4 *__restrict__ pos, const double4 *__restrict__ pw, const double *__restrict__ diam,
              const uint32_t *__restrict__ cell_start, uint32_t ngroups, int zg, uint32_t n, BoxDev box, GridDev g, StencilDev st,
              double skin, double lmax, double thr_min, double uthr, uint32_t kmax, uint32_t *__restrict__ nbr,
-             uint32_t *__restrict__ cnt, NlistFlags *flags, const uint8_t *__restrict__ ghost) {
+             uint32_t *__restrict__ cnt, NlistFlags *flags, const uint8_t *__restrict__ ghost, uint32_t tagcols) {
     __shared__ double4 s_c[CB_WARPS][32];
     __shared__ uint32_t s_buf[CB_WARPS][8][32];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -489,6 +489,8 @@ k_build_cell(const double4 *__restrict__ pos, const double4 *__restrict__ pw, co
                 double sy = 0.0;
                 if (y2 < 0) { y2 += g.nc[1]; sy = -box.L[1]; }
                 else if (y2 >= g.nc[1]) { y2 -= g.nc[1]; sy = box.L[1]; }
+                // stencil column 0..8 in the top bits of the entries (tile.cu turns them into tile-local indices)
+                const uint32_t tag = tagcols ? (uint32_t)((xx - x0) * 3 + (yy - y0)) << PARM_NBR_SLOT_BITS : 0u;
                 for (int seg = 0; seg < 3; seg++) {
                     int za, zb;
                     double sr = 0.0; // image shift along the run axis
@@ -571,7 +573,7 @@ k_build_cell(const double4 *__restrict__ pos, const double4 *__restrict__ pw, co
                         while (m) { // append this lane's survivors; a full 8-entry buffer leaves as one 32-byte sector
                             const int bit = __ffs(m) - 1;
                             m &= m - 1;
-                            s_buf[wib][count & 7u][lane] = jbase + (uint32_t)bit;
+                            s_buf[wib][count & 7u][lane] = (jbase + (uint32_t)bit) | tag;
                             count++;
                             if ((count & 7u) == 0 && count <= kmax) {
                                 uint4 u0, u1;
@@ -887,8 +889,8 @@ int parm_nlist_append_ghosts(parm_nlist *nl, uint32_t first, uint32_t count) {
 // removed from the finished rows. One warp per slot whose atom has exclusions; the row is compacted in place
 // (stable), 32 entries at a time.
 __global__ void k_apply_ignore(const uint32_t *__restrict__ order, const uint32_t *__restrict__ excl_start,
-                               const uint32_t *__restrict__ excl, uint32_t nown, uint32_t kmax, uint32_t *nbr, uint32_t *cnt,
-                               NlistFlags *flags) {
+                               const uint32_t *__restrict__ excl, uint32_t nown, uint32_t kmax, uint32_t mask, uint32_t *nbr,
+                               uint32_t *cnt, NlistFlags *flags) {
     const uint32_t s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint32_t lane = threadIdx.x & 31;
     if (s >= nown) return;
@@ -901,10 +903,10 @@ __global__ void k_apply_ignore(const uint32_t *__restrict__ order, const uint32_
     for (uint32_t k0 = 0; k0 < my; k0 += 32) {
         const uint32_t k = k0 + lane;
         const bool valid = k < my;
-        const uint32_t j = valid ? row[k] : 0;
+        const uint32_t j = valid ? row[k] : 0; // (tag bits move with the entry)
         bool keep = valid;
         if (valid) {
-            const uint32_t jid = order[j];
+            const uint32_t jid = order[j & mask];
             for (uint32_t e = e0; e < e1; e++) keep = keep && excl[e] != jid;
         }
         const uint32_t m = __ballot_sync(0xffffffffu, keep);
@@ -940,7 +942,7 @@ static int apply_ignore(parm_nlist *nl) {
     const uint32_t nown = parm_owned(c);
     if (!nown) return 0;
     k_apply_ignore<<<(unsigned)(((size_t)nown * 32 + 255) / 256), 256, 0, c->stream>>>(c->order, nl->d_excl_start, nl->d_excl, nown,
-                                                                                      nl->kmax, nl->nbr, nl->cnt, nl->d_flags);
+                                                                                      nl->kmax, PARM_NBR_MASK_OF(nl), nl->nbr, nl->cnt, nl->d_flags);
     CK_LAUNCH(c);
     CK(cudaMemcpyAsync(nl->h_flags, nl->d_flags, sizeof(NlistFlags), cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
@@ -958,7 +960,7 @@ __global__ void k_pack_species(const uint8_t *__restrict__ spec, uint32_t nown, 
     const uint32_t my = min(cnt[s], kmax);
     uint32_t *row = nbr + (size_t)s * kmax;
     for (uint32_t k = lane; k < my; k += 32) {
-        const uint32_t j = row[k];
+        const uint32_t j = row[k] & PARM_NBR_SLOT_MASK; // drops the stencil-column tag of the build
         row[k] = j | ((uint32_t)spec[j] << PARM_NBR_SLOT_BITS);
     }
 }
@@ -979,6 +981,7 @@ static int pack_species(parm_nlist *nl) {
     k_pack_species<<<(unsigned)(((size_t)nown * 32 + 255) / 256), 256, 0, c->stream>>>(primary->d_spec, nown, nl->kmax, nl->nbr, nl->cnt);
     CK_LAUNCH(c);
     nl->packed = true;
+    nl->tagged = false;
     nl->packed_for = primary;
     primary->spec_stale = false;
     return 0;
@@ -986,8 +989,8 @@ static int pack_species(parm_nlist *nl) {
 
 static int finish_rows(parm_nlist *nl) {
     PTRY(apply_ignore(nl));
-    PTRY(pack_species(nl));
-    return parm_tile_localize(nl); // 16-bit tile-local rows for the cell-tile pair kernel (tile.cu)
+    PTRY(parm_tile_localize(nl)); // 16-bit tile-local rows for the cell-tile pair kernel (tile.cu): needs the column tags
+    return pack_species(nl);
 }
 
 // Build the rows for the atoms now in slots 0..n-1, growing the per-atom capacity if a row overflowed.
@@ -1015,11 +1018,15 @@ int parm_nlist_build_rows(parm_nlist *nl) {
         CK(cudaMemsetAsync((char *)nl->d_flags + offsetof(NlistFlags, maxcnt), 0,
                            offsetof(NlistFlags, xmax_bits) - offsetof(NlistFlags, maxcnt), c->stream));
 #define CARGS c->pos, nl->pw, nl->d_diam, nl->cell_start, ngroups, zg, n, c->box, nl->g, nl->st, nl->skin, nl->lmax, \
-              nl->thr_min, uthr, nl->kmax, nl->nbr, nl->cnt, nl->d_flags, c->sh.on ? c->ghost : nullptr
+              nl->thr_min, uthr, nl->kmax, nl->nbr, nl->cnt, nl->d_flags, c->sh.on ? c->ghost : nullptr, tagcols
 #define BARGS c->pos, nl->pw, nl->d_diam, nl->cell_id_sorted, nl->cell_start, n, c->box, nl->g, nl->st, nl->skin, nl->lmax, \
               nl->thr_min, uthr, nl->kmax, nl->nbr, nl->cnt, nl->d_flags, c->sh.on ? c->ghost : nullptr
         static int per_cell = -1;
         if (per_cell < 0) { const char *e = getenv("PARM_B200_BUILD_PER_CELL"); per_cell = e ? atoi(e) : 1; }
+        // with a tile plan (3 x 3 stencil columns, tile.cu) the entries carry their stencil column in the top bits
+        const uint32_t tagcols = per_cell && nl->tile.planned && c->npad <= PARM_NBR_SLOT_MASK ? 1u : 0u;
+        nl->tagged = tagcols != 0;
+        if (!tagcols) parm_tile_invalidate(nl);
         if (per_cell) {
             // one warp per group of zg consecutive cells along the run axis, ~28 atoms per group
             const bool run2d = c->D == 2;
@@ -1154,7 +1161,7 @@ static int collect_pairs(parm_nlist *nl, std::vector<std::pair<uint32_t, uint32_
         const uint32_t i = h_order[s];
         const uint32_t *row = h_nbr.data() + (size_t)s * nl->kmax;
         for (uint32_t q = 0; q < h_cnt[s]; q++) {
-            uint32_t j = h_order[nl->packed ? (row[q] & PARM_NBR_SLOT_MASK) : row[q]];
+            uint32_t j = h_order[row[q] & PARM_NBR_MASK_OF(nl)];
             if (j < i) out.push_back(std::make_pair(i, j));
         }
     }

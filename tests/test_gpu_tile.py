@@ -63,7 +63,7 @@ def _check_against_oracle(w, sim, steps=0, expect_wide=None):
     return nl
 
 
-@pytest.mark.parametrize("team,v,ch", [(4, 8, 128), (4, 4, 64), (8, 4, 256), (2, 8, 96)])
+@pytest.mark.parametrize("team,v,ch", [(4, 8, 128), (4, 4, 64), (8, 4, 112), (2, 8, 96)])
 def test_tile_narrow_chunks_vs_oracle(oracle_built, team, v, ch):
     """Box of 12 cells per axis: chunks cover a few cells of a column, no per-pair minimum image; every
     (team, entries per lane, chunk size) variant of the kernel."""

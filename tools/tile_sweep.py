@@ -49,7 +49,7 @@ def main():
     a = ap.parse_args()
     w = W.config3(a.side)
     run(w, a.steps, {"PARM_B200_TILE": 0})
-    combos = [(4, 8, 128), (4, 4, 128), (8, 4, 128), (2, 8, 128), (4, 8, 64), (4, 8, 256), (4, 4, 64), (8, 4, 256)]
+    combos = [(4, 8, 128), (4, 4, 128), (2, 8, 128), (4, 8, 96), (4, 8, 160), (4, 8, 192)]
     if a.quick:
         combos = combos[:2]
     for team, v, ch in combos:
