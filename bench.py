@@ -218,15 +218,19 @@ def run_ours(args):
     tp = os.path.join(ROOT, "profiles", "force_kernel_traffic.json")
     if os.path.exists(tp):
         try:
-            traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+            tj = json.load(open(tp))
+            traffic = tj.get("dram_bytes_per_launch") if nl.tile_stats()[0] else tj.get("gather_kernel", {}).get("dram_bytes_per_launch")
         except Exception:
             traffic = None
     roofline = {
-        "bound": "hbm", "kernel": "k_force<LJAttractRepulse> (pair force, full neighbour rows)",
+        "bound": "hbm",
+        "kernel": ("k_force_tile<LJAttractRepulse> (pair force, full neighbour rows, positions staged per cell tile in "
+                   "shared memory)" if nl.tile_stats()[0] else "k_force<LJAttractRepulse> (pair force, full neighbour rows)"),
         "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm, "traffic": traffic,
         "peak_source": hbm_src, "algorithmic_bytes_per_launch": bytes_force, "mean_full_neighbors": mean_n,
         "kernel_ms": force_ms,
         "fp64_gflops_est": 30.0 * mean_n * n / (force_ms * 1e-3) / 1e9,  # ~30 flop/pair, SURVEY 8d
+        "tile": dict(zip(("active", "chunks", "max_tile_atoms", "wide_chunks"), nl.tile_stats())),
         "step_share": {"integrate1_ms": pms[0] / max(pcnt[0], 1), "force_ms": force_ms,
                        "integrate2_drift_ms": pms[2] / max(pcnt[2], 1),
                        "rebuild_ms_each": pms[3] / max(pcnt[3], 1), "rebuilds": int(pcnt[3]), "steps": K},

@@ -434,7 +434,7 @@ k_build_cell(const double4 *__restrict__ pos, const double4 *__restrict__ pw, co
              double skin, double lmax, double thr_min, double uthr, uint32_t kmax, uint32_t *__restrict__ nbr,
              uint32_t *__restrict__ cnt, NlistFlags *flags, const uint8_t *__restrict__ ghost, uint32_t tagcols) {
     __shared__ double4 s_c[CB_WARPS][32];
-    __shared__ uint32_t s_buf[CB_WARPS][8][32];
+    __shared__ uint32_t s_buf[CB_WARPS][16][32]; // per lane: ring of 16 pending row entries, flushed 8 (one 32-byte sector) at a time
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const uint32_t cur = blockIdx.x * CB_WARPS + wib;
     if (cur >= ngroups) return;
@@ -475,8 +475,17 @@ k_build_cell(const double4 *__restrict__ pos, const double4 *__restrict__ pw, co
             if (valid) cnt[i] = 0;
             continue;
         }
-        uint32_t count = 0;
+        uint32_t count = 0, flushed = 0; // entries found / entries already written to the row (a multiple of 8)
         uint32_t *row = nbr + (size_t)(valid ? i : a0) * kmax;
+        auto flush8 = [&](uint32_t *r, uint32_t at) {
+            const uint32_t h = at & 8u;
+            uint4 u0, u1;
+            u0.x = s_buf[wib][h + 0][lane]; u0.y = s_buf[wib][h + 1][lane]; u0.z = s_buf[wib][h + 2][lane]; u0.w = s_buf[wib][h + 3][lane];
+            u1.x = s_buf[wib][h + 4][lane]; u1.y = s_buf[wib][h + 5][lane]; u1.z = s_buf[wib][h + 6][lane]; u1.w = s_buf[wib][h + 7][lane];
+            uint4 *dst = reinterpret_cast<uint4 *>(r + at);
+            dst[0] = u0;
+            dst[1] = u1;
+        };
         for (int xx = x0; xx <= x1; xx++) {
             int x2 = xx;
             double sx = 0.0;
@@ -570,27 +579,29 @@ k_build_cell(const double4 *__restrict__ pos, const double4 *__restrict__ pw, co
                             }
                         }
                         if (!member) m = 0;
-                        while (m) { // append this lane's survivors; a full 8-entry buffer leaves as one 32-byte sector
+                        // append this lane's survivors to its ring; full groups of 8 leave as one 32-byte sector. The flush
+                        // is checked once per candidate block (not per survivor: with 32 lanes some lane would be flushing
+                        // in nearly every iteration of the divergent loop), inside the loop only when the ring is full
+                        while (m) {
                             const int bit = __ffs(m) - 1;
                             m &= m - 1;
-                            s_buf[wib][count & 7u][lane] = (jbase + (uint32_t)bit) | tag;
+                            s_buf[wib][count & 15u][lane] = (jbase + (uint32_t)bit) | tag;
                             count++;
-                            if ((count & 7u) == 0 && count <= kmax) {
-                                uint4 u0, u1;
-                                u0.x = s_buf[wib][0][lane]; u0.y = s_buf[wib][1][lane]; u0.z = s_buf[wib][2][lane]; u0.w = s_buf[wib][3][lane];
-                                u1.x = s_buf[wib][4][lane]; u1.y = s_buf[wib][5][lane]; u1.z = s_buf[wib][6][lane]; u1.w = s_buf[wib][7][lane];
-                                uint4 *dst = reinterpret_cast<uint4 *>(row + (count - 8));
-                                dst[0] = u0;
-                                dst[1] = u1;
+                            if (count - flushed == 16u) {
+                                if (flushed + 8 <= kmax) flush8(row, flushed);
+                                flushed += 8;
                             }
+                        }
+                        if (count - flushed >= 8u) {
+                            if (flushed + 8 <= kmax) flush8(row, flushed);
+                            flushed += 8;
                         }
                     }
                 }
             }
         }
         if (member) { // tail of the row
-            const uint32_t done = count & ~7u;
-            for (uint32_t k = done; k < count && k < kmax; k++) row[k] = s_buf[wib][k & 7u][lane];
+            for (uint32_t k = flushed; k < count && k < kmax; k++) row[k] = s_buf[wib][k & 15u][lane];
         }
         if (valid) cnt[i] = count;
         wsum_tot += count;
