@@ -424,16 +424,31 @@ k_build(const double4 *__restrict__ pos, const double4 *__restrict__ pw, const d
 // one full 32-byte sector, so the row stores cost one L2 transaction per 8 neighbours. Same banded
 // classification / exact predicate as k_build; ~2.4x fewer instructions per candidate test.
 #define CB_WARPS 4
+// packed fp32 pairs (FADD2 / FMUL2 / FFMA2 on sm_100): two candidates per instruction in the fp32 pre-test
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 f2_add(f32x2 a, f32x2 b) { f32x2 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ f32x2 f2_sub(f32x2 a, f32x2 b) { f32x2 r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ f32x2 f2_mul(f32x2 a, f32x2 b) { f32x2 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ f32x2 f2_fma(f32x2 a, f32x2 b, f32x2 c) { f32x2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+__device__ __forceinline__ f32x2 f2_dup(float x) { const unsigned long long b = __float_as_uint(x); return b | (b << 32); }
 // RUN2D: in 2-D the cells that are contiguous in slot order run along y (z is a single layer), so y takes the
 // role of the run axis. zg: consecutive cells of the run axis handled by one warp (sparse systems have only a
 // few atoms per cell; grouping keeps the lanes busy and shares the stencil between the group's cells).
-template <bool SMALLBOX, bool UNIFORM, bool RUN2D>
+// F32: candidates are first classified in packed fp32 on coordinates relative to the centre of the warp's own
+// cells (two candidates per FADD2/FFMA2, pass bits collected with funnel shifts of the sign of
+// bits(dsq) - bits(threshold)): clearly inside / clearly outside a relative band beta32 (the rigorous fp32
+// rounding bound, x3) around the threshold. A lane that sees a candidate inside that band repeats the block
+// with the fp64 test below (which in turn defers to the reference's exact predicate inside its own ~1e-9 band),
+// so the pair set stays bit-exact; ~1e-5 of the tests take that path.
+template <bool SMALLBOX, bool UNIFORM, bool RUN2D, bool F32>
 __global__ void __launch_bounds__(CB_WARPS * 32)
 k_build_cell(const double4 *__restrict__ pos, const double4 *__restrict__ pw, const double *__restrict__ diam,
              const uint32_t *__restrict__ cell_start, uint32_t ngroups, int zg, uint32_t n, BoxDev box, GridDev g, StencilDev st,
              double skin, double lmax, double thr_min, double uthr, uint32_t kmax, uint32_t *__restrict__ nbr,
-             uint32_t *__restrict__ cnt, NlistFlags *flags, const uint8_t *__restrict__ ghost, uint32_t tagcols) {
+             uint32_t *__restrict__ cnt, NlistFlags *flags, const uint8_t *__restrict__ ghost, uint32_t tagcols,
+             double cs0, double beta32) {
     __shared__ double4 s_c[CB_WARPS][32];
+    __shared__ __align__(8) float s_fx[CB_WARPS][32], s_fy[CB_WARPS][32], s_fz[CB_WARPS][32], s_fw[CB_WARPS][32];
     __shared__ uint32_t s_buf[CB_WARPS][16][32]; // per lane: ring of 16 pending row entries, flushed 8 (one 32-byte sector) at a time
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const uint32_t cur = blockIdx.x * CB_WARPS + wib;
@@ -456,6 +471,13 @@ k_build_cell(const double4 *__restrict__ pos, const double4 *__restrict__ pw, co
     const double delta = band_delta(flags, lmax, thr_min);
     const double lo = ((1.0 - delta) / (1.0 + delta)) * ((1.0 - delta) / (1.0 + delta));
     const double uthr2 = uthr * (1.0 + delta) * (uthr * (1.0 + delta)), uthr2lo = uthr2 * lo;
+    // fp32 pre-test: origin = centre of the warp's own cells (frame of pw), thresholds widened by the band
+    const double bt = beta32 + 4.0 * delta;
+    const double Ox = ((double)cx + 0.5) * cs0;
+    const double Oy = RUN2D ? 0.5 * (double)(cr0 + cr1 + 1) / g.scale[1] : ((double)cy + 0.5) / g.scale[1];
+    const double Oz = RUN2D ? 0.0 : 0.5 * (double)(cr0 + cr1 + 1) / g.scale[2];
+    const uint32_t u_thi = __float_as_uint(__double2float_ru(uthr2 * (1.0 + bt))), u_tlo = __float_as_uint(__double2float_rd(uthr2lo * (1.0 - bt)));
+    const f32x2 c_hi2 = f2_dup(__double2float_ru(1.0 + bt)), c_lo2 = f2_dup(__double2float_rd(lo * (1.0 - bt)));
     int x0 = st.full[0] ? cx - st.sub : 0, x1 = st.full[0] ? cx + st.sub : g.nc[0] - 1;
     if (st.open0) { // slab axis: layer -1 is the halo below (stored as layer nc-1), layer nc-2 the halo above
         x0 = cx - 1;
@@ -475,6 +497,8 @@ k_build_cell(const double4 *__restrict__ pos, const double4 *__restrict__ pw, co
             if (valid) cnt[i] = 0;
             continue;
         }
+        const f32x2 xi2 = f2_dup((float)(wi.x - Ox)), yi2 = f2_dup((float)(wi.y - Oy)), zi2 = f2_dup((float)(wi.z - Oz));
+        const f32x2 wi2 = f2_dup((float)wi.w);
         uint32_t count = 0, flushed = 0; // entries found / entries already written to the row (a multiple of 8)
         uint32_t *row = nbr + (size_t)(valid ? i : a0) * kmax;
         auto flush8 = [&](uint32_t *r, uint32_t at) {
@@ -520,41 +544,90 @@ k_build_cell(const double4 *__restrict__ pos, const double4 *__restrict__ pw, co
                             wj.z += sz;
                             __syncwarp();
                             s_c[wib][lane] = wj;
+                            if (F32) { // non-members and lanes past the end of the run hold NaN and fail every test
+                                const bool cand = wj.w == wj.w;
+                                s_fx[wib][lane] = cand ? (float)(wj.x - Ox) : __int_as_float(0x7fffffff);
+                                s_fy[wib][lane] = (float)(wj.y - Oy);
+                                s_fz[wib][lane] = (float)(wj.z - Oz);
+                                s_fw[wib][lane] = (float)wj.w;
+                            }
                             __syncwarp();
                         }
                         const int nb = (int)min(32u, je - jbase);
                         const uint32_t iself = i - jbase; // candidate index of this lane's own atom, if in the block
                         uint32_t m = 0;
                         bool near_any = false;
-                        // 4 x 8: the inner 8 tests are unrolled (bit position = immediate + c0); lanes past the end of the
-                        // run hold NaN and fail every test
-                        for (int c0 = 0; c0 < 32; c0 += 8) {
-                            uint32_t m8 = 0;
+                        // fp64 test, 4 x 8: the inner 8 tests are unrolled (bit position = immediate + c0); lanes past the end
+                        // of the run hold NaN and fail every test
+                        auto test64 = [&]() {
+                            m = 0;
+                            for (int c0 = 0; c0 < 32; c0 += 8) {
+                                uint32_t m8 = 0;
 #pragma unroll
-                            for (int k = 0; k < 8; k++) {
-                                const double4 q = s_c[wib][c0 + k];
-                                double dx = wi.x - q.x, dy = wi.y - q.y, dz = wi.z - q.z;
-                                if (SMALLBOX) {
-                                    if (!st.open0) dx = min_image_fast(dx, box.L[0], box.invL[0]);
-                                    dy = min_image_fast(dy, box.L[1], box.invL[1]);
-                                    dz = min_image_fast(dz, box.L[2], box.invL[2]);
+                                for (int k = 0; k < 8; k++) {
+                                    const double4 q = s_c[wib][c0 + k];
+                                    double dx = wi.x - q.x, dy = wi.y - q.y, dz = wi.z - q.z;
+                                    if (SMALLBOX) {
+                                        if (!st.open0) dx = min_image_fast(dx, box.L[0], box.invL[0]);
+                                        dy = min_image_fast(dy, box.L[1], box.invL[1]);
+                                        dz = min_image_fast(dz, box.L[2], box.invL[2]);
+                                    }
+                                    const double dsq = fma(dx, dx, fma(dy, dy, dz * dz));
+                                    double thr2, thr2lo;
+                                    if (UNIFORM) {
+                                        thr2 = uthr2;
+                                        thr2lo = uthr2lo;
+                                    } else {
+                                        const double thr = wi.w + q.w; // NaN for non-members
+                                        thr2 = thr * thr;
+                                        thr2lo = thr2 * lo;
+                                    }
+                                    const bool pass = dsq < thr2;
+                                    near_any |= pass && !(dsq < thr2lo);
+                                    if (pass) m8 |= 1u << k;
                                 }
-                                const double dsq = fma(dx, dx, fma(dy, dy, dz * dz));
-                                double thr2, thr2lo;
-                                if (UNIFORM) {
-                                    thr2 = uthr2;
-                                    thr2lo = uthr2lo;
-                                } else {
-                                    const double thr = wi.w + q.w; // NaN for non-members
-                                    thr2 = thr * thr;
-                                    thr2lo = thr2 * lo;
-                                }
-                                const bool pass = dsq < thr2;
-                                near_any |= pass && !(dsq < thr2lo);
-                                if (pass) m8 |= 1u << k;
+                                m |= m8 << c0;
+                                if (c0 + 8 >= nb) break;
                             }
-                            m |= m8 << c0;
-                            if (c0 + 8 >= nb) break;
+                        };
+                        if (F32) {
+                            uint32_t mp = 0, mi = 0; // "possibly inside" / "certainly inside", first candidate in the top bit
+                            int done = 0;
+                            for (int c0 = 0; c0 < 32; c0 += 8) {
+#pragma unroll
+                                for (int k = 0; k < 4; k++) {
+                                    const int p2 = c0 + 2 * k;
+                                    const f32x2 dx = f2_sub(xi2, *reinterpret_cast<const f32x2 *>(&s_fx[wib][p2]));
+                                    const f32x2 dy = f2_sub(yi2, *reinterpret_cast<const f32x2 *>(&s_fy[wib][p2]));
+                                    const f32x2 dz = f2_sub(zi2, *reinterpret_cast<const f32x2 *>(&s_fz[wib][p2]));
+                                    const f32x2 dsq = f2_fma(dx, dx, f2_fma(dy, dy, f2_mul(dz, dz)));
+                                    uint32_t h0 = u_thi, h1 = u_thi, l0 = u_tlo, l1 = u_tlo;
+                                    if (!UNIFORM) {
+                                        const f32x2 t = f2_add(wi2, *reinterpret_cast<const f32x2 *>(&s_fw[wib][p2]));
+                                        const f32x2 t2 = f2_mul(t, t);
+                                        const f32x2 th = f2_mul(t2, c_hi2), tl = f2_mul(t2, c_lo2);
+                                        h0 = (uint32_t)th; h1 = (uint32_t)(th >> 32);
+                                        l0 = (uint32_t)tl; l1 = (uint32_t)(tl >> 32);
+                                    }
+                                    // non-negative floats order like their bit patterns; NaN (0x7fffffff) is never below a threshold
+                                    const uint32_t s0 = (uint32_t)dsq, s1 = (uint32_t)(dsq >> 32);
+                                    mp = __funnelshift_l(s0 - h0, mp, 1);
+                                    mi = __funnelshift_l(s0 - l0, mi, 1);
+                                    mp = __funnelshift_l(s1 - h1, mp, 1);
+                                    mi = __funnelshift_l(s1 - l1, mi, 1);
+                                }
+                                done = c0 + 8;
+                                if (done >= nb) break;
+                            }
+                            mp = __brev(mp << (32 - done));
+                            mi = __brev(mi << (32 - done));
+                            m = mp;
+                            const bool near32 = (mp & ~mi) != 0 && member;
+                            if (__any_sync(0xffffffffu, near32)) {
+                                if (near32) test64(); // some candidate within the fp32 band: this lane repeats the block in fp64
+                            }
+                        } else {
+                            test64();
                         }
                         if (iself < 32u) m &= ~(1u << iself); // never its own neighbour
                         if (__any_sync(0xffffffffu, near_any && member)) {
@@ -1029,7 +1102,7 @@ int parm_nlist_build_rows(parm_nlist *nl) {
         CK(cudaMemsetAsync((char *)nl->d_flags + offsetof(NlistFlags, maxcnt), 0,
                            offsetof(NlistFlags, xmax_bits) - offsetof(NlistFlags, maxcnt), c->stream));
 #define CARGS c->pos, nl->pw, nl->d_diam, nl->cell_start, ngroups, zg, n, c->box, nl->g, nl->st, nl->skin, nl->lmax, \
-              nl->thr_min, uthr, nl->kmax, nl->nbr, nl->cnt, nl->d_flags, c->sh.on ? c->ghost : nullptr, tagcols
+              nl->thr_min, uthr, nl->kmax, nl->nbr, nl->cnt, nl->d_flags, c->sh.on ? c->ghost : nullptr, tagcols, cs0, beta32
 #define BARGS c->pos, nl->pw, nl->d_diam, nl->cell_id_sorted, nl->cell_start, n, c->box, nl->g, nl->st, nl->skin, nl->lmax, \
               nl->thr_min, uthr, nl->kmax, nl->nbr, nl->cnt, nl->d_flags, c->sh.on ? c->ghost : nullptr
         static int per_cell = -1;
@@ -1052,13 +1125,27 @@ int parm_nlist_build_rows(parm_nlist *nl) {
             const uint32_t gpc = (uint32_t)((ncr + zg - 1) / zg);
             const uint32_t ngroups = (uint32_t)nl->g.nc[0] * (run2d ? 1u : (uint32_t)nl->g.nc[1]) * gpc;
             const unsigned cblocks = (ngroups + CB_WARPS - 1) / CB_WARPS;
-#define CLAUNCH(SB, UN)                                                                                         \
+            // fp32 pre-test: |coordinate - warp origin| <= E, so |dsq32 - dsq| <= (6.93 E / thr + 5) 2^-24 thr^2 at the
+            // threshold, plus 7 x 2^-24 for a per-pair threshold formed in fp32 and 2 x 2^-24 for its scaling; x3 margin
+            const double cs0 = c->sh.on ? nl->sd.Ls / nl->sd.nci : c->box.L[0] / nl->g.nc[0];
+            double ext = (nl->st.sub + 1.0) * cs0;
+            for (int d = 1; d < c->D; d++) {
+                const double cs = c->box.L[d] / nl->g.nc[d];
+                ext = std::max(ext, d == rax ? (0.5 * zg + nl->st.sub) * cs : (nl->st.sub + 1.0) * cs);
+            }
+            double beta32 = 3.0 * ((6.93 * ext / nl->thr_min + 14.0) * 5.9604644775390625e-8);
+            static int use_f32 = -1;
+            if (use_f32 < 0) { const char *e = getenv("PARM_B200_BUILD_F32"); use_f32 = e ? atoi(e) : 1; }
+            const bool f32 = use_f32 && !nl->smallbox && beta32 < 1e-4;
+            if (!f32) beta32 = 0.0;
+#define CLAUNCH(SB, UN, F)                                                                                      \
     do {                                                                                                        \
-        if (run2d) k_build_cell<SB, UN, true><<<cblocks, CB_WARPS * 32, 0, c->stream>>>(CARGS);                    \
-        else k_build_cell<SB, UN, false><<<cblocks, CB_WARPS * 32, 0, c->stream>>>(CARGS);                         \
+        if (run2d) k_build_cell<SB, UN, true, F><<<cblocks, CB_WARPS * 32, 0, c->stream>>>(CARGS);                 \
+        else k_build_cell<SB, UN, false, F><<<cblocks, CB_WARPS * 32, 0, c->stream>>>(CARGS);                      \
     } while (0)
-            if (nl->smallbox) { if (nl->uniform) CLAUNCH(true, true); else CLAUNCH(true, false); }
-            else { if (nl->uniform) CLAUNCH(false, true); else CLAUNCH(false, false); }
+            if (nl->smallbox) { if (nl->uniform) CLAUNCH(true, true, false); else CLAUNCH(true, false, false); }
+            else if (f32) { if (nl->uniform) CLAUNCH(false, true, true); else CLAUNCH(false, false, true); }
+            else { if (nl->uniform) CLAUNCH(false, true, false); else CLAUNCH(false, false, false); }
 #undef CLAUNCH
         } else if (nl->smallbox) {
             if (nl->uniform) k_build<true, true><<<nblocks, BUILD_WARPS * 32, 0, c->stream>>>(BARGS);

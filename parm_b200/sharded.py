@@ -278,7 +278,11 @@ def bench_main(args, rank, world, local, metric, unit, config, peak):
             "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic", "config": config, "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
             "rebuilds_in_timed_region": int(rebuilds),
-            "roofline": {"bound": "hbm", "kernel": "k_force<LJAttractRepulse> (rank 0 share)", "achieved": achieved,
+            "roofline": {"bound": "hbm",
+                         "kernel": ("k_force_tile<LJAttractRepulse> (rank 0 share; cell tiles staged in shared memory)"
+                                    if nl.tile_stats()[0] else "k_force<LJAttractRepulse> (rank 0 share)"),
+                         "tile": dict(zip(("active", "chunks", "max_tile_atoms", "wide_chunks"), nl.tile_stats())),
+                         "achieved": achieved,
                          "peak": hbm, "unit": "GB/s", "frac": achieved / hbm, "traffic": None, "peak_source": hbm_src,
                          "algorithmic_bytes_per_launch": bytes_force, "mean_full_neighbors": mean_n, "kernel_ms": force_ms,
                          "step_share": {"integrate1_ms": pms[0] / max(pcnt[0], 1), "force_ms": force_ms,
