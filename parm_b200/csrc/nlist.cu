@@ -449,7 +449,7 @@ k_build_cell(const double4 *__restrict__ pos, const double4 *__restrict__ pw, co
              double cs0, double beta32) {
     __shared__ double4 s_c[CB_WARPS][32];
     __shared__ __align__(8) float s_fx[CB_WARPS][32], s_fy[CB_WARPS][32], s_fz[CB_WARPS][32], s_fw[CB_WARPS][32];
-    __shared__ uint32_t s_buf[CB_WARPS][16][32]; // per lane: ring of 16 pending row entries, flushed 8 (one 32-byte sector) at a time
+    __shared__ uint32_t s_buf[CB_WARPS][64][32]; // per lane: ring of 64 pending row entries (a block adds <= 32 to <= 7), flushed 8 (one 32-byte sector) at a time
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const uint32_t cur = blockIdx.x * CB_WARPS + wib;
     if (cur >= ngroups) return;
@@ -502,7 +502,7 @@ k_build_cell(const double4 *__restrict__ pos, const double4 *__restrict__ pw, co
         uint32_t count = 0, flushed = 0; // entries found / entries already written to the row (a multiple of 8)
         uint32_t *row = nbr + (size_t)(valid ? i : a0) * kmax;
         auto flush8 = [&](uint32_t *r, uint32_t at) {
-            const uint32_t h = at & 8u;
+            const uint32_t h = at & 56u;
             uint4 u0, u1;
             u0.x = s_buf[wib][h + 0][lane]; u0.y = s_buf[wib][h + 1][lane]; u0.z = s_buf[wib][h + 2][lane]; u0.w = s_buf[wib][h + 3][lane];
             u1.x = s_buf[wib][h + 4][lane]; u1.y = s_buf[wib][h + 5][lane]; u1.z = s_buf[wib][h + 6][lane]; u1.w = s_buf[wib][h + 7][lane];
@@ -653,19 +653,16 @@ k_build_cell(const double4 *__restrict__ pos, const double4 *__restrict__ pw, co
                         }
                         if (!member) m = 0;
                         // append this lane's survivors to its ring; full groups of 8 leave as one 32-byte sector. The flush
-                        // is checked once per candidate block (not per survivor: with 32 lanes some lane would be flushing
-                        // in nearly every iteration of the divergent loop), inside the loop only when the ring is full
+                        // is checked once per candidate block, not per survivor: with 32 lanes some lane would be flushing
+                        // in nearly every iteration of the divergent loop
+                        const uint32_t jt = jbase | tag;
                         while (m) {
                             const int bit = __ffs(m) - 1;
                             m &= m - 1;
-                            s_buf[wib][count & 15u][lane] = (jbase + (uint32_t)bit) | tag;
+                            s_buf[wib][count & 63u][lane] = jt + (uint32_t)bit;
                             count++;
-                            if (count - flushed == 16u) {
-                                if (flushed + 8 <= kmax) flush8(row, flushed);
-                                flushed += 8;
-                            }
                         }
-                        if (count - flushed >= 8u) {
+                        while (count - flushed >= 8u) {
                             if (flushed + 8 <= kmax) flush8(row, flushed);
                             flushed += 8;
                         }
@@ -674,7 +671,7 @@ k_build_cell(const double4 *__restrict__ pos, const double4 *__restrict__ pw, co
             }
         }
         if (member) { // tail of the row
-            for (uint32_t k = flushed; k < count && k < kmax; k++) row[k] = s_buf[wib][k & 15u][lane];
+            for (uint32_t k = flushed; k < count && k < kmax; k++) row[k] = s_buf[wib][k & 63u][lane];
         }
         if (valid) cnt[i] = count;
         wsum_tot += count;
