@@ -56,7 +56,7 @@ __device__ __forceinline__ void lj_eval(const PairConst &P, double c12, double d
 }
 
 template <int KIND, int MODE, int TEAM, int V, bool MI>
-__device__ __forceinline__ void tile_rows(const TileForceArgs &A, const TileChunk *C, const double *sx, const double *sy,
+__device__ __forceinline__ void tile_rows(const TileForceArgs &A, const TileChunk *C, const double2 *sxy,
                                           const double *sz, double (&acc)[NPART]) {
     constexpr bool want_obs = MODE != MODE_F;
     const uint32_t tl = threadIdx.x % TEAM;
@@ -86,7 +86,8 @@ __device__ __forceinline__ void tile_rows(const TileForceArgs &A, const TileChun
 #pragma unroll
             for (int e = 0; e < V; e++) {
                 const uint32_t idx = (e & 1) ? (w[e >> 1] >> 16) : (w[e >> 1] & 0xffffu);
-                double dx = xi - sx[idx], dy = yi - sy[idx], dz = zi - sz[idx];
+                const double2 pxy = sxy[idx]; // one LDS.128 (quarter-warp phases: two teams share a phase, not four)
+                double dx = xi - pxy.x, dy = yi - pxy.y, dz = zi - sz[idx];
                 if (MI) {
                     dx = min_image_fast(dx, A.box.L[0], A.box.invL[0]);
                     dy = min_image_fast(dy, A.box.L[1], A.box.invL[1]);
@@ -136,12 +137,13 @@ __device__ __forceinline__ void tile_rows(const TileForceArgs &A, const TileChun
 template <int KIND, int MODE, int TEAM, int V>
 __global__ void __launch_bounds__(TILE_NT) k_force_tile(const TileForceArgs A) {
     if (A.abort_flag && *A.abort_flag) return; // speculatively enqueued step whose predecessor asked for a rebuild
-    extern __shared__ double s_xyz[];
+    extern __shared__ __align__(16) double s_xyz[];
     __shared__ uint32_t s_start[TILE_MAXSEG], s_off[TILE_MAXSEG + 1];
     const TileChunk *C = A.chunks + blockIdx.x;
     if (threadIdx.x < TILE_MAXSEG) s_start[threadIdx.x] = C->seg_start[threadIdx.x];
     if (threadIdx.x <= TILE_MAXSEG) s_off[threadIdx.x] = C->seg_off[threadIdx.x];
-    double *sx = s_xyz, *sy = s_xyz + A.cap, *sz = s_xyz + 2 * (size_t)A.cap;
+    double2 *sxy = reinterpret_cast<double2 *>(s_xyz); // (x, y) pairs, then the z array
+    double *sz = s_xyz + 2 * (size_t)A.cap;
     const uint32_t ntile = C->ntile;
     const double ox = C->o[0], oy = C->o[1], oz = C->o[2];
     __syncthreads();
@@ -150,19 +152,21 @@ __global__ void __launch_bounds__(TILE_NT) k_force_tile(const TileForceArgs A) {
         for (uint32_t t = threadIdx.x; t < ntile; t += TILE_NT) {
             while (t >= s_off[seg + 1]) seg++;
             const double4 p = A.pos[s_start[seg] + (t - s_off[seg])];
-            sx[t] = min_image_fast(p.x - ox, A.box.L[0], A.box.invL[0]);
-            sy[t] = min_image_fast(p.y - oy, A.box.L[1], A.box.invL[1]);
+            sxy[t] = make_double2(min_image_fast(p.x - ox, A.box.L[0], A.box.invL[0]), min_image_fast(p.y - oy, A.box.L[1], A.box.invL[1]));
             sz[t] = min_image_fast(p.z - oz, A.box.L[2], A.box.invL[2]);
         }
-        if (threadIdx.x == 0) sx[ntile] = sy[ntile] = sz[ntile] = 1e100; // the sentinel every row is padded with
+        if (threadIdx.x == 0) { // the sentinel every row is padded with
+            sxy[ntile] = make_double2(1e100, 1e100);
+            sz[ntile] = 1e100;
+        }
     }
     __syncthreads();
     double acc[NPART];
     if (MODE != MODE_F)
 #pragma unroll
         for (int q = 0; q < NPART; q++) acc[q] = 0.0;
-    if (C->flags & 1u) tile_rows<KIND, MODE, TEAM, V, true>(A, C, sx, sy, sz, acc);
-    else tile_rows<KIND, MODE, TEAM, V, false>(A, C, sx, sy, sz, acc);
+    if (C->flags & 1u) tile_rows<KIND, MODE, TEAM, V, true>(A, C, sxy, sz, acc);
+    else tile_rows<KIND, MODE, TEAM, V, false>(A, C, sxy, sz, acc);
     if (MODE != MODE_F) {
         __shared__ double red[NPART][TILE_NT / 32];
         const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
