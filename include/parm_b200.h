@@ -47,6 +47,10 @@ const char *parm_b200_last_error(void);
 /* number of kernels launched by this library since load (bench.py's gpu_launches) */
 uint64_t parm_b200_launch_count(void);
 const char *parm_b200_version(void);
+/* roofline denominators measured by this library's own micro-kernels (csrc/probe.cu): fp64 DFMA-chain
+ * throughput in GFLOP/s (2 flops per DFMA) and the bandwidth of a 1 GiB -> 1 GiB streaming copy in GB/s
+ * (read + write bytes). No reference counterpart; used by bench.py next to MEASURED_PEAKS.json. */
+int parm_b200_probe_peaks(int device, double *fp64_gflops, double *copy_gbs);
 
 /* ---- context: AtomVec(N, m) box.hpp:441-479 + OriginBox(L) box.hpp:97-158 ---- */
 int parm_ctx_create(int ndim, uint32_t n_atoms, int device, parm_ctx **out);

@@ -32,6 +32,7 @@ SIGNATURES = {
     "parm_b200_last_error": (C.c_char_p, []),
     "parm_b200_launch_count": (C.c_uint64, []),
     "parm_b200_version": (C.c_char_p, []),
+    "parm_b200_probe_peaks": (C.c_int, [C.c_int, dp, dp]),
     "parm_ctx_create": (C.c_int, [C.c_int, C.c_uint32, C.c_int, vpp]),
     "parm_ctx_destroy": (C.c_int, [vp]),
     "parm_set_box": (C.c_int, [vp, dp]),

@@ -99,3 +99,14 @@ def test_nve_drift_matches_reference_10k_steps(oracle_built):
     assert dg.max() < 1e-5 and dc.max() < 1e-5
     assert dg.max() < 3 * dc.max() + 1e-9 and dc.max() < 3 * dg.max() + 1e-9
     assert abs(nl.which() - c.which()) <= max(2, 0.05 * c.which())
+
+
+def test_peak_probes_are_plausible():
+    """csrc/probe.cu: the DFMA-chain and streaming-copy probes bench.py uses as roofline denominators.
+    B200: fp64 vector peak ~37 TFLOP/s, HBM3e copy ~6.5 TB/s; anything far outside means a broken probe."""
+    import ctypes as C
+    from parm_b200 import capi
+    f, c = C.c_double(), C.c_double()
+    capi.call("parm_b200_probe_peaks", 0, C.byref(f), C.byref(c))
+    assert 1.5e4 < f.value < 6e4, f.value
+    assert 3.0e3 < c.value < 9.0e3, c.value
