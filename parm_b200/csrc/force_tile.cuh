@@ -55,37 +55,59 @@ __device__ __forceinline__ void lj_eval(const PairConst &P, double c12, double d
     }
 }
 
+// One pass of a team's row: V 16-bit entries of this lane as V/2 words (one vector load)
+template <int V>
+struct RowWords {
+    uint32_t w[V / 2];
+};
+template <int V>
+__device__ __forceinline__ RowWords<V> load_row_words(const uint16_t *p) {
+    RowWords<V> r;
+    if constexpr (V == 8) {
+        const uint4 q = __ldg(reinterpret_cast<const uint4 *>(p));
+        r.w[0] = q.x; r.w[1] = q.y; r.w[2] = q.z; r.w[3] = q.w;
+    } else {
+        const uint2 q = __ldg(reinterpret_cast<const uint2 *>(p));
+        r.w[0] = q.x; r.w[1] = q.y;
+    }
+    return r;
+}
+
+// The row words of pass k+1 (or of the first pass of the team's NEXT atom) and the next atom's row length are
+// requested before the arithmetic of pass k starts, so the DRAM latency of the streamed rows (the top stall
+// of the non-pipelined loop: long_scoreboard 5.6 warps per issue) hides behind ~160 fp64 instructions.
+// my0 / q0: length and first pass of the team's first atom, loaded by the caller before the tile was staged.
 template <int KIND, int MODE, int TEAM, int V, bool MI>
 __device__ __forceinline__ void tile_rows(const TileForceArgs &A, const TileChunk *C, const double2 *sxy,
-                                          const double *sz, double (&acc)[NPART]) {
+                                          const double *sz, double (&acc)[NPART], uint32_t my0, RowWords<V> q) {
     constexpr bool want_obs = MODE != MODE_F;
+    constexpr uint32_t NTEAM = TILE_NT / TEAM;
     const uint32_t tl = threadIdx.x % TEAM;
     const uint32_t na = C->n, s0 = C->s0;
     const double ox = C->o[0], oy = C->o[1], oz = C->o[2];
     const double c12 = 12.0 * A.P1.eps;
-    for (uint32_t a0 = 0; a0 < na; a0 += TILE_NT / TEAM) {
-        const uint32_t a = a0 + threadIdx.x / TEAM;
+    uint32_t my = my0;
+    for (uint32_t a = threadIdx.x / TEAM; a - threadIdx.x / TEAM < na; a += NTEAM) { // every lane of a warp runs the same trips (shuffles below)
         const bool valid = a < na;
         const uint32_t s = s0 + (valid ? a : 0);
-        const uint32_t my = valid ? min(A.cnt[s], A.kmax) : 0;
+        const bool validn = a + NTEAM < na;
+        const uint32_t sn = s0 + (validn ? a + NTEAM : 0);
+        const uint32_t myn = validn ? min(A.cnt[sn], A.kmax) : 0; // consumed after this atom's passes
         const double4 pi = A.pos[s];
         const double xi = min_image_fast(pi.x - ox, A.box.L[0], A.box.invL[0]);
         const double yi = min_image_fast(pi.y - oy, A.box.L[1], A.box.invL[1]);
         const double zi = min_image_fast(pi.z - oz, A.box.L[2], A.box.invL[2]);
-        const uint16_t *row = A.rows16 + (size_t)s * A.kmax;
+        const uint16_t *row = A.rows16 + (size_t)s * A.kmax + tl * V;
+        const uint16_t *rown = A.rows16 + (size_t)sn * A.kmax + tl * V;
         double fx = 0, fy = 0, fz = 0;
+        if (my == 0 && validn) q = load_row_words<V>(rown);
         for (uint32_t k0 = 0; k0 < my; k0 += TEAM * V) {
-            uint32_t w[V / 2];
-            if constexpr (V == 8) {
-                const uint4 q = __ldg(reinterpret_cast<const uint4 *>(row + k0 + tl * V));
-                w[0] = q.x; w[1] = q.y; w[2] = q.z; w[3] = q.w;
-            } else {
-                const uint2 q = __ldg(reinterpret_cast<const uint2 *>(row + k0 + tl * V));
-                w[0] = q.x; w[1] = q.y;
-            }
+            RowWords<V> qn = q;
+            if (k0 + TEAM * V < my) qn = load_row_words<V>(row + k0 + TEAM * V);
+            else if (validn) qn = load_row_words<V>(rown); // rows are allocated to kmax: safe whatever the next length is
 #pragma unroll
             for (int e = 0; e < V; e++) {
-                const uint32_t idx = (e & 1) ? (w[e >> 1] >> 16) : (w[e >> 1] & 0xffffu);
+                const uint32_t idx = (e & 1) ? (q.w[e >> 1] >> 16) : (q.w[e >> 1] & 0xffffu);
                 const double2 pxy = sxy[idx]; // one LDS.128 (quarter-warp phases: two teams share a phase, not four)
                 double dx = xi - pxy.x, dy = yi - pxy.y, dz = zi - sz[idx];
                 if (MI) {
@@ -110,7 +132,9 @@ __device__ __forceinline__ void tile_rows(const TileForceArgs &A, const TileChun
                     acc[12] += (en > 0.0) ? 1.0 : 0.0;  // overlaps :2140-2151
                 }
             }
+            q = qn;
         }
+        my = myn;
         if (MODE == MODE_F || A.store) {
 #pragma unroll
             for (int o = TEAM / 2; o; o >>= 1) {
@@ -146,6 +170,19 @@ __global__ void __launch_bounds__(TILE_NT) k_force_tile(const TileForceArgs A) {
     double *sz = s_xyz + 2 * (size_t)A.cap;
     const uint32_t ntile = C->ntile;
     const double ox = C->o[0], oy = C->o[1], oz = C->o[2];
+    // first atom of this team: row length and first pass, in flight while the tile is staged
+    uint32_t my0 = 0;
+    RowWords<V> q0;
+#pragma unroll
+    for (int e = 0; e < V / 2; e++) q0.w[e] = 0;
+    {
+        const uint32_t a = threadIdx.x / TEAM;
+        if (a < C->n) {
+            const uint32_t s = C->s0 + a;
+            my0 = min(A.cnt[s], A.kmax);
+            q0 = load_row_words<V>(A.rows16 + (size_t)s * A.kmax + (threadIdx.x % TEAM) * V);
+        }
+    }
     __syncthreads();
     {
         uint32_t seg = 0;
@@ -165,8 +202,8 @@ __global__ void __launch_bounds__(TILE_NT) k_force_tile(const TileForceArgs A) {
     if (MODE != MODE_F)
 #pragma unroll
         for (int q = 0; q < NPART; q++) acc[q] = 0.0;
-    if (C->flags & 1u) tile_rows<KIND, MODE, TEAM, V, true>(A, C, sxy, sz, acc);
-    else tile_rows<KIND, MODE, TEAM, V, false>(A, C, sxy, sz, acc);
+    if (C->flags & 1u) tile_rows<KIND, MODE, TEAM, V, true>(A, C, sxy, sz, acc, my0, q0);
+    else tile_rows<KIND, MODE, TEAM, V, false>(A, C, sxy, sz, acc, my0, q0);
     if (MODE != MODE_F) {
         __shared__ double red[NPART][TILE_NT / 32];
         const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
