@@ -84,8 +84,11 @@ __device__ __forceinline__ void tile_rows(const TileForceArgs &A, const TileChun
     constexpr uint32_t NTEAM = TILE_NT / TEAM;
     const uint32_t tl = threadIdx.x % TEAM;
     const uint32_t na = C->n, s0 = C->s0;
-    const double ox = C->o[0], oy = C->o[1], oz = C->o[2];
     const double c12 = 12.0 * A.P1.eps;
+    // the chunk's own atoms are consecutive entries of the centre column's run (piece 0 or 1 of stencil column 4)
+    const uint32_t d8 = s0 - C->seg_start[8];
+    const uint32_t own = (s0 >= C->seg_start[8] && d8 < C->seg_off[9] - C->seg_off[8]) ? C->seg_off[8] + d8
+                                                                                      : C->seg_off[9] + (s0 - C->seg_start[9]);
     uint32_t my = my0;
     for (uint32_t a = threadIdx.x / TEAM; a - threadIdx.x / TEAM < na; a += NTEAM) { // every lane of a warp runs the same trips (shuffles below)
         const bool valid = a < na;
@@ -93,10 +96,9 @@ __device__ __forceinline__ void tile_rows(const TileForceArgs &A, const TileChun
         const bool validn = a + NTEAM < na;
         const uint32_t sn = s0 + (validn ? a + NTEAM : 0);
         const uint32_t myn = validn ? min(A.cnt[sn], A.kmax) : 0; // consumed after this atom's passes
-        const double4 pi = A.pos[s];
-        const double xi = min_image_fast(pi.x - ox, A.box.L[0], A.box.invL[0]);
-        const double yi = min_image_fast(pi.y - oy, A.box.L[1], A.box.invL[1]);
-        const double zi = min_image_fast(pi.z - oz, A.box.L[2], A.box.invL[2]);
+        const uint32_t ti = own + (valid ? a : 0); // staged copy of this atom: same min_image(x - origin) as its neighbours
+        const double2 pixy = sxy[ti];
+        const double xi = pixy.x, yi = pixy.y, zi = sz[ti];
         const uint16_t *row = A.rows16 + (size_t)s * A.kmax + tl * V;
         const uint16_t *rown = A.rows16 + (size_t)sn * A.kmax + tl * V;
         double fx = 0, fy = 0, fz = 0;
