@@ -187,12 +187,28 @@ __global__ void __launch_bounds__(TILE_NT) k_force_tile(const TileForceArgs A) {
     }
     __syncthreads();
     {
+        // four positions per thread in flight: the loads of a group are issued before the first is reduced and stored
+        constexpr int SU = 4;
         uint32_t seg = 0;
-        for (uint32_t t = threadIdx.x; t < ntile; t += TILE_NT) {
-            while (t >= s_off[seg + 1]) seg++;
-            const double4 p = A.pos[s_start[seg] + (t - s_off[seg])];
-            sxy[t] = make_double2(min_image_fast(p.x - ox, A.box.L[0], A.box.invL[0]), min_image_fast(p.y - oy, A.box.L[1], A.box.invL[1]));
-            sz[t] = min_image_fast(p.z - oz, A.box.L[2], A.box.invL[2]);
+        for (uint32_t t0 = threadIdx.x; t0 < ntile; t0 += SU * TILE_NT) {
+            double4 p[SU];
+#pragma unroll
+            for (int u = 0; u < SU; u++) {
+                const uint32_t t = t0 + u * TILE_NT;
+                if (t < ntile) {
+                    while (t >= s_off[seg + 1]) seg++;
+                    p[u] = A.pos[s_start[seg] + (t - s_off[seg])];
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < SU; u++) {
+                const uint32_t t = t0 + u * TILE_NT;
+                if (t < ntile) {
+                    sxy[t] = make_double2(min_image_fast(p[u].x - ox, A.box.L[0], A.box.invL[0]),
+                                          min_image_fast(p[u].y - oy, A.box.L[1], A.box.invL[1]));
+                    sz[t] = min_image_fast(p[u].z - oz, A.box.L[2], A.box.invL[2]);
+                }
+            }
         }
         if (threadIdx.x == 0) { // the sentinel every row is padded with
             sxy[ntile] = make_double2(1e100, 1e100);
