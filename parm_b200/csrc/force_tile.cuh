@@ -45,7 +45,7 @@ __device__ __forceinline__ void lj_eval(const PairConst &P, double c12, double d
     const double w = rcp_pos(dsq);
     const double s2 = P.sig2 * w;
     const double ir6 = s2 * s2 * s2;
-    const double t = c12 * ir6 * (ir6 - 1.0) * w;
+    const double t = fma(ir6, ir6, -ir6) * (c12 * w); // 12 eps ir6 (ir6 - 1) / dsq in three operations
     scal = in ? t : 0.0;
     e = 0.0;
     if (want_e) {
