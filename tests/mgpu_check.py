@@ -55,6 +55,17 @@ def check(name, w, steps, tol_traj=1e-9):
     ga1, gb1 = sharded.merge_pairs(parts)
     info = atoms.info()
     tile = nl.tile_stats()
+    # page-locked round trip (the bench's e2e leg): same local state as get_local(), and writing it back is a no-op
+    loc = atoms.get_local()
+    bufs = atoms.pinned_buffers(len(loc["gid"]) + 64)
+    nloc = atoms.get_local_into(bufs)
+    assert nloc == len(loc["gid"]) and np.array_equal(bufs["gid"][:nloc], loc["gid"])
+    for k in "xvaf":
+        assert np.array_equal(bufs[k][:nloc], loc[k]), "%s: pinned get of %s differs" % (name, k)
+    atoms.put_local_from(bufs, nloc)
+    loc2 = atoms.get_local()
+    for k in "xvaf":
+        assert np.array_equal(loc2[k], loc[k]), "%s: put_local_from changed %s" % (name, k)
     if name == "lj3d_tile":
         assert tile[0] and tile[3] == 0, "sharded run should use the cell-tile kernel without wide chunks: %r" % (tile,)
     if rank == 0:
