@@ -39,7 +39,19 @@ k_verlet1(double4 *__restrict__ pos, double *__restrict__ v, const double *__res
     if (abort_flag && *abort_flag) return; // speculative step behind a rebuild request: leave the state alone
     double b1 = 0.0, b2 = 0.0;
     for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < n; s += gridDim.x * blockDim.x) {
+        // every load of the atom is issued before the first use (one memory round trip per atom, not two)
         double4 p = pos[s];
+        double vd[D], ad[D], xl[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+        for (int d = 0; d < D; d++) {
+            vd[d] = v[(size_t)d * npad + s];
+            ad[d] = a[(size_t)d * npad + s];
+        }
+        if (DRIFT) {
+            xl[0] = xlast[s];
+            xl[1] = xlast[npad + s];
+            xl[2] = xlast[2 * (size_t)npad + s];
+        }
         if (frozen_le(p.w)) { // m <= 0 || isinf(m): v = 0, position untouched
 #pragma unroll
             for (int d = 0; d < D; d++) v[(size_t)d * npad + s] = 0.0;
@@ -47,10 +59,8 @@ k_verlet1(double4 *__restrict__ pos, double *__restrict__ v, const double *__res
             double x[3] = {p.x, p.y, p.z};
 #pragma unroll
             for (int d = 0; d < D; d++) {
-                const size_t q = (size_t)d * npad + s;
-                const double vd = v[q], ad = a[q];
-                x[d] = __dadd_rn(x[d], __dadd_rn(__dmul_rn(vd, dt), __dmul_rn(ad, hdt2)));
-                v[q] = __dadd_rn(vd, __dmul_rn(ad, hdt));
+                x[d] = __dadd_rn(x[d], __dadd_rn(__dmul_rn(vd[d], dt), __dmul_rn(ad[d], hdt2)));
+                v[(size_t)d * npad + s] = __dadd_rn(vd[d], __dmul_rn(ad[d], hdt));
             }
             p.x = x[0];
             p.y = x[1];
@@ -58,7 +68,7 @@ k_verlet1(double4 *__restrict__ pos, double *__restrict__ v, const double *__res
             pos[s] = p;
         }
         // atoms that were never add()ed have NaN lastlocs (set at rebuild): NaN never wins a '>' comparison
-        if (DRIFT) top2_push(b1, b2, drift_dist(p, xlast[s], xlast[npad + s], xlast[2 * (size_t)npad + s]));
+        if (DRIFT) top2_push(b1, b2, drift_dist(p, xl[0], xl[1], xl[2]));
     }
     if (DRIFT) drift_finish(b1, b2, skin, d_top2, counter, dflags, hflags, d_slot, h_slot);
 }
@@ -71,6 +81,12 @@ k_verlet2(const double4 *__restrict__ pos, double *__restrict__ v, double *__res
     if (abort_flag && *abort_flag) return;
     for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < n; s += gridDim.x * blockDim.x) {
         const double m = pos[s].w;
+        double fd[D], vd[D];
+#pragma unroll
+        for (int d = 0; d < D; d++) { // loads issued before the branch on m
+            fd[d] = f[(size_t)d * npad + s];
+            vd[d] = v[(size_t)d * npad + s];
+        }
         if (frozen_le(m)) {
 #pragma unroll
             for (int d = 0; d < D; d++) a[(size_t)d * npad + s] = 0.0;
@@ -78,9 +94,9 @@ k_verlet2(const double4 *__restrict__ pos, double *__restrict__ v, double *__res
 #pragma unroll
             for (int d = 0; d < D; d++) {
                 const size_t q = (size_t)d * npad + s;
-                const double ad = __ddiv_rn(f[q], m);
+                const double ad = __ddiv_rn(fd[d], m);
                 a[q] = ad;
-                v[q] = __dadd_rn(v[q], __dmul_rn(ad, hdt));
+                v[q] = __dadd_rn(vd[d], __dmul_rn(ad, hdt));
             }
         }
     }

@@ -1,7 +1,7 @@
 #!/bin/bash
 # quick GPU iteration: tile-kernel parity tests, then the gather-vs-tile timing of the bench workload
 mkdir -p gpurun_out
-python -m pytest tests/test_gpu_tile.py tests/test_gpu_parity.py -m gpu -x -q 2>&1 | tail -4
+python -m pytest tests/test_gpu_tile.py tests/test_gpu_parity.py tests/test_gpu_edge.py -m gpu -x -q 2>&1 | tail -4
 python tools/tile_sweep.py --quick 2>gpurun_out/quick.err | tee gpurun_out/quick.jsonl | python -c "
 import sys, json
 for l in sys.stdin:
