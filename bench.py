@@ -240,11 +240,14 @@ def run_ours(args):
     # ---- secondary bound: fp64 pipe. Peak from this library's own DFMA-chain probe (csrc/probe.cu), measured now
     # on this GPU; flops per listed pair as counted by SURVEY 8d (~30, FMA = 2).
     pf, pc = C.c_double(), C.c_double()
-    capi.call("parm_b200_probe_peaks", local, C.byref(pf), C.byref(pc))
-    roofline["fp64"] = {"achieved": roofline["fp64_gflops_est"] / 1e3, "peak": pf.value / 1e3, "unit": "TFLOP/s",
-                        "frac": roofline["fp64_gflops_est"] / pf.value, "flops_per_pair": 30.0,
-                        "peak_source": "measured now: 8 independent DFMA chains per thread (parm_b200_probe_peaks)"}
-    roofline["own_copy_kernel_gbs"] = pc.value  # 1 GiB -> 1 GiB double4 streaming copy, read + write bytes
+    try:
+        capi.call("parm_b200_probe_peaks", local, C.byref(pf), C.byref(pc))
+        roofline["fp64"] = {"achieved": roofline["fp64_gflops_est"] / 1e3, "peak": pf.value / 1e3, "unit": "TFLOP/s",
+                            "frac": roofline["fp64_gflops_est"] / pf.value, "flops_per_pair": 30.0,
+                            "peak_source": "measured now: 8 independent DFMA chains per thread (parm_b200_probe_peaks)"}
+        roofline["own_copy_kernel_gbs"] = pc.value  # 1 GiB -> 1 GiB double4 streaming copy, read + write bytes
+    except capi.ParmError as exc:  # the probe is reporting only: never lose the bench line over it
+        roofline["fp64"] = {"error": str(exc)}
 
     # ---- end to end through the C ABI with HOST buffers: every step uploads the full Atom array from the
     # pinned AoS mirror, runs timestep(), and downloads the full Atom array (what a caller of the reference
