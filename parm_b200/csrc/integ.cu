@@ -13,6 +13,7 @@
 
 #include <algorithm>
 
+#include <stdlib.h>
 #include "drift.cuh"
 #include "rng.cuh"
 #include "internal.cuh"
@@ -420,8 +421,11 @@ static int enqueue_step_core(parm_integ *g, uint64_t step, const int *abort_flag
     parm_ctx *c = g->ctx;
     const uint32_t n = parm_owned(c); // ghost copies are never integrated
     parm_nlist *nl = g->trackers.empty() ? nullptr : g->trackers[0];
+    // Verlet K1 is a pure stream with a block reduction at its end: 4 blocks per SM (6-7 atoms per thread at 1e6
+    // atoms) measured best (0.034 ms; 16 per SM: 0.039). The Langevin K1 generates its noise in the kernel and keeps 16.
+    static const unsigned k1_per_sm = getenv("PARM_B200_K1_PER_SM") ? (unsigned)atoi(getenv("PARM_B200_K1_PER_SM")) : 4u;
     const unsigned grid = grid_for(c, n, I_BLOCK, 16);
-    const unsigned grid1 = std::min(grid, 4096u); // drift_finish: d_top2 holds 4096 block entries
+    const unsigned grid1 = std::min(grid_for(c, n, I_BLOCK, g->type == 0 ? std::max(k1_per_sm, 1u) : 16u), 4096u); // drift_finish: d_top2 holds 4096 block entries
     const double dt = g->dt;
     // sharded: K1 only leaves the local top-2; the global decision is folded after the all-gather
     int *d_slot = nl && !c->sh.on ? nl->d_slot + slot : nullptr;
