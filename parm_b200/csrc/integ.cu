@@ -483,9 +483,18 @@ static int enqueue_step_core(parm_integ *g, uint64_t step, const int *abort_flag
         PTRY(parm_shard_step_comm(c, nl, nl ? nl->d_slot + slot : nullptr, nl ? nl->h_slot + slot : nullptr));
         const uint32_t lo = c->sh.s_dn, hi = n - c->sh.s_up;
         if (hi > lo) PTRY(launch_all_forces(g, abort_flag, lo, hi - lo));
-        PTRY(parm_shard_step_join(c));
-        if (lo) PTRY(launch_all_forces(g, abort_flag, 0, lo));
-        if (n > hi) PTRY(launch_all_forces(g, abort_flag, std::max(hi, lo), n - std::max(hi, lo)));
+        // the two boundary layers follow the exchange on the communication stream itself (highest priority), so
+        // their small grids share the GPU with the interior kernel instead of running as two partial waves after it
+        {
+            cudaStream_t main_stream = c->stream;
+            c->stream = c->sh.comm_stream;
+            int rc = 0;
+            if (lo) rc = launch_all_forces(g, abort_flag, 0, lo);
+            if (!rc && n > hi) rc = launch_all_forces(g, abort_flag, std::max(hi, lo), n - std::max(hi, lo));
+            c->stream = main_stream;
+            PTRY(rc);
+        }
+        PTRY(parm_shard_step_join(c)); // records the end of the communication stream's work; the main stream waits for it
     } else {
         PTRY(launch_all_forces(g, abort_flag));
     }

@@ -373,6 +373,7 @@ int parm_shard_step_comm(parm_ctx *c, parm_nlist *nl, int *d_slot, int *h_slot) 
     return 0;
 }
 int parm_shard_step_join(parm_ctx *c) {
+    CK(cudaEventRecord(c->sh.ev_comm, c->sh.comm_stream)); // after whatever was queued behind the exchange
     CK(cudaStreamWaitEvent(c->stream, c->sh.ev_comm, 0));
     return 0;
 }
