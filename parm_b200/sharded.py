@@ -314,8 +314,8 @@ def bench_main(args, rank, world, local, metric, unit, config, peak):
                          "achieved": achieved,
                          "peak": hbm, "unit": "GB/s", "frac": achieved / hbm, "traffic": None, "peak_source": hbm_src,
                          "algorithmic_bytes_per_launch": bytes_force, "mean_full_neighbors": mean_n, "kernel_ms": force_ms,
-                         "step_share": {"integrate1_ms": pms[0] / max(pcnt[0], 1), "force_ms": force_ms,
-                                        "integrate2_drift_ms": pms[2] / max(pcnt[2], 1),
+                         "step_share": {"integrate1_drift_ms": pms[0] / max(pcnt[0], 1), "force_ms": force_ms,
+                                        "integrate2_ms": pms[2] / max(pcnt[2], 1),
                                         "rebuild_ms_each": pms[3] / max(pcnt[3], 1), "rebuilds": int(pcnt[3]), "steps": K},
                          "rank0_slots": info},
             "cpu_baseline": None,
