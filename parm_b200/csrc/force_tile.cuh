@@ -1,9 +1,10 @@
 // Cell-tile variant of the NListed pair kernel (interaction.hpp:2154-2291) for single-species interactions
 // with long rows (the LJ configurations of BASELINE.json). One block per chunk (tile.cu):
 //   1. stage the chunk's tile: every position of the <= 18 contiguous slot runs is loaded ONCE, coalesced,
-//      reduced to min_image(x - origin) and stored SoA in shared memory (24 B per atom);
-//   2. TEAM lanes per atom walk the atom's 16-bit tile-local row: one vector load brings V entries per lane,
-//      every pair costs three LDS.64 instead of a 32-byte global gather, and there is no per-pair minimum
+//      reduced to min_image(x - origin) and stored in shared memory as (x, y) double2 + z (24 B per atom);
+//   2. TEAM lanes per atom walk the atom's 16-bit tile-local row: one vector load brings V entries per lane
+//      (requested one pass ahead), every pair costs one LDS.128 + one LDS.64 instead of a 32-byte global
+//      gather, the atom's own position comes from the tile too, and there is no per-pair minimum
 //      image (OriginBox::diff, box.hpp:103, is applied once per staged atom) unless the tile is wider than
 //      half the box (small boxes), in which case the per-pair form runs on top.
 // Same FULL rows, same fixed summation order inside a lane, team and block as force_kernel.cuh: no atomics,
