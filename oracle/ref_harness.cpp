@@ -244,6 +244,8 @@ int ref_add_interaction_ex(void *h, int kind, double skin, const double *params,
                            int injected, int share_nl) {
     Sys *s = static_cast<Sys *>(h);
     AtomVec &av = *s->atoms;
+    // an epsilon table selects the indexed atom structs; IEpsISig* need the sigma table as well
+    if ((kind == 1 || kind == 3) && eps_table && !sig_table) return -3;
     sptr<InjectedNeighborList> nl;
     if (share_nl >= 0)
         nl = s->nls[share_nl];
