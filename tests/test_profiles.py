@@ -61,3 +61,16 @@ def test_traffic_file_matches_the_ncu_export():
     wr = [float(r[hdr.index("dram__bytes_write.sum")]) for r in rows[2:]]
     assert any(abs(a * 1e6 - t["dram_bytes_read_per_launch"]) < 1e3 and abs(b * 1e6 - t["dram_bytes_write_per_launch"]) < 1e3
                for a, b in zip(rd, wr))
+
+
+def test_cpu_baseline_table_tool_runs():
+    """tools/cpu_baseline_table.py on the smallest size: the harness cell list and the reference's O(N^2)
+    update_list(true) give the same number of pairs (asserted inside the tool) and a timing line comes out."""
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "cpu_baseline_table.py"), "--max-n", "1000",
+                          "--rebuild-max-n", "1000", "--seconds", "0.2", "--pot", "lj,harm2d"], capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr[-400:]
+    lines = [json.loads(l) for l in out.stdout.strip().splitlines()]
+    assert "host" in lines[0] and lines[0]["host"]["threads_used"] == 1
+    assert [l["potential"] for l in lines[1:]] == ["lj", "harm2d"]
+    for l in lines[1:]:
+        assert l["atom_steps_per_s"] > 0 and l["update_list_s"] > 0 and l["pairs"] > 0
