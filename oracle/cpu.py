@@ -367,6 +367,8 @@ class CpuSystem:
         """z: (steps, n_mobile, 2, ndim) standard normals: [.,.,0,:] -> x1, [.,.,1,:] -> x2 of
         BivariateGauss::gen_vecs (vecrand.cpp:73-85)."""
         z = np.ascontiguousarray(z, dtype=np.float64)
+        if z.shape[-1] != self.ndim:  # the reference's draw order is undone along the last axis
+            raise ValueError("inject_noise: last axis must be ndim = %d, got shape %r" % (self.ndim, z.shape))
         if self.backend == "ref":
             order = (C.c_int * self.ndim)()
             self.api["probe_draw_order"](order)

@@ -252,3 +252,40 @@ def test_reference_hertzian_verlet_test(oracle_built):
         Ts.append(s.temp())
     assert abs(np.mean(Ts) - 1.0) < 0.1
     assert abs(np.std(Es) / np.mean(Es)) < 1e-2
+
+
+@pytest.mark.parametrize("integ", [0, 1], ids=["verlet", "sol"])
+def test_port_equals_reference_frozen_mass_rules(oracle_built, integ):
+    """Frozen atoms under both hot-path integrators: m == 0, m < 0 and m == inf. CollectionVerlet tests
+    `m <= 0 || isinf(m)` in both loops (collection.cpp:445,459); CollectionSol tests `m <= 0` in its first loop
+    (plus isinf) but `m == 0` later (collection.cpp:278 vs :304,313) -- the C restatement must reproduce that asymmetry bit
+    for bit, because the GPU kernels are checked against it."""
+    if "ref" not in backends(oracle_built):
+        pytest.skip("compiled reference not present")
+    w = W.random_system(180, 3, W.KIND_LJREPULSE, seed=4242, ntypes=1, frozen=6, T=0.3)
+    rng = np.random.default_rng(5)
+    free = np.nonzero(w["m"] > 0)[0]
+    w["m"][rng.choice(free, 3, replace=False)] = np.inf
+    if integ == 0:  # a negative mass would enter CollectionSol's sqrt(T/m): Verlet only
+        w["m"][rng.choice(np.nonzero(np.isfinite(w["m"]) & (w["m"] > 0))[0], 3, replace=False)] = -1.0
+    w["v"] = w["v"].copy()
+    w["v"][~np.isfinite(w["v"])] = 0.0
+    if integ == 1:
+        w.update(integrator=1, damping=1.0, T=0.3)
+    outs = []
+    for be in ("ref", "port"):
+        s = cpu_system(be, w)
+        s.set_forces(True)
+        if integ == 1:
+            # the first loop skips `m <= 0 or isinf(m)` before drawing (collection.cpp:278-281): those atoms draw no noise
+            nmob = int(((w["m"] > 0) & np.isfinite(w["m"])).sum())
+            s.inject_noise(np.random.default_rng(9).standard_normal((60, nmob, 2, 3)))
+        s.timestep(60)
+        outs.append((s.get_atoms(), s.which(), s.kinetic_energy()))
+    for a, b in zip(outs[0][0], outs[1][0]):
+        assert np.array_equal(a, b, equal_nan=True)
+    assert outs[0][1] == outs[1][1] and (outs[0][2] == outs[1][2] or (np.isnan(outs[0][2]) and np.isnan(outs[1][2])))
+    x_end = outs[0][0][0]
+    frozen = (w["m"] <= 0) | np.isinf(w["m"])
+    if integ == 0:
+        assert np.array_equal(x_end[frozen], w["x"][frozen])  # frozen atoms never move under Verlet
