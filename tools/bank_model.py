@@ -26,9 +26,21 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--side", type=int, default=46)
     ap.add_argument("--max-chunks", type=int, default=400)
+    ap.add_argument("--melt-steps", type=int, default=0, help="CollectionVerlet steps on the CPU oracle first (liquid, like the bench after warm-up)")
     a = ap.parse_args()
     w = W.lj_lattice((a.side,) * 3, seed=3003)
     L = w["L"]
+    if a.melt_steps:  # test infrastructure only: the CPU restatement of the reference advances the system
+        from oracle import cpu
+        cpu.build(("port",))
+        sysc = cpu.CpuSystem("port", w["L"], w["x"], w["v"], w["m"])
+        sysc.add_interaction(w["kind"], w["skin"], w["params"], w["types"], w["eps_table"], injected=True)
+        sysc.update_list(True)
+        sysc.make_collection(0, w["dt"])
+        sysc.set_forces(True)
+        sysc.timestep(a.melt_steps)
+        w["x"] = sysc.get_atoms()[0]
+        sysc.close()
     x = np.mod(w["x"], L)
     n = len(x)
     rl = 2.5 + w["skin"]
