@@ -4,8 +4,9 @@ on the BASELINE potentials at N in {1000, 4096, 10648, 32768}:
   (i)  steady-state atom-steps/s of Collection*::timestep() with the pair list kept fresh by the harness cell list
        (InjectedNeighborList: same pair set as the reference's update_list, proved at small N), and
   (ii) seconds per NeighborList::update_list(true) -- the reference's own O(N^2) rebuild -- separately.
-   python tools/cpu_baseline_table.py [--max-n 32768] [--rebuild-max-n 10648] [--pot lj,wca,harm2d] [--seconds 4]
-The CPU figures are a reported baseline, not an optimisation target. TEST/BENCH infrastructure: uses oracle/."""
+   python tests/cpu_baseline_table.py [--max-n 32768] [--rebuild-max-n 10648] [--pot lj,wca,harm2d] [--seconds 4]
+The CPU figures are a reported baseline, not an optimisation target. Lives under tests/ because it drives oracle/
+(test infrastructure; nothing outside tests/, smoke() and bench.py's cpu_baseline leg touches it)."""
 import argparse
 import json
 import os

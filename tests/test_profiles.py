@@ -64,9 +64,9 @@ def test_traffic_file_matches_the_ncu_export():
 
 
 def test_cpu_baseline_table_tool_runs():
-    """tools/cpu_baseline_table.py on the smallest size: the harness cell list and the reference's O(N^2)
+    """tests/cpu_baseline_table.py on the smallest size: the harness cell list and the reference's O(N^2)
     update_list(true) give the same number of pairs (asserted inside the tool) and a timing line comes out."""
-    out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "cpu_baseline_table.py"), "--max-n", "1000",
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "cpu_baseline_table.py"), "--max-n", "1000",
                           "--rebuild-max-n", "1000", "--seconds", "0.2", "--pot", "lj,harm2d"], capture_output=True, text=True)
     assert out.returncode == 0, out.stderr[-400:]
     lines = [json.loads(l) for l in out.stdout.strip().splitlines()]

@@ -6,7 +6,7 @@ out, replays the LDS.128 (x,y) and LDS.64 (z) reads of every warp step of the TE
   current : entry k of a row is read by lane k & 3 at step (k & 31) >> 2 (k_tile_localize)
   banked  : entries ordered so that lane tl of team q reads class 4*((q + step) & 3) + tl of (tile index mod 16),
             surplus entries of a class fill the holes of the others (lead 2).
-   python tools/bank_model.py [--side 46]
+   python tools/bank_model.py [--side 46] [--positions melted.npy]
 No GPU needed; the model is checked against ncu: 6.4-7.9 wavefronts per LDS.128 and 3.5-4.3 per LDS.64 measured."""
 import argparse
 import os
@@ -26,21 +26,14 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--side", type=int, default=46)
     ap.add_argument("--max-chunks", type=int, default=400)
-    ap.add_argument("--melt-steps", type=int, default=0, help="CollectionVerlet steps on the CPU oracle first (liquid, like the bench after warm-up)")
+    ap.add_argument("--positions", default=None, help=".npy with positions of the same system after some steps (liquid, like "
+                    "the bench after warm-up); tests/make_melted_positions.py writes one with the CPU oracle")
     a = ap.parse_args()
     w = W.lj_lattice((a.side,) * 3, seed=3003)
     L = w["L"]
-    if a.melt_steps:  # test infrastructure only: the CPU restatement of the reference advances the system
-        from oracle import cpu
-        cpu.build(("port",))
-        sysc = cpu.CpuSystem("port", w["L"], w["x"], w["v"], w["m"])
-        sysc.add_interaction(w["kind"], w["skin"], w["params"], w["types"], w["eps_table"], injected=True)
-        sysc.update_list(True)
-        sysc.make_collection(0, w["dt"])
-        sysc.set_forces(True)
-        sysc.timestep(a.melt_steps)
-        w["x"] = sysc.get_atoms()[0]
-        sysc.close()
+    if a.positions:
+        w["x"] = np.load(a.positions)
+        assert w["x"].shape == (a.side ** 3, 3)
     x = np.mod(w["x"], L)
     n = len(x)
     rl = 2.5 + w["skin"]
