@@ -112,7 +112,7 @@ static int launch_forces(parm_inter *it, int run, bool accumulate, double *d_out
         T.rows16 = nl->tile.rows16;
         T.cnt = nl->cnt;
         T.kmax = nl->kmax;
-        T.cap = (nl->tile.max_tile + 1 + 15u) & ~15u;
+        T.cap = ((nl->tile.max_tile + 1 + 15u) & ~15u) + 16u; // tile + the single sentinel, rounded up, + 16 class sentinels
         T.P1 = it->h_table[0];
         T.f = c->f;
         T.npad = c->npad;

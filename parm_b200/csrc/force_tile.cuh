@@ -207,9 +207,12 @@ __global__ void __launch_bounds__(TILE_NT) k_force_tile(const TileForceArgs A) {
                 }
             }
         }
-        if (threadIdx.x == 0) { // the sentinel every row is padded with
-            sxy[ntile] = make_double2(1e100, 1e100);
-            sz[ntile] = 1e100;
+        // the sentinel every row is padded with (index ntile) and the 16 class sentinels of bank-ordered rows
+        // (S .. S + 15, bank_order.cuh): all staged far away
+        const uint32_t send = ((ntile + 1u + 15u) & ~15u) + 16u;
+        for (uint32_t t = ntile + threadIdx.x; t < send; t += TILE_NT) {
+            sxy[t] = make_double2(1e100, 1e100);
+            sz[t] = 1e100;
         }
     }
     __syncthreads();

@@ -13,6 +13,7 @@
 #include <string.h>
 
 #include "pairs.cuh"
+#include "bank_order.cuh"
 
 // ---- K5a: chunks per owned column, exclusive scan (one block; a few thousand columns at most) ----
 __global__ void __launch_bounds__(1024)
@@ -219,6 +220,51 @@ k_tile_localize(const TileChunk *__restrict__ chunks, const uint32_t *__restrict
     if (lost) atomicOr(&info->bad, 2u);
 }
 
+// ---- bank-aware row order (experimental, bank_order.cuh) ---------------------------------------------------------
+// One block per chunk, the pair kernel's thread layout (4 lanes per atom). A team copies its row to shared memory,
+// pre-fills the output with the class sentinels, runs the two lane phases of bank_order.cuh and writes its vectors back.
+__global__ void __launch_bounds__(TILE_NT)
+k_tile_bank_order(const TileChunk *__restrict__ chunks, const uint32_t *__restrict__ cnt, uint32_t kmax, uint16_t *__restrict__ rows16) {
+    extern __shared__ __align__(16) uint16_t s_io[]; // [2][TILE_NT / 4][kmax]: rows in, rows out
+    __shared__ uint32_t s_packed[TILE_NT / 4][4], s_nrest[TILE_NT / 4][4];
+    __shared__ uint16_t s_rest[TILE_NT / 4][4 * BO_RCAP];
+    __shared__ uint32_t s_ovf[TILE_NT / 4];
+    const TileChunk *C = chunks + blockIdx.x;
+    const uint32_t ntile = C->ntile, s0 = C->s0, na = C->n;
+    const uint32_t S = (ntile + 1u + 15u) & ~15u; // first of the 16 class sentinels staged behind the tile
+    const uint32_t tl = threadIdx.x & 3u, team = threadIdx.x >> 2;
+    uint16_t *in = s_io + (size_t)team * kmax, *out = s_io + (size_t)(TILE_NT / 4 + team) * kmax;
+    for (uint32_t a0 = 0; a0 < na; a0 += TILE_NT / 4) {
+        const uint32_t a = a0 + team;
+        const bool valid = a < na;
+        const uint32_t s = s0 + (valid ? a : 0);
+        const uint32_t my = valid ? min(cnt[s], kmax) : 0;
+        const uint32_t mypad = (my + 31u) & ~31u, G = mypad >> 2, q = a & 3u;
+        uint16_t *row = rows16 + (size_t)s * kmax;
+        for (uint32_t k0 = 0; k0 < mypad; k0 += 32) {
+            *reinterpret_cast<uint4 *>(in + k0 + tl * 8) = *reinterpret_cast<const uint4 *>(row + k0 + tl * 8);
+#pragma unroll
+            for (uint32_t e = 0; e < 8; e++) out[k0 + tl * 8 + e] = bo_sentinel(S, (k0 >> 2) + e, q, tl);
+        }
+        if (tl == 0) s_ovf[team] = 0;
+        __syncwarp();
+        bool ovf = false;
+        uint32_t nrest = 0;
+        const uint32_t packed = bo_phase1(in, my, G, q, tl, out, &s_rest[team][tl * BO_RCAP], &nrest, &ovf);
+        s_packed[team][tl] = packed;
+        s_nrest[team][tl] = nrest;
+        if (ovf) s_ovf[team] = 1;
+        __syncwarp();
+        const bool keep = s_ovf[team] != 0; // a lane ran out of surplus space: the row keeps its build order
+        if (!keep) bo_phase2(G, q, tl, s_packed[team], s_rest[team], s_nrest[team], out);
+        __syncwarp();
+        if (valid && !keep)
+            for (uint32_t k0 = 0; k0 < mypad; k0 += 32)
+                *reinterpret_cast<uint4 *>(row + k0 + tl * 8) = *reinterpret_cast<const uint4 *>(out + k0 + tl * 8);
+        __syncwarp();
+    }
+}
+
 // ---- host side -----------------------------------------------------------------------------------
 static bool kind_on_tile(int kind) {
     const int kk = PARM_KERNEL_KIND(kind);
@@ -342,6 +388,16 @@ int parm_tile_localize(parm_nlist *nl) {
     if (t.v == 8) k_tile_localize<8><<<t.nchunks, TILE_NT, 0, c->stream>>>(t.d_chunks, nl->nbr, nl->cnt, nl->kmax, t.team, t.rows16, t.d_info);
     else k_tile_localize<4><<<t.nchunks, TILE_NT, 0, c->stream>>>(t.d_chunks, nl->nbr, nl->cnt, nl->kmax, t.team, t.rows16, t.d_info);
     CK_LAUNCH(c);
+    static int banks = -1;
+    if (banks < 0) { const char *e = getenv("PARM_B200_TILE_BANKS"); banks = e ? atoi(e) : 0; }
+    if (banks && t.team == 4 && t.v == 8) { // experimental: bank-aware order of every row (bank_order.cuh)
+        const size_t smem = 2 * (size_t)(TILE_NT / 4) * nl->kmax * sizeof(uint16_t);
+        if (smem <= 160 * 1024) {
+            if (smem > 32 * 1024) CK(cudaFuncSetAttribute(k_tile_bank_order, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            k_tile_bank_order<<<t.nchunks, TILE_NT, smem, c->stream>>>(t.d_chunks, nl->cnt, nl->kmax, t.rows16);
+            CK_LAUNCH(c);
+        }
+    }
     static int check = -1;
     if (check < 0) { const char *e = getenv("PARM_B200_TILE_CHECK"); check = e ? atoi(e) : 0; }
     if (check) { // debugging aid: every row entry must have been found in its chunk's tile
