@@ -131,6 +131,7 @@ static int launch_forces(parm_inter *it, int run, bool accumulate, double *d_out
         }
         return 0;
     }
+    PTRY(parm_nlist_ensure_rows32(nl)); // gather kernel: needs the expanded 32-bit rows (mask-mode lists build them on demand)
     // 0 one species, 1 species table in shared memory, 2 per-atom parameters, 3 two species in registers
     const bool long_rows = nl->total_full >= (uint64_t)PARM_PACK_MIN_NEIGHBORS * (parm_owned(c) ? parm_owned(c) : 1);
     const int specmode = it->generic ? 2 : (it->nspecies == 1 ? 0 : (it->nspecies == 2 && long_rows ? 3 : 1));

@@ -130,6 +130,7 @@ struct ShardDev {
 struct NlistFlags { // device-written; a pinned host mirror receives need_rebuild / top2
     int need_rebuild;
     uint32_t maxcnt;              // longest row of the last build
+    uint32_t nbmax, pad_;         // mask-mode build: most candidate blocks any warp group walked
     unsigned long long total;     // sum of row lengths of the last build
     unsigned long long xmax_bits; // bit pattern of max |coordinate| seen by the last binning pass
     double top2[2];
@@ -173,9 +174,30 @@ struct TileState {
     TileInfo *d_info, *h_info; // h_info pinned
 };
 
+// Mask-mode build (EXPERIMENTAL, PARM_B200_BUILD_MASKS=1, off by default): instead of expanded 32-bit rows the build
+// kernel leaves one 32-bit pass mask per (atom, candidate block) and the first candidate slot (+ stencil column tag) of
+// every block per warp group; tile.cu expands the masks straight into the 16-bit tile-local rows and the 32-bit rows
+// are materialised only on demand (parm_nlist_ensure_rows32: pair download, gather kernel).
+struct MaskOut { // kernel argument of the build
+    uint32_t *masks;    // [mb_cap][npad]: masks[b * npad + slot]
+    uint32_t *blk_base; // [ngroups][mb_cap]: first candidate slot | column tag << PARM_NBR_SLOT_BITS
+    uint32_t *grp_nb;   // [ngroups]: candidate blocks of the group
+    uint32_t mb_cap, npad;
+};
+struct MaskState {
+    int enabled;        // PARM_B200_BUILD_MASKS
+    bool active;        // the current list was built in mask mode
+    bool rows32_valid;  // nbr[] has been expanded from the masks since the last build
+    MaskOut out;
+    size_t masks_cap, blk_cap, grp_cap;
+    uint32_t ngroups, gpc;
+    int zg;
+};
+
 struct parm_nlist {
     parm_ctx *ctx;
     TileState tile;
+    MaskState mask;
     double skin;
     std::vector<double> h_diam; // by AtomVec index; < 0: not a member
     bool have_diam;
@@ -321,6 +343,7 @@ int parm_nlist_sort_permute(parm_nlist *nl, const uint32_t *d_src, uint32_t nsrc
 int parm_nlist_build_rows(parm_nlist *nl);
 int parm_nlist_append_ghosts(parm_nlist *nl, uint32_t first, uint32_t count);
 int parm_nlist_rebuild(parm_nlist *nl);
+int parm_nlist_ensure_rows32(parm_nlist *nl);  // mask-mode lists: expand nbr[] from the pass masks if that has not happened yet
 int parm_nlist_drift_check_async(parm_nlist *nl);   // standalone drift kernel (update_list(false) outside timestep)
 int parm_inter_regather(parm_inter *inter);          // re-gather per-slot species after a re-sort
 int parm_inter_launch_forces(parm_inter *inter, unsigned want, bool accumulate, double *d_out /*device, 13 doubles*/,
@@ -332,6 +355,8 @@ int parm_tile_plan_fetch(parm_nlist *nl);     // queue the device->host copy of 
 int parm_tile_localize(parm_nlist *nl);       // after the rows are final (ignore applied, before species packing): write rows16
 void parm_tile_invalidate(parm_nlist *nl);
 void parm_tile_free(parm_nlist *nl);
+int parm_tile_localize_masks(parm_nlist *nl); // mask-mode lists: rows16 straight from the pass masks
+bool parm_tile_all_fit(const parm_nlist *nl); // every interaction on the list can run on the tile kernel
 bool parm_tile_usable(const parm_inter *it);  // this interaction can run on the tile kernel right now
 bool parm_tile_chunk_range(const parm_nlist *nl, uint32_t first, uint32_t end, uint32_t *c0, uint32_t *c1);
 

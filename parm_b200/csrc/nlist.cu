@@ -440,16 +440,18 @@ __device__ __forceinline__ f32x2 f2_dup(float x) { const unsigned long long b = 
 // rounding bound, x3) around the threshold. A lane that sees a candidate inside that band repeats the block
 // with the fp64 test below (which in turn defers to the reference's exact predicate inside its own ~1e-9 band),
 // so the pair set stays bit-exact; ~1e-5 of the tests take that path.
-template <bool SMALLBOX, bool UNIFORM, bool RUN2D, bool F32>
+// MASK (experimental, internal.cuh MaskState): no rows are written; every lane stores the 32-bit pass mask of each
+// candidate block and lane 0 the block's first candidate slot (+ column tag), see tile.cu for the expansion.
+template <bool SMALLBOX, bool UNIFORM, bool RUN2D, bool F32, bool MASK = false>
 __global__ void __launch_bounds__(CB_WARPS * 32)
 k_build_cell(const double4 *__restrict__ pos, const double4 *__restrict__ pw, const double *__restrict__ diam,
              const uint32_t *__restrict__ cell_start, uint32_t ngroups, int zg, uint32_t n, BoxDev box, GridDev g, StencilDev st,
              double skin, double lmax, double thr_min, double uthr, uint32_t kmax, uint32_t *__restrict__ nbr,
              uint32_t *__restrict__ cnt, NlistFlags *flags, const uint8_t *__restrict__ ghost, uint32_t tagcols,
-             double cs0, double beta32) {
+             double cs0, double beta32, MaskOut mo = MaskOut()) {
     __shared__ double4 s_c[CB_WARPS][32];
     __shared__ __align__(8) float s_fx[CB_WARPS][32], s_fy[CB_WARPS][32], s_fz[CB_WARPS][32], s_fw[CB_WARPS][32];
-    __shared__ uint32_t s_buf[CB_WARPS][64][32]; // per lane: ring of 64 pending row entries (a block adds <= 32 to <= 7), flushed 8 (one 32-byte sector) at a time
+    __shared__ uint32_t s_buf[CB_WARPS][MASK ? 1 : 64][32]; // per lane: ring of 64 pending row entries (a block adds <= 32 to <= 7), flushed 8 (one 32-byte sector) at a time
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const uint32_t cur = blockIdx.x * CB_WARPS + wib;
     if (cur >= ngroups) return;
@@ -500,9 +502,10 @@ k_build_cell(const double4 *__restrict__ pos, const double4 *__restrict__ pw, co
         const f32x2 xi2 = f2_dup((float)(wi.x - Ox)), yi2 = f2_dup((float)(wi.y - Oy)), zi2 = f2_dup((float)(wi.z - Oz));
         const f32x2 wi2 = f2_dup((float)wi.w);
         uint32_t count = 0, flushed = 0; // entries found / entries already written to the row (a multiple of 8)
+        uint32_t nblk = 0;               // MASK: candidate blocks walked so far (the same sequence for every chunk of the group)
         uint32_t *row = nbr + (size_t)(valid ? i : a0) * kmax;
         auto flush8 = [&](uint32_t *r, uint32_t at) {
-            const uint32_t h = at & 56u;
+            const uint32_t h = MASK ? 0u : (at & 56u);
             uint4 u0, u1;
             u0.x = s_buf[wib][h + 0][lane]; u0.y = s_buf[wib][h + 1][lane]; u0.z = s_buf[wib][h + 2][lane]; u0.w = s_buf[wib][h + 3][lane];
             u1.x = s_buf[wib][h + 4][lane]; u1.y = s_buf[wib][h + 5][lane]; u1.z = s_buf[wib][h + 6][lane]; u1.w = s_buf[wib][h + 7][lane];
@@ -656,6 +659,15 @@ k_build_cell(const double4 *__restrict__ pos, const double4 *__restrict__ pw, co
                         // is checked once per candidate block, not per survivor: with 32 lanes some lane would be flushing
                         // in nearly every iteration of the divergent loop
                         const uint32_t jt = jbase | tag;
+                        if (MASK) {
+                            if (nblk < mo.mb_cap) {
+                                if (valid) mo.masks[(size_t)nblk * mo.npad + i] = m;
+                                if (lane == 0) mo.blk_base[(size_t)cur * mo.mb_cap + nblk] = jt;
+                            }
+                            count += __popc(m);
+                            nblk++;
+                            continue;
+                        }
                         while (m) {
                             const int bit = __ffs(m) - 1;
                             m &= m - 1;
@@ -670,7 +682,12 @@ k_build_cell(const double4 *__restrict__ pos, const double4 *__restrict__ pw, co
                 }
             }
         }
-        if (member) { // tail of the row
+        if (MASK) {
+            if (lane == 0) {
+                mo.grp_nb[cur] = nblk;
+                atomicMax(&flags->nbmax, nblk);
+            }
+        } else if (member) { // tail of the row
             for (uint32_t k = flushed; k < count && k < kmax; k++) row[k] = s_buf[wib][k & 63u][lane];
         }
         if (valid) cnt[i] = count;
@@ -1069,9 +1086,95 @@ static int pack_species(parm_nlist *nl) {
 }
 
 static int finish_rows(parm_nlist *nl) {
+    if (nl->mask.active) { // no exclusions, one species: the masks go straight into the 16-bit tile rows
+        nl->packed = false;
+        nl->packed_for = nullptr;
+        return parm_tile_localize_masks(nl);
+    }
     PTRY(apply_ignore(nl));
     PTRY(parm_tile_localize(nl)); // 16-bit tile-local rows for the cell-tile pair kernel (tile.cu): needs the column tags
     return pack_species(nl);
+}
+
+// ---- mask-mode build (experimental): 32-bit rows on demand ---------------------------------------------------
+// One warp per atom: lane b takes candidate block b of the atom's warp group, a warp scan of the pass-mask popcounts
+// gives every block its position in the row, and each lane writes `first slot | tag` + bit for its set bits -- the
+// same entries, in the same order, as the append loop of the classic build.
+__global__ void __launch_bounds__(256)
+k_expand_masks(MaskOut mo, const uint32_t *__restrict__ cell_id_sorted, uint32_t nc2, uint32_t gpc, uint32_t zg, uint32_t n,
+               uint32_t kmax, const uint32_t *__restrict__ cnt, uint32_t *__restrict__ nbr) {
+    const uint32_t s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (s >= n) return;
+    if (cnt[s] == 0) return; // (groups without members never wrote their masks)
+    const uint32_t cid = cell_id_sorted[s];
+    const uint32_t grp = (cid / nc2) * gpc + (cid % nc2) / zg;
+    const uint32_t nb = min(mo.grp_nb[grp], mo.mb_cap);
+    uint32_t *row = nbr + (size_t)s * kmax;
+    uint32_t pos0 = 0;
+    for (uint32_t r = 0; r < nb; r += 32) {
+        const uint32_t b = r + lane;
+        uint32_t m = b < nb ? mo.masks[(size_t)b * mo.npad + s] : 0u;
+        const uint32_t base = b < nb ? mo.blk_base[(size_t)grp * mo.mb_cap + b] : 0u;
+        const uint32_t p = __popc(m);
+        uint32_t incl = p;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t y = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= (uint32_t)o) incl += y;
+        }
+        uint32_t k = pos0 + incl - p;
+        while (m) {
+            const int bit = __ffs(m) - 1;
+            m &= m - 1;
+            if (k < kmax) row[k] = base + (uint32_t)bit;
+            k++;
+        }
+        pos0 += __shfl_sync(0xffffffffu, incl, 31);
+    }
+}
+
+int parm_nlist_ensure_rows32(parm_nlist *nl) {
+    MaskState &ms = nl->mask;
+    if (!ms.active || ms.rows32_valid) return 0;
+    parm_ctx *c = nl->ctx;
+    const uint32_t n = c->n;
+    if (n) {
+        k_expand_masks<<<(unsigned)(((size_t)n * 32 + 255) / 256), 256, 0, c->stream>>>(
+            ms.out, nl->cell_id_sorted, (uint32_t)nl->g.nc[2], ms.gpc, (uint32_t)ms.zg, n, nl->kmax, nl->cnt, nl->nbr);
+        CK_LAUNCH(c);
+    }
+    ms.rows32_valid = true;
+    return 0;
+}
+
+static int alloc_masks(parm_nlist *nl, uint32_t mb_cap, uint32_t ngroups) {
+    parm_ctx *c = nl->ctx;
+    MaskState &ms = nl->mask;
+    const size_t need_m = (size_t)mb_cap * c->npad, need_b = (size_t)ngroups * mb_cap;
+    if (need_m > ms.masks_cap) {
+        if (ms.out.masks) cudaFree(ms.out.masks);
+        ms.out.masks = 0;
+        ms.masks_cap = 0;
+        CK(cudaMalloc(&ms.out.masks, need_m * 4));
+        ms.masks_cap = need_m;
+    }
+    if (need_b > ms.blk_cap) {
+        if (ms.out.blk_base) cudaFree(ms.out.blk_base);
+        ms.out.blk_base = 0;
+        ms.blk_cap = 0;
+        CK(cudaMalloc(&ms.out.blk_base, need_b * 4));
+        ms.blk_cap = need_b;
+    }
+    if (ngroups > ms.grp_cap) {
+        if (ms.out.grp_nb) cudaFree(ms.out.grp_nb);
+        ms.out.grp_nb = 0;
+        ms.grp_cap = 0;
+        CK(cudaMalloc(&ms.out.grp_nb, (size_t)ngroups * 4));
+        ms.grp_cap = ngroups;
+    }
+    ms.out.mb_cap = mb_cap;
+    ms.out.npad = c->npad;
+    return 0;
 }
 
 // Build the rows for the atoms now in slots 0..n-1, growing the per-atom capacity if a row overflowed.
@@ -1131,6 +1234,21 @@ int parm_nlist_build_rows(parm_nlist *nl) {
                 ext = std::max(ext, d == rax ? (0.5 * zg + nl->st.sub) * cs : (nl->st.sub + 1.0) * cs);
             }
             double beta32 = 3.0 * ((6.93 * ext / nl->thr_min + 14.0) * 5.9604644775390625e-8);
+            // mask mode (experimental, off by default): 3-D tile-planned single-GPU lists without exclusions whose last build
+            // had long rows and whose interactions all run on the cell-tile kernel
+            static int masks_env = -1;
+            if (masks_env < 0) { const char *e = getenv("PARM_B200_BUILD_MASKS"); masks_env = e ? atoi(e) : 0; }
+            nl->mask.enabled = masks_env;
+            const bool use_masks = masks_env && tagcols && !run2d && !nl->smallbox && !c->sh.on && nl->ignored.empty() &&
+                                   nl->total_full >= (uint64_t)nl->tile.min_nbrs * n && parm_tile_all_fit(nl);
+            if (use_masks) {
+                PTRY(alloc_masks(nl, std::max(nl->mask.out.mb_cap, 48u), ngroups));
+                nl->mask.ngroups = ngroups;
+                nl->mask.gpc = gpc;
+                nl->mask.zg = zg;
+            }
+            nl->mask.active = use_masks;
+            nl->mask.rows32_valid = !use_masks;
             static int use_f32 = -1;
             if (use_f32 < 0) { const char *e = getenv("PARM_B200_BUILD_F32"); use_f32 = e ? atoi(e) : 1; }
             const bool f32 = use_f32 && !nl->smallbox && beta32 < 1e-4;
@@ -1140,10 +1258,16 @@ int parm_nlist_build_rows(parm_nlist *nl) {
         if (run2d) k_build_cell<SB, UN, true, F><<<cblocks, CB_WARPS * 32, 0, c->stream>>>(CARGS);                 \
         else k_build_cell<SB, UN, false, F><<<cblocks, CB_WARPS * 32, 0, c->stream>>>(CARGS);                      \
     } while (0)
+#define MLAUNCH(UN, F) k_build_cell<false, UN, false, F, true><<<cblocks, CB_WARPS * 32, 0, c->stream>>>(CARGS, nl->mask.out)
+            if (use_masks) {
+                if (f32) { if (nl->uniform) MLAUNCH(true, true); else MLAUNCH(false, true); }
+                else { if (nl->uniform) MLAUNCH(true, false); else MLAUNCH(false, false); }
+            } else
             if (nl->smallbox) { if (nl->uniform) CLAUNCH(true, true, false); else CLAUNCH(true, false, false); }
             else if (f32) { if (nl->uniform) CLAUNCH(false, true, true); else CLAUNCH(false, false, true); }
             else { if (nl->uniform) CLAUNCH(false, true, false); else CLAUNCH(false, false, false); }
 #undef CLAUNCH
+#undef MLAUNCH
         } else if (nl->smallbox) {
             if (nl->uniform) k_build<true, true><<<nblocks, BUILD_WARPS * 32, 0, c->stream>>>(BARGS);
             else k_build<true, false><<<nblocks, BUILD_WARPS * 32, 0, c->stream>>>(BARGS);
@@ -1160,6 +1284,14 @@ int parm_nlist_build_rows(parm_nlist *nl) {
         CK(cudaStreamSynchronize(c->stream));
         nl->total_full = nl->h_flags->total;
         nl->maxcnt = nl->h_flags->maxcnt;
+        if (nl->mask.active) {
+            if (nl->h_flags->nbmax > nl->mask.out.mb_cap) { // a group walked more candidate blocks than the mask table holds
+                nl->mask.out.mb_cap = nl->h_flags->nbmax + 8;
+                continue; // (alloc_masks runs again at the top of the next attempt)
+            }
+            if (nl->maxcnt > nl->kmax) PTRY(alloc_nbr(nl, nl->maxcnt + nl->maxcnt / 8 + 8)); // capacity only: the masks are complete
+            return finish_rows(nl);
+        }
         if (nl->maxcnt <= nl->kmax) return finish_rows(nl);
         uint32_t k2 = nl->maxcnt + nl->maxcnt / 8 + 8;
         PTRY(alloc_nbr(nl, k2));
@@ -1245,6 +1377,7 @@ static int collect_pairs(parm_nlist *nl, std::vector<std::pair<uint32_t, uint32_
     if (n == 0 || nl->updatenum == 0) return 0;
     std::vector<uint32_t> h_cnt(n), h_order(n), h_nbr((size_t)n * nl->kmax);
     std::vector<uint8_t> h_ghost(n, 0);
+    PTRY(parm_nlist_ensure_rows32(nl)); // mask-mode lists expand their 32-bit rows on demand
     CK(cudaMemcpyAsync(h_cnt.data(), nl->cnt, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream));
     CK(cudaMemcpyAsync(h_order.data(), c->order, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream));
     CK(cudaMemcpyAsync(h_nbr.data(), nl->nbr, h_nbr.size() * 4, cudaMemcpyDeviceToHost, c->stream));

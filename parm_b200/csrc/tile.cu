@@ -265,6 +265,88 @@ k_tile_bank_order(const TileChunk *__restrict__ chunks, const uint32_t *__restri
     }
 }
 
+// ---- mask-mode lists (experimental): rows16 straight from the build's pass masks --------------------------------
+// Same thread layout as k_tile_localize<8> (TEAM = 4 lanes per atom, V = 8). Lane tl of a team takes candidate blocks
+// tl, tl + 4, ... of the atom's warp group; a team-wide exclusive scan of the mask popcounts gives every block its
+// position in the row (the append order of the classic build), every set bit becomes a tile index through the same
+// 9-entry column table, and the row is assembled in shared memory in the permuted lane-vector layout of the pair
+// kernel before it leaves as 16-byte stores. Rows are padded to whole passes with the sentinel index ntile.
+__global__ void __launch_bounds__(TILE_NT)
+k_tile_localize_masks(const TileChunk *__restrict__ chunks, MaskOut mo, const uint32_t *__restrict__ cell_id_sorted, uint32_t nc2,
+                      uint32_t gpc, uint32_t zg, const uint32_t *__restrict__ cnt, uint32_t kmax, uint16_t *__restrict__ rows16,
+                      TileInfo *info) {
+    extern __shared__ __align__(16) uint16_t s_rows[]; // [TILE_NT / 4][kmax]
+    __shared__ uint4 s_tab[9];
+    __shared__ uint32_t s_ntile;
+    const TileChunk *C = chunks + blockIdx.x;
+    if (threadIdx.x < 9) {
+        const int kc = 2 * threadIdx.x;
+        s_tab[threadIdx.x] = make_uint4(C->seg_start[kc], C->seg_off[kc], C->seg_start[kc + 1], C->seg_off[kc + 1]);
+    }
+    if (threadIdx.x == 0) s_ntile = C->ntile;
+    __syncthreads();
+    const uint32_t ntile = s_ntile, s0 = C->s0, na = C->n;
+    const uint32_t tl = threadIdx.x & 3u, team = threadIdx.x >> 2;
+    uint16_t *buf = s_rows + (size_t)team * kmax;
+    bool lost = false;
+    for (uint32_t a0 = 0; a0 < na; a0 += TILE_NT / 4) { // every lane of a warp runs the same trips (team shuffles below)
+        const uint32_t a = a0 + team;
+        const bool valid = a < na;
+        const uint32_t s = s0 + (valid ? a : 0);
+        const uint32_t my = valid ? min(cnt[s], kmax) : 0;
+        const uint32_t mypad = (my + 31u) & ~31u;
+        for (uint32_t k = tl; k < mypad; k += 4) buf[k] = (uint16_t)ntile; // sentinel everywhere, entries overwrite it
+        __syncwarp();
+        uint32_t nb = 0, grp = 0;
+        if (my) {
+            const uint32_t cid = cell_id_sorted[s];
+            grp = (cid / nc2) * gpc + (cid % nc2) / zg;
+            nb = min(mo.grp_nb[grp], mo.mb_cap);
+        }
+        // teams of a warp may walk different block counts: run to the warp-wide maximum so that the shuffles stay converged
+        uint32_t nbw = nb;
+#pragma unroll
+        for (int o = 16; o >= 4; o >>= 1) nbw = max(nbw, __shfl_xor_sync(0xffffffffu, nbw, o));
+        uint32_t pos0 = 0;
+        for (uint32_t r = 0; r < nbw; r += 4) {
+            const uint32_t b = r + tl;
+            uint32_t m = b < nb ? mo.masks[(size_t)b * mo.npad + s] : 0u;
+            const uint32_t base = b < nb ? mo.blk_base[(size_t)grp * mo.mb_cap + b] : 0u;
+            const uint32_t p = __popc(m);
+            uint32_t incl = p; // inclusive scan over the 4 lanes of the team
+            uint32_t y = __shfl_up_sync(0xffffffffu, incl, 1, 4);
+            if (tl >= 1) incl += y;
+            y = __shfl_up_sync(0xffffffffu, incl, 2, 4);
+            if (tl >= 2) incl += y;
+            const uint32_t tot = __shfl_sync(0xffffffffu, incl, 3, 4);
+            uint32_t k = pos0 + incl - p;
+            const uint4 t = s_tab[min(base >> PARM_NBR_SLOT_BITS, 8u)];
+            const uint32_t jb = base & PARM_NBR_SLOT_MASK;
+            while (m) {
+                const uint32_t j = jb + (uint32_t)(__ffs(m) - 1);
+                m &= m - 1;
+                const uint32_t l = j - t.x < t.w - t.y ? t.y + (j - t.x) : t.w + (j - t.z);
+                if (l >= ntile) lost = true; // (not expected: the entry is in neither run of its column)
+                if (k < my) {
+                    // entry k of the row is read by lane (k & 3) of the team at step (k & 31) >> 2 of pass k / 32
+                    const uint32_t r32 = k & 31u;
+                    buf[(k & ~31u) + (r32 & 3u) * 8u + (r32 >> 2)] = (uint16_t)(l >= ntile ? ntile : l);
+                }
+                k++;
+            }
+            pos0 += tot;
+        }
+        __syncwarp();
+        if (valid) {
+            uint16_t *out = rows16 + (size_t)s * kmax;
+            for (uint32_t k0 = 0; k0 < mypad; k0 += 32)
+                *reinterpret_cast<uint4 *>(out + k0 + tl * 8) = *reinterpret_cast<const uint4 *>(buf + k0 + tl * 8);
+        }
+        __syncwarp();
+    }
+    if (lost) atomicOr(&info->bad, 2u);
+}
+
 // ---- host side -----------------------------------------------------------------------------------
 static bool kind_on_tile(int kind) {
     const int kk = PARM_KERNEL_KIND(kind);
@@ -364,6 +446,21 @@ int parm_tile_plan_fetch(parm_nlist *nl) {
     return 0;
 }
 
+// experimental (PARM_B200_TILE_BANKS=1): bank-aware order of every row (bank_order.cuh), after either localize pass
+static int tile_bank_order(parm_nlist *nl) {
+    parm_ctx *c = nl->ctx;
+    TileState &t = nl->tile;
+    static int banks = -1;
+    if (banks < 0) { const char *e = getenv("PARM_B200_TILE_BANKS"); banks = e ? atoi(e) : 0; }
+    if (!banks || t.team != 4 || t.v != 8) return 0;
+    const size_t smem = 2 * (size_t)(TILE_NT / 4) * nl->kmax * sizeof(uint16_t);
+    if (smem > 160 * 1024) return 0;
+    if (smem > 32 * 1024) CK(cudaFuncSetAttribute(k_tile_bank_order, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_tile_bank_order<<<t.nchunks, TILE_NT, smem, c->stream>>>(t.d_chunks, nl->cnt, nl->kmax, t.rows16);
+    CK_LAUNCH(c);
+    return 0;
+}
+
 // Called when the rows are final (after NeighborList::ignore, before species packing drops the column tags) and
 // the plan summary is on the host.
 int parm_tile_localize(parm_nlist *nl) {
@@ -388,22 +485,61 @@ int parm_tile_localize(parm_nlist *nl) {
     if (t.v == 8) k_tile_localize<8><<<t.nchunks, TILE_NT, 0, c->stream>>>(t.d_chunks, nl->nbr, nl->cnt, nl->kmax, t.team, t.rows16, t.d_info);
     else k_tile_localize<4><<<t.nchunks, TILE_NT, 0, c->stream>>>(t.d_chunks, nl->nbr, nl->cnt, nl->kmax, t.team, t.rows16, t.d_info);
     CK_LAUNCH(c);
-    static int banks = -1;
-    if (banks < 0) { const char *e = getenv("PARM_B200_TILE_BANKS"); banks = e ? atoi(e) : 0; }
-    if (banks && t.team == 4 && t.v == 8) { // experimental: bank-aware order of every row (bank_order.cuh)
-        const size_t smem = 2 * (size_t)(TILE_NT / 4) * nl->kmax * sizeof(uint16_t);
-        if (smem <= 160 * 1024) {
-            if (smem > 32 * 1024) CK(cudaFuncSetAttribute(k_tile_bank_order, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            k_tile_bank_order<<<t.nchunks, TILE_NT, smem, c->stream>>>(t.d_chunks, nl->cnt, nl->kmax, t.rows16);
-            CK_LAUNCH(c);
-        }
-    }
+    if (int rc = tile_bank_order(nl)) return rc;
     static int check = -1;
     if (check < 0) { const char *e = getenv("PARM_B200_TILE_CHECK"); check = e ? atoi(e) : 0; }
     if (check) { // debugging aid: every row entry must have been found in its chunk's tile
         CK(cudaMemcpyAsync(t.h_info, t.d_info, sizeof(TileInfo), cudaMemcpyDeviceToHost, c->stream));
         CK(cudaStreamSynchronize(c->stream));
         if (t.h_info->bad) { parm_set_error("cell-tile plan lost a neighbour (bad = %u)", t.h_info->bad); return PARM_ERR_RUNTIME; }
+    }
+    t.valid = true;
+    return 0;
+}
+
+bool parm_tile_all_fit(const parm_nlist *nl) {
+    bool any = false;
+    for (const parm_inter *it : nl->ctx->inters)
+        if (it->nl == nl) {
+            if (!inter_fits(it)) return false;
+            any = true;
+        }
+    return any;
+}
+
+// Mask-mode twin of parm_tile_localize (TEAM = 4, V = 8 only; other layouts fall back to the 32-bit rows).
+int parm_tile_localize_masks(parm_nlist *nl) {
+    parm_ctx *c = nl->ctx;
+    TileState &t = nl->tile;
+    t.valid = false;
+    if (!t.planned || !nl->mask.active) return 0;
+    const uint32_t nown = parm_owned(c);
+    t.nchunks = t.h_info->nchunks;
+    t.max_tile = t.h_info->max_tile;
+    if (t.h_info->bad || !t.nchunks || t.max_tile + 1 > TILE_MAX_ATOMS) return 0;
+    if (nl->total_full < (uint64_t)t.min_nbrs * nown) return 0;
+    if (t.team != 4 || t.v != 8) return 0;
+    const size_t smem = (size_t)(TILE_NT / 4) * nl->kmax * sizeof(uint16_t);
+    if (smem > 160 * 1024) return 0;
+    const size_t need = (size_t)c->npad * nl->kmax;
+    if (need > t.rows16_cap) {
+        if (t.rows16) cudaFree(t.rows16);
+        t.rows16 = 0;
+        t.rows16_cap = 0;
+        CK(cudaMalloc(&t.rows16, need * 2));
+        t.rows16_cap = need;
+    }
+    if (smem > 48 * 1024) CK(cudaFuncSetAttribute(k_tile_localize_masks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_tile_localize_masks<<<t.nchunks, TILE_NT, smem, c->stream>>>(t.d_chunks, nl->mask.out, nl->cell_id_sorted, (uint32_t)nl->g.nc[2],
+                                                                  nl->mask.gpc, (uint32_t)nl->mask.zg, nl->cnt, nl->kmax, t.rows16, t.d_info);
+    CK_LAUNCH(c);
+    if (int rc = tile_bank_order(nl)) return rc;
+    static int check = -1;
+    if (check < 0) { const char *e = getenv("PARM_B200_TILE_CHECK"); check = e ? atoi(e) : 0; }
+    if (check) {
+        CK(cudaMemcpyAsync(t.h_info, t.d_info, sizeof(TileInfo), cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+        if (t.h_info->bad) { parm_set_error("cell-tile plan lost a neighbour in mask mode (bad = %u)", t.h_info->bad); return PARM_ERR_RUNTIME; }
     }
     t.valid = true;
     return 0;
