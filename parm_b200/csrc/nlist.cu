@@ -1236,8 +1236,8 @@ int parm_nlist_build_rows(parm_nlist *nl) {
             double beta32 = 3.0 * ((6.93 * ext / nl->thr_min + 14.0) * 5.9604644775390625e-8);
             // mask mode (experimental, off by default): 3-D tile-planned single-GPU lists without exclusions whose last build
             // had long rows and whose interactions all run on the cell-tile kernel
-            static int masks_env = -1;
-            if (masks_env < 0) { const char *e = getenv("PARM_B200_BUILD_MASKS"); masks_env = e ? atoi(e) : 0; }
+            const char *em = getenv("PARM_B200_BUILD_MASKS"); // read per rebuild: the sweeps toggle it inside one process
+            const int masks_env = em ? atoi(em) : 0;
             nl->mask.enabled = masks_env;
             const bool use_masks = masks_env && tagcols && !run2d && !nl->smallbox && !c->sh.on && nl->ignored.empty() &&
                                    nl->total_full >= (uint64_t)nl->tile.min_nbrs * n && parm_tile_all_fit(nl);

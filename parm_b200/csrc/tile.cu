@@ -450,8 +450,8 @@ int parm_tile_plan_fetch(parm_nlist *nl) {
 static int tile_bank_order(parm_nlist *nl) {
     parm_ctx *c = nl->ctx;
     TileState &t = nl->tile;
-    static int banks = -1;
-    if (banks < 0) { const char *e = getenv("PARM_B200_TILE_BANKS"); banks = e ? atoi(e) : 0; }
+    const char *eb = getenv("PARM_B200_TILE_BANKS"); // read per rebuild: the sweeps toggle it inside one process
+    const int banks = eb ? atoi(eb) : 0;
     if (!banks || t.team != 4 || t.v != 8) return 0;
     const size_t smem = 2 * (size_t)(TILE_NT / 4) * nl->kmax * sizeof(uint16_t);
     if (smem > 160 * 1024) return 0;

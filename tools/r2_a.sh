@@ -1,0 +1,22 @@
+#!/bin/bash
+# round 2, first GPU call: validate the two env-gated leads of round 1 (bank-aware rows, mask-mode build) and time them
+mkdir -p gpurun_out
+for env in "PARM_B200_TILE_BANKS=1" "PARM_B200_BUILD_MASKS=1" "PARM_B200_TILE_BANKS=1 PARM_B200_BUILD_MASKS=1"; do
+  echo "== $env"
+  env $env PARM_B200_TILE_CHECK=1 timeout 900 python -m pytest tests/test_gpu_tile.py tests/test_gpu_parity.py tests/test_gpu_scale.py -m gpu -x -q 2>&1 | tail -4
+done
+python - <<'PY' 2>gpurun_out/r2a.err | tee gpurun_out/r2a_sweep.jsonl
+import os, sys, json
+sys.path.insert(0, os.getcwd())
+sys.argv = ["tile_sweep"]
+import tools.tile_sweep as ts
+from parm_b200 import workloads as W
+w = W.config3(100)
+for env in [{}, {"PARM_B200_TILE_BANKS": 1}, {"PARM_B200_BUILD_MASKS": 1}, {"PARM_B200_TILE_BANKS": 1, "PARM_B200_BUILD_MASKS": 1}]:
+    for k in ("PARM_B200_TILE_BANKS", "PARM_B200_BUILD_MASKS"):
+        os.environ.pop(k, None)
+    e = {"PARM_B200_TILE": 1}
+    e.update(env)
+    ts.run(w, 200, e)
+PY
+tail -3 gpurun_out/r2a.err
