@@ -72,6 +72,75 @@ def test_config3_full_size_properties():
     assert collec.stats()["rebuilds"] >= 10
 
 
+def test_config3_full_size_1m_vs_oracle(oracle_built):
+    """BASELINE configs[2] at its FULL size (N = 1e6) against the reference's own NListed / CollectionVerlet code
+    (oracle/_ref when built, else the C port) fed by the harness cell list (InjectedNeighborList, SURVEY 8c
+    "Large-N oracle"): pair set bit-exact, forces / energy / virial within 1e-10, then 8 steps across a rebuild
+    (interaction.hpp:2102-2115, 2166-2175; collection.cpp:442-469; trackers.cpp:19-85). ~1-2 min of one host core."""
+    from parm_b200 import sim
+    from parity_util import backends
+    w = W.config3()
+    be = backends(oracle_built)[-1]
+    box, atoms, inter, nl, collec = sim.from_workload(w)
+    assert nl.tile_stats()[0]  # the cell-tile pair kernel is the one under test
+    c = cpu_system(be, w, injected=True)
+    a, b = nl.pairs()
+    ca, cb = c.pairs()
+    assert len(a) == len(ca) > 45_000_000
+    assert np.array_equal(a, ca) and np.array_equal(b, cb)
+    del a, b, ca, cb
+    collec.set_forces(True)
+    c.set_forces(True)
+    assert rel_err_vec(atoms.peek("f"), c.get_atoms()[3]) < 1e-10
+    assert rel_err(collec.potential_energy(), c.potential_energy()) < 1e-10
+    assert rel_err(collec.virial(), c.virial()) < 1e-10
+    assert rel_err(collec.pressure(), c.pressure()) < 1e-10
+    collec.timestep(8)
+    c.timestep(8)
+    assert c.which() >= 2 and nl.which() == c.which()  # at least one drift-triggered rebuild, at the same step
+    x, v, _, f = c.get_atoms()
+    assert rel_err_vec(atoms.peek("x") - w["x"], x - w["x"]) < 1e-10
+    assert rel_err_vec(atoms.peek("v"), v) < 1e-10
+    assert rel_err_vec(atoms.peek("f"), f) < 1e-10
+    assert rel_err(collec.energy(), c.energy()) < 1e-10
+    a, b = nl.pairs()
+    ca, cb = c.pairs()
+    assert np.array_equal(a, ca) and np.array_equal(b, cb)
+
+
+def test_config4_shape_256k_sol_vs_oracle(oracle_built):
+    """BASELINE configs[3] (binary WCA-like LJRepulsePair under CollectionSol, collection.cpp:265-322) at 64^3 =
+    262 144 atoms with INJECTED normals (the Boost stream is unpinned): pair set bit-exact, forces 1e-10,
+    trajectories after 20 Langevin steps across a drift-triggered rebuild."""
+    from parm_b200 import sim
+    from parity_util import backends
+    w = W.config4(shape=(64, 64, 64), seed=4004)
+    be = backends(oracle_built)[-1]
+    steps = 20
+    box, atoms, inter, nl, collec = sim.from_workload(w)
+    c = cpu_system(be, w, injected=True)
+    a, b = nl.pairs()
+    ca, cb = c.pairs()
+    assert np.array_equal(a, ca) and np.array_equal(b, cb)
+    collec.set_forces(True)
+    c.set_forces(True)
+    assert rel_err_vec(atoms.peek("f"), c.get_atoms()[3]) < 1e-10
+    assert rel_err(collec.potential_energy(), c.potential_energy()) < 1e-10
+    z = np.random.default_rng(44).standard_normal((steps, w["x"].shape[0], 2, 3))
+    collec.inject_noise(z)
+    c.inject_noise(z)
+    collec.timestep(steps)
+    c.timestep(steps)
+    x, v, _, f = c.get_atoms()
+    assert c.which() >= 2 and nl.which() == c.which()
+    assert rel_err_vec(atoms.peek("x") - w["x"], x - w["x"]) < 1e-10
+    assert rel_err_vec(atoms.peek("v"), v) < 1e-10
+    assert rel_err_vec(atoms.peek("f"), f) < 1e-9
+    a, b = nl.pairs()
+    ca, cb = c.pairs()
+    assert np.array_equal(a, ca) and np.array_equal(b, cb)
+
+
 def test_nve_drift_matches_reference_10k_steps(oracle_built):
     """BASELINE config 1 (LJatoms.cpp-like, N=1000): 10^4 NVE steps on the GPU and on the CPU oracle from the
     same inputs. Trajectories decorrelate after ~10^3 steps (chaos), so the comparison is statistical:
