@@ -5,7 +5,8 @@
 
 One "step" is one CollectionVerlet::timestep() (collection.cpp:442-469) over the whole system:
 K1 integrate + skin-drift reduction -> pair forces -> K3 integrate -> (when the drift rule triggered) neighbour rebuild.
-Rebuilds are inside the timed region (amortised), setup is not.
+Rebuilds are inside the timed region (amortised), setup is not. The timed state is the equilibrated T = 1.44
+configuration (--equil untimed steps with velocity rescaling from the jittered lattice), not the lattice itself.
 
 N = 1 workload: BASELINE.json configs[2] -- 3-D LJ, LJAttractRepulsePair cut 2.5 sigma, N = 1e6
 (the largest single-GPU configuration the metric is quoted on; SURVEY 8d cfg 3: rho = 1.1939,
@@ -89,6 +90,46 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+EQUIL_EVERY = 100
+
+
+def equilibrate(collec, steps, T=1.44):
+    """Untimed: melt the jittered simple-cubic start and hold the state point (collection.cpp:31-35 rescaling every
+    EQUIL_EVERY steps), so that the timed region sees the disordered T = 1.44 configuration the config names."""
+    done = 0
+    while done < steps:
+        k = min(EQUIL_EVERY, steps - done)
+        collec.timestep(k)
+        collec.scale_velocities_to_temp(T)
+        done += k
+    return {"steps": steps, "rescale_every": EQUIL_EVERY, "T_target": T, "T_end": float(collec.temp())}
+
+
+def kernel_source_sha16():
+    """Hash of the pair-kernel sources of the library that is running (ties profiles/force_kernel_traffic.json to it)."""
+    import hashlib
+    h = hashlib.sha256()
+    for f in ("force_tile.cuh", "force_kernel.cuh", "tile.cu", "force.cu", "pairs.cuh"):
+        with open(os.path.join(ROOT, "parm_b200", "csrc", f), "rb") as fh:
+            h.update(fh.read())
+    return h.hexdigest()[:16]
+
+
+def kernel_traffic(tile_active):
+    """DRAM bytes per launch of the pair kernel from the committed ncu capture -- only when that capture was taken
+    from these very kernel sources (source_sha16), else None (the number would be stale)."""
+    tp = os.path.join(ROOT, "profiles", "force_kernel_traffic.json")
+    try:
+        tj = json.load(open(tp))
+        ent = tj if tile_active else tj.get("gather_kernel", {})
+        if ent.get("source_sha16") != kernel_source_sha16():
+            return None, "profiles/force_kernel_traffic.json is from other kernel sources (sha %s, running %s)" % (
+                ent.get("source_sha16"), kernel_source_sha16())
+        return ent.get("dram_bytes_per_launch"), ent.get("kernel")
+    except Exception as exc:
+        return None, "no capture (%s)" % exc
+
+
 def build_cpu_sample(backend_pref=("ref", "port")):
     """The reference's own CPU implementation on a bounded sample of the same workload."""
     from oracle import cpu
@@ -140,7 +181,8 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
         "warmup": warmup, "ms_per_step": dt / steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": workload_config(args, args.gpus),
+        "config": dict(workload_config(args, args.gpus), n_atoms_timed=int(n),
+                       timed_sample="the CPU arm times a %d-atom sample of this workload (see cpu_baseline.sample)" % n),
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": 1, "kind": "reference" if kind == "ref" else "port",
                          "sample": cpu_sample_desc(n, steps, kind)},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -152,8 +194,9 @@ def run_reference(args):
 def workload_config(args, world):
     n = args.side * args.side * args.side_z * world
     return {"workload": "3D LJ (NListed<IEpsSigCutAtom,LJAttractRepulsePair>, cut 2.5 sigma), CollectionVerlet NVE, "
-                        "simple-cubic start %dx%dx%d per GPU, rho=1.1939, T=1.44, skin=0.3, dt=0.004" %
-                        (args.side, args.side, args.side_z),
+                        "simple-cubic start %dx%dx%d per GPU melted and held at T=1.44 for %d untimed steps before the "
+                        "timed region, rho=1.1939, skin=0.3, dt=0.004" %
+                        (args.side, args.side, args.side_z, args.equil),
             "n_atoms": n, "atoms_per_gpu": n // world, "parallelism": "slab%d" % world if world > 1 else "single",
             "l2": "working set (positions+velocities+forces+neighbour list ~0.7 GB per 1e6 atoms) is larger than the "
                   "126 MB L2, no explicit flush"}
@@ -169,7 +212,25 @@ def run_ours(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if world > 1:
         from parm_b200 import sharded
-        return sharded.bench_main(args, rank, world, local, METRIC, UNIT, workload_config(args, world), peaks())
+
+        def parity_hook(rank, world):
+            # the oracle as the checker, before the timed region (tests/mgpu_check.py "lj3d_tile": slab-decomposed
+            # run vs the CPU restatement on rank 0); the numbers travel in the bench line as "parity_check"
+            sys.path.insert(0, os.path.join(ROOT, "tests"))
+            import mgpu_check
+            w = workloads.lj_lattice((14 * world, 28, 28), seed=17)
+            w["name"] = "lj3d_tile %dx28x28" % (14 * world)
+            return mgpu_check.parity_metrics(w, 25)
+
+        def cpu_hook():
+            val, dt, ncpu, kind = time_cpu(100, 3)
+            return {"value": val, "unit": UNIT, "cores": 1, "kind": "reference" if kind == "ref" else "port",
+                    "sample": cpu_sample_desc(ncpu, 100, kind)}
+
+        hooks = {"equilibrate": equilibrate, "cpu_baseline": cpu_hook}
+        if not args.no_parity:
+            hooks["parity"] = parity_hook
+        return sharded.bench_main(args, rank, world, local, METRIC, UNIT, workload_config(args, world), peaks(), hooks)
     torch.cuda.set_device(local)
     w = workloads.lj_lattice((args.side, args.side, args.side_z), seed=3003)
     n = w["x"].shape[0]
@@ -180,6 +241,7 @@ def run_ours(args):
     stream = torch.cuda.ExternalStream(st.value, device=local)
     K, W = args.steps, max(args.warmup, 3)
 
+    equil = equilibrate(collec, args.equil)
     collec.timestep(W)
     capi.call("parm_sync", atoms._h)
     # ---- timed region: K steps, device clock, rebuilds included
@@ -214,19 +276,13 @@ def run_ours(args):
     bytes_force = (16 * 3 + 16 + 4 * mean_n) * n   # K2 = 16D + 16 + 4n per atom
     bytes_step = (104 * 3 + 24 + 4 * mean_n) * n   # whole step
     achieved = bytes_force / (force_ms * 1e-3) / 1e9
-    traffic = None
-    tp = os.path.join(ROOT, "profiles", "force_kernel_traffic.json")
-    if os.path.exists(tp):
-        try:
-            tj = json.load(open(tp))
-            traffic = tj.get("dram_bytes_per_launch") if nl.tile_stats()[0] else tj.get("gather_kernel", {}).get("dram_bytes_per_launch")
-        except Exception:
-            traffic = None
+    traffic, traffic_src = kernel_traffic(nl.tile_stats()[0])
     roofline = {
         "bound": "hbm",
         "kernel": ("k_force_tile<LJAttractRepulse> (pair force, full neighbour rows, positions staged per cell tile in "
                    "shared memory)" if nl.tile_stats()[0] else "k_force<LJAttractRepulse> (pair force, full neighbour rows)"),
         "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm, "traffic": traffic,
+        "traffic_source": traffic_src, "kernel_source_sha16": kernel_source_sha16(),
         "peak_source": hbm_src, "algorithmic_bytes_per_launch": bytes_force, "mean_full_neighbors": mean_n,
         "kernel_ms": force_ms,
         "fp64_gflops_est": 30.0 * mean_n * n / (force_ms * 1e-3) / 1e9,  # ~30 flop/pair, SURVEY 8d
@@ -236,6 +292,20 @@ def run_ours(args):
                        "rebuild_ms_each": pms[3] / max(pcnt[3], 1), "rebuilds": int(pcnt[3]), "steps": K},
         "whole_step_gbs": bytes_step * K / (ms * 1e-3) / 1e9,
     }
+
+    # ---- steady state: a window long enough that the rebuild count is not quantised (the driver's K may hold 3 or 4)
+    Ks = max(args.steady_steps, K)
+    r0 = collec.stats()["rebuilds"]
+    torch.cuda.synchronize()
+    e0.record(stream)
+    collec.timestep(Ks)
+    e1.record(stream)
+    capi.call("parm_sync", atoms._h)
+    torch.cuda.synchronize()
+    ms_s = e0.elapsed_time(e1)
+    rb_s = collec.stats()["rebuilds"] - r0
+    steady = {"steps": Ks, "ms_per_step": ms_s / Ks, "value": n * Ks / (ms_s * 1e-3), "unit": UNIT, "rebuilds": int(rb_s),
+              "steps_per_rebuild": Ks / max(rb_s, 1), "T_end": float(collec.temp())}
 
     # ---- secondary bound: fp64 pipe. Peak from this library's own DFMA-chain probe (csrc/probe.cu), measured now
     # on this GPU; flops per listed pair as counted by SURVEY 8d (~30, FMA = 2).
@@ -284,7 +354,7 @@ def run_ours(args):
         "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic", "config": workload_config(args, 1), "clocks": clocks, "e2e": e2e,
         "gpu_launches": int(launches), "rebuilds_in_timed_region": int(rebuilds), "roofline": roofline,
-        "cpu_baseline": cpu,
+        "steady_state": steady, "equilibration": equil, "cpu_baseline": cpu,
     }
     print(json.dumps(line))
 
@@ -298,7 +368,11 @@ def main():
     ap.add_argument("--side", type=int, default=100, help="lattice sites along x and y")
     ap.add_argument("--side-z", type=int, default=100, help="lattice sites along z PER GPU")
     ap.add_argument("--e2e-steps", type=int, default=20)
+    ap.add_argument("--equil", type=int, default=600, help="untimed equilibration steps (velocity rescaling to T=1.44)")
+    ap.add_argument("--steady-steps", type=int, default=300, help="length of the steady_state window")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-parity", action="store_true", help="N > 1: skip the pre-run parity_check against the oracle")
+    ap.add_argument("--no-config5", action="store_true", help="N = 8: skip the BASELINE config 5 (16e6 atoms) window")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

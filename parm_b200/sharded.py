@@ -217,14 +217,8 @@ def build_system(L, n_global, gid, x, v, m, kind, params, types, eps_table, skin
 
 
 # ---- bench.py --gpus N (N > 1) --------------------------------------------------------------------
-def bench_main(args, rank, world, local, metric, unit, config, peak):
-    import torch
-    import torch.distributed as dist
-    torch.cuda.set_device(local)
-    init_distributed("nccl")
-    from bench import ClockSampler
-    # slabs stacked along x: --side-z lattice planes per GPU along the slab axis, --side x --side across
-    s = lj_lattice_slab(args.side_z, args.side, args.side, rank, world)
+def _bench_system(side_x_per_rank, side_y, side_z, rank, world, seed=3003):
+    s = lj_lattice_slab(side_x_per_rank, side_y, side_z, rank, world, seed=seed)
     n_global = s["n_global"]
     params = np.tile(np.array([1.0, 1.0, 2.5]), (n_global, 1))
     box, atoms, inter, nl, collec = build_system(
@@ -233,19 +227,16 @@ def bench_main(args, rank, world, local, metric, unit, config, peak):
     collec.reset_com_velocity()
     collec.scale_velocities_to_temp(1.44)
     collec.set_forces(True)
-    st = C.c_void_p()
-    call("parm_get_stream", atoms._h, C.byref(st))
-    stream = torch.cuda.ExternalStream(st.value, device=local)
-    K, W = args.steps, max(args.warmup, 3)
-    collec.timestep(W)
-    call("parm_sync", atoms._h)
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
-        time.sleep(0.3)
+    return n_global, box, atoms, inter, nl, collec
+
+
+def _timed_window(collec, atoms, stream, K):
+    """K steps bracketed by barrier + synchronize on both sides, CUDA events on the context's stream, max over ranks."""
+    import torch
+    import torch.distributed as dist
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     l0 = capi.lib().parm_b200_launch_count()
     r0 = collec.stats()["rebuilds"]
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     dist.barrier()
     torch.cuda.synchronize()
     e0.record(stream)
@@ -255,10 +246,34 @@ def bench_main(args, rank, world, local, metric, unit, config, peak):
     torch.cuda.synchronize()
     dist.barrier()
     ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
-    dist.all_reduce(ms, op=dist.ReduceOp.MAX)   # device time, max over ranks
-    ms = float(ms.item())
-    launches = capi.lib().parm_b200_launch_count() - l0
-    rebuilds = collec.stats()["rebuilds"] - r0
+    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    return float(ms.item()), capi.lib().parm_b200_launch_count() - l0, collec.stats()["rebuilds"] - r0
+
+
+def bench_main(args, rank, world, local, metric, unit, config, peak, hooks=None):
+    """hooks (supplied by bench.py, which alone may drive the CPU oracle): "parity" -> dict printed as parity_check,
+    "cpu_baseline" -> dict (rank 0 only), "equilibrate"(collec, steps) -> dict."""
+    import torch
+    import torch.distributed as dist
+    torch.cuda.set_device(local)
+    init_distributed("nccl")
+    from bench import ClockSampler
+    hooks = hooks or {}
+    parity = hooks["parity"](rank, world) if "parity" in hooks else None
+    # slabs stacked along x: --side-z lattice planes per GPU along the slab axis, --side x --side across
+    n_global, box, atoms, inter, nl, collec = _bench_system(args.side_z, args.side, args.side, rank, world)
+    st = C.c_void_p()
+    call("parm_get_stream", atoms._h, C.byref(st))
+    stream = torch.cuda.ExternalStream(st.value, device=local)
+    K, W = args.steps, max(args.warmup, 3)
+    equil = hooks["equilibrate"](collec, args.equil) if "equilibrate" in hooks else None
+    collec.timestep(W)
+    call("parm_sync", atoms._h)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    ms, launches, rebuilds = _timed_window(collec, atoms, stream, K)
     clocks = sampler.stop() if rank == 0 else None
     value = n_global * K / (ms * 1e-3)
 
@@ -275,9 +290,17 @@ def bench_main(args, rank, world, local, metric, unit, config, peak):
     hbm, hbm_src = peak
     bytes_force = (16 * 3 + 16 + 4 * mean_n) * info["n_local"]
     achieved = bytes_force / (force_ms * 1e-3) / 1e9
+    halo_bytes = 32 * (info["send_down"] + info["send_up"])   # double4 positions sent per step by this rank
+
+    # steady state: a window long enough that the rebuild count is not quantised
+    Ks = max(args.steady_steps, K)
+    ms_s, _, rb_s = _timed_window(collec, atoms, stream, Ks)
+    steady = {"steps": Ks, "ms_per_step": ms_s / Ks, "value": n_global * Ks / (ms_s * 1e-3), "unit": unit,
+              "rebuilds": int(rb_s), "steps_per_rebuild": Ks / max(rb_s, 1), "T_end": float(collec.temp())}
 
     # end to end with host buffers: every step the full local state is downloaded into page-locked host arrays
     # and x, v, a, f are written back from that host copy before the next step
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     Ke = max(3, min(args.e2e_steps, K))
     bufs = atoms.pinned_buffers(int(1.05 * info["n_local"]) + 4096)
     dist.barrier()
@@ -301,6 +324,32 @@ def bench_main(args, rank, world, local, metric, unit, config, peak):
            "d2h_bytes_per_step": int(nbytes_dn), "steps": Ke,
            "note": "per rank, pinned host arrays: full local state (x,v,a,f,m,id) device->host and x,v,a,f "
                    "host->device every step"}
+    tile = nl.tile_stats()
+    del collec, inter, nl
+    atoms.close()
+
+    # BASELINE configs[4] (N = 16e6 = 200 x 200 x 400 sites on 8 GPUs, strong-scaling point of the north star): run
+    # after the weak-scaling window whenever the job has 8 ranks, so that the driver's own 8-GPU run carries it
+    config5 = None
+    if world == 8 and not args.no_config5:
+        n5, box5, atoms5, inter5, nl5, collec5 = _bench_system(50, 200, 200, rank, world, seed=5005)
+        call("parm_get_stream", atoms5._h, C.byref(st))
+        stream5 = torch.cuda.ExternalStream(st.value, device=local)
+        eq5 = hooks["equilibrate"](collec5, args.equil) if "equilibrate" in hooks else None
+        collec5.timestep(W)
+        call("parm_sync", atoms5._h)
+        K5 = max(K, 100)
+        ms5, _, rb5 = _timed_window(collec5, atoms5, stream5, K5)
+        config5 = {"workload": "BASELINE configs[4]: 3D LJ N=16e6 (200x200x400 sites, 2e6 atoms per GPU), slab8, same "
+                               "state point and equilibration as the weak-scaling line",
+                   "n_atoms": int(n5), "value": n5 * K5 / (ms5 * 1e-3), "unit": unit, "ms_per_step": ms5 / K5, "steps": K5,
+                   "rebuilds": int(rb5), "equilibration": eq5, "tile": list(nl5.tile_stats())}
+        del collec5, inter5, nl5
+        atoms5.close()
+
+    cpu = None
+    if rank == 0 and "cpu_baseline" in hooks and not args.no_cpu:
+        cpu = hooks["cpu_baseline"]()
     if rank == 0:
         line = {
             "metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": K, "warmup": W,
@@ -309,16 +358,17 @@ def bench_main(args, rank, world, local, metric, unit, config, peak):
             "rebuilds_in_timed_region": int(rebuilds),
             "roofline": {"bound": "hbm",
                          "kernel": ("k_force_tile<LJAttractRepulse> (rank 0 share; cell tiles staged in shared memory)"
-                                    if nl.tile_stats()[0] else "k_force<LJAttractRepulse> (rank 0 share)"),
-                         "tile": dict(zip(("active", "chunks", "max_tile_atoms", "wide_chunks"), nl.tile_stats())),
+                                    if tile[0] else "k_force<LJAttractRepulse> (rank 0 share)"),
+                         "tile": dict(zip(("active", "chunks", "max_tile_atoms", "wide_chunks"), tile)),
                          "achieved": achieved,
                          "peak": hbm, "unit": "GB/s", "frac": achieved / hbm, "traffic": None, "peak_source": hbm_src,
                          "algorithmic_bytes_per_launch": bytes_force, "mean_full_neighbors": mean_n, "kernel_ms": force_ms,
                          "step_share": {"integrate1_drift_ms": pms[0] / max(pcnt[0], 1), "force_ms": force_ms,
                                         "integrate2_ms": pms[2] / max(pcnt[2], 1),
                                         "rebuild_ms_each": pms[3] / max(pcnt[3], 1), "rebuilds": int(pcnt[3]), "steps": K},
-                         "rank0_slots": info},
-            "cpu_baseline": None,
+                         "rank0_slots": info, "halo_bytes_sent_per_step_rank0": int(halo_bytes)},
+            "steady_state": steady, "equilibration": equil, "parity_check": parity, "config5_16M": config5,
+            "cpu_baseline": cpu,
         }
         print(json.dumps(line))
     dist.barrier()

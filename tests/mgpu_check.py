@@ -92,6 +92,58 @@ def check(name, w, steps, tol_traj=1e-9):
     atoms.close()
 
 
+def parity_metrics(w, steps):
+    """The lj3d_tile comparison as numbers instead of assertions (bench.py prints them as "parity_check" in every
+    N > 1 line): merged pair set vs the oracle's list, forces, energy, state after `steps` steps, rebuild count.
+    Collective; returns the dict on rank 0, None elsewhere."""
+    rank, world = dist.get_rank(), dist.get_world_size()
+    n = w["x"].shape[0]
+    gid, x, v, m = sharded.partition_workload(w, rank, world)
+    box, atoms, inter, nl, collec = sharded.build_system(
+        w["L"], n, gid, x, v, m, w["kind"], w["params"], w["types"], w["eps_table"], w["skin"], w["dt"])
+    a, b = nl.pairs()
+    parts = [None] * world
+    dist.all_gather_object(parts, (a, b))
+    ga, gb = sharded.merge_pairs(parts)
+    collec.set_forces(True)
+    st0, counts = gather_state(atoms, n, w["ndim"])
+    E0 = collec.energy()
+    collec.timestep(steps)
+    st1, counts1 = gather_state(atoms, n, w["ndim"])
+    E1 = collec.energy()
+    which = nl.which()
+    a, b = nl.pairs()
+    dist.all_gather_object(parts, (a, b))
+    ga1, gb1 = sharded.merge_pairs(parts)
+    tile = nl.tile_stats()
+    out = None
+    if rank == 0:
+        c = cpu_system("port", w, injected=True)
+        ca, cb = c.pairs()
+        out = {"world": world, "case": w.get("name", "lj3d_tile"), "n_atoms": int(n), "steps": int(steps), "oracle": "oracle/parm_oracle.c (C port)",
+               "pairs": int(len(ca)), "pairs_equal": bool(np.array_equal(ga, ca) and np.array_equal(gb, cb))}
+        c.set_forces(True)
+        out["force_rel"] = rel_err_vec(st0["f"], c.get_atoms()[3])
+        out["energy_rel"] = rel_err(E0, c.energy())
+        c.timestep(steps)
+        cx, cv, _, _ = c.get_atoms()
+        out["rebuilds"] = int(which)
+        out["rebuilds_oracle"] = int(c.which())
+        out["x_rel_after_steps"] = rel_err_vec(st1["x"] - w["x"], cx - w["x"])
+        out["v_rel_after_steps"] = rel_err_vec(st1["v"], cv)
+        out["energy_rel_after_steps"] = rel_err(E1, c.energy())
+        ca, cb = c.pairs()
+        out["pairs_equal_after_steps"] = bool(np.array_equal(ga1, ca) and np.array_equal(gb1, cb))
+        out["migrated"] = bool(counts != counts1)
+        out["tile_kernel"] = bool(tile[0])
+        out["ok"] = bool(out["pairs_equal"] and out["pairs_equal_after_steps"] and out["force_rel"] < 1e-10 and
+                         out["energy_rel"] < 1e-10 and out["x_rel_after_steps"] < 1e-9 and out["rebuilds"] == out["rebuilds_oracle"])
+    dist.barrier()
+    del collec, inter, nl
+    atoms.close()
+    return out
+
+
 def main():
     rank = int(os.environ.get("RANK", "0"))
     torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", rank)))
