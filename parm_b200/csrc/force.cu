@@ -108,6 +108,11 @@ static int launch_forces(parm_inter *it, int run, bool accumulate, double *d_out
     if (tl) {
         TileForceArgs T;
         T.pos = c->pos;
+        const bool bulk = nl->tile.stage_aligned;
+        T.prel_xy = bulk ? nl->tile.prel_xy : nullptr;
+        T.prel_z = bulk ? nl->tile.prel_z : nullptr;
+        // prel of every slot (ghost copies included) from the current positions, unless the caller has done it
+        if (bulk && !c->tile_prep_external) PTRY(parm_tile_prep(nl, 0, c->n, c->stream, abort_flag));
         T.chunks = nl->tile.d_chunks + chunk0;
         T.rows16 = nl->tile.rows16;
         T.cnt = nl->cnt;

@@ -14,6 +14,8 @@
 
 struct TileForceArgs {
     const double4 *pos;
+    const double2 *prel_xy;  // STAGE 1: positions in the image of the last rebuild (tile.cu: k_tile_prep), (x, y)
+    const double *prel_z;    //          and z; the runs of a tile are bulk-copied from these two arrays
     const TileChunk *chunks; // already offset to the first chunk of the launch
     const uint16_t *rows16;
     const uint32_t *cnt;
@@ -156,11 +158,40 @@ __device__ __forceinline__ void tile_rows(const TileForceArgs &A, uint32_t na, u
     }
 }
 
-template <int KIND, int MODE, int TEAM, int V>
+// ---- bulk-copy staging (STAGE 1): mbarrier + cp.async.bulk (the TMA unit's linear copy), sm_90+ PTX ----------------
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+                 "r"(bytes), "r"(bar) : "memory");
+}
+
+// STAGE 0: every thread loads positions from pos, reduces them to min_image(x - origin) and stores them (any box, any
+// team layout). STAGE 1: the <= 18 runs of the tile arrive as <= 36 cp.async.bulk copies from prel (tile.cu) issued by
+// the lanes of warp 0 and counted by one mbarrier; no thread touches the positions, except in the chunks next to a
+// periodic face, whose wrapped runs get their image shift (TileChunk::sh) added once they have landed.
+template <int KIND, int MODE, int TEAM, int V, int STAGE>
 __global__ void __launch_bounds__(TILE_NT) k_force_tile(const TileForceArgs A) {
     if (A.abort_flag && *A.abort_flag) return; // speculatively enqueued step whose predecessor asked for a rebuild
     extern __shared__ __align__(16) double s_xyz[];
     __shared__ uint32_t s_start[TILE_MAXSEG], s_off[TILE_MAXSEG + 1];
+    __shared__ __align__(8) unsigned long long s_bar;
     const TileChunk *C = A.chunks + blockIdx.x;
     if (threadIdx.x < TILE_MAXSEG) s_start[threadIdx.x] = C->seg_start[threadIdx.x];
     if (threadIdx.x <= TILE_MAXSEG) s_off[threadIdx.x] = C->seg_off[threadIdx.x];
@@ -181,8 +212,46 @@ __global__ void __launch_bounds__(TILE_NT) k_force_tile(const TileForceArgs A) {
             q0 = load_row_words<V>(A.rows16 + (size_t)s * A.kmax + (threadIdx.x % TEAM) * V);
         }
     }
-    __syncthreads();
-    {
+    // the sentinel every row is padded with (index ntile) and the 16 class sentinels of bank-ordered rows
+    // (S .. S + 15, bank_order.cuh): all staged far away
+    const uint32_t send = ((ntile + 1u + 15u) & ~15u) + 16u;
+    for (uint32_t t = ntile + threadIdx.x; t < send; t += TILE_NT) {
+        sxy[t] = make_double2(1e100, 1e100);
+        sz[t] = 1e100;
+    }
+    if (STAGE == 1) {
+        const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&s_bar);
+        if (threadIdx.x == 0) mbar_init(bar, 1);
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            if (threadIdx.x == 0) mbar_arrive_expect_tx(bar, ntile * 24u);
+            __syncwarp();
+            if (threadIdx.x < TILE_MAXSEG) {
+                const uint32_t o0 = s_off[threadIdx.x], len = s_off[threadIdx.x + 1] - o0, j0 = s_start[threadIdx.x];
+                if (len) { // even start, even length: both copies are 16-byte aligned at both ends
+                    bulk_g2s((uint32_t)__cvta_generic_to_shared(sxy + o0), A.prel_xy + j0, len * 16u, bar);
+                    bulk_g2s((uint32_t)__cvta_generic_to_shared(sz + o0), A.prel_z + j0, len * 8u, bar);
+                }
+            }
+        }
+        mbar_wait(bar, 0);
+        if (cflags & 2u) { // runs reached across a periodic face: add their image shift
+            for (uint32_t seg = 0; seg < TILE_MAXSEG; seg++) {
+                const int sx = C->sh[seg][0], sy = C->sh[seg][1], szz = C->sh[seg][2];
+                if (!(sx | sy | szz)) continue;
+                const double ax = sx * A.box.L[0], ay = sy * A.box.L[1], az = szz * A.box.L[2];
+                for (uint32_t t = s_off[seg] + threadIdx.x; t < s_off[seg + 1]; t += TILE_NT) {
+                    double2 p = sxy[t];
+                    p.x += ax;
+                    p.y += ay;
+                    sxy[t] = p;
+                    sz[t] += az;
+                }
+            }
+            __syncthreads();
+        }
+    } else {
+        __syncthreads();
         // four positions per thread in flight: the loads of a group are issued before the first is reduced and stored
         // (a run-major variant -- thread t takes element t of every run, no table search -- was slower: 0.292 vs 0.278 ms)
         constexpr int SU = 4;
@@ -207,15 +276,8 @@ __global__ void __launch_bounds__(TILE_NT) k_force_tile(const TileForceArgs A) {
                 }
             }
         }
-        // the sentinel every row is padded with (index ntile) and the 16 class sentinels of bank-ordered rows
-        // (S .. S + 15, bank_order.cuh): all staged far away
-        const uint32_t send = ((ntile + 1u + 15u) & ~15u) + 16u;
-        for (uint32_t t = ntile + threadIdx.x; t < send; t += TILE_NT) {
-            sxy[t] = make_double2(1e100, 1e100);
-            sz[t] = 1e100;
-        }
+        __syncthreads();
     }
-    __syncthreads();
     double acc[NPART];
     if (MODE != MODE_F)
 #pragma unroll
@@ -244,24 +306,26 @@ __global__ void __launch_bounds__(TILE_NT) k_force_tile(const TileForceArgs A) {
     }
 }
 
-template <int KIND, int TEAM, int V>
+template <int KIND, int TEAM, int V, int STAGE>
 static cudaError_t launch_tile_mode(int mode, unsigned nchunks, size_t smem, cudaStream_t st, const TileForceArgs &A) {
     if (mode == MODE_F) {
-        if (smem > 48 * 1024) cudaFuncSetAttribute(k_force_tile<KIND, MODE_F, TEAM, V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        k_force_tile<KIND, MODE_F, TEAM, V><<<nchunks, TILE_NT, smem, st>>>(A);
+        if (smem > 48 * 1024) cudaFuncSetAttribute(k_force_tile<KIND, MODE_F, TEAM, V, STAGE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        k_force_tile<KIND, MODE_F, TEAM, V, STAGE><<<nchunks, TILE_NT, smem, st>>>(A);
     } else {
-        if (smem > 48 * 1024) cudaFuncSetAttribute(k_force_tile<KIND, MODE_FALL, TEAM, V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        k_force_tile<KIND, MODE_FALL, TEAM, V><<<nchunks, TILE_NT, smem, st>>>(A);
+        if (smem > 48 * 1024) cudaFuncSetAttribute(k_force_tile<KIND, MODE_FALL, TEAM, V, STAGE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        k_force_tile<KIND, MODE_FALL, TEAM, V, STAGE><<<nchunks, TILE_NT, smem, st>>>(A);
     }
     return cudaGetLastError();
 }
 
+// A.prel_xy != NULL selects bulk-copy staging (TEAM 4, V 8 only: tile.cu plans aligned runs for no other layout)
 template <int KIND>
 cudaError_t parm_launch_force_tile_kind(int team, int v, int mode, unsigned nchunks, size_t smem, cudaStream_t st, const TileForceArgs &A) {
-    if (team == 8) return launch_tile_mode<KIND, 8, 4>(mode, nchunks, smem, st, A);
-    if (team == 2) return launch_tile_mode<KIND, 2, 8>(mode, nchunks, smem, st, A);
-    if (v == 4) return launch_tile_mode<KIND, 4, 4>(mode, nchunks, smem, st, A);
-    return launch_tile_mode<KIND, 4, 8>(mode, nchunks, smem, st, A);
+    if (team == 8) return launch_tile_mode<KIND, 8, 4, 0>(mode, nchunks, smem, st, A);
+    if (team == 2) return launch_tile_mode<KIND, 2, 8, 0>(mode, nchunks, smem, st, A);
+    if (v == 4) return launch_tile_mode<KIND, 4, 4, 0>(mode, nchunks, smem, st, A);
+    if (A.prel_xy) return launch_tile_mode<KIND, 4, 8, 1>(mode, nchunks, smem, st, A);
+    return launch_tile_mode<KIND, 4, 8, 0>(mode, nchunks, smem, st, A);
 }
 
 #define PARM_INSTANTIATE_FORCE_TILE_KIND(K) \

@@ -480,18 +480,29 @@ static int enqueue_step_core(parm_integ *g, uint64_t step, const int *abort_flag
     if (c->sh.on) {
         // communication stream: ghost positions for x(t+dt) and the global drift decision, overlapped with the
         // forces of the atoms whose neighbours are all owned (everything but the two boundary layers)
-        PTRY(parm_shard_step_comm(c, nl, nl ? nl->d_slot + slot : nullptr, nl ? nl->h_slot + slot : nullptr));
+        // bulk-copy staged tile kernels read prel: owned slots are refreshed here, behind K1 and ahead of the event the
+        // communication stream waits for; the ghost slots behind the exchange on that stream (below)
+        std::vector<parm_nlist *> lists;
+        for (parm_inter *it : g->inters)
+            if (std::find(lists.begin(), lists.end(), it->nl) == lists.end()) lists.push_back(it->nl);
+        for (parm_nlist *l : lists) PTRY(parm_tile_prep(l, 0, n, c->stream, abort_flag));
+        c->tile_prep_external = true;
+        int rcs = parm_shard_step_comm(c, nl, nl ? nl->d_slot + slot : nullptr, nl ? nl->h_slot + slot : nullptr);
         const uint32_t lo = c->sh.s_dn, hi = n - c->sh.s_up;
-        if (hi > lo) PTRY(launch_all_forces(g, abort_flag, lo, hi - lo));
+        if (!rcs && hi > lo) rcs = launch_all_forces(g, abort_flag, lo, hi - lo);
+        if (rcs) { c->tile_prep_external = false; return rcs; }
         // the two boundary layers follow the exchange on the communication stream itself (highest priority), so
         // their small grids share the GPU with the interior kernel instead of running as two partial waves after it
         {
             cudaStream_t main_stream = c->stream;
             c->stream = c->sh.comm_stream;
             int rc = 0;
-            if (lo) rc = launch_all_forces(g, abort_flag, 0, lo);
+            for (parm_nlist *l : lists)
+                if (!rc && c->n > n) rc = parm_tile_prep(l, n, c->n - n, c->stream, abort_flag);
+            if (!rc && lo) rc = launch_all_forces(g, abort_flag, 0, lo);
             if (!rc && n > hi) rc = launch_all_forces(g, abort_flag, std::max(hi, lo), n - std::max(hi, lo));
             c->stream = main_stream;
+            c->tile_prep_external = false;
             PTRY(rc);
         }
         PTRY(parm_shard_step_join(c)); // records the end of the communication stream's work; the main stream waits for it

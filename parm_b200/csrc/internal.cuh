@@ -100,6 +100,7 @@ struct parm_ctx {
     std::vector<parm_nlist *> nlists;
     std::vector<parm_inter *> inters;
     int num_sms;
+    bool tile_prep_external;   // the caller refreshes prel itself (sharded step: owned slots after K1, ghosts after the exchange)
     // optional per-class CUDA-event timing
     bool prof_on;
     struct ProfRec { int cls; cudaEvent_t a, b; };
@@ -150,8 +151,11 @@ struct TileChunk {
     uint32_t nseg, ntile;      // contiguous slot runs, staged atoms in total
     double o[3];               // origin the staged coordinates are relative to
     uint32_t flags, pad;       // bit 0: tile is wider than half the box on some axis: minimum image per pair as well
+                               // bit 1: some run carries a periodic image shift (sh[][] below; bulk-copy staging only)
     uint32_t seg_start[TILE_MAXSEG];
     uint32_t seg_off[TILE_MAXSEG + 1]; // exclusive prefix of the run lengths
+    int8_t sh[TILE_MAXSEG][3]; // image shift of every run in box lengths (-1, 0, +1), applied after the bulk copies land
+    uint8_t pad2[2];
 };
 struct TileInfo { // device-written, copied to the host with the build flags
     uint32_t nchunks, max_tile, bad, wide;
@@ -172,6 +176,13 @@ struct TileState {
     uint32_t col_cap;
     uint32_t *h_col;           // pinned copy of d_col (same layout, stride col_cap)
     TileInfo *d_info, *h_info; // h_info pinned
+    // bulk-copy staging (stage == 1): the pair kernel copies the runs of its tile from prel with cp.async.bulk (TMA)
+    // instead of loading, re-imaging and storing them with its own threads
+    int stage;                 // PARM_B200_TILE_STAGE (default 1); 0 = stage from pos inside the pair kernel
+    bool stage_aligned;        // the current chunk table has even-aligned runs and shift codes (what stage == 1 needs)
+    double2 *prel_xy;          // [npad] (x, y) - img * L: the image every atom had at the last rebuild, refreshed every step
+    double *prel_z;            // [npad]
+    float4 *img;               // [npad] image numbers (exact small integers), written with pw at every rebuild
 };
 
 // Mask-mode build (EXPERIMENTAL, PARM_B200_BUILD_MASKS=1, off by default): instead of expanded 32-bit rows the build
@@ -356,6 +367,8 @@ int parm_tile_localize(parm_nlist *nl);       // after the rows are final (ignor
 void parm_tile_invalidate(parm_nlist *nl);
 void parm_tile_free(parm_nlist *nl);
 int parm_tile_localize_masks(parm_nlist *nl); // mask-mode lists: rows16 straight from the pass masks
+// prel of slots [first, first + count) from pos (bulk-copy staging); no-op when the list does not stage that way
+int parm_tile_prep(parm_nlist *nl, uint32_t first, uint32_t count, cudaStream_t stream, const int *abort_flag);
 bool parm_tile_all_fit(const parm_nlist *nl); // every interaction on the list can run on the tile kernel
 bool parm_tile_usable(const parm_inter *it);  // this interaction can run on the tile kernel right now
 bool parm_tile_chunk_range(const parm_nlist *nl, uint32_t first, uint32_t end, uint32_t *c0, uint32_t *c1);

@@ -176,7 +176,8 @@ __global__ void k_permute(const uint32_t *__restrict__ perm, uint32_t n, uint32_
                           const uint32_t *__restrict__ order, double4 *pos_o, double *v_o, double *a_o, double *f_o,
                           uint32_t *order_o, uint32_t *slot_of, const double *__restrict__ diam_id, double *diam,
                           double *xlast, double4 *pw, BoxDev box, double half_skin, double lmax, double thr_min,
-                          const NlistFlags *flags, ShardDev sd, const uint8_t *__restrict__ ghost, uint8_t *ghost_o) {
+                          const NlistFlags *flags, ShardDev sd, const uint8_t *__restrict__ ghost, uint8_t *ghost_o,
+                          float4 *img) {
     const double delta = band_delta(flags, lmax, thr_min);
     for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < n; s += gridDim.x * blockDim.x) {
         uint32_t o = perm[s];
@@ -203,6 +204,9 @@ __global__ void k_permute(const uint32_t *__restrict__ perm, uint32_t n, uint32_
         q.z = p.z - box.L[2] * floor(p.z * box.invL[2]);
         q.w = dm >= 0.0 ? (0.5 * dm + half_skin) * (1.0 + delta) : __longlong_as_double(0x7ff8000000000000LL);
         pw[s] = q;
+        // image numbers of the wrapped copy (the slab axis of a sharded context: of the slab-relative frame lo + rel)
+        img[s] = make_float4((float)rint((p.x - (sd.on ? q.x + sd.lo : q.x)) * box.invL[0]), (float)rint((p.y - q.y) * box.invL[1]),
+                             (float)rint((p.z - q.z) * box.invL[2]), 0.f);
         // lastlocs[i] = a1->x (trackers.cpp:61); ghosts never take part in the drift rule (NaN never wins a >)
         const bool gh = ghost ? ghost[o] != 0 : false;
         if (ghost_o) ghost_o[s] = gh ? 1 : 0;
@@ -221,7 +225,7 @@ __global__ void k_append_ghosts(uint32_t first, uint32_t count, uint32_t npad, c
                                 const uint32_t *__restrict__ order, uint32_t *slot_of, const double *__restrict__ diam_id,
                                 double *diam, double *xlast, double4 *pw, uint8_t *ghost, uint32_t *cell_id_sorted,
                                 uint32_t *cnt, BoxDev box, GridDev g, ShardDev sd, double half_skin, double lmax,
-                                double thr_min, const NlistFlags *flags) {
+                                double thr_min, const NlistFlags *flags, float4 *img) {
     const double delta = band_delta(flags, lmax, thr_min);
     const double nanv = __longlong_as_double(0x7ff8000000000000LL);
     for (uint32_t q = blockIdx.x * blockDim.x + threadIdx.x; q < count; q += gridDim.x * blockDim.x) {
@@ -244,6 +248,8 @@ __global__ void k_append_ghosts(uint32_t first, uint32_t count, uint32_t npad, c
         diam[s] = dm;
         q4.w = dm >= 0.0 ? (0.5 * dm + half_skin) * (1.0 + delta) : nanv;
         pw[s] = q4;
+        img[s] = make_float4((float)rint((p.x - (rel + sd.lo)) * box.invL[0]), (float)rint((p.y - q4.y) * box.invL[1]),
+                             (float)rint((p.z - q4.z) * box.invL[2]), 0.f);
         xlast[s] = nanv;
         xlast[npad + s] = nanv;
         xlast[2 * (size_t)npad + s] = nanv;
@@ -744,6 +750,11 @@ extern "C" int parm_nlist_create(parm_ctx *c, double skin, parm_nlist **out) {
     CK(cudaMalloc(&nl->d_diam, np * 8));
     CK(cudaMalloc(&nl->xlast, 3 * np * 8));
     CK(cudaMalloc(&nl->pw, np * sizeof(double4)));
+    CK(cudaMalloc(&nl->tile.img, np * sizeof(float4)));
+    CK(cudaMalloc(&nl->tile.prel_xy, np * sizeof(double2)));
+    CK(cudaMalloc(&nl->tile.prel_z, np * sizeof(double)));
+    CK(cudaMemsetAsync(nl->tile.prel_xy, 0, np * sizeof(double2), c->stream));
+    CK(cudaMemsetAsync(nl->tile.prel_z, 0, np * sizeof(double), c->stream));
     nl->cell_sub = 1;
     if (const char *e = getenv("PARM_B200_CELL_SUB")) nl->cell_sub = atoi(e) == 2 ? 2 : 1;
     CK(cudaMemsetAsync(nl->xlast, 0, 3 * np * 8, c->stream));
@@ -955,7 +966,7 @@ int parm_nlist_sort_permute(parm_nlist *nl, const uint32_t *d_src, uint32_t nsrc
                                                           c->pos_alt, c->v_alt, c->a_alt, c->f_alt, c->order_alt,
                                                           c->slot_of, nl->d_diam_id, nl->d_diam, nl->xlast, nl->pw,
                                                           c->box, 0.5 * nl->skin, nl->lmax, nl->thr_min, nl->d_flags,
-                                                          nl->sd, c->ghost, c->ghost_alt);
+                                                          nl->sd, c->ghost, c->ghost_alt, nl->tile.img);
     CK_LAUNCH(c);
     std::swap(c->pos, c->pos_alt);
     std::swap(c->v, c->v_alt);
@@ -975,7 +986,7 @@ int parm_nlist_append_ghosts(parm_nlist *nl, uint32_t first, uint32_t count) {
         k_append_ghosts<<<grid_for(c, count, 256), 256, 0, c->stream>>>(first, count, c->npad, c->pos, c->order, c->slot_of,
                                                                         nl->d_diam_id, nl->d_diam, nl->xlast, nl->pw, c->ghost,
                                                                         nl->cell_id_sorted, nl->cnt, c->box, nl->g, nl->sd,
-                                                                        0.5 * nl->skin, nl->lmax, nl->thr_min, nl->d_flags);
+                                                                        0.5 * nl->skin, nl->lmax, nl->thr_min, nl->d_flags, nl->tile.img);
         CK_LAUNCH(c);
     }
     k_cell_start<<<grid_for(c, c->n + 1, 256), 256, 0, c->stream>>>(nl->cell_id_sorted, c->n, nl->ncell, nl->cell_start);

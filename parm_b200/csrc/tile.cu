@@ -70,7 +70,7 @@ k_tile_cols(const uint32_t *__restrict__ cell_start, uint32_t nc2, uint32_t ncol
 __global__ void __launch_bounds__(128)
 k_tile_chunks(const uint32_t *__restrict__ cell_start, const uint32_t *__restrict__ cell_id_sorted,
               const uint32_t *__restrict__ col_slot, const uint32_t *__restrict__ col_chunk, uint32_t ncol, uint32_t ch,
-              BoxDev box, GridDev g, StencilDev st, ShardDev sd, double margin, TileChunk *chunks, TileInfo *info) {
+              BoxDev box, GridDev g, StencilDev st, ShardDev sd, double margin, int aligned, TileChunk *chunks, TileInfo *info) {
     const uint32_t cidx = blockIdx.x * blockDim.x + threadIdx.x;
     if (cidx >= col_chunk[ncol]) return;
     uint32_t lo = 0, hi = ncol; // largest q with col_chunk[q] <= cidx (columns without atoms own no chunk)
@@ -88,6 +88,7 @@ k_tile_chunks(const uint32_t *__restrict__ cell_start, const uint32_t *__restric
     C.s0 = a;
     C.n = b - a;
     C.pad = 0;
+    C.pad2[0] = C.pad2[1] = 0;
     // z pieces (run axis): the chunk's cells +- one, split where the range wraps; the whole column once when
     // the range would overlap itself
     int za[2], zb[2], npiece = 1;
@@ -111,6 +112,16 @@ k_tile_chunks(const uint32_t *__restrict__ cell_start, const uint32_t *__restric
     uint32_t off = 0;
     const uint32_t nseg = TILE_MAXSEG;
     int sidx = 0;
+    // origin: centre of the chunk's cells (wrapped frame); min_image(x - o) then picks the right image of every
+    // staged atom whatever multiple of L its unwrapped coordinate carries
+    double h[3];
+    C.o[0] = st.open0 ? sd.lo + (cx + 0.5) * (sd.Ls / sd.nci) : (cx + 0.5) / g.scale[0];
+    h[0] = st.open0 ? 0.5 * sd.Ls / sd.nci : 0.5 / g.scale[0];
+    C.o[1] = (cy + 0.5) / g.scale[1];
+    h[1] = 0.5 / g.scale[1];
+    C.o[2] = 0.5 * (zlo + zhi + 1) / g.scale[2];
+    h[2] = 0.5 * (zhi - zlo + 1) / g.scale[2];
+    bool shifted = false;
     for (int xx = cx - 1; xx <= cx + 1; xx++) {
         int x2 = xx;
         if (st.open0) {
@@ -127,6 +138,22 @@ k_tile_chunks(const uint32_t *__restrict__ cell_start, const uint32_t *__restric
                     jb = cell_start[cbase + (uint32_t)za[p]];
                     je = cell_start[cbase + (uint32_t)zb[p] + 1];
                 }
+                C.sh[sidx][0] = C.sh[sidx][1] = C.sh[sidx][2] = 0;
+                if (aligned && je > jb) {
+                    // bulk-copy staging: 16-byte aligned source and size for the 8-byte z array -> runs start and end on
+                    // even slots (at most one stranger at either end, staged but never referenced by a row)
+                    jb &= ~1u;
+                    je = (je + 1u) & ~1u;
+                    // image of the run next to the chunk, from the geometry alone: centre of the run's cells in the frame
+                    // of prel (wrapped; slab-relative and continuous along the slab axis of a sharded context)
+                    const double cxr = (x2 + 0.5) / g.scale[0], cyr = (y2 + 0.5) / g.scale[1];
+                    const double czr = 0.5 * (za[p] + zb[p] + 1) / g.scale[2];
+                    const int s0i = st.open0 ? 0 : -(int)rint((cxr - C.o[0]) * box.invL[0]);
+                    const int s1i = -(int)rint((cyr - C.o[1]) * box.invL[1]);
+                    const int s2i = -(int)rint((czr - C.o[2]) * box.invL[2]);
+                    C.sh[sidx][0] = (int8_t)s0i; C.sh[sidx][1] = (int8_t)s1i; C.sh[sidx][2] = (int8_t)s2i;
+                    if (s0i | s1i | s2i) shifted = true;
+                }
                 C.seg_start[sidx] = jb;
                 C.seg_off[sidx] = off;
                 off += je - jb;
@@ -136,19 +163,14 @@ k_tile_chunks(const uint32_t *__restrict__ cell_start, const uint32_t *__restric
     C.seg_off[TILE_MAXSEG] = off;
     C.nseg = nseg;
     C.ntile = off;
-    // origin: centre of the chunk's cells (wrapped frame); min_image(x - o) then picks the right image of every
-    // staged atom whatever multiple of L its unwrapped coordinate carries
-    double h[3];
-    C.o[0] = st.open0 ? sd.lo + (cx + 0.5) * (sd.Ls / sd.nci) : (cx + 0.5) / g.scale[0];
-    h[0] = st.open0 ? 0.5 * sd.Ls / sd.nci : 0.5 / g.scale[0];
-    C.o[1] = (cy + 0.5) / g.scale[1];
-    h[1] = 0.5 / g.scale[1];
-    C.o[2] = 0.5 * (zlo + zhi + 1) / g.scale[2];
-    h[2] = 0.5 * (zhi - zlo + 1) / g.scale[2];
-    // staged differences equal the minimum image iff |x_i - o| + r_list stays below L/2 (margin = r_list + 2 skin)
-    for (int d = 0; d < 3; d++)
-        if (!(h[d] + margin < 0.4999 * box.L[d])) wide = true;
-    C.flags = wide ? 1u : 0u;
+    // staged differences equal the minimum image iff |x_i - o| + r_list stays below L/2 (margin = r_list + 2 skin); with
+    // per-run image shifts every atom of a run (whole cells) must lie on the same side: one more cell instead
+    for (int d = 0; d < 3; d++) {
+        const double cell = d == 0 && st.open0 ? sd.Ls / sd.nci : 1.0 / g.scale[d];
+        const double reach = aligned ? fmax(margin, cell * (1.0 + 1e-9)) : margin;
+        if (!(h[d] + reach < 0.4999 * box.L[d])) wide = true;
+    }
+    C.flags = (wide ? 1u : 0u) | (shifted ? 2u : 0u);
     chunks[cidx] = C;
     atomicMax(&info->max_tile, off);
     if (wide) atomicAdd(&info->wide, 1u);
@@ -347,6 +369,32 @@ k_tile_localize_masks(const TileChunk *__restrict__ chunks, MaskOut mo, const ui
     if (lost) atomicOr(&info->bad, 2u);
 }
 
+// ---- per step: positions in the image every atom had at the last rebuild (bulk-copy staging) ----------------------
+// prel = x - img * L is what the pair kernel's cp.async.bulk copies bring into shared memory unchanged: OriginBox::diff
+// (box.hpp:103) is resolved once per atom and step here instead of once per staged copy (17.7 per atom) there.
+__global__ void __launch_bounds__(256)
+k_tile_prep(const double4 *__restrict__ pos, const float4 *__restrict__ img, uint32_t first, uint32_t count, BoxDev box,
+            double2 *__restrict__ prel_xy, double *__restrict__ prel_z, const int *abort_flag) {
+    if (abort_flag && *abort_flag) return;
+    for (uint32_t q = blockIdx.x * blockDim.x + threadIdx.x; q < count; q += gridDim.x * blockDim.x) {
+        const uint32_t s = first + q;
+        const double4 p = pos[s];
+        const float4 g = img[s];
+        prel_xy[s] = make_double2(fma(-(double)g.x, box.L[0], p.x), fma(-(double)g.y, box.L[1], p.y));
+        prel_z[s] = fma(-(double)g.z, box.L[2], p.z);
+    }
+}
+
+int parm_tile_prep(parm_nlist *nl, uint32_t first, uint32_t count, cudaStream_t stream, const int *abort_flag) {
+    parm_ctx *c = nl->ctx;
+    const TileState &t = nl->tile;
+    if (!t.valid || !t.stage_aligned || !count) return 0;
+    const unsigned nb = std::min<unsigned>((count + 255) / 256, (unsigned)c->num_sms * 16u);
+    k_tile_prep<<<nb, 256, 0, stream>>>(c->pos, t.img, first, count, c->box, t.prel_xy, t.prel_z, abort_flag);
+    CK_LAUNCH(c);
+    return 0;
+}
+
 // ---- host side -----------------------------------------------------------------------------------
 static bool kind_on_tile(int kind) {
     const int kk = PARM_KERNEL_KIND(kind);
@@ -371,6 +419,8 @@ static void tile_config(parm_nlist *nl) {
     t.team = e ? atoi(e) : 4;
     e = getenv("PARM_B200_TILE_V");
     t.v = e ? atoi(e) : 8;
+    e = getenv("PARM_B200_TILE_STAGE");
+    t.stage = e ? atoi(e) : 1;
     if (!((t.team == 4 && (t.v == 8 || t.v == 4)) || (t.team == 8 && t.v == 4) || (t.team == 2 && t.v == 8))) {
         t.team = 4;
         t.v = 8;
@@ -390,6 +440,10 @@ void parm_tile_free(parm_nlist *nl) {
     if (t.d_info) cudaFree(t.d_info);
     if (t.h_info) cudaFreeHost(t.h_info);
     if (t.h_col) cudaFreeHost(t.h_col);
+    if (t.img) cudaFree(t.img);
+    if (t.prel_xy) cudaFree(t.prel_xy);
+    if (t.prel_z) cudaFree(t.prel_z);
+    t.img = 0; t.prel_xy = 0; t.prel_z = 0;
     t.d_chunks = 0; t.rows16 = 0; t.d_col = 0; t.d_info = 0; t.h_info = 0; t.h_col = 0;
 }
 
@@ -430,8 +484,13 @@ int parm_tile_plan_enqueue(parm_nlist *nl) {
     k_tile_cols<<<1, 1024, 0, c->stream>>>(nl->cell_start, (uint32_t)nl->g.nc[2], ncol, (uint32_t)t.ch, t.d_col, t.d_col + t.col_cap, t.d_info);
     CK_LAUNCH(c);
     const double margin = (nl->maxdiam + nl->skin) * (1.0 + 1e-6) + 2.0 * nl->skin;
+    // bulk-copy staging subtracts absolute coordinates of the order of the box edge: keep it to boxes where that costs
+    // less than 2^-40 (|x| < 4096); larger boxes stage origin-relative positions with the kernel's own threads
+    const double lmaxbox = std::max(c->box.L[0], std::max(c->box.L[1], c->box.L[2]));
+    t.stage_aligned = t.stage == 1 && lmaxbox < 4096.0 && t.team == 4 && t.v == 8;
     k_tile_chunks<<<(maxchunks + 127) / 128, 128, 0, c->stream>>>(nl->cell_start, nl->cell_id_sorted, t.d_col, t.d_col + t.col_cap, ncol,
-                                                                 (uint32_t)t.ch, c->box, nl->g, nl->st, nl->sd, margin, t.d_chunks, t.d_info);
+                                                                 (uint32_t)t.ch, c->box, nl->g, nl->st, nl->sd, margin,
+                                                                 t.stage_aligned ? 1 : 0, t.d_chunks, t.d_info);
     CK_LAUNCH(c);
     t.planned = true;
     return 0;
