@@ -31,12 +31,19 @@ static inline unsigned grid_for(const parm_ctx *ctx, uint32_t n, unsigned block,
 // fused with the NeighborList skin-drift reduction (trackers.cpp:23-53): the displacement only depends on
 // x(t+dt), which this kernel produces, so the rebuild decision of the step is known while the forces of the
 // step are still being computed (and, sharded, its all-gather overlaps the force kernel).
-template <int D, bool DRIFT>
+// PREL: also writes the image-resolved copy of x(t+dt) that the bulk-copy staged pair kernel reads (tile.cu, k_tile_prep)
+struct PrelOut {
+    const float4 *img;
+    double2 *xy;
+    double *z;
+    double L[3];
+};
+template <int D, bool DRIFT, bool PREL>
 __global__ void __launch_bounds__(I_BLOCK)
 k_verlet1(double4 *__restrict__ pos, double *__restrict__ v, const double *__restrict__ a, uint32_t n, uint32_t npad,
           double dt, double hdt2, double hdt, const int *__restrict__ abort_flag, const double *__restrict__ xlast,
           double skin, double *d_top2, unsigned int *counter, NlistFlags *dflags, NlistFlags *hflags, int *d_slot,
-          int *h_slot) {
+          int *h_slot, const PrelOut R) {
     if (abort_flag && *abort_flag) return; // speculative step behind a rebuild request: leave the state alone
     double b1 = 0.0, b2 = 0.0;
     for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < n; s += gridDim.x * blockDim.x) {
@@ -53,6 +60,8 @@ k_verlet1(double4 *__restrict__ pos, double *__restrict__ v, const double *__res
             xl[1] = xlast[npad + s];
             xl[2] = xlast[2 * (size_t)npad + s];
         }
+        float4 im = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (PREL) im = R.img[s];
         if (frozen_le(p.w)) { // m <= 0 || isinf(m): v = 0, position untouched
 #pragma unroll
             for (int d = 0; d < D; d++) v[(size_t)d * npad + s] = 0.0;
@@ -67,6 +76,10 @@ k_verlet1(double4 *__restrict__ pos, double *__restrict__ v, const double *__res
             p.y = x[1];
             if (D == 3) p.z = x[2];
             pos[s] = p;
+        }
+        if (PREL) {
+            R.xy[s] = make_double2(fma(-(double)im.x, R.L[0], p.x), fma(-(double)im.y, R.L[1], p.y));
+            R.z[s] = fma(-(double)im.z, R.L[2], p.z);
         }
         // atoms that were never add()ed have NaN lastlocs (set at rebuild): NaN never wins a '>' comparison
         if (DRIFT) top2_push(b1, b2, drift_dist(p, xl[0], xl[1], xl[2]));
@@ -433,15 +446,28 @@ static int enqueue_step_core(parm_integ *g, uint64_t step, const int *abort_flag
 #define DRIFTARGS abort_flag, nl ? nl->xlast : nullptr, nl ? nl->skin : 0.0, nl ? nl->d_top2 : nullptr, \
                   nl ? nl->d_counter : nullptr, nl ? nl->d_flags : nullptr, nl ? nl->h_flags : nullptr, d_slot, h_slot
     SolConst K;
+    // CollectionVerlet whose interactions all use the tracked list, staged by bulk copies: K1 itself leaves the
+    // image-resolved copy of x(t+dt) for the pair kernel (one pass over the positions fewer per step)
+    bool k1_prel = g->type == 0 && nl && c->D == 3 && nl->tile.valid && nl->tile.stage_aligned && !g->inters.empty();
+    for (parm_inter *it : g->inters) k1_prel = k1_prel && it->nl == nl;
+    const char *ef = getenv("PARM_B200_K1_PREL"); // (read per step: the sweeps toggle it inside one process)
+    const int fuse_env = ef ? atoi(ef) : 1;
+    k1_prel = k1_prel && fuse_env;
+    PrelOut R;
+    R.img = nl ? nl->tile.img : nullptr;
+    R.xy = nl ? nl->tile.prel_xy : nullptr;
+    R.z = nl ? nl->tile.prel_z : nullptr;
+    for (int d = 0; d < 3; d++) R.L[d] = c->box.L[d];
     PTRY(parm_prof_begin(c, PARM_PROF_INTEG1));
     if (g->type == 0) {
         const double hdt2 = dt * dt / 2, hdt = dt / 2;
         if (c->D == 3) {
-            if (nl) k_verlet1<3, true><<<grid1, I_BLOCK, 0, c->stream>>>(c->pos, c->v, c->a, n, c->npad, dt, hdt2, hdt, DRIFTARGS);
-            else k_verlet1<3, false><<<grid1, I_BLOCK, 0, c->stream>>>(c->pos, c->v, c->a, n, c->npad, dt, hdt2, hdt, DRIFTARGS);
+            if (k1_prel) k_verlet1<3, true, true><<<grid1, I_BLOCK, 0, c->stream>>>(c->pos, c->v, c->a, n, c->npad, dt, hdt2, hdt, DRIFTARGS, R);
+            else if (nl) k_verlet1<3, true, false><<<grid1, I_BLOCK, 0, c->stream>>>(c->pos, c->v, c->a, n, c->npad, dt, hdt2, hdt, DRIFTARGS, R);
+            else k_verlet1<3, false, false><<<grid1, I_BLOCK, 0, c->stream>>>(c->pos, c->v, c->a, n, c->npad, dt, hdt2, hdt, DRIFTARGS, R);
         } else {
-            if (nl) k_verlet1<2, true><<<grid1, I_BLOCK, 0, c->stream>>>(c->pos, c->v, c->a, n, c->npad, dt, hdt2, hdt, DRIFTARGS);
-            else k_verlet1<2, false><<<grid1, I_BLOCK, 0, c->stream>>>(c->pos, c->v, c->a, n, c->npad, dt, hdt2, hdt, DRIFTARGS);
+            if (nl) k_verlet1<2, true, false><<<grid1, I_BLOCK, 0, c->stream>>>(c->pos, c->v, c->a, n, c->npad, dt, hdt2, hdt, DRIFTARGS, R);
+            else k_verlet1<2, false, false><<<grid1, I_BLOCK, 0, c->stream>>>(c->pos, c->v, c->a, n, c->npad, dt, hdt2, hdt, DRIFTARGS, R);
         }
     } else {
         K.dt = dt;
@@ -485,7 +511,8 @@ static int enqueue_step_core(parm_integ *g, uint64_t step, const int *abort_flag
         std::vector<parm_nlist *> lists;
         for (parm_inter *it : g->inters)
             if (std::find(lists.begin(), lists.end(), it->nl) == lists.end()) lists.push_back(it->nl);
-        for (parm_nlist *l : lists) PTRY(parm_tile_prep(l, 0, n, c->stream, abort_flag));
+        for (parm_nlist *l : lists)
+            if (!(k1_prel && l == nl)) PTRY(parm_tile_prep(l, 0, n, c->stream, abort_flag));
         c->tile_prep_external = true;
         int rcs = parm_shard_step_comm(c, nl, nl ? nl->d_slot + slot : nullptr, nl ? nl->h_slot + slot : nullptr);
         const uint32_t lo = c->sh.s_dn, hi = n - c->sh.s_up;
@@ -507,7 +534,10 @@ static int enqueue_step_core(parm_integ *g, uint64_t step, const int *abort_flag
         }
         PTRY(parm_shard_step_join(c)); // records the end of the communication stream's work; the main stream waits for it
     } else {
-        PTRY(launch_all_forces(g, abort_flag));
+        c->tile_prep_external = k1_prel;
+        const int rcf = launch_all_forces(g, abort_flag);
+        c->tile_prep_external = false;
+        PTRY(rcf);
     }
     PTRY(parm_prof_end(c));
 

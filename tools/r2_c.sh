@@ -9,8 +9,9 @@ sys.argv = ["tile_sweep"]
 import tools.tile_sweep as ts
 from parm_b200 import workloads as W
 w = W.config3(100)
-for env in [{"PARM_B200_TILE_STAGE": 0}, {"PARM_B200_TILE_STAGE": 1}, {"PARM_B200_TILE_STAGE": 1, "PARM_B200_BUILD_MASKS": 1}]:
-    for k in ("PARM_B200_TILE_BANKS", "PARM_B200_BUILD_MASKS", "PARM_B200_TILE_STAGE"):
+for env in [{"PARM_B200_TILE_STAGE": 0}, {"PARM_B200_TILE_STAGE": 1, "PARM_B200_K1_PREL": 0}, {"PARM_B200_TILE_STAGE": 1},
+            {"PARM_B200_TILE_STAGE": 1, "PARM_B200_TILE_BANKS": 1}]:
+    for k in ("PARM_B200_TILE_BANKS", "PARM_B200_BUILD_MASKS", "PARM_B200_TILE_STAGE", "PARM_B200_K1_PREL"):
         os.environ.pop(k, None)
     e = {"PARM_B200_TILE": 1}
     e.update(env)
