@@ -87,6 +87,7 @@ __device__ __forceinline__ void tile_rows(const TileForceArgs &A, uint32_t na, u
     constexpr uint32_t NTEAM = TILE_NT / TEAM;
     const uint32_t tl = threadIdx.x % TEAM;
     const double c12 = 12.0 * A.P1.eps;
+    const long long rc2_bits = __double_as_longlong(A.P1.rc2);
     uint32_t my = my0;
     for (uint32_t a = threadIdx.x / TEAM; a - threadIdx.x / TEAM < na; a += NTEAM) { // every lane of a warp runs the same trips (shuffles below)
         const bool valid = a < na;
@@ -116,6 +117,22 @@ __device__ __forceinline__ void tile_rows(const TileForceArgs &A, uint32_t na, u
                     dz = min_image_fast(dz, A.box.L[2], A.box.invL[2]);
                 }
                 const double dsq = dx * dx + (dy * dy + dz * dz);
+                if (!want_obs) {
+                    // forces only: 17 operations on the fp64 pipe per pair (it bounds this kernel). The factor 12 epsilon
+                    // is applied once per atom, the cut-off test is an integer comparison of the bit patterns (both
+                    // numbers are positive), ir6 (ir6 - 1) / dsq comes out of one fused multiply-add
+                    const double w = rcp_pos(dsq);
+                    const double s2 = A.P1.sig2 * w;
+                    const double ir6 = (s2 * s2) * s2;
+                    const double b = ir6 * w;
+                    const double t = fma(b, ir6, -b);
+                    const bool in = __double_as_longlong(dsq) <= rc2_bits; // sentinel pads: dsq ~ 1e200, beyond any cutoff
+                    const double scal = in ? t : 0.0;
+                    fx = fma(dx, scal, fx);
+                    fy = fma(dy, scal, fy);
+                    fz = fma(dz, scal, fz);
+                    continue;
+                }
                 double scal, en;
                 lj_eval<KIND>(A.P1, c12, dsq, want_obs, scal, en); // sentinel pads: dsq ~ 1e200, beyond any cutoff
                 const double gx = dx * scal, gy = dy * scal, gz = dz * scal;
@@ -135,6 +152,11 @@ __device__ __forceinline__ void tile_rows(const TileForceArgs &A, uint32_t na, u
             q = qn;
         }
         my = myn;
+        if (!want_obs) {
+            fx *= c12;
+            fy *= c12;
+            fz *= c12;
+        }
         if (MODE == MODE_F || A.store) {
 #pragma unroll
             for (int o = TEAM / 2; o; o >>= 1) {
