@@ -10,6 +10,7 @@
 // Same FULL rows, same fixed summation order inside a lane, team and block as force_kernel.cuh: no atomics,
 // run-to-run deterministic.
 #pragma once
+#include <algorithm>
 #include "force_kernel.cuh"
 
 struct TileForceArgs {
@@ -28,6 +29,7 @@ struct TileForceArgs {
     int accumulate, store;
     double *partials;
     const int *abort_flag;
+    uint32_t pers_blocks;    // > 0: persistent double-buffered kernel with this many blocks (bulk-copy staging only)
 };
 
 // 1/x for normal positive x without the division's special-case path: MUFU.RCP64H seed (2^-23) and one
@@ -80,11 +82,11 @@ __device__ __forceinline__ RowWords<V> load_row_words(const uint16_t *p) {
 // requested before the arithmetic of pass k starts, so the DRAM latency of the streamed rows (the top stall
 // of the non-pipelined loop: long_scoreboard 5.6 warps per issue) hides behind ~160 fp64 instructions.
 // my0 / q0: length and first pass of the team's first atom, loaded by the caller before the tile was staged.
-template <int KIND, int MODE, int TEAM, int V, bool MI>
+template <int KIND, int MODE, int TEAM, int V, bool MI, int NT = TILE_NT>
 __device__ __forceinline__ void tile_rows(const TileForceArgs &A, uint32_t na, uint32_t s0, uint32_t own, const double2 *sxy,
                                           const double *sz, double (&acc)[NPART], uint32_t my0, RowWords<V> q) {
     constexpr bool want_obs = MODE != MODE_F;
-    constexpr uint32_t NTEAM = TILE_NT / TEAM;
+    constexpr uint32_t NTEAM = NT / TEAM;
     const uint32_t tl = threadIdx.x % TEAM;
     const double c12 = 12.0 * A.P1.eps;
     const long long rc2_bits = __double_as_longlong(A.P1.rc2);
@@ -328,6 +330,150 @@ __global__ void __launch_bounds__(TILE_NT) k_force_tile(const TileForceArgs A) {
     }
 }
 
+// ---- persistent, double-buffered variant (TEAM 4, V 8, bulk-copy staging) --------------------------------------------
+// ncu on the one-block-per-chunk kernel: a quarter of the warp time is spent waiting for the chunk's tile (the block
+// reads its run table, then issues the copies, then waits for them) and every block pays its own tail. Here 2 blocks of
+// 512 threads stay resident per SM and walk the chunks blockIdx.x, blockIdx.x + gridDim.x, ...; each owns TWO tile
+// buffers: while the 128 teams work on chunk k out of one buffer, the copies of chunk k+1 land in the other (issued by
+// warp 0, whose lanes carry the run table of the next chunk in registers one chunk ahead). Same rows, same summation
+// order: the results are bit-identical to k_force_tile.
+#define TILE_PNT 512
+struct TileMeta { // per buffer, written by warp 0 when it issues the copies
+    uint32_t ntile, na, s0, flags, own, cidx, pad0, pad1;
+    uint32_t off[TILE_MAXSEG + 1];
+    int8_t sh[TILE_MAXSEG][3];
+};
+
+template <int KIND, int MODE>
+__global__ void __launch_bounds__(TILE_PNT, 2) k_force_tile_pers(const TileForceArgs A, const uint32_t nchunks) {
+    if (A.abort_flag && *A.abort_flag) return; // speculatively enqueued step whose predecessor asked for a rebuild
+    constexpr int TEAM = 4, V = 8;
+    extern __shared__ __align__(16) double s_xyz[]; // two buffers of 3 * cap doubles
+    __shared__ TileMeta s_meta[2];
+    __shared__ __align__(8) unsigned long long s_bar[2];
+    __shared__ double red[MODE != MODE_F ? NPART : 1][TILE_PNT / 32];
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t bufdoubles = 3 * A.cap;
+    if (threadIdx.x == 0) {
+        mbar_init((uint32_t)__cvta_generic_to_shared(&s_bar[0]), 1);
+        mbar_init((uint32_t)__cvta_generic_to_shared(&s_bar[1]), 1);
+    }
+    __syncthreads();
+    // warp 0: issue the copies of chunk `c` into buffer b (every reader of that buffer has passed the barrier that ends
+    // the chunk before the previous one)
+    auto issue = [&](uint32_t c, uint32_t b) {
+        const TileChunk *C = A.chunks + c;
+        double2 *sxy = reinterpret_cast<double2 *>(s_xyz + (size_t)b * bufdoubles);
+        double *sz = s_xyz + (size_t)b * bufdoubles + 2 * (size_t)A.cap;
+        const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&s_bar[b]);
+        uint32_t st = 0, o0 = 0, o1 = 0;
+        if (lane < TILE_MAXSEG) {
+            st = C->seg_start[lane];
+            o0 = C->seg_off[lane];
+            o1 = C->seg_off[lane + 1];
+        }
+        const uint32_t ntile = C->ntile, s0 = C->s0;
+        TileMeta &M = s_meta[b];
+        if (lane < TILE_MAXSEG) {
+            M.off[lane] = o0;
+            M.sh[lane][0] = C->sh[lane][0];
+            M.sh[lane][1] = C->sh[lane][1];
+            M.sh[lane][2] = C->sh[lane][2];
+        }
+        // the chunk's own atoms are consecutive entries of the centre column's run (piece 0 or 1 of stencil column 4)
+        const uint32_t st8 = __shfl_sync(0xffffffffu, st, 8), st9 = __shfl_sync(0xffffffffu, st, 9);
+        const uint32_t of8 = __shfl_sync(0xffffffffu, o0, 8), of9 = __shfl_sync(0xffffffffu, o0, 9);
+        if (lane == 0) {
+            M.off[TILE_MAXSEG] = ntile;
+            M.ntile = ntile;
+            M.na = C->n;
+            M.s0 = s0;
+            M.flags = C->flags;
+            M.cidx = c;
+            const uint32_t d8 = s0 - st8;
+            M.own = (s0 >= st8 && d8 < of9 - of8) ? of8 + d8 : of9 + (s0 - st9);
+            mbar_arrive_expect_tx(bar, ntile * 24u);
+        }
+        // the sentinel every row is padded with (index ntile) and the 16 class sentinels of bank-ordered rows
+        const uint32_t send = ((ntile + 1u + 15u) & ~15u) + 16u;
+        for (uint32_t t = ntile + lane; t < send; t += 32) {
+            sxy[t] = make_double2(1e100, 1e100);
+            sz[t] = 1e100;
+        }
+        __syncwarp();
+        if (lane < TILE_MAXSEG && o1 > o0) { // even start, even length: both copies are 16-byte aligned at both ends
+            bulk_g2s((uint32_t)__cvta_generic_to_shared(sxy + o0), A.prel_xy + st, (o1 - o0) * 16u, bar);
+            bulk_g2s((uint32_t)__cvta_generic_to_shared(sz + o0), A.prel_z + st, (o1 - o0) * 8u, bar);
+        }
+    };
+    uint32_t c = blockIdx.x;
+    if (c >= nchunks) return;
+    if (warp == 0) issue(c, 0);
+    __syncthreads(); // s_meta[0] is visible to every warp
+    for (uint32_t k = 0; c < nchunks; k++, c += gridDim.x) {
+        const uint32_t b = k & 1u;
+        const uint32_t cn = c + gridDim.x;
+        if (warp == 0 && cn < nchunks) issue(cn, b ^ 1u);
+        const TileChunk *C = A.chunks + c;
+        const uint32_t na = C->n, s0 = C->s0; // (also in s_meta[b]; read here so that the row prefetch does not wait for it)
+        // first (only) atom of this team: row length and first pass, in flight while the tile lands
+        uint32_t my0 = 0;
+        RowWords<V> q0;
+#pragma unroll
+        for (int e = 0; e < V / 2; e++) q0.w[e] = 0;
+        {
+            const uint32_t a = threadIdx.x / TEAM;
+            if (a < na) {
+                const uint32_t s = s0 + a;
+                my0 = min(A.cnt[s], A.kmax);
+                q0 = load_row_words<V>(A.rows16 + (size_t)s * A.kmax + (threadIdx.x % TEAM) * V);
+            }
+        }
+        double2 *sxy = reinterpret_cast<double2 *>(s_xyz + (size_t)b * bufdoubles);
+        double *sz = s_xyz + (size_t)b * bufdoubles + 2 * (size_t)A.cap;
+        mbar_wait((uint32_t)__cvta_generic_to_shared(&s_bar[b]), (k >> 1) & 1u);
+        const TileMeta &M = s_meta[b]; // written before the barrier that ended the previous chunk (or the one after init)
+        const uint32_t cflags = M.flags;
+        if (cflags & 2u) { // runs reached across a periodic face: add their image shift
+            for (uint32_t seg = 0; seg < TILE_MAXSEG; seg++) {
+                const int sx = M.sh[seg][0], sy = M.sh[seg][1], szz = M.sh[seg][2];
+                if (!(sx | sy | szz)) continue;
+                const double ax = sx * A.box.L[0], ay = sy * A.box.L[1], az = szz * A.box.L[2];
+                for (uint32_t t = M.off[seg] + threadIdx.x; t < M.off[seg + 1]; t += TILE_PNT) {
+                    double2 p = sxy[t];
+                    p.x += ax;
+                    p.y += ay;
+                    sxy[t] = p;
+                    sz[t] += az;
+                }
+            }
+            __syncthreads();
+        }
+        double acc[NPART];
+        if (MODE != MODE_F)
+#pragma unroll
+            for (int q = 0; q < NPART; q++) acc[q] = 0.0;
+        if (cflags & 1u) tile_rows<KIND, MODE, TEAM, V, true, TILE_PNT>(A, na, s0, M.own, sxy, sz, acc, my0, q0);
+        else tile_rows<KIND, MODE, TEAM, V, false, TILE_PNT>(A, na, s0, M.own, sxy, sz, acc, my0, q0);
+        if (MODE != MODE_F) {
+#pragma unroll
+            for (int q = 0; q < NPART; q++) {
+                double x = acc[q];
+#pragma unroll
+                for (int o = 16; o; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+                if (lane == 0) red[q][warp] = x;
+            }
+            __syncthreads();
+            if (threadIdx.x < NPART) {
+                double x = 0;
+                for (int ww = 0; ww < TILE_PNT / 32; ww++) x += red[threadIdx.x][ww];
+                A.partials[(size_t)c * NPART + threadIdx.x] = x;
+            }
+        }
+        __syncthreads(); // everyone is done with buffer b (and red[]): the next iteration's issue() may overwrite it
+    }
+}
+
 template <int KIND, int TEAM, int V, int STAGE>
 static cudaError_t launch_tile_mode(int mode, unsigned nchunks, size_t smem, cudaStream_t st, const TileForceArgs &A) {
     if (mode == MODE_F) {
@@ -346,6 +492,17 @@ cudaError_t parm_launch_force_tile_kind(int team, int v, int mode, unsigned nchu
     if (team == 8) return launch_tile_mode<KIND, 8, 4, 0>(mode, nchunks, smem, st, A);
     if (team == 2) return launch_tile_mode<KIND, 2, 8, 0>(mode, nchunks, smem, st, A);
     if (v == 4) return launch_tile_mode<KIND, 4, 4, 0>(mode, nchunks, smem, st, A);
+    if (A.prel_xy && A.pers_blocks) { // persistent double-buffered kernel: 2 blocks of 512 threads per SM, two tile buffers each
+        const size_t smem2 = 2 * smem;
+        if (mode == MODE_F) {
+            cudaFuncSetAttribute(k_force_tile_pers<KIND, MODE_F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
+            k_force_tile_pers<KIND, MODE_F><<<std::min(nchunks, A.pers_blocks), TILE_PNT, smem2, st>>>(A, nchunks);
+        } else {
+            cudaFuncSetAttribute(k_force_tile_pers<KIND, MODE_FALL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
+            k_force_tile_pers<KIND, MODE_FALL><<<std::min(nchunks, A.pers_blocks), TILE_PNT, smem2, st>>>(A, nchunks);
+        }
+        return cudaGetLastError();
+    }
     if (A.prel_xy) return launch_tile_mode<KIND, 4, 8, 1>(mode, nchunks, smem, st, A);
     return launch_tile_mode<KIND, 4, 8, 0>(mode, nchunks, smem, st, A);
 }

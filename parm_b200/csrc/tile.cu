@@ -80,7 +80,10 @@ k_tile_chunks(const uint32_t *__restrict__ cell_start, const uint32_t *__restric
     }
     const uint32_t q = lo;
     const uint32_t k = cidx - col_chunk[q];
-    const uint32_t a = col_slot[q] + k * ch, b = min(a + ch, col_slot[q + 1]);
+    // the column's atoms are spread evenly over its chunks (a column of 907 atoms: 8 x 114 instead of 7 x 128 + 11)
+    const uint32_t ccnt = col_slot[q + 1] - col_slot[q], cnch = col_chunk[q + 1] - col_chunk[q];
+    const uint32_t csz = min(ch, (ccnt + cnch - 1) / cnch);
+    const uint32_t a = col_slot[q] + k * csz, b = min(a + csz, col_slot[q + 1]);
     const int nc0 = g.nc[0], nc1 = g.nc[1], nc2 = g.nc[2];
     const int cx = (int)(q / (uint32_t)nc1), cy = (int)(q % (uint32_t)nc1);
     const int zlo = (int)(cell_id_sorted[a] % (uint32_t)nc2), zhi = (int)(cell_id_sorted[b - 1] % (uint32_t)nc2);
