@@ -117,6 +117,7 @@ static int launch_forces(parm_inter *it, int run, bool accumulate, double *d_out
         const char *ep = getenv("PARM_B200_TILE_PERS"); // (read per launch: the sweeps toggle it inside one process)
         const bool pers = bulk && (ep ? atoi(ep) != 0 : true) && 2 * 3 * (size_t)T.cap * 8 + 2048 <= 113 * 1024;
         T.pers_blocks = pers ? 2u * (uint32_t)c->num_sms : 0u;
+        T.chunk_s0 = nl->tile.d_s0 + chunk0;
         T.chunks = nl->tile.d_chunks + chunk0;
         T.rows16 = nl->tile.rows16;
         T.cnt = nl->cnt;

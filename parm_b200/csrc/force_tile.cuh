@@ -30,6 +30,7 @@ struct TileForceArgs {
     double *partials;
     const int *abort_flag;
     uint32_t pers_blocks;    // > 0: persistent double-buffered kernel with this many blocks (bulk-copy staging only)
+    const uint32_t *chunk_s0; // first slot of every chunk of the launch and the end of the last one (persistent kernel)
 };
 
 // 1/x for normal positive x without the division's special-case path: MUFU.RCP64H seed (2^-23) and one
@@ -409,26 +410,36 @@ __global__ void __launch_bounds__(TILE_PNT, 2) k_force_tile_pers(const TileForce
     uint32_t c = blockIdx.x;
     if (c >= nchunks) return;
     if (warp == 0) issue(c, 0);
-    __syncthreads(); // s_meta[0] is visible to every warp
-    for (uint32_t k = 0; c < nchunks; k++, c += gridDim.x) {
-        const uint32_t b = k & 1u;
-        const uint32_t cn = c + gridDim.x;
-        if (warp == 0 && cn < nchunks) issue(cn, b ^ 1u);
-        const TileChunk *C = A.chunks + c;
-        const uint32_t na = C->n, s0 = C->s0; // (also in s_meta[b]; read here so that the row prefetch does not wait for it)
-        // first (only) atom of this team: row length and first pass, in flight while the tile lands
-        uint32_t my0 = 0;
-        RowWords<V> q0;
+    // Three chunks are in flight per thread: the one being computed (row length and first pass of the team's atom in
+    // registers), the next one (its first slot known: row length and first pass requested now) and the one after
+    // (first slot requested now) -- no dependent global load is ever waited for at the start of a chunk.
+    const uint32_t G = gridDim.x, team = threadIdx.x / TEAM, tl = threadIdx.x % TEAM;
+    auto rows_of = [&](uint32_t s0x, uint32_t nax, uint32_t &my, RowWords<V> &q) {
+        my = 0;
 #pragma unroll
-        for (int e = 0; e < V / 2; e++) q0.w[e] = 0;
-        {
-            const uint32_t a = threadIdx.x / TEAM;
-            if (a < na) {
-                const uint32_t s = s0 + a;
-                my0 = min(A.cnt[s], A.kmax);
-                q0 = load_row_words<V>(A.rows16 + (size_t)s * A.kmax + (threadIdx.x % TEAM) * V);
-            }
+        for (int e = 0; e < V / 2; e++) q.w[e] = 0;
+        if (team < nax) {
+            const uint32_t s = s0x + team;
+            my = min(A.cnt[s], A.kmax);
+            q = load_row_words<V>(A.rows16 + (size_t)s * A.kmax + tl * V);
         }
+    };
+    uint32_t s0 = A.chunk_s0[c], na = A.chunk_s0[c + 1] - s0;
+    uint32_t s0n = 0, nan = 0;
+    if (c + G < nchunks) { s0n = A.chunk_s0[c + G]; nan = A.chunk_s0[c + G + 1] - s0n; }
+    uint32_t my0;
+    RowWords<V> q0;
+    rows_of(s0, na, my0, q0);
+    __syncthreads(); // s_meta[0] is visible to every warp
+    for (uint32_t k = 0; c < nchunks; k++, c += G) {
+        const uint32_t b = k & 1u;
+        const uint32_t cn = c + G;
+        if (warp == 0 && cn < nchunks) issue(cn, b ^ 1u);
+        uint32_t my1;
+        RowWords<V> q1;
+        rows_of(s0n, nan, my1, q1); // next chunk: consumed at the bottom of this iteration
+        uint32_t s0nn = 0, nann = 0;
+        if (cn + G < nchunks) { s0nn = A.chunk_s0[cn + G]; nann = A.chunk_s0[cn + G + 1] - s0nn; }
         double2 *sxy = reinterpret_cast<double2 *>(s_xyz + (size_t)b * bufdoubles);
         double *sz = s_xyz + (size_t)b * bufdoubles + 2 * (size_t)A.cap;
         mbar_wait((uint32_t)__cvta_generic_to_shared(&s_bar[b]), (k >> 1) & 1u);
@@ -471,6 +482,8 @@ __global__ void __launch_bounds__(TILE_PNT, 2) k_force_tile_pers(const TileForce
             }
         }
         __syncthreads(); // everyone is done with buffer b (and red[]): the next iteration's issue() may overwrite it
+        s0 = s0n; na = nan; my0 = my1; q0 = q1;
+        s0n = s0nn; nan = nann;
     }
 }
 

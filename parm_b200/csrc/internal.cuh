@@ -169,6 +169,8 @@ struct TileState {
     uint32_t nchunks, max_tile;
     uint32_t ncol;             // owned cell columns
     TileChunk *d_chunks;
+    uint32_t *d_s0;            // [chunk_cap + 1] first slot of every chunk, then the end of the last one (the persistent pair
+                               // kernel reads row lengths and row words one chunk ahead of the chunk table)
     uint32_t chunk_cap;
     uint16_t *rows16;          // [npad][kmax], permuted per (team, v) block, padded with the sentinel index
     size_t rows16_cap;

@@ -70,8 +70,10 @@ k_tile_cols(const uint32_t *__restrict__ cell_start, uint32_t nc2, uint32_t ncol
 __global__ void __launch_bounds__(128)
 k_tile_chunks(const uint32_t *__restrict__ cell_start, const uint32_t *__restrict__ cell_id_sorted,
               const uint32_t *__restrict__ col_slot, const uint32_t *__restrict__ col_chunk, uint32_t ncol, uint32_t ch,
-              BoxDev box, GridDev g, StencilDev st, ShardDev sd, double margin, int aligned, TileChunk *chunks, TileInfo *info) {
+              BoxDev box, GridDev g, StencilDev st, ShardDev sd, double margin, int aligned, TileChunk *chunks, uint32_t *s0arr,
+              TileInfo *info) {
     const uint32_t cidx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (cidx == col_chunk[ncol]) s0arr[cidx] = col_slot[ncol]; // end of the last chunk
     if (cidx >= col_chunk[ncol]) return;
     uint32_t lo = 0, hi = ncol; // largest q with col_chunk[q] <= cidx (columns without atoms own no chunk)
     while (hi - lo > 1) {
@@ -88,6 +90,7 @@ k_tile_chunks(const uint32_t *__restrict__ cell_start, const uint32_t *__restric
     const int cx = (int)(q / (uint32_t)nc1), cy = (int)(q % (uint32_t)nc1);
     const int zlo = (int)(cell_id_sorted[a] % (uint32_t)nc2), zhi = (int)(cell_id_sorted[b - 1] % (uint32_t)nc2);
     TileChunk C;
+    s0arr[cidx] = a;
     C.s0 = a;
     C.n = b - a;
     C.pad = 0;
@@ -438,6 +441,8 @@ void parm_tile_invalidate(parm_nlist *nl) {
 void parm_tile_free(parm_nlist *nl) {
     TileState &t = nl->tile;
     if (t.d_chunks) cudaFree(t.d_chunks);
+    if (t.d_s0) cudaFree(t.d_s0);
+    t.d_s0 = 0;
     if (t.rows16) cudaFree(t.rows16);
     if (t.d_col) cudaFree(t.d_col);
     if (t.d_info) cudaFree(t.d_info);
@@ -478,9 +483,12 @@ int parm_tile_plan_enqueue(parm_nlist *nl) {
     const uint32_t maxchunks = nown / (uint32_t)t.ch + ncol + 1;
     if (maxchunks > t.chunk_cap) {
         if (t.d_chunks) cudaFree(t.d_chunks);
+        if (t.d_s0) cudaFree(t.d_s0);
         t.d_chunks = 0;
+        t.d_s0 = 0;
         t.chunk_cap = maxchunks + maxchunks / 4;
         CK(cudaMalloc(&t.d_chunks, (size_t)t.chunk_cap * sizeof(TileChunk)));
+        CK(cudaMalloc(&t.d_s0, ((size_t)t.chunk_cap + 1) * 4));
     }
     t.ncol = ncol;
     CK(cudaMemsetAsync(t.d_info, 0, sizeof(TileInfo), c->stream));
@@ -491,9 +499,9 @@ int parm_tile_plan_enqueue(parm_nlist *nl) {
     // less than 2^-40 (|x| < 4096); larger boxes stage origin-relative positions with the kernel's own threads
     const double lmaxbox = std::max(c->box.L[0], std::max(c->box.L[1], c->box.L[2]));
     t.stage_aligned = t.stage == 1 && lmaxbox < 4096.0 && t.team == 4 && t.v == 8;
-    k_tile_chunks<<<(maxchunks + 127) / 128, 128, 0, c->stream>>>(nl->cell_start, nl->cell_id_sorted, t.d_col, t.d_col + t.col_cap, ncol,
+    k_tile_chunks<<<(maxchunks + 1 + 127) / 128, 128, 0, c->stream>>>(nl->cell_start, nl->cell_id_sorted, t.d_col, t.d_col + t.col_cap, ncol,
                                                                  (uint32_t)t.ch, c->box, nl->g, nl->st, nl->sd, margin,
-                                                                 t.stage_aligned ? 1 : 0, t.d_chunks, t.d_info);
+                                                                 t.stage_aligned ? 1 : 0, t.d_chunks, t.d_s0, t.d_info);
     CK_LAUNCH(c);
     t.planned = true;
     return 0;
