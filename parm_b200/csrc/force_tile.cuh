@@ -331,89 +331,130 @@ __global__ void __launch_bounds__(TILE_NT) k_force_tile(const TileForceArgs A) {
     }
 }
 
-// ---- persistent, double-buffered variant (TEAM 4, V 8, bulk-copy staging) --------------------------------------------
-// ncu on the one-block-per-chunk kernel: a quarter of the warp time is spent waiting for the chunk's tile (the block
+// ---- persistent, double-buffered, warp-specialised variant (forces only, TEAM 4, V 8, bulk-copy staging) ------------
+// ncu on the one-block-per-chunk kernel: a quarter of the warp time goes into waiting for the chunk's tile (the block
 // reads its run table, then issues the copies, then waits for them) and every block pays its own tail. Here 2 blocks of
 // 512 threads stay resident per SM and walk the chunks blockIdx.x, blockIdx.x + gridDim.x, ...; each owns TWO tile
-// buffers: while the 128 teams work on chunk k out of one buffer, the copies of chunk k+1 land in the other (issued by
-// warp 0, whose lanes carry the run table of the next chunk in registers one chunk ahead). Same rows, same summation
-// order: the results are bit-identical to k_force_tile.
+// buffers. Warp 0 is the PRODUCER: it waits until the 15 compute warps have released a buffer (mbarrier `empty`), reads
+// the next chunk's run table, issues its bulk copies (mbarrier `full`) and, for the chunks next to a periodic face,
+// adds the image shifts once the copies have landed (mbarrier `ready`). The 15 COMPUTE warps (120 teams: chunks hold at
+// most TILE_PCH atoms) never meet at a block barrier: each walks the chunks at its own pace, at most one chunk ahead of
+// the slowest, with the row length and first pass of its team's next atom requested one chunk ahead and the first slot
+// of the chunk after that two chunks ahead. Same rows, same summation order: bit-identical to k_force_tile.
 #define TILE_PNT 512
-struct TileMeta { // per buffer, written by warp 0 when it issues the copies
-    uint32_t ntile, na, s0, flags, own, cidx, pad0, pad1;
+#define TILE_PCH 120 // (TILE_PNT / 32 - 1) compute warps x 8 teams
+struct TileMeta { // per buffer, written by the producer before it arms `full`
+    uint32_t ntile, flags, own, pad0;
     uint32_t off[TILE_MAXSEG + 1];
     int8_t sh[TILE_MAXSEG][3];
 };
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
 
-template <int KIND, int MODE>
+template <int KIND>
 __global__ void __launch_bounds__(TILE_PNT, 2) k_force_tile_pers(const TileForceArgs A, const uint32_t nchunks) {
     if (A.abort_flag && *A.abort_flag) return; // speculatively enqueued step whose predecessor asked for a rebuild
-    constexpr int TEAM = 4, V = 8;
+    constexpr int TEAM = 4, V = 8, NCW = TILE_PNT / 32 - 1;
     extern __shared__ __align__(16) double s_xyz[]; // two buffers of 3 * cap doubles
     __shared__ TileMeta s_meta[2];
-    __shared__ __align__(8) unsigned long long s_bar[2];
-    __shared__ double red[MODE != MODE_F ? NPART : 1][TILE_PNT / 32];
+    __shared__ __align__(8) unsigned long long s_full[2], s_empty[2], s_ready[2];
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint32_t bufdoubles = 3 * A.cap;
+    const uint32_t bufdoubles = 3 * A.cap, G = gridDim.x;
     if (threadIdx.x == 0) {
-        mbar_init((uint32_t)__cvta_generic_to_shared(&s_bar[0]), 1);
-        mbar_init((uint32_t)__cvta_generic_to_shared(&s_bar[1]), 1);
+        for (int b = 0; b < 2; b++) {
+            mbar_init((uint32_t)__cvta_generic_to_shared(&s_full[b]), 1);
+            mbar_init((uint32_t)__cvta_generic_to_shared(&s_empty[b]), NCW);
+            mbar_init((uint32_t)__cvta_generic_to_shared(&s_ready[b]), 1);
+        }
     }
     __syncthreads();
-    // warp 0: issue the copies of chunk `c` into buffer b (every reader of that buffer has passed the barrier that ends
-    // the chunk before the previous one)
-    auto issue = [&](uint32_t c, uint32_t b) {
-        const TileChunk *C = A.chunks + c;
-        double2 *sxy = reinterpret_cast<double2 *>(s_xyz + (size_t)b * bufdoubles);
-        double *sz = s_xyz + (size_t)b * bufdoubles + 2 * (size_t)A.cap;
-        const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&s_bar[b]);
-        uint32_t st = 0, o0 = 0, o1 = 0;
-        if (lane < TILE_MAXSEG) {
-            st = C->seg_start[lane];
-            o0 = C->seg_off[lane];
-            o1 = C->seg_off[lane + 1];
+    if (blockIdx.x >= nchunks) return;
+    if (warp == 0) {
+        // ---------------- producer ----------------
+        // run table of the next chunk in registers one chunk ahead (lane t: run t)
+        const TileChunk *C = A.chunks + blockIdx.x;
+        uint32_t st = 0, o0 = 0, o1 = 0, sh = 0;
+        auto load_hdr = [&](const TileChunk *Cx) {
+            st = o0 = o1 = sh = 0;
+            if (lane < TILE_MAXSEG) {
+                st = Cx->seg_start[lane];
+                o0 = Cx->seg_off[lane];
+                o1 = Cx->seg_off[lane + 1];
+                sh = (uint32_t)(uint8_t)Cx->sh[lane][0] | (uint32_t)(uint8_t)Cx->sh[lane][1] << 8 | (uint32_t)(uint8_t)Cx->sh[lane][2] << 16;
+            } else if (lane == 18) {
+                st = Cx->ntile;
+                o0 = Cx->s0;
+                o1 = Cx->flags;
+            }
+        };
+        load_hdr(C);
+        uint32_t k = 0;
+        for (uint32_t c = blockIdx.x; c < nchunks; c += G, k++) {
+            const uint32_t b = k & 1u;
+            double2 *sxy = reinterpret_cast<double2 *>(s_xyz + (size_t)b * bufdoubles);
+            double *sz = s_xyz + (size_t)b * bufdoubles + 2 * (size_t)A.cap;
+            const uint32_t full = (uint32_t)__cvta_generic_to_shared(&s_full[b]);
+            const uint32_t cst = st, co0 = o0, co1 = o1, csh = sh;
+            if (c + G < nchunks) load_hdr(A.chunks + c + G); // consumed in the next iteration
+            if (k >= 2) mbar_wait((uint32_t)__cvta_generic_to_shared(&s_empty[b]), ((k >> 1) - 1u) & 1u); // chunk k - 2 released it
+            const uint32_t ntile = __shfl_sync(0xffffffffu, cst, 18), s0 = __shfl_sync(0xffffffffu, co0, 18);
+            const uint32_t flags = __shfl_sync(0xffffffffu, co1, 18);
+            TileMeta &M = s_meta[b];
+            if (lane < TILE_MAXSEG) {
+                M.off[lane] = co0;
+                M.sh[lane][0] = (int8_t)(csh & 0xffu);
+                M.sh[lane][1] = (int8_t)((csh >> 8) & 0xffu);
+                M.sh[lane][2] = (int8_t)((csh >> 16) & 0xffu);
+            }
+            // the chunk's own atoms are consecutive entries of the centre column's run (piece 0 or 1 of stencil column 4)
+            const uint32_t st8 = __shfl_sync(0xffffffffu, cst, 8), st9 = __shfl_sync(0xffffffffu, cst, 9);
+            const uint32_t of8 = __shfl_sync(0xffffffffu, co0, 8), of9 = __shfl_sync(0xffffffffu, co0, 9);
+            if (lane == 0) {
+                M.off[TILE_MAXSEG] = ntile;
+                M.ntile = ntile;
+                M.flags = flags;
+                const uint32_t d8 = s0 - st8;
+                M.own = (s0 >= st8 && d8 < of9 - of8) ? of8 + d8 : of9 + (s0 - st9);
+            }
+            // the sentinel every row is padded with (index ntile) and the 16 class sentinels of bank-ordered rows
+            const uint32_t send = ((ntile + 1u + 15u) & ~15u) + 16u;
+            for (uint32_t t = ntile + lane; t < send; t += 32) {
+                sxy[t] = make_double2(1e100, 1e100);
+                sz[t] = 1e100;
+            }
+            __syncwarp(); // the lanes' writes are ordered before lane 0's (releasing) arrive
+            if (lane == 0) mbar_arrive_expect_tx(full, ntile * 24u);
+            __syncwarp();
+            if (lane < TILE_MAXSEG && co1 > co0) { // even start, even length: both copies are 16-byte aligned at both ends
+                bulk_g2s((uint32_t)__cvta_generic_to_shared(sxy + co0), A.prel_xy + cst, (co1 - co0) * 16u, full);
+                bulk_g2s((uint32_t)__cvta_generic_to_shared(sz + co0), A.prel_z + cst, (co1 - co0) * 8u, full);
+            }
+            if (flags & 2u) { // runs reached across a periodic face: add their image shift once they have landed
+                mbar_wait(full, (k >> 1) & 1u);
+                for (uint32_t seg = 0; seg < TILE_MAXSEG; seg++) {
+                    const uint32_t sg = __shfl_sync(0xffffffffu, csh, seg);
+                    if (!sg) continue;
+                    const uint32_t t0 = __shfl_sync(0xffffffffu, co0, seg), t1 = __shfl_sync(0xffffffffu, co1, seg);
+                    const double ax = (int8_t)(sg & 0xffu) * A.box.L[0], ay = (int8_t)((sg >> 8) & 0xffu) * A.box.L[1];
+                    const double az = (int8_t)((sg >> 16) & 0xffu) * A.box.L[2];
+                    for (uint32_t t = t0 + lane; t < t1; t += 32) {
+                        double2 p = sxy[t];
+                        p.x += ax;
+                        p.y += ay;
+                        sxy[t] = p;
+                        sz[t] += az;
+                    }
+                }
+                __syncwarp();
+            }
+            // `ready` completes one phase per chunk like `full` (the compute warps only look at it for shifted chunks)
+            if (lane == 0) mbar_arrive((uint32_t)__cvta_generic_to_shared(&s_ready[b]));
         }
-        const uint32_t ntile = C->ntile, s0 = C->s0;
-        TileMeta &M = s_meta[b];
-        if (lane < TILE_MAXSEG) {
-            M.off[lane] = o0;
-            M.sh[lane][0] = C->sh[lane][0];
-            M.sh[lane][1] = C->sh[lane][1];
-            M.sh[lane][2] = C->sh[lane][2];
-        }
-        // the chunk's own atoms are consecutive entries of the centre column's run (piece 0 or 1 of stencil column 4)
-        const uint32_t st8 = __shfl_sync(0xffffffffu, st, 8), st9 = __shfl_sync(0xffffffffu, st, 9);
-        const uint32_t of8 = __shfl_sync(0xffffffffu, o0, 8), of9 = __shfl_sync(0xffffffffu, o0, 9);
-        if (lane == 0) {
-            M.off[TILE_MAXSEG] = ntile;
-            M.ntile = ntile;
-            M.na = C->n;
-            M.s0 = s0;
-            M.flags = C->flags;
-            M.cidx = c;
-            const uint32_t d8 = s0 - st8;
-            M.own = (s0 >= st8 && d8 < of9 - of8) ? of8 + d8 : of9 + (s0 - st9);
-            mbar_arrive_expect_tx(bar, ntile * 24u);
-        }
-        // the sentinel every row is padded with (index ntile) and the 16 class sentinels of bank-ordered rows
-        const uint32_t send = ((ntile + 1u + 15u) & ~15u) + 16u;
-        for (uint32_t t = ntile + lane; t < send; t += 32) {
-            sxy[t] = make_double2(1e100, 1e100);
-            sz[t] = 1e100;
-        }
-        __syncwarp();
-        if (lane < TILE_MAXSEG && o1 > o0) { // even start, even length: both copies are 16-byte aligned at both ends
-            bulk_g2s((uint32_t)__cvta_generic_to_shared(sxy + o0), A.prel_xy + st, (o1 - o0) * 16u, bar);
-            bulk_g2s((uint32_t)__cvta_generic_to_shared(sz + o0), A.prel_z + st, (o1 - o0) * 8u, bar);
-        }
-    };
-    uint32_t c = blockIdx.x;
-    if (c >= nchunks) return;
-    if (warp == 0) issue(c, 0);
-    // Three chunks are in flight per thread: the one being computed (row length and first pass of the team's atom in
-    // registers), the next one (its first slot known: row length and first pass requested now) and the one after
-    // (first slot requested now) -- no dependent global load is ever waited for at the start of a chunk.
-    const uint32_t G = gridDim.x, team = threadIdx.x / TEAM, tl = threadIdx.x % TEAM;
+        return;
+    }
+    // ---------------- compute warps ----------------
+    const uint32_t team = (threadIdx.x - 32) / TEAM, tl = threadIdx.x % TEAM;
     auto rows_of = [&](uint32_t s0x, uint32_t nax, uint32_t &my, RowWords<V> &q) {
         my = 0;
 #pragma unroll
@@ -424,64 +465,89 @@ __global__ void __launch_bounds__(TILE_PNT, 2) k_force_tile_pers(const TileForce
             q = load_row_words<V>(A.rows16 + (size_t)s * A.kmax + tl * V);
         }
     };
+    uint32_t c = blockIdx.x;
     uint32_t s0 = A.chunk_s0[c], na = A.chunk_s0[c + 1] - s0;
     uint32_t s0n = 0, nan = 0;
     if (c + G < nchunks) { s0n = A.chunk_s0[c + G]; nan = A.chunk_s0[c + G + 1] - s0n; }
     uint32_t my0;
     RowWords<V> q0;
     rows_of(s0, na, my0, q0);
-    __syncthreads(); // s_meta[0] is visible to every warp
+    const double c12 = 12.0 * A.P1.eps;
+    const long long rc2_bits = __double_as_longlong(A.P1.rc2);
     for (uint32_t k = 0; c < nchunks; k++, c += G) {
-        const uint32_t b = k & 1u;
+        const uint32_t b = k & 1u, par = (k >> 1) & 1u;
         const uint32_t cn = c + G;
-        if (warp == 0 && cn < nchunks) issue(cn, b ^ 1u);
         uint32_t my1;
         RowWords<V> q1;
         rows_of(s0n, nan, my1, q1); // next chunk: consumed at the bottom of this iteration
         uint32_t s0nn = 0, nann = 0;
         if (cn + G < nchunks) { s0nn = A.chunk_s0[cn + G]; nann = A.chunk_s0[cn + G + 1] - s0nn; }
-        double2 *sxy = reinterpret_cast<double2 *>(s_xyz + (size_t)b * bufdoubles);
-        double *sz = s_xyz + (size_t)b * bufdoubles + 2 * (size_t)A.cap;
-        mbar_wait((uint32_t)__cvta_generic_to_shared(&s_bar[b]), (k >> 1) & 1u);
-        const TileMeta &M = s_meta[b]; // written before the barrier that ended the previous chunk (or the one after init)
+        const double2 *sxy = reinterpret_cast<const double2 *>(s_xyz + (size_t)b * bufdoubles);
+        const double *sz = s_xyz + (size_t)b * bufdoubles + 2 * (size_t)A.cap;
+        mbar_wait((uint32_t)__cvta_generic_to_shared(&s_full[b]), par);
+        const TileMeta &M = s_meta[b];
         const uint32_t cflags = M.flags;
-        if (cflags & 2u) { // runs reached across a periodic face: add their image shift
-            for (uint32_t seg = 0; seg < TILE_MAXSEG; seg++) {
-                const int sx = M.sh[seg][0], sy = M.sh[seg][1], szz = M.sh[seg][2];
-                if (!(sx | sy | szz)) continue;
-                const double ax = sx * A.box.L[0], ay = sy * A.box.L[1], az = szz * A.box.L[2];
-                for (uint32_t t = M.off[seg] + threadIdx.x; t < M.off[seg + 1]; t += TILE_PNT) {
-                    double2 p = sxy[t];
-                    p.x += ax;
-                    p.y += ay;
-                    sxy[t] = p;
-                    sz[t] += az;
+        if (cflags & 2u) mbar_wait((uint32_t)__cvta_generic_to_shared(&s_ready[b]), par);
+        // one atom per team: the row walk of tile_rows without its next-atom bookkeeping
+        const bool valid = team < na;
+        const uint32_t s = s0 + (valid ? team : 0);
+        const uint32_t ti = M.own + (valid ? team : 0);
+        const double2 pixy = sxy[ti];
+        const double xi = pixy.x, yi = pixy.y, zi = sz[ti];
+        const uint16_t *row = A.rows16 + (size_t)s * A.kmax + tl * V;
+        double fx = 0, fy = 0, fz = 0;
+        RowWords<V> q = q0;
+        const bool mi = (cflags & 1u) != 0;
+        for (uint32_t k0 = 0; k0 < my0; k0 += TEAM * V) {
+            RowWords<V> qn = q;
+            if (k0 + TEAM * V < my0) qn = load_row_words<V>(row + k0 + TEAM * V);
+#pragma unroll
+            for (int e = 0; e < V; e++) {
+                const uint32_t idx = (e & 1) ? (q.w[e >> 1] >> 16) : (q.w[e >> 1] & 0xffffu);
+                const double2 pxy = sxy[idx];
+                double dx = xi - pxy.x, dy = yi - pxy.y, dz = zi - sz[idx];
+                if (mi) { // (uniform per chunk) tile wider than half the box: minimum image per pair as well
+                    dx = min_image_fast(dx, A.box.L[0], A.box.invL[0]);
+                    dy = min_image_fast(dy, A.box.L[1], A.box.invL[1]);
+                    dz = min_image_fast(dz, A.box.L[2], A.box.invL[2]);
                 }
+                const double dsq = dx * dx + (dy * dy + dz * dz);
+                const double w = rcp_pos(dsq);
+                const double s2 = A.P1.sig2 * w;
+                const double ir6 = (s2 * s2) * s2;
+                const double bb = ir6 * w;
+                const double t = fma(bb, ir6, -bb);
+                const bool in = __double_as_longlong(dsq) <= rc2_bits; // sentinel pads: dsq ~ 1e200, beyond any cutoff
+                const double scal = in ? t : 0.0;
+                fx = fma(dx, scal, fx);
+                fy = fma(dy, scal, fy);
+                fz = fma(dz, scal, fz);
             }
-            __syncthreads();
+            q = qn;
         }
-        double acc[NPART];
-        if (MODE != MODE_F)
+        fx *= c12;
+        fy *= c12;
+        fz *= c12;
 #pragma unroll
-            for (int q = 0; q < NPART; q++) acc[q] = 0.0;
-        if (cflags & 1u) tile_rows<KIND, MODE, TEAM, V, true, TILE_PNT>(A, na, s0, M.own, sxy, sz, acc, my0, q0);
-        else tile_rows<KIND, MODE, TEAM, V, false, TILE_PNT>(A, na, s0, M.own, sxy, sz, acc, my0, q0);
-        if (MODE != MODE_F) {
-#pragma unroll
-            for (int q = 0; q < NPART; q++) {
-                double x = acc[q];
-#pragma unroll
-                for (int o = 16; o; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
-                if (lane == 0) red[q][warp] = x;
-            }
-            __syncthreads();
-            if (threadIdx.x < NPART) {
-                double x = 0;
-                for (int ww = 0; ww < TILE_PNT / 32; ww++) x += red[threadIdx.x][ww];
-                A.partials[(size_t)c * NPART + threadIdx.x] = x;
+        for (int o = TEAM / 2; o; o >>= 1) {
+            fx += __shfl_xor_sync(0xffffffffu, fx, o);
+            fy += __shfl_xor_sync(0xffffffffu, fy, o);
+            fz += __shfl_xor_sync(0xffffffffu, fz, o);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive((uint32_t)__cvta_generic_to_shared(&s_empty[b])); // this warp is done with buffer b
+        if (valid && tl == 0) {
+            double *f = A.f;
+            if (A.accumulate) {
+                f[s] += fx;
+                f[A.npad + s] += fy;
+                f[2 * (size_t)A.npad + s] += fz;
+            } else {
+                f[s] = fx;
+                f[A.npad + s] = fy;
+                f[2 * (size_t)A.npad + s] = fz;
             }
         }
-        __syncthreads(); // everyone is done with buffer b (and red[]): the next iteration's issue() may overwrite it
         s0 = s0n; na = nan; my0 = my1; q0 = q1;
         s0n = s0nn; nan = nann;
     }
@@ -505,15 +571,10 @@ cudaError_t parm_launch_force_tile_kind(int team, int v, int mode, unsigned nchu
     if (team == 8) return launch_tile_mode<KIND, 8, 4, 0>(mode, nchunks, smem, st, A);
     if (team == 2) return launch_tile_mode<KIND, 2, 8, 0>(mode, nchunks, smem, st, A);
     if (v == 4) return launch_tile_mode<KIND, 4, 4, 0>(mode, nchunks, smem, st, A);
-    if (A.prel_xy && A.pers_blocks) { // persistent double-buffered kernel: 2 blocks of 512 threads per SM, two tile buffers each
+    if (A.prel_xy && A.pers_blocks && mode == MODE_F) { // persistent kernel: 2 blocks of 512 threads per SM, two tile buffers each
         const size_t smem2 = 2 * smem;
-        if (mode == MODE_F) {
-            cudaFuncSetAttribute(k_force_tile_pers<KIND, MODE_F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
-            k_force_tile_pers<KIND, MODE_F><<<std::min(nchunks, A.pers_blocks), TILE_PNT, smem2, st>>>(A, nchunks);
-        } else {
-            cudaFuncSetAttribute(k_force_tile_pers<KIND, MODE_FALL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
-            k_force_tile_pers<KIND, MODE_FALL><<<std::min(nchunks, A.pers_blocks), TILE_PNT, smem2, st>>>(A, nchunks);
-        }
+        cudaFuncSetAttribute(k_force_tile_pers<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
+        k_force_tile_pers<KIND><<<std::min(nchunks, A.pers_blocks), TILE_PNT, smem2, st>>>(A, nchunks);
         return cudaGetLastError();
     }
     if (A.prel_xy) return launch_tile_mode<KIND, 4, 8, 1>(mode, nchunks, smem, st, A);

@@ -418,7 +418,7 @@ static void tile_config(parm_nlist *nl) {
     e = getenv("PARM_B200_TILE_MIN_NEIGHBORS");
     t.min_nbrs = e ? atoi(e) : 32;
     e = getenv("PARM_B200_TILE_CH");
-    t.ch = e ? atoi(e) : 128;
+    t.ch = e ? atoi(e) : 120; // 15 compute warps x 8 teams of the persistent pair kernel (force_tile.cuh: TILE_PCH)
     if (t.ch < 32) t.ch = 32;
     if (t.ch > 1024) t.ch = 1024;
     e = getenv("PARM_B200_TILE_TEAM");
