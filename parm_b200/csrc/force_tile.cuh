@@ -480,8 +480,8 @@ __global__ void __launch_bounds__(TILE_PNT, 2) k_force_tile_pers(const TileForce
         uint32_t my1;
         RowWords<V> q1;
         rows_of(s0n, nan, my1, q1); // next chunk: consumed at the bottom of this iteration
-        uint32_t s0nn = 0, nann = 0;
-        if (cn + G < nchunks) { s0nn = A.chunk_s0[cn + G]; nann = A.chunk_s0[cn + G + 1] - s0nn; }
+        uint32_t s0nn = 0, ennn = 0; // first slot and end of the chunk after the next: raw loads, subtracted at the bottom
+        if (cn + G < nchunks) { s0nn = A.chunk_s0[cn + G]; ennn = A.chunk_s0[cn + G + 1]; }
         const double2 *sxy = reinterpret_cast<const double2 *>(s_xyz + (size_t)b * bufdoubles);
         const double *sz = s_xyz + (size_t)b * bufdoubles + 2 * (size_t)A.cap;
         mbar_wait((uint32_t)__cvta_generic_to_shared(&s_full[b]), par);
@@ -549,7 +549,7 @@ __global__ void __launch_bounds__(TILE_PNT, 2) k_force_tile_pers(const TileForce
             }
         }
         s0 = s0n; na = nan; my0 = my1; q0 = q1;
-        s0n = s0nn; nan = nann;
+        s0n = s0nn; nan = ennn - s0nn;
     }
 }
 

@@ -293,17 +293,20 @@ k_tile_bank_order(const TileChunk *__restrict__ chunks, const uint32_t *__restri
     }
 }
 
-// ---- mask-mode lists (experimental): rows16 straight from the build's pass masks --------------------------------
-// Same thread layout as k_tile_localize<8> (TEAM = 4 lanes per atom, V = 8). Lane tl of a team takes candidate blocks
-// tl, tl + 4, ... of the atom's warp group; a team-wide exclusive scan of the mask popcounts gives every block its
-// position in the row (the append order of the classic build), every set bit becomes a tile index through the same
-// 9-entry column table, and the row is assembled in shared memory in the permuted lane-vector layout of the pair
-// kernel before it leaves as 16-byte stores. Rows are padded to whole passes with the sentinel index ntile.
+// ---- mask-mode lists: rows16 straight from the build's pass masks -------------------------------------------------
+// Same thread layout as k_tile_localize<8> (TEAM = 4 lanes per atom, V = 8). Lane tl of a team takes a CONTIGUOUS quarter
+// of the candidate blocks of the atom's warp group: one pass adds up the popcounts of its masks, one exclusive scan over
+// the four lanes gives the lane its first row position (rows keep the block order of the classic build), a second pass
+// turns every set bit into a tile index through the 9-entry column table. A lane never waits for its team mates between
+// blocks, so a warp runs as long as its busiest lane (~40 entries), not as long as the sum of the per-round maxima.
+// The row is assembled in shared memory in the permuted lane-vector layout of the pair kernel (row stride padded by 16
+// bytes: the eight teams of a warp start in different banks) and leaves as 16-byte stores, padded to whole passes with
+// the sentinel index ntile.
 __global__ void __launch_bounds__(TILE_NT)
 k_tile_localize_masks(const TileChunk *__restrict__ chunks, MaskOut mo, const uint32_t *__restrict__ cell_id_sorted, uint32_t nc2,
                       uint32_t gpc, uint32_t zg, const uint32_t *__restrict__ cnt, uint32_t kmax, uint16_t *__restrict__ rows16,
                       TileInfo *info) {
-    extern __shared__ __align__(16) uint16_t s_rows[]; // [TILE_NT / 4][kmax]
+    extern __shared__ __align__(16) uint16_t s_rows[]; // [TILE_NT / 4][kmax + 8]
     __shared__ uint4 s_tab[9];
     __shared__ uint32_t s_ntile;
     const TileChunk *C = chunks + blockIdx.x;
@@ -315,7 +318,8 @@ k_tile_localize_masks(const TileChunk *__restrict__ chunks, MaskOut mo, const ui
     __syncthreads();
     const uint32_t ntile = s_ntile, s0 = C->s0, na = C->n;
     const uint32_t tl = threadIdx.x & 3u, team = threadIdx.x >> 2;
-    uint16_t *buf = s_rows + (size_t)team * kmax;
+    const uint32_t stride = kmax + 8u;
+    uint16_t *buf = s_rows + (size_t)team * stride;
     bool lost = false;
     for (uint32_t a0 = 0; a0 < na; a0 += TILE_NT / 4) { // every lane of a warp runs the same trips (team shuffles below)
         const uint32_t a = a0 + team;
@@ -323,37 +327,40 @@ k_tile_localize_masks(const TileChunk *__restrict__ chunks, MaskOut mo, const ui
         const uint32_t s = s0 + (valid ? a : 0);
         const uint32_t my = valid ? min(cnt[s], kmax) : 0;
         const uint32_t mypad = (my + 31u) & ~31u;
-        for (uint32_t k = tl; k < mypad; k += 4) buf[k] = (uint16_t)ntile; // sentinel everywhere, entries overwrite it
-        __syncwarp();
+        for (uint32_t k = tl * 8u; k < mypad; k += 32u) // sentinel everywhere, entries overwrite it
+            *reinterpret_cast<uint4 *>(buf + k) = make_uint4(ntile * 0x10001u, ntile * 0x10001u, ntile * 0x10001u, ntile * 0x10001u);
         uint32_t nb = 0, grp = 0;
         if (my) {
             const uint32_t cid = cell_id_sorted[s];
             grp = (cid / nc2) * gpc + (cid % nc2) / zg;
             nb = min(mo.grp_nb[grp], mo.mb_cap);
         }
-        // teams of a warp may walk different block counts: run to the warp-wide maximum so that the shuffles stay converged
-        uint32_t nbw = nb;
-#pragma unroll
-        for (int o = 16; o >= 4; o >>= 1) nbw = max(nbw, __shfl_xor_sync(0xffffffffu, nbw, o));
-        uint32_t pos0 = 0;
-        for (uint32_t r = 0; r < nbw; r += 4) {
-            const uint32_t b = r + tl;
-            uint32_t m = b < nb ? mo.masks[(size_t)b * mo.npad + s] : 0u;
-            const uint32_t base = b < nb ? mo.blk_base[(size_t)grp * mo.mb_cap + b] : 0u;
-            const uint32_t p = __popc(m);
-            uint32_t incl = p; // inclusive scan over the 4 lanes of the team
-            uint32_t y = __shfl_up_sync(0xffffffffu, incl, 1, 4);
-            if (tl >= 1) incl += y;
-            y = __shfl_up_sync(0xffffffffu, incl, 2, 4);
-            if (tl >= 2) incl += y;
-            const uint32_t tot = __shfl_sync(0xffffffffu, incl, 3, 4);
-            uint32_t k = pos0 + incl - p;
+        const uint32_t nbq = (nb + 3u) >> 2, b0 = tl * nbq, b1 = min(b0 + nbq, nb);
+        const uint32_t *mp = mo.masks + (size_t)b0 * mo.npad + s;
+        uint32_t tot = 0;
+        for (uint32_t b = b0; b < b1; b++, mp += mo.npad) tot += __popc(__ldg(mp));
+        uint32_t incl = tot; // inclusive scan over the 4 lanes of the team
+        uint32_t y = __shfl_up_sync(0xffffffffu, incl, 1, 4);
+        if (tl >= 1) incl += y;
+        y = __shfl_up_sync(0xffffffffu, incl, 2, 4);
+        if (tl >= 2) incl += y;
+        uint32_t k = incl - tot;
+        __syncwarp(); // the sentinel fill of the whole row is complete
+        mp = mo.masks + (size_t)b0 * mo.npad + s;
+        const uint32_t *bp = mo.blk_base + (size_t)grp * mo.mb_cap + b0;
+        for (uint32_t b = b0; b < b1; b++, mp += mo.npad, bp++) {
+            uint32_t m = __ldg(mp);
+            if (!m) continue;
+            const uint32_t base = __ldg(bp);
             const uint4 t = s_tab[min(base >> PARM_NBR_SLOT_BITS, 8u)];
             const uint32_t jb = base & PARM_NBR_SLOT_MASK;
+            // candidate slot jb + bit -> tile index: both runs of the column in one unsigned comparison each
+            const uint32_t l0 = jb - t.x, n0 = t.w - t.y;
             while (m) {
-                const uint32_t j = jb + (uint32_t)(__ffs(m) - 1);
-                m &= m - 1;
-                const uint32_t l = j - t.x < t.w - t.y ? t.y + (j - t.x) : t.w + (j - t.z);
+                const uint32_t bit = (uint32_t)__ffs(m) - 1u;
+                m &= m - 1u;
+                const uint32_t r = l0 + bit;
+                const uint32_t l = r < n0 ? t.y + r : t.w + (jb + bit - t.z);
                 if (l >= ntile) lost = true; // (not expected: the entry is in neither run of its column)
                 if (k < my) {
                     // entry k of the row is read by lane (k & 3) of the team at step (k & 31) >> 2 of pass k / 32
@@ -362,7 +369,6 @@ k_tile_localize_masks(const TileChunk *__restrict__ chunks, MaskOut mo, const ui
                 }
                 k++;
             }
-            pos0 += tot;
         }
         __syncwarp();
         if (valid) {
@@ -589,7 +595,7 @@ int parm_tile_localize_masks(parm_nlist *nl) {
     if (t.h_info->bad || !t.nchunks || t.max_tile + 1 > TILE_MAX_ATOMS) return 0;
     if (nl->total_full < (uint64_t)t.min_nbrs * nown) return 0;
     if (t.team != 4 || t.v != 8) return 0;
-    const size_t smem = (size_t)(TILE_NT / 4) * nl->kmax * sizeof(uint16_t);
+    const size_t smem = (size_t)(TILE_NT / 4) * (nl->kmax + 8) * sizeof(uint16_t);
     if (smem > 160 * 1024) return 0;
     const size_t need = (size_t)c->npad * nl->kmax;
     if (need > t.rows16_cap) {
