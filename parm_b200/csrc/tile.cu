@@ -381,6 +381,108 @@ k_tile_localize_masks(const TileChunk *__restrict__ chunks, MaskOut mo, const ui
     if (lost) atomicOr(&info->bad, 2u);
 }
 
+// Fast path of the above for groups of at most 4 * MAXQ candidate blocks (nbmax of the build): the lane keeps its masks
+// in registers and walks all their set bits in ONE flat loop, so the lanes of a warp only re-converge at the end of the
+// row: the warp runs max-over-lanes(entries + blocks) iterations instead of the sum of the per-block maxima.
+template <int MAXQ>
+__global__ void __launch_bounds__(TILE_NT)
+k_tile_localize_masks_flat(const TileChunk *__restrict__ chunks, MaskOut mo, const uint32_t *__restrict__ cell_id_sorted, uint32_t nc2,
+                           uint32_t gpc, uint32_t zg, const uint32_t *__restrict__ cnt, uint32_t kmax, uint16_t *__restrict__ rows16,
+                           TileInfo *info) {
+    extern __shared__ __align__(16) uint16_t s_rows[]; // [TILE_NT / 4][kmax + 8]
+    __shared__ uint4 s_tab[9];
+    __shared__ uint32_t s_ntile;
+    __shared__ uint32_t s_mk[MAXQ * TILE_NT], s_bs[MAXQ * TILE_NT];
+    const TileChunk *C = chunks + blockIdx.x;
+    if (threadIdx.x < 9) {
+        const int kc = 2 * threadIdx.x;
+        s_tab[threadIdx.x] = make_uint4(C->seg_start[kc], C->seg_off[kc], C->seg_start[kc + 1], C->seg_off[kc + 1]);
+    }
+    if (threadIdx.x == 0) s_ntile = C->ntile;
+    __syncthreads();
+    const uint32_t ntile = s_ntile, s0 = C->s0, na = C->n;
+    const uint32_t tl = threadIdx.x & 3u, team = threadIdx.x >> 2;
+    const uint32_t stride = kmax + 8u;
+    uint16_t *buf = s_rows + (size_t)team * stride;
+    uint32_t lost = 0;
+    for (uint32_t a0 = 0; a0 < na; a0 += TILE_NT / 4) { // every lane of a warp runs the same trips (team shuffles below)
+        const uint32_t a = a0 + team;
+        const bool valid = a < na;
+        const uint32_t s = s0 + (valid ? a : 0);
+        const uint32_t my = valid ? min(cnt[s], kmax) : 0;
+        const uint32_t mypad = (my + 31u) & ~31u;
+        const uint32_t sent = ntile * 0x10001u;
+        for (uint32_t k = tl * 8u; k < mypad; k += 32u) // sentinel everywhere, entries overwrite it
+            *reinterpret_cast<uint4 *>(buf + k) = make_uint4(sent, sent, sent, sent);
+        uint32_t nb = 0, grp = 0;
+        if (my) {
+            const uint32_t cid = cell_id_sorted[s];
+            grp = (cid / nc2) * gpc + (cid % nc2) / zg;
+            nb = min(mo.grp_nb[grp], mo.mb_cap);
+        }
+        const uint32_t nbq = (nb + 3u) >> 2, b0 = tl * nbq, b1 = min(b0 + nbq, nb);
+        // the lane's non-empty masks and their block bases, compacted into its private column of shared memory
+        uint32_t tot = 0, nq = 0;
+        {
+            uint32_t mk[MAXQ], bs[MAXQ];
+#pragma unroll
+            for (int q = 0; q < MAXQ; q++) { // all loads in flight before the first use
+                const uint32_t b = b0 + (uint32_t)q;
+                mk[q] = b < b1 ? __ldg(mo.masks + (size_t)b * mo.npad + s) : 0u;
+                bs[q] = b < b1 ? __ldg(mo.blk_base + (size_t)grp * mo.mb_cap + b) : 0u;
+            }
+#pragma unroll
+            for (int q = 0; q < MAXQ; q++)
+                if (mk[q]) {
+                    s_mk[nq * TILE_NT + threadIdx.x] = mk[q];
+                    s_bs[nq * TILE_NT + threadIdx.x] = bs[q];
+                    nq++;
+                    tot += __popc(mk[q]);
+                }
+        }
+        uint32_t incl = tot; // inclusive scan over the 4 lanes of the team
+        uint32_t y = __shfl_up_sync(0xffffffffu, incl, 1, 4);
+        if (tl >= 1) incl += y;
+        y = __shfl_up_sync(0xffffffffu, incl, 2, 4);
+        if (tl >= 2) incl += y;
+        uint32_t k = incl - tot;
+        __syncwarp(); // the sentinel fill of the whole row is complete
+        // flat walk: (m, ty, tw, l0, n0, jz) describe the current block; an empty m pulls the next non-empty mask
+        uint32_t m = 0, ty = 0, tw = 0, l0 = 0, n0 = 0, jz = 0;
+        uint32_t q = 0;
+        for (;;) {
+            if (!m) {
+                if (q >= nq) break;
+                m = s_mk[q * TILE_NT + threadIdx.x];
+                const uint32_t base = s_bs[q * TILE_NT + threadIdx.x];
+                q++;
+                const uint4 t = s_tab[min(base >> PARM_NBR_SLOT_BITS, 8u)];
+                const uint32_t jb = base & PARM_NBR_SLOT_MASK;
+                ty = t.y; tw = t.w; l0 = jb - t.x; n0 = t.w - t.y; jz = jb - t.z;
+            }
+            const uint32_t bit = (uint32_t)__ffs(m) - 1u;
+            m &= m - 1u;
+            const uint32_t r = l0 + bit;
+            const uint32_t l = r < n0 ? ty + r : tw + (jz + bit);
+            lost |= l >= ntile ? 1u : 0u; // (not expected: the entry is in neither run of its column)
+            if (k < my) {
+                // entry k of the row is read by lane (k & 3) of the team at step (k & 31) >> 2 of pass k / 32
+                const uint32_t r32 = k & 31u;
+                buf[(k & ~31u) + (r32 & 3u) * 8u + (r32 >> 2)] = (uint16_t)min(l, ntile);
+            }
+            k++;
+        }
+        __syncwarp();
+        if (valid) {
+            uint16_t *out = rows16 + (size_t)s * kmax;
+            for (uint32_t k0 = 0; k0 < mypad; k0 += 32)
+                *reinterpret_cast<uint4 *>(out + k0 + tl * 8) = *reinterpret_cast<const uint4 *>(buf + k0 + tl * 8);
+        }
+        __syncwarp();
+    }
+    if (lost) atomicOr(&info->bad, 2u);
+}
+
 // ---- per step: positions in the image every atom had at the last rebuild (bulk-copy staging) ----------------------
 // prel = x - img * L is what the pair kernel's cp.async.bulk copies bring into shared memory unchanged: OriginBox::diff
 // (box.hpp:103) is resolved once per atom and step here instead of once per staged copy (17.7 per atom) there.
@@ -605,9 +707,15 @@ int parm_tile_localize_masks(parm_nlist *nl) {
         CK(cudaMalloc(&t.rows16, need * 2));
         t.rows16_cap = need;
     }
-    if (smem > 48 * 1024) CK(cudaFuncSetAttribute(k_tile_localize_masks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_tile_localize_masks<<<t.nchunks, TILE_NT, smem, c->stream>>>(t.d_chunks, nl->mask.out, nl->cell_id_sorted, (uint32_t)nl->g.nc[2],
-                                                                  nl->mask.gpc, (uint32_t)nl->mask.zg, nl->cnt, nl->kmax, t.rows16, t.d_info);
+#define LMARGS t.d_chunks, nl->mask.out, nl->cell_id_sorted, (uint32_t)nl->g.nc[2], nl->mask.gpc, (uint32_t)nl->mask.zg, nl->cnt, nl->kmax, t.rows16, t.d_info
+    if (nl->h_flags->nbmax <= 48) {
+        if (smem > 48 * 1024) CK(cudaFuncSetAttribute(k_tile_localize_masks_flat<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_tile_localize_masks_flat<12><<<t.nchunks, TILE_NT, smem, c->stream>>>(LMARGS);
+    } else {
+        if (smem > 48 * 1024) CK(cudaFuncSetAttribute(k_tile_localize_masks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_tile_localize_masks<<<t.nchunks, TILE_NT, smem, c->stream>>>(LMARGS);
+    }
+#undef LMARGS
     CK_LAUNCH(c);
     if (int rc = tile_bank_order(nl)) return rc;
     static int check = -1;
