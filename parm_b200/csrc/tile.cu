@@ -93,7 +93,7 @@ k_tile_chunks(const uint32_t *__restrict__ cell_start, const uint32_t *__restric
     s0arr[cidx] = a;
     C.s0 = a;
     C.n = b - a;
-    C.pad = 0;
+    C.pad = q; // owned column index (the mask-mode localize pass derives the atoms' warp groups from it)
     C.pad2[0] = C.pad2[1] = 0;
     // z pieces (run axis): the chunk's cells +- one, split where the range wraps; the whole column once when
     // the range would overlap itself
@@ -381,9 +381,12 @@ k_tile_localize_masks(const TileChunk *__restrict__ chunks, MaskOut mo, const ui
     if (lost) atomicOr(&info->bad, 2u);
 }
 
-// Fast path of the above for groups of at most 4 * MAXQ candidate blocks (nbmax of the build): the lane keeps its masks
-// in registers and walks all their set bits in ONE flat loop, so the lanes of a warp only re-converge at the end of the
-// row: the warp runs max-over-lanes(entries + blocks) iterations instead of the sum of the per-block maxima.
+// Fast path of the above for groups of at most 4 * MAXQ candidate blocks (nbmax of the build): the lane takes blocks tl,
+// tl + 4, ... (the populous blocks of the centre columns are dealt round the team), compacts its non-empty masks into
+// shared memory and walks all their set bits in ONE flat loop, so the lanes of a warp only re-converge at the end of the
+// row: the warp runs max-over-lanes(entries) iterations instead of the sum of the per-block maxima. Row order: lane 0's
+// blocks in block order, then lane 1's, ... -- another fixed order of the same set than the classic build's (the pair
+// kernel's sums are deterministic either way; they differ from the classic order in the last bits only).
 template <int MAXQ>
 __global__ void __launch_bounds__(TILE_NT)
 k_tile_localize_masks_flat(const TileChunk *__restrict__ chunks, MaskOut mo, const uint32_t *__restrict__ cell_id_sorted, uint32_t nc2,
@@ -400,7 +403,7 @@ k_tile_localize_masks_flat(const TileChunk *__restrict__ chunks, MaskOut mo, con
     }
     if (threadIdx.x == 0) s_ntile = C->ntile;
     __syncthreads();
-    const uint32_t ntile = s_ntile, s0 = C->s0, na = C->n;
+    const uint32_t ntile = s_ntile, s0 = C->s0, na = C->n, col = C->pad, colcell0 = C->pad * nc2;
     const uint32_t tl = threadIdx.x & 3u, team = threadIdx.x >> 2;
     const uint32_t stride = kmax + 8u;
     uint16_t *buf = s_rows + (size_t)team * stride;
@@ -416,20 +419,20 @@ k_tile_localize_masks_flat(const TileChunk *__restrict__ chunks, MaskOut mo, con
             *reinterpret_cast<uint4 *>(buf + k) = make_uint4(sent, sent, sent, sent);
         uint32_t nb = 0, grp = 0;
         if (my) {
-            const uint32_t cid = cell_id_sorted[s];
-            grp = (cid / nc2) * gpc + (cid % nc2) / zg;
+            const uint32_t cz = cell_id_sorted[s] - colcell0; // cell along the column (every atom of a chunk is in column `col`)
+            grp = col * gpc + (zg == 1u ? cz : cz / zg);
             nb = min(mo.grp_nb[grp], mo.mb_cap);
         }
-        const uint32_t nbq = (nb + 3u) >> 2, b0 = tl * nbq, b1 = min(b0 + nbq, nb);
         // the lane's non-empty masks and their block bases, compacted into its private column of shared memory
         uint32_t tot = 0, nq = 0;
         {
             uint32_t mk[MAXQ], bs[MAXQ];
 #pragma unroll
             for (int q = 0; q < MAXQ; q++) { // all loads in flight before the first use
-                const uint32_t b = b0 + (uint32_t)q;
-                mk[q] = b < b1 ? __ldg(mo.masks + (size_t)b * mo.npad + s) : 0u;
-                bs[q] = b < b1 ? __ldg(mo.blk_base + (size_t)grp * mo.mb_cap + b) : 0u;
+                // blocks tl, tl + 4, ...: the populous blocks of the centre columns are dealt round the team
+                const uint32_t b = tl + 4u * (uint32_t)q;
+                mk[q] = b < nb ? __ldg(mo.masks + (size_t)b * mo.npad + s) : 0u;
+                bs[q] = b < nb ? __ldg(mo.blk_base + (size_t)grp * mo.mb_cap + b) : 0u;
             }
 #pragma unroll
             for (int q = 0; q < MAXQ; q++)
