@@ -196,11 +196,21 @@ struct MaskOut { // kernel argument of the build
     uint32_t *blk_base; // [ngroups][mb_cap]: first candidate slot | column tag << PARM_NBR_SLOT_BITS
     uint32_t *grp_nb;   // [ngroups]: candidate blocks of the group
     uint32_t mb_cap, npad;
+    // direct mode: the build warp also keeps the masks of its 32 atoms in shared memory and expands them itself, lane =
+    // atom, straight into the 16-bit tile-local rows (no separate localize pass); needs the tile plan of this rebuild
+    uint32_t direct;                 // 1: write rows16 from the build kernel
+    const TileChunk *chunks;
+    const uint32_t *col_slot, *col_chunk; // first slot / first chunk of every owned column (tile.cu: k_tile_cols)
+    uint32_t ch;                     // chunk size of the plan
+    uint16_t *rows16;
+    uint32_t *direct_fail;           // set when a warp group walked more candidate blocks than its shared memory holds
 };
 struct MaskState {
     int enabled;        // PARM_B200_BUILD_MASKS
     bool active;        // the current list was built in mask mode
     bool rows32_valid;  // nbr[] has been expanded from the masks since the last build
+    bool direct;        // the build kernel wrote rows16 itself (no localize pass)
+    uint32_t *d_fail, *h_fail; // direct mode: overflow flag of the in-kernel expansion (device / pinned)
     MaskOut out;
     size_t masks_cap, blk_cap, grp_cap;
     uint32_t ngroups, gpc;
@@ -369,6 +379,7 @@ int parm_tile_localize(parm_nlist *nl);       // after the rows are final (ignor
 void parm_tile_invalidate(parm_nlist *nl);
 void parm_tile_free(parm_nlist *nl);
 int parm_tile_localize_masks(parm_nlist *nl); // mask-mode lists: rows16 straight from the pass masks
+int parm_tile_rows16_reserve(parm_nlist *nl);  // rows16 allocated for the current npad x kmax (before a direct-mode build)
 // prel of slots [first, first + count) from pos (bulk-copy staging); no-op when the list does not stage that way
 int parm_tile_prep(parm_nlist *nl, uint32_t first, uint32_t count, cudaStream_t stream, const int *abort_flag);
 bool parm_tile_all_fit(const parm_nlist *nl); // every interaction on the list can run on the tile kernel

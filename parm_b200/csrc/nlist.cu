@@ -430,6 +430,7 @@ k_build(const double4 *__restrict__ pos, const double4 *__restrict__ pw, const d
 // one full 32-byte sector, so the row stores cost one L2 transaction per 8 neighbours. Same banded
 // classification / exact predicate as k_build; ~2.4x fewer instructions per candidate test.
 #define CB_WARPS 4
+#define CB_DIRECT_BLOCKS 44 // candidate blocks per warp group whose masks fit the warp's shared memory (direct mode)
 // packed fp32 pairs (FADD2 / FMUL2 / FFMA2 on sm_100): two candidates per instruction in the fp32 pre-test
 typedef unsigned long long f32x2;
 __device__ __forceinline__ f32x2 f2_add(f32x2 a, f32x2 b) { f32x2 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
@@ -458,6 +459,11 @@ k_build_cell(const double4 *__restrict__ pos, const double4 *__restrict__ pw, co
     __shared__ double4 s_c[CB_WARPS][32];
     __shared__ __align__(8) float s_fx[CB_WARPS][32], s_fy[CB_WARPS][32], s_fz[CB_WARPS][32], s_fw[CB_WARPS][32];
     __shared__ uint32_t s_buf[CB_WARPS][MASK ? 1 : 64][32]; // per lane: ring of 64 pending row entries (a block adds <= 32 to <= 7), flushed 8 (one 32-byte sector) at a time
+    // MASK, direct mode: the warp's pass masks [block][lane], the blocks' first slot | column tag, and a per-lane ring of
+    // one 32-entry pass of the 16-bit row being assembled
+    __shared__ uint32_t s_dm[MASK ? CB_WARPS : 1][MASK ? CB_DIRECT_BLOCKS : 1][32];
+    __shared__ uint32_t s_db[MASK ? CB_WARPS : 1][MASK ? CB_DIRECT_BLOCKS : 1];
+    __shared__ __align__(16) uint16_t s_dr[MASK ? CB_WARPS : 1][MASK ? 32 : 1][MASK ? 40 : 8]; // row stride 80 bytes: conflict-free 16-byte reads
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const uint32_t cur = blockIdx.x * CB_WARPS + wib;
     if (cur >= ngroups) return;
@@ -670,6 +676,10 @@ k_build_cell(const double4 *__restrict__ pos, const double4 *__restrict__ pw, co
                                 if (valid) mo.masks[(size_t)nblk * mo.npad + i] = m;
                                 if (lane == 0) mo.blk_base[(size_t)cur * mo.mb_cap + nblk] = jt;
                             }
+                            if (mo.direct && nblk < CB_DIRECT_BLOCKS) {
+                                s_dm[wib][nblk][lane] = m;
+                                if (lane == 0) s_db[wib][nblk] = jt;
+                            }
                             count += __popc(m);
                             nblk++;
                             continue;
@@ -692,6 +702,61 @@ k_build_cell(const double4 *__restrict__ pos, const double4 *__restrict__ pw, co
             if (lane == 0) {
                 mo.grp_nb[cur] = nblk;
                 atomicMax(&flags->nbmax, nblk);
+            }
+            if (mo.direct) {
+                // Expansion, lane = atom: every lane walks the set bits of ITS masks in one flat loop (rows are ~110 +- 10
+                // long, so the lanes of a warp finish almost together), turns candidate slots into indices of its chunk's
+                // tile through the chunk's run table, assembles one 32-entry pass of the row at a time in the pair
+                // kernel's lane-vector layout and writes it out as 64 bytes; the last pass is padded with the sentinel.
+                __syncwarp();
+                if (nblk > CB_DIRECT_BLOCKS) {
+                    if (lane == 0) *mo.direct_fail = 1u;
+                } else if (valid) {
+                    const uint32_t q = tcol; // owned column (single GPU: column index = cx * nc1 + cy)
+                    const uint32_t cs = mo.col_slot[q], cc = mo.col_chunk[q];
+                    const uint32_t ccnt = mo.col_slot[q + 1] - cs, cnch = mo.col_chunk[q + 1] - cc;
+                    const uint32_t csz = min(mo.ch, (ccnt + cnch - 1) / cnch);
+                    const TileChunk *TC = mo.chunks + cc + (i - cs) / csz;
+                    const uint32_t ntile = TC->ntile;
+                    uint16_t *out = mo.rows16 + (size_t)i * kmax;
+                    uint16_t *ring = s_dr[wib][lane];
+                    const uint32_t kend = min(count, kmax);
+                    uint32_t k = 0, m = 0, ty = 0, tw = 0, l0 = 0, n0 = 0, jz = 0, b = 0;
+                    for (;;) {
+                        if (!m) {
+                            while (b < nblk && !(m = s_dm[wib][b][lane])) b++;
+                            if (b >= nblk) break;
+                            const uint32_t base = s_db[wib][b++];
+                            const uint32_t kc = 2u * min(base >> PARM_NBR_SLOT_BITS, 8u);
+                            const uint32_t jb = base & PARM_NBR_SLOT_MASK;
+                            const uint32_t tx = TC->seg_start[kc], tz = TC->seg_start[kc + 1];
+                            ty = TC->seg_off[kc];
+                            tw = TC->seg_off[kc + 1];
+                            l0 = jb - tx; n0 = tw - ty; jz = jb - tz;
+                        }
+                        const uint32_t bit = (uint32_t)__ffs(m) - 1u;
+                        m &= m - 1u;
+                        const uint32_t r = l0 + bit;
+                        const uint32_t l = r < n0 ? ty + r : tw + (jz + bit);
+                        if (k < kend) {
+                            const uint32_t r32 = k & 31u;
+                            ring[((r32 << 3) & 24u) | (r32 >> 2)] = (uint16_t)min(l, ntile);
+                            if (r32 == 31u) { // a whole pass: 64 bytes
+                                uint4 *dst = reinterpret_cast<uint4 *>(out + (k & ~31u));
+                                const uint4 *src = reinterpret_cast<const uint4 *>(ring);
+                                dst[0] = src[0]; dst[1] = src[1]; dst[2] = src[2]; dst[3] = src[3];
+                            }
+                        }
+                        k++;
+                    }
+                    if (kend & 31u) { // tail: pad the last pass with the sentinel index
+                        for (uint32_t kk = kend & 31u; kk < 32u; kk++) ring[((kk << 3) & 24u) | (kk >> 2)] = (uint16_t)ntile;
+                        uint4 *dst = reinterpret_cast<uint4 *>(out + (kend & ~31u));
+                        const uint4 *src = reinterpret_cast<const uint4 *>(ring);
+                        dst[0] = src[0]; dst[1] = src[1]; dst[2] = src[2]; dst[3] = src[3];
+                    }
+                }
+                __syncwarp();
             }
         } else if (member) { // tail of the row
             for (uint32_t k = flushed; k < count && k < kmax; k++) row[k] = s_buf[wib][k & 63u][lane];
@@ -799,6 +864,8 @@ extern "C" int parm_nlist_destroy(parm_nlist *nl) {
     if (nl->d_excl) cudaFree(nl->d_excl);
     if (nl->h_flags) cudaFreeHost(nl->h_flags);
     if (nl->h_slot) cudaFreeHost(nl->h_slot);
+    if (nl->mask.d_fail) cudaFree(nl->mask.d_fail);
+    if (nl->mask.h_fail) cudaFreeHost(nl->mask.h_fail);
     parm_tile_free(nl);
     c->nlists.erase(std::remove(c->nlists.begin(), c->nlists.end(), nl), c->nlists.end());
     delete nl;
@@ -1210,6 +1277,7 @@ int parm_nlist_build_rows(parm_nlist *nl) {
     const double uthr = nl->maxdiam + nl->skin;
     PTRY(parm_tile_plan_enqueue(nl)); // chunk table of the cell-tile pair kernel: needs the cell structure only
     for (int attempt = 0; attempt < 8; attempt++) {
+        uint32_t kmax_launch = nl->kmax;
         CK(cudaMemsetAsync((char *)nl->d_flags + offsetof(NlistFlags, maxcnt), 0,
                            offsetof(NlistFlags, xmax_bits) - offsetof(NlistFlags, maxcnt), c->stream));
 #define CARGS c->pos, nl->pw, nl->d_diam, nl->cell_start, ngroups, zg, n, c->box, nl->g, nl->st, nl->skin, nl->lmax, \
@@ -1252,11 +1320,32 @@ int parm_nlist_build_rows(parm_nlist *nl) {
             nl->mask.enabled = masks_env;
             const bool use_masks = masks_env && tagcols && !run2d && !nl->smallbox && !c->sh.on && nl->ignored.empty() &&
                                    nl->total_full >= (uint64_t)nl->tile.min_nbrs * n && parm_tile_all_fit(nl);
+            kmax_launch = nl->kmax;
+            nl->mask.direct = false;
             if (use_masks) {
                 PTRY(alloc_masks(nl, std::max(nl->mask.out.mb_cap, 48u), ngroups));
                 nl->mask.ngroups = ngroups;
                 nl->mask.gpc = gpc;
                 nl->mask.zg = zg;
+                // direct mode: the build warps expand their masks into rows16 themselves (tile.cu's localize pass is skipped)
+                const char *ed = getenv("PARM_B200_BUILD_DIRECT");
+                MaskOut &mo = nl->mask.out;
+                mo.direct = (ed ? atoi(ed) != 0 : true) && nl->tile.team == 4 && nl->tile.v == 8 ? 1u : 0u;
+                if (mo.direct) {
+                    if (!nl->mask.d_fail) {
+                        CK(cudaMalloc(&nl->mask.d_fail, 4));
+                        CK(cudaHostAlloc(&nl->mask.h_fail, 4, cudaHostAllocDefault));
+                    }
+                    PTRY(parm_tile_rows16_reserve(nl));
+                    CK(cudaMemsetAsync(nl->mask.d_fail, 0, 4, c->stream));
+                    mo.chunks = nl->tile.d_chunks;
+                    mo.col_slot = nl->tile.d_col;
+                    mo.col_chunk = nl->tile.d_col + nl->tile.col_cap;
+                    mo.ch = (uint32_t)nl->tile.ch;
+                    mo.rows16 = nl->tile.rows16;
+                    mo.direct_fail = nl->mask.d_fail;
+                    nl->mask.direct = true;
+                }
             }
             nl->mask.active = use_masks;
             nl->mask.rows32_valid = !use_masks;
@@ -1291,6 +1380,7 @@ int parm_nlist_build_rows(parm_nlist *nl) {
         CK_LAUNCH(c);
         if (attempt == 0) PTRY(parm_prof_end(c));
         CK(cudaMemcpyAsync(nl->h_flags, nl->d_flags, sizeof(NlistFlags), cudaMemcpyDeviceToHost, c->stream));
+        if (nl->mask.active && nl->mask.direct) CK(cudaMemcpyAsync(nl->mask.h_fail, nl->mask.d_fail, 4, cudaMemcpyDeviceToHost, c->stream));
         PTRY(parm_tile_plan_fetch(nl));
         CK(cudaStreamSynchronize(c->stream));
         nl->total_full = nl->h_flags->total;
@@ -1300,6 +1390,8 @@ int parm_nlist_build_rows(parm_nlist *nl) {
                 nl->mask.out.mb_cap = nl->h_flags->nbmax + 8;
                 continue; // (alloc_masks runs again at the top of the next attempt)
             }
+            // rows16 written by the build itself are good unless a group overflowed its shared-memory masks or a row its capacity
+            if (nl->mask.direct && (*nl->mask.h_fail || nl->maxcnt > kmax_launch)) nl->mask.direct = false;
             if (nl->maxcnt > nl->kmax) PTRY(alloc_nbr(nl, nl->maxcnt + nl->maxcnt / 8 + 8)); // capacity only: the masks are complete
             return finish_rows(nl);
         }

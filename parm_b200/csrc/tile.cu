@@ -688,6 +688,20 @@ bool parm_tile_all_fit(const parm_nlist *nl) {
     return any;
 }
 
+int parm_tile_rows16_reserve(parm_nlist *nl) {
+    parm_ctx *c = nl->ctx;
+    TileState &t = nl->tile;
+    const size_t need = (size_t)c->npad * nl->kmax;
+    if (need > t.rows16_cap) {
+        if (t.rows16) cudaFree(t.rows16);
+        t.rows16 = 0;
+        t.rows16_cap = 0;
+        CK(cudaMalloc(&t.rows16, need * 2));
+        t.rows16_cap = need;
+    }
+    return 0;
+}
+
 // Mask-mode twin of parm_tile_localize (TEAM = 4, V = 8 only; other layouts fall back to the 32-bit rows).
 int parm_tile_localize_masks(parm_nlist *nl) {
     parm_ctx *c = nl->ctx;
@@ -711,7 +725,9 @@ int parm_tile_localize_masks(parm_nlist *nl) {
         t.rows16_cap = need;
     }
 #define LMARGS t.d_chunks, nl->mask.out, nl->cell_id_sorted, (uint32_t)nl->g.nc[2], nl->mask.gpc, (uint32_t)nl->mask.zg, nl->cnt, nl->kmax, t.rows16, t.d_info
-    if (nl->h_flags->nbmax <= 48) {
+    if (nl->mask.direct) {
+        // the build kernel has written rows16 itself
+    } else if (nl->h_flags->nbmax <= 48) {
         if (smem > 48 * 1024) CK(cudaFuncSetAttribute(k_tile_localize_masks_flat<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         k_tile_localize_masks_flat<12><<<t.nchunks, TILE_NT, smem, c->stream>>>(LMARGS);
     } else {

@@ -9,9 +9,9 @@ sys.argv = ["tile_sweep"]
 import tools.tile_sweep as ts
 from parm_b200 import workloads as W
 w = W.config3(100)
-KEYS = ("PARM_B200_TILE_BANKS", "PARM_B200_BUILD_MASKS", "PARM_B200_TILE_STAGE", "PARM_B200_K1_PREL", "PARM_B200_TILE_PERS")
-for env in [{"PARM_B200_TILE_PERS": 0}, {"PARM_B200_TILE_PERS": 1}, {"PARM_B200_TILE_PERS": 0, "PARM_B200_BUILD_MASKS": 1},
-            {"PARM_B200_TILE_PERS": 1, "PARM_B200_BUILD_MASKS": 1}]:
+KEYS = ("PARM_B200_TILE_BANKS", "PARM_B200_BUILD_MASKS", "PARM_B200_TILE_STAGE", "PARM_B200_K1_PREL", "PARM_B200_TILE_PERS", "PARM_B200_BUILD_DIRECT")
+for env in [{"PARM_B200_TILE_PERS": 0}, {"PARM_B200_TILE_PERS": 0, "PARM_B200_BUILD_MASKS": 1, "PARM_B200_BUILD_DIRECT": 0},
+            {"PARM_B200_TILE_PERS": 0, "PARM_B200_BUILD_MASKS": 1, "PARM_B200_BUILD_DIRECT": 1}]:
     for k in KEYS:
         os.environ.pop(k, None)
     e = {"PARM_B200_TILE": 1}
