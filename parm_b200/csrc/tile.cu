@@ -407,16 +407,14 @@ k_tile_localize_masks_flat(const TileChunk *__restrict__ chunks, MaskOut mo, con
     const uint32_t tl = threadIdx.x & 3u, team = threadIdx.x >> 2;
     const uint32_t stride = kmax + 8u;
     uint16_t *buf = s_rows + (size_t)team * stride;
-    uint32_t lost = 0;
+    uint32_t lmax = 0;
     for (uint32_t a0 = 0; a0 < na; a0 += TILE_NT / 4) { // every lane of a warp runs the same trips (team shuffles below)
         const uint32_t a = a0 + team;
         const bool valid = a < na;
         const uint32_t s = s0 + (valid ? a : 0);
         const uint32_t my = valid ? min(cnt[s], kmax) : 0;
         const uint32_t mypad = (my + 31u) & ~31u;
-        const uint32_t sent = ntile * 0x10001u;
-        for (uint32_t k = tl * 8u; k < mypad; k += 32u) // sentinel everywhere, entries overwrite it
-            *reinterpret_cast<uint4 *>(buf + k) = make_uint4(sent, sent, sent, sent);
+        // (the row is assembled in NATURAL order; the lane-vector permutation of the pair kernel happens on the way out)
         uint32_t nb = 0, grp = 0;
         if (my) {
             const uint32_t cz = cell_id_sorted[s] - colcell0; // cell along the column (every atom of a chunk is in column `col`)
@@ -449,7 +447,7 @@ k_tile_localize_masks_flat(const TileChunk *__restrict__ chunks, MaskOut mo, con
         y = __shfl_up_sync(0xffffffffu, incl, 2, 4);
         if (tl >= 2) incl += y;
         uint32_t k = incl - tot;
-        __syncwarp(); // the sentinel fill of the whole row is complete
+        __syncwarp();
         // flat walk: (m, ty, tw, l0, n0, jz) describe the current block; an empty m pulls the next non-empty mask
         uint32_t m = 0, ty = 0, tw = 0, l0 = 0, n0 = 0, jz = 0;
         uint32_t q = 0;
@@ -467,23 +465,28 @@ k_tile_localize_masks_flat(const TileChunk *__restrict__ chunks, MaskOut mo, con
             m &= m - 1u;
             const uint32_t r = l0 + bit;
             const uint32_t l = r < n0 ? ty + r : tw + (jz + bit);
-            lost |= l >= ntile ? 1u : 0u; // (not expected: the entry is in neither run of its column)
-            if (k < my) {
-                // entry k of the row is read by lane (k & 3) of the team at step (k & 31) >> 2 of pass k / 32
-                const uint32_t r32 = k & 31u;
-                buf[(k & ~31u) + (r32 & 3u) * 8u + (r32 >> 2)] = (uint16_t)min(l, ntile);
-            }
+            lmax = max(lmax, l); // (an index beyond the tile is not expected: the entry would be in neither run of its column)
+            if (k < kmax) buf[k] = (uint16_t)l; // (cnt = sum of the popcounts and kmax >= every cnt, parm_nlist_build_rows: never false)
             k++;
         }
         __syncwarp();
         if (valid) {
+            // lane tl's vector of pass p: entries 32 p + tl, + 4, ..., + 28 of the row (sentinel index past its end)
             uint16_t *out = rows16 + (size_t)s * kmax;
-            for (uint32_t k0 = 0; k0 < mypad; k0 += 32)
-                *reinterpret_cast<uint4 *>(out + k0 + tl * 8) = *reinterpret_cast<const uint4 *>(buf + k0 + tl * 8);
+            for (uint32_t k0 = 0; k0 < mypad; k0 += 32) {
+                uint32_t w[4];
+#pragma unroll
+                for (int g = 0; g < 8; g += 2) {
+                    const uint32_t ka = k0 + tl + 4u * g, kb = ka + 4u;
+                    const uint32_t ea = ka < my ? buf[ka] : ntile, eb = kb < my ? buf[kb] : ntile;
+                    w[g >> 1] = ea | eb << 16;
+                }
+                *reinterpret_cast<uint4 *>(out + k0 + tl * 8) = make_uint4(w[0], w[1], w[2], w[3]);
+            }
         }
         __syncwarp();
     }
-    if (lost) atomicOr(&info->bad, 2u);
+    if (lmax >= ntile) atomicOr(&info->bad, 2u);
 }
 
 // ---- per step: positions in the image every atom had at the last rebuild (bulk-copy staging) ----------------------

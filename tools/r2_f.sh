@@ -10,8 +10,7 @@ import tools.tile_sweep as ts
 from parm_b200 import workloads as W
 w = W.config3(100)
 KEYS = ("PARM_B200_TILE_BANKS", "PARM_B200_BUILD_MASKS", "PARM_B200_TILE_STAGE", "PARM_B200_K1_PREL", "PARM_B200_TILE_PERS", "PARM_B200_BUILD_DIRECT")
-for env in [{"PARM_B200_TILE_PERS": 0}, {"PARM_B200_TILE_PERS": 0, "PARM_B200_BUILD_MASKS": 1, "PARM_B200_BUILD_DIRECT": 0},
-            {"PARM_B200_TILE_PERS": 0, "PARM_B200_BUILD_MASKS": 1, "PARM_B200_BUILD_DIRECT": 1}]:
+for env in [{"PARM_B200_TILE_PERS": 0}, {"PARM_B200_TILE_PERS": 0, "PARM_B200_BUILD_MASKS": 1}]:
     for k in KEYS:
         os.environ.pop(k, None)
     e = {"PARM_B200_TILE": 1}
@@ -19,7 +18,7 @@ for env in [{"PARM_B200_TILE_PERS": 0}, {"PARM_B200_TILE_PERS": 0, "PARM_B200_BU
     ts.run(w, 200, e)
 PY
 tail -3 gpurun_out/r2f.err
-PARM_B200_BUILD_MASKS=1 ncu --set full --clock-control none --import-source on -k regex:'k_tile_localize_masks|k_build_cell' -s 2 -c 2 \
+PARM_B200_BUILD_MASKS=1 ncu --set full --clock-control none --import-source on -k regex:'k_tile_localize_masks|k_build_cell' -s 2 -c 4 \
     -o gpurun_out/r2f_reb -f python tools/tile_probe.py --steps 12 > gpurun_out/r2f_ncu.log 2>&1
 tail -2 gpurun_out/r2f_ncu.log
 ncu -i gpurun_out/r2f_reb.ncu-rep --page raw --csv > gpurun_out/r2f_reb_raw.csv 2>/dev/null
