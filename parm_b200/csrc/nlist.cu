@@ -1313,10 +1313,10 @@ int parm_nlist_build_rows(parm_nlist *nl) {
                 ext = std::max(ext, d == rax ? (0.5 * zg + nl->st.sub) * cs : (nl->st.sub + 1.0) * cs);
             }
             double beta32 = 3.0 * ((6.93 * ext / nl->thr_min + 14.0) * 5.9604644775390625e-8);
-            // mask mode (experimental, off by default): 3-D tile-planned single-GPU lists without exclusions whose last build
+            // mask mode (default; PARM_B200_BUILD_MASKS=0 selects the classic append build): 3-D tile-planned single-GPU lists without exclusions whose last build
             // had long rows and whose interactions all run on the cell-tile kernel
             const char *em = getenv("PARM_B200_BUILD_MASKS"); // read per rebuild: the sweeps toggle it inside one process
-            const int masks_env = em ? atoi(em) : 0;
+            const int masks_env = em ? atoi(em) : 1;
             nl->mask.enabled = masks_env;
             const bool use_masks = masks_env && tagcols && !run2d && !nl->smallbox && !c->sh.on && nl->ignored.empty() &&
                                    nl->total_full >= (uint64_t)nl->tile.min_nbrs * n && parm_tile_all_fit(nl);
