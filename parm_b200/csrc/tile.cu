@@ -731,7 +731,8 @@ int parm_tile_localize_masks(parm_nlist *nl) {
     if (nl->mask.direct) {
         // the build kernel has written rows16 itself
     } else if (nl->h_flags->nbmax <= 48) {
-        if (smem > 48 * 1024) CK(cudaFuncSetAttribute(k_tile_localize_masks_flat<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        // (25 KB of static shared memory on top: the opt-in is needed from 23 KB of row buffers)
+        if (smem > 20 * 1024) CK(cudaFuncSetAttribute(k_tile_localize_masks_flat<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         k_tile_localize_masks_flat<12><<<t.nchunks, TILE_NT, smem, c->stream>>>(LMARGS);
     } else {
         if (smem > 48 * 1024) CK(cudaFuncSetAttribute(k_tile_localize_masks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
