@@ -117,6 +117,7 @@ static int launch_forces(parm_inter *it, int run, bool accumulate, double *d_out
         const char *ep = getenv("PARM_B200_TILE_PERS"); // (read per launch: the sweeps toggle it inside one process)
         // (measured at N = 1e6: 0.250 ms against 0.243 ms for the one-block-per-chunk kernel -- two tile buffers per block
         // leave the compute warps at most one chunk of slack; off by default)
+        T.cap = ((nl->tile.max_tile + 1 + 15u) & ~15u) + 16u; // tile + the single sentinel, rounded up, + 16 class sentinels
         const bool pers = bulk && (ep ? atoi(ep) != 0 : false) && 2 * 3 * (size_t)T.cap * 8 + 2048 <= 113 * 1024 && nl->tile.ch <= 120;
         T.pers_blocks = pers ? 2u * (uint32_t)c->num_sms : 0u;
         T.chunk_s0 = nl->tile.d_s0 + chunk0;
@@ -135,7 +136,11 @@ static int launch_forces(parm_inter *it, int run, bool accumulate, double *d_out
         T.abort_flag = abort_flag;
         cudaError_t e = tl(nl->tile.team, nl->tile.v, mode, nblocks, 3 * (size_t)T.cap * 8, c->stream, T);
         parm_count_launch(c);
-        CK(e);
+        if (e != cudaSuccess) {
+            parm_set_error("cell-tile pair kernel launch failed: %s (chunks %u..%u, tile capacity %u atoms = %zu bytes of shared memory, "
+                           "bulk staging %d)", cudaGetErrorString(e), chunk0, chunk1, T.cap, 3 * (size_t)T.cap * 8, (int)bulk);
+            return PARM_ERR_CUDA;
+        }
         if (mode != MODE_F) {
             if (!d_out) { parm_set_error("internal: observables requested without an output buffer"); return PARM_ERR_RUNTIME; }
             k_force_fold<<<1, 256, 0, c->stream>>>(it->d_partials, nblocks, d_out);

@@ -556,10 +556,10 @@ __global__ void __launch_bounds__(TILE_PNT, 2) k_force_tile_pers(const TileForce
 template <int KIND, int TEAM, int V, int STAGE>
 static cudaError_t launch_tile_mode(int mode, unsigned nchunks, size_t smem, cudaStream_t st, const TileForceArgs &A) {
     if (mode == MODE_F) {
-        if (smem > 48 * 1024) cudaFuncSetAttribute(k_force_tile<KIND, MODE_F, TEAM, V, STAGE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (smem + 2048 > 48 * 1024) cudaFuncSetAttribute(k_force_tile<KIND, MODE_F, TEAM, V, STAGE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         k_force_tile<KIND, MODE_F, TEAM, V, STAGE><<<nchunks, TILE_NT, smem, st>>>(A);
     } else {
-        if (smem > 48 * 1024) cudaFuncSetAttribute(k_force_tile<KIND, MODE_FALL, TEAM, V, STAGE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (smem + 2048 > 48 * 1024) cudaFuncSetAttribute(k_force_tile<KIND, MODE_FALL, TEAM, V, STAGE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         k_force_tile<KIND, MODE_FALL, TEAM, V, STAGE><<<nchunks, TILE_NT, smem, st>>>(A);
     }
     return cudaGetLastError();

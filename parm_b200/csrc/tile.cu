@@ -735,7 +735,7 @@ int parm_tile_localize_masks(parm_nlist *nl) {
         if (smem > 20 * 1024) CK(cudaFuncSetAttribute(k_tile_localize_masks_flat<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         k_tile_localize_masks_flat<12><<<t.nchunks, TILE_NT, smem, c->stream>>>(LMARGS);
     } else {
-        if (smem > 48 * 1024) CK(cudaFuncSetAttribute(k_tile_localize_masks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        if (smem + 2048 > 48 * 1024) CK(cudaFuncSetAttribute(k_tile_localize_masks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         k_tile_localize_masks<<<t.nchunks, TILE_NT, smem, c->stream>>>(LMARGS);
     }
 #undef LMARGS
