@@ -1318,7 +1318,9 @@ int parm_nlist_build_rows(parm_nlist *nl) {
             const char *em = getenv("PARM_B200_BUILD_MASKS"); // read per rebuild: the sweeps toggle it inside one process
             const int masks_env = em ? atoi(em) : 1;
             nl->mask.enabled = masks_env;
-            const bool use_masks = masks_env && tagcols && !run2d && !nl->smallbox && !c->sh.on && nl->ignored.empty() &&
+            const char *ems = getenv("PARM_B200_BUILD_MASKS_SHARDED");
+            const bool masks_sharded = ems ? atoi(ems) != 0 : true; // slab-decomposed contexts: rows of the owned atoms only, ghosts are candidates
+            const bool use_masks = masks_env && tagcols && !run2d && !nl->smallbox && (!c->sh.on || masks_sharded) && nl->ignored.empty() &&
                                    nl->total_full >= (uint64_t)nl->tile.min_nbrs * n && parm_tile_all_fit(nl);
             kmax_launch = nl->kmax;
             nl->mask.direct = false;
