@@ -10,9 +10,9 @@ configuration (--equil untimed steps with velocity rescaling from the jittered l
 
 N = 1 workload: BASELINE.json configs[2] -- 3-D LJ, LJAttractRepulsePair cut 2.5 sigma, N = 1e6
 (the largest single-GPU configuration the metric is quoted on; SURVEY 8d cfg 3: rho = 1.1939,
-T = 1.44, skin 0.3, dt 0.004).  N > 1: the same per-GPU slab stacked along z (weak scaling),
+T = 1.44, skin 0.3, dt 0.004).  N > 1: the same per-GPU slab stacked along x, the slab axis (weak scaling),
 i.e. 1e6 atoms per GPU, slab-decomposed with NCCL halo exchange (config 5 is N=16e6 on 8 GPUs
-= 2e6 per GPU; --side-z 200 reproduces it).
+= 2e6 per GPU; the 8-GPU run also times it and prints it as config5_16M).
 """
 import argparse
 import json

@@ -69,7 +69,11 @@ int parm_box_diff(parm_ctx *ctx, uint32_t npts, const double *r1, const double *
 #define PARM_ALL 31u
 /* Atom fields (box.hpp:234-249) host->device / device->host. Pointers address the
  * field of atom 0; consecutive atoms are stride_vec (x,v,a,f) / stride_m (m) BYTES
- * apart. For ParM's AoS pass &atoms[0].x, ... with both strides = sizeof(Atom). */
+ * apart. For ParM's AoS pass &atoms[0].x, ... with both strides = sizeof(Atom).
+ * A whole struct-Atom array (mask PARM_ALL, AoS) travels as ONE copy on the context's stream and parm_upload_atoms
+ * returns without waiting for it: when that array is page-locked (parm_host_register), the caller must leave it
+ * unchanged until the next call that synchronises (parm_sync, parm_download_atoms, any reduction or query). Every
+ * other layout is staged and has been consumed when the call returns. */
 int parm_upload_atoms(parm_ctx *ctx, unsigned mask, const double *x, const double *v, const double *a,
                       const double *f, const double *m, size_t stride_vec, size_t stride_m);
 int parm_download_atoms(parm_ctx *ctx, unsigned mask, double *x, double *v, double *a, double *f, double *m,

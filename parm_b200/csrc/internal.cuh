@@ -62,7 +62,8 @@ struct PairConst {
 
 // Slab decomposition state (one process per GPU; csrc/shard.cu). The slab axis is x (axis 0, the
 // slowest index of the cell id), rank r owns wrapped x in [lo, lo + Ls). Slot layout after a
-// rebuild: [ghosts from the lower neighbour | local atoms | ghosts from the upper neighbour].
+// rebuild: [owned atoms, lowest layer first | ghosts from the upper neighbour | ghosts from the lower
+// neighbour] -- every range that is ever communicated is contiguous.
 struct ShardState {
     bool on;
     int rank, nranks, up, down;

@@ -1261,7 +1261,12 @@ int parm_nlist_build_rows(parm_nlist *nl) {
     const uint32_t n = c->n;
     for (parm_inter *it : c->inters) PTRY(parm_inter_regather(it));
     parm_tile_invalidate(nl);
-    if (n == 0) { nl->total_full = 0; nl->maxcnt = 0; return 0; }
+    if (n == 0) { // (a sharded rank that owns no atoms) close the profiling record opened by the caller
+        nl->total_full = 0;
+        nl->maxcnt = 0;
+        if (c->prof_on && !c->prof_pending.empty()) PTRY(parm_prof_end(c));
+        return 0;
+    }
     if (nl->kmax == 0) {
         double vol = 1;
         for (int d = 0; d < c->D; d++) vol *= c->box.L[d];
@@ -1382,7 +1387,6 @@ int parm_nlist_build_rows(parm_nlist *nl) {
 #undef BARGS
 #undef CARGS
         CK_LAUNCH(c);
-        if (attempt == 0) PTRY(parm_prof_end(c));
         CK(cudaMemcpyAsync(nl->h_flags, nl->d_flags, sizeof(NlistFlags), cudaMemcpyDeviceToHost, c->stream));
         if (nl->mask.active && nl->mask.direct) CK(cudaMemcpyAsync(nl->mask.h_fail, nl->mask.d_fail, 4, cudaMemcpyDeviceToHost, c->stream));
         PTRY(parm_tile_plan_fetch(nl));
@@ -1397,9 +1401,13 @@ int parm_nlist_build_rows(parm_nlist *nl) {
             // rows16 written by the build itself are good unless a group overflowed its shared-memory masks or a row its capacity
             if (nl->mask.direct && (*nl->mask.h_fail || nl->maxcnt > kmax_launch)) nl->mask.direct = false;
             if (nl->maxcnt > nl->kmax) PTRY(alloc_nbr(nl, nl->maxcnt + nl->maxcnt / 8 + 8)); // capacity only: the masks are complete
-            return finish_rows(nl);
+            PTRY(finish_rows(nl));
+            return parm_prof_end(c); // the rebuild record covers sort, build and the tile rows
         }
-        if (nl->maxcnt <= nl->kmax) return finish_rows(nl);
+        if (nl->maxcnt <= nl->kmax) {
+            PTRY(finish_rows(nl));
+            return parm_prof_end(c);
+        }
         uint32_t k2 = nl->maxcnt + nl->maxcnt / 8 + 8;
         PTRY(alloc_nbr(nl, k2));
     }

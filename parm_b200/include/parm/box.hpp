@@ -7,6 +7,8 @@
 //     date and marks it "possibly modified": it is uploaded before the next device operation;
 //   - timestep(), set_forces(), velocity scaling ... mark the device copy as newer.
 // Group reductions (kinetic_energy, momentum, ...) run on the device and never force a download.
+#include <stdexcept>
+#include <cstdlib>
 #include "vecrand.hpp"
 
 #ifndef PARM_B200_BOX_H
@@ -193,7 +195,24 @@ class AtomVec : public virtual AtomGroup {
     bool registered;
     mutable bool host_dirty;  // mirror may hold changes the device has not seen
     mutable bool dev_newer;   // device holds results the mirror has not seen
+    // STORED REFERENCES (difference from the reference, where Atom& / AtomID are live views of the only copy): the host
+    // array is a MIRROR. operator[] / get_id() synchronise at the moment of the call; an `Atom&` or `AtomID` kept across a
+    // device operation (timestep(), set_forces(), update_list(), a reduction after one of those) goes stale: reads
+    // through it see the state at the time of the call, writes through it are never uploaded. Re-fetch with operator[]
+    // after device work, or bracket the access with sync_to_host() / touch_host(). PARM_B200_CHECK_VIEWS=1 (environment)
+    // turns on a checksum of the mirror that makes device() throw std::logic_error when it finds such a lost write.
+    bool check_views;
+    mutable unsigned long long mirror_sum;
+    unsigned long long checksum() const { // FNV-1a over the mirror (debug aid only)
+        unsigned long long h = 1469598103934665603ull;
+        const unsigned char *p = reinterpret_cast<const unsigned char *>(atoms);
+        for (size_t i = 0, n = sizeof(Atom) * (size_t)sz; i < n; i++) h = (h ^ p[i]) * 1099511628211ull;
+        return h;
+    }
     void init(int device) {
+        const char *cv = getenv("PARM_B200_CHECK_VIEWS");
+        check_views = cv && atoi(cv) != 0;
+        mirror_sum = 0;
         atoms = new Atom[sz ? sz : 1];
         for (uint i = 0; i < sz; i++) {
             atoms[i].x = Vec::Zero();
@@ -234,12 +253,18 @@ class AtomVec : public virtual AtomGroup {
         if (dev_newer && sz)
             parm_b200::check(parm_download_atoms(ctx, PARM_ALL, atoms[0].x.data(), atoms[0].v.data(), atoms[0].a.data(),
                                                  atoms[0].f.data(), &atoms[0].m, sizeof(Atom), sizeof(Atom)));
+        if (dev_newer && check_views) mirror_sum = checksum();
         dev_newer = false;
     }
     void sync_to_device() const {
-        if (host_dirty && sz)
+        if (!host_dirty && !dev_newer && check_views && sz && checksum() != mirror_sum)
+            throw std::logic_error("AtomVec: the host mirror changed without operator[] / get_id() / touch_host(): an Atom& or "
+                                   "AtomID kept across a device operation was written through (parm/box.hpp, STORED REFERENCES)");
+        if (host_dirty && sz) {
             parm_b200::check(parm_upload_atoms(ctx, PARM_ALL, atoms[0].x.data(), atoms[0].v.data(), atoms[0].a.data(),
                                                atoms[0].f.data(), &atoms[0].m, sizeof(Atom), sizeof(Atom)));
+            if (check_views) mirror_sum = checksum();
+        }
         host_dirty = false;
     }
     // called by every facade class before it launches device work
@@ -254,6 +279,9 @@ class AtomVec : public virtual AtomGroup {
         host_dirty = true;
     }
 
+    // read-only access: refreshes the mirror if the device is ahead, but does NOT mark it modified, so that a read
+    // followed by a timestep() does not upload the whole array again (operator[] has to assume a write)
+    const Atom &read(cuint n) const { sync_to_host(); return atoms[n]; }
     AtomVec &vec() { return *this; }
     inline Atom &operator[](cuint n) { touch_host(); return atoms[n]; }
     inline Atom &operator[](cuint n) const { touch_host(); return atoms[n]; }
