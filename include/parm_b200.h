@@ -82,6 +82,19 @@ int parm_download_atoms(parm_ctx *ctx, unsigned mask, double *x, double *v, doub
 int parm_host_register(void *ptr, size_t bytes);
 int parm_host_unregister(void *ptr);
 int parm_sync(parm_ctx *ctx);
+
+/* Asynchronous trajectory frame (the XYZ output of LJatoms.cpp:130-158 and pyparm/xyzfile.py:7-76 without stopping the
+ * run): _begin gathers x and/or v (mask of PARM_X | PARM_V) by AtomVec index on the context's stream and starts their
+ * device->host copy on a second stream; parm_integ_timestep calls issued afterwards overlap that copy. _wait blocks
+ * until the frame has arrived and copies it to x / v (host, n * ndim doubles each, either may be NULL). One frame at a
+ * time per context. */
+int parm_snapshot_begin(parm_ctx *ctx, unsigned mask);
+int parm_snapshot_wait(parm_ctx *ctx, double *x, double *v);
+
+/* Grid::get_loc (trackers.cpp:192-219, class Grid trackers.hpp:227-309) of every atom, computed on the device from the
+ * resident positions: loc[i] = cell of AtomVec index i for `widths` (ndim entries) divisions per axis; the facade
+ * builds Grid::gridlocs from it. */
+int parm_grid_locs(parm_ctx *ctx, const uint32_t *widths, uint32_t *loc);
 /* the CUDA stream (cudaStream_t) every kernel of this context is launched on, so a caller
  * can bracket calls with its own CUDA events */
 int parm_get_stream(parm_ctx *ctx, void **cuda_stream);

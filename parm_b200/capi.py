@@ -43,6 +43,9 @@ SIGNATURES = {
     "parm_host_register": (C.c_int, [vp, C.c_size_t]),
     "parm_host_unregister": (C.c_int, [vp]),
     "parm_sync": (C.c_int, [vp]),
+    "parm_snapshot_begin": (C.c_int, [vp, C.c_uint]),
+    "parm_snapshot_wait": (C.c_int, [vp, dp, dp]),
+    "parm_grid_locs": (C.c_int, [vp, u32p, u32p]),
     "parm_get_stream": (C.c_int, [vp, vpp]),
     "parm_profile_enable": (C.c_int, [vp, C.c_int]),
     "parm_profile_read": (C.c_int, [vp, dp, u64p]),

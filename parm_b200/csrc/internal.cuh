@@ -101,6 +101,13 @@ struct parm_ctx {
     std::vector<parm_nlist *> nlists;
     std::vector<parm_inter *> inters;
     int num_sms;
+    // asynchronous trajectory frames (csrc/snapshot.cu)
+    cudaStream_t snap_stream;
+    cudaEvent_t snap_ready, snap_done;
+    double *d_snap, *h_snap;   // device staging / pinned host copy of one frame (x and v by AtomVec index)
+    size_t snap_doubles;
+    unsigned snap_mask;
+    bool snap_pending, snap_init;
     bool tile_prep_external;   // the caller refreshes prel itself (sharded step: owned slots after K1, ghosts after the exchange)
     // optional per-class CUDA-event timing
     bool prof_on;
@@ -373,6 +380,7 @@ int parm_inter_regather(parm_inter *inter);          // re-gather per-slot speci
 int parm_inter_launch_forces(parm_inter *inter, unsigned want, bool accumulate, double *d_out /*device, 13 doubles*/,
                              const int *abort_flag = nullptr, uint32_t first = 0, uint32_t count = 0xffffffffu);
 int parm_ctx_ensure_red(parm_ctx *ctx, size_t doubles);
+void parm_snapshot_free(parm_ctx *c); // csrc/snapshot.cu
 // cell-tile path (csrc/tile.cu)
 int parm_tile_plan_enqueue(parm_nlist *nl);   // chunk table from the cell structure (async, before the build's sync)
 int parm_tile_plan_fetch(parm_nlist *nl);     // queue the device->host copy of the plan summary (before that sync)

@@ -116,6 +116,7 @@ extern "C" int parm_ctx_destroy(parm_ctx *c) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     parm_shard_destroy(c);
+    parm_snapshot_free(c);
     void *ptrs[] = {c->pos, c->pos_alt, c->v, c->a, c->f, c->v_alt, c->a_alt, c->f_alt, c->order, c->order_alt,
                     c->slot_of, c->d_stage, c->d_red, c->ghost, c->ghost_alt};
     for (void *p : ptrs)

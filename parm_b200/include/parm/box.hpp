@@ -279,6 +279,19 @@ class AtomVec : public virtual AtomGroup {
         host_dirty = true;
     }
 
+    // Asynchronous trajectory frame (the writefile() of LJatoms.cpp:130-158 without stalling the run): snapshot_begin()
+    // starts the device->host copy of x (and v) on a second stream, timestep() calls made before snapshot_wait()
+    // overlap it; snapshot_wait() fills x[i], v[i] (AtomVec order; v may be NULL).
+    void snapshot_begin(bool velocities = true) { parm_b200::check(parm_snapshot_begin(device(false), PARM_X | (velocities ? PARM_V : 0u))); }
+    void snapshot_wait(Vec *x, Vec *v = NULL) {
+        vector<double> bx((size_t)sz * NDIM + 1), bv((size_t)sz * NDIM + 1);
+        parm_b200::check(parm_snapshot_wait(ctx, x ? bx.data() : NULL, v ? bv.data() : NULL));
+        for (uint i = 0; i < sz; i++)
+            for (uint d = 0; d < NDIM; d++) {
+                if (x) x[i][d] = bx[(size_t)i * NDIM + d];
+                if (v) v[i][d] = bv[(size_t)i * NDIM + d];
+            }
+    }
     // read-only access: refreshes the mirror if the device is ahead, but does NOT mark it modified, so that a read
     // followed by a timestep() does not upload the whole array again (operator[] has to assume a write)
     const Atom &read(cuint n) const { sync_to_host(); return atoms[n]; }

@@ -2,6 +2,7 @@
 // 157-214). The list lives on the device (skin-drift trigger + cell-list build, see
 // parm_b200/csrc/nlist.cu); `begin()/end()/get(i)` materialise the reference's `vector<IDPair>`
 // (same pair set, same (i asc, j<i asc) order) on demand for host-side consumers.
+#include <set>
 #include "box.hpp"
 
 #ifndef PARM_B200_TRACKERS_H
@@ -105,6 +106,111 @@ class NeighborList : public StateTracker {
     // device-side handles for the other facade classes
     parm_nlist *handle() { flush(); return nl; }
     sptr<AtomVec> atomvec() { return atoms; }
+};
+
+// Grid (trackers.hpp:227-309, trackers.cpp:97-219): cells no narrower than any atom; the atoms of a cell and of its
+// neighbouring cells are an atom's candidate neighbours. make_grid() bins every atom ON THE DEVICE from the resident
+// positions (parm_grid_locs: Grid::get_loc for all atoms at once, 4 bytes per atom come back) and keeps the cells as
+// sorted index vectors (the reference's set<AtomID> orders by index as well). The event-driven collections that drive
+// time_to_edge / GridIterator step by step are out of scope; all_pairs() / all_pairs(AtomID)
+// give the same sets as the reference's iterators.
+class Grid {
+   public:
+    sptr<OriginBox> box;
+    sptr<AtomVec> atoms;
+    flt minwidth, goalwidth;
+    uint widths[NDIM];
+    vector<vector<uint> > gridlocs;  // atoms (AtomVec indices, ascending) of every cell
+    vector<uint32_t> locs;           // cell of every atom, as of the last make_grid()
+
+    Grid(sptr<OriginBox> box, sptr<AtomVec> atoms, const uint width = 1) : box(box), atoms(atoms), minwidth(-1), goalwidth(-1) {
+        for (uint d = 0; d < NDIM; d++) widths[d] = width;
+    }
+    Grid(sptr<OriginBox> box, sptr<AtomVec> atoms, vector<uint> width) : box(box), atoms(atoms), minwidth(-1), goalwidth(-1) {
+        assert(width.size() == NDIM);
+        for (uint d = 0; d < NDIM; d++) widths[d] = width[d];
+    }
+    Grid(sptr<OriginBox> box, sptr<AtomVec> atoms, const flt minwidth, const flt goalwidth)
+        : box(box), atoms(atoms), minwidth(minwidth), goalwidth(goalwidth) {
+        for (uint d = 0; d < NDIM; d++) widths[d] = 1;
+        optimize_widths();
+    }
+    void optimize_widths() {  // trackers.cpp:168-190
+        if (minwidth <= 0) return;
+        flt wpa = pow(box->V() * goalwidth / atoms->size(), OVERNDIM);
+        if (wpa < minwidth) wpa = minwidth;
+        Vec b = box->box_shape();
+        bool small = false;
+        for (uint d = 0; d < NDIM; d++) {
+            widths[d] = (uint)floor(b[d] / wpa);
+            small = small || widths[d] < 3;
+        }
+        if (small)
+            for (uint d = 0; d < NDIM; d++) widths[d] = 1;
+    }
+    uint numcells(uint i) { assert(i < NDIM); return widths[i]; }
+    uint numcells() {
+        uint k = 1;
+        for (uint d = 0; d < NDIM; d++) k *= widths[d];
+        return k;
+    }
+    void make_grid() {
+        box->attach(atoms->context());
+        uint32_t w[3] = {1, 1, 1};
+        for (uint d = 0; d < NDIM; d++) w[d] = widths[d];
+        locs.assign(atoms->size() ? atoms->size() : 1, 0);
+        parm_b200::check(parm_grid_locs(atoms->device(false), w, locs.data()));
+        locs.resize(atoms->size());
+        gridlocs.assign(numcells(), vector<uint>());
+        for (uint i = 0; i < atoms->size(); i++) gridlocs[locs[i]].push_back(i);
+    }
+    uint get_loc(Vec v, Vec bsize) {  // trackers.cpp:192-206
+        v = vec_mod(v - bsize / 2., bsize) + bsize / 2;
+        uint k[3] = {0, 0, 0};
+        for (uint d = 0; d < NDIM; d++) {
+            k[d] = (uint)floor(v[d] * widths[d] / bsize[d]);
+            if (k[d] == widths[d]) k[d] = 0;
+        }
+        return NDIM == 3 ? (k[2] * widths[1] + k[1]) * widths[0] + k[0] : k[1] * widths[0] + k[0];
+    }
+    vector<uint> neighbors(uint i) {  // trackers.cpp:125-166: the 3^NDIM cells around (and including) cell i, periodic
+        vector<uint> v;
+        uint w0 = widths[0], w1 = widths[1];
+        uint x = i % w0, y = (i / w0) % w1, z = NDIM == 3 ? i / (w0 * w1) : 0;
+        for (int dz = (NDIM == 3 ? -1 : 0); dz <= (NDIM == 3 ? 1 : 0); dz++)
+            for (int dy = -1; dy <= 1; dy++)
+                for (int dx = -1; dx <= 1; dx++) {
+                    uint zz = NDIM == 3 ? (uint)((int)(z + widths[NDIM - 1]) + dz) % widths[NDIM - 1] : 0;
+                    uint yy = (uint)((int)(y + w1) + dy) % w1, xx = (uint)((int)(x + w0) + dx) % w0;
+                    v.push_back((zz * w1 + yy) * w0 + xx);
+                }
+        return v;
+    }
+    vector<AtomID> all_pairs(AtomID a) {
+        vector<AtomID> out;
+        std::set<uint> seen;
+        vector<uint> nb = neighbors(locs[a.n()]);
+        for (size_t c = 0; c < nb.size(); c++) {
+            if (!seen.insert(nb[c]).second) continue;  // (an axis with fewer than 3 cells lists a cell more than once)
+            for (size_t k = 0; k < gridlocs[nb[c]].size(); k++)
+                if (gridlocs[nb[c]][k] != a.n()) out.push_back(atoms->get_id(gridlocs[nb[c]][k]));
+        }
+        return out;
+    }
+    vector<IDPair> all_pairs() {
+        std::set<std::pair<uint, uint> > ps;
+        for (uint c = 0; c < gridlocs.size(); c++) {
+            vector<uint> nb = neighbors(c);
+            for (size_t q = 0; q < nb.size(); q++)
+                for (size_t a = 0; a < gridlocs[c].size(); a++)
+                    for (size_t b = 0; b < gridlocs[nb[q]].size(); b++)
+                        if (gridlocs[nb[q]][b] < gridlocs[c][a]) ps.insert(std::make_pair(gridlocs[c][a], gridlocs[nb[q]][b]));
+        }
+        vector<IDPair> out;
+        for (std::set<std::pair<uint, uint> >::iterator it = ps.begin(); it != ps.end(); ++it)
+            out.push_back(IDPair(atoms->get_id(it->first), atoms->get_id(it->second)));
+        return out;
+    }
 };
 
 #endif

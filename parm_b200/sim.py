@@ -117,6 +117,9 @@ class Atom:
             raise AttributeError(k)
         self._av._host()[k][self._i] = val
 
+    def n(self):  # iterating an AtomVec yields objects that also serve as AtomID (sim.i AtomVec.__iter__ -> get_id)
+        return self._i
+
 
 class AtomID:
     def __init__(self, av, n):
@@ -197,6 +200,21 @@ class AtomVec:
 
     def get_id(self, n):
         return AtomID(self, n)
+
+    # -- asynchronous trajectory frames (parm_snapshot_begin / _wait; pyparm/xyzfile.py, LJatoms.cpp:130-158) -----------
+    def snapshot_begin(self, velocities=True):
+        """Start copying the current x (and v) to the host on a second stream; timestep() calls made before
+        snapshot_wait() overlap the copy."""
+        self._device_op(modifies=False)
+        call("parm_snapshot_begin", self._h, capi.X | (capi.V if velocities else 0))
+        self._snap_v = bool(velocities)
+
+    def snapshot_wait(self):
+        """(x, v) of the frame started by snapshot_begin(), arrays of shape (n, ndim); v is None without velocities."""
+        x = np.empty((self.n, self.ndim))
+        v = np.empty((self.n, self.ndim)) if self._snap_v else None
+        call("parm_snapshot_wait", self._h, _dptr(x), _dptr(v) if v is not None else None)
+        return x, v
 
     x = property(lambda self: self._host()["x"])
     v = property(lambda self: self._host()["v"])
@@ -353,6 +371,87 @@ class NeighborList:
         nch, mt, wide = C.c_uint32(0), C.c_uint32(0), C.c_uint32(0)
         call("parm_nlist_tile_stats", self._h, C.byref(act), C.byref(nch), C.byref(mt), C.byref(wide))
         return bool(act.value), nch.value, mt.value, wide.value
+
+
+class Grid:
+    """Grid (trackers.hpp:227-309): cells no narrower than any atom; the atoms of the same and of the neighbouring cells
+    are an atom's candidate neighbours. get_loc (trackers.cpp:192-219) runs on the device for all atoms at once
+    (parm_grid_locs); the per-cell lists are assembled here from the 4-byte cell indices."""
+
+    def __init__(self, box, atoms, width_or_minwidth=1, goalwidth=None):
+        self.box, self.atoms = box, atoms
+        nd = atoms.ndim
+        self.minwidth, self.goalwidth = -1.0, -1.0
+        if goalwidth is not None:  # Grid(box, atoms, minwidth, goalwidth)
+            self.minwidth, self.goalwidth = float(width_or_minwidth), float(goalwidth)
+            self.widths = [1] * nd
+            self.optimize_widths()
+        elif np.ndim(width_or_minwidth) == 0:
+            self.widths = [int(width_or_minwidth)] * nd
+        else:
+            self.widths = [int(w) for w in width_or_minwidth]
+        self.gridlocs = []
+
+    def optimize_widths(self):  # trackers.cpp:168-190
+        if self.minwidth <= 0:
+            return
+        nd = self.atoms.ndim
+        wpa = (self.box.V() * self.goalwidth / self.atoms.size()) ** (1.0 / nd)
+        wpa = max(wpa, self.minwidth)
+        self.widths = [int(np.floor(b / wpa)) for b in self.box.box_shape()]
+        if min(self.widths) < 3:
+            self.widths = [1] * nd
+
+    def numcells(self, i=None):
+        return int(np.prod(self.widths)) if i is None else self.widths[i]
+
+    def make_grid(self):
+        self.box._attach(self.atoms)
+        self.atoms._device_op(modifies=False)
+        w = np.ascontiguousarray(self.widths + [1] * (3 - len(self.widths)), dtype=np.uint32)
+        loc = np.empty(self.atoms.n, np.uint32)
+        call("parm_grid_locs", self.atoms._h, w.ctypes.data_as(capi.u32p), loc.ctypes.data_as(capi.u32p))
+        self.locs = loc
+        order = np.argsort(loc, kind="stable")
+        bounds = np.searchsorted(loc[order], np.arange(self.numcells() + 1))
+        self.gridlocs = [order[bounds[c]:bounds[c + 1]].tolist() for c in range(self.numcells())]  # sets of AtomID, by index
+
+    def get_loc(self, v, bsize=None):
+        bsize = self.box.box_shape() if bsize is None else np.asarray(bsize, dtype=np.float64)
+        v = np.asarray(v, dtype=np.float64)
+        import math
+        r = np.array([math.remainder(v[d] - bsize[d] / 2.0, bsize[d]) for d in range(len(bsize))]) + bsize / 2.0
+        k = [int(np.floor(r[d] * self.widths[d] / bsize[d])) for d in range(len(bsize))]
+        k = [0 if k[d] == self.widths[d] else k[d] for d in range(len(bsize))]
+        return (k[2] * self.widths[1] + k[1]) * self.widths[0] + k[0] if len(bsize) == 3 else k[1] * self.widths[0] + k[0]
+
+    def neighbors(self, i):  # trackers.cpp:125-166 (the cell itself included; duplicates when an axis has < 3 cells)
+        w = self.widths
+        if len(w) == 2:
+            x, y = i % w[0], i // w[0]
+            return [((y + dy) % w[1]) * w[0] + (x + dx) % w[0] for dy in (-1, 0, 1) for dx in (-1, 0, 1)]
+        x, y, z = i % w[0], (i // w[0]) % w[1], i // (w[0] * w[1])
+        return [(((z + dz) % w[2]) * w[1] + (y + dy) % w[1]) * w[0] + (x + dx) % w[0]
+                for dz in (-1, 0, 1) for dy in (-1, 0, 1) for dx in (-1, 0, 1)]
+
+    def all_pairs(self, a=None):
+        """all_pairs(): every (i, j), j < i ... of neighbouring cells, each once; all_pairs(n): the candidates of atom n."""
+        if a is not None:
+            n = a.n() if hasattr(a, "n") else int(a)
+            out = []
+            for c in dict.fromkeys(self.neighbors(int(self.locs[n]))):
+                out.extend(j for j in self.gridlocs[c] if j != n)
+            return out
+        pairs = set()
+        for c, members in enumerate(self.gridlocs):
+            if not members:
+                continue
+            for c2 in dict.fromkeys(self.neighbors(c)):
+                for i in members:
+                    for j in self.gridlocs[c2]:
+                        if j < i:
+                            pairs.add((i, j))
+        return sorted(pairs)
 
 
 # ---- per-atom parameter structs; .p follows the table in include/parm_b200.h (parm_inter_set_params_ex) ----
