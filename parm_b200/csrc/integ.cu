@@ -116,6 +116,74 @@ k_verlet2(const double4 *__restrict__ pos, double *__restrict__ v, double *__res
     }
 }
 
+// ---- K3 of step s fused with K1 of step s+1 (inside a multi-step timestep(n) call) ----------------------------------
+// One pass over the atoms instead of two: reads f, v, x (+m), lastlocs and writes a, v, x (and the image-resolved copy
+// of x for the pair kernel): 224 bytes per atom against 328 for K3 followed by K1. `abort_flag` is the guard of step s
+// (the decision of step s-1), `next_flag` the decision of step s itself -- taken by K1 of step s, i.e. before this
+// kernel started: when it asks for a rebuild only the K3 half runs, the host rebuilds and starts step s+1 with a plain
+// K1. Same expressions, in the same order, as k_verlet2 followed by k_verlet1: bit-identical trajectories.
+template <int D, bool PREL>
+__global__ void __launch_bounds__(I_BLOCK)
+k_verlet21(double4 *__restrict__ pos, double *__restrict__ v, double *__restrict__ a, const double *__restrict__ f, uint32_t n,
+           uint32_t npad, double dt, double hdt2, double hdt, const int *__restrict__ abort_flag, const int *__restrict__ next_flag,
+           const double *__restrict__ xlast, double skin, double *d_top2, unsigned int *counter, NlistFlags *dflags,
+           NlistFlags *hflags, int *d_slot, int *h_slot, const PrelOut R) {
+    if (abort_flag && *abort_flag) return;
+    const bool go = !(*next_flag);
+    double b1 = 0.0, b2 = 0.0;
+    for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < n; s += gridDim.x * blockDim.x) {
+        double4 p = pos[s];
+        double fd[D], vd[D], xl[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+        for (int d = 0; d < D; d++) {
+            fd[d] = f[(size_t)d * npad + s];
+            vd[d] = v[(size_t)d * npad + s];
+        }
+        float4 im = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (go) {
+            xl[0] = xlast[s];
+            xl[1] = xlast[npad + s];
+            xl[2] = xlast[2 * (size_t)npad + s];
+            if (PREL) im = R.img[s];
+        }
+        if (frozen_le(p.w)) { // K3: a = 0; K1: v = 0, position untouched
+#pragma unroll
+            for (int d = 0; d < D; d++) {
+                a[(size_t)d * npad + s] = 0.0;
+                if (go) v[(size_t)d * npad + s] = 0.0;
+            }
+        } else {
+            double x[3] = {p.x, p.y, p.z};
+#pragma unroll
+            for (int d = 0; d < D; d++) {
+                const size_t q = (size_t)d * npad + s;
+                const double ad = __ddiv_rn(fd[d], p.w);                    // K3: a = f / m
+                a[q] = ad;
+                double vn = __dadd_rn(vd[d], __dmul_rn(ad, hdt));           //     v += a dt/2
+                if (go) {
+                    x[d] = __dadd_rn(x[d], __dadd_rn(__dmul_rn(vn, dt), __dmul_rn(ad, hdt2))); // K1: x += v dt + a dt^2/2
+                    vn = __dadd_rn(vn, __dmul_rn(ad, hdt));                                    //     v += a dt/2
+                }
+                v[q] = vn;
+            }
+            if (go) {
+                p.x = x[0];
+                p.y = x[1];
+                if (D == 3) p.z = x[2];
+                pos[s] = p;
+            }
+        }
+        if (go) {
+            if (PREL) {
+                R.xy[s] = make_double2(fma(-(double)im.x, R.L[0], p.x), fma(-(double)im.y, R.L[1], p.y));
+                R.z[s] = fma(-(double)im.z, R.L[2], p.z);
+            }
+            top2_push(b1, b2, drift_dist(p, xl[0], xl[1], xl[2]));
+        }
+    }
+    if (go) drift_finish(b1, b2, skin, d_top2, counter, dflags, hflags, d_slot, h_slot);
+}
+
 struct SolConst {
     double dt, c0, c1dt, c2dtdt, dtc1mc2, dtc2, x11, x21, x22, desT, damping;
 };
@@ -422,15 +490,23 @@ extern "C" int parm_integ_inject_noise(parm_integ *g, const double *z, size_t le
 // word). abort_flag (device, may be NULL) is the decision word of the PREVIOUS step: when it is set the
 // kernels of this step return immediately, so a step can be enqueued before the host has seen whether
 // its predecessor asked for a rebuild.
-static int enqueue_step_core(parm_integ *g, uint64_t step, const int *abort_flag, int slot);
-static int enqueue_step(parm_integ *g, uint64_t step, const int *abort_flag, int slot) {
+// k1_done: the first half of this step already ran inside the previous step's fused K3+K1 kernel. fuse_next: end this
+// step with that fused kernel (K3 of this step + K1 of the next, the latter guarded by THIS step's decision and leaving
+// the next step's decision in slot (slot + 1) % 3) instead of a plain K3. Both only for CollectionVerlet (fusable()).
+static int enqueue_step_core(parm_integ *g, uint64_t step, const int *abort_flag, int slot, bool k1_done, bool fuse_next);
+static bool fusable(const parm_integ *g) {
+    const parm_ctx *c = g->ctx;
+    const char *e = getenv("PARM_B200_FUSE_K3K1"); // (read per call: the sweeps toggle it inside one process)
+    return g->type == 0 && !g->trackers.empty() && g->stat_trackers.empty() && !c->prof_on && (e ? atoi(e) != 0 : true);
+}
+static int enqueue_step(parm_integ *g, uint64_t step, const int *abort_flag, int slot, bool k1_done = false, bool fuse_next = false) {
     if (g->type >= PARM_INTEG_DAMPED) PTRY(parm_integ_extra_enqueue(g, step, abort_flag, slot));
-    else PTRY(enqueue_step_core(g, step, abort_flag, slot));
+    else PTRY(enqueue_step_core(g, step, abort_flag, slot, k1_done, fuse_next));
     // update_trackers() ends every step: the statistics trackers follow the NeighborList
     for (parm_tracker *t : g->stat_trackers) PTRY(parm_tracker_enqueue_update(t, abort_flag));
     return 0;
 }
-static int enqueue_step_core(parm_integ *g, uint64_t step, const int *abort_flag, int slot) {
+static int enqueue_step_core(parm_integ *g, uint64_t step, const int *abort_flag, int slot, bool k1_done, bool fuse_next) {
     parm_ctx *c = g->ctx;
     const uint32_t n = parm_owned(c); // ghost copies are never integrated
     parm_nlist *nl = g->trackers.empty() ? nullptr : g->trackers[0];
@@ -459,7 +535,9 @@ static int enqueue_step_core(parm_integ *g, uint64_t step, const int *abort_flag
     R.z = nl ? nl->tile.prel_z : nullptr;
     for (int d = 0; d < 3; d++) R.L[d] = c->box.L[d];
     PTRY(parm_prof_begin(c, PARM_PROF_INTEG1));
-    if (g->type == 0) {
+    if (k1_done) {
+        // x(t+dt), v(t+dt/2), the drift reduction (and prel) of this step were produced by the previous step's fused kernel
+    } else if (g->type == 0) {
         const double hdt2 = dt * dt / 2, hdt = dt / 2;
         if (c->D == 3) {
             if (k1_prel) k_verlet1<3, true, true><<<grid1, I_BLOCK, 0, c->stream>>>(c->pos, c->v, c->a, n, c->npad, dt, hdt2, hdt, DRIFTARGS, R);
@@ -498,8 +576,7 @@ static int enqueue_step_core(parm_integ *g, uint64_t step, const int *abort_flag
         }
 #undef S1ARGS
     }
-#undef DRIFTARGS
-    CK_LAUNCH(c);
+    if (!k1_done) CK_LAUNCH(c);
     PTRY(parm_prof_end(c));
 
     PTRY(parm_prof_begin(c, PARM_PROF_FORCE));
@@ -542,7 +619,22 @@ static int enqueue_step_core(parm_integ *g, uint64_t step, const int *abort_flag
     PTRY(parm_prof_end(c));
 
     PTRY(parm_prof_begin(c, PARM_PROF_INTEG2));
-    if (g->type == 0) {
+    if (g->type == 0 && fuse_next && nl) {
+        // K3 of this step + K1 of the next in one pass; the next step's decision goes to slot (slot + 1) % 3 (sharded:
+        // folded from the all-gather by the next step's communication phase, as for a plain K1)
+        const int nslot = (slot + 1) % 3;
+        int *d_slot2 = !c->sh.on ? nl->d_slot + nslot : nullptr, *h_slot2 = !c->sh.on ? nl->h_slot + nslot : nullptr;
+        const double hdt2 = dt * dt / 2, hdt = dt / 2;
+#define F21ARGS c->pos, c->v, c->a, c->f, n, c->npad, dt, hdt2, hdt, abort_flag, nl->d_slot + slot, nl->xlast, nl->skin, nl->d_top2, \
+                nl->d_counter, nl->d_flags, nl->h_flags, d_slot2, h_slot2, R
+        if (c->D == 3) {
+            if (k1_prel) k_verlet21<3, true><<<grid1, I_BLOCK, 0, c->stream>>>(F21ARGS);
+            else k_verlet21<3, false><<<grid1, I_BLOCK, 0, c->stream>>>(F21ARGS);
+        } else {
+            k_verlet21<2, false><<<grid1, I_BLOCK, 0, c->stream>>>(F21ARGS);
+        }
+#undef F21ARGS
+    } else if (g->type == 0) {
         if (c->D == 3) k_verlet2<3><<<grid, I_BLOCK, 0, c->stream>>>(c->pos, c->v, c->a, c->f, n, c->npad, dt / 2, abort_flag);
         else k_verlet2<2><<<grid, I_BLOCK, 0, c->stream>>>(c->pos, c->v, c->a, c->f, n, c->npad, dt / 2, abort_flag);
     } else {
@@ -551,6 +643,7 @@ static int enqueue_step_core(parm_integ *g, uint64_t step, const int *abort_flag
     }
     CK_LAUNCH(c);
     PTRY(parm_prof_end(c));
+#undef DRIFTARGS
     return 0;
 }
 
@@ -593,30 +686,39 @@ extern "C" int parm_integ_timestep(parm_integ *g, int nsteps) {
     // The host runs one step ahead of the decisions: step s+1 is enqueued (guarded by the decision word
     // of step s) before the host waits for step s. A rebuild request makes the guarded kernels no-ops;
     // the host then rebuilds and enqueues step s+1 again.
-    PTRY(enqueue_step(g, g->steps, nullptr, 0));
+    // Decision slots are used round robin modulo 3: a fused K3+K1 kernel reads the slots of the two previous steps and
+    // writes the third. With CollectionVerlet every step but the last of the call ends with that fused kernel.
+    const bool fuse = fusable(g);
+    int cur = 0; // slot of step s
+    PTRY(enqueue_step(g, g->steps, nullptr, cur, false, fuse && nsteps > 1));
     CK(cudaEventRecord(g->ev[0], c->stream));
     for (int s = 0; s < nsteps; s++) {
-        const int p = s & 1;
+        const int p = s & 1, nxt = (cur + 1) % 3;
         // (per-class event timing counts launches, so it runs without speculation)
         // (statistics trackers keep host-side step counters: their steps are never enqueued speculatively)
         const bool spec = speculate && !c->prof_on && s + 1 < nsteps && !nl->ignorechanged && g->stat_trackers.empty();
+        const bool fuse_after_next = fuse && s + 2 < nsteps; // step s+1 ends with a fused kernel as well
         if (spec) {
-            PTRY(enqueue_step(g, g->steps + 1, nl->d_slot + p, p ^ 1));
+            // step s+1, guarded by step s's decision; its K1 ran inside step s's fused kernel when there was one
+            PTRY(enqueue_step(g, g->steps + 1, nl->d_slot + cur, nxt, fuse, fuse_after_next));
             CK(cudaEventRecord(g->ev[p ^ 1], c->stream));
         }
         CK(cudaEventSynchronize(g->ev[p]));
-        const bool rebuild = nl->ignorechanged || nl->h_slot[p] != 0;
+        const bool rebuild = nl->ignorechanged || nl->h_slot[cur] != 0;
         g->steps++;
         if (rebuild) {
             PTRY(parm_nlist_rebuild(nl)); // synchronises the stream: the guarded kernels of step s+1 have returned
             g->rebuilds++;
-            CK(cudaMemsetAsync(nl->d_slot, 0, 2 * sizeof(int), c->stream));
-            nl->h_slot[0] = nl->h_slot[1] = 0;
+            CK(cudaMemsetAsync(nl->d_slot, 0, 4 * sizeof(int), c->stream));
+            nl->h_slot[0] = nl->h_slot[1] = nl->h_slot[2] = nl->h_slot[3] = 0;
         }
         if (s + 1 < nsteps && (rebuild || !spec)) {
-            PTRY(enqueue_step(g, g->steps, nullptr, p ^ 1));
+            // after a rebuild the fused kernel only did its K3 half: step s+1 starts with a plain K1. Without speculation
+            // and without a rebuild the K1 half did run.
+            PTRY(enqueue_step(g, g->steps, nullptr, nxt, fuse && !rebuild, fuse_after_next));
             CK(cudaEventRecord(g->ev[p ^ 1], c->stream));
         }
+        cur = nxt;
     }
     return 0;
 }

@@ -275,7 +275,7 @@ struct parm_nlist {
     unsigned int *d_counter;
     NlistFlags *d_flags;
     NlistFlags *h_flags; // pinned
-    int *d_slot, *h_slot; // [2] per-step rebuild decisions (device / pinned): see parm_integ_timestep
+    int *d_slot, *h_slot; // [3 (+1)] per-step rebuild decisions (device / pinned), used round robin: see parm_integ_timestep
     uint64_t rebuilds;
 };
 

@@ -837,10 +837,10 @@ extern "C" int parm_nlist_create(parm_ctx *c, double skin, parm_nlist **out) {
     CK(cudaMemsetAsync(nl->d_flags, 0, sizeof(NlistFlags), c->stream));
     CK(cudaHostAlloc(&nl->h_flags, sizeof(NlistFlags), cudaHostAllocMapped));
     memset(nl->h_flags, 0, sizeof(NlistFlags));
-    CK(cudaMalloc(&nl->d_slot, 2 * sizeof(int)));
-    CK(cudaMemsetAsync(nl->d_slot, 0, 2 * sizeof(int), c->stream));
-    CK(cudaHostAlloc(&nl->h_slot, 2 * sizeof(int), cudaHostAllocMapped));
-    nl->h_slot[0] = nl->h_slot[1] = 0;
+    CK(cudaMalloc(&nl->d_slot, 4 * sizeof(int)));
+    CK(cudaMemsetAsync(nl->d_slot, 0, 4 * sizeof(int), c->stream));
+    CK(cudaHostAlloc(&nl->h_slot, 4 * sizeof(int), cudaHostAllocMapped));
+    nl->h_slot[0] = nl->h_slot[1] = nl->h_slot[2] = nl->h_slot[3] = 0;
     // all atoms start as non-members
     std::vector<double> neg(nidp, -1.0);
     CK(cudaMemcpyAsync(nl->d_diam_id, neg.data(), nidp * 8, cudaMemcpyHostToDevice, c->stream));

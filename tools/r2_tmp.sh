@@ -1,1 +1,1 @@
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29533 tests/mgpu_check.py 2>&1 | grep -v Warning | grep -E "mgpu ok|Error|error|assert|MGPU" | head -20
+timeout 900 python -m pytest tests/test_gpu_pyparm.py tests/test_gpu_facade.py -m gpu -x -q 2>&1 | tail -15
