@@ -381,21 +381,24 @@ k_tile_localize_masks(const TileChunk *__restrict__ chunks, MaskOut mo, const ui
     if (lost) atomicOr(&info->bad, 2u);
 }
 
-// Fast path of the above for groups of at most 4 * MAXQ candidate blocks (nbmax of the build): the lane takes blocks tl,
-// tl + 4, ... (the populous blocks of the centre columns are dealt round the team), compacts its non-empty masks into
-// shared memory and walks all their set bits in ONE flat loop, so the lanes of a warp only re-converge at the end of the
-// row: the warp runs max-over-lanes(entries) iterations instead of the sum of the per-block maxima. Row order: lane 0's
-// blocks in block order, then lane 1's, ... -- another fixed order of the same set than the classic build's (the pair
-// kernel's sums are deterministic either way; they differ from the classic order in the last bits only).
+// Fast path of the above for groups of at most 4 * MAXQ candidate blocks (nbmax of the build). The four lanes of a team
+// load the masks of contiguous quarters of the candidate blocks into team-shared memory together with the exclusive
+// prefix of their popcounts; then the ROW ENTRIES, not the blocks, are dealt out: lane tl produces entries
+// [tl T/4, (tl+1) T/4) of the T-entry row, starting in the middle of whatever block holds its first entry, in ONE flat
+// loop over set bits. Every lane of the warp therefore runs the same ~28 iterations (the populous blocks of the centre
+// columns no longer make one lane the straggler), and the row keeps the block order of the classic build, so the pair
+// kernel's sums are bit-identical to it.
 template <int MAXQ>
 __global__ void __launch_bounds__(TILE_NT)
 k_tile_localize_masks_flat(const TileChunk *__restrict__ chunks, MaskOut mo, const uint32_t *__restrict__ cell_id_sorted, uint32_t nc2,
                            uint32_t gpc, uint32_t zg, const uint32_t *__restrict__ cnt, uint32_t kmax, uint16_t *__restrict__ rows16,
                            TileInfo *info) {
+    constexpr uint32_t NB = 4 * MAXQ, NTEAMS = TILE_NT / 4;
     extern __shared__ __align__(16) uint16_t s_rows[]; // [TILE_NT / 4][kmax + 8]
     __shared__ uint4 s_tab[9];
     __shared__ uint32_t s_ntile;
-    __shared__ uint32_t s_mk[MAXQ * TILE_NT], s_bs[MAXQ * TILE_NT];
+    __shared__ uint32_t s_mk[NTEAMS][NB + 1], s_bs[NTEAMS][NB + 1]; // (+1: the teams of a warp start in different banks)
+    __shared__ uint16_t s_pre[NTEAMS][NB + 2];
     const TileChunk *C = chunks + blockIdx.x;
     if (threadIdx.x < 9) {
         const int kc = 2 * threadIdx.x;
@@ -419,44 +422,68 @@ k_tile_localize_masks_flat(const TileChunk *__restrict__ chunks, MaskOut mo, con
         if (my) {
             const uint32_t cz = cell_id_sorted[s] - colcell0; // cell along the column (every atom of a chunk is in column `col`)
             grp = col * gpc + (zg == 1u ? cz : cz / zg);
-            nb = min(mo.grp_nb[grp], mo.mb_cap);
+            nb = min(min(mo.grp_nb[grp], mo.mb_cap), NB);
         }
-        // the lane's non-empty masks and their block bases, compacted into its private column of shared memory
-        uint32_t tot = 0, nq = 0;
+        // masks and block bases of the lane's contiguous quarter of the blocks -> team-shared memory, with the running
+        // number of entries before each block
+        const uint32_t nbq = (nb + 3u) >> 2, b0 = tl * nbq, b1 = min(b0 + nbq, nb);
+        uint32_t tot = 0;
         {
             uint32_t mk[MAXQ], bs[MAXQ];
 #pragma unroll
             for (int q = 0; q < MAXQ; q++) { // all loads in flight before the first use
-                // blocks tl, tl + 4, ...: the populous blocks of the centre columns are dealt round the team
-                const uint32_t b = tl + 4u * (uint32_t)q;
-                mk[q] = b < nb ? __ldg(mo.masks + (size_t)b * mo.npad + s) : 0u;
-                bs[q] = b < nb ? __ldg(mo.blk_base + (size_t)grp * mo.mb_cap + b) : 0u;
+                const uint32_t bq = b0 + (uint32_t)q;
+                mk[q] = bq < b1 ? __ldg(mo.masks + (size_t)bq * mo.npad + s) : 0u;
+                bs[q] = bq < b1 ? __ldg(mo.blk_base + (size_t)grp * mo.mb_cap + bq) : 0u;
+                tot += __popc(mk[q]);
             }
+            uint32_t incl = tot; // inclusive scan over the 4 lanes of the team
+            uint32_t y = __shfl_up_sync(0xffffffffu, incl, 1, 4);
+            if (tl >= 1) incl += y;
+            y = __shfl_up_sync(0xffffffffu, incl, 2, 4);
+            if (tl >= 2) incl += y;
+            uint32_t run = incl - tot;
 #pragma unroll
-            for (int q = 0; q < MAXQ; q++)
-                if (mk[q]) {
-                    s_mk[nq * TILE_NT + threadIdx.x] = mk[q];
-                    s_bs[nq * TILE_NT + threadIdx.x] = bs[q];
-                    nq++;
-                    tot += __popc(mk[q]);
+            for (int q = 0; q < MAXQ; q++) {
+                const uint32_t bq = b0 + (uint32_t)q;
+                if (bq < b1) {
+                    s_mk[team][bq] = mk[q];
+                    s_bs[team][bq] = bs[q];
+                    s_pre[team][bq] = (uint16_t)run;
+                    run += __popc(mk[q]);
                 }
+            }
+            tot = __shfl_sync(0xffffffffu, incl, 3, 4); // entries of the whole row (= cnt[s])
         }
-        uint32_t incl = tot; // inclusive scan over the 4 lanes of the team
-        uint32_t y = __shfl_up_sync(0xffffffffu, incl, 1, 4);
-        if (tl >= 1) incl += y;
-        y = __shfl_up_sync(0xffffffffu, incl, 2, 4);
-        if (tl >= 2) incl += y;
-        uint32_t k = incl - tot;
         __syncwarp();
-        // flat walk: (m, ty, tw, l0, n0, jz) describe the current block; an empty m pulls the next non-empty mask
-        uint32_t m = 0, ty = 0, tw = 0, l0 = 0, n0 = 0, jz = 0;
-        uint32_t q = 0;
-        for (;;) {
-            if (!m) {
-                if (q >= nq) break;
-                m = s_mk[q * TILE_NT + threadIdx.x];
-                const uint32_t base = s_bs[q * TILE_NT + threadIdx.x];
-                q++;
+        // this lane's share of the entries and the block its first entry lies in
+        const uint32_t T = min(tot, my);
+        const uint32_t k0 = (T * tl) >> 2, k1 = (T * (tl + 1u)) >> 2;
+        uint32_t k = k0, bq = 0, m = 0;
+        uint32_t ty = 0, tw = 0, l0 = 0, n0 = 0, jz = 0;
+        if (k1 > k0) {
+            uint32_t lo = 0, hi = nb; // last block whose prefix is <= k0
+            while (hi - lo > 1) {
+                const uint32_t mid = (lo + hi) >> 1;
+                if (s_pre[team][mid] <= k0) lo = mid; else hi = mid;
+            }
+            bq = lo;
+            m = s_mk[team][bq];
+            for (uint32_t skip = k0 - s_pre[team][bq]; skip; skip--) m &= m - 1u; // entries of that block that belong to the lane before
+            if (!m) { // (k0 lies at the very end of an emptyish block: move on)
+                bq++;
+                while (bq < nb && !(m = s_mk[team][bq])) bq++;
+            }
+            const uint32_t base = s_bs[team][bq];
+            const uint4 t = s_tab[min(base >> PARM_NBR_SLOT_BITS, 8u)];
+            const uint32_t jb = base & PARM_NBR_SLOT_MASK;
+            ty = t.y; tw = t.w; l0 = jb - t.x; n0 = t.w - t.y; jz = jb - t.z;
+        }
+        while (k < k1) {
+            if (!m) { // next non-empty block
+                bq++;
+                while (!(m = s_mk[team][bq])) bq++; // (there is one: k < k1 <= T)
+                const uint32_t base = s_bs[team][bq];
                 const uint4 t = s_tab[min(base >> PARM_NBR_SLOT_BITS, 8u)];
                 const uint32_t jb = base & PARM_NBR_SLOT_MASK;
                 ty = t.y; tw = t.w; l0 = jb - t.x; n0 = t.w - t.y; jz = jb - t.z;
@@ -466,22 +493,21 @@ k_tile_localize_masks_flat(const TileChunk *__restrict__ chunks, MaskOut mo, con
             const uint32_t r = l0 + bit;
             const uint32_t l = r < n0 ? ty + r : tw + (jz + bit);
             lmax = max(lmax, l); // (an index beyond the tile is not expected: the entry would be in neither run of its column)
-            if (k < kmax) buf[k] = (uint16_t)l; // (cnt = sum of the popcounts and kmax >= every cnt, parm_nlist_build_rows: never false)
-            k++;
+            buf[k++] = (uint16_t)l;
         }
         __syncwarp();
         if (valid) {
             // lane tl's vector of pass p: entries 32 p + tl, + 4, ..., + 28 of the row (sentinel index past its end)
             uint16_t *out = rows16 + (size_t)s * kmax;
-            for (uint32_t k0 = 0; k0 < mypad; k0 += 32) {
+            for (uint32_t kk = 0; kk < mypad; kk += 32) {
                 uint32_t w[4];
 #pragma unroll
                 for (int g = 0; g < 8; g += 2) {
-                    const uint32_t ka = k0 + tl + 4u * g, kb = ka + 4u;
-                    const uint32_t ea = ka < my ? buf[ka] : ntile, eb = kb < my ? buf[kb] : ntile;
+                    const uint32_t ka = kk + tl + 4u * g, kb = ka + 4u;
+                    const uint32_t ea = ka < T ? buf[ka] : ntile, eb = kb < T ? buf[kb] : ntile;
                     w[g >> 1] = ea | eb << 16;
                 }
-                *reinterpret_cast<uint4 *>(out + k0 + tl * 8) = make_uint4(w[0], w[1], w[2], w[3]);
+                *reinterpret_cast<uint4 *>(out + kk + tl * 8) = make_uint4(w[0], w[1], w[2], w[3]);
             }
         }
         __syncwarp();
@@ -731,8 +757,8 @@ int parm_tile_localize_masks(parm_nlist *nl) {
     if (nl->mask.direct) {
         // the build kernel has written rows16 itself
     } else if (nl->h_flags->nbmax <= 48) {
-        // (25 KB of static shared memory on top: the opt-in is needed from 23 KB of row buffers)
-        if (smem > 20 * 1024) CK(cudaFuncSetAttribute(k_tile_localize_masks_flat<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        // (31 KB of static shared memory on top: the opt-in is needed from 17 KB of row buffers)
+        if (smem > 14 * 1024) CK(cudaFuncSetAttribute(k_tile_localize_masks_flat<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         k_tile_localize_masks_flat<12><<<t.nchunks, TILE_NT, smem, c->stream>>>(LMARGS);
     } else {
         if (smem + 2048 > 48 * 1024) CK(cudaFuncSetAttribute(k_tile_localize_masks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
