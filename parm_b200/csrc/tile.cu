@@ -381,23 +381,25 @@ k_tile_localize_masks(const TileChunk *__restrict__ chunks, MaskOut mo, const ui
     if (lost) atomicOr(&info->bad, 2u);
 }
 
-// Fast path of the above for groups of at most 4 * MAXQ candidate blocks (nbmax of the build). The four lanes of a team
-// load the masks of contiguous quarters of the candidate blocks into team-shared memory together with the exclusive
-// prefix of their popcounts; then the ROW ENTRIES, not the blocks, are dealt out: lane tl produces entries
+// Fast path of the above for groups of at most NB = 32 candidate blocks (nbmax of the build). The four lanes of a team
+// load the masks of contiguous quarters of the candidate blocks; the NON-EMPTY ones are compacted into team-shared
+// memory together with the exclusive prefix of their popcounts and a ready-made descriptor (what turns a bit of the
+// block into a tile index). Then the ROW ENTRIES, not the blocks, are dealt out: lane tl produces entries
 // [tl T/4, (tl+1) T/4) of the T-entry row, starting in the middle of whatever block holds its first entry, in ONE flat
-// loop over set bits. Every lane of the warp therefore runs the same ~28 iterations (the populous blocks of the centre
-// columns no longer make one lane the straggler), and the row keeps the block order of the classic build, so the pair
-// kernel's sums are bit-identical to it.
-template <int MAXQ>
+// loop over set bits in which moving to the next block costs two shared-memory loads. Every lane of the warp runs the
+// same ~28 iterations (the populous blocks of the centre columns no longer make one lane the straggler), and the row
+// keeps the block order of the classic build, so the pair kernel's sums are bit-identical to it.
+#define LM_NB 32
 __global__ void __launch_bounds__(TILE_NT)
 k_tile_localize_masks_flat(const TileChunk *__restrict__ chunks, MaskOut mo, const uint32_t *__restrict__ cell_id_sorted, uint32_t nc2,
                            uint32_t gpc, uint32_t zg, const uint32_t *__restrict__ cnt, uint32_t kmax, uint16_t *__restrict__ rows16,
                            TileInfo *info) {
-    constexpr uint32_t NB = 4 * MAXQ, NTEAMS = TILE_NT / 4;
+    constexpr uint32_t NB = LM_NB, MAXQ = LM_NB / 4, NTEAMS = TILE_NT / 4;
     extern __shared__ __align__(16) uint16_t s_rows[]; // [TILE_NT / 4][kmax + 8]
     __shared__ uint4 s_tab[9];
     __shared__ uint32_t s_ntile;
-    __shared__ uint32_t s_mk[NTEAMS][NB + 1], s_bs[NTEAMS][NB + 1]; // (+1: the teams of a warp start in different banks)
+    __shared__ uint4 s_desc[NTEAMS][NB + 1];     // per non-empty block: (l0, n0, ty, tw + jz), see below
+    __shared__ uint32_t s_mk[NTEAMS][NB + 1];    // (+1: the teams of a warp start in different banks)
     __shared__ uint16_t s_pre[NTEAMS][NB + 2];
     const TileChunk *C = chunks + blockIdx.x;
     if (threadIdx.x < 9) {
@@ -424,74 +426,65 @@ k_tile_localize_masks_flat(const TileChunk *__restrict__ chunks, MaskOut mo, con
             grp = col * gpc + (zg == 1u ? cz : cz / zg);
             nb = min(min(mo.grp_nb[grp], mo.mb_cap), NB);
         }
-        // masks and block bases of the lane's contiguous quarter of the blocks -> team-shared memory, with the running
-        // number of entries before each block
         const uint32_t nbq = (nb + 3u) >> 2, b0 = tl * nbq, b1 = min(b0 + nbq, nb);
-        uint32_t tot = 0;
-        {
-            uint32_t mk[MAXQ], bs[MAXQ];
+        uint32_t tot = 0, nne = 0; // entries / non-empty blocks of this lane's quarter
+        uint32_t mk[MAXQ], bs[MAXQ];
 #pragma unroll
-            for (int q = 0; q < MAXQ; q++) { // all loads in flight before the first use
-                const uint32_t bq = b0 + (uint32_t)q;
-                mk[q] = bq < b1 ? __ldg(mo.masks + (size_t)bq * mo.npad + s) : 0u;
-                bs[q] = bq < b1 ? __ldg(mo.blk_base + (size_t)grp * mo.mb_cap + bq) : 0u;
-                tot += __popc(mk[q]);
-            }
-            uint32_t incl = tot; // inclusive scan over the 4 lanes of the team
-            uint32_t y = __shfl_up_sync(0xffffffffu, incl, 1, 4);
-            if (tl >= 1) incl += y;
-            y = __shfl_up_sync(0xffffffffu, incl, 2, 4);
-            if (tl >= 2) incl += y;
-            uint32_t run = incl - tot;
-#pragma unroll
-            for (int q = 0; q < MAXQ; q++) {
-                const uint32_t bq = b0 + (uint32_t)q;
-                if (bq < b1) {
-                    s_mk[team][bq] = mk[q];
-                    s_bs[team][bq] = bs[q];
-                    s_pre[team][bq] = (uint16_t)run;
-                    run += __popc(mk[q]);
-                }
-            }
-            tot = __shfl_sync(0xffffffffu, incl, 3, 4); // entries of the whole row (= cnt[s])
+        for (int q = 0; q < (int)MAXQ; q++) { // all loads in flight before the first use
+            const uint32_t bq = b0 + (uint32_t)q;
+            mk[q] = bq < b1 ? __ldg(mo.masks + (size_t)bq * mo.npad + s) : 0u;
+            bs[q] = bq < b1 ? __ldg(mo.blk_base + (size_t)grp * mo.mb_cap + bq) : 0u;
+            tot += __popc(mk[q]);
+            nne += mk[q] ? 1u : 0u;
         }
+        // inclusive scans over the 4 lanes of the team: entries and non-empty blocks (packed: both fit 16 bits)
+        uint32_t pk = tot | nne << 16, incl = pk;
+        uint32_t y = __shfl_up_sync(0xffffffffu, incl, 1, 4);
+        if (tl >= 1) incl += y;
+        y = __shfl_up_sync(0xffffffffu, incl, 2, 4);
+        if (tl >= 2) incl += y;
+        const uint32_t all = __shfl_sync(0xffffffffu, incl, 3, 4);
+        uint32_t run = (incl - pk) & 0xffffu, slot = (incl - pk) >> 16;
+        const uint32_t nbc = all >> 16; // non-empty blocks of the row
+#pragma unroll
+        for (int q = 0; q < (int)MAXQ; q++)
+            if (mk[q]) {
+                // candidate slot jb + bit -> tile index: r = l0 + bit < n0 ? ty + r : (tw + jz) + bit  (the two runs of the column)
+                const uint4 t = s_tab[min(bs[q] >> PARM_NBR_SLOT_BITS, 8u)];
+                const uint32_t jb = bs[q] & PARM_NBR_SLOT_MASK;
+                s_desc[team][slot] = make_uint4(jb - t.x, t.w - t.y, t.y, t.w + (jb - t.z));
+                s_mk[team][slot] = mk[q];
+                s_pre[team][slot] = (uint16_t)run;
+                run += __popc(mk[q]);
+                slot++;
+            }
         __syncwarp();
         // this lane's share of the entries and the block its first entry lies in
-        const uint32_t T = min(tot, my);
+        const uint32_t T = min(all & 0xffffu, my);
         const uint32_t k0 = (T * tl) >> 2, k1 = (T * (tl + 1u)) >> 2;
         uint32_t k = k0, bq = 0, m = 0;
-        uint32_t ty = 0, tw = 0, l0 = 0, n0 = 0, jz = 0;
+        uint4 d = make_uint4(0, 0, 0, 0);
         if (k1 > k0) {
-            uint32_t lo = 0, hi = nb; // last block whose prefix is <= k0
+            uint32_t lo = 0, hi = nbc; // last block whose prefix is <= k0: it holds entry k0
             while (hi - lo > 1) {
                 const uint32_t mid = (lo + hi) >> 1;
                 if (s_pre[team][mid] <= k0) lo = mid; else hi = mid;
             }
             bq = lo;
             m = s_mk[team][bq];
-            for (uint32_t skip = k0 - s_pre[team][bq]; skip; skip--) m &= m - 1u; // entries of that block that belong to the lane before
-            if (!m) { // (k0 lies at the very end of an emptyish block: move on)
-                bq++;
-                while (bq < nb && !(m = s_mk[team][bq])) bq++;
-            }
-            const uint32_t base = s_bs[team][bq];
-            const uint4 t = s_tab[min(base >> PARM_NBR_SLOT_BITS, 8u)];
-            const uint32_t jb = base & PARM_NBR_SLOT_MASK;
-            ty = t.y; tw = t.w; l0 = jb - t.x; n0 = t.w - t.y; jz = jb - t.z;
+            d = s_desc[team][bq];
+            for (uint32_t skip = k0 - s_pre[team][bq]; skip; skip--) m &= m - 1u; // its entries that belong to the lane before
         }
         while (k < k1) {
-            if (!m) { // next non-empty block
+            if (!m) { // next block (all stored blocks are non-empty; there is one: k < k1 <= T)
                 bq++;
-                while (!(m = s_mk[team][bq])) bq++; // (there is one: k < k1 <= T)
-                const uint32_t base = s_bs[team][bq];
-                const uint4 t = s_tab[min(base >> PARM_NBR_SLOT_BITS, 8u)];
-                const uint32_t jb = base & PARM_NBR_SLOT_MASK;
-                ty = t.y; tw = t.w; l0 = jb - t.x; n0 = t.w - t.y; jz = jb - t.z;
+                m = s_mk[team][bq];
+                d = s_desc[team][bq];
             }
             const uint32_t bit = (uint32_t)__ffs(m) - 1u;
             m &= m - 1u;
-            const uint32_t r = l0 + bit;
-            const uint32_t l = r < n0 ? ty + r : tw + (jz + bit);
+            const uint32_t r = d.x + bit;
+            const uint32_t l = r < d.y ? d.z + r : d.w + bit;
             lmax = max(lmax, l); // (an index beyond the tile is not expected: the entry would be in neither run of its column)
             buf[k++] = (uint16_t)l;
         }
@@ -756,10 +749,10 @@ int parm_tile_localize_masks(parm_nlist *nl) {
 #define LMARGS t.d_chunks, nl->mask.out, nl->cell_id_sorted, (uint32_t)nl->g.nc[2], nl->mask.gpc, (uint32_t)nl->mask.zg, nl->cnt, nl->kmax, t.rows16, t.d_info
     if (nl->mask.direct) {
         // the build kernel has written rows16 itself
-    } else if (nl->h_flags->nbmax <= 48) {
-        // (31 KB of static shared memory on top: the opt-in is needed from 17 KB of row buffers)
-        if (smem > 14 * 1024) CK(cudaFuncSetAttribute(k_tile_localize_masks_flat<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_tile_localize_masks_flat<12><<<t.nchunks, TILE_NT, smem, c->stream>>>(LMARGS);
+    } else if (nl->h_flags->nbmax <= LM_NB) {
+        // (~31 KB of static shared memory on top of the row buffers: always opt in)
+        CK(cudaFuncSetAttribute(k_tile_localize_masks_flat, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_tile_localize_masks_flat<<<t.nchunks, TILE_NT, smem, c->stream>>>(LMARGS);
     } else {
         if (smem + 2048 > 48 * 1024) CK(cudaFuncSetAttribute(k_tile_localize_masks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         k_tile_localize_masks<<<t.nchunks, TILE_NT, smem, c->stream>>>(LMARGS);
