@@ -381,7 +381,7 @@ k_tile_localize_masks(const TileChunk *__restrict__ chunks, MaskOut mo, const ui
     if (lost) atomicOr(&info->bad, 2u);
 }
 
-// Fast path of the above for groups of at most NB = 32 candidate blocks (nbmax of the build). The four lanes of a team
+// Fast path of the above for groups of at most NB = 48 candidate blocks (nbmax of the build). The four lanes of a team
 // load the masks of contiguous quarters of the candidate blocks; the NON-EMPTY ones are compacted into team-shared
 // memory together with the exclusive prefix of their popcounts and a ready-made descriptor (what turns a bit of the
 // block into a tile index). Then the ROW ENTRIES, not the blocks, are dealt out: lane tl produces entries
@@ -389,13 +389,14 @@ k_tile_localize_masks(const TileChunk *__restrict__ chunks, MaskOut mo, const ui
 // loop over set bits in which moving to the next block costs two shared-memory loads. Every lane of the warp runs the
 // same ~28 iterations (the populous blocks of the centre columns no longer make one lane the straggler), and the row
 // keeps the block order of the classic build, so the pair kernel's sums are bit-identical to it.
-#define LM_NB 32
-__global__ void __launch_bounds__(TILE_NT)
+#define LM_NB 48
+#define LM_NT 128 // 32 teams per block: the per-team block tables of 48 entries fit the static shared memory
+__global__ void __launch_bounds__(LM_NT)
 k_tile_localize_masks_flat(const TileChunk *__restrict__ chunks, MaskOut mo, const uint32_t *__restrict__ cell_id_sorted, uint32_t nc2,
                            uint32_t gpc, uint32_t zg, const uint32_t *__restrict__ cnt, uint32_t kmax, uint16_t *__restrict__ rows16,
                            TileInfo *info) {
-    constexpr uint32_t NB = LM_NB, MAXQ = LM_NB / 4, NTEAMS = TILE_NT / 4;
-    extern __shared__ __align__(16) uint16_t s_rows[]; // [TILE_NT / 4][kmax + 8]
+    constexpr uint32_t NB = LM_NB, MAXQ = LM_NB / 4, NTEAMS = LM_NT / 4;
+    extern __shared__ __align__(16) uint16_t s_rows[]; // [LM_NT / 4][kmax + 8]
     __shared__ uint4 s_tab[9];
     __shared__ uint32_t s_ntile;
     __shared__ uint4 s_desc[NTEAMS][NB + 1];     // per non-empty block: (l0, n0, ty, tw + jz), see below
@@ -413,7 +414,7 @@ k_tile_localize_masks_flat(const TileChunk *__restrict__ chunks, MaskOut mo, con
     const uint32_t stride = kmax + 8u;
     uint16_t *buf = s_rows + (size_t)team * stride;
     uint32_t lmax = 0;
-    for (uint32_t a0 = 0; a0 < na; a0 += TILE_NT / 4) { // every lane of a warp runs the same trips (team shuffles below)
+    for (uint32_t a0 = 0; a0 < na; a0 += LM_NT / 4) { // every lane of a warp runs the same trips (team shuffles below)
         const uint32_t a = a0 + team;
         const bool valid = a < na;
         const uint32_t s = s0 + (valid ? a : 0);
@@ -750,9 +751,10 @@ int parm_tile_localize_masks(parm_nlist *nl) {
     if (nl->mask.direct) {
         // the build kernel has written rows16 itself
     } else if (nl->h_flags->nbmax <= LM_NB) {
-        // (~31 KB of static shared memory on top of the row buffers: always opt in)
-        CK(cudaFuncSetAttribute(k_tile_localize_masks_flat, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_tile_localize_masks_flat<<<t.nchunks, TILE_NT, smem, c->stream>>>(LMARGS);
+        const size_t smem_f = (size_t)(LM_NT / 4) * (nl->kmax + 8) * sizeof(uint16_t);
+        // (~35 KB of static shared memory on top of the row buffers: always opt in)
+        CK(cudaFuncSetAttribute(k_tile_localize_masks_flat, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_f));
+        k_tile_localize_masks_flat<<<t.nchunks, LM_NT, smem_f, c->stream>>>(LMARGS);
     } else {
         if (smem + 2048 > 48 * 1024) CK(cudaFuncSetAttribute(k_tile_localize_masks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         k_tile_localize_masks<<<t.nchunks, TILE_NT, smem, c->stream>>>(LMARGS);
