@@ -389,8 +389,8 @@ k_tile_localize_masks(const TileChunk *__restrict__ chunks, MaskOut mo, const ui
 // loop over set bits in which moving to the next block costs two shared-memory loads. Every lane of the warp runs the
 // same ~28 iterations (the populous blocks of the centre columns no longer make one lane the straggler), and the row
 // keeps the block order of the classic build, so the pair kernel's sums are bit-identical to it.
-#define LM_NB 48
-#define LM_NT 128 // 32 teams per block: the per-team block tables of 48 entries fit the static shared memory
+// two shapes: 64 teams per block with tables of 32 blocks, or 32 teams per block with tables of 48 (static shared memory)
+template <int LM_NT, int LM_NB>
 __global__ void __launch_bounds__(LM_NT)
 k_tile_localize_masks_flat(const TileChunk *__restrict__ chunks, MaskOut mo, const uint32_t *__restrict__ cell_id_sorted, uint32_t nc2,
                            uint32_t gpc, uint32_t zg, const uint32_t *__restrict__ cnt, uint32_t kmax, uint16_t *__restrict__ rows16,
@@ -750,11 +750,14 @@ int parm_tile_localize_masks(parm_nlist *nl) {
 #define LMARGS t.d_chunks, nl->mask.out, nl->cell_id_sorted, (uint32_t)nl->g.nc[2], nl->mask.gpc, (uint32_t)nl->mask.zg, nl->cnt, nl->kmax, t.rows16, t.d_info
     if (nl->mask.direct) {
         // the build kernel has written rows16 itself
-    } else if (nl->h_flags->nbmax <= LM_NB) {
-        const size_t smem_f = (size_t)(LM_NT / 4) * (nl->kmax + 8) * sizeof(uint16_t);
-        // (~35 KB of static shared memory on top of the row buffers: always opt in)
-        CK(cudaFuncSetAttribute(k_tile_localize_masks_flat, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_f));
-        k_tile_localize_masks_flat<<<t.nchunks, LM_NT, smem_f, c->stream>>>(LMARGS);
+    } else if (nl->h_flags->nbmax <= 32) {
+        // (~45 KB of static shared memory on top of the row buffers: always opt in)
+        CK(cudaFuncSetAttribute(k_tile_localize_masks_flat<256, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_tile_localize_masks_flat<256, 32><<<t.nchunks, 256, smem, c->stream>>>(LMARGS);
+    } else if (nl->h_flags->nbmax <= 48) {
+        const size_t smem_f = (size_t)(128 / 4) * (nl->kmax + 8) * sizeof(uint16_t);
+        CK(cudaFuncSetAttribute(k_tile_localize_masks_flat<128, 48>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_f));
+        k_tile_localize_masks_flat<128, 48><<<t.nchunks, 128, smem_f, c->stream>>>(LMARGS);
     } else {
         if (smem + 2048 > 48 * 1024) CK(cudaFuncSetAttribute(k_tile_localize_masks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         k_tile_localize_masks<<<t.nchunks, TILE_NT, smem, c->stream>>>(LMARGS);
