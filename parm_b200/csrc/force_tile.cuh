@@ -111,9 +111,10 @@ __device__ __forceinline__ void tile_rows(const TileForceArgs &A, uint32_t na, u
             else if (validn) qn = load_row_words<V>(rown); // rows are allocated to kmax: safe whatever the next length is
 #pragma unroll
             for (int e = 0; e < V; e++) {
-                const uint32_t idx = (e & 1) ? (q.w[e >> 1] >> 16) : (q.w[e >> 1] & 0xffffu);
-                const double2 pxy = sxy[idx]; // one LDS.128 (quarter-warp phases: two teams share a phase, not four)
-                double dx = xi - pxy.x, dy = yi - pxy.y, dz = zi - sz[idx];
+                // the entry is 8 * index: byte offset of z, half the byte offset of (x, y)
+                const uint32_t eo = (e & 1) ? (q.w[e >> 1] >> 16) : (q.w[e >> 1] & 0xffffu);
+                const double2 pxy = *reinterpret_cast<const double2 *>(reinterpret_cast<const char *>(sxy) + 2u * eo); // one LDS.128
+                double dx = xi - pxy.x, dy = yi - pxy.y, dz = zi - *reinterpret_cast<const double *>(reinterpret_cast<const char *>(sz) + eo);
                 if (MI) {
                     dx = min_image_fast(dx, A.box.L[0], A.box.invL[0]);
                     dy = min_image_fast(dy, A.box.L[1], A.box.invL[1]);
@@ -129,8 +130,8 @@ __device__ __forceinline__ void tile_rows(const TileForceArgs &A, uint32_t na, u
                     const double ir6 = (s2 * s2) * s2;
                     const double b = ir6 * w;
                     const double t = fma(b, ir6, -b);
-                    const bool in = __double_as_longlong(dsq) <= rc2_bits; // sentinel pads: dsq ~ 1e200, beyond any cutoff
-                    const double scal = in ? t : 0.0;
+                    // (select, then accumulate: predicated DFMAs -- C or PTX -- come out of ptxas as DFMA + 6 FSEL)
+                    const double scal = __double_as_longlong(dsq) <= rc2_bits ? t : 0.0; // sentinel pads: dsq ~ 1e200, beyond any cutoff
                     fx = fma(dx, scal, fx);
                     fy = fma(dy, scal, fy);
                     fz = fma(dz, scal, fz);
@@ -503,9 +504,9 @@ __global__ void __launch_bounds__(TILE_PNT, 2) k_force_tile_pers(const TileForce
             if (k0 + TEAM * V < my0) qn = load_row_words<V>(row + k0 + TEAM * V);
 #pragma unroll
             for (int e = 0; e < V; e++) {
-                const uint32_t idx = (e & 1) ? (q.w[e >> 1] >> 16) : (q.w[e >> 1] & 0xffffu);
-                const double2 pxy = sxy[idx];
-                double dx = xi - pxy.x, dy = yi - pxy.y, dz = zi - sz[idx];
+                const uint32_t eo = (e & 1) ? (q.w[e >> 1] >> 16) : (q.w[e >> 1] & 0xffffu); // 8 * index
+                const double2 pxy = *reinterpret_cast<const double2 *>(reinterpret_cast<const char *>(sxy) + 2u * eo);
+                double dx = xi - pxy.x, dy = yi - pxy.y, dz = zi - *reinterpret_cast<const double *>(reinterpret_cast<const char *>(sz) + eo);
                 if (mi) { // (uniform per chunk) tile wider than half the box: minimum image per pair as well
                     dx = min_image_fast(dx, A.box.L[0], A.box.invL[0]);
                     dy = min_image_fast(dy, A.box.L[1], A.box.invL[1]);
@@ -517,8 +518,7 @@ __global__ void __launch_bounds__(TILE_PNT, 2) k_force_tile_pers(const TileForce
                 const double ir6 = (s2 * s2) * s2;
                 const double bb = ir6 * w;
                 const double t = fma(bb, ir6, -bb);
-                const bool in = __double_as_longlong(dsq) <= rc2_bits; // sentinel pads: dsq ~ 1e200, beyond any cutoff
-                const double scal = in ? t : 0.0;
+                const double scal = __double_as_longlong(dsq) <= rc2_bits ? t : 0.0; // sentinel pads: dsq ~ 1e200, beyond any cutoff
                 fx = fma(dx, scal, fx);
                 fy = fma(dy, scal, fy);
                 fz = fma(dz, scal, fz);

@@ -153,7 +153,8 @@ struct NlistFlags { // device-written; a pinned host mirror receives need_rebuil
 // once per staged atom, and walks 16-bit tile-local neighbour rows (rows16) written once per rebuild.
 #define TILE_MAXSEG 18
 #define TILE_NT 256            // threads per block of the tile kernels
-#define TILE_MAX_ATOMS 9000    // staged positions per tile that fit 227 KB of shared memory (24 B each)
+#define TILE_MAX_ATOMS 8150    // staged positions per tile: 24 B each in shared memory, and 8 * (index + sentinels) must fit 16 bits
+#define TILE_IDX_SHIFT 3       // rows16 entries are 8 * tile index = the byte offset of z in the staged tile (16 * index for (x, y))
 struct TileChunk {
     uint32_t s0, n;            // first slot, number of atoms (<= ch)
     uint32_t nseg, ntile;      // contiguous slot runs, staged atoms in total

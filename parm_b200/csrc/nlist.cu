@@ -740,7 +740,7 @@ k_build_cell(const double4 *__restrict__ pos, const double4 *__restrict__ pw, co
                         const uint32_t l = r < n0 ? ty + r : tw + (jz + bit);
                         if (k < kend) {
                             const uint32_t r32 = k & 31u;
-                            ring[((r32 << 3) & 24u) | (r32 >> 2)] = (uint16_t)min(l, ntile);
+                            ring[((r32 << 3) & 24u) | (r32 >> 2)] = (uint16_t)(min(l, ntile) << TILE_IDX_SHIFT);
                             if (r32 == 31u) { // a whole pass: 64 bytes
                                 uint4 *dst = reinterpret_cast<uint4 *>(out + (k & ~31u));
                                 const uint4 *src = reinterpret_cast<const uint4 *>(ring);
@@ -750,7 +750,7 @@ k_build_cell(const double4 *__restrict__ pos, const double4 *__restrict__ pw, co
                         k++;
                     }
                     if (kend & 31u) { // tail: pad the last pass with the sentinel index
-                        for (uint32_t kk = kend & 31u; kk < 32u; kk++) ring[((kk << 3) & 24u) | (kk >> 2)] = (uint16_t)ntile;
+                        for (uint32_t kk = kend & 31u; kk < 32u; kk++) ring[((kk << 3) & 24u) | (kk >> 2)] = (uint16_t)(ntile << TILE_IDX_SHIFT);
                         uint4 *dst = reinterpret_cast<uint4 *>(out + (kend & ~31u));
                         const uint4 *src = reinterpret_cast<const uint4 *>(ring);
                         dst[0] = src[0]; dst[1] = src[1]; dst[2] = src[2]; dst[3] = src[3];

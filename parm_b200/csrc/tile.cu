@@ -231,7 +231,7 @@ k_tile_localize(const TileChunk *__restrict__ chunks, const uint32_t *__restrict
                 const uint32_t l = j - t.x < t.w - t.y ? t.y + (j - t.x) : t.w + (j - t.z);
                 const bool pad = e[q] == 0xffffffffu;
                 if (!pad && l >= ntile) lost = true; // (not expected: the entry is in neither run of its column)
-                loc[q] = pad || l >= ntile ? ntile : l;
+                loc[q] = (pad || l >= ntile ? ntile : l) << TILE_IDX_SHIFT; // rows hold 8 * index: the pair kernel's byte offset of z
             }
             if (V == 8) {
                 uint4 o;
@@ -270,7 +270,11 @@ k_tile_bank_order(const TileChunk *__restrict__ chunks, const uint32_t *__restri
         const uint32_t mypad = (my + 31u) & ~31u, G = mypad >> 2, q = a & 3u;
         uint16_t *row = rows16 + (size_t)s * kmax;
         for (uint32_t k0 = 0; k0 < mypad; k0 += 32) {
-            *reinterpret_cast<uint4 *>(in + k0 + tl * 8) = *reinterpret_cast<const uint4 *>(row + k0 + tl * 8);
+            {   // rows hold 8 * index (TILE_IDX_SHIFT): the classes are those of the index
+                const uint4 rv = *reinterpret_cast<const uint4 *>(row + k0 + tl * 8);
+                *reinterpret_cast<uint4 *>(in + k0 + tl * 8) = make_uint4((rv.x >> TILE_IDX_SHIFT) & 0x1fff1fffu, (rv.y >> TILE_IDX_SHIFT) & 0x1fff1fffu,
+                                                                          (rv.z >> TILE_IDX_SHIFT) & 0x1fff1fffu, (rv.w >> TILE_IDX_SHIFT) & 0x1fff1fffu);
+            }
 #pragma unroll
             for (uint32_t e = 0; e < 8; e++) out[k0 + tl * 8 + e] = bo_sentinel(S, (k0 >> 2) + e, q, tl);
         }
@@ -288,7 +292,10 @@ k_tile_bank_order(const TileChunk *__restrict__ chunks, const uint32_t *__restri
         __syncwarp();
         if (valid && !keep)
             for (uint32_t k0 = 0; k0 < mypad; k0 += 32)
-                *reinterpret_cast<uint4 *>(row + k0 + tl * 8) = *reinterpret_cast<const uint4 *>(out + k0 + tl * 8);
+            {
+                const uint4 ov = *reinterpret_cast<const uint4 *>(out + k0 + tl * 8);
+                *reinterpret_cast<uint4 *>(row + k0 + tl * 8) = make_uint4(ov.x << TILE_IDX_SHIFT, ov.y << TILE_IDX_SHIFT, ov.z << TILE_IDX_SHIFT, ov.w << TILE_IDX_SHIFT);
+            }
         __syncwarp();
     }
 }
@@ -328,7 +335,8 @@ k_tile_localize_masks(const TileChunk *__restrict__ chunks, MaskOut mo, const ui
         const uint32_t my = valid ? min(cnt[s], kmax) : 0;
         const uint32_t mypad = (my + 31u) & ~31u;
         for (uint32_t k = tl * 8u; k < mypad; k += 32u) // sentinel everywhere, entries overwrite it
-            *reinterpret_cast<uint4 *>(buf + k) = make_uint4(ntile * 0x10001u, ntile * 0x10001u, ntile * 0x10001u, ntile * 0x10001u);
+            *reinterpret_cast<uint4 *>(buf + k) = make_uint4((ntile << TILE_IDX_SHIFT) * 0x10001u, (ntile << TILE_IDX_SHIFT) * 0x10001u,
+                                                             (ntile << TILE_IDX_SHIFT) * 0x10001u, (ntile << TILE_IDX_SHIFT) * 0x10001u);
         uint32_t nb = 0, grp = 0;
         if (my) {
             const uint32_t cid = cell_id_sorted[s];
@@ -365,7 +373,7 @@ k_tile_localize_masks(const TileChunk *__restrict__ chunks, MaskOut mo, const ui
                 if (k < my) {
                     // entry k of the row is read by lane (k & 3) of the team at step (k & 31) >> 2 of pass k / 32
                     const uint32_t r32 = k & 31u;
-                    buf[(k & ~31u) + (r32 & 3u) * 8u + (r32 >> 2)] = (uint16_t)(l >= ntile ? ntile : l);
+                    buf[(k & ~31u) + (r32 & 3u) * 8u + (r32 >> 2)] = (uint16_t)((l >= ntile ? ntile : l) << TILE_IDX_SHIFT);
                 }
                 k++;
             }
@@ -487,7 +495,7 @@ k_tile_localize_masks_flat(const TileChunk *__restrict__ chunks, MaskOut mo, con
             const uint32_t r = d.x + bit;
             const uint32_t l = r < d.y ? d.z + r : d.w + bit;
             lmax = max(lmax, l); // (an index beyond the tile is not expected: the entry would be in neither run of its column)
-            buf[k++] = (uint16_t)l;
+            buf[k++] = (uint16_t)(l << TILE_IDX_SHIFT); // rows hold 8 * index: the pair kernel's byte offset of z
         }
         __syncwarp();
         if (valid) {
@@ -498,7 +506,7 @@ k_tile_localize_masks_flat(const TileChunk *__restrict__ chunks, MaskOut mo, con
 #pragma unroll
                 for (int g = 0; g < 8; g += 2) {
                     const uint32_t ka = kk + tl + 4u * g, kb = ka + 4u;
-                    const uint32_t ea = ka < T ? buf[ka] : ntile, eb = kb < T ? buf[kb] : ntile;
+                    const uint32_t ea = ka < T ? buf[ka] : ntile << TILE_IDX_SHIFT, eb = kb < T ? buf[kb] : ntile << TILE_IDX_SHIFT;
                     w[g >> 1] = ea | eb << 16;
                 }
                 *reinterpret_cast<uint4 *>(out + kk + tl * 8) = make_uint4(w[0], w[1], w[2], w[3]);
