@@ -577,6 +577,8 @@ cudaError_t parm_launch_force_tile_kind(int team, int v, int mode, unsigned nchu
         k_force_tile_pers<KIND><<<std::min(nchunks, A.pers_blocks), TILE_PNT, smem2, st>>>(A, nchunks);
         return cudaGetLastError();
     }
+    // (register budgets other than ptxas's own 64 were measured and lost: 80 / 114 registers (3 / 2 blocks per SM) 0.256 /
+    // 0.321 ms against 0.243; 48 registers with 5 blocks of 91-atom chunks 0.250; 40 registers with 6 blocks 0.305)
     if (A.prel_xy) return launch_tile_mode<KIND, 4, 8, 1>(mode, nchunks, smem, st, A);
     return launch_tile_mode<KIND, 4, 8, 0>(mode, nchunks, smem, st, A);
 }
