@@ -38,7 +38,7 @@ __device__ __forceinline__ void top2_warp(double &b1, double &b2) {
 // the host, so the host can enqueue step s+1 before it has seen the decision of step s.
 __device__ __forceinline__ void drift_finish(double b1, double b2, double skin, double *d_top2, unsigned int *counter,
                                              NlistFlags *dflags, NlistFlags *hflags, int *d_slot = nullptr,
-                                             int *h_slot = nullptr) {
+                                             int *h_slot = nullptr, int step_no = -1) {
     __shared__ double s1[32], s2[32];
     __shared__ int s_last;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
@@ -87,6 +87,9 @@ __device__ __forceinline__ void drift_finish(double b1, double b2, double skin, 
             hflags->need_rebuild = need;
             if (d_slot) *d_slot = need;
             if (h_slot) *h_slot = need;
+            // batched stepping (parm_integ_timestep): the first step of the batch that asks for a rebuild leaves its
+            // number for the host (the steps behind it abort, so there is no second writer)
+            if (need && step_no >= 0) hflags->trigger = (uint32_t)step_no;
             __threadfence_system();
         }
     }

@@ -43,7 +43,7 @@ __global__ void __launch_bounds__(I_BLOCK)
 k_verlet1(double4 *__restrict__ pos, double *__restrict__ v, const double *__restrict__ a, uint32_t n, uint32_t npad,
           double dt, double hdt2, double hdt, const int *__restrict__ abort_flag, const double *__restrict__ xlast,
           double skin, double *d_top2, unsigned int *counter, NlistFlags *dflags, NlistFlags *hflags, int *d_slot,
-          int *h_slot, const PrelOut R) {
+          int *h_slot, const PrelOut R, const int step_no) {
     if (abort_flag && *abort_flag) return; // speculative step behind a rebuild request: leave the state alone
     double b1 = 0.0, b2 = 0.0;
     for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < n; s += gridDim.x * blockDim.x) {
@@ -84,7 +84,7 @@ k_verlet1(double4 *__restrict__ pos, double *__restrict__ v, const double *__res
         // atoms that were never add()ed have NaN lastlocs (set at rebuild): NaN never wins a '>' comparison
         if (DRIFT) top2_push(b1, b2, drift_dist(p, xl[0], xl[1], xl[2]));
     }
-    if (DRIFT) drift_finish(b1, b2, skin, d_top2, counter, dflags, hflags, d_slot, h_slot);
+    if (DRIFT) drift_finish(b1, b2, skin, d_top2, counter, dflags, hflags, d_slot, h_slot, step_no);
 }
 
 // ---- K3: a = f/m; v += a*(dt/2)  (collection.cpp:457-465) -----------------------------------
@@ -127,9 +127,15 @@ __global__ void __launch_bounds__(I_BLOCK)
 k_verlet21(double4 *__restrict__ pos, double *__restrict__ v, double *__restrict__ a, const double *__restrict__ f, uint32_t n,
            uint32_t npad, double dt, double hdt2, double hdt, const int *__restrict__ abort_flag, const int *__restrict__ next_flag,
            const double *__restrict__ xlast, double skin, double *d_top2, unsigned int *counter, NlistFlags *dflags,
-           NlistFlags *hflags, int *d_slot, int *h_slot, const PrelOut R) {
-    if (abort_flag && *abort_flag) return;
+           NlistFlags *hflags, int *d_slot, int *h_slot, const PrelOut R, const int step_no) {
+    // An aborted step hands the abort on (its own decision slot is what guards the step after it): with several steps
+    // queued behind a rebuild request every one of them stays a no-op.
+    if (abort_flag && *abort_flag) {
+        if (d_slot && blockIdx.x == 0 && threadIdx.x == 0) *d_slot = 1;
+        return;
+    }
     const bool go = !(*next_flag);
+    if (!go && d_slot && blockIdx.x == 0 && threadIdx.x == 0) *d_slot = 1; // K3 half only: step s+1 does not start
     double b1 = 0.0, b2 = 0.0;
     for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < n; s += gridDim.x * blockDim.x) {
         double4 p = pos[s];
@@ -181,7 +187,7 @@ k_verlet21(double4 *__restrict__ pos, double *__restrict__ v, double *__restrict
             top2_push(b1, b2, drift_dist(p, xl[0], xl[1], xl[2]));
         }
     }
-    if (go) drift_finish(b1, b2, skin, d_top2, counter, dflags, hflags, d_slot, h_slot);
+    if (go) drift_finish(b1, b2, skin, d_top2, counter, dflags, hflags, d_slot, h_slot, step_no);
 }
 
 struct SolConst {
@@ -493,20 +499,21 @@ extern "C" int parm_integ_inject_noise(parm_integ *g, const double *z, size_t le
 // k1_done: the first half of this step already ran inside the previous step's fused K3+K1 kernel. fuse_next: end this
 // step with that fused kernel (K3 of this step + K1 of the next, the latter guarded by THIS step's decision and leaving
 // the next step's decision in slot (slot + 1) % 3) instead of a plain K3. Both only for CollectionVerlet (fusable()).
-static int enqueue_step_core(parm_integ *g, uint64_t step, const int *abort_flag, int slot, bool k1_done, bool fuse_next);
+static int enqueue_step_core(parm_integ *g, uint64_t step, const int *abort_flag, int slot, bool k1_done, bool fuse_next, int batch_step);
 static bool fusable(const parm_integ *g) {
     const parm_ctx *c = g->ctx;
     const char *e = getenv("PARM_B200_FUSE_K3K1"); // (read per call: the sweeps toggle it inside one process)
     return g->type == 0 && !g->trackers.empty() && g->stat_trackers.empty() && !c->prof_on && (e ? atoi(e) != 0 : true);
 }
-static int enqueue_step(parm_integ *g, uint64_t step, const int *abort_flag, int slot, bool k1_done = false, bool fuse_next = false) {
+static int enqueue_step(parm_integ *g, uint64_t step, const int *abort_flag, int slot, bool k1_done = false, bool fuse_next = false,
+                        int batch_step = -1) {
     if (g->type >= PARM_INTEG_DAMPED) PTRY(parm_integ_extra_enqueue(g, step, abort_flag, slot));
-    else PTRY(enqueue_step_core(g, step, abort_flag, slot, k1_done, fuse_next));
+    else PTRY(enqueue_step_core(g, step, abort_flag, slot, k1_done, fuse_next, batch_step));
     // update_trackers() ends every step: the statistics trackers follow the NeighborList
     for (parm_tracker *t : g->stat_trackers) PTRY(parm_tracker_enqueue_update(t, abort_flag));
     return 0;
 }
-static int enqueue_step_core(parm_integ *g, uint64_t step, const int *abort_flag, int slot, bool k1_done, bool fuse_next) {
+static int enqueue_step_core(parm_integ *g, uint64_t step, const int *abort_flag, int slot, bool k1_done, bool fuse_next, int batch_step) {
     parm_ctx *c = g->ctx;
     const uint32_t n = parm_owned(c); // ghost copies are never integrated
     parm_nlist *nl = g->trackers.empty() ? nullptr : g->trackers[0];
@@ -540,12 +547,12 @@ static int enqueue_step_core(parm_integ *g, uint64_t step, const int *abort_flag
     } else if (g->type == 0) {
         const double hdt2 = dt * dt / 2, hdt = dt / 2;
         if (c->D == 3) {
-            if (k1_prel) k_verlet1<3, true, true><<<grid1, I_BLOCK, 0, c->stream>>>(c->pos, c->v, c->a, n, c->npad, dt, hdt2, hdt, DRIFTARGS, R);
-            else if (nl) k_verlet1<3, true, false><<<grid1, I_BLOCK, 0, c->stream>>>(c->pos, c->v, c->a, n, c->npad, dt, hdt2, hdt, DRIFTARGS, R);
-            else k_verlet1<3, false, false><<<grid1, I_BLOCK, 0, c->stream>>>(c->pos, c->v, c->a, n, c->npad, dt, hdt2, hdt, DRIFTARGS, R);
+            if (k1_prel) k_verlet1<3, true, true><<<grid1, I_BLOCK, 0, c->stream>>>(c->pos, c->v, c->a, n, c->npad, dt, hdt2, hdt, DRIFTARGS, R, batch_step);
+            else if (nl) k_verlet1<3, true, false><<<grid1, I_BLOCK, 0, c->stream>>>(c->pos, c->v, c->a, n, c->npad, dt, hdt2, hdt, DRIFTARGS, R, batch_step);
+            else k_verlet1<3, false, false><<<grid1, I_BLOCK, 0, c->stream>>>(c->pos, c->v, c->a, n, c->npad, dt, hdt2, hdt, DRIFTARGS, R, batch_step);
         } else {
-            if (nl) k_verlet1<2, true, false><<<grid1, I_BLOCK, 0, c->stream>>>(c->pos, c->v, c->a, n, c->npad, dt, hdt2, hdt, DRIFTARGS, R);
-            else k_verlet1<2, false, false><<<grid1, I_BLOCK, 0, c->stream>>>(c->pos, c->v, c->a, n, c->npad, dt, hdt2, hdt, DRIFTARGS, R);
+            if (nl) k_verlet1<2, true, false><<<grid1, I_BLOCK, 0, c->stream>>>(c->pos, c->v, c->a, n, c->npad, dt, hdt2, hdt, DRIFTARGS, R, batch_step);
+            else k_verlet1<2, false, false><<<grid1, I_BLOCK, 0, c->stream>>>(c->pos, c->v, c->a, n, c->npad, dt, hdt2, hdt, DRIFTARGS, R, batch_step);
         }
     } else {
         K.dt = dt;
@@ -626,7 +633,7 @@ static int enqueue_step_core(parm_integ *g, uint64_t step, const int *abort_flag
         int *d_slot2 = !c->sh.on ? nl->d_slot + nslot : nullptr, *h_slot2 = !c->sh.on ? nl->h_slot + nslot : nullptr;
         const double hdt2 = dt * dt / 2, hdt = dt / 2;
 #define F21ARGS c->pos, c->v, c->a, c->f, n, c->npad, dt, hdt2, hdt, abort_flag, nl->d_slot + slot, nl->xlast, nl->skin, nl->d_top2, \
-                nl->d_counter, nl->d_flags, nl->h_flags, d_slot2, h_slot2, R
+                nl->d_counter, nl->d_flags, nl->h_flags, d_slot2, h_slot2, R, batch_step >= 0 ? batch_step + 1 : -1
         if (c->D == 3) {
             if (k1_prel) k_verlet21<3, true><<<grid1, I_BLOCK, 0, c->stream>>>(F21ARGS);
             else k_verlet21<3, false><<<grid1, I_BLOCK, 0, c->stream>>>(F21ARGS);
@@ -689,6 +696,38 @@ extern "C" int parm_integ_timestep(parm_integ *g, int nsteps) {
     // Decision slots are used round robin modulo 3: a fused K3+K1 kernel reads the slots of the two previous steps and
     // writes the third. With CollectionVerlet every step but the last of the call ends with that fused kernel.
     const bool fuse = fusable(g);
+    // Batched stepping (single GPU, CollectionVerlet): up to `batch` steps are queued without the host looking at a single
+    // decision in between. Every step is guarded on the device by its predecessor's decision slot, an aborted step hands
+    // the abort on, and the step whose drift rule fired leaves its number in pinned memory: the host waits ONCE per
+    // batch, counts the steps that ran, rebuilds if one of them asked for it and queues the rest again. Semantics are
+    // those of collection.cpp:442-469 step by step (the rebuild still follows the step that triggered it); what changes
+    // is that small systems are no longer bound by one host round trip per step.
+    {
+        const char *eb = getenv("PARM_B200_STEP_BATCH");
+        const int batch = eb ? atoi(eb) : 16;
+        if (fuse && batch > 1 && !c->sh.on && !nl->ignorechanged && nsteps > 1) {
+            int s = 0;
+            while (s < nsteps) {
+                const int B = std::min(nsteps - s, batch);
+                nl->h_flags->trigger = 0xffffffffu;
+                for (int j = 0; j < B; j++)
+                    PTRY(enqueue_step(g, g->steps + j, j ? nl->d_slot + (j - 1) % 3 : nullptr, j % 3, j > 0, j + 1 < B, j));
+                CK(cudaEventRecord(g->ev[0], c->stream));
+                CK(cudaEventSynchronize(g->ev[0]));
+                const uint32_t trig = nl->h_flags->trigger;
+                const int done = trig < (uint32_t)B ? (int)trig + 1 : B;
+                g->steps += done;
+                s += done;
+                if (trig < (uint32_t)B) {
+                    PTRY(parm_nlist_rebuild(nl));
+                    g->rebuilds++;
+                }
+                CK(cudaMemsetAsync(nl->d_slot, 0, 4 * sizeof(int), c->stream));
+                nl->h_slot[0] = nl->h_slot[1] = nl->h_slot[2] = nl->h_slot[3] = 0;
+            }
+            return 0;
+        }
+    }
     int cur = 0; // slot of step s
     PTRY(enqueue_step(g, g->steps, nullptr, cur, false, fuse && nsteps > 1));
     CK(cudaEventRecord(g->ev[0], c->stream));

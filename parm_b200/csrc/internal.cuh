@@ -139,7 +139,8 @@ struct ShardDev {
 struct NlistFlags { // device-written; a pinned host mirror receives need_rebuild / top2
     int need_rebuild;
     uint32_t maxcnt;              // longest row of the last build
-    uint32_t nbmax, pad_;         // mask-mode build: most candidate blocks any warp group walked
+    uint32_t nbmax;               // mask-mode build: most candidate blocks any warp group walked
+    uint32_t trigger;             // (pinned host copy only) batched stepping: number of the step of the batch whose drift rule fired
     unsigned long long total;     // sum of row lengths of the last build
     unsigned long long xmax_bits; // bit pattern of max |coordinate| seen by the last binning pass
     double top2[2];
