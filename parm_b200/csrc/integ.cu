@@ -704,7 +704,9 @@ extern "C" int parm_integ_timestep(parm_integ *g, int nsteps) {
     // is that small systems are no longer bound by one host round trip per step.
     {
         const char *eb = getenv("PARM_B200_STEP_BATCH");
-        const int batch = eb ? atoi(eb) : 16;
+        // (measured, profiles/README.md r02: no gain -- N = 1000 is bound by ~20 us of dependent kernel latency per step,
+        // not by the host round trip, and at N = 1e6 the kernels queued behind a trigger cost 4 %: off unless asked for)
+        const int batch = eb ? atoi(eb) : 0;
         if (fuse && batch > 1 && !c->sh.on && !nl->ignorechanged && nsteps > 1) {
             int s = 0;
             while (s < nsteps) {
