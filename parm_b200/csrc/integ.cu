@@ -196,7 +196,7 @@ struct SolConst {
 
 // ---- Sol K1 (collection.cpp:276-298), fused with the drift reduction like k_verlet1 --------------
 template <int D, bool DRIFT>
-__global__ void __launch_bounds__(I_BLOCK)
+__global__ void __launch_bounds__(I_BLOCK, 4)
 k_sol1(double4 *__restrict__ pos, double *__restrict__ v, const double *__restrict__ a, const uint32_t *__restrict__ order,
        uint32_t n, uint32_t npad, SolConst K, const double *__restrict__ noise, const uint32_t *__restrict__ mobile_rank,
        uint64_t step, uint64_t seed, const int *__restrict__ abort_flag, const double *__restrict__ xlast, double skin,
@@ -204,7 +204,21 @@ k_sol1(double4 *__restrict__ pos, double *__restrict__ v, const double *__restri
     if (abort_flag && *abort_flag) return;
     double b1 = 0.0, b2 = 0.0;
     for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < n; s += gridDim.x * blockDim.x) {
+        // every load of the atom is issued before the ~500 instructions of the noise generation: the memory round trip
+        // hides behind them instead of following them (ncu r02_d: 35 % active warps at 80 registers, long-scoreboard bound)
         double4 p = pos[s];
+        double vd0[D], ad0[D], xl[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+        for (int d = 0; d < D; d++) {
+            vd0[d] = v[(size_t)d * npad + s];
+            ad0[d] = a[(size_t)d * npad + s];
+        }
+        if (DRIFT) {
+            xl[0] = xlast[s];
+            xl[1] = xlast[npad + s];
+            xl[2] = xlast[2 * (size_t)npad + s];
+        }
+        const uint32_t id = K.damping > 0 ? order[s] : 0u;
         if (frozen_le(p.w)) {
 #pragma unroll
             for (int d = 0; d < D; d++) v[(size_t)d * npad + s] = 0.0;
@@ -213,7 +227,6 @@ k_sol1(double4 *__restrict__ pos, double *__restrict__ v, const double *__restri
             const double r0 = __dmul_rn(K.dt, v0);
             double x1[3] = {0, 0, 0}, x2[3] = {0, 0, 0};
             if (K.damping > 0) {
-                const uint32_t id = order[s];
                 if (noise) {
                     const double *z = noise + (size_t)mobile_rank[id] * 2 * D;
 #pragma unroll
@@ -236,7 +249,7 @@ k_sol1(double4 *__restrict__ pos, double *__restrict__ v, const double *__restri
 #pragma unroll
             for (int d = 0; d < D; d++) {
                 const size_t q = (size_t)d * npad + s;
-                const double vd = v[q], ad = a[q];
+                const double vd = vd0[d], ad = ad0[d];
                 const double drG = __dmul_rn(x1[d], K.x11);                                           // x1 * x11
                 const double dvG = __dadd_rn(__dmul_rn(x1[d], K.x21), __dmul_rn(x2[d], K.x22));       // x1*x21 + x2*x22
                 x[d] = __dadd_rn(x[d], __dadd_rn(__dadd_rn(__dmul_rn(vd, K.c1dt), __dmul_rn(ad, K.c2dtdt)), __dmul_rn(drG, r0)));
@@ -247,7 +260,7 @@ k_sol1(double4 *__restrict__ pos, double *__restrict__ v, const double *__restri
             if (D == 3) p.z = x[2];
             pos[s] = p;
         }
-        if (DRIFT) top2_push(b1, b2, drift_dist(p, xlast[s], xlast[npad + s], xlast[2 * (size_t)npad + s]));
+        if (DRIFT) top2_push(b1, b2, drift_dist(p, xl[0], xl[1], xl[2]));
     }
     if (DRIFT) drift_finish(b1, b2, skin, d_top2, counter, dflags, hflags, d_slot, h_slot);
 }
