@@ -17,7 +17,7 @@ def _latest(pattern):
 
 
 def test_latest_bench_line_has_the_contract_keys():
-    d = json.load(open(_latest("r01_*_bench_1M.json")))
+    d = json.load(open(_latest("r0[0-9]_*_bench_1M.json")))
     for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
               "vs_baseline", "dtype", "data", "config", "clocks", "e2e", "gpu_launches", "roofline", "cpu_baseline"):
         assert k in d, k
@@ -37,17 +37,17 @@ def test_latest_bench_line_has_the_contract_keys():
 
 
 def test_reference_arm_line():
-    d = json.load(open(_latest("r01_*_bench_reference.json")))
+    d = json.load(open(_latest("r0[0-9]_*_bench_reference.json")))
     assert d["impl"] == "reference" and d["gpu_launches"] == 0
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
     assert d["e2e"]["value"] == d["value"] == d["cpu_baseline"]["value"]
 
 
 def test_ncu_exports_parse():
-    raw = _latest("r01_*_force_tile_ncu_raw.csv")
+    raw = _latest("r0[0-9]_*_force_tile_ncu_raw.csv")
     out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_summary.py"), raw], capture_output=True, text=True)
     assert out.returncode == 0 and "k_force_tile" in out.stdout and "gpu__time_duration.sum" in out.stdout
-    src = _latest("r01_*_force_tile_ncu_source.csv")
+    src = _latest("r0[0-9]_*_force_tile_ncu_source.csv")
     out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_sass_profile.py"), src], capture_output=True, text=True)
     assert out.returncode == 0 and "LDS.128" in out.stdout and "by region between barriers" in out.stdout
 
