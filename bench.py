@@ -105,6 +105,18 @@ def equilibrate(collec, steps, T=1.44):
     return {"steps": steps, "rescale_every": EQUIL_EVERY, "T_target": T, "T_end": float(collec.temp())}
 
 
+def align_to_rebuild(collec, max_steps=12):
+    """Untimed: single steps until one of them ends with a neighbour-list rebuild, so that the timed window always
+    starts from a freshly built list (like the first step of any run). A 20-step window then holds the same number of
+    rebuilds in every run and every round; the unaligned long-window figure is `steady_state`."""
+    r0 = collec.stats()["rebuilds"]
+    for k in range(max_steps):
+        collec.timestep(1)
+        if collec.stats()["rebuilds"] > r0:
+            return k + 1
+    return max_steps
+
+
 def kernel_source_sha16():
     """Hash of the pair-kernel sources of the library that is running (ties profiles/force_kernel_traffic.json to it)."""
     import hashlib
@@ -227,7 +239,7 @@ def run_ours(args):
             return {"value": val, "unit": UNIT, "cores": 1, "kind": "reference" if kind == "ref" else "port",
                     "sample": cpu_sample_desc(ncpu, 100, kind)}
 
-        hooks = {"equilibrate": equilibrate, "cpu_baseline": cpu_hook}
+        hooks = {"equilibrate": equilibrate, "cpu_baseline": cpu_hook, "align": align_to_rebuild}
         if not args.no_parity:
             hooks["parity"] = parity_hook
         return sharded.bench_main(args, rank, world, local, METRIC, UNIT, workload_config(args, world), peaks(), hooks)
@@ -243,6 +255,8 @@ def run_ours(args):
 
     equil = equilibrate(collec, args.equil)
     collec.timestep(W)
+    equil["alignment_steps"] = align_to_rebuild(collec)
+    equil["timed_region_starts"] = "on the first step after a neighbour-list rebuild"
     capi.call("parm_sync", atoms._h)
     # ---- timed region: K steps, device clock, rebuilds included
     sampler = ClockSampler(local)

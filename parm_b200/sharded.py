@@ -268,6 +268,9 @@ def bench_main(args, rank, world, local, metric, unit, config, peak, hooks=None)
     K, W = args.steps, max(args.warmup, 3)
     equil = hooks["equilibrate"](collec, args.equil) if "equilibrate" in hooks else None
     collec.timestep(W)
+    if equil is not None and "align" in hooks:  # the timed window starts from a freshly built list (every rank takes the same steps)
+        equil["alignment_steps"] = hooks["align"](collec)
+        equil["timed_region_starts"] = "on the first step after a neighbour-list rebuild"
     call("parm_sync", atoms._h)
     sampler = ClockSampler(local)
     if rank == 0:
@@ -337,6 +340,8 @@ def bench_main(args, rank, world, local, metric, unit, config, peak, hooks=None)
         stream5 = torch.cuda.ExternalStream(st.value, device=local)
         eq5 = hooks["equilibrate"](collec5, args.equil) if "equilibrate" in hooks else None
         collec5.timestep(W)
+        if eq5 is not None and "align" in hooks:
+            eq5["alignment_steps"] = hooks["align"](collec5)
         call("parm_sync", atoms5._h)
         K5 = max(K, 100)
         ms5, _, rb5 = _timed_window(collec5, atoms5, stream5, K5)
