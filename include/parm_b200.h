@@ -338,6 +338,11 @@ int parm_shard_get_atoms(parm_ctx *ctx, uint32_t cap, uint32_t *n_local, uint32_
 /* overwrite fields of the local atoms in the order parm_shard_get_atoms returned them (NULL = keep) */
 int parm_shard_put_atoms(parm_ctx *ctx, uint32_t n_local, const double *x, const double *v, const double *a, const double *f);
 int parm_shard_info(parm_ctx *ctx, uint32_t *out6 /* n_local, ghosts_down, ghosts_up, send_down, send_up, slots */);
+/* how the list rebuilds of this rank migrated their atoms so far: out2[0] one-sort rebuilds (leavers packed into
+ * fixed-capacity messages, PARM_B200_SHARD_MIGCAP atoms each), out2[1] two-sort rebuilds (the fall-back when more atoms
+ * than that left a slab at once anywhere, or with PARM_B200_SHARD_FAST=0). No reference counterpart (the reference is
+ * single-process); NeighborList::update_list, trackers.cpp:19-85, is what both paths implement. */
+int parm_shard_rebuild_stats(parm_ctx *ctx, uint64_t *out2);
 
 #ifdef __cplusplus
 }

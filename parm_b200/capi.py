@@ -121,6 +121,7 @@ SIGNATURES = {
     "parm_shard_get_atoms": (C.c_int, [vp, C.c_uint32, u32p, u32p, dp, dp, dp, dp, dp]),
     "parm_shard_put_atoms": (C.c_int, [vp, C.c_uint32, dp, dp, dp, dp]),
     "parm_shard_info": (C.c_int, [vp, u32p]),
+    "parm_shard_rebuild_stats": (C.c_int, [vp, C.POINTER(C.c_uint64)]),
 }
 
 

@@ -98,6 +98,21 @@ static int launch_forces(parm_inter *it, int run, bool accumulate, double *d_out
     tile_launcher tl = parm_tile_usable(it) ? tile_launcher_of(PARM_KERNEL_KIND(it->kind)) : nullptr;
     if (tl && !parm_tile_chunk_range(nl, first, nown, &chunk0, &chunk1)) tl = nullptr;
     if (tl && chunk1 == chunk0) tl = nullptr;
+    // Small systems (BASELINE config 1, N = 1000): a step is a chain of dependent kernel latencies, not throughput. The
+    // tile kernel would run one block per chunk on a handful of SMs (9 chunks at N = 1000) and four lanes would walk a
+    // row of ~100 entries in 13 dependent trips; 16 lanes per atom of the gather kernel spread the same rows over every
+    // SM and finish in 4 trips.
+    {
+        static int small_team = -1;
+        if (small_team < 0) { const char *e = getenv("PARM_B200_SMALL_TEAM"); small_team = e ? atoi(e) : 16; }
+        const bool one_species = !it->generic && it->nspecies == 1;
+        const uint32_t nch = tl ? chunk1 - chunk0 : (nrange + 119u) / 120u;
+        if (small_team == 16 && one_species && nch < (uint32_t)c->num_sms && nl->total_full >= 16ull * nrange) {
+            team = 16;
+            tl = nullptr;
+            nblocks = (uint32_t)(((size_t)nrange * team + F_BLOCK - 1) / F_BLOCK);
+        }
+    }
     if (tl) nblocks = chunk1 - chunk0;
     if (mode != MODE_F && (size_t)nblocks * NPART > it->partial_doubles) {
         if (it->d_partials) cudaFree(it->d_partials);
@@ -120,6 +135,11 @@ static int launch_forces(parm_inter *it, int run, bool accumulate, double *d_out
         T.cap = ((nl->tile.max_tile + 1 + 15u) & ~15u) + 16u; // tile + the single sentinel, rounded up, + 16 class sentinels
         const bool pers = bulk && (ep ? atoi(ep) != 0 : false) && 2 * 3 * (size_t)T.cap * 8 + 2048 <= 113 * 1024 && nl->tile.ch <= 120;
         T.pers_blocks = pers ? 2u * (uint32_t)c->num_sms : 0u;
+        {   // measurement switches (read per launch like the one above)
+            const char *eh = getenv("PARM_B200_TILE_HALF"), *ef = getenv("PARM_B200_TILE_PF");
+            T.half_ok = (eh ? atoi(eh) != 0 : true) && !nl->tile.banked ? 1u : 0u;
+            T.pf_dist = ef ? (uint32_t)atoi(ef) : 4u * (uint32_t)c->num_sms; // one wave of blocks ahead
+        }
         T.chunk_s0 = nl->tile.d_s0 + chunk0;
         T.chunks = nl->tile.d_chunks + chunk0;
         T.rows16 = nl->tile.rows16;

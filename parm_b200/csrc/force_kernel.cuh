@@ -214,10 +214,11 @@ static cudaError_t launch_mode(int mode, dim3 grid, size_t smem, cudaStream_t st
     return cudaGetLastError();
 }
 
-// specmode 0/1/2 as SPEC above; team 4 or 8; natoms = number of slots in [first, n)
+// specmode 0/1/2 as SPEC above; team 4 or 8 (16: one species, small systems); natoms = number of slots in [first, n)
 template <int KIND>
 cudaError_t parm_launch_force_kind(int specmode, int team, int mode, uint32_t natoms, size_t smem, cudaStream_t st, const ForceArgs &A) {
     const dim3 grid((unsigned)(((size_t)natoms * team + F_BLOCK - 1) / F_BLOCK));
+    if (team == 16 && specmode == 0) return launch_mode<KIND, 0, 16>(mode, grid, 0, st, A);
     if (team == 8) {
         if (specmode == 0) return launch_mode<KIND, 0, 8>(mode, grid, 0, st, A);
         if (specmode == 1) return launch_mode<KIND, 1, 8>(mode, grid, smem, st, A);

@@ -30,6 +30,9 @@ struct TileForceArgs {
     double *partials;
     const int *abort_flag;
     uint32_t pers_blocks;    // > 0: persistent double-buffered kernel with this many blocks (bulk-copy staging only)
+    uint32_t half_ok;        // rows are in the lane-vector layout of tile.cu (not bank-ordered): a pass whose longest row has
+                             // <= TEAM * m entries left holds them all in the first m entries of every lane's vector
+    uint32_t pf_dist;        // > 0: every block pulls the descriptor of chunk blockIdx.x + pf_dist into L2
     const uint32_t *chunk_s0; // first slot of every chunk of the launch and the end of the last one (persistent kernel)
 };
 
@@ -79,18 +82,77 @@ __device__ __forceinline__ RowWords<V> load_row_words(const uint16_t *p) {
     return r;
 }
 
-// The row words of pass k+1 (or of the first pass of the team's NEXT atom) and the next atom's row length are
-// requested before the arithmetic of pass k starts, so the DRAM latency of the streamed rows (the top stall
-// of the non-pipelined loop: long_scoreboard 5.6 warps per issue) hides behind ~160 fp64 instructions.
-// my0 / q0: length and first pass of the team's first atom, loaded by the caller before the tile was staged.
+// V pair evaluations of one lane: entries [0, NV) of the lane's vector of this pass
+template <int KIND, int MODE, int V, int NV, bool MI>
+__device__ __forceinline__ void tile_pairs(const TileForceArgs &A, const RowWords<V> &q, const double2 *sxy, const double *sz, double xi,
+                                           double yi, double zi, double c12, long long rc2_bits, double &fx, double &fy, double &fz,
+                                           double (&acc)[NPART]) {
+    constexpr bool want_obs = MODE != MODE_F;
+#pragma unroll
+    for (int e = 0; e < NV; e++) {
+        // the entry is 8 * index: byte offset of z, half the byte offset of (x, y)
+        const uint32_t eo = (e & 1) ? (q.w[e >> 1] >> 16) : (q.w[e >> 1] & 0xffffu);
+        const double2 pxy = *reinterpret_cast<const double2 *>(reinterpret_cast<const char *>(sxy) + 2u * eo); // one LDS.128
+        double dx = xi - pxy.x, dy = yi - pxy.y, dz = zi - *reinterpret_cast<const double *>(reinterpret_cast<const char *>(sz) + eo);
+        if (MI) {
+            dx = min_image_fast(dx, A.box.L[0], A.box.invL[0]);
+            dy = min_image_fast(dy, A.box.L[1], A.box.invL[1]);
+            dz = min_image_fast(dz, A.box.L[2], A.box.invL[2]);
+        }
+        const double dsq = dx * dx + (dy * dy + dz * dz);
+        if (!want_obs) {
+            // forces only: 17 operations on the fp64 pipe per pair. The factor 12 epsilon is applied once per atom, the
+            // cut-off test is an integer comparison of the bit patterns (both numbers are positive),
+            // ir6 (ir6 - 1) / dsq comes out of one fused multiply-add
+            const double w = rcp_pos(dsq);
+            const double s2 = A.P1.sig2 * w;
+            const double ir6 = (s2 * s2) * s2;
+            const double b = ir6 * w;
+            const double t = fma(b, ir6, -b);
+            // (select, then accumulate: predicated DFMAs -- C or PTX -- come out of ptxas as DFMA + 6 FSEL)
+            const double scal = __double_as_longlong(dsq) <= rc2_bits ? t : 0.0; // sentinel pads: dsq ~ 1e200, beyond any cutoff
+            fx = fma(dx, scal, fx);
+            fy = fma(dy, scal, fy);
+            fz = fma(dz, scal, fz);
+            continue;
+        }
+        double scal, en;
+        lj_eval<KIND>(A.P1, c12, dsq, want_obs, scal, en); // sentinel pads: dsq ~ 1e200, beyond any cutoff
+        const double gx = dx * scal, gy = dy * scal, gz = dz * scal;
+        fx += gx;
+        fy += gy;
+        fz += gz;
+        if (want_obs) {
+            acc[0] += en;
+            acc[1] += dx * gx + (dy * gy + dz * gz); // r.dot(f), :2241
+            acc[2] += dx * gx; acc[3] += dx * gy; acc[4] += dx * gz; // stress += r * f^T, :2274
+            acc[5] += dy * gx; acc[6] += dy * gy; acc[7] += dy * gz;
+            acc[8] += dz * gx; acc[9] += dz * gy; acc[10] += dz * gz;
+            acc[11] += (en != 0.0) ? 1.0 : 0.0; // contacts :2126-2137
+            acc[12] += (en > 0.0) ? 1.0 : 0.0;  // overlaps :2140-2151
+        }
+    }
+}
+
+// The 8 teams of a warp walk their rows in lock step, one pass of TEAM * V entries at a time, for as many passes as the
+// warp's LONGEST row has (a team that has run out of entries walks sentinel words: exact zeros). The trip count is
+// therefore warp-uniform, and so is the decision that ends the row: when the longest row has at most TEAM * m entries
+// left, all of them sit in the first m entries of every lane's vector (entry k of a pass belongs to lane k % TEAM,
+// position k / TEAM: tile.cu) and the pass runs m = 2, 4 or 6 pair evaluations per lane instead of 8: the rows of a
+// warp are padded to the next multiple of 8 entries of its longest row, not of 32.
+// The row words of pass k+1 (or, in the warp's last pass, of the first pass of the team's NEXT atom) and the next atom's
+// row length are requested before the arithmetic of pass k starts, so the DRAM latency of the streamed rows hides behind
+// ~160 fp64 instructions. my0 / q: length and first pass of the team's first atom, loaded by the caller before the tile
+// was staged. sentw: two sentinel entries (8 * ntile in both halves).
 template <int KIND, int MODE, int TEAM, int V, bool MI, int NT = TILE_NT>
 __device__ __forceinline__ void tile_rows(const TileForceArgs &A, uint32_t na, uint32_t s0, uint32_t own, const double2 *sxy,
-                                          const double *sz, double (&acc)[NPART], uint32_t my0, RowWords<V> q) {
+                                          const double *sz, double (&acc)[NPART], uint32_t my0, RowWords<V> q, uint32_t sentw) {
     constexpr bool want_obs = MODE != MODE_F;
     constexpr uint32_t NTEAM = NT / TEAM;
     const uint32_t tl = threadIdx.x % TEAM;
     const double c12 = 12.0 * A.P1.eps;
     const long long rc2_bits = __double_as_longlong(A.P1.rc2);
+    const uint32_t partial = A.half_ok ? 1u : 0u; // 0: every pass walks all V entries of the lane's vector
     uint32_t my = my0;
     for (uint32_t a = threadIdx.x / TEAM; a - threadIdx.x / TEAM < na; a += NTEAM) { // every lane of a warp runs the same trips (shuffles below)
         const bool valid = a < na;
@@ -104,55 +166,24 @@ __device__ __forceinline__ void tile_rows(const TileForceArgs &A, uint32_t na, u
         const uint16_t *row = A.rows16 + (size_t)s * A.kmax + tl * V;
         const uint16_t *rown = A.rows16 + (size_t)sn * A.kmax + tl * V;
         double fx = 0, fy = 0, fz = 0;
-        if (my == 0 && validn) q = load_row_words<V>(rown);
-        for (uint32_t k0 = 0; k0 < my; k0 += TEAM * V) {
-            RowWords<V> qn = q;
-            if (k0 + TEAM * V < my) qn = load_row_words<V>(row + k0 + TEAM * V);
-            else if (validn) qn = load_row_words<V>(rown); // rows are allocated to kmax: safe whatever the next length is
+        const uint32_t mymax = __reduce_max_sync(0xffffffffu, my);
+        if (my == 0) { // no row (or no atom) for this team: whatever was prefetched is not a row
 #pragma unroll
-            for (int e = 0; e < V; e++) {
-                // the entry is 8 * index: byte offset of z, half the byte offset of (x, y)
-                const uint32_t eo = (e & 1) ? (q.w[e >> 1] >> 16) : (q.w[e >> 1] & 0xffffu);
-                const double2 pxy = *reinterpret_cast<const double2 *>(reinterpret_cast<const char *>(sxy) + 2u * eo); // one LDS.128
-                double dx = xi - pxy.x, dy = yi - pxy.y, dz = zi - *reinterpret_cast<const double *>(reinterpret_cast<const char *>(sz) + eo);
-                if (MI) {
-                    dx = min_image_fast(dx, A.box.L[0], A.box.invL[0]);
-                    dy = min_image_fast(dy, A.box.L[1], A.box.invL[1]);
-                    dz = min_image_fast(dz, A.box.L[2], A.box.invL[2]);
-                }
-                const double dsq = dx * dx + (dy * dy + dz * dz);
-                if (!want_obs) {
-                    // forces only: 17 operations on the fp64 pipe per pair (it bounds this kernel). The factor 12 epsilon
-                    // is applied once per atom, the cut-off test is an integer comparison of the bit patterns (both
-                    // numbers are positive), ir6 (ir6 - 1) / dsq comes out of one fused multiply-add
-                    const double w = rcp_pos(dsq);
-                    const double s2 = A.P1.sig2 * w;
-                    const double ir6 = (s2 * s2) * s2;
-                    const double b = ir6 * w;
-                    const double t = fma(b, ir6, -b);
-                    // (select, then accumulate: predicated DFMAs -- C or PTX -- come out of ptxas as DFMA + 6 FSEL)
-                    const double scal = __double_as_longlong(dsq) <= rc2_bits ? t : 0.0; // sentinel pads: dsq ~ 1e200, beyond any cutoff
-                    fx = fma(dx, scal, fx);
-                    fy = fma(dy, scal, fy);
-                    fz = fma(dz, scal, fz);
-                    continue;
-                }
-                double scal, en;
-                lj_eval<KIND>(A.P1, c12, dsq, want_obs, scal, en); // sentinel pads: dsq ~ 1e200, beyond any cutoff
-                const double gx = dx * scal, gy = dy * scal, gz = dz * scal;
-                fx += gx;
-                fy += gy;
-                fz += gz;
-                if (want_obs) {
-                    acc[0] += en;
-                    acc[1] += dx * gx + (dy * gy + dz * gz); // r.dot(f), :2241
-                    acc[2] += dx * gx; acc[3] += dx * gy; acc[4] += dx * gz; // stress += r * f^T, :2274
-                    acc[5] += dy * gx; acc[6] += dy * gy; acc[7] += dy * gz;
-                    acc[8] += dz * gx; acc[9] += dz * gy; acc[10] += dz * gz;
-                    acc[11] += (en != 0.0) ? 1.0 : 0.0; // contacts :2126-2137
-                    acc[12] += (en > 0.0) ? 1.0 : 0.0;  // overlaps :2140-2151
-                }
-            }
+            for (int e = 0; e < V / 2; e++) q.w[e] = sentw;
+        }
+        if (mymax == 0 && validn) q = load_row_words<V>(rown);
+        for (uint32_t k0 = 0; k0 < mymax; k0 += TEAM * V) {
+            RowWords<V> qn;
+#pragma unroll
+            for (int e = 0; e < V / 2; e++) qn.w[e] = sentw;
+            if (k0 + TEAM * V < my) qn = load_row_words<V>(row + k0 + TEAM * V);
+            else if (k0 + TEAM * V >= mymax && validn) qn = load_row_words<V>(rown); // rows are allocated to kmax: safe whatever the next length is
+            // entries per lane this pass needs: the longest row's remainder dealt over the TEAM lanes, in steps of two
+            const uint32_t rem = mymax - k0;
+            if (V == 8 && rem <= 2 * TEAM * partial) tile_pairs<KIND, MODE, V, 2, MI>(A, q, sxy, sz, xi, yi, zi, c12, rc2_bits, fx, fy, fz, acc);
+            else if (rem <= V / 2 * TEAM * partial) tile_pairs<KIND, MODE, V, V / 2, MI>(A, q, sxy, sz, xi, yi, zi, c12, rc2_bits, fx, fy, fz, acc);
+            else if (V == 8 && rem <= 6 * TEAM * partial) tile_pairs<KIND, MODE, V, 6, MI>(A, q, sxy, sz, xi, yi, zi, c12, rc2_bits, fx, fy, fz, acc);
+            else tile_pairs<KIND, MODE, V, V, MI>(A, q, sxy, sz, xi, yi, zi, c12, rc2_bits, fx, fy, fz, acc);
             q = qn;
         }
         my = myn;
@@ -212,24 +243,35 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t
 // team layout). STAGE 1: the <= 18 runs of the tile arrive as <= 36 cp.async.bulk copies from prel (tile.cu) issued by
 // the lanes of warp 0 and counted by one mbarrier; no thread touches the positions, except in the chunks next to a
 // periodic face, whose wrapped runs get their image shift (TileChunk::sh) added once they have landed.
+// The time between a block's first instruction and the arrival of its tile is dead time for its 8 warps (ncu, round 2:
+// a third of the kernel's warp time), so the chain is kept short: the chunk descriptor is read ONCE, as 64 coalesced
+// words that go to shared memory -- run table, origin, flags and image shifts all come from there (the shifts used to
+// be read from global memory run by run, after the tile had landed) --, the read is issued before the abort word is
+// looked at, and every block pulls the descriptor of the chunk a wave of blocks later into L2.
+static_assert(sizeof(TileChunk) % 4 == 0 && sizeof(TileChunk) / 4 <= TILE_NT, "chunk descriptor is read as one word per thread");
 template <int KIND, int MODE, int TEAM, int V, int STAGE>
 __global__ void __launch_bounds__(TILE_NT) k_force_tile(const TileForceArgs A) {
-    if (A.abort_flag && *A.abort_flag) return; // speculatively enqueued step whose predecessor asked for a rebuild
+    constexpr uint32_t HW = sizeof(TileChunk) / 4;
     extern __shared__ __align__(16) double s_xyz[];
-    __shared__ uint32_t s_start[TILE_MAXSEG], s_off[TILE_MAXSEG + 1];
+    __shared__ __align__(16) uint32_t s_hdr[HW];
     __shared__ __align__(8) unsigned long long s_bar;
     const TileChunk *C = A.chunks + blockIdx.x;
-    if (threadIdx.x < TILE_MAXSEG) s_start[threadIdx.x] = C->seg_start[threadIdx.x];
-    if (threadIdx.x <= TILE_MAXSEG) s_off[threadIdx.x] = C->seg_off[threadIdx.x];
+    uint32_t hw = 0;
+    if (threadIdx.x < HW) hw = __ldg(reinterpret_cast<const uint32_t *>(C) + threadIdx.x);
+    const uint32_t s0 = __ldg(&C->s0), na = __ldg(&C->n), ntile = __ldg(&C->ntile); // (the same line: what the row prefetch below needs)
+    if (A.abort_flag && *A.abort_flag) return; // speculatively enqueued step whose predecessor asked for a rebuild
+    if (threadIdx.x < HW) s_hdr[threadIdx.x] = hw;
+    if (A.pf_dist && threadIdx.x < (sizeof(TileChunk) + 127) / 128 && blockIdx.x + A.pf_dist < gridDim.x)
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char *>(C + A.pf_dist) + 128 * threadIdx.x));
+    const TileChunk *H = reinterpret_cast<const TileChunk *>(s_hdr); // valid after the first block barrier
     double2 *sxy = reinterpret_cast<double2 *>(s_xyz); // (x, y) pairs, then the z array
     double *sz = s_xyz + 2 * (size_t)A.cap;
-    const uint32_t ntile = C->ntile, na = C->n, s0 = C->s0, cflags = C->flags;
-    const double ox = C->o[0], oy = C->o[1], oz = C->o[2];
     // first atom of this team: row length and first pass, in flight while the tile is staged
     uint32_t my0 = 0;
     RowWords<V> q0;
+    const uint32_t sentw = (ntile << TILE_IDX_SHIFT) | (ntile << (TILE_IDX_SHIFT + 16));
 #pragma unroll
-    for (int e = 0; e < V / 2; e++) q0.w[e] = 0;
+    for (int e = 0; e < V / 2; e++) q0.w[e] = sentw;
     {
         const uint32_t a = threadIdx.x / TEAM;
         if (a < na) {
@@ -245,15 +287,17 @@ __global__ void __launch_bounds__(TILE_NT) k_force_tile(const TileForceArgs A) {
         sxy[t] = make_double2(1e100, 1e100);
         sz[t] = 1e100;
     }
+    uint32_t cflags;
     if (STAGE == 1) {
         const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&s_bar);
         if (threadIdx.x == 0) mbar_init(bar, 1);
         __syncthreads();
+        cflags = H->flags;
         if (threadIdx.x < 32) {
             if (threadIdx.x == 0) mbar_arrive_expect_tx(bar, ntile * 24u);
             __syncwarp();
             if (threadIdx.x < TILE_MAXSEG) {
-                const uint32_t o0 = s_off[threadIdx.x], len = s_off[threadIdx.x + 1] - o0, j0 = s_start[threadIdx.x];
+                const uint32_t o0 = H->seg_off[threadIdx.x], len = H->seg_off[threadIdx.x + 1] - o0, j0 = H->seg_start[threadIdx.x];
                 if (len) { // even start, even length: both copies are 16-byte aligned at both ends
                     bulk_g2s((uint32_t)__cvta_generic_to_shared(sxy + o0), A.prel_xy + j0, len * 16u, bar);
                     bulk_g2s((uint32_t)__cvta_generic_to_shared(sz + o0), A.prel_z + j0, len * 8u, bar);
@@ -263,10 +307,10 @@ __global__ void __launch_bounds__(TILE_NT) k_force_tile(const TileForceArgs A) {
         mbar_wait(bar, 0);
         if (cflags & 2u) { // runs reached across a periodic face: add their image shift
             for (uint32_t seg = 0; seg < TILE_MAXSEG; seg++) {
-                const int sx = C->sh[seg][0], sy = C->sh[seg][1], szz = C->sh[seg][2];
+                const int sx = H->sh[seg][0], sy = H->sh[seg][1], szz = H->sh[seg][2];
                 if (!(sx | sy | szz)) continue;
                 const double ax = sx * A.box.L[0], ay = sy * A.box.L[1], az = szz * A.box.L[2];
-                for (uint32_t t = s_off[seg] + threadIdx.x; t < s_off[seg + 1]; t += TILE_NT) {
+                for (uint32_t t = H->seg_off[seg] + threadIdx.x; t < H->seg_off[seg + 1]; t += TILE_NT) {
                     double2 p = sxy[t];
                     p.x += ax;
                     p.y += ay;
@@ -278,6 +322,8 @@ __global__ void __launch_bounds__(TILE_NT) k_force_tile(const TileForceArgs A) {
         }
     } else {
         __syncthreads();
+        cflags = H->flags;
+        const double ox = H->o[0], oy = H->o[1], oz = H->o[2];
         // four positions per thread in flight: the loads of a group are issued before the first is reduced and stored
         // (a run-major variant -- thread t takes element t of every run, no table search -- was slower: 0.292 vs 0.278 ms)
         constexpr int SU = 4;
@@ -288,8 +334,8 @@ __global__ void __launch_bounds__(TILE_NT) k_force_tile(const TileForceArgs A) {
             for (int u = 0; u < SU; u++) {
                 const uint32_t t = t0 + u * TILE_NT;
                 if (t < ntile) {
-                    while (t >= s_off[seg + 1]) seg++;
-                    p[u] = A.pos[s_start[seg] + (t - s_off[seg])];
+                    while (t >= H->seg_off[seg + 1]) seg++;
+                    p[u] = A.pos[H->seg_start[seg] + (t - H->seg_off[seg])];
                 }
             }
 #pragma unroll
@@ -309,10 +355,10 @@ __global__ void __launch_bounds__(TILE_NT) k_force_tile(const TileForceArgs A) {
 #pragma unroll
         for (int q = 0; q < NPART; q++) acc[q] = 0.0;
     // the chunk's own atoms are consecutive entries of the centre column's run (piece 0 or 1 of stencil column 4)
-    const uint32_t d8 = s0 - s_start[8];
-    const uint32_t own = (s0 >= s_start[8] && d8 < s_off[9] - s_off[8]) ? s_off[8] + d8 : s_off[9] + (s0 - s_start[9]);
-    if (cflags & 1u) tile_rows<KIND, MODE, TEAM, V, true>(A, na, s0, own, sxy, sz, acc, my0, q0);
-    else tile_rows<KIND, MODE, TEAM, V, false>(A, na, s0, own, sxy, sz, acc, my0, q0);
+    const uint32_t st8 = H->seg_start[8], d8 = s0 - st8;
+    const uint32_t own = (s0 >= st8 && d8 < H->seg_off[9] - H->seg_off[8]) ? H->seg_off[8] + d8 : H->seg_off[9] + (s0 - H->seg_start[9]);
+    if (cflags & 1u) tile_rows<KIND, MODE, TEAM, V, true>(A, na, s0, own, sxy, sz, acc, my0, q0, sentw);
+    else tile_rows<KIND, MODE, TEAM, V, false>(A, na, s0, own, sxy, sz, acc, my0, q0, sentw);
     if (MODE != MODE_F) {
         __shared__ double red[NPART][TILE_NT / 32];
         const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;

@@ -75,6 +75,13 @@ struct ShardState {
     cudaEvent_t ev_k1, ev_comm;
     uint32_t *d_counts, *h_counts;    // small exchange buffers (device, pinned host)
     double *d_gather, *h_gather;      // drift top-2 of every rank
+    // one-sort rebuild (shard.cu: parm_shard_rebuild): the atoms that left the slab travel in fixed-capacity messages
+    int mig_fast;                     // PARM_B200_SHARD_FAST (default 1)
+    uint32_t mig_cap;                 // atoms per message (PARM_B200_SHARD_MIGCAP, default 4096); more leavers: two-sort path
+    uint32_t *mig_list;               // [2][mig_cap] slots of the atoms leaving downwards / upwards
+    uint32_t *mig_cnt;                // [4] leavers down, leavers up, overflow flag (max over ranks), spare
+    char *mig_send[2], *mig_recv[2];  // [to down, to up] / [from up, from down]
+    uint64_t fast_rebuilds, slow_rebuilds;
 };
 
 struct parm_ctx {
@@ -176,6 +183,7 @@ struct TileState {
     int ch, team, v;           // chunk size; lanes per atom and row entries per lane and pass of the pair kernel
     bool planned;              // chunk table matches the current cell structure
     bool valid;                // rows16 match the current rows
+    bool banked;               // rows16 were re-ordered by the experimental bank-aware pass (no half passes in the pair kernel)
     uint32_t nchunks, max_tile;
     uint32_t ncol;             // owned cell columns
     TileChunk *d_chunks;
@@ -399,6 +407,14 @@ bool parm_tile_chunk_range(const parm_nlist *nl, uint32_t first, uint32_t end, u
 
 // ---- device helpers ----
 #ifdef __CUDACC__
+// coordinate along the slab axis relative to the slab's lower face, continuous across both halos
+__device__ __forceinline__ double shard_rel(double x, const ShardDev &sd) {
+    double w = x - sd.L * floor(x / sd.L);
+    double rel = w - sd.lo;
+    if (rel < 0.0) rel += sd.L;
+    if (rel >= sd.Ls + 0.5 * (sd.L - sd.Ls)) rel -= sd.L;
+    return rel;
+}
 // IEEE remainder(dx, L) (box.hpp:69-72) without the libm loop: exact whenever rint picks
 // the nearest integer; the fix-up restores exactness when dx*invL was mis-rounded next to a
 // half-integer; exact ties follow remainder()'s round-half-even rule.

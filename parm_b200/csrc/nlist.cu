@@ -27,15 +27,6 @@ static inline unsigned grid_for(const parm_ctx *ctx, uint32_t n, unsigned block,
 
 // ---- K4a: cell index from the wrapped coordinate; also max |x| (bounds the wrap rounding) ----
 // (nearest reference analogue: Grid::get_loc, trackers.cpp:192-219)
-__device__ __forceinline__ double shard_rel(double x, const ShardDev &sd) {
-    // coordinate along the slab axis relative to the slab's lower face, continuous across both halos
-    double w = x - sd.L * floor(x / sd.L);
-    double rel = w - sd.lo;
-    if (rel < 0.0) rel += sd.L;
-    if (rel >= sd.Ls + 0.5 * (sd.L - sd.Ls)) rel -= sd.L;
-    return rel;
-}
-
 __global__ void k_cell_id(const double4 *__restrict__ pos, const uint32_t *__restrict__ src, uint32_t n, BoxDev box,
                           GridDev g, ShardDev sd, uint32_t *cell_id, uint32_t *iota, NlistFlags *flags,
                           uint32_t *cell_count) {

@@ -75,6 +75,27 @@ extern "C" int parm_nccl_unique_id(void *out128) {
     return 0;
 }
 
+// ---- migration messages of the one-sort rebuild --------------------------------------------------
+// [header 16 B: count, overflow, -, -][pos: cap double4][v: 3 x cap][a: 3 x cap][f: 3 x cap][id: cap u32]; always sent whole
+// (ncclSend / ncclRecv need the size on both sides before the counts are known anywhere but on the sender's device)
+static inline size_t mig_bytes(uint32_t cap) { return 16 + (size_t)cap * (32 + 9 * 8 + 4); }
+struct MigView {
+    uint32_t *hdr;
+    double4 *pos;
+    double *v, *a, *f; // [3][cap]
+    uint32_t *id;
+};
+static __host__ __device__ inline MigView mig_view(char *buf, uint32_t cap) {
+    MigView m;
+    m.hdr = reinterpret_cast<uint32_t *>(buf);
+    m.pos = reinterpret_cast<double4 *>(buf + 16);
+    m.v = reinterpret_cast<double *>(buf + 16 + (size_t)cap * 32);
+    m.a = m.v + 3 * (size_t)cap;
+    m.f = m.a + 3 * (size_t)cap;
+    m.id = reinterpret_cast<uint32_t *>(m.f + 3 * (size_t)cap);
+    return m;
+}
+
 extern "C" int parm_ctx_create_sharded(int ndim, uint32_t n_global, uint32_t cap_slots, int device, int rank, int nranks,
                                        const void *id128, parm_ctx **out) {
     if (nranks < 2 || rank < 0 || rank >= nranks || !id128) { parm_set_error("parm_ctx_create_sharded: bad rank/nranks/id"); return PARM_ERR_INVALID; }
@@ -101,6 +122,18 @@ extern "C" int parm_ctx_create_sharded(int ndim, uint32_t n_global, uint32_t cap
         int lo_prio = 0, hi_prio = 0;
         CK(cudaDeviceGetStreamPriorityRange(&lo_prio, &hi_prio));
         CK(cudaStreamCreateWithPriority(&sh.comm_stream, cudaStreamNonBlocking, hi_prio));
+    }
+    {
+        const char *e = getenv("PARM_B200_SHARD_FAST");
+        sh.mig_fast = e ? atoi(e) : 1;
+        e = getenv("PARM_B200_SHARD_MIGCAP");
+        sh.mig_cap = e ? (uint32_t)std::max(1, atoi(e)) : 4096u;
+        CK(cudaMalloc(&sh.mig_list, 2 * (size_t)sh.mig_cap * 4));
+        CK(cudaMalloc(&sh.mig_cnt, 4 * 4));
+        for (int d = 0; d < 2; d++) {
+            CK(cudaMalloc(&sh.mig_send[d], mig_bytes(sh.mig_cap)));
+            CK(cudaMalloc(&sh.mig_recv[d], mig_bytes(sh.mig_cap)));
+        }
     }
     CK(cudaEventCreateWithFlags(&sh.ev_k1, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&sh.ev_comm, cudaEventDisableTiming));
@@ -290,6 +323,13 @@ extern "C" int parm_shard_info(parm_ctx *c, uint32_t *out /*n_local, ghosts_down
     return 0;
 }
 
+extern "C" int parm_shard_rebuild_stats(parm_ctx *c, uint64_t *out2) {
+    if (!c || !c->sh.on || !out2) { parm_set_error("parm_shard_rebuild_stats: not a sharded context"); return PARM_ERR_INVALID; }
+    out2[0] = c->sh.fast_rebuilds;
+    out2[1] = c->sh.slow_rebuilds;
+    return 0;
+}
+
 int parm_shard_allreduce_sum(parm_ctx *c, double *d_buf, int count) {
     NcclApi *n = nccl_api();
     NCK(n->AllReduce(d_buf, d_buf, (size_t)count, ncclFloat64, ncclSum, (ncclComm_t)c->sh.comm, c->stream));
@@ -444,6 +484,161 @@ static int exchange_ranges(parm_ctx *c, bool full, uint32_t dn0, uint32_t ndn, u
     return 0;
 }
 
+// ---- one-sort rebuild -------------------------------------------------------------------------------
+// The two-sort path below sorts every owned atom to find the few hundred that left the slab, waits for their number,
+// tells the neighbours, waits again, and sorts the new owned set a second time. Here the leavers are FOUND without a
+// sort (the binning rule of k_cell_id on the slab axis, nothing else), packed in slot order -- which is what makes the
+// order of the arrivals, and with it every later summation order, reproducible -- into fixed-capacity messages whose
+// header carries the count, and exchanged before the host knows any number. One host round trip later (counts +
+// overflow flag, max over all ranks) the arrivals are appended behind the owned slots and ONE sort bins everything: the
+// leavers land in the halo layers behind the new owned set, exactly where the two-sort path left them, and are
+// overwritten by the ghosts. The resulting slot order is the two-sort path's (stable sorts, same source order).
+__global__ void k_find_leavers(const double4 *__restrict__ pos, uint32_t n, ShardDev sd, uint32_t cap, uint32_t *list, uint32_t *cnt) {
+    for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < n; s += gridDim.x * blockDim.x) {
+        const double rel = shard_rel(pos[s].x, sd);
+        const int dir = rel < 0.0 ? 0 : (rel >= sd.Ls ? 1 : -1); // k_cell_id: halo layer below / above / an interior layer
+        if (dir >= 0) {
+            const uint32_t k = atomicAdd(cnt + dir, 1u); // (claim order is arbitrary: k_pack_leavers sorts the slots)
+            if (k < cap) list[(size_t)dir * cap + k] = s;
+        }
+    }
+}
+
+// block 0: leavers downwards, block 1: upwards. Ranks every slot among the direction's leavers (a few hundred) and packs
+// the full state in ascending slot order.
+__global__ void __launch_bounds__(1024) k_pack_leavers(const uint32_t *__restrict__ list, uint32_t *cnt, uint32_t cap, uint32_t npad,
+                                                       const double4 *__restrict__ pos, const double *__restrict__ v,
+                                                       const double *__restrict__ a, const double *__restrict__ f,
+                                                       const uint32_t *__restrict__ order, char *buf_dn, char *buf_up) {
+    extern __shared__ uint32_t s_list[];
+    const int dir = blockIdx.x;
+    const uint32_t nraw = cnt[dir], n = min(nraw, cap);
+    const MigView m = mig_view(dir ? buf_up : buf_dn, cap);
+    for (uint32_t k = threadIdx.x; k < n; k += blockDim.x) s_list[k] = list[(size_t)dir * cap + k];
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        m.hdr[0] = nraw > cap ? 0u : n;
+        m.hdr[1] = nraw > cap ? 1u : 0u;
+        m.hdr[2] = m.hdr[3] = 0u;
+        if (nraw > cap) atomicMax(cnt + 2, 1u);
+    }
+    if (nraw > cap) return; // (uniform) every rank falls back to the two-sort path
+    for (uint32_t k = threadIdx.x; k < n; k += blockDim.x) {
+        const uint32_t s = s_list[k];
+        uint32_t rank = 0;
+        for (uint32_t j = 0; j < n; j++) rank += s_list[j] < s;
+        m.pos[rank] = pos[s];
+        for (int d = 0; d < 3; d++) {
+            m.v[(size_t)d * cap + rank] = v[(size_t)d * npad + s];
+            m.a[(size_t)d * cap + rank] = a[(size_t)d * npad + s];
+            m.f[(size_t)d * cap + rank] = f[(size_t)d * npad + s];
+        }
+        m.id[rank] = order[s];
+    }
+}
+
+// arrivals behind the owned slots: first what came from the upper neighbour, then from the lower one
+__global__ void k_unpack_arrivals(const char *from_up, const char *from_dn, uint32_t cap, uint32_t dst, uint32_t npad, double4 *pos,
+                                  double *v, double *a, double *f, uint32_t *order, uint8_t *ghost) {
+    const MigView mu = mig_view(const_cast<char *>(from_up), cap), md = mig_view(const_cast<char *>(from_dn), cap);
+    const uint32_t ru = mu.hdr[0], rd = md.hdr[0];
+    for (uint32_t q = blockIdx.x * blockDim.x + threadIdx.x; q < ru + rd; q += gridDim.x * blockDim.x) {
+        const MigView &m = q < ru ? mu : md;
+        const uint32_t k = q < ru ? q : q - ru, s = dst + q;
+        pos[s] = m.pos[k];
+        for (int d = 0; d < 3; d++) {
+            v[(size_t)d * npad + s] = m.v[(size_t)d * cap + k];
+            a[(size_t)d * npad + s] = m.a[(size_t)d * cap + k];
+            f[(size_t)d * npad + s] = m.f[(size_t)d * cap + k];
+        }
+        order[s] = m.id[k];
+        ghost[s] = 0;
+    }
+}
+
+// boundary-layer sizes of the freshly sorted owned set, straight from the cell table
+__global__ void k_ghost_counts(const uint32_t *__restrict__ cell_start, uint32_t plane, uint32_t nci, uint32_t n_local, uint32_t *out) {
+    if (threadIdx.x || blockIdx.x) return;
+    out[0] = cell_start[plane];                                 // lowest interior layer -> ghosts of the lower neighbour
+    out[1] = n_local - cell_start[(size_t)(nci - 1) * plane];   // highest interior layer -> ghosts of the upper neighbour
+    out[4] = cell_start[(size_t)nci * plane];                   // atoms binned into interior layers (must be n_local)
+}
+
+static int shard_rebuild_two_sorts(parm_nlist *nl);
+
+// 0: done; 1: more leavers than a message holds somewhere -- nothing was changed, take the two-sort path
+static int shard_rebuild_one_sort(parm_nlist *nl, bool *fallback) {
+    parm_ctx *c = nl->ctx;
+    ShardState &sh = c->sh;
+    NcclApi *n = nccl_api();
+    ncclComm_t comm = (ncclComm_t)sh.comm;
+    *fallback = false;
+    const uint32_t plane = (uint32_t)nl->g.nc[1] * (uint32_t)nl->g.nc[2];
+    const uint32_t nci = (uint32_t)nl->sd.nci;
+    const uint32_t cap = sh.mig_cap, n_old = sh.n_local;
+    auto grid = [&](uint32_t k) { return std::max(1u, std::min<unsigned>((k + 255) / 256, (unsigned)c->num_sms * 8)); };
+    CK(cudaMemsetAsync(sh.mig_cnt, 0, 16, c->stream));
+    if (n_old) {
+        k_find_leavers<<<grid(n_old), 256, 0, c->stream>>>(c->pos, n_old, nl->sd, cap, sh.mig_list, sh.mig_cnt);
+        CK_LAUNCH(c);
+    }
+    if ((size_t)cap * 4 > 48 * 1024) CK(cudaFuncSetAttribute(k_pack_leavers, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(cap * 4)));
+    k_pack_leavers<<<2, 1024, (size_t)cap * 4, c->stream>>>(sh.mig_list, sh.mig_cnt, cap, c->npad, c->pos, c->v, c->a, c->f, c->order,
+                                                            sh.mig_send[0], sh.mig_send[1]);
+    CK_LAUNCH(c);
+    const size_t mb = mig_bytes(cap);
+    NCK(n->GroupStart());
+    // sends: [to down, to up]; receives: [from up, from down] (same-peer ordering, see the halo exchange)
+    NCK(n->Send(sh.mig_send[0], mb, ncclUint8, sh.down, comm, c->stream));
+    NCK(n->Send(sh.mig_send[1], mb, ncclUint8, sh.up, comm, c->stream));
+    NCK(n->Recv(sh.mig_recv[0], mb, ncclUint8, sh.up, comm, c->stream));
+    NCK(n->Recv(sh.mig_recv[1], mb, ncclUint8, sh.down, comm, c->stream));
+    NCK(n->GroupEnd());
+    NCK(n->AllReduce(sh.mig_cnt + 2, sh.mig_cnt + 2, 1, ncclUint32, ncclMax, comm, c->stream)); // anyone over capacity?
+    CK(cudaMemcpyAsync(sh.h_counts, sh.mig_cnt, 12, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(sh.h_counts + 4, sh.mig_recv[0], 4, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(sh.h_counts + 5, sh.mig_recv[1], 4, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    if (sh.h_counts[2]) { *fallback = true; return 0; }
+    const uint32_t m_dn = sh.h_counts[0], m_up = sh.h_counts[1], r_up = sh.h_counts[4], r_dn = sh.h_counts[5];
+    if ((uint64_t)n_old + r_up + r_dn > c->npad) { parm_set_error("slab rank %d: slot capacity %u too small for migration", sh.rank, c->npad); return PARM_ERR_RUNTIME; }
+    if (r_up + r_dn) {
+        k_unpack_arrivals<<<grid(r_up + r_dn), 256, 0, c->stream>>>(sh.mig_recv[0], sh.mig_recv[1], cap, n_old, c->npad, c->pos, c->v, c->a,
+                                                                   c->f, c->order, c->ghost);
+        CK_LAUNCH(c);
+    }
+    // the one sort: stayers in their old slot order, then the arrivals; the leavers are binned into the halo layers
+    const uint32_t n_local = n_old - m_dn - m_up + r_up + r_dn;
+    PTRY(parm_nlist_sort_permute(nl, nullptr, n_old + r_up + r_dn));
+    k_ghost_counts<<<1, 32, 0, c->stream>>>(nl->cell_start, plane, nci, n_local, sh.d_counts);
+    CK_LAUNCH(c);
+    NCK(n->GroupStart());
+    NCK(n->Send(sh.d_counts + 0, 1, ncclUint32, sh.down, comm, c->stream));
+    NCK(n->Send(sh.d_counts + 1, 1, ncclUint32, sh.up, comm, c->stream));
+    NCK(n->Recv(sh.d_counts + 2, 1, ncclUint32, sh.up, comm, c->stream));
+    NCK(n->Recv(sh.d_counts + 3, 1, ncclUint32, sh.down, comm, c->stream));
+    NCK(n->GroupEnd());
+    CK(cudaMemcpyAsync(sh.h_counts + 8, sh.d_counts, 20, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    if (sh.h_counts[12] != n_local) {
+        parm_set_error("slab rank %d: %d atoms are more than one layer outside the slab after migration "
+                       "(atoms must start in, or next to, their slab)", sh.rank, (int)n_local - (int)sh.h_counts[12]);
+        return PARM_ERR_RUNTIME;
+    }
+    const uint32_t s_dn = sh.h_counts[8], s_up = sh.h_counts[9], g_up = sh.h_counts[10], g_dn = sh.h_counts[11];
+    if ((uint64_t)n_local + g_up + g_dn > c->npad) { parm_set_error("slab rank %d: slot capacity %u too small for %u ghosts", sh.rank, c->npad, g_up + g_dn); return PARM_ERR_RUNTIME; }
+    // ghosts land behind the owned atoms (over the leavers): first the upper neighbour's lowest layer, then the lower neighbour's highest
+    PTRY(exchange_ranges(c, false, 0, s_dn, n_local - s_up, s_up, n_local, g_up, g_dn));
+    PTRY(parm_nlist_append_ghosts(nl, n_local, g_up + g_dn));
+    sh.n_local = n_local;
+    sh.g_dn = g_dn;
+    sh.g_up = g_up;
+    sh.s_dn = s_dn;
+    sh.s_up = s_up;
+    sh.fast_rebuilds++;
+    return parm_nlist_build_rows(nl);
+}
+
 int parm_shard_rebuild(parm_nlist *nl) {
     parm_ctx *c = nl->ctx;
     ShardState &sh = c->sh;
@@ -452,6 +647,18 @@ int parm_shard_rebuild(parm_nlist *nl) {
     PTRY(parm_nlist_prepare_grid(nl));
     PTRY(parm_prof_begin(c, PARM_PROF_REBUILD));
     CK(cudaMemsetAsync(nl->d_flags, 0, sizeof(NlistFlags), c->stream));
+    if (sh.mig_fast) {
+        bool fallback = false;
+        PTRY(shard_rebuild_one_sort(nl, &fallback));
+        if (!fallback) return 0;
+    }
+    sh.slow_rebuilds++;
+    return shard_rebuild_two_sorts(nl);
+}
+
+static int shard_rebuild_two_sorts(parm_nlist *nl) {
+    parm_ctx *c = nl->ctx;
+    ShardState &sh = c->sh;
     const uint32_t plane = (uint32_t)nl->g.nc[1] * (uint32_t)nl->g.nc[2];
     const uint32_t nci = (uint32_t)nl->sd.nci; // layers 0..nci-1 interior, nci = halo above, nci+1 = halo below
     auto grid = [&](uint32_t n) { return std::max(1u, std::min<unsigned>((n + 255) / 256, (unsigned)c->num_sms * 8)); };
@@ -508,6 +715,12 @@ int parm_shard_destroy(parm_ctx *c) {
     NcclApi *n = nccl_api();
     if (n && c->sh.comm) n->CommDestroy((ncclComm_t)c->sh.comm);
     if (c->sh.comm_stream) { cudaStreamDestroy(c->sh.comm_stream); cudaEventDestroy(c->sh.ev_k1); cudaEventDestroy(c->sh.ev_comm); }
+    if (c->sh.mig_list) cudaFree(c->sh.mig_list);
+    if (c->sh.mig_cnt) cudaFree(c->sh.mig_cnt);
+    for (int d = 0; d < 2; d++) {
+        if (c->sh.mig_send[d]) cudaFree(c->sh.mig_send[d]);
+        if (c->sh.mig_recv[d]) cudaFree(c->sh.mig_recv[d]);
+    }
     if (c->sh.d_counts) cudaFree(c->sh.d_counts);
     if (c->sh.h_counts) cudaFreeHost(c->sh.h_counts);
     if (c->sh.d_gather) cudaFree(c->sh.d_gather);

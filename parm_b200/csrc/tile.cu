@@ -664,12 +664,14 @@ static int tile_bank_order(parm_nlist *nl) {
     TileState &t = nl->tile;
     const char *eb = getenv("PARM_B200_TILE_BANKS"); // read per rebuild: the sweeps toggle it inside one process
     const int banks = eb ? atoi(eb) : 0;
+    t.banked = false;
     if (!banks || t.team != 4 || t.v != 8) return 0;
     const size_t smem = 2 * (size_t)(TILE_NT / 4) * nl->kmax * sizeof(uint16_t);
     if (smem > 160 * 1024) return 0;
     if (smem > 32 * 1024) CK(cudaFuncSetAttribute(k_tile_bank_order, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k_tile_bank_order<<<t.nchunks, TILE_NT, smem, c->stream>>>(t.d_chunks, nl->cnt, nl->kmax, t.rows16);
     CK_LAUNCH(c);
+    t.banked = true;
     return 0;
 }
 

@@ -116,6 +116,11 @@ class ShardedAtomVec:
         call("parm_shard_info", self._h, out)
         return dict(zip(("n_local", "ghosts_down", "ghosts_up", "send_down", "send_up", "slots"), list(out)))
 
+    def rebuild_stats(self):
+        out = (C.c_uint64 * 2)()
+        call("parm_shard_rebuild_stats", self._h, out)
+        return {"one_sort": int(out[0]), "two_sorts": int(out[1])}
+
     def get_local(self):
         n = C.c_uint32(0)
         call("parm_shard_get_atoms", self._h, 0, C.byref(n), None, None, None, None, None, None)

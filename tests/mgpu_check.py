@@ -85,8 +85,8 @@ def check(name, w, steps, tol_traj=1e-9):
         assert rel_err(E1, c.energy()) < 1e-10
         ca, cb = c.pairs()
         assert np.array_equal(ga1, ca) and np.array_equal(gb1, cb), "%s: merged pair set after %d steps differs" % (name, steps)
-        print("mgpu ok: %s world=%d N=%d pairs=%d rebuilds=%d local %s -> %s, rank0 %s tile %s" %
-              (name, world, n, len(ca), which, counts, counts1, info, tile), flush=True)
+        print("mgpu ok: %s world=%d N=%d pairs=%d rebuilds=%d local %s -> %s, rank0 %s tile %s rebuild paths %s" %
+              (name, world, n, len(ca), which, counts, counts1, info, tile, atoms.rebuild_stats()), flush=True)
     dist.barrier()
     del collec, inter, nl
     atoms.close()
@@ -136,12 +136,54 @@ def parity_metrics(w, steps):
         out["pairs_equal_after_steps"] = bool(np.array_equal(ga1, ca) and np.array_equal(gb1, cb))
         out["migrated"] = bool(counts != counts1)
         out["tile_kernel"] = bool(tile[0])
+        out["rebuild_paths_rank0"] = atoms.rebuild_stats()
         out["ok"] = bool(out["pairs_equal"] and out["pairs_equal_after_steps"] and out["force_rel"] < 1e-10 and
                          out["energy_rel"] < 1e-10 and out["x_rel_after_steps"] < 1e-9 and out["rebuilds"] == out["rebuilds_oracle"])
     dist.barrier()
     del collec, inter, nl
     atoms.close()
     return out
+
+
+def migration_paths(w, steps):
+    """The sharded rebuild has two migration paths (csrc/shard.cu: one sort with fixed-capacity messages, two sorts with
+    exact counts) and falls from the first to the second when a message overflows. All three ways must leave every
+    atom in the same slot: the states after `steps` steps of a hot liquid (many atoms change slab) are compared
+    bit for bit, and the run with a one-atom message capacity must have used both paths."""
+    import hashlib
+    rank, world = dist.get_rank(), dist.get_world_size()
+    n = w["x"].shape[0]
+    digests, paths, moved = [], [], []
+    for env in ({}, {"PARM_B200_SHARD_MIGCAP": "1"}, {"PARM_B200_SHARD_FAST": "0"}):
+        for k in ("PARM_B200_SHARD_MIGCAP", "PARM_B200_SHARD_FAST"):
+            os.environ.pop(k, None)
+        os.environ.update(env)  # read when the context is created
+        gid, x, v, m = sharded.partition_workload(w, rank, world)
+        box, atoms, inter, nl, collec = sharded.build_system(
+            w["L"], n, gid, x, v, m, w["kind"], w["params"], w["types"], w["eps_table"], w["skin"], w["dt"])
+        collec.set_forces(True)
+        g0 = set(atoms.get_local()["gid"].tolist())
+        collec.timestep(steps)
+        st, counts = gather_state(atoms, n, w["ndim"])
+        g1 = set(atoms.get_local()["gid"].tolist())
+        h = hashlib.sha256()
+        for k in ("x", "v", "f"):
+            h.update(np.ascontiguousarray(st[k]).tobytes())
+        digests.append(h.hexdigest()[:16])
+        paths.append(atoms.rebuild_stats())
+        moved.append(len(g1 - g0))
+        dist.barrier()
+        del collec, inter, nl
+        atoms.close()
+    for k in ("PARM_B200_SHARD_MIGCAP", "PARM_B200_SHARD_FAST"):
+        os.environ.pop(k, None)
+    if rank == 0:
+        assert digests[0] == digests[1] == digests[2], "migration paths disagree: %s" % digests
+        assert paths[0]["two_sorts"] == 0 and paths[2]["one_sort"] == 0, paths
+        assert paths[1]["two_sorts"] > 0, "the overflow fall-back was not exercised: %s" % paths
+        assert moved[0] >= 8, "too few atoms changed slab for this check to mean anything (%d)" % moved[0]
+        print("mgpu ok: migration paths bit-identical after %d steps (N=%d, %d atoms arrived on rank 0), digest %s, paths %s"
+              % (steps, n, moved[0], digests[0], paths), flush=True)
 
 
 def main():
@@ -168,6 +210,8 @@ def main():
     # Sol with device RNG has no CPU twin; compare 1-step NVE of the same system instead, then run Sol for sanity
     w4v = dict(w4, integrator=W.VERLET)
     check("wca3d", w4v, steps=40)
+    # hot liquid, long enough that dozens of atoms change slab: one-sort, overflow fall-back and two-sort rebuilds
+    migration_paths(W.lj_lattice((12 * world, 12, 12), T=4.0, seed=23), steps=400)
     if rank == 0:
         print("MGPU_CHECK_PASSED world=%d" % world, flush=True)
     dist.destroy_process_group()
