@@ -385,8 +385,7 @@ __global__ void k_fold_decision(const double *__restrict__ gathered, int nvals, 
     }
     const int need = (__dadd_rn(b2, b1) >= skin) ? 1 : 0; // bigdist + biggestdist >= skin
     *d_slot = need;
-    *h_slot = need;
-    __threadfence_system();
+    *h_slot = need; // (read by the host behind an event: no system-scope fence needed, see drift.cuh)
 }
 
 static int drift_enqueue_on(parm_nlist *nl, int *d_slot, int *h_slot, cudaStream_t st) {
