@@ -103,8 +103,8 @@ static int launch_forces(parm_inter *it, int run, bool accumulate, double *d_out
     // row of ~100 entries in 13 dependent trips; 16 lanes per atom of the gather kernel spread the same rows over every
     // SM and finish in 4 trips.
     {
-        static int small_team = -1;
-        if (small_team < 0) { const char *e = getenv("PARM_B200_SMALL_TEAM"); small_team = e ? atoi(e) : 16; }
+        const char *est = getenv("PARM_B200_SMALL_TEAM"); // (read per launch: the tests of the tile kernel's small-box path turn it off)
+        const int small_team = est ? atoi(est) : 16;
         const bool one_species = !it->generic && it->nspecies == 1;
         const uint32_t nch = tl ? chunk1 - chunk0 : (nrange + 119u) / 120u;
         if (small_team == 16 && one_species && nch < (uint32_t)c->num_sms && nl->total_full >= 16ull * nrange) {

@@ -86,7 +86,7 @@ __device__ __forceinline__ RowWords<V> load_row_words(const uint16_t *p) {
 template <int KIND, int MODE, int V, int NV, bool MI>
 __device__ __forceinline__ void tile_pairs(const TileForceArgs &A, const RowWords<V> &q, const double2 *sxy, const double *sz, double xi,
                                            double yi, double zi, double c12, long long rc2_bits, double &fx, double &fy, double &fz,
-                                           double (&acc)[NPART]) {
+                                           double (&acc)[NPART], uint32_t sent_eo) {
     constexpr bool want_obs = MODE != MODE_F;
 #pragma unroll
     for (int e = 0; e < NV; e++) {
@@ -94,10 +94,15 @@ __device__ __forceinline__ void tile_pairs(const TileForceArgs &A, const RowWord
         const uint32_t eo = (e & 1) ? (q.w[e >> 1] >> 16) : (q.w[e >> 1] & 0xffffu);
         const double2 pxy = *reinterpret_cast<const double2 *>(reinterpret_cast<const char *>(sxy) + 2u * eo); // one LDS.128
         double dx = xi - pxy.x, dy = yi - pxy.y, dz = zi - *reinterpret_cast<const double *>(reinterpret_cast<const char *>(sz) + eo);
+        bool pad = false;
         if (MI) {
+            // the minimum image folds the far-away sentinel of the row pads back into the box (to distance ZERO when a box
+            // edge is a power of two: 1e100 / L is exact): pads are recognised by their index here, not by their distance
+            pad = eo >= sent_eo;
             dx = min_image_fast(dx, A.box.L[0], A.box.invL[0]);
             dy = min_image_fast(dy, A.box.L[1], A.box.invL[1]);
             dz = min_image_fast(dz, A.box.L[2], A.box.invL[2]);
+            if (pad) dx = dy = dz = 1e100;
         }
         const double dsq = dx * dx + (dy * dy + dz * dz);
         if (!want_obs) {
@@ -153,6 +158,7 @@ __device__ __forceinline__ void tile_rows(const TileForceArgs &A, uint32_t na, u
     const double c12 = 12.0 * A.P1.eps;
     const long long rc2_bits = __double_as_longlong(A.P1.rc2);
     const uint32_t partial = A.half_ok ? 1u : 0u; // 0: every pass walks all V entries of the lane's vector
+    const uint32_t sent_eo = sentw & 0xffffu;     // 8 * ntile: entries from here on are pads (also the class sentinels of bank-ordered rows)
     uint32_t my = my0;
     for (uint32_t a = threadIdx.x / TEAM; a - threadIdx.x / TEAM < na; a += NTEAM) { // every lane of a warp runs the same trips (shuffles below)
         const bool valid = a < na;
@@ -180,10 +186,10 @@ __device__ __forceinline__ void tile_rows(const TileForceArgs &A, uint32_t na, u
             else if (k0 + TEAM * V >= mymax && validn) qn = load_row_words<V>(rown); // rows are allocated to kmax: safe whatever the next length is
             // entries per lane this pass needs: the longest row's remainder dealt over the TEAM lanes, in steps of two
             const uint32_t rem = mymax - k0;
-            if (V == 8 && rem <= 2 * TEAM * partial) tile_pairs<KIND, MODE, V, 2, MI>(A, q, sxy, sz, xi, yi, zi, c12, rc2_bits, fx, fy, fz, acc);
-            else if (rem <= V / 2 * TEAM * partial) tile_pairs<KIND, MODE, V, V / 2, MI>(A, q, sxy, sz, xi, yi, zi, c12, rc2_bits, fx, fy, fz, acc);
-            else if (V == 8 && rem <= 6 * TEAM * partial) tile_pairs<KIND, MODE, V, 6, MI>(A, q, sxy, sz, xi, yi, zi, c12, rc2_bits, fx, fy, fz, acc);
-            else tile_pairs<KIND, MODE, V, V, MI>(A, q, sxy, sz, xi, yi, zi, c12, rc2_bits, fx, fy, fz, acc);
+            if (V == 8 && rem <= 2 * TEAM * partial) tile_pairs<KIND, MODE, V, 2, MI>(A, q, sxy, sz, xi, yi, zi, c12, rc2_bits, fx, fy, fz, acc, sent_eo);
+            else if (rem <= V / 2 * TEAM * partial) tile_pairs<KIND, MODE, V, V / 2, MI>(A, q, sxy, sz, xi, yi, zi, c12, rc2_bits, fx, fy, fz, acc, sent_eo);
+            else if (V == 8 && rem <= 6 * TEAM * partial) tile_pairs<KIND, MODE, V, 6, MI>(A, q, sxy, sz, xi, yi, zi, c12, rc2_bits, fx, fy, fz, acc, sent_eo);
+            else tile_pairs<KIND, MODE, V, V, MI>(A, q, sxy, sz, xi, yi, zi, c12, rc2_bits, fx, fy, fz, acc, sent_eo);
             q = qn;
         }
         my = myn;
@@ -557,6 +563,7 @@ __global__ void __launch_bounds__(TILE_PNT, 2) k_force_tile_pers(const TileForce
                     dx = min_image_fast(dx, A.box.L[0], A.box.invL[0]);
                     dy = min_image_fast(dy, A.box.L[1], A.box.invL[1]);
                     dz = min_image_fast(dz, A.box.L[2], A.box.invL[2]);
+                    if (eo >= (M.ntile << TILE_IDX_SHIFT)) dx = dy = dz = 1e100; // pads: see tile_pairs
                 }
                 const double dsq = dx * dx + (dy * dy + dz * dz);
                 const double w = rcp_pos(dsq);

@@ -367,6 +367,7 @@ extern "C" int parm_integ_destroy(parm_integ *g) {
     if (g->d_noise) cudaFree(g->d_noise);
     if (g->d_mobile_rank) cudaFree(g->d_mobile_rank);
     if (g->nlcg) parm_nlcg_free(g);
+    if (g->small) parm_small_free(g);
     if (g->d_gear) cudaFree(g->d_gear);
     if (g->d_scal) cudaFree(g->d_scal);
     if (g->d_xpart) cudaFree(g->d_xpart);
@@ -742,6 +743,11 @@ extern "C" int parm_integ_timestep(parm_integ *g, int nsteps) {
             }
             return 0;
         }
+    }
+    // small systems: the whole call as one persistent kernel (small.cu); what it leaves over takes the general path
+    if (nsteps >= 2) {
+        PTRY(parm_small_run(g, nl, &nsteps));
+        if (nsteps <= 0) return 0;
     }
     int cur = 0; // slot of step s
     PTRY(enqueue_step(g, g->steps, nullptr, cur, false, fuse && nsteps > 1));

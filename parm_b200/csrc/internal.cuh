@@ -325,6 +325,7 @@ struct parm_integ {
     struct IntegScalars *d_scal;
     double *d_xpart; // per-block partials of the thermostat reductions
     struct NlcgState *nlcg; // CollectionNLCG (nlcg.cu)
+    struct SmallState *small; // scratch of the persistent small-system kernel (small.cu)
     double dt, damping, force_mag, desT;
     double c0, c1, c2, sigmar, sigmav, corr, x11, x21, x22;
     uint64_t seed;
@@ -359,6 +360,9 @@ struct NlcgState {
     unsigned sec;
 };
 int parm_nlcg_timestep(parm_integ *g); // nlcg.cu
+// small.cu: whole timestep(n) calls of small CollectionVerlet systems as one persistent kernel; *nsteps = steps left over
+int parm_small_run(parm_integ *g, parm_nlist *nl, int *nsteps);
+void parm_small_free(parm_integ *g);
 void parm_nlcg_free(parm_integ *g);
 
 int parm_tracker_enqueue_update(parm_tracker *t, const int *abort_flag); // trackers.cu

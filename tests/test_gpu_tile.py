@@ -78,7 +78,22 @@ def test_tile_wide_chunks_small_box(oracle_built):
     keeps the per-pair minimum image on top of the staged one."""
     from parm_b200 import sim
     w = W.lj_lattice((15, 15, 15), seed=812)
-    _check_against_oracle(w, sim, steps=20, expect_wide=True)
+    # (systems this small run the 16-lane gather kernel / the persistent kernel by default: switch both off)
+    with _env(PARM_B200_SMALL_TEAM=0, PARM_B200_SMALL_PERSIST=0):
+        _check_against_oracle(w, sim, steps=20, expect_wide=True)
+
+
+@pytest.mark.parametrize("small_paths", [0, 1])
+def test_power_of_two_box_row_pads(oracle_built, small_paths):
+    """L = 16 exactly: 1e100 / L is exact, so the per-pair minimum image folds the far-away sentinel of the row pads to
+    distance ZERO -- pads must be recognised by their index (tile kernel with wide chunks, persistent small-system
+    kernel), not by their distance. small_paths = 1: the default kernels for a system of this size."""
+    from parm_b200 import sim
+    w = W.lj_lattice((16, 16, 16), rho=1.0, seed=816)
+    assert np.all(w["L"] == 16.0)
+    env = {} if small_paths else dict(PARM_B200_SMALL_TEAM=0, PARM_B200_SMALL_PERSIST=0)
+    with _env(**env):
+        nl = _check_against_oracle(w, sim, steps=20, expect_wide=True)
 
 
 def test_tile_unwrapped_coordinates(oracle_built):
