@@ -92,6 +92,13 @@ __global__ void __launch_bounds__(F_BLOCK) k_force(const ForceArgs A) {
         viy = A.vel[A.npad + sc];
         viz = A.vel[2 * (size_t)A.npad + sc];
     }
+    // The row words of a trip are requested one trip ahead -- those of the first trip together with the row length and
+    // the atom's own position, before either has arrived (rows are allocated to kmax, a multiple of 32 = of TEAM * U, so
+    // every word of a trip is readable; what lies beyond the row's length is discarded below). Short rows (contact
+    // potentials: one trip) thus cost two dependent memory round trips instead of three.
+    uint32_t ew[U];
+#pragma unroll
+    for (int u = 0; u < U; u++) ew[u] = __ldg(row + tl + u * TEAM);
     for (uint32_t k0 = tl; k0 < my; k0 += TEAM * U) {
         uint32_t j[U], sp[U];
         bool ok[U];
@@ -100,9 +107,13 @@ __global__ void __launch_bounds__(F_BLOCK) k_force(const ForceArgs A) {
         for (int u = 0; u < U; u++) {
             const uint32_t k = k0 + u * TEAM;
             ok[u] = k < my;
-            const uint32_t e = ok[u] ? __ldg(row + k) : sc;
+            const uint32_t e = ok[u] ? ew[u] : sc;
             j[u] = e & A.mask;
             sp[u] = e >> PARM_NBR_SLOT_BITS;
+        }
+        if (k0 + TEAM * U < my) {
+#pragma unroll
+            for (int u = 0; u < U; u++) ew[u] = __ldg(row + k0 + TEAM * U + u * TEAM);
         }
 #pragma unroll
         for (int u = 0; u < U; u++) pj[u] = ld_pos4(pos + j[u]);
