@@ -90,9 +90,7 @@ __device__ __forceinline__ void drift_finish(double b1, double b2, double skin, 
             // batched stepping (parm_integ_timestep): the first step of the batch that asks for a rebuild leaves its
             // number for the host (the steps behind it abort, so there is no second writer)
             if (need && step_no >= 0) hflags->trigger = (uint32_t)step_no;
-            // (no system-scope fence: the host reads these words only after an event recorded behind this kernel, and the
-            // next kernels read d_slot across a kernel boundary; the fence kept the kernel's last thread waiting for the
-            // PCIe round trip of the pinned-memory writes -- a third of k_verlet21's 7.7 us at N = 1000)
+            __threadfence_system();
         }
     }
 }

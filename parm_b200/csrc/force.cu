@@ -107,7 +107,8 @@ static int launch_forces(parm_inter *it, int run, bool accumulate, double *d_out
         const int small_team = est ? atoi(est) : 16;
         const bool one_species = !it->generic && it->nspecies == 1;
         const uint32_t nch = tl ? chunk1 - chunk0 : (nrange + 119u) / 120u;
-        if (small_team == 16 && one_species && nch < (uint32_t)c->num_sms && nl->total_full >= 16ull * nrange) {
+        // (single-GPU contexts only: the slot ranges of a slab-decomposed step keep the kernels they were validated with)
+        if (small_team == 16 && !c->sh.on && one_species && nch < (uint32_t)c->num_sms && nl->total_full >= 16ull * nrange) {
             team = 16;
             tl = nullptr;
             nblocks = (uint32_t)(((size_t)nrange * team + F_BLOCK - 1) / F_BLOCK);

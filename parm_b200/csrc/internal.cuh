@@ -73,6 +73,8 @@ struct ShardState {
     uint32_t s_dn, s_up;              // boundary-layer atoms sent to down / up every step
     cudaStream_t comm_stream;         // per-step exchanges run here, overlapped with the interior forces
     cudaEvent_t ev_k1, ev_comm;
+    cudaEvent_t ev_rows;              // behind an on-demand expansion of the 32-bit rows: both streams wait for it (nlist.cu)
+    cudaStream_t main_stream;         // the context's own stream (parm_ctx::stream is swapped for the boundary launches of a step)
     uint32_t *d_counts, *h_counts;    // small exchange buffers (device, pinned host)
     double *d_gather, *h_gather;      // drift top-2 of every rank
     // one-sort rebuild (shard.cu: parm_shard_rebuild): the atoms that left the slab travel in fixed-capacity messages

@@ -1211,6 +1211,14 @@ int parm_nlist_ensure_rows32(parm_nlist *nl) {
         k_expand_masks<<<(unsigned)(((size_t)n * 32 + 255) / 256), 256, 0, c->stream>>>(
             ms.out, nl->cell_id_sorted, (uint32_t)nl->g.nc[2], ms.gpc, (uint32_t)ms.zg, n, nl->kmax, nl->cnt, nl->nbr);
         CK_LAUNCH(c);
+        // Slab-decomposed contexts run the force launches of a step on two streams (interior: the context's own stream,
+        // boundary layers: the communication stream, integ.cu). Whichever of them asked for the rows first, BOTH wait for
+        // the expansion: the host-side flag below is all the second one would look at.
+        if (c->sh.on) {
+            CK(cudaEventRecord(c->sh.ev_rows, c->stream));
+            CK(cudaStreamWaitEvent(c->sh.main_stream, c->sh.ev_rows, 0));
+            CK(cudaStreamWaitEvent(c->sh.comm_stream, c->sh.ev_rows, 0));
+        }
     }
     ms.rows32_valid = true;
     return 0;

@@ -137,6 +137,8 @@ extern "C" int parm_ctx_create_sharded(int ndim, uint32_t n_global, uint32_t cap
     }
     CK(cudaEventCreateWithFlags(&sh.ev_k1, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&sh.ev_comm, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&sh.ev_rows, cudaEventDisableTiming));
+    sh.main_stream = c->stream;
     ncclUniqueId id;
     memcpy(&id, id128, 128);
     ncclComm_t comm;
@@ -385,7 +387,8 @@ __global__ void k_fold_decision(const double *__restrict__ gathered, int nvals, 
     }
     const int need = (__dadd_rn(b2, b1) >= skin) ? 1 : 0; // bigdist + biggestdist >= skin
     *d_slot = need;
-    *h_slot = need; // (read by the host behind an event: no system-scope fence needed, see drift.cuh)
+    *h_slot = need;
+    __threadfence_system();
 }
 
 static int drift_enqueue_on(parm_nlist *nl, int *d_slot, int *h_slot, cudaStream_t st) {
@@ -713,7 +716,7 @@ int parm_shard_destroy(parm_ctx *c) {
     if (!c->sh.on) return 0;
     NcclApi *n = nccl_api();
     if (n && c->sh.comm) n->CommDestroy((ncclComm_t)c->sh.comm);
-    if (c->sh.comm_stream) { cudaStreamDestroy(c->sh.comm_stream); cudaEventDestroy(c->sh.ev_k1); cudaEventDestroy(c->sh.ev_comm); }
+    if (c->sh.comm_stream) { cudaStreamDestroy(c->sh.comm_stream); cudaEventDestroy(c->sh.ev_k1); cudaEventDestroy(c->sh.ev_comm); cudaEventDestroy(c->sh.ev_rows); }
     if (c->sh.mig_list) cudaFree(c->sh.mig_list);
     if (c->sh.mig_cnt) cudaFree(c->sh.mig_cnt);
     for (int d = 0; d < 2; d++) {

@@ -55,6 +55,7 @@ struct SmallState { // hung off parm_integ
     unsigned int *bar;
     int *d_res, *h_res;
     uint32_t nS, grid_cap;
+    bool unavailable; // a cooperative launch failed once: this integrator stays on the general path
 };
 
 __device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int *p) {
@@ -282,7 +283,7 @@ static bool small_eligible(const parm_integ *g, const parm_nlist *nl) {
 // Runs as many of the `*nsteps` steps as stay eligible; *nsteps holds what is left for the general path (0: all done).
 int parm_small_run(parm_integ *g, parm_nlist *nl, int *nsteps) {
     parm_ctx *c = g->ctx;
-    while (*nsteps > 0 && small_eligible(g, nl)) {
+    while (*nsteps > 0 && small_eligible(g, nl) && !(g->small && g->small->unavailable)) {
         PTRY(parm_nlist_ensure_rows32(nl));
         const uint32_t n = c->n;
         const unsigned grid = (n + SM_APB - 1) / SM_APB;
@@ -325,7 +326,14 @@ int parm_small_run(parm_integ *g, parm_nlist *nl, int *nsteps) {
         CK(cudaMemsetAsync(S->bar, 0, 4, c->stream));
         const size_t smem = 3 * (size_t)nS * 8;
         bool fits = false;
-        CK(small_launch(grid, smem, c->stream, A, c->num_sms, &fits));
+        {
+            const cudaError_t e = small_launch(grid, smem, c->stream, A, c->num_sms, &fits);
+            if (e != cudaSuccess) { // no cooperative launch here (e.g. under a tool that does not support it): general path
+                cudaGetLastError();
+                S->unavailable = true;
+                return 0;
+            }
+        }
         if (!fits) return 0; // the grid would not be co-resident: general path
         parm_count_launch(c);
         CK(cudaStreamSynchronize(c->stream));
