@@ -218,4 +218,13 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    try:
+        main()
+    except BaseException:
+        # a failed comparison on rank 0 must not leave the other ranks waiting in a collective until NCCL's watchdog
+        # fires (10 minutes per GPU): leave at once, the launcher takes the remaining ranks down
+        import traceback
+        traceback.print_exc()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(1)
