@@ -138,7 +138,9 @@ __global__ void __launch_bounds__(SM_NT) k_small_steps(const SmallArgs A) {
                 }
             }
         }
-        // ---- grid barrier: every block's coordinates and top-2 slot are out
+        // ---- grid barrier: every block's coordinates and top-2 slot are out (the coordinates are read back through the
+        // async proxy -- bulk copies --, so the writers order their generic-proxy stores against it as well)
+        asm volatile("fence.proxy.async;" ::: "memory");
         __syncthreads();
         if (tid == 0) {
             __threadfence();
