@@ -333,6 +333,10 @@ def bench_main(args, rank, world, local, metric, unit, config, peak, hooks=None)
            "note": "per rank, pinned host arrays: full local state (x,v,a,f,m,id) device->host and x,v,a,f "
                    "host->device every step"}
     tile = nl.tile_stats()
+    try:  # reporting only: how this rank's list rebuilds migrated their atoms (csrc/shard.cu)
+        rebuild_paths = atoms.rebuild_stats()
+    except Exception as exc:  # never lose the bench line over it
+        rebuild_paths = {"error": str(exc)}
     del collec, inter, nl
     atoms.close()
 
@@ -376,7 +380,8 @@ def bench_main(args, rank, world, local, metric, unit, config, peak, hooks=None)
                          "step_share": {"integrate1_drift_ms": pms[0] / max(pcnt[0], 1), "force_ms": force_ms,
                                         "integrate2_ms": pms[2] / max(pcnt[2], 1),
                                         "rebuild_ms_each": pms[3] / max(pcnt[3], 1), "rebuilds": int(pcnt[3]), "steps": K},
-                         "rank0_slots": info, "halo_bytes_sent_per_step_rank0": int(halo_bytes)},
+                         "rank0_slots": info, "halo_bytes_sent_per_step_rank0": int(halo_bytes),
+                         "rank0_rebuild_paths": rebuild_paths},
             "steady_state": steady, "equilibration": equil, "parity_check": parity, "config5_16M": config5,
             "cpu_baseline": cpu,
         }
