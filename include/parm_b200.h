@@ -304,8 +304,12 @@ int parm_integ_initialize(parm_integ *integ);                  /* Collection::in
 int parm_integ_set_dt(parm_integ *integ, double dt);           /* set_dt; Sol recomputes constants :230-263 */
 int parm_integ_set_temperature(parm_integ *integ, double damping, double T); /* CollectionSol::change_temperature */
 int parm_integ_set_forces(parm_integ *integ, int constraints_and_a); /* Collection::set_forces :159-179 */
-/* nsteps x timestep() (collection.cpp:442-469 / 265-322). Asynchronous: returns when the
- * steps are enqueued and every rebuild decision has been taken; parm_sync / any download waits. */
+/* nsteps x timestep() (collection.cpp:442-469 / 265-322). Returns when every rebuild decision of the call has been
+ * taken: with a NeighborList that means the host has waited for the decision word of every step (an event wait per
+ * step, one step behind the enqueued work), so only the tail of the last step may still be running; without a tracker
+ * the steps are just enqueued. parm_sync / any download waits for the rest. Small CollectionVerlet systems (one
+ * one-species Lennard-Jones interaction, N <= 4096) run the whole call as one persistent kernel and return when it has
+ * finished (csrc/small.cu). */
 int parm_integ_timestep(parm_integ *integ, int nsteps);
 int parm_integ_update_trackers(parm_integ *integ);             /* collection.cpp:45-50 */
 int parm_integ_potential_energy(parm_integ *integ, double *E); /* collection.cpp:98-108 */
