@@ -255,12 +255,46 @@ def _timed_window(collec, atoms, stream, K):
     return float(ms.item()), capi.lib().parm_b200_launch_count() - l0, collec.stats()["rebuilds"] - r0
 
 
+def _parse_cpulist(text):
+    cpus = set()
+    for part in text.strip().split(","):
+        if not part:
+            continue
+        a, _, b = part.partition("-")
+        cpus.update(range(int(a), int(b or a) + 1))
+    return cpus
+
+
+def bind_to_gpu_numa_node(local, sysfs="/sys"):
+    """Keep this rank's host threads -- and with them the page-locked staging they first-touch -- on the NUMA node its
+    GPU hangs off (the e2e leg of an N > 1 bench line moves ~200 MB per rank and step through host memory). Best
+    effort: whatever goes wrong leaves the affinity as it was; returns what was done for the bench line."""
+    try:
+        import torch
+        p = torch.cuda.get_device_properties(local)
+        bdf = "%04x:%02x:%02x.0" % (p.pci_domain_id, p.pci_bus_id, p.pci_device_id)
+        with open(os.path.join(sysfs, "bus/pci/devices", bdf, "numa_node")) as fh:
+            node = int(fh.read())
+        if node < 0:
+            return {"gpu": bdf, "numa_node": node, "bound": False, "reason": "no NUMA information for the device"}
+        with open(os.path.join(sysfs, "devices/system/node/node%d/cpulist" % node)) as fh:
+            cpus = _parse_cpulist(fh.read())
+        use = cpus & os.sched_getaffinity(0)
+        if not use:
+            return {"gpu": bdf, "numa_node": node, "bound": False, "reason": "none of the node's cpus is in this process's cpu set"}
+        os.sched_setaffinity(0, use)
+        return {"gpu": bdf, "numa_node": node, "bound": True, "cpus": len(use)}
+    except Exception as exc:  # noqa: BLE001 -- reporting only
+        return {"bound": False, "reason": ("%s: %s" % (type(exc).__name__, exc))[:120]}
+
+
 def bench_main(args, rank, world, local, metric, unit, config, peak, hooks=None):
     """hooks (supplied by bench.py, which alone may drive the CPU oracle): "parity" -> dict printed as parity_check,
     "cpu_baseline" -> dict (rank 0 only), "equilibrate"(collec, steps) -> dict."""
     import torch
     import torch.distributed as dist
     torch.cuda.set_device(local)
+    host_binding = bind_to_gpu_numa_node(local) if os.environ.get("PARM_B200_BENCH_BIND", "1") != "0" else {"bound": False, "reason": "PARM_B200_BENCH_BIND=0"}
     init_distributed("nccl")
     from bench import ClockSampler
     hooks = hooks or {}
@@ -383,7 +417,7 @@ def bench_main(args, rank, world, local, metric, unit, config, peak, hooks=None)
                          "rank0_slots": info, "halo_bytes_sent_per_step_rank0": int(halo_bytes),
                          "rank0_rebuild_paths": rebuild_paths},
             "steady_state": steady, "equilibration": equil, "parity_check": parity, "config5_16M": config5,
-            "cpu_baseline": cpu,
+            "cpu_baseline": cpu, "rank0_host_binding": host_binding,
         }
         print(json.dumps(line))
     dist.barrier()

@@ -26,3 +26,15 @@ def test_two_gpu_parity_vs_oracle(oracle_built):
         pytest.skip("needs 2 GPUs (run with gpurun --gpus 2)")
     r = _torchrun("mgpu_check.py", 2, 29542, 600)
     assert r.returncode == 0 and "MGPU_CHECK_PASSED" in r.stdout, r.stdout[-2000:] + r.stderr[-3000:]
+
+
+def test_numa_binding_is_best_effort():
+    """bench.py's N > 1 runs bind every rank to the NUMA node of its GPU (parm_b200/sharded.py): the cpulist parser,
+    and that without a GPU (or without sysfs entries) the call reports why and leaves the affinity alone."""
+    from parm_b200 import sharded
+    assert sharded._parse_cpulist("0-3,8,10-11\n") == {0, 1, 2, 3, 8, 10, 11}
+    assert sharded._parse_cpulist("\n") == set()
+    before = os.sched_getaffinity(0)
+    out = sharded.bind_to_gpu_numa_node(0, sysfs="/nonexistent")
+    assert out["bound"] is False and "reason" in out
+    assert os.sched_getaffinity(0) == before
