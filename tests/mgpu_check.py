@@ -74,14 +74,22 @@ def check(name, w, steps, tol_traj=1e-9):
         assert np.array_equal(ga, ca) and np.array_equal(gb, cb), "%s: merged pair set differs" % name
         c.set_forces(True)
         cx, cv, cacc, cf = c.get_atoms()
-        assert rel_err_vec(st0["f"], cf) < 1e-10, "%s: forces" % name
+        ef = rel_err_vec(st0["f"], cf)
+        assert ef < 1e-10, "%s: forces differ from the oracle by %.3g (relative to the largest force)" % (name, ef)
         assert rel_err(E0, c.energy()) < 1e-10 and rel_err(K0, c.kinetic_energy()) < 1e-10
         assert rel_err(P0, c.pressure()) < 1e-10 and rel_err(T0, c.temp()) < 1e-10
         c.timestep(steps)
         cx, cv, cacc, cf = c.get_atoms()
         assert which == c.which(), "%s: rebuild count %d vs %d" % (name, which, c.which())
-        assert rel_err_vec(st1["x"] - w["x"], cx - w["x"]) < tol_traj, "%s: positions" % name
-        assert rel_err_vec(st1["v"], cv) < tol_traj, "%s: velocities" % name
+        ex, ev = rel_err_vec(st1["x"] - w["x"], cx - w["x"]), rel_err_vec(st1["v"], cv)
+        if not ex < tol_traj:  # which atoms, owned by whom: the first thing to look at when a slab-specific path is wrong
+            dxa = np.abs((st1["x"] - w["x"]) - (cx - w["x"])).max(1)
+            worst = np.argsort(dxa)[-5:][::-1]
+            print("%s: worst atoms %s, |dx| %s, wrapped x / slab width %s" % (
+                name, worst.tolist(), dxa[worst].tolist(), (np.mod(cx[worst, 0], w["L"][0]) / (w["L"][0] / world)).tolist()), flush=True)
+        assert ex < tol_traj, "%s: positions after %d steps differ from the oracle by %.3g (rebuild paths %s)" % (
+            name, steps, ex, atoms.rebuild_stats())
+        assert ev < tol_traj, "%s: velocities after %d steps differ from the oracle by %.3g" % (name, steps, ev)
         assert rel_err(E1, c.energy()) < 1e-10
         ca, cb = c.pairs()
         assert np.array_equal(ga1, ca) and np.array_equal(gb1, cb), "%s: merged pair set after %d steps differs" % (name, steps)
