@@ -70,6 +70,15 @@ def main():
     def walked(gran):
         return ((-(-longest // gran)) * gran * 8).sum() / n  # entries per atom the warps execute (idle teams included)
     same_chunk = chunk_of[pairs[:, 0]] == chunk_of[pairs[:, 1]]
+    # lead: deal the atoms of a chunk to the teams in order of row length (a per-chunk permutation table), so that the 8
+    # rows a warp walks in lock step are as equal as they can be
+    srt = np.lexsort((-cnt, chunk_of))                 # by chunk, longest rows first
+    rank_s = np.empty(n, np.int64)
+    rank_s[srt] = np.arange(n) - np.searchsorted(chunk_of[srt], chunk_of[srt])
+    _, inv_s = np.unique(chunk_of * 1000 + rank_s // 8, return_inverse=True)
+    longest_s = np.zeros(inv_s.max() + 1, np.int64)
+    np.maximum.at(longest_s, inv_s, cnt)
+    walked_sorted8 = ((-(-longest_s // 8)) * 8 * 8).sum() / n
     out = {
         "atoms": int(n), "cells": nc.tolist(), "chunks": int(nchunks), "atoms_per_chunk": n / nchunks,
         "state": "positions from " + a.positions if a.positions else "jittered lattice (t = 0)",
@@ -78,6 +87,7 @@ def main():
         "entries_walked_per_atom_pad32": walked(32), "entries_walked_per_atom_pad8": walked(8),
         "passes_per_warp_and_atom_pad32": float((-(-longest // 32)).mean()),
         "pad8_over_pad32": walked(8) / walked(32),
+        "entries_walked_per_atom_pad8_rows_sorted_by_length_inside_the_chunk": walked_sorted8,
         "partial_warps_share": float((lanes < 8).mean()),
         "listed_pairs_beyond_cutoff": float((r > rc).mean()),
         "listed_pairs_inside_one_chunk": float(same_chunk.mean()),
