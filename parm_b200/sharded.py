@@ -280,8 +280,9 @@ def bind_to_gpu_numa_node(local, sysfs="/sys"):
         with open(os.path.join(sysfs, "devices/system/node/node%d/cpulist" % node)) as fh:
             cpus = _parse_cpulist(fh.read())
         use = cpus & os.sched_getaffinity(0)
-        if not use:
-            return {"gpu": bdf, "numa_node": node, "bound": False, "reason": "none of the node's cpus is in this process's cpu set"}
+        if len(use) < 16:  # (too few to share between the ranks of the node and their NCCL proxy threads: stay unbound)
+            return {"gpu": bdf, "numa_node": node, "bound": False,
+                    "reason": "only %d of the node's cpus are in this process's cpu set" % len(use)}
         os.sched_setaffinity(0, use)
         return {"gpu": bdf, "numa_node": node, "bound": True, "cpus": len(use)}
     except Exception as exc:  # noqa: BLE001 -- reporting only
