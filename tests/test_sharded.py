@@ -19,6 +19,12 @@ def test_slab_host_logic_gloo_world2(oracle_built):
     assert r.returncode == 0 and "GLOO_WORKER_PASSED" in r.stdout, r.stdout[-2000:] + r.stderr[-3000:]
 
 
+def test_slab_host_logic_gloo_world4(oracle_built):
+    """four ranks: every rank has two DIFFERENT neighbours (with two, the upper and the lower neighbour are one rank)"""
+    r = _torchrun("_gloo_worker.py", 4, 29543, 300)
+    assert r.returncode == 0 and "GLOO_WORKER_PASSED" in r.stdout, r.stdout[-2000:] + r.stderr[-3000:]
+
+
 @pytest.mark.gpu
 def test_two_gpu_parity_vs_oracle(oracle_built):
     import torch
